@@ -1,0 +1,119 @@
+"""CPU: the oracle against the golden vectors produced by the reference's own code
+(tests/golden/make_golden.py).  This is the pin of the checker, not a product test."""
+import numpy as np
+import pytest
+
+from oracle import bpr, evaluator, sampler
+from helpers import csr, golden, rel_err, tiny_dataset
+
+
+def test_sampler_reference_stream_matches_reference():
+    g = golden("sampler_ref.npz")
+    U, I, tr, _, _, _ = tiny_dataset()
+    u, p, n = sampler.reference_stream_triples(tr, I, int(g["batch_size"]), int(g["epochs"]), seed=0)
+    assert len(u) == len(g["users"]) == (sum(map(len, tr)) // 16) * 16 * 3
+    assert (u == g["users"]).all() and (p == g["pos"]).all() and (n == g["neg"]).all()
+
+
+def test_evaluator_metrics_match_reference():
+    g = golden("evaluator_ref.npz")
+    U, I, tr, va, te, _ = tiny_dataset()
+    res = evaluator.evaluate(g["scores"], I, tr, va, te, int(g["k"]))
+    for key, want in zip(g["results_keys"].tolist(), g["results"].tolist()):
+        assert res[key] == pytest.approx(want, rel=1e-12, abs=1e-15), key
+
+
+def test_evaluator_topk_matches_reference_tsv():
+    g = golden("evaluator_ref.npz")
+    U, I, tr, _, _, _ = tiny_dataset()
+    k = int(g["k"])
+    ids, val = evaluator.masked_topk(g["scores"], tr, k)
+    rows = [l.split("\t") for l in str(g["recs_tsv"]).strip().split("\n")]
+    assert len(rows) == U * k
+    ref_ids = np.array([int(r[1]) for r in rows]).reshape(U, k)
+    ref_val = np.array([float(r[2]) for r in rows]).reshape(U, k)
+    for u in range(U):
+        ok, msg = evaluator.topk_matches(ids[u], val[u], ref_ids[u], ref_val[u])
+        assert ok, (u, msg)
+        assert not set(ids[u].tolist()) & set(tr[u])
+
+
+@pytest.mark.parametrize("name,vis", [("bprmf_ref.npz", False), ("vbpr_ref.npz", True)])
+def test_train_steps_match_reference_model_code(name, vis):
+    g = golden(name)
+    names = ["Bi", "Gu", "Gi"] + (["Tu", "E", "Bp"] if vis else [])
+    P = {k: g["init_" + k].astype(np.float32).copy() for k in names}
+    F = g["init_F"].astype(np.float32) if vis else None
+    if vis:   # the reference normalises by the global max-abs (visual_loader_mixin.py:30)
+        raw = tiny_dataset()[5]
+        assert np.array_equal(bpr.normalise_features(raw), F)
+    S = bpr.init_adam(P)
+    lr, reg = float(g["hyper"][0]), float(g["hyper"][1])
+    steps = len(g["losses"])
+    for s in range(steps):
+        loss = bpr.train_step(P, S, (g["users"][s], g["pos"][s], g["neg"][s]), reg, lr, F)
+        assert loss == pytest.approx(float(g["losses"][s]), rel=2e-5), s
+        if s + 1 in (1, 5):
+            for k in names:
+                assert rel_err(P[k], g["step%d_%s" % (s + 1, k)]) < 2e-5, (s, k)
+    for k in names:
+        assert rel_err(P[k], g["final_" + k]) < 1e-4, k
+    assert rel_err(bpr.predict_all(P, F), g["predict_all_final"]) < 1e-4
+
+
+@pytest.mark.parametrize("name,vis", [("bprmf_ref.npz", False), ("vbpr_ref.npz", True)])
+def test_golden_batches_are_the_reference_sampler_stream(name, vis):
+    g, s = golden(name), golden("sampler_ref.npz")
+    assert (g["users"].reshape(-1) == s["users"]).all()
+    assert (g["neg"].reshape(-1) == s["neg"]).all()
+
+
+def test_closed_form_gradients_against_autograd():
+    torch = pytest.importorskip("torch")
+    rng = np.random.default_rng(0)
+    U, I, K, d, D, B = 9, 13, 5, 3, 7, 32
+    P = bpr.init_params(U, I, K, d, D, seed=1, dtype=np.float64)
+    P["Bi"] = rng.standard_normal(I)
+    F = np.abs(rng.standard_normal((I, D)))
+    batch = (rng.integers(0, U, B), rng.integers(0, I, B), rng.integers(0, I, B))
+    reg = 0.01
+    loss, G, _ = bpr.loss_and_grads(P, batch, reg, F)
+    T = {k: torch.tensor(v, requires_grad=True) for k, v in P.items()}
+    Ft = torch.tensor(F)
+    u, i, j = (torch.tensor(b) for b in batch)
+
+    def s(it):
+        return (T["Bi"][it] + (T["Gu"][u] * T["Gi"][it]).sum(1)
+                + (T["Tu"][u] * (Ft[it] @ T["E"])).sum(1) + (Ft[it] @ T["Bp"])[:, 0])
+    x = torch.clamp(s(i) - s(j), -80.0, 1e8)
+    L = torch.nn.functional.softplus(-x).sum()
+    L = L + reg * ((T["Gu"][u] ** 2).sum() + (T["Gi"][i] ** 2).sum() + (T["Gi"][j] ** 2).sum()
+                   + (T["Tu"][u] ** 2).sum()) + reg * (T["Bi"][i] ** 2).sum() \
+        + reg * (T["Bi"][j] ** 2).sum() / 10 + reg * ((T["E"] ** 2).sum() + (T["Bp"] ** 2).sum())
+    L.backward()
+    assert float(L.detach()) == pytest.approx(float(loss), rel=1e-12)
+    for k in P:
+        assert np.max(np.abs(T[k].grad.numpy() - G[k])) < 1e-12, k
+
+
+def test_philox_known_answer():
+    # Random123 known-answer vectors for philox4x32-10
+    out = sampler.philox4x32([0], [0], [0], [0], 0, 0)
+    assert [int(o[0]) for o in out] == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    out = sampler.philox4x32([0xFFFFFFFF], [0xFFFFFFFF], [0xFFFFFFFF], [0xFFFFFFFF], 0xFFFFFFFF, 0xFFFFFFFF)
+    assert [int(o[0]) for o in out] == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+    out = sampler.philox4x32([0x243F6A88], [0x85A308D3], [0x13198A2E], [0x03707344], 0xA4093822, 0x299F31D0)
+    assert [int(o[0]) for o in out] == [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]
+
+
+def test_philox_negatives_never_in_train_and_deterministic():
+    U, I, tr, _, _, _ = tiny_dataset()
+    row_ptr, col_file, col_sorted = csr(tr)
+    perm, _ = sampler.philox_user_permutation(U, seed=5, epoch=0)
+    assert sorted(perm.tolist()) == list(range(U))
+    users, pos = sampler.enumerate_epoch(row_ptr, col_file, perm)
+    neg = sampler.philox_negatives(row_ptr, col_sorted, users, I, seed=5, offset=100)
+    assert all(int(j) not in tr[int(u)] for u, j in zip(users, neg))
+    assert (0 <= neg).all() and (neg < I).all()
+    again = sampler.philox_negatives(row_ptr, col_sorted, users[7:], I, seed=5, offset=107)
+    assert (again == neg[7:]).all()
