@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""Benchmark of the BPR train step (+ full-catalog top-100 evaluation) on B200.
+
+    python bench.py --gpus 1 --steps 50 --warmup 5            # this repo's CUDA path
+    python bench.py --impl reference --steps 5 --warmup 1      # the reference's CPU path (oracle port)
+
+Prints ONE JSON line (contract in the task statement / DESIGN.md "Measurement").
+Workload at N=1: BASELINE.json configs[1] - VBPR K=64, d=20, 2048-d features,
+40k users x 100k items, synthetic Amazon-fashion-shaped data, random-init weights.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+METRIC = "BPR triples/s (train)"
+UNIT = "triples/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="fvx", choices=["fvx", "reference"])
+    ap.add_argument("--users", type=int, default=40000)
+    ap.add_argument("--items", type=int, default=100000)
+    ap.add_argument("--embed_k", type=int, default=64)
+    ap.add_argument("--embed_d", type=int, default=20)
+    ap.add_argument("--feat_dim", type=int, default=2048)
+    ap.add_argument("--batch", type=int, default=16384)
+    ap.add_argument("--top_k", type=int, default=100)
+    ap.add_argument("--adam_mode", default="deferred", choices=["deferred", "dense", "lazy"])
+    ap.add_argument("--tensor_cores", type=int, default=0)
+    ap.add_argument("--no_eval", action="store_true")
+    ap.add_argument("--no_cpu_baseline", action="store_true")
+    ap.add_argument("--cpu_seconds", type=float, default=12.0)
+    return ap.parse_args()
+
+
+def bytes_per_triple(K, d, D, B):
+    """algorithmic HBM bytes of one triple of one train step."""
+    if D == 0:
+        return 24 * (3 * K + 2) + 12
+    return 24 * (3 * K + d + 2) + 8 * D + 12 + 24.0 * (D * d + D) / B
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), float(p["bf16_tflops"]), float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), "measured"
+    except Exception:
+        return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_problem(args, device=None):
+    """Synthetic interactions (host) + normalised features (device tensor or numpy)."""
+    from fvx import synth
+    inter = synth.make_interactions(args.users, args.items, seed=1234)
+    return inter
+
+
+def make_features_device(I, D, device, seed=4321):
+    import torch
+    g = torch.Generator(device=device).manual_seed(seed)
+    F = torch.empty(I, D, dtype=torch.float32, device=device)
+    chunk = 65536
+    for s in range(0, I, chunk):
+        e = min(I, s + chunk)
+        n = torch.randn(e - s, D, generator=g, device=device).clamp_(min=0)
+        x = torch.empty(e - s, D, device=device).exponential_(1.0, generator=g)
+        F[s:e] = n * x
+    F /= F.abs().max()                       # visual_loader_mixin.py:30
+    return F
+
+
+# ------------------------------------------------------------------------------------------
+def cpu_oracle_rate(args, inter, F_host, seconds, B):
+    """triples/s of the CPU oracle (NumPy restatement of the reference step, dense Keras-Adam)."""
+    from oracle import bpr
+    rng = np.random.default_rng(0)
+    P = bpr.init_params(args.users, args.items, args.embed_k, args.embed_d, args.feat_dim, seed=0)
+    S = bpr.init_adam(P)
+    owner = np.repeat(np.arange(args.users), np.diff(inter.row_ptr))
+    N = len(owner)
+
+    def batch(i):
+        s = (i * B) % max(N - B, 1)
+        return owner[s:s + B], inter.col_file[s:s + B].astype(np.int64), rng.integers(0, args.items, B)
+
+    bpr.train_step(P, S, batch(0), 1e-5, 1e-3, F_host)          # warm-up
+    t0 = time.perf_counter()
+    n = 0
+    while True:
+        bpr.train_step(P, S, batch(n + 1), 1e-5, 1e-3, F_host)
+        n += 1
+        el = time.perf_counter() - t0
+        if el >= seconds or n >= 200:
+            break
+    return n * B / el, n, el
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path.  TensorFlow 2.3.1 is
+    not installable here, so this times the oracle port (NumPy, all host cores through BLAS)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from fvx import synth
+    from oracle import bpr
+    B = args.batch
+    inter = make_problem(args)
+    F = None
+    if args.feat_dim:
+        F = bpr.normalise_features(synth.make_features(args.items, args.feat_dim))
+    rng = np.random.default_rng(0)
+    P = bpr.init_params(args.users, args.items, args.embed_k, args.embed_d, args.feat_dim, seed=0)
+    S = bpr.init_adam(P)
+    owner = np.repeat(np.arange(args.users), np.diff(inter.row_ptr))
+    N = len(owner)
+
+    def batch(i):
+        s = (i * B) % max(N - B, 1)
+        return owner[s:s + B], inter.col_file[s:s + B].astype(np.int64), rng.integers(0, args.items, B)
+
+    for i in range(args.warmup):
+        bpr.train_step(P, S, batch(i), 1e-5, 1e-3, F)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        bpr.train_step(P, S, batch(args.warmup + i), 1e-5, 1e-3, F)
+    el = time.perf_counter() - t0
+    v = args.steps * B / el
+    cores = len(os.sched_getaffinity(0))
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, 1),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": "%d full steps of B=%d on the full tables (NumPy oracle, dense Keras-Adam "
+                                       "sweep like TF 2.3; TensorFlow itself not installable)" % (args.steps, B)},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_config(args, n):
+    return {"workload": "VBPR train step, K=%d d=%d D=%d, %d users x %d items (BASELINE configs[1]), "
+                        "B=%d triples/step, on-device Philox sampler, %s Adam"
+                        % (args.embed_k, args.embed_d, args.feat_dim, args.users, args.items, args.batch,
+                           args.adam_mode),
+            "users": args.users, "items": args.items, "K": args.embed_k, "d": args.embed_d, "D": args.feat_dim,
+            "batch": args.batch, "adam_mode": args.adam_mode, "tensor_cores": bool(args.tensor_cores),
+            "parallelism": "1 GPU" if n == 1 else "%d independent replicas" % n,
+            "l2": "F (%.2f GB) and the tables exceed the 126 MB L2; rows are gathered at random, no flush needed"
+                  % (args.items * args.feat_dim * 4 / 1e9)}
+
+
+def run_fvx(args):
+    import torch
+    import torch.distributed as dist
+    from fvx.build import build
+    from fvx.dataset.dataset import DataLoader
+    from fvx.engine import Engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if rank == 0:
+        build()
+    if world > 1:
+        dist.barrier()
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    B, K, d, D = args.batch, args.embed_k, args.embed_d, args.feat_dim
+
+    inter = make_problem(args)
+    p = argparse.Namespace(dataset="synthetic", batch_size=B, epochs=10 ** 6, sampler="device", seed=rank)
+    data = DataLoader(p, interactions=inter)
+    e = Engine(args.users, args.items, K, d=d, D=D, lr=1e-3, reg=1e-5, adam_mode=args.adam_mode,
+               max_batch=B, device=str(dev), seed=0, use_tensor_cores=bool(args.tensor_cores))
+    if D:
+        e.set_features(make_features_device(args.items, D, dev))
+    batches = data.next_triple_batch(str(dev))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        e.step(*next(batches))
+    launches_per_step = 10 if D else 7
+    if args.adam_mode != "deferred":
+        launches_per_step -= 2
+    clocks = ClockSampler(local)
+    barrier()
+    clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ep0 = data_epochs = 0
+    ev0.record()
+    for _ in range(args.steps):
+        e.step(*next(batches))
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clk = clocks.stop()
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * args.steps * B / ms * 1e3
+    epochs_in_region = (args.steps * B) / max(data.num_train, 1)
+    gpu_launches = args.steps * launches_per_step + int(np.ceil(epochs_in_region)) * 3
+
+    # ---- end to end through the reference-facing call: host batches in, float loss out ----
+    hb = [tuple(x.cpu().pin_memory() for x in next(batches)) for _ in range(min(args.steps, 20))]
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    for b in hb[:2]:
+        e.step(*(x.to(dev, non_blocking=True) for x in b)); e.read_loss(0)
+    barrier()
+    t0.record()
+    for b in hb:
+        e.step(*(x.to(dev, non_blocking=True) for x in b), loss_slot=0)
+        e.read_loss(0)                                   # D2H of the batch loss (BPRMF.py:125)
+    t1.record()
+    barrier()
+    e2e_ms = t0.elapsed_time(t1)
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = world * len(hb) * B / e2e_ms * 1e3
+
+    # ---- per-kernel shares (profiling entry point; separate from the timed region) ----------
+    phases = {}
+    for _ in range(8):
+        for k_, v in e.step_timed(*next(batches)).items():
+            phases[k_] = phases.get(k_, 0.0) + v / 8
+    hbm, tf_burst, tf_sus, src = load_peaks()
+    step_ms = ms / args.steps
+    bpt = bytes_per_triple(K, d, D, B)
+    dom = max(phases, key=phases.get)
+    rows_bytes = 2 * B * D * 4.0
+    kern_bytes = {"project": rows_bytes + 2 * B * e.de * 4.0, "grad_E": rows_bytes + 2 * B * e.de * 4.0,
+                  "score_grad": B * (24.0 * (3 * K + d + 2) / 6 * 2), "adam_rows": B * 24.0 * (3 * K + d + 2) * 4 / 6,
+                  "catchup": B * 24.0 * (3 * K + d + 2), "mark": 12.0 * B, "adam_E": 28.0 * D * e.de if D else 0,
+                  "finish": 0.0}
+    ach = kern_bytes.get(dom, 0.0) / (phases[dom] * 1e-3) / 1e9 if phases[dom] > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm, "unit": "GB/s",
+                "frac": ach / hbm, "traffic": None, "peak_source": src,
+                "kernel_ms": phases[dom], "phase_ms": phases}
+    step_roof = {"achieved": B * bpt / (step_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                 "bytes_per_triple": bpt}
+    step_roof["frac"] = step_roof["achieved"] / hbm
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
+            "clocks": clk, "gpu_launches": gpu_launches,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 12 * B, "d2h_bytes_per_step": 8,
+                    "steps": len(hb)},
+            "roofline": roofline, "step_roofline": step_roof}
+
+    # ---- evaluation: users/s full-catalog top-k, train items masked -------------------------
+    if not args.no_eval:
+        st = data.device_state(str(dev))
+        e.flush()
+        torch.cuda.synchronize()
+        nu = min(args.users, 8192)
+        e.score_topk(st["row_ptr"], st["col_sorted"], args.top_k, u0=0, u1=256)      # warm-up
+        barrier()
+        a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        e.theta(refresh=True)
+        ids, sc = e.score_topk(st["row_ptr"], st["col_sorted"], args.top_k, u0=0, u1=nu)
+        b2.record()
+        barrier()
+        ems = a.elapsed_time(b2)
+        flops_user = 2.0 * args.items * (K + d) + 2.0 * args.items
+        line["eval"] = {"metric": "users/s full-catalog top-%d eval" % args.top_k, "value": nu / ems * 1e3,
+                        "unit": "users/s", "users": nu, "ms": ems, "kernel": "k_score_topk (fp32 CUDA cores)",
+                        "roofline": {"bound": "tensor", "achieved": nu * flops_user / (ems * 1e-3) / 1e12,
+                                     "peak": tf_burst, "unit": "TFLOP/s",
+                                     "frac": nu * flops_user / (ems * 1e-3) / 1e12 / tf_burst}}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        F_host = e.F.cpu().numpy() if D else None
+        v, n, el = cpu_oracle_rate(args, inter, F_host, args.cpu_seconds, B)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": len(os.sched_getaffinity(0)), "kind": "port",
+                                "sample": "%d steps of B=%d in %.1f s on the full tables (NumPy oracle of the "
+                                          "reference step with TF-2.3 dense Keras-Adam)" % (n, B, el)}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_fvx(a)

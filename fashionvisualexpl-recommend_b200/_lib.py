@@ -1,0 +1,109 @@
+"""ctypes binding of csrc/libfvx.so (the C ABI declared in include/fvx.h).
+
+The library is loaded lazily on first use; loading or calling it without the built
+shared object or without a CUDA device raises - there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "libfvx.so")
+
+ABI_VERSION = 1
+ADAM_DENSE, ADAM_DEFERRED, ADAM_LAZY = 0, 1, 2
+N_PHASES = 8
+PHASES = ("mark", "catchup", "project", "score_grad", "grad_E", "adam_rows", "adam_E", "finish")
+ADAM_MODES = {"dense": ADAM_DENSE, "deferred": ADAM_DEFERRED, "lazy": ADAM_LAZY}
+
+_p = C.c_void_p
+
+
+class FvxTable(C.Structure):
+    _fields_ = [("w", _p), ("m", _p), ("v", _p), ("g", _p), ("last", _p), ("mark", _p), ("list", _p),
+                ("count", _p), ("rows", C.c_int64), ("stride", C.c_int32), ("list_cap", C.c_int32)]
+
+
+class FvxModel(C.Structure):
+    _fields_ = [("abi_version", C.c_int32), ("num_users", C.c_int32), ("num_items", C.c_int32),
+                ("item_lo", C.c_int32), ("item_cnt", C.c_int32), ("K", C.c_int32), ("d", C.c_int32),
+                ("D", C.c_int32), ("de", C.c_int32), ("adam_mode", C.c_int32), ("lr", C.c_float),
+                ("reg", C.c_float), ("users", FvxTable), ("items", FvxTable), ("E", _p), ("mE", _p),
+                ("vE", _p), ("gE_part", _p), ("ge_parts", C.c_int32), ("_pad0", C.c_int32), ("F", _p),
+                ("F_hi", _p), ("F_lo", _p), ("step", _p), ("loss", _p), ("loss_slots", C.c_int32),
+                ("_pad1", C.c_int32), ("TH", _p), ("W", _p), ("rows", _p), ("max_batch", C.c_int32),
+                ("use_tensor_cores", C.c_int32)]
+
+
+# name -> (restype, argtypes); exactly the prototypes of include/fvx.h
+_i32, _i64, _u32, _u64 = C.c_int32, C.c_int64, C.c_uint32, C.c_uint64
+_MP = C.POINTER(FvxModel)
+PROTOTYPES = {
+    "fvx_abi_version": (C.c_int, []),
+    "fvx_last_error": (C.c_char_p, []),
+    "fvx_sizeof_model": (C.c_int, []),
+    "fvx_sizeof_table": (C.c_int, []),
+    "fvx_enumerate_epoch": (C.c_int, [_p, _p, _p, _p, _i32, _p, _p, _p]),
+    "fvx_perm_keys": (C.c_int, [_p, _i32, _u64, _u32, _p]),
+    "fvx_sample_negatives": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _u64, _u64, _p]),
+    "fvx_bpr_step": (C.c_int, [_MP, _p, _p, _p, _i32, _i32, _p]),
+    "fvx_bpr_step_timed": (C.c_int, [_MP, _p, _p, _p, _i32, _i32, C.POINTER(C.c_float), _p]),
+    "fvx_adam_flush": (C.c_int, [_MP, _p]),
+    "fvx_project": (C.c_int, [_MP, _p, _p]),
+    "fvx_predict_all": (C.c_int, [_MP, _p, _i32, _i32, _p, _p]),
+    "fvx_score_topk": (C.c_int, [_MP, _p, _i32, _i32, _p, _p, _i32, _p, _p, _i32, _p, _p, _p]),
+    "fvx_score_pairs": (C.c_int, [_MP, _p, _p, _p, _i64, _p, _p]),
+    "fvx_topk_merge": (C.c_int, [_p, _p, _i64, _i32, _i32, _p, _p, _p]),
+    "fvx_split_bf16": (C.c_int, [_p, _p, _p, _i64, _p]),
+}
+
+_lib = None
+
+
+class FvxError(RuntimeError):
+    pass
+
+
+def load():
+    """Loads libfvx.so (once) and checks the ABI version and struct layouts."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FvxError("libfvx.so is not built (%s missing): run `python -m fvx.build`; "
+                       "this package has no CPU fallback" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)          # AttributeError if a declared symbol is not exported
+        fn.restype, fn.argtypes = res, args
+    if lib.fvx_abi_version() != ABI_VERSION:
+        raise FvxError("libfvx ABI %d != binding %d" % (lib.fvx_abi_version(), ABI_VERSION))
+    if lib.fvx_sizeof_model() != C.sizeof(FvxModel) or lib.fvx_sizeof_table() != C.sizeof(FvxTable):
+        raise FvxError("struct layout mismatch between include/fvx.h and fvx/_lib.py")
+    _lib = lib
+    return lib
+
+
+def call(name, *args):
+    """Calls an entry point; non-zero return -> FvxError(fvx_last_error())."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise FvxError("%s failed (%d): %s" % (name, rc, lib.fvx_last_error().decode()))
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (None -> NULL); must be a contiguous CUDA tensor."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise FvxError("libfvx entry points take CUDA tensors only (got a %s tensor)" % t.device)
+    if not t.is_contiguous():
+        raise FvxError("libfvx entry points take contiguous tensors")
+    return t.data_ptr()
+
+
+def stream_ptr():
+    import torch
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,267 @@
+"""Device-resident model state and the thin host wrappers over the C ABI.
+
+``Engine`` owns the torch tensors (torch is used for device memory and streams only),
+fills the ``FvxModel`` struct of include/fvx.h with their raw pointers and exposes one
+method per entry point.  The reference-facing classes (recommender/models/BPRMF.py,
+VBPR.py, recommender/Evaluator.py, dataset/dataset.py) are built on it.
+
+HBM layout (fp32, row-major):
+  users table  UT[U, Su]   Su = round_up4(K+d):  cols [0,K) = Gu, [K,K+d) = Tu
+  items table  IT[Ic, Si]  Si = round_up4(K+1):  cols [0,K) = Gi, col K = Bi   (Ic = owned rows)
+  E_ext[D, de]             de = round_up4(d+1):  cols [0,d) = E,  col d = Bp
+  each table has m, v (Adam) and g (gradient accumulator) twins of the same shape.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import FvxModel, FvxTable, call, ptr, stream_ptr
+
+
+def _r4(x):
+    return (x + 3) // 4 * 4
+
+
+class Engine:
+    def __init__(self, num_users, num_items, K, d=0, D=0, lr=1e-3, reg=0.0, adam_mode="deferred",
+                 max_batch=4096, device="cuda:0", item_lo=0, item_cnt=None, loss_slots=4096,
+                 ge_parts=80, seed=0, use_tensor_cores=False):
+        if not torch.cuda.is_available():
+            raise _lib.FvxError("no CUDA device: the fvx engine has no CPU path")
+        _lib.load()
+        self.device = torch.device(device)
+        torch.cuda.set_device(self.device)
+        self.U, self.I, self.K, self.d, self.D = int(num_users), int(num_items), int(K), int(d), int(D)
+        if self.D == 0:
+            self.d = 0
+        self.item_lo = int(item_lo)
+        self.Ic = int(item_cnt) if item_cnt is not None else self.I - self.item_lo
+        self.Su, self.Si, self.de = _r4(self.K + self.d), _r4(self.K + 1), _r4(self.d + 1) if self.D else 0
+        self.lr, self.reg = float(lr), float(reg)
+        self.adam_mode = _lib.ADAM_MODES[adam_mode] if isinstance(adam_mode, str) else int(adam_mode)
+        self.max_batch = int(max_batch)
+        self.loss_slots = int(loss_slots)
+        dev = self.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        i32 = dict(dtype=torch.int32, device=dev)
+
+        def table(rows, stride, cap):
+            t = {k: torch.zeros(rows, stride, **f32) for k in ("w", "m", "v", "g")}
+            t["last"] = torch.zeros(rows, **i32)
+            t["mark"] = torch.zeros(rows, **i32)
+            t["list"] = torch.zeros(cap, **i32)
+            t["count"] = torch.zeros(1, **i32)
+            return t
+
+        self.users = table(self.U, self.Su, self.max_batch)
+        self.items = table(self.Ic, self.Si, 2 * self.max_batch)
+        self.step_t = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.loss_t = torch.zeros(self.loss_slots, dtype=torch.float64, device=dev)
+        self.rows_t = torch.zeros(2 * self.max_batch, **i32)
+        self.F = self.F_hi = self.F_lo = None
+        if self.D:
+            self.E = torch.zeros(self.D, self.de, **f32)
+            self.mE, self.vE = torch.zeros_like(self.E), torch.zeros_like(self.E)
+            self.ge_parts = int(ge_parts)
+            self.gE_part = torch.zeros(self.ge_parts, self.D, self.de, **f32)
+            self.TH = torch.zeros(2 * self.max_batch, self.de, **f32)
+            self.W = torch.zeros(2 * self.max_batch, self.de, **f32)
+        else:
+            self.E = self.mE = self.vE = self.gE_part = self.TH = self.W = None
+            self.ge_parts = 0
+        self.use_tensor_cores = bool(use_tensor_cores)
+        self._theta = None
+        self._theta_step = -1
+        self.init_glorot(seed)
+        self._struct = None
+
+    # ---- parameters ---------------------------------------------------------------------
+    def init_glorot(self, seed=0):
+        """GlorotUniform with the reference's 2-D shapes (BPRMF.py:35,48-50; VBPR.py:44-54);
+        Bi = 0.  TF's RNG stream is not reproducible, so values differ from a TF run."""
+        g = torch.Generator(device=self.device).manual_seed(int(seed))
+
+        def glorot(r, c, rows, cols):
+            lim = math.sqrt(6.0 / (r + c))
+            return (torch.rand(rows, cols, generator=g, device=self.device) * 2 - 1) * lim
+
+        uw, iw = self.users["w"], self.items["w"]
+        uw.zero_()
+        iw.zero_()
+        uw[:, :self.K] = glorot(self.U, self.K, self.U, self.K)
+        iw[:, :self.K] = glorot(self.I, self.K, self.Ic, self.K)
+        if self.D:
+            uw[:, self.K:self.K + self.d] = glorot(self.U, self.d, self.U, self.d)
+            self.E.zero_()
+            self.E[:, :self.d] = glorot(self.D, self.d, self.D, self.d)
+            self.E[:, self.d:self.d + 1] = glorot(self.D, 1, self.D, 1)
+
+    # reference attribute names as views into the packed tables
+    @property
+    def Gu(self): return self.users["w"][:, :self.K]
+    @property
+    def Tu(self): return self.users["w"][:, self.K:self.K + self.d]
+    @property
+    def Gi(self): return self.items["w"][:, :self.K]
+    @property
+    def Bi(self): return self.items["w"][:, self.K]
+    @property
+    def Ew(self): return self.E[:, :self.d]
+    @property
+    def Bp(self): return self.E[:, self.d:self.d + 1]
+
+    def load_params(self, P):
+        """P: dict with Gu, Gi, Bi (and Tu, E, Bp) as numpy arrays / tensors; Gi, Bi in
+        GLOBAL item order (the owned rows are sliced out)."""
+        def dv(x):
+            return torch.as_tensor(np.asarray(x), dtype=torch.float32).to(self.device)
+        lo, hi = self.item_lo, self.item_lo + self.Ic
+        self.Gu.copy_(dv(P["Gu"]))
+        self.Gi.copy_(dv(P["Gi"])[lo:hi])
+        self.Bi.copy_(dv(P["Bi"])[lo:hi])
+        if self.D:
+            self.Tu.copy_(dv(P["Tu"]))
+            self.Ew.copy_(dv(P["E"]))
+            self.Bp.copy_(dv(P["Bp"]).reshape(self.D, 1))
+        self._theta_step = -1
+
+    def params(self):
+        """Flushes deferred optimiser state and returns the parameters as numpy arrays."""
+        self.flush()
+        out = {"Gu": self.Gu, "Gi": self.Gi, "Bi": self.Bi}
+        if self.D:
+            out.update({"Tu": self.Tu, "E": self.Ew, "Bp": self.Bp})
+        return {k: v.detach().cpu().numpy().copy() for k, v in out.items()}
+
+    def set_features(self, F):
+        """F: [Ic, D] (owned rows) already normalised by the global max|F|."""
+        F = torch.as_tensor(np.asarray(F) if not torch.is_tensor(F) else F)
+        if tuple(F.shape) != (self.Ic, self.D):
+            raise ValueError("features must be [%d, %d], got %s" % (self.Ic, self.D, tuple(F.shape)))
+        self.F = F.to(self.device, dtype=torch.float32).contiguous()
+        if self.use_tensor_cores:
+            self.F_hi = torch.empty(self.Ic, self.D, dtype=torch.uint16, device=self.device)
+            self.F_lo = torch.empty_like(self.F_hi)
+            call("fvx_split_bf16", ptr(self.F), ptr(self.F_hi), ptr(self.F_lo), self.F.numel(), stream_ptr())
+        self._struct = None
+        self._theta_step = -1
+
+    # ---- the struct handed to the C ABI ------------------------------------------------
+    def _table_struct(self, t, rows, stride):
+        return FvxTable(ptr(t["w"]), ptr(t["m"]), ptr(t["v"]), ptr(t["g"]), ptr(t["last"]), ptr(t["mark"]),
+                        ptr(t["list"]), ptr(t["count"]), rows, stride, t["list"].numel())
+
+    def struct(self):
+        if self._struct is None:
+            if self.D and self.F is None:
+                raise _lib.FvxError("VBPR engine: set_features() must be called before use")
+            m = FvxModel()
+            m.abi_version = _lib.ABI_VERSION
+            m.num_users, m.num_items, m.item_lo, m.item_cnt = self.U, self.I, self.item_lo, self.Ic
+            m.K, m.d, m.D, m.de, m.adam_mode = self.K, self.d, self.D, self.de, self.adam_mode
+            m.lr, m.reg = self.lr, self.reg
+            m.users = self._table_struct(self.users, self.U, self.Su)
+            m.items = self._table_struct(self.items, self.Ic, self.Si)
+            m.E, m.mE, m.vE, m.gE_part = ptr(self.E), ptr(self.mE), ptr(self.vE), ptr(self.gE_part)
+            m.ge_parts = self.ge_parts
+            m.F, m.F_hi, m.F_lo = ptr(self.F), ptr(self.F_hi), ptr(self.F_lo)
+            m.step, m.loss, m.loss_slots = ptr(self.step_t), ptr(self.loss_t), self.loss_slots
+            m.TH, m.W, m.rows = ptr(self.TH), ptr(self.W), ptr(self.rows_t)
+            m.max_batch, m.use_tensor_cores = self.max_batch, int(self.use_tensor_cores)
+            self._struct = m
+        return self._struct
+
+    def set_hyper(self, lr=None, reg=None):
+        if lr is not None:
+            self.lr = float(lr)
+        if reg is not None:
+            self.reg = float(reg)
+        self._struct = None
+
+    # ---- training ------------------------------------------------------------------------
+    @staticmethod
+    def _i32(x, dev):
+        if torch.is_tensor(x):
+            return x.to(device=dev, dtype=torch.int32).contiguous()
+        return torch.as_tensor(np.ascontiguousarray(np.asarray(x), dtype=np.int32)).to(dev)
+
+    def step(self, user, pos, neg, loss_slot=0):
+        """One optimiser step (fvx_bpr_step); asynchronous.  Index tensors: int32 CUDA."""
+        B = user.numel()
+        call("fvx_bpr_step", C.byref(self.struct()), ptr(user), ptr(pos), ptr(neg), B, loss_slot, stream_ptr())
+
+    def step_timed(self, user, pos, neg, loss_slot=0):
+        """Profiling step: returns {phase: ms} (synchronises)."""
+        out = (C.c_float * _lib.N_PHASES)()
+        call("fvx_bpr_step_timed", C.byref(self.struct()), ptr(user), ptr(pos), ptr(neg), user.numel(),
+             loss_slot, out, stream_ptr())
+        return dict(zip(_lib.PHASES, [float(x) for x in out]))
+
+    def flush(self):
+        call("fvx_adam_flush", C.byref(self.struct()), stream_ptr())
+
+    def steps_done(self):
+        return int(self.step_t.item())
+
+    def read_loss(self, slot=0, clear=True):
+        v = float(self.loss_t[slot].item())
+        if clear:
+            self.loss_t[slot] = 0
+        return v
+
+    # ---- evaluation ----------------------------------------------------------------------
+    def theta(self, refresh=False):
+        """theta_ext = F * E_ext over the owned catalog rows, cached per optimiser step."""
+        if not self.D:
+            return None
+        s = self.steps_done()
+        if refresh or self._theta is None or self._theta_step != s:
+            if self._theta is None:
+                self._theta = torch.empty(self.Ic, self.de, dtype=torch.float32, device=self.device)
+            call("fvx_project", C.byref(self.struct()), ptr(self._theta), stream_ptr())
+            self._theta_step = s
+        return self._theta
+
+    def predict_all(self, u0=0, u1=None):
+        u1 = self.U if u1 is None else u1
+        self.flush()
+        out = torch.empty(u1 - u0, self.Ic, dtype=torch.float32, device=self.device)
+        call("fvx_predict_all", C.byref(self.struct()), ptr(self.theta()), u0, u1, ptr(out), stream_ptr())
+        return out
+
+    def score_pairs(self, user, item):
+        self.flush()
+        out = torch.empty(user.numel(), dtype=torch.float32, device=self.device)
+        call("fvx_score_pairs", C.byref(self.struct()), ptr(self.theta()), ptr(user), ptr(item), user.numel(),
+             ptr(out), stream_ptr())
+        return out
+
+    def score_topk(self, mask_row_ptr, mask_col, k, u0=0, u1=None, thr_scores=None):
+        """Masked top-k (+ optional rank counts) for users [u0,u1): (ids, scores[, counts])."""
+        u1 = self.U if u1 is None else u1
+        self.flush()
+        n = u1 - u0
+        ids = torch.empty(n, k, dtype=torch.int32, device=self.device)
+        sc = torch.empty(n, k, dtype=torch.float32, device=self.device)
+        n_thr, counts = 0, None
+        if thr_scores is not None:
+            n_thr = thr_scores.shape[1]
+            counts = torch.zeros(n, n_thr, dtype=torch.int32, device=self.device)
+        call("fvx_score_topk", C.byref(self.struct()), ptr(self.theta()), u0, u1, ptr(mask_row_ptr),
+             ptr(mask_col), k, ptr(ids), ptr(sc), n_thr, ptr(thr_scores), ptr(counts), stream_ptr())
+        return (ids, sc, counts) if thr_scores is not None else (ids, sc)
+
+
+def topk_merge(ids, scores):
+    """ids/scores: [n_users, R, k] per-shard sorted lists -> merged [n_users, k]."""
+    n, R, k = ids.shape
+    out_i = torch.empty(n, k, dtype=torch.int32, device=ids.device)
+    out_s = torch.empty(n, k, dtype=torch.float32, device=ids.device)
+    call("fvx_topk_merge", ptr(ids.contiguous()), ptr(scores.contiguous()), n, R, k, ptr(out_i), ptr(out_s),
+         stream_ptr())
+    return out_i, out_s

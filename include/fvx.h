@@ -1,0 +1,184 @@
+/* fvx.h - C ABI of libfvx.so: the B200 (sm_100a) BPR train step and full-catalog
+ * top-k evaluation of BPRMF / VBPR.
+ *
+ * The reference (peternara/FashionVisualExpl-recommend) has no FFI layer: its hot
+ * path is a Python class protocol over TensorFlow ops.  Each entry point below
+ * replaces the TensorFlow/NumPy work of the reference call site cited next to it;
+ * the Python mirror classes in fashionvisualexpl-recommend_b200/ bind them with
+ * ctypes (see INTEGRATION.md for the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - plain C: pointers and sizes only, no torch / C++ types;
+ *   - every pointer in FvxModel / FvxTable / arguments is a DEVICE pointer unless
+ *     its name ends in _host; memory is owned by the caller (torch tensors) and
+ *     only borrowed for the duration of the stream-ordered call;
+ *   - every call is asynchronous on `stream` (a cudaStream_t) and performs no
+ *     host synchronisation, so it can be captured into a CUDA graph;
+ *   - return value 0 = success, negative = error; fvx_last_error() gives the text
+ *     (thread-local).  There is no CPU fallback.
+ *   - the optimiser step counter lives on the device (FvxModel.step) so that a
+ *     captured graph of steps can be replayed.
+ */
+#ifndef FVX_H_
+#define FVX_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* fvx_stream_t; /* cudaStream_t */
+
+#define FVX_ABI_VERSION 1
+
+/* Adam semantics.  The reference's Keras Adam moves
+ * EVERY row of an embedding table on every step (rows without gradient keep
+ * moving on momentum).  DENSE reproduces that literally with a whole-table sweep;
+ * DEFERRED gives the same result (to fp32 rounding) by replaying the skipped
+ * zero-gradient steps of a row when it is next touched; LAZY skips untouched rows
+ * (NOT reference semantics - a labelled fast mode). */
+enum { FVX_ADAM_DENSE = 0, FVX_ADAM_DEFERRED = 1, FVX_ADAM_LAZY = 2 };
+
+/* One embedding table with its optimiser state, row-major, row stride `stride`
+ * floats (a multiple of 4 so rows are 16-byte aligned).
+ *   user table: cols [0,K) = Gu (BPRMF.py:49), cols [K,K+d) = Tu (VBPR.py:46-48)
+ *   item table: cols [0,K) = Gi (BPRMF.py:50), col K = Bi (BPRMF.py:48)          */
+typedef struct FvxTable {
+  float* w;        /* [rows, stride] parameters                                   */
+  float* m;        /* [rows, stride] Adam first moment                            */
+  float* v;        /* [rows, stride] Adam second moment                           */
+  float* g;        /* [rows, stride] gradient accumulator, all-zero between steps */
+  int32_t* last;   /* [rows] step up to which the row is current (DEFERRED)       */
+  int32_t* mark;   /* [rows] step at which the row was last marked as touched     */
+  int32_t* list;   /* [list_cap] rows touched by the step in flight               */
+  int32_t* count;  /* [1] number of valid entries in list                         */
+  int64_t rows;
+  int32_t stride;
+  int32_t list_cap;
+} FvxTable;
+
+typedef struct FvxModel {
+  int32_t abi_version;  /* FVX_ABI_VERSION */
+  int32_t num_users;    /* U */
+  int32_t num_items;    /* I: size of the whole catalog                            */
+  int32_t item_lo;      /* first catalog row owned by this rank (0 on one GPU)      */
+  int32_t item_cnt;     /* catalog rows owned by this rank (I on one GPU)           */
+  int32_t K;            /* embed_k                                                  */
+  int32_t d;            /* embed_d (0 for BPRMF)                                    */
+  int32_t D;            /* CNN feature dimension (0 for BPRMF)                      */
+  int32_t de;           /* row stride of E_ext: round_up4(d+1)                      */
+  int32_t adam_mode;    /* FVX_ADAM_*                                               */
+  float lr, reg;        /* Adam(lr) BPRMF.py:52; reg BPRMF.py:38                    */
+  FvxTable users;       /* [U, round_up4(K+d)]                                      */
+  FvxTable items;       /* [item_cnt, round_up4(K+1)], local row = item - item_lo   */
+  /* dense visual parameters, VBPR.py:44-54: E_ext[D,de], cols [0,d) = E, col d = Bp */
+  float *E, *mE, *vE;
+  float* gE_part;       /* [ge_parts, D, de] per-CTA-group partial gradients        */
+  int32_t ge_parts;
+  int32_t _pad0;
+  const float* F;       /* [item_cnt, D] fp32 features, already /max|F|
+                           (visual_loader_mixin.py:30)                              */
+  const uint16_t* F_hi; /* [item_cnt, D] bf16 high plane of F (tensor-core path)    */
+  const uint16_t* F_lo; /* [item_cnt, D] bf16 plane of F - float(F_hi)              */
+  int64_t* step;        /* [1] number of optimiser steps applied so far             */
+  double* loss;         /* [loss_slots] per-step loss accumulators                  */
+  int32_t loss_slots;
+  int32_t _pad1;
+  /* per-step scratch, sized for max_batch triples */
+  float* TH;            /* [2*max_batch, de] F[i]*E_ext for (triple, side)          */
+  float* W;             /* [2*max_batch, de] backward coefficients                  */
+  int32_t* rows;        /* [2*max_batch] local item row of each (triple, side) slot,
+                           -1 when the item belongs to another rank                 */
+  int32_t max_batch;
+  int32_t use_tensor_cores; /* 0: fp32 SIMT projection; 1: tcgen05 (needs F_hi/F_lo) */
+} FvxModel;
+
+/* ---- library ------------------------------------------------------------------ */
+int fvx_abi_version(void);
+const char* fvx_last_error(void);
+/* size of the structs as compiled, so a binding can assert its own layout */
+int fvx_sizeof_model(void);
+int fvx_sizeof_table(void);
+
+/* ---- data: replaces DataLoader.all_triple_batches (dataset.py:83-114) ---------- */
+
+/* (user, pos) pairs of one epoch in the reference's enumeration order: users in
+ * `perm` order, each user's positives in file order (dataset.py:96-99).
+ * offs[p] = exclusive prefix sum of the train-list lengths in perm order. */
+int fvx_enumerate_epoch(const int64_t* row_ptr, const int32_t* col_file, const int32_t* perm,
+                        const int64_t* offs, int32_t num_users, int32_t* out_user,
+                        int32_t* out_pos, fvx_stream_t stream);
+
+/* One 32-bit Philox key per user for the epoch permutation (stable argsort of the
+ * keys = user order of that epoch); replaces random.shuffle (dataset.py:95). */
+int fvx_perm_keys(uint32_t* keys, int32_t num_users, uint64_t seed, uint32_t epoch,
+                  fvx_stream_t stream);
+
+/* Uniform negatives with rejection against the user's TRAIN items
+ * (dataset.py:100-103); counter-based: triple n uses counter offset+n. */
+int fvx_sample_negatives(const int64_t* row_ptr, const int32_t* col_sorted, const int32_t* user,
+                         int32_t* neg, int64_t n, int32_t num_items, uint64_t seed,
+                         uint64_t offset, fvx_stream_t stream);
+
+/* ---- training: replaces train_step (BPRMF.py:87-125, VBPR.py:99-144) ----------- */
+
+/* One optimiser step on a batch of B triples (global item ids).  Adds the batch
+ * loss (BPRMF.py:104-115 / VBPR.py:117-130) into model->loss[loss_slot]. */
+int fvx_bpr_step(const FvxModel* model, const int32_t* user, const int32_t* pos,
+                 const int32_t* neg, int32_t B, int32_t loss_slot, fvx_stream_t stream);
+
+/* Profiling variant of fvx_bpr_step: same work, CUDA events between the phases, and a
+ * host synchronisation at the end (so it cannot be graph-captured).  phase_ms_host
+ * receives FVX_N_PHASES durations in launch order: mark, catch-up, projection,
+ * score+grad, grad_E, Adam rows, Adam E, finish. */
+#define FVX_N_PHASES 8
+int fvx_bpr_step_timed(const FvxModel* model, const int32_t* user, const int32_t* pos,
+                       const int32_t* neg, int32_t B, int32_t loss_slot, float* phase_ms_host,
+                       fvx_stream_t stream);
+
+/* DEFERRED mode: bring every row of both tables up to the current step (call
+ * before reading parameters: evaluation, checkpoint, predict_all). */
+int fvx_adam_flush(const FvxModel* model, fvx_stream_t stream);
+
+/* ---- evaluation: replaces predict_all + the evaluator's host loops ------------- */
+
+/* theta_ext[rows, de] = F[rows] * E_ext  (VBPR.py:95-97: matmul(F, E), matmul(F, Bp)) */
+int fvx_project(const FvxModel* model, float* theta_ext, fvx_stream_t stream);
+
+/* Dense scores for users [u0,u1) over the owned catalog rows, row-major
+ * [u1-u0, item_cnt] (BPRMF.py:85 / VBPR.py:95-97).  Small sizes only. */
+int fvx_predict_all(const FvxModel* model, const float* theta_ext, int32_t u0, int32_t u1,
+                    float* out, fvx_stream_t stream);
+
+/* Masked top-k for users [u0,u1) over the owned catalog rows without materialising
+ * the score matrix: items in the mask CSR (the user's train items, Evaluator.py:235;
+ * global ids, ascending per user) are excluded; ties go to the smaller item id.
+ * out_ids [u1-u0, k] are GLOBAL item ids (-1 / -inf when fewer than k candidates).
+ * Rank counts (Evaluator.py:96-98): with n_thr > 0, thr_scores[(u-u0)*n_thr + t]
+ * (NaN = unused) are scores of held-out items and out_counts[(u-u0)*n_thr + t]
+ * receives the number of owned, non-masked items whose score is >= that value
+ * (the held-out item itself included when owned).  k <= 128, n_thr <= 4. */
+int fvx_score_topk(const FvxModel* model, const float* theta_ext, int32_t u0, int32_t u1,
+                   const int64_t* mask_row_ptr, const int32_t* mask_col, int32_t k,
+                   int32_t* out_ids, float* out_scores, int32_t n_thr, const float* thr_scores,
+                   int32_t* out_counts, fvx_stream_t stream);
+
+/* Scores of explicit (user, item) pairs with owned items (0 for others):
+ * BPRMF.call / VBPR.call x_ui (BPRMF.py:69-74, VBPR.py:73-84). */
+int fvx_score_pairs(const FvxModel* model, const float* theta_ext, const int32_t* user,
+                    const int32_t* item, int64_t n, float* out, fvx_stream_t stream);
+
+/* Merge R per-shard top-k lists per user ([n_users, R, k] ids/scores, each list
+ * sorted descending) into one [n_users, k] list; ties -> smaller item id. */
+int fvx_topk_merge(const int32_t* ids, const float* scores, int64_t n_users, int32_t R, int32_t k,
+                   int32_t* out_ids, float* out_scores, fvx_stream_t stream);
+
+/* ---- feature planes for the tensor-core path ----------------------------------- */
+/* hi = bf16(F), lo = bf16(F - float(hi)) : 4 bytes/element like fp32, ~2^-17 rel. */
+int fvx_split_bf16(const float* src, uint16_t* hi, uint16_t* lo, int64_t n, fvx_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FVX_H_ */

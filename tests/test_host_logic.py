@@ -1,0 +1,175 @@
+"""CPU: host-side logic of the package (no CUDA): the reference-stream sampler, the
+evaluator's count->metric arithmetic against the reference's own Evaluator output, the
+TSV writer, and that the C-ABI library loads and exports every declared symbol."""
+import argparse
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN, golden, tiny_dataset
+
+from fvx.config import configs
+from fvx.dataset.dataset import DataLoader
+from fvx.recommender.Evaluator import Evaluator, write_recs_tsv
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def tiny_params(**kw):
+    d = dict(dataset="tiny", batch_size=16, epochs=3, validation=True, batch_eval=128, top_k=5)
+    d.update(kw)
+    return argparse.Namespace(**d)
+
+
+@pytest.fixture()
+def tiny_loader():
+    configs.set_roots(data=GOLDEN)
+    return DataLoader(tiny_params())
+
+
+def test_dataloader_matches_reference_lists(tiny_loader):
+    U, I, tr, va, te, _ = tiny_dataset()
+    d = tiny_loader
+    assert (d.num_users, d.num_items) == (U, I)
+    assert [d.training_list[u] for u in range(U)] == tr
+    assert [d.validation_list[u] for u in range(U)] == va
+    assert [d.test_list[u] for u in range(U)] == te
+    assert len(d.training_list) == U and bool(d.validation_list)
+
+
+def test_host_ref_sampler_is_the_reference_stream(tiny_loader):
+    g = golden("sampler_ref.npz")
+    u, p, n = tiny_loader.all_triple_batches()
+    assert (u == g["users"]).all() and (p == g["pos"]).all() and (n == g["neg"]).all()
+
+
+def test_host_ref_sampler_empty_and_truncated():
+    configs.set_roots(data=GOLDEN)
+    d = DataLoader(tiny_params(batch_size=100000))           # N // B == 0 -> no triples at all
+    u, p, n = d.all_triple_batches()
+    assert len(u) == len(p) == len(n) == 0
+    d = DataLoader(tiny_params(batch_size=100, epochs=1))     # truncated inside the first epoch
+    u, p, n = d.all_triple_batches()
+    assert len(u) == (d.num_train // 100) * 100
+    full = golden("sampler_ref.npz")
+    assert (u == full["users"][:len(u)]).all() and (n == full["neg"][:len(u)]).all()
+
+
+class _MockEngine:
+    """Stands in for fvx.engine.Engine on the CPU: same call contract, scores from a matrix."""
+
+    def __init__(self, scores, train_lists):
+        self.scores, self.tr = scores, train_lists
+        self.device = torch.device("cpu")
+
+    def score_pairs(self, users, items):
+        return torch.from_numpy(self.scores[users.numpy(), items.numpy()])
+
+    def score_topk(self, row_ptr, col, k, u0=0, u1=None, thr_scores=None):
+        U, I = self.scores.shape
+        ids = np.zeros((U, k), np.int32)
+        sc = np.zeros((U, k), np.float32)
+        cnt = np.zeros((U, thr_scores.shape[1]), np.int32) if thr_scores is not None else None
+        for u in range(U):
+            row = self.scores[u].copy()
+            keep = np.ones(I, bool)
+            keep[self.tr[u]] = False
+            if cnt is not None:
+                with np.errstate(invalid="ignore"):
+                    for t in range(cnt.shape[1]):
+                        cnt[u, t] = int((row[keep] >= thr_scores[u, t].item()).sum())
+            row[~keep] = -np.inf
+            o = np.argsort(-row.astype(np.float64), kind="stable")[:k]
+            ids[u], sc[u] = o, row[o]
+        out = (torch.from_numpy(ids), torch.from_numpy(sc))
+        return out + (torch.from_numpy(cnt),) if cnt is not None else out
+
+
+class _MockModel:
+    def __init__(self, engine):
+        self.engine = engine
+
+
+def test_evaluator_count_arithmetic_matches_reference_evaluator(tiny_loader, capsys):
+    g = golden("evaluator_ref.npz")
+    _, _, tr, _, _, _ = tiny_dataset()
+    ev = Evaluator(_MockModel(_MockEngine(g["scores"], tr)), tiny_loader, int(g["k"]))
+    results = {}
+    text = ev.eval(1, results, "golden", 0.0)
+    for key, want in zip(g["results_keys"].tolist(), g["results"].tolist()):
+        assert results[1][key] == pytest.approx(want, rel=1e-12, abs=1e-15), key
+    assert "Metrics@5 (Validation)" in text and "Metrics@5 (Test)" in text
+    assert results[1]["auc_t"] == results[1]["auc_v"]          # the reference's quirk, kept
+
+
+def test_evaluator_ragged_and_empty_held_lists(tiny_loader):
+    """Users with 0 or 2 held-out items: compare with the oracle's per-user restatement."""
+    from oracle import evaluator as oe
+    g = golden("evaluator_ref.npz")
+    U, I, tr, va, te, _ = tiny_dataset()
+    d = tiny_loader
+    te2 = [list(x) for x in te]
+    te2[0] = []                                                 # no test item: user skipped
+    te2[1] = te2[1] + [va[1][0]]                                # two test items, one shared with val
+    te2[2] = te2[2] + [tr[2][0]]                                # a held-out item that is also a train item
+    d.test_ptr = np.concatenate([[0], np.cumsum([len(x) for x in te2])]).astype(np.int64)
+    d.test_col = np.array([i for x in te2 for i in x], np.int32)
+    ev = Evaluator(_MockModel(_MockEngine(g["scores"], tr)), d, 5)
+    m = ev.user_metrics()
+    for u in range(U):
+        for split, lists in (("v", va), ("t", te2)):
+            want = oe.eval_by_user(g["scores"][u], I, tr[u], lists[u], 5)
+            if not want:
+                assert np.isnan(m[split][u]).all()
+            else:
+                assert m[split][u] == pytest.approx(np.array(want, dtype=np.float64), rel=1e-12), (u, split)
+
+
+def test_recs_tsv_format_matches_reference(tmp_path):
+    from oracle import evaluator as oe
+    g = golden("evaluator_ref.npz")
+    U, I, tr, _, _, _ = tiny_dataset()
+    k = int(g["k"])
+    ids, val = oe.masked_topk(g["scores"], tr, k)
+    path = str(tmp_path / "recs.tsv")
+    write_recs_tsv(path, ids.astype(np.int32), val)
+    mine = open(path).read().strip().split("\n")
+    ref = str(g["recs_tsv"]).strip().split("\n")
+    assert len(mine) == len(ref) == U * k
+    for u in range(U):
+        a, b = mine[u * k:(u + 1) * k], ref[u * k:(u + 1) * k]
+        if len(set(x.split("\t")[2] for x in b)) == k:          # tie-free: identical text
+            assert a == b, u
+        else:
+            assert sorted(a) == sorted(b) or [x.split("\t")[2] for x in a] == [x.split("\t")[2] for x in b]
+
+
+def test_library_exports_every_declared_symbol():
+    from fvx import _lib
+    from fvx.build import build
+    build()
+    header = open(os.path.join(REPO, "include", "fvx.h")).read()
+    declared = set(re.findall(r"\b(fvx_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.PROTOTYPES), declared ^ set(_lib.PROTOTYPES)
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    lib.fvx_last_error.restype = ctypes.c_char_p
+    assert lib.fvx_abi_version() == _lib.ABI_VERSION
+    assert lib.fvx_sizeof_model() == ctypes.sizeof(_lib.FvxModel)
+    assert lib.fvx_sizeof_table() == ctypes.sizeof(_lib.FvxTable)
+
+
+def test_no_cpu_fallback():
+    from fvx import _lib
+    from fvx.engine import Engine
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(_lib.FvxError):
+        Engine(10, 10, 4)
+    with pytest.raises(_lib.FvxError):
+        _lib.ptr(torch.zeros(4))
