@@ -4,7 +4,7 @@
 set -u
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.txt 2>&1
-echo "== pytest -m gpu" ; timeout 900 python -m pytest tests -m gpu -q -x --timeout 300 > gpurun_out/pytest_gpu.log 2>&1
+echo "== pytest -m gpu" ; timeout 900 python -m pytest tests -m gpu -q --timeout 300 > gpurun_out/pytest_gpu.log 2>&1
 T=$? ; tail -n 25 gpurun_out/pytest_gpu.log ; echo "pytest rc=$T"
 echo "== smoke" ; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
 S=$? ; tail -n 5 gpurun_out/smoke.log ; echo "smoke rc=$S"
