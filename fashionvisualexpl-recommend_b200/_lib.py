@@ -36,6 +36,12 @@ class FvxModel(C.Structure):
                 ("use_tensor_cores", C.c_int32)]
 
 
+class FvxEvalWs(C.Structure):
+    _fields_ = [("A", _p), ("Bm", _p), ("unorm", _p), ("bmax", _p), ("cand", _p), ("ccount", _p), ("flags", _p),
+                ("u_cap", C.c_int32), ("i_cap", C.c_int32), ("KP", C.c_int32), ("splits", C.c_int32),
+                ("cap", C.c_int32), ("_pad", C.c_int32)]
+
+
 # name -> (restype, argtypes); exactly the prototypes of include/fvx.h
 _i32, _i64, _u32, _u64 = C.c_int32, C.c_int64, C.c_uint32, C.c_uint64
 _MP = C.POINTER(FvxModel)
@@ -53,6 +59,8 @@ PROTOTYPES = {
     "fvx_project": (C.c_int, [_MP, _p, _p]),
     "fvx_predict_all": (C.c_int, [_MP, _p, _i32, _i32, _p, _p]),
     "fvx_score_topk": (C.c_int, [_MP, _p, _i32, _i32, _p, _p, _i32, _p, _p, _i32, _p, _p, _p]),
+    "fvx_eval_ws_query": (C.c_int, [_MP, _i32, C.POINTER(FvxEvalWs)]),
+    "fvx_score_topk_tc": (C.c_int, [_MP, _p, _i32, _i32, _p, _p, _i32, _p, _p, C.POINTER(FvxEvalWs), _p]),
     "fvx_score_pairs": (C.c_int, [_MP, _p, _p, _p, _i64, _p, _p]),
     "fvx_topk_merge": (C.c_int, [_p, _p, _i64, _i32, _i32, _p, _p, _p]),
     "fvx_split_bf16": (C.c_int, [_p, _p, _p, _i64, _p]),

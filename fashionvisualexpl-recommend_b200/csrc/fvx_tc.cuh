@@ -34,12 +34,15 @@ TC_D bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol error must not hang the GPU box - after ~2^28 polls the
-// kernel traps (reported by the host as a launch failure).
+// Bounded wait: a protocol error must not hang the GPU box - after ~2 s of polling the
+// kernel traps (the host sees a launch failure instead of a dead GPU).
 TC_D void mbar_wait(uint64_t* bar, uint32_t parity) {
-  for (uint32_t i = 0; i < (1u << 28); ++i)
-    if (mbar_try_wait(bar, parity)) return;
-  __trap();
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+#pragma unroll 1
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
 }
 
 // generic-proxy writes to shared memory -> visible to the async proxy (TMA / UMMA reads)
@@ -142,7 +145,6 @@ TC_D bool tc_elect_one() {
 }
 
 // ---- host: tensor-map encoding through the driver entry point (no link-time libcuda) ----
-#ifndef __CUDA_ARCH__
 typedef CUresult (*tc_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
                                        CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
@@ -152,4 +154,3 @@ tc_encode_tiled_fn tc_get_encode_tiled();
 // box = {box_cols, box_rows}; swizzle: 0 none, 1 32B, 2 64B, 3 128B.  Returns 0 on success.
 int tc_make_tensor_map_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_bytes,
                             uint32_t box_cols, uint32_t box_rows, int swizzle);
-#endif

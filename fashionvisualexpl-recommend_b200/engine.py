@@ -241,13 +241,27 @@ class Engine:
              ptr(out), stream_ptr())
         return out
 
-    def score_topk(self, mask_row_ptr, mask_col, k, u0=0, u1=None, thr_scores=None):
-        """Masked top-k (+ optional rank counts) for users [u0,u1): (ids, scores[, counts])."""
+    def score_topk(self, mask_row_ptr, mask_col, k, u0=0, u1=None, thr_scores=None, tc=None):
+        """Masked top-k (+ optional rank counts) for users [u0,u1): (ids, scores[, counts]).
+        ``tc``: use the tcgen05 sweep (default: the engine's ``use_tensor_cores``); it returns
+        the same ids / scores as the fp32 kernel and is only available without rank counts."""
         u1 = self.U if u1 is None else u1
         self.flush()
         n = u1 - u0
         ids = torch.empty(n, k, dtype=torch.int32, device=self.device)
         sc = torch.empty(n, k, dtype=torch.float32, device=self.device)
+        tc = self.use_tensor_cores if tc is None else tc
+        if tc and thr_scores is None and self.K + self.d + 1 <= 128 and n > 0:
+            ws = self._eval_ws(n)
+            call("fvx_score_topk_tc", C.byref(self.struct()), ptr(self.theta()), u0, u1, ptr(mask_row_ptr),
+                 ptr(mask_col), k, ptr(ids), ptr(sc), C.byref(ws["struct"]), stream_ptr())
+            bad = torch.nonzero(ws["flags"][:n]).reshape(-1)
+            self.tc_overflow_rows = int(bad.numel())
+            for r in bad.tolist():          # candidate list overflowed: exact fp32 sweep for that user
+                call("fvx_score_topk", C.byref(self.struct()), ptr(self.theta()), u0 + r, u0 + r + 1,
+                     ptr(mask_row_ptr), ptr(mask_col), k, ptr(ids[r:r + 1]), ptr(sc[r:r + 1]), 0, None, None,
+                     stream_ptr())
+            return ids, sc
         n_thr, counts = 0, None
         if thr_scores is not None:
             n_thr = thr_scores.shape[1]
@@ -255,6 +269,27 @@ class Engine:
         call("fvx_score_topk", C.byref(self.struct()), ptr(self.theta()), u0, u1, ptr(mask_row_ptr),
              ptr(mask_col), k, ptr(ids), ptr(sc), n_thr, ptr(thr_scores), ptr(counts), stream_ptr())
         return (ids, sc, counts) if thr_scores is not None else (ids, sc)
+
+    def _eval_ws(self, n_users):
+        """Caller-owned workspace of fvx_score_topk_tc, sized by fvx_eval_ws_query and cached."""
+        ws = getattr(self, "_ws", None)
+        q = _lib.FvxEvalWs()
+        call("fvx_eval_ws_query", C.byref(self.struct()), n_users, C.byref(q))
+        if ws is None or ws["n"] != n_users or ws["KP"] != q.KP or ws["splits"] != q.splits:
+            dv = self.device
+            ws = {"n": n_users, "KP": q.KP, "splits": q.splits,
+                  "A": torch.empty(n_users * q.KP, dtype=torch.uint16, device=dv),
+                  "Bm": torch.empty(self.Ic * q.KP, dtype=torch.uint16, device=dv),
+                  "unorm": torch.empty(n_users, dtype=torch.float32, device=dv),
+                  "bmax": torch.zeros(1, dtype=torch.float32, device=dv),
+                  "cand": torch.empty(n_users * q.splits * q.cap, dtype=torch.int64, device=dv),
+                  "ccount": torch.zeros(n_users * q.splits, dtype=torch.int32, device=dv),
+                  "flags": torch.zeros(n_users, dtype=torch.int32, device=dv)}
+            q.A, q.Bm, q.unorm, q.bmax = ptr(ws["A"]), ptr(ws["Bm"]), ptr(ws["unorm"]), ptr(ws["bmax"])
+            q.cand, q.ccount, q.flags = ptr(ws["cand"]), ptr(ws["ccount"]), ptr(ws["flags"])
+            ws["struct"] = q
+            self._ws = ws
+        return ws
 
 
 def topk_merge(ids, scores):

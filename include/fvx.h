@@ -164,6 +164,30 @@ int fvx_score_topk(const FvxModel* model, const float* theta_ext, int32_t u0, in
                    int32_t* out_ids, float* out_scores, int32_t n_thr, const float* thr_scores,
                    int32_t* out_counts, fvx_stream_t stream);
 
+/* Tensor-core variant of fvx_score_topk (tcgen05 + TMA; top-k only, no rank counts):
+ * a bf16 sweep selects, per user, every item whose bf16 score is within the rounding
+ * bound of the running k-th best, then the candidates are re-scored in fp32 with the
+ * same arithmetic as fvx_score_topk, so both return identical ids and scores.
+ * The caller owns the workspace: fill KP / splits / cap with fvx_eval_ws_query() and
+ * allocate A [u_cap*KP] bf16, Bm [i_cap*KP] bf16, unorm [u_cap] f32, bmax [1] f32,
+ * cand [u_cap*splits*cap] u64, ccount [u_cap*splits] i32, flags [u_cap] i32.
+ * On return flags[u-u0] != 0 marks a user whose candidate list overflowed: its output
+ * row is not valid and must be recomputed with fvx_score_topk.  Needs K+d+1 <= 128. */
+typedef struct FvxEvalWs {
+  uint16_t* A;
+  uint16_t* Bm;
+  float* unorm;
+  float* bmax;
+  uint64_t* cand;
+  int32_t* ccount;
+  int32_t* flags;
+  int32_t u_cap, i_cap, KP, splits, cap, _pad;
+} FvxEvalWs;
+int fvx_eval_ws_query(const FvxModel* model, int32_t n_users, FvxEvalWs* ws);
+int fvx_score_topk_tc(const FvxModel* model, const float* theta_ext, int32_t u0, int32_t u1,
+                      const int64_t* mask_row_ptr, const int32_t* mask_col, int32_t k,
+                      int32_t* out_ids, float* out_scores, const FvxEvalWs* ws, fvx_stream_t stream);
+
 /* Scores of explicit (user, item) pairs with owned items (0 for others):
  * BPRMF.call / VBPR.call x_ui (BPRMF.py:69-74, VBPR.py:73-84). */
 int fvx_score_pairs(const FvxModel* model, const float* theta_ext, const int32_t* user,
