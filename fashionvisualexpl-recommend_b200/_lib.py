@@ -11,7 +11,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libfvx.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 ADAM_DENSE, ADAM_DEFERRED, ADAM_LAZY = 0, 1, 2
 N_PHASES = 8
 PHASES = ("mark", "catchup", "project", "score_grad", "grad_E", "adam_rows", "adam_E", "finish")
@@ -31,8 +31,9 @@ class FvxModel(C.Structure):
                 ("D", C.c_int32), ("de", C.c_int32), ("adam_mode", C.c_int32), ("lr", C.c_float),
                 ("reg", C.c_float), ("users", FvxTable), ("items", FvxTable), ("E", _p), ("mE", _p),
                 ("vE", _p), ("gE_part", _p), ("ge_parts", C.c_int32), ("_pad0", C.c_int32), ("F", _p),
-                ("F_hi", _p), ("F_lo", _p), ("step", _p), ("loss", _p), ("loss_slots", C.c_int32),
-                ("_pad1", C.c_int32), ("TH", _p), ("W", _p), ("rows", _p), ("max_batch", C.c_int32),
+                ("F_pl", _p), ("ET_hi", _p), ("ET_lo", _p), ("W_hi", _p), ("W_lo", _p),
+                ("step", _p), ("loss", _p), ("loss_slots", C.c_int32), ("_pad1", C.c_int32), ("TH", _p),
+                ("th_cap", C.c_int64), ("W", _p), ("rows", _p), ("max_batch", C.c_int32),
                 ("use_tensor_cores", C.c_int32)]
 
 
@@ -63,7 +64,10 @@ PROTOTYPES = {
     "fvx_score_topk_tc": (C.c_int, [_MP, _p, _i32, _i32, _p, _p, _i32, _p, _p, C.POINTER(FvxEvalWs), _p]),
     "fvx_score_pairs": (C.c_int, [_MP, _p, _p, _p, _i64, _p, _p]),
     "fvx_topk_merge": (C.c_int, [_p, _p, _i64, _i32, _i32, _p, _p, _p]),
-    "fvx_split_bf16": (C.c_int, [_p, _p, _p, _i64, _p]),
+    "fvx_split_planes": (C.c_int, [_p, _p, _i64, _i32, _p]),
+    "fvx_tc_width": (C.c_int, [_i32]),
+    "fvx_project_rows": (C.c_int, [_MP, _p, _i64, _p, _p]),
+    "fvx_grad_e_rows": (C.c_int, [_MP, _p, _i64, _p, _p, _p]),
 }
 
 _lib = None

@@ -9,7 +9,22 @@ int fvx_launch_project(const FvxModel* m, const int32_t* rows, int64_t nrows, fl
 // gE_part[p] = sum over the rows of group p of F[rows[r], :]^T * W[r, :]; *parts_out groups written.
 int fvx_launch_grad_E(const FvxModel* m, const int32_t* rows, int64_t nrows, int* parts_out, cudaStream_t st);
 
-int fvx_launch_score_grad(const FvxModel* m, const int32_t* user, int B, int loss_slot, cudaStream_t st);
+// tensor-core versions (fvx_project_tc.cu).  The forward writes [ksplit][nrows][NP] fp32 K-split
+// partials (NP = fvx_tc_np(de), ksplit = fvx_tc_ksplit(...)); the backward reads the bf16 planes
+// m->W_hi / m->W_lo [nrows][NP] and writes gE_part[parts][D][NP].
+int fvx_tc_np(int de);
+int fvx_tc_ksplit(const FvxModel* m, long long nrows);
+int fvx_launch_split_E(const FvxModel* m, cudaStream_t st);
+int fvx_launch_split_planes(const float* src, uint16_t* dst, long long n_rows, int D, cudaStream_t st);
+int fvx_launch_project_tc(const FvxModel* m, const int32_t* rows, int row0, int64_t nrows, int ksplit, float* out,
+                          cudaStream_t st);
+int fvx_launch_reduce_partials(const float* part, long long nrows, int NP, int ks, int de, float* out,
+                               cudaStream_t st);
+int fvx_launch_split_W(const FvxModel* m, const float* W, const int32_t* rows, long long nrows, cudaStream_t st);
+int fvx_launch_reduce_gE(const FvxModel* m, int parts, int gnp, float* out, cudaStream_t st);
+int fvx_launch_grad_E_tc(const FvxModel* m, const int32_t* rows, int64_t nrows, int* parts_out, cudaStream_t st);
+
+int fvx_launch_score_grad(const FvxModel* m, const int32_t* user, int B, int loss_slot, int th_ks, cudaStream_t st);
 
 // x_ui for one (user row, item row, theta row): the single definition every scoring
 // kernel uses, so that a score compared with itself compares equal

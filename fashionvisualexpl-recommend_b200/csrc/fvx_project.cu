@@ -174,17 +174,6 @@ k_grad_E(const float* __restrict__ F, const int32_t* __restrict__ rows, long lon
   }
 }
 
-__global__ void k_split_bf16(const float* __restrict__ src, __nv_bfloat16* __restrict__ hi,
-                             __nv_bfloat16* __restrict__ lo, long long n) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-       i += (long long)gridDim.x * blockDim.x) {
-    const float f = src[i];
-    const __nv_bfloat16 h = __float2bfloat16_rn(f);
-    hi[i] = h;
-    lo[i] = __float2bfloat16_rn(f - __bfloat162float(h));
-  }
-}
-
 // ---------------------------------------------------------------------------------
 int fvx_launch_project(const FvxModel* m, const int32_t* rows, int64_t nrows, float* out, cudaStream_t st) {
   FVX_CHECK_ARG(m->D % 4 == 0, "projection: D=%d must be a multiple of 4", m->D);
@@ -221,21 +210,66 @@ int fvx_launch_grad_E(const FvxModel* m, const int32_t* rows, int64_t nrows, int
 
 extern "C" {
 
-int fvx_project(const FvxModel* model, float* theta_ext, fvx_stream_t stream) {
-  FVX_CHECK_ARG(model && model->abi_version == FVX_ABI_VERSION, "fvx_project: bad model");
-  FVX_CHECK_ARG(model->D > 0 && model->F && model->E, "fvx_project: model has no visual part");
-  return fvx_launch_project(model, nullptr, model->item_cnt, theta_ext, fvx_cu(stream));
+// rows == nullptr: catalog rows row0 .. row0+nrows.  TC path: blocks that fit the TH scratch.
+static int project_any(const FvxModel* m, const int32_t* rows, int row0, int64_t nrows, float* out, cudaStream_t st) {
+  if (!m->use_tensor_cores) {
+    FVX_CHECK_ARG(m->F != nullptr, "projection: the fp32 path needs F");
+    FVX_CHECK_ARG(rows != nullptr || row0 == 0, "projection: internal (row0)");
+    return fvx_launch_project(m, rows, nrows, out, st);
+  }
+  FVX_CHECK_ARG(m->TH && m->th_cap > 0, "projection: TH scratch missing");
+  if (int rc = fvx_launch_split_E(m, st)) return rc;
+  const int NP = fvx_tc_np(m->de);
+  const int64_t blk = m->th_cap / NP / 128 * 128;
+  FVX_CHECK_ARG(blk >= 128, "projection: TH scratch too small");
+  for (int64_t r0 = 0; r0 < nrows; r0 += blk) {
+    const int64_t n = nrows - r0 < blk ? nrows - r0 : blk;
+    int ks = fvx_tc_ksplit(m, n);
+    while (ks > 1 && (int64_t)ks * n * NP > m->th_cap) ks >>= 1;
+    if (int rc = fvx_launch_project_tc(m, rows ? rows + r0 : nullptr, row0 + (int)r0, n, ks, m->TH, st)) return rc;
+    if (int rc = fvx_launch_reduce_partials(m->TH, n, NP, ks, m->de, out + (size_t)r0 * m->de, st)) return rc;
+  }
+  return 0;
 }
 
-int fvx_split_bf16(const float* src, uint16_t* hi, uint16_t* lo, int64_t n, fvx_stream_t stream) {
-  FVX_CHECK_ARG(src && hi && lo, "fvx_split_bf16: null pointer");
-  if (n <= 0) return 0;
-  long long g = (n + 255) / 256;
-  if (g > (long long)fvx_num_sms() * 16) g = (long long)fvx_num_sms() * 16;
-  k_split_bf16<<<(int)g, 256, 0, fvx_cu(stream)>>>(src, reinterpret_cast<__nv_bfloat16*>(hi),
-                                                  reinterpret_cast<__nv_bfloat16*>(lo), n);
-  FVX_CHECK_LAUNCH("k_split_bf16");
-  return 0;
+int fvx_project(const FvxModel* model, float* theta_ext, fvx_stream_t stream) {
+  FVX_CHECK_ARG(model && model->abi_version == FVX_ABI_VERSION, "fvx_project: bad model");
+  FVX_CHECK_ARG(model->D > 0 && model->E && theta_ext, "fvx_project: model has no visual part");
+  return project_any(model, nullptr, 0, model->item_cnt, theta_ext, fvx_cu(stream));
+}
+
+int fvx_tc_width(int32_t de) { return fvx_tc_np(de); }
+
+int fvx_project_rows(const FvxModel* model, const int32_t* rows, int64_t nrows, float* out, fvx_stream_t stream) {
+  FVX_CHECK_ARG(model && model->abi_version == FVX_ABI_VERSION, "fvx_project_rows: bad model");
+  FVX_CHECK_ARG(model->D > 0 && model->E && rows && out, "fvx_project_rows: bad arguments");
+  FVX_CHECK_ARG(nrows >= 0 && nrows <= 2LL * model->max_batch, "fvx_project_rows: nrows outside [0, 2*max_batch]");
+  return project_any(model, rows, 0, nrows, out, fvx_cu(stream));
+}
+
+int fvx_grad_e_rows(const FvxModel* model, const int32_t* rows, int64_t nrows, const float* W, float* out,
+                    fvx_stream_t stream) {
+  FVX_CHECK_ARG(model && model->abi_version == FVX_ABI_VERSION, "fvx_grad_e_rows: bad model");
+  FVX_CHECK_ARG(model->D > 0 && rows && W && out && model->gE_part, "fvx_grad_e_rows: bad arguments");
+  FVX_CHECK_ARG(nrows >= 0 && nrows <= 2LL * model->max_batch, "fvx_grad_e_rows: nrows outside [0, 2*max_batch]");
+  cudaStream_t st = fvx_cu(stream);
+  int parts = 0;
+  if (model->use_tensor_cores) {
+    FVX_CHECK_ARG(model->W_hi && model->W_lo, "fvx_grad_e_rows: W planes missing");
+    if (int rc = fvx_launch_split_W(model, W, rows, nrows, st)) return rc;
+    if (int rc = fvx_launch_grad_E_tc(model, rows, nrows, &parts, st)) return rc;
+    return fvx_launch_reduce_gE(model, parts, fvx_tc_np(model->de), out, st);
+  }
+  FVX_CHECK_ARG(model->F != nullptr && model->W != nullptr, "fvx_grad_e_rows: the fp32 path needs F and W scratch");
+  if (cudaMemcpyAsync(model->W, W, sizeof(float) * nrows * model->de, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+    FVX_FAIL(-3, "fvx_grad_e_rows: copy failed");
+  if (int rc = fvx_launch_grad_E(model, rows, nrows, &parts, st)) return rc;
+  return fvx_launch_reduce_gE(model, parts, model->de, out, st);
+}
+
+int fvx_split_planes(const float* src, uint16_t* dst, int64_t n_rows, int32_t D, fvx_stream_t stream) {
+  FVX_CHECK_ARG(src && dst && D > 0, "fvx_split_planes: bad arguments");
+  return fvx_launch_split_planes(src, dst, n_rows, D, fvx_cu(stream));
 }
 
 }  // extern "C"

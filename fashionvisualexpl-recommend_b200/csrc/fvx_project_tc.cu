@@ -1,0 +1,578 @@
+// The VBPR visual projection and its gradient on the 5th-generation tensor cores
+// (tcgen05 + TMEM), fed by TMA row gathers (cp.async.bulk.tensor ... tile::gather4).
+//
+//   forward : TH[r,:]  = F[rows[r],:] * E_ext          (VBPR.py:83-84: matmul(feature_i, E / Bp))
+//   backward: gE_ext   = sum_r F[rows[r],:]^T * W[r,:]  (tape.gradient w.r.t. E, Bp; VBPR.py:141)
+//
+// fp32-faithful on bf16 tensor cores: F lives in HBM as two bf16 planes (hi = bf16(F),
+// lo = bf16(F - hi): 4 bytes per element like fp32, relative error ~2^-17) and the small
+// operand (E_ext or W) is split the same way; each product is issued as three MMAs
+// (hi*hi + lo*hi + hi*lo) accumulating in fp32 in TMEM.
+//
+// forward  (k_proj_fwd_tc): work unit = (128-row tile, K split).  A = gathered rows
+//   [128 x 64 features] per stage (K-major, 128B swizzle), B = E_ext^T [NP x 64] (K-major),
+//   D[128 x NP] in TMEM (double buffered).  The epilogue writes one fp32 partial per K
+//   split; the consumer sums them.
+// backward (k_grad_E_tc): CTA = (row group, 512-feature group).  The same gathered tile
+//   [32 rows x 64 features] x 8 is now read as the MN-major operand A = F^T (M = features),
+//   B = W tile [32 rows x NP] (MN-major), D[512 features x NP] stays in TMEM over all row
+//   tiles of the group and leaves once as a per-row-group partial of gE_ext.
+#include <cuda_bf16.h>
+
+#include "fvx_common.cuh"
+#include "fvx_kernels.cuh"
+#include "fvx_tc.cuh"
+
+#define PT_BM 128      // rows per forward tile (UMMA M)
+#define PT_KC 64       // features per shared-memory chunk: 128 bytes of bf16 = one 128B-swizzle span
+#define PT_PROD 128    // producer threads (warps 0-3, cp.async row gathers)
+#define PT_THREADS 288 // warps 0-3: producers, warp 4: UMMA issuer, warps 5-8: epilogue
+#define GE_RT 32       // rows per backward stage (2 UMMA K steps)
+#define GE_FG 512      // features per backward CTA (4 UMMA M blocks)
+
+// Feature planes in HBM ("F_pl"): per item row, per 64-feature chunk, 128 bytes of bf16 hi followed
+// by 128 bytes of bf16 lo: [item][D/64][2][64].  One (row, chunk) is 256 contiguous bytes, a whole
+// row 4*D bytes - the same footprint as fp32.  Rows are gathered with 16-byte cp.async (measured
+// on B200: 5.3-5.8 TB/s for random 4 KB rows; TMA tile::gather4 saturates at 1.67 TB/s and 1-D
+// bulk copies of <= 512 B at 1.9 TB/s - scripts/ubench/gather_bw.cu), each thread writing its
+// 16 bytes at the 128B-swizzled position the UMMA descriptors expect.
+__device__ __forceinline__ void pt_cp16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void pt_cp_arrive(uint64_t* bar) {   // arrives when this thread's copies have landed
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tc_smem_u32(bar)) : "memory");
+}
+
+struct ProjFwdParams {
+  const uint8_t* Fpl;   // interleaved planes
+  const int32_t* rows;  // nullptr: identity (catalog row row0 + r)
+  long long nrows;
+  int row0;
+  int D;
+  int NP;               // padded output width (multiple of 32)
+  int ksplit;           // K splits
+  int chunks;           // 64-feature chunks per split
+  int n_tiles;          // 128-row tiles
+  int stages;
+  float* out;           // [ksplit][nrows][NP]
+};
+
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(PT_THREADS, 1)
+k_proj_fwd_tc(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+              const ProjFwdParams P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (tc_smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t a_bytes = PT_BM * 128u;              // one plane of one stage
+  const uint32_t b_bytes = (uint32_t)P.NP * 128u;
+  const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)P.stages * stage_bytes);
+  uint64_t* full_b = bars;
+  uint64_t* empty_b = bars + P.stages;
+  uint64_t* t_full = bars + 2 * P.stages;   // [2]
+  uint64_t* t_empty = t_full + 2;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < P.stages; ++s) { mbar_init(&full_b[s], PT_PROD + 1); mbar_init(&empty_b[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 4); }
+    mbar_fence_init();
+    tma_prefetch_desc(&tmB_hi); tma_prefetch_desc(&tmB_lo);
+  }
+  uint32_t tcols = 32;
+  while (tcols < 2u * P.NP) tcols <<= 1;
+  if (warp == 4) tmem_alloc(tmem_slot, tcols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int n_units = P.n_tiles * P.ksplit;
+
+  if (warp < 4) {
+    // ===== producers: 16 lanes copy the 256 bytes (hi | lo) of one (row, chunk); a round of the
+    //       128 threads covers 8 rows, 16 rounds fill the stage =====
+    const int tid = threadIdx.x;
+    const int sub = tid >> 4;                 // row within a round
+    const int e = tid & 15;                   // 16-byte element of the 256 bytes
+    const int plane = e >> 3, c16 = e & 7;
+    const size_t row_bytes = (size_t)P.D * 4;
+    uint32_t stage = 0, phase = 0;
+    for (int w = blockIdx.x; w < n_units; w += gridDim.x) {
+      const int tile = w / P.ksplit, ks = w - tile * P.ksplit;
+      const uint8_t* src[16];
+#pragma unroll
+      for (int it = 0; it < 16; ++it) {
+        const long long r = (long long)tile * PT_BM + it * 8 + sub;
+        long long item = 0;
+        if (r < P.nrows) item = P.rows ? (long long)P.rows[r] : (long long)P.row0 + r;
+        if (item < 0) item = 0;               // slot of another rank's item: any valid row, result unused
+        src[it] = P.Fpl + (size_t)item * row_bytes + e * 16;
+      }
+      for (int c = 0; c < P.chunks; ++c) {
+        const int chunk = ks * P.chunks + c;
+        mbar_wait(&empty_b[stage], phase ^ 1);
+        const uint32_t sA = tc_smem_u32(smem + (size_t)stage * stage_bytes) + plane * a_bytes;
+#pragma unroll
+        for (int it = 0; it < 16; ++it) {
+          const int r = it * 8 + sub;
+          pt_cp16(sA + r * 128 + ((c16 ^ (r & 7)) << 4), src[it] + (size_t)chunk * 256);
+        }
+        pt_cp_arrive(&full_b[stage]);
+        if (tid == 0) {
+          uint8_t* sB_hi = smem + (size_t)stage * stage_bytes + 2 * a_bytes;
+          mbar_expect_tx(&full_b[stage], 2 * b_bytes);
+          tma_load_2d(sB_hi, &tmB_hi, &full_b[stage], chunk * PT_KC, 0);
+          tma_load_2d(sB_hi + b_bytes, &tmB_lo, &full_b[stage], chunk * PT_KC, 0);
+        }
+        if (++stage == (uint32_t)P.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 4) {
+    // ===== UMMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(PT_BM, P.NP, 0, 0);
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (int w = blockIdx.x; w < n_units; w += gridDim.x) {
+        mbar_wait(&t_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem_base + acc * P.NP;
+        for (int c = 0; c < P.chunks; ++c) {
+          mbar_wait(&full_b[stage], phase);
+          fence_proxy_async_smem();           // cp.async (generic proxy) writes -> UMMA (async proxy) reads
+          tc_fence_after();
+          const uint32_t a_hi = tc_smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint32_t a_lo = a_hi + a_bytes, b_hi = a_lo + a_bytes, b_lo = b_hi + b_bytes;
+#pragma unroll
+          for (int k = 0; k < PT_KC / 16; ++k) {
+            const uint64_t dah = umma_smem_desc(a_hi + k * 32, 16, 1024, TC_SWZ_128B);
+            const uint64_t dal = umma_smem_desc(a_lo + k * 32, 16, 1024, TC_SWZ_128B);
+            const uint64_t dbh = umma_smem_desc(b_hi + k * 32, 16, 1024, TC_SWZ_128B);
+            const uint64_t dbl = umma_smem_desc(b_lo + k * 32, 16, 1024, TC_SWZ_128B);
+            umma_f16(d, dah, dbh, idesc, (c | k) ? 1u : 0u);
+            umma_f16(d, dal, dbh, idesc, 1u);
+            umma_f16(d, dah, dbl, idesc, 1u);
+          }
+          umma_commit(&empty_b[stage]);
+          if (++stage == (uint32_t)P.stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&t_full[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===== epilogue: TMEM -> registers -> fp32 partial rows =====
+    const int quad = warp & 3;
+    uint32_t acc = 0, acc_phase = 0;
+    for (int w = blockIdx.x; w < n_units; w += gridDim.x) {
+      const int tile = w / P.ksplit, ks = w - tile * P.ksplit;
+      const long long row = (long long)tile * PT_BM + quad * 32 + lane;
+      mbar_wait(&t_full[acc], acc_phase);
+      tc_fence_after();
+      float* dst = P.out + ((size_t)ks * P.nrows + (size_t)(row < P.nrows ? row : 0)) * P.NP;
+      for (int n0 = 0; n0 < P.NP; n0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * P.NP + n0, v);
+        tmem_ld_wait();
+        if (row < P.nrows) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(dst + n0 + j) =
+                make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                            __uint_as_float(v[j + 3]));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&t_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tcols);
+  }
+}
+
+// ---------------------------------------------------------------------------------
+struct GradEParams {
+  const uint8_t* Fpl;
+  const int32_t* rows;
+  long long nrows;
+  int D, NP;
+  int fgs;              // features per CTA (multiple of 128)
+  int nfg;              // feature groups = D / fgs
+  int rows_per_group;   // multiple of GE_RT
+  int stages;
+  int w_atoms;          // 64-column sub-tiles of the W tile (1 for NP <= 64)
+  int w_sw;             // swizzle of the W tile: TC_SWZ_64B (NP == 32) or TC_SWZ_128B
+  float* out;           // [row groups][D][NP]
+};
+
+__global__ void __launch_bounds__(PT_THREADS, 1)
+k_grad_E_tc(const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
+            const GradEParams P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (tc_smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nchunk = P.fgs / PT_KC;                          // 64-feature chunks per stage
+  const uint32_t chunk_bytes = GE_RT * 128u;                 // [32 rows x 128 B]
+  const uint32_t a_bytes = (uint32_t)nchunk * chunk_bytes;   // one plane
+  const uint32_t wrow_bytes = P.NP <= 64 ? (uint32_t)P.NP * 2u : 128u;
+  const uint32_t watom_bytes = GE_RT * wrow_bytes;
+  const uint32_t w_bytes = (uint32_t)P.w_atoms * watom_bytes;  // one plane
+  const uint32_t stage_bytes = 2 * a_bytes + 2 * w_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)P.stages * stage_bytes);
+  uint64_t* full_b = bars;
+  uint64_t* empty_b = bars + P.stages;
+  uint64_t* t_full = bars + 2 * P.stages;   // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_full + 1);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < P.stages; ++s) { mbar_init(&full_b[s], PT_PROD + 1); mbar_init(&empty_b[s], 1); }
+    mbar_init(t_full, 1);
+    mbar_fence_init();
+    tma_prefetch_desc(&tmW_hi); tma_prefetch_desc(&tmW_lo);
+  }
+  const int nmb = P.fgs / 128;
+  uint32_t tcols = 32;
+  while (tcols < (uint32_t)(nmb * P.NP)) tcols <<= 1;
+  if (warp == 4) tmem_alloc(tmem_slot, tcols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int rg = blockIdx.x / P.nfg, fg = blockIdx.x - rg * P.nfg;
+  const long long r_begin = (long long)rg * P.rows_per_group;
+  long long r_end = r_begin + P.rows_per_group;
+  if (r_end > P.nrows) r_end = P.nrows;
+  const int n_tiles = r_end > r_begin ? (int)((r_end - r_begin + GE_RT - 1) / GE_RT) : 0;
+
+  if (warp < 4) {
+    // ===== producers: a warp copies the (fgs*4)-byte slice of one row per pass, 8 rows per stage =====
+    const int tid = threadIdx.x;
+    const size_t row_bytes = (size_t)P.D * 4;
+    const int per_row = P.fgs / 4;            // 16-byte elements of one row slice (both planes)
+    uint32_t stage = 0, phase = 0;
+    for (int t = 0; t < n_tiles; ++t) {
+      const long long r0 = r_begin + (long long)t * GE_RT;
+      const uint8_t* src[GE_RT / 4];
+#pragma unroll
+      for (int j = 0; j < GE_RT / 4; ++j) {
+        const long long r = r0 + j * 4 + warp;
+        long long item = 0;
+        if (r < P.nrows) item = P.rows ? (long long)P.rows[r] : r;
+        if (item < 0) item = 0;
+        src[j] = P.Fpl + (size_t)item * row_bytes + (size_t)fg * P.fgs * 4;
+      }
+      mbar_wait(&empty_b[stage], phase ^ 1);
+      const uint32_t sA = tc_smem_u32(smem + (size_t)stage * stage_bytes);
+      for (int e = lane; e < per_row; e += 32) {
+        const int c = e >> 4, plane = (e >> 3) & 1, c16 = e & 7;
+        const uint32_t doff = (uint32_t)plane * a_bytes + (uint32_t)c * chunk_bytes;
+#pragma unroll
+        for (int j = 0; j < GE_RT / 4; ++j) {
+          const int r = j * 4 + warp;
+          pt_cp16(sA + doff + r * 128 + ((c16 ^ (r & 7)) << 4), src[j] + (size_t)e * 16);
+        }
+      }
+      pt_cp_arrive(&full_b[stage]);
+      if (tid == 0) {
+        uint8_t* sW_hi = smem + (size_t)stage * stage_bytes + 2 * a_bytes;
+        mbar_expect_tx(&full_b[stage], 2 * w_bytes);
+        for (int a = 0; a < P.w_atoms; ++a) {
+          tma_load_2d(sW_hi + (size_t)a * watom_bytes, &tmW_hi, &full_b[stage], a * 64, (int)r0);
+          tma_load_2d(sW_hi + w_bytes + (size_t)a * watom_bytes, &tmW_lo, &full_b[stage], a * 64, (int)r0);
+        }
+      }
+      if (++stage == (uint32_t)P.stages) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 4) {
+    // ===== UMMA issuer: D[mb][128 features x NP] += F^T[128 x 16 rows] * W[16 rows x NP] =====
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, P.NP, 1, 1);
+      const uint32_t w_sbo = 8u * wrow_bytes;
+      uint32_t stage = 0, phase = 0;
+      for (int t = 0; t < n_tiles; ++t) {
+        mbar_wait(&full_b[stage], phase);
+        fence_proxy_async_smem();
+        tc_fence_after();
+        const uint32_t a_hi = tc_smem_u32(smem + (size_t)stage * stage_bytes);
+        const uint32_t a_lo = a_hi + a_bytes, w_hi = a_lo + a_bytes, w_lo = w_hi + w_bytes;
+        for (int mb = 0; mb < nmb; ++mb) {
+          const uint32_t d = tmem_base + mb * P.NP;
+#pragma unroll
+          for (int k = 0; k < GE_RT / 16; ++k) {
+            const uint32_t aoff = (uint32_t)(2 * mb) * chunk_bytes + k * 16 * 128;
+            const uint64_t dah = umma_smem_desc(a_hi + aoff, chunk_bytes, 1024, TC_SWZ_128B);
+            const uint64_t dal = umma_smem_desc(a_lo + aoff, chunk_bytes, 1024, TC_SWZ_128B);
+            const uint64_t dwh = umma_smem_desc(w_hi + k * 16 * wrow_bytes, watom_bytes, w_sbo, P.w_sw);
+            const uint64_t dwl = umma_smem_desc(w_lo + k * 16 * wrow_bytes, watom_bytes, w_sbo, P.w_sw);
+            umma_f16(d, dah, dwh, idesc, (t | k) ? 1u : 0u);
+            umma_f16(d, dal, dwh, idesc, 1u);
+            umma_f16(d, dah, dwl, idesc, 1u);
+          }
+        }
+        umma_commit(&empty_b[stage]);
+        if (++stage == (uint32_t)P.stages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(t_full);
+    }
+  } else {
+    // ===== epilogue: the CTA's partial of gE_ext =====
+    const int quad = warp & 3;
+    if (n_tiles > 0) {
+      mbar_wait(t_full, 0);
+      tc_fence_after();
+    }
+    for (int mb = 0; mb < nmb; ++mb) {
+      const int f = fg * P.fgs + mb * 128 + quad * 32 + lane;
+      float* dst = P.out + ((size_t)rg * P.D + f) * P.NP;
+      for (int n0 = 0; n0 < P.NP; n0 += 32) {
+        uint32_t v[32];
+        if (n_tiles > 0) {
+          tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + mb * P.NP + n0, v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(dst + n0 + j) =
+              make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                          __uint_as_float(v[j + 3]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tcols);
+  }
+}
+
+// fp32 rows [n, D] -> interleaved bf16 planes [n][D/64][2][64]
+__global__ void k_split_planes(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n_rows, int D) {
+  const long long total = n_rows * D;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / D;
+    const int f = (int)(i - r * D);
+    const float x = src[i];
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    const size_t o = (size_t)r * 2 * D + (size_t)(f >> 6) * 128 + (f & 63);
+    dst[o] = h;
+    dst[o + 64] = __float2bfloat16_rn(x - __bfloat162float(h));
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// E_ext [D, de] fp32 -> ET_hi / ET_lo [NP, D] bf16 (row n = column n of E_ext, rows >= de zero)
+__global__ void k_split_E(const float* __restrict__ E, int D, int de, int NP, __nv_bfloat16* __restrict__ hi,
+                          __nv_bfloat16* __restrict__ lo) {
+  const int total = NP * D;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int n = i / D, f = i - n * D;
+    const float x = n < de ? E[(size_t)f * de + n] : 0.0f;
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    hi[i] = h;
+    lo[i] = __float2bfloat16_rn(x - __bfloat162float(h));
+  }
+}
+
+// ---------------------------------------------------------------------------------
+int fvx_tc_np(int de) { return de <= 32 ? 32 : (de + 63) / 64 * 64; }
+
+int fvx_tc_ksplit(const FvxModel* m, long long nrows) {
+  const long long tiles = (nrows + PT_BM - 1) / PT_BM;
+  const int chunks = m->D / PT_KC;
+  int ks = 1;
+  // aim at >= 6 work units per SM so that the last wave is short; a split keeps >= 4 chunks
+  while (tiles * ks < 6LL * fvx_num_sms() && ks * 2 <= chunks / 4 && chunks % (ks * 2) == 0) ks *= 2;
+  return ks;
+}
+
+static int set_smem(const void* fn, size_t bytes, const char* who) {
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) FVX_FAIL(-3, "%s: cannot set %zu B of shared memory: %s", who, bytes, cudaGetErrorString(e));
+  return 0;
+}
+
+int fvx_launch_split_E(const FvxModel* m, cudaStream_t st) {
+  FVX_CHECK_ARG(m->ET_hi && m->ET_lo, "tensor-core projection: ET planes missing");
+  const int NP = fvx_tc_np(m->de);
+  k_split_E<<<(NP * m->D + 255) / 256, 256, 0, st>>>(m->E, m->D, m->de, NP, reinterpret_cast<__nv_bfloat16*>(m->ET_hi),
+                                                     reinterpret_cast<__nv_bfloat16*>(m->ET_lo));
+  FVX_CHECK_LAUNCH("k_split_E");
+  return 0;
+}
+
+// out: [ksplit][nrows][NP] fp32 partials (ksplit from fvx_tc_ksplit)
+int fvx_launch_project_tc(const FvxModel* m, const int32_t* rows, int row0, int64_t nrows, int ksplit, float* out,
+                          cudaStream_t st) {
+  FVX_CHECK_ARG(m->F_pl && m->ET_hi && m->ET_lo, "tensor-core projection: bf16 planes missing");
+  FVX_CHECK_ARG(m->D % PT_KC == 0, "tensor-core projection: D=%d must be a multiple of %d", m->D, PT_KC);
+  const int NP = fvx_tc_np(m->de);
+  FVX_CHECK_ARG(NP <= 256, "tensor-core projection: d+1=%d too wide", m->de);
+  if (nrows <= 0) return 0;
+  const int chunks_total = m->D / PT_KC;
+  FVX_CHECK_ARG(ksplit >= 1 && chunks_total % ksplit == 0, "tensor-core projection: bad K split %d", ksplit);
+  CUtensorMap b_hi, b_lo;
+  int rc = 0;
+  const uint64_t pitch = (uint64_t)m->D * 2;
+  rc |= tc_make_tensor_map_bf16(&b_hi, m->ET_hi, NP, m->D, pitch, PT_KC, NP, 3);
+  rc |= tc_make_tensor_map_bf16(&b_lo, m->ET_lo, NP, m->D, pitch, PT_KC, NP, 3);
+  if (rc != 0) FVX_FAIL(-4, "tensor-core projection: cuTensorMapEncodeTiled failed");
+  ProjFwdParams P;
+  P.Fpl = reinterpret_cast<const uint8_t*>(m->F_pl); P.D = m->D;
+  P.rows = rows; P.row0 = row0; P.nrows = nrows; P.NP = NP; P.ksplit = ksplit; P.chunks = chunks_total / ksplit;
+  P.n_tiles = (int)((nrows + PT_BM - 1) / PT_BM);
+  P.out = out;
+  const size_t stage_bytes = 2 * PT_BM * 128 + 2 * (size_t)NP * 128;
+  int stages = (int)((220 * 1024) / stage_bytes);
+  if (stages > 6) stages = 6;
+  FVX_CHECK_ARG(stages >= 2, "tensor-core projection: tile does not fit shared memory");
+  P.stages = stages;
+  const size_t smem = stages * stage_bytes + (2 * stages + 4) * 8 + 16 + 1024;
+  static size_t configured = 0;
+  if (smem > configured) {
+    if (int r = set_smem((const void*)k_proj_fwd_tc, smem, "k_proj_fwd_tc")) return r;
+    configured = smem;
+  }
+  long long grid = (long long)P.n_tiles * ksplit;
+  if (grid > fvx_num_sms()) grid = fvx_num_sms();
+  k_proj_fwd_tc<<<(int)grid, PT_THREADS, smem, st>>>(b_hi, b_lo, P);
+  FVX_CHECK_LAUNCH("k_proj_fwd_tc");
+  return 0;
+}
+
+// gE_part[p][D][NP] = partial sums; W planes [nrows][NP] bf16.  *parts_out = row groups written.
+int fvx_launch_grad_E_tc(const FvxModel* m, const int32_t* rows, int64_t nrows, int* parts_out, cudaStream_t st) {
+  FVX_CHECK_ARG(m->F_pl && m->W_hi && m->W_lo && m->gE_part, "tensor-core grad_E: buffers missing");
+  FVX_CHECK_ARG(m->D % 128 == 0, "tensor-core grad_E: D=%d must be a multiple of 128", m->D);
+  const int NP = fvx_tc_np(m->de);
+  int fgs = GE_FG;
+  while (fgs > 128 && (m->D % fgs != 0 || (fgs / 128) * NP > 512)) fgs >>= 1;
+  FVX_CHECK_ARG(m->D % fgs == 0 && (fgs / 128) * NP <= 512, "tensor-core grad_E: d+1=%d too wide", m->de);
+  const int nfg = m->D / fgs;
+  int max_rg = fvx_num_sms() / nfg;
+  if (max_rg < 1) max_rg = 1;
+  if (max_rg > m->ge_parts) max_rg = m->ge_parts;
+  long long rpg = (nrows + max_rg - 1) / max_rg;
+  rpg = (rpg + GE_RT - 1) / GE_RT * GE_RT;
+  if (rpg < GE_RT) rpg = GE_RT;
+  const int parts = nrows > 0 ? (int)((nrows + rpg - 1) / rpg) : 0;
+  *parts_out = parts;
+  if (parts == 0) return 0;
+  CUtensorMap w_hi, w_lo;
+  int rc = 0;
+  const int wbox = NP <= 64 ? NP : 64;
+  const int wsw = NP == 32 ? 2 : 3;
+  rc |= tc_make_tensor_map_bf16(&w_hi, m->W_hi, nrows, NP, (uint64_t)NP * 2, wbox, GE_RT, wsw);
+  rc |= tc_make_tensor_map_bf16(&w_lo, m->W_lo, nrows, NP, (uint64_t)NP * 2, wbox, GE_RT, wsw);
+  if (rc != 0) FVX_FAIL(-4, "tensor-core grad_E: cuTensorMapEncodeTiled failed");
+  GradEParams P;
+  P.Fpl = reinterpret_cast<const uint8_t*>(m->F_pl);
+  P.rows = rows; P.nrows = nrows; P.D = m->D; P.NP = NP; P.fgs = fgs; P.nfg = nfg; P.rows_per_group = (int)rpg;
+  P.w_atoms = NP <= 64 ? 1 : NP / 64;
+  P.w_sw = NP == 32 ? TC_SWZ_64B : TC_SWZ_128B;
+  P.out = m->gE_part;
+  const size_t wrow = NP <= 64 ? (size_t)NP * 2 : 128;
+  const size_t stage_bytes = 2 * (size_t)(fgs / PT_KC) * GE_RT * 128 + 2 * (size_t)P.w_atoms * GE_RT * wrow;
+  int stages = (int)((220 * 1024) / stage_bytes);
+  if (stages > 4) stages = 4;
+  FVX_CHECK_ARG(stages >= 2, "tensor-core grad_E: tile does not fit shared memory");
+  P.stages = stages;
+  const size_t smem = stages * stage_bytes + (2 * stages + 1) * 8 + 16 + 1024;
+  static size_t configured = 0;
+  if (smem > configured) {
+    if (int r = set_smem((const void*)k_grad_E_tc, smem, "k_grad_E_tc")) return r;
+    configured = smem;
+  }
+  k_grad_E_tc<<<parts * nfg, PT_THREADS, smem, st>>>(w_hi, w_lo, P);
+  FVX_CHECK_LAUNCH("k_grad_E_tc");
+  return 0;
+}
+
+// out[r, 0:de] = sum over the K-split partials part[s][r][0:de]
+__global__ void k_reduce_partials(const float* __restrict__ part, long long nrows, int NP, int ks, int de,
+                                  float* __restrict__ out) {
+  const long long total = nrows * de;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / de;
+    const int c = (int)(i - r * de);
+    float v = 0.0f;
+    for (int s = 0; s < ks; ++s) v += part[((size_t)s * nrows + r) * NP + c];
+    out[i] = v;
+  }
+}
+
+int fvx_launch_reduce_partials(const float* part, long long nrows, int NP, int ks, int de, float* out,
+                               cudaStream_t st) {
+  if (nrows <= 0) return 0;
+  long long g = (nrows * de + 255) / 256;
+  if (g > (long long)fvx_num_sms() * 8) g = (long long)fvx_num_sms() * 8;
+  k_reduce_partials<<<(int)g, 256, 0, st>>>(part, nrows, NP, ks, de, out);
+  FVX_CHECK_LAUNCH("k_reduce_partials");
+  return 0;
+}
+
+// W fp32 [nrows, de] -> bf16 planes [nrows, NP] (rows with rows[r] < 0 and columns >= de: zero)
+__global__ void k_split_W(const float* __restrict__ W, const int32_t* __restrict__ rows, long long nrows, int de,
+                          int NP, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  const long long total = nrows * NP;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / NP;
+    const int c = (int)(i - r * NP);
+    float x = 0.0f;
+    if (c < de && (rows == nullptr || rows[r] >= 0)) x = W[r * de + c];
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    hi[i] = h;
+    lo[i] = __float2bfloat16_rn(x - __bfloat162float(h));
+  }
+}
+
+int fvx_launch_split_W(const FvxModel* m, const float* W, const int32_t* rows, long long nrows, cudaStream_t st) {
+  if (nrows <= 0) return 0;
+  const int NP = fvx_tc_np(m->de);
+  long long g = (nrows * NP + 255) / 256;
+  if (g > (long long)fvx_num_sms() * 8) g = (long long)fvx_num_sms() * 8;
+  k_split_W<<<(int)g, 256, 0, st>>>(W, rows, nrows, m->de, NP, reinterpret_cast<__nv_bfloat16*>(m->W_hi),
+                                    reinterpret_cast<__nv_bfloat16*>(m->W_lo));
+  FVX_CHECK_LAUNCH("k_split_W");
+  return 0;
+}
+
+// out[D, de] = sum over the row-group partials gE_part[p][D][gnp]
+__global__ void k_reduce_gE(const float* __restrict__ part, int parts, int D, int gnp, int de, float* __restrict__ out) {
+  const int n = D * de;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int f = i / de, c = i - f * de;
+    float g = 0.0f;
+    for (int p = 0; p < parts; ++p) g += part[((size_t)p * D + f) * gnp + c];
+    out[i] = g;
+  }
+}
+
+int fvx_launch_reduce_gE(const FvxModel* m, int parts, int gnp, float* out, cudaStream_t st) {
+  k_reduce_gE<<<(m->D * m->de + 255) / 256, 256, 0, st>>>(m->gE_part, parts, m->D, gnp, m->de, out);
+  FVX_CHECK_LAUNCH("k_reduce_gE");
+  return 0;
+}
+
+int fvx_launch_split_planes(const float* src, uint16_t* dst, long long n_rows, int D, cudaStream_t st) {
+  FVX_CHECK_ARG(D % PT_KC == 0, "feature planes: D=%d must be a multiple of %d", D, PT_KC);
+  if (n_rows <= 0) return 0;
+  long long g = (n_rows * D + 255) / 256;
+  if (g > (long long)fvx_num_sms() * 16) g = (long long)fvx_num_sms() * 16;
+  k_split_planes<<<(int)g, 256, 0, st>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), n_rows, D);
+  FVX_CHECK_LAUNCH("k_split_planes");
+  return 0;
+}

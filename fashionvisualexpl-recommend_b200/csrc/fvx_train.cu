@@ -11,6 +11,8 @@
 //   k_adam_rows x2 / k_adam_sweep x2   Adam on touched rows / on whole tables (DENSE)
 //   k_adam_E      dense Adam on E_ext (+ its L2 term)       (VBPR only)
 //   k_finish      step += 1, reset lists
+#include <cuda_bf16.h>
+
 #include "fvx_common.cuh"
 #include "fvx_kernels.cuh"
 
@@ -106,8 +108,21 @@ __global__ void k_catchup_all(FvxTable T, const int64_t* __restrict__ step, floa
 #define SG_TPW 8
 #define SG_WARPS 8
 
+// TH layout: row stride th_np, th_ks K-split partials th_ss floats apart (summed here).
+struct SgTheta {
+  const float* p;
+  int np, ks;
+  long long ss;
+  __device__ __forceinline__ float at(long long slot, int n) const {
+    const float* q = p + slot * np + n;
+    float v = q[0];
+    for (int s = 1; s < ks; ++s) v += q[s * ss];
+    return v;
+  }
+};
+
 __global__ void __launch_bounds__(SG_WARPS * 32)
-k_score_grad(FvxModel M, const int32_t* __restrict__ user, int B, int loss_slot) {
+k_score_grad(FvxModel M, const int32_t* __restrict__ user, int B, int loss_slot, SgTheta T, int wnp) {
   extern __shared__ float sg_smem[];
   const int Su = M.users.stride, Si = M.items.stride, K = M.K, d = M.d, de = M.de;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -135,7 +150,20 @@ k_score_grad(FvxModel M, const int32_t* __restrict__ user, int B, int loss_slot)
         __syncwarp();
       }
       const int32_t li = M.rows[b], lj = M.rows[B + b];
-      if (li < 0 || lj < 0) continue;  // item id outside the catalog: triple ignored
+      if (li < 0 || lj < 0) {  // item id outside the catalog: triple ignored (no gradient to E either)
+        if (vis && wnp > 0) {
+          for (int n = lane; n < wnp; n += 32) {
+            const __nv_bfloat16 z = __float2bfloat16_rn(0.0f);
+            reinterpret_cast<__nv_bfloat16*>(M.W_hi)[(size_t)b * wnp + n] = z;
+            reinterpret_cast<__nv_bfloat16*>(M.W_lo)[(size_t)b * wnp + n] = z;
+            reinterpret_cast<__nv_bfloat16*>(M.W_hi)[(size_t)(B + b) * wnp + n] = z;
+            reinterpret_cast<__nv_bfloat16*>(M.W_lo)[(size_t)(B + b) * wnp + n] = z;
+          }
+        } else if (vis) {
+          for (int n = lane; n < de; n += 32) { M.W[(size_t)b * de + n] = 0.0f; M.W[(size_t)(B + b) * de + n] = 0.0f; }
+        }
+        continue;
+      }
       const float* gi = M.items.w + (size_t)li * Si;
       const float* gj = M.items.w + (size_t)lj * Si;
       float part = 0.0f, sq = 0.0f;
@@ -146,15 +174,16 @@ k_score_grad(FvxModel M, const int32_t* __restrict__ user, int B, int loss_slot)
       }
       const float bi = gi[K], bj = gj[K];
       float vb = 0.0f;
-      const float* thi = vis ? M.TH + (size_t)b * de : nullptr;
-      const float* thj = vis ? M.TH + (size_t)(B + b) * de : nullptr;
+      float dth0 = 0.0f;   // (theta_i - theta_j)[lane]; further columns are re-read below when d > 32
       if (vis) {
         for (int n = lane; n < d; n += 32) {
           const float a = urow[K + n];
-          part = fmaf(a, thi[n] - thj[n], part);
+          const float dt = T.at(b, n) - T.at(B + b, n);
+          if (n < 32) dth0 = dt;
+          part = fmaf(a, dt, part);
           sq += a * a;
         }
-        vb = thi[d] - thj[d];
+        vb = T.at(b, d) - T.at(B + b, d);
       }
       const float x = fvx_warp_sum(part) + (bi - bj) + vb;
       const float sqs = fvx_warp_sum(sq);
@@ -177,19 +206,30 @@ k_score_grad(FvxModel M, const int32_t* __restrict__ user, int B, int loss_slot)
         fvx_red_add(ggj + K, -coef + (reg2 / 10.0f) * bj);
       }
       if (vis) {
-        float* wi = M.W + (size_t)b * de;
-        float* wj = M.W + (size_t)(B + b) * de;
-        for (int n = lane; n < de; n += 32) {
+        const int nw = wnp > 0 ? wnp : de;
+        for (int n = lane; n < nw; n += 32) {
           float wv = 0.0f;
           if (n < d) {
             const float a = urow[K + n];
-            uacc[K + n] += coef * (thi[n] - thj[n]) + reg2 * a;
+            const float dt = n < 32 ? dth0 : T.at(b, n) - T.at(B + b, n);
+            uacc[K + n] += coef * dt + reg2 * a;
             wv = coef * a;
           } else if (n == d) {
             wv = coef;
           }
-          wi[n] = wv;
-          wj[n] = -wv;
+          if (wnp > 0) {   // bf16 hi/lo planes for the tensor-core backward
+            const __nv_bfloat16 h = __float2bfloat16_rn(wv);
+            const __nv_bfloat16 l = __float2bfloat16_rn(wv - __bfloat162float(h));
+            __nv_bfloat16* wh = reinterpret_cast<__nv_bfloat16*>(M.W_hi);
+            __nv_bfloat16* wl = reinterpret_cast<__nv_bfloat16*>(M.W_lo);
+            wh[(size_t)b * wnp + n] = h;
+            wl[(size_t)b * wnp + n] = l;
+            wh[(size_t)(B + b) * wnp + n] = __hneg(h);
+            wl[(size_t)(B + b) * wnp + n] = __hneg(l);
+          } else {
+            M.W[(size_t)b * de + n] = wv;
+            M.W[(size_t)(B + b) * de + n] = -wv;
+          }
         }
       }
       __syncwarp();
@@ -253,7 +293,8 @@ __global__ void k_adam_sweep(FvxTable T, const int64_t* __restrict__ step, float
 
 // Dense Adam on E_ext [D,de]: gradient = sum of the per-group partials + 2*reg*E
 // (VBPR.py:129 puts reg*(|E|^2+|Bp|^2) into the loss); adds that loss term as well.
-__global__ void k_adam_E(FvxModel M, int parts, int loss_slot, const float* __restrict__ extra_grad) {
+// gE_part rows have stride gnp floats (de on the fp32 path, NP on the tensor-core path).
+__global__ void k_adam_E(FvxModel M, int parts, int loss_slot, const float* __restrict__ extra_grad, int gnp) {
   const long long t = *M.step + 1;
   const float a = fvx_alpha(M.lr, t);
   const int n = M.D * M.de;
@@ -261,7 +302,8 @@ __global__ void k_adam_E(FvxModel M, int parts, int loss_slot, const float* __re
   float sq = 0.0f;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     float g = extra_grad ? extra_grad[i] : 0.0f;
-    for (int p = 0; p < parts; ++p) g += M.gE_part[(size_t)p * n + i];
+    const int f = i / M.de, c = i - f * M.de;
+    for (int p = 0; p < parts; ++p) g += M.gE_part[((size_t)p * M.D + f) * gnp + c];
     const float e = M.E[i];
     sq += e * e;
     g += 2.0f * reg * e;
@@ -295,7 +337,7 @@ static int check_model(const FvxModel* m, const char* who) {
   FVX_CHECK_ARG(m->users.w && m->items.w && m->step, "%s: null table pointer", who);
   if (m->D > 0) {
     FVX_CHECK_ARG(m->d > 0 && m->de % 4 == 0 && m->de >= m->d + 1, "%s: bad de", who);
-    FVX_CHECK_ARG(m->E && m->F, "%s: VBPR needs E and F", who);
+    FVX_CHECK_ARG(m->E && (m->F || (m->use_tensor_cores && m->F_pl)), "%s: VBPR needs E and F", who);
   }
   return 0;
 }
@@ -307,14 +349,20 @@ static inline int warp_grid(long long rows, int block = 256, int per_sm = 8) {
   return g < 1 ? 1 : (int)g;
 }
 
-int fvx_launch_score_grad(const FvxModel* m, const int32_t* user, int B, int loss_slot, cudaStream_t st) {
+int fvx_launch_score_grad(const FvxModel* m, const int32_t* user, int B, int loss_slot, int th_ks, cudaStream_t st) {
   const size_t smem = (size_t)SG_WARPS * 2 * m->users.stride * sizeof(float);
   FVX_CHECK_ARG(smem <= 48 * 1024, "fvx_bpr_step: K+d too large for the score kernel (%zu B smem)", smem);
   long long groups = ((long long)B + SG_TPW - 1) / SG_TPW;
   long long g = (groups + SG_WARPS - 1) / SG_WARPS;
   long long cap = (long long)fvx_num_sms() * 8;
   if (g > cap) g = cap;
-  k_score_grad<<<(int)g, SG_WARPS * 32, smem, st>>>(*m, user, B, loss_slot);
+  SgTheta T;
+  T.p = m->TH;
+  const bool tc = m->D > 0 && m->use_tensor_cores;
+  T.np = tc ? fvx_tc_np(m->de) : m->de;
+  T.ks = tc ? th_ks : 1;
+  T.ss = 2LL * B * T.np;
+  k_score_grad<<<(int)g, SG_WARPS * 32, smem, st>>>(*m, user, B, loss_slot, T, tc ? T.np : 0);
   FVX_CHECK_LAUNCH("k_score_grad");
   return 0;
 }
@@ -334,7 +382,19 @@ static int bpr_step_impl(const FvxModel* model, const int32_t* user, const int32
   FVX_CHECK_ARG(M.users.list_cap >= B && M.items.list_cap >= 2 * B, "fvx_bpr_step: touched-row lists too small");
   FVX_CHECK_ARG(M.rows != nullptr && M.loss != nullptr, "fvx_bpr_step: null scratch");
   const bool vis = M.D > 0;
-  if (vis) FVX_CHECK_ARG(M.TH && M.W && M.gE_part && M.ge_parts > 0, "fvx_bpr_step: VBPR scratch missing");
+  const bool tc = vis && M.use_tensor_cores;
+  int th_ks = 1;
+  if (vis) FVX_CHECK_ARG(M.TH && M.gE_part && M.ge_parts > 0 && (tc || M.W), "fvx_bpr_step: VBPR scratch missing");
+  if (tc) {
+    FVX_CHECK_ARG(M.F_pl && M.ET_hi && M.ET_lo && M.W_hi && M.W_lo,
+                  "fvx_bpr_step: use_tensor_cores=1 needs the bf16 planes (F_pl, ET_*, W_*)");
+    th_ks = fvx_tc_ksplit(&M, 2LL * B);
+    while (th_ks > 1 && (long long)th_ks * 2 * B * fvx_tc_np(M.de) > M.th_cap) th_ks >>= 1;
+    FVX_CHECK_ARG((long long)th_ks * 2 * B * fvx_tc_np(M.de) <= M.th_cap, "fvx_bpr_step: TH scratch too small");
+  } else if (vis) {
+    FVX_CHECK_ARG(M.F != nullptr, "fvx_bpr_step: fp32 projection needs F");
+    FVX_CHECK_ARG(2LL * B * M.de <= M.th_cap, "fvx_bpr_step: TH scratch too small");
+  }
 #define PHASE(i) do { if (ev) cudaEventRecord(ev[i], st); } while (0)
 
   PHASE(PH_MARK);
@@ -347,14 +407,19 @@ static int bpr_step_impl(const FvxModel* model, const int32_t* user, const int32
     FVX_CHECK_LAUNCH("k_catchup_list");
   }
   PHASE(PH_PROJECT);
-  if (vis) {
+  if (tc) {
+    if (int rc = fvx_launch_split_E(&M, st)) return rc;
+    if (int rc = fvx_launch_project_tc(&M, M.rows, 0, 2 * B, th_ks, M.TH, st)) return rc;
+  } else if (vis) {
     if (int rc = fvx_launch_project(&M, M.rows, 2 * B, M.TH, st)) return rc;
   }
   PHASE(PH_SCORE_GRAD);
-  if (int rc = fvx_launch_score_grad(&M, user, B, loss_slot, st)) return rc;
+  if (int rc = fvx_launch_score_grad(&M, user, B, loss_slot, th_ks, st)) return rc;
   PHASE(PH_GRAD_E);
   int parts = 0;
-  if (vis) {
+  if (tc) {
+    if (int rc = fvx_launch_grad_E_tc(&M, M.rows, 2 * B, &parts, st)) return rc;
+  } else if (vis) {
     if (int rc = fvx_launch_grad_E(&M, M.rows, 2 * B, &parts, st)) return rc;
   }
   PHASE(PH_ADAM_ROWS);
@@ -372,7 +437,7 @@ static int bpr_step_impl(const FvxModel* model, const int32_t* user, const int32
     const int n = M.D * M.de;
     int g = (n + 255) / 256;
     if (g > fvx_num_sms() * 4) g = fvx_num_sms() * 4;
-    k_adam_E<<<g, 256, 0, st>>>(M, parts, loss_slot, nullptr);
+    k_adam_E<<<g, 256, 0, st>>>(M, parts, loss_slot, nullptr, tc ? fvx_tc_np(M.de) : M.de);
     FVX_CHECK_LAUNCH("k_adam_E");
   }
   PHASE(PH_FINISH);

@@ -63,18 +63,33 @@ class Engine:
         self.step_t = torch.zeros(1, dtype=torch.int64, device=dev)
         self.loss_t = torch.zeros(self.loss_slots, dtype=torch.float64, device=dev)
         self.rows_t = torch.zeros(2 * self.max_batch, **i32)
-        self.F = self.F_hi = self.F_lo = None
+        self.F = self.F_pl = None
+        self.ET_hi = self.ET_lo = self.W_hi = self.W_lo = None
+        self.use_tensor_cores = bool(use_tensor_cores) and self.D > 0
         if self.D:
             self.E = torch.zeros(self.D, self.de, **f32)
             self.mE, self.vE = torch.zeros_like(self.E), torch.zeros_like(self.E)
             self.ge_parts = int(ge_parts)
-            self.gE_part = torch.zeros(self.ge_parts, self.D, self.de, **f32)
-            self.TH = torch.zeros(2 * self.max_batch, self.de, **f32)
-            self.W = torch.zeros(2 * self.max_batch, self.de, **f32)
+            self.NP = self.de
+            if self.use_tensor_cores:
+                # padded operand width of the tcgen05 kernels (fvx_tc_width) and up to 8 K-split partials
+                self.NP = self.de if self.de <= 0 else (32 if self.de <= 32 else (self.de + 63) // 64 * 64)
+                u16 = dict(dtype=torch.uint16, device=dev)
+                self.ET_hi = torch.zeros(self.NP, self.D, **u16)
+                self.ET_lo = torch.zeros(self.NP, self.D, **u16)
+                self.W_hi = torch.zeros(2 * self.max_batch, self.NP, **u16)
+                self.W_lo = torch.zeros(2 * self.max_batch, self.NP, **u16)
+                self.ge_parts = max(self.ge_parts, 148)
+                th_rows = max(4 * 2 * self.max_batch, 1 << 17)
+                self.TH = torch.zeros(th_rows, self.NP, **f32)
+                self.W = None
+            else:
+                self.TH = torch.zeros(2 * self.max_batch, self.de, **f32)
+                self.W = torch.zeros(2 * self.max_batch, self.de, **f32)
+            self.gE_part = torch.zeros(self.ge_parts, self.D, self.NP, **f32)
         else:
             self.E = self.mE = self.vE = self.gE_part = self.TH = self.W = None
             self.ge_parts = 0
-        self.use_tensor_cores = bool(use_tensor_cores)
         self._theta = None
         self._theta_step = -1
         self.init_glorot(seed)
@@ -138,16 +153,19 @@ class Engine:
             out.update({"Tu": self.Tu, "E": self.Ew, "Bp": self.Bp})
         return {k: v.detach().cpu().numpy().copy() for k, v in out.items()}
 
-    def set_features(self, F):
+    def set_features(self, F, keep_fp32=True):
         """F: [Ic, D] (owned rows) already normalised by the global max|F|."""
         F = torch.as_tensor(np.asarray(F) if not torch.is_tensor(F) else F)
         if tuple(F.shape) != (self.Ic, self.D):
             raise ValueError("features must be [%d, %d], got %s" % (self.Ic, self.D, tuple(F.shape)))
         self.F = F.to(self.device, dtype=torch.float32).contiguous()
         if self.use_tensor_cores:
-            self.F_hi = torch.empty(self.Ic, self.D, dtype=torch.uint16, device=self.device)
-            self.F_lo = torch.empty_like(self.F_hi)
-            call("fvx_split_bf16", ptr(self.F), ptr(self.F_hi), ptr(self.F_lo), self.F.numel(), stream_ptr())
+            # two bf16 planes (hi, lo): the same 4 bytes per element as fp32, ~2^-17 relative
+            self.F_pl = torch.empty(self.Ic, 2 * self.D, dtype=torch.uint16, device=self.device)
+            call("fvx_split_planes", ptr(self.F), ptr(self.F_pl), self.Ic, self.D, stream_ptr())
+            if not keep_fp32:
+                torch.cuda.current_stream().synchronize()
+                self.F = None
         self._struct = None
         self._theta_step = -1
 
@@ -158,7 +176,7 @@ class Engine:
 
     def struct(self):
         if self._struct is None:
-            if self.D and self.F is None:
+            if self.D and self.F is None and self.F_pl is None:
                 raise _lib.FvxError("VBPR engine: set_features() must be called before use")
             m = FvxModel()
             m.abi_version = _lib.ABI_VERSION
@@ -169,9 +187,11 @@ class Engine:
             m.items = self._table_struct(self.items, self.Ic, self.Si)
             m.E, m.mE, m.vE, m.gE_part = ptr(self.E), ptr(self.mE), ptr(self.vE), ptr(self.gE_part)
             m.ge_parts = self.ge_parts
-            m.F, m.F_hi, m.F_lo = ptr(self.F), ptr(self.F_hi), ptr(self.F_lo)
+            m.F, m.F_pl = ptr(self.F), ptr(self.F_pl)
+            m.ET_hi, m.ET_lo, m.W_hi, m.W_lo = ptr(self.ET_hi), ptr(self.ET_lo), ptr(self.W_hi), ptr(self.W_lo)
             m.step, m.loss, m.loss_slots = ptr(self.step_t), ptr(self.loss_t), self.loss_slots
             m.TH, m.W, m.rows = ptr(self.TH), ptr(self.W), ptr(self.rows_t)
+            m.th_cap = self.TH.numel() if self.TH is not None else 0
             m.max_batch, m.use_tensor_cores = self.max_batch, int(self.use_tensor_cores)
             self._struct = m
         return self._struct
@@ -232,6 +252,19 @@ class Engine:
         self.flush()
         out = torch.empty(u1 - u0, self.Ic, dtype=torch.float32, device=self.device)
         call("fvx_predict_all", C.byref(self.struct()), ptr(self.theta()), u0, u1, ptr(out), stream_ptr())
+        return out
+
+    def project_rows(self, rows):
+        """F[rows] * E_ext -> [n, de] (fvx_project_rows; VBPR.py:83-84)."""
+        out = torch.empty(rows.numel(), self.de, dtype=torch.float32, device=self.device)
+        call("fvx_project_rows", C.byref(self.struct()), ptr(rows), rows.numel(), ptr(out), stream_ptr())
+        return out
+
+    def grad_E_rows(self, rows, W):
+        """sum_r F[rows[r]]^T W[r] -> [D, de] (fvx_grad_e_rows)."""
+        out = torch.empty(self.D, self.de, dtype=torch.float32, device=self.device)
+        call("fvx_grad_e_rows", C.byref(self.struct()), ptr(rows), rows.numel(), ptr(W.contiguous()), ptr(out),
+             stream_ptr())
         return out
 
     def score_pairs(self, user, item):

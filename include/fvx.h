@@ -30,7 +30,7 @@ extern "C" {
 
 typedef void* fvx_stream_t; /* cudaStream_t */
 
-#define FVX_ABI_VERSION 1
+#define FVX_ABI_VERSION 2
 
 /* Adam semantics.  The reference's Keras Adam moves
  * EVERY row of an embedding table on every step (rows without gradient keep
@@ -74,24 +74,33 @@ typedef struct FvxModel {
   FvxTable items;       /* [item_cnt, round_up4(K+1)], local row = item - item_lo   */
   /* dense visual parameters, VBPR.py:44-54: E_ext[D,de], cols [0,d) = E, col d = Bp */
   float *E, *mE, *vE;
-  float* gE_part;       /* [ge_parts, D, de] per-CTA-group partial gradients        */
+  float* gE_part;       /* [ge_parts, D, max(de, NP)] per-row-group partial gradients */
   int32_t ge_parts;
   int32_t _pad0;
   const float* F;       /* [item_cnt, D] fp32 features, already /max|F|
-                           (visual_loader_mixin.py:30)                              */
-  const uint16_t* F_hi; /* [item_cnt, D] bf16 high plane of F (tensor-core path)    */
-  const uint16_t* F_lo; /* [item_cnt, D] bf16 plane of F - float(F_hi)              */
+                           (visual_loader_mixin.py:30); may be NULL when
+                           use_tensor_cores = 1 (only the planes are read then)      */
+  const uint16_t* F_pl; /* [item_cnt, D/64, 2, 64] bf16 planes of F (tensor-core path):
+                           per 64-feature chunk 64 x hi = bf16(F) then 64 x lo =
+                           bf16(F - hi); 4*D bytes per row (fvx_split_planes)       */
+  uint16_t* ET_hi;      /* [NP, D] bf16 planes of E_ext^T (NP = fvx_tc_width(de)),  */
+  uint16_t* ET_lo;      /*   scratch refreshed by every call that projects          */
+  uint16_t* W_hi;       /* [2*max_batch, NP] bf16 planes of the backward            */
+  uint16_t* W_lo;       /*   coefficients (tensor-core path)                        */
   int64_t* step;        /* [1] number of optimiser steps applied so far             */
   double* loss;         /* [loss_slots] per-step loss accumulators                  */
   int32_t loss_slots;
   int32_t _pad1;
   /* per-step scratch, sized for max_batch triples */
-  float* TH;            /* [2*max_batch, de] F[i]*E_ext for (triple, side)          */
-  float* W;             /* [2*max_batch, de] backward coefficients                  */
+  float* TH;            /* F[i]*E_ext for every (triple, side) slot: [2*max_batch, de]
+                           (fp32 path) or [ksplit, 2*max_batch, NP] K-split partials
+                           (tensor-core path)                                       */
+  int64_t th_cap;       /* floats available at TH                                   */
+  float* W;             /* [2*max_batch, de] backward coefficients (fp32 path)      */
   int32_t* rows;        /* [2*max_batch] local item row of each (triple, side) slot,
                            -1 when the item belongs to another rank                 */
   int32_t max_batch;
-  int32_t use_tensor_cores; /* 0: fp32 SIMT projection; 1: tcgen05 (needs F_hi/F_lo) */
+  int32_t use_tensor_cores; /* 0: fp32 SIMT projection; 1: tcgen05 (needs the planes) */
 } FvxModel;
 
 /* ---- library ------------------------------------------------------------------ */
@@ -198,9 +207,22 @@ int fvx_score_pairs(const FvxModel* model, const float* theta_ext, const int32_t
 int fvx_topk_merge(const int32_t* ids, const float* scores, int64_t n_users, int32_t R, int32_t k,
                    int32_t* out_ids, float* out_scores, fvx_stream_t stream);
 
+/* ---- the projection as a building block (VBPR.py:83-84 and its gradient) ------- */
+/* Padded width of the tensor-core operands for a given de = round_up4(d+1). */
+int fvx_tc_width(int32_t de);
+/* out[r, 0:de] = F[rows[r], :] * E_ext for r in [0, nrows); rows[r] < 0 gives an
+ * unspecified row.  nrows <= 2*max_batch.  Uses tcgen05 when use_tensor_cores = 1. */
+int fvx_project_rows(const FvxModel* model, const int32_t* rows, int64_t nrows, float* out,
+                     fvx_stream_t stream);
+/* out[D, de] = sum_r F[rows[r], :]^T * W[r, :], W fp32 [nrows, de] (rows[r] < 0: skipped).
+ * nrows <= 2*max_batch.  Uses tcgen05 when use_tensor_cores = 1. */
+int fvx_grad_e_rows(const FvxModel* model, const int32_t* rows, int64_t nrows, const float* W,
+                    float* out, fvx_stream_t stream);
+
 /* ---- feature planes for the tensor-core path ----------------------------------- */
-/* hi = bf16(F), lo = bf16(F - float(hi)) : 4 bytes/element like fp32, ~2^-17 rel. */
-int fvx_split_bf16(const float* src, uint16_t* hi, uint16_t* lo, int64_t n, fvx_stream_t stream);
+/* hi = bf16(F), lo = bf16(F - float(hi)) : 4 bytes/element like fp32, ~2^-17 relative.
+ * src fp32 [n_rows, D] -> dst [n_rows, D/64, 2, 64] (the FvxModel.F_pl layout); D % 64 == 0. */
+int fvx_split_planes(const float* src, uint16_t* dst, int64_t n_rows, int32_t D, fvx_stream_t stream);
 
 #ifdef __cplusplus
 }
