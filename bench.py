@@ -39,7 +39,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=16384)
     ap.add_argument("--top_k", type=int, default=100)
     ap.add_argument("--adam_mode", default="deferred", choices=["deferred", "dense", "lazy"])
-    ap.add_argument("--tensor_cores", type=int, default=0)
+    ap.add_argument("--tensor_cores", type=int, default=1)
     ap.add_argument("--no_eval", action="store_true")
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--cpu_seconds", type=float, default=12.0)
@@ -246,9 +246,7 @@ def run_fvx(args):
 
     for _ in range(args.warmup):
         e.step(*next(batches))
-    launches_per_step = 10 if D else 7
-    if args.adam_mode != "deferred":
-        launches_per_step -= 2
+    launches_per_step = 5 if D else 3      # prep, projection, score+grad, grad_E, update
     clocks = ClockSampler(local)
     barrier()
     clocks.start()
@@ -299,10 +297,10 @@ def run_fvx(args):
     bpt = bytes_per_triple(K, d, D, B)
     dom = max(phases, key=phases.get)
     rows_bytes = 2 * B * D * 4.0
+    tbl = 4.0 * (3 * K + d + 2)                      # floats of the three rows of a triple, once
     kern_bytes = {"project": rows_bytes + 2 * B * e.de * 4.0, "grad_E": rows_bytes + 2 * B * e.de * 4.0,
-                  "score_grad": B * (24.0 * (3 * K + d + 2) / 6 * 2), "adam_rows": B * 24.0 * (3 * K + d + 2) * 4 / 6,
-                  "catchup": B * 24.0 * (3 * K + d + 2), "mark": 12.0 * B, "adam_E": 28.0 * D * e.de if D else 0,
-                  "finish": 0.0}
+                  "score_grad": B * 2 * tbl, "update": B * 4 * tbl + (28.0 * D * e.de if D else 0),
+                  "prep": B * (12.0 + 3 * tbl)}
     ach = kern_bytes.get(dom, 0.0) / (phases[dom] * 1e-3) / 1e9 if phases[dom] > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm, "unit": "GB/s",
                 "frac": ach / hbm, "traffic": None, "peak_source": src,

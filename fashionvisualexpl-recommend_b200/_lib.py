@@ -13,8 +13,8 @@ LIB_PATH = os.path.join(HERE, "csrc", "libfvx.so")
 
 ABI_VERSION = 2
 ADAM_DENSE, ADAM_DEFERRED, ADAM_LAZY = 0, 1, 2
-N_PHASES = 8
-PHASES = ("mark", "catchup", "project", "score_grad", "grad_E", "adam_rows", "adam_E", "finish")
+N_PHASES = 5
+PHASES = ("prep", "project", "score_grad", "grad_E", "update")
 ADAM_MODES = {"dense": ADAM_DENSE, "deferred": ADAM_DEFERRED, "lazy": ADAM_LAZY}
 
 _p = C.c_void_p
@@ -33,7 +33,7 @@ class FvxModel(C.Structure):
                 ("vE", _p), ("gE_part", _p), ("ge_parts", C.c_int32), ("_pad0", C.c_int32), ("F", _p),
                 ("F_pl", _p), ("ET_hi", _p), ("ET_lo", _p), ("W_hi", _p), ("W_lo", _p),
                 ("step", _p), ("loss", _p), ("loss_slots", C.c_int32), ("_pad1", C.c_int32), ("TH", _p),
-                ("th_cap", C.c_int64), ("W", _p), ("rows", _p), ("max_batch", C.c_int32),
+                ("th_cap", C.c_int64), ("W", _p), ("rows", _p), ("sync", _p), ("max_batch", C.c_int32),
                 ("use_tensor_cores", C.c_int32)]
 
 
@@ -52,7 +52,8 @@ PROTOTYPES = {
     "fvx_sizeof_model": (C.c_int, []),
     "fvx_sizeof_table": (C.c_int, []),
     "fvx_enumerate_epoch": (C.c_int, [_p, _p, _p, _p, _i32, _p, _p, _p]),
-    "fvx_perm_keys": (C.c_int, [_p, _i32, _u64, _u32, _p]),
+    "fvx_epoch_perm": (C.c_int, [_p, _p, _p, _i32, _u64, _u32, _p]),
+    "fvx_epoch_triples": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _u64, _u64, _p, _p, _p, _p]),
     "fvx_sample_negatives": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _u64, _u64, _p]),
     "fvx_bpr_step": (C.c_int, [_MP, _p, _p, _p, _i32, _i32, _p]),
     "fvx_bpr_step_timed": (C.c_int, [_MP, _p, _p, _p, _i32, _i32, C.POINTER(C.c_float), _p]),

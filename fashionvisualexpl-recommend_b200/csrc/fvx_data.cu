@@ -19,9 +19,48 @@ __global__ void k_enumerate_epoch(const int64_t* __restrict__ row_ptr, const int
   }
 }
 
-__global__ void k_perm_keys(uint32_t* __restrict__ keys, int num_users, unsigned long long seed, uint32_t epoch) {
-  for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < num_users; u += gridDim.x * blockDim.x)
-    keys[u] = fvx_philox((uint32_t)u, 0u, epoch, FVX_STREAM_PERM, (uint32_t)seed, (uint32_t)(seed >> 32)).x;
+// Epoch permutation without a sort: a 4-round Feistel network over 2h bits (2^(2h) >= U) whose
+// round function is one Philox word, restricted to [0, U) by cycle walking.  Replaces
+// random.shuffle (dataset.py:95); restated in oracle/sampler.py: feistel_user_permutation.
+__global__ void k_epoch_perm(int32_t* __restrict__ perm, int64_t* __restrict__ lens,
+                             const int64_t* __restrict__ row_ptr, int num_users, int h, unsigned long long seed,
+                             uint32_t epoch) {
+  const uint32_t mask = (1u << h) - 1u;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < num_users; p += gridDim.x * blockDim.x) {
+    uint32_t x = (uint32_t)p;
+    do {
+      uint32_t L = x >> h, R = x & mask;
+#pragma unroll 1
+      for (uint32_t r = 0; r < 4; ++r) {
+        const uint32_t f = fvx_philox(R, r, epoch, FVX_STREAM_PERM, (uint32_t)seed, (uint32_t)(seed >> 32)).x & mask;
+        const uint32_t nl = R;
+        R = L ^ f;
+        L = nl;
+      }
+      x = (L << h) | R;
+    } while (x >= (uint32_t)num_users);
+    perm[p] = (int32_t)x;
+    if (lens) lens[p] = row_ptr[x + 1] - row_ptr[x];
+  }
+}
+
+// enumerate + negatives in one pass: triple o+t of the epoch uses Philox counter offset+o+t
+__global__ void k_epoch_triples(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col_file,
+                                const int32_t* __restrict__ col_sorted, const int32_t* __restrict__ perm,
+                                const int64_t* __restrict__ offs_incl, int num_users, uint32_t num_items,
+                                unsigned long long seed, unsigned long long offset, int32_t* __restrict__ out_user,
+                                int32_t* __restrict__ out_pos, int32_t* __restrict__ out_neg) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
+  for (int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; p < num_users; p += warps_per_grid) {
+    const int32_t u = perm[p];
+    const int64_t a = row_ptr[u], b = row_ptr[u + 1], n = b - a, o = offs_incl[p] - n;
+    for (int64_t t = lane; t < n; t += 32) {
+      out_user[o + t] = u;
+      out_pos[o + t] = col_file[a + t];
+      out_neg[o + t] = fvx_draw_negative(col_sorted, a, b, offset + (unsigned long long)(o + t), num_items, seed);
+    }
+  }
 }
 
 __global__ void k_sample_negatives(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col_sorted,
@@ -55,11 +94,30 @@ int fvx_enumerate_epoch(const int64_t* row_ptr, const int32_t* col_file, const i
   return 0;
 }
 
-int fvx_perm_keys(uint32_t* keys, int32_t num_users, uint64_t seed, uint32_t epoch, fvx_stream_t stream) {
-  FVX_CHECK_ARG(keys, "fvx_perm_keys: null pointer");
+int fvx_epoch_perm(int32_t* perm, int64_t* lens, const int64_t* row_ptr, int32_t num_users, uint64_t seed,
+                   uint32_t epoch, fvx_stream_t stream) {
+  FVX_CHECK_ARG(perm && (lens == nullptr || row_ptr != nullptr), "fvx_epoch_perm: null pointer");
   if (num_users <= 0) return 0;
-  k_perm_keys<<<grid_for(num_users, 256), 256, 0, fvx_cu(stream)>>>(keys, num_users, seed, epoch);
-  FVX_CHECK_LAUNCH("k_perm_keys");
+  int bits = 1;
+  while (bits < 31 && (1LL << bits) < (long long)num_users) ++bits;
+  const int h = (bits + 1) / 2;
+  k_epoch_perm<<<grid_for(num_users, 256), 256, 0, fvx_cu(stream)>>>(perm, lens, row_ptr, num_users, h, seed, epoch);
+  FVX_CHECK_LAUNCH("k_epoch_perm");
+  return 0;
+}
+
+int fvx_epoch_triples(const int64_t* row_ptr, const int32_t* col_file, const int32_t* col_sorted,
+                      const int32_t* perm, const int64_t* offs_incl, int32_t num_users, int32_t num_items,
+                      uint64_t seed, uint64_t offset, int32_t* out_user, int32_t* out_pos, int32_t* out_neg,
+                      fvx_stream_t stream) {
+  FVX_CHECK_ARG(row_ptr && col_file && col_sorted && perm && offs_incl && out_user && out_pos && out_neg,
+                "fvx_epoch_triples: null pointer");
+  FVX_CHECK_ARG(num_items > 0, "fvx_epoch_triples: num_items must be positive");
+  if (num_users <= 0) return 0;
+  k_epoch_triples<<<grid_for((long long)num_users * 32, 256), 256, 0, fvx_cu(stream)>>>(
+      row_ptr, col_file, col_sorted, perm, offs_incl, num_users, (uint32_t)num_items, seed, offset, out_user,
+      out_pos, out_neg);
+  FVX_CHECK_LAUNCH("k_epoch_triples");
   return 0;
 }
 

@@ -2,44 +2,18 @@
 // (src/recommender/models/BPRMF.py:87-125, VBPR.py:99-144) and the Keras-Adam update
 // they call (math: SURVEY.md Appendix A; restated in oracle/bpr.py).
 //
-// Kernel sequence per step (all on one stream, no host sync):
-//   k_mark        unique touched user / item rows -> lists; local row ids for the GEMMs
-//   k_catchup x2  DEFERRED Adam: replay skipped zero-gradient steps of touched rows
-//   projection    TH = F[rows] * E_ext                      (fvx_project.cu, VBPR only)
+// Kernel sequence per step (one stream, no host synchronisation, graph-capturable):
+//   k_prep        unique touched user / item rows -> lists, local row ids of the slots,
+//                 DEFERRED Adam catch-up of the touched rows, bf16 planes of E_ext^T
+//   projection    TH = F[rows] * E_ext                       (fvx_project[_tc].cu, VBPR only)
 //   k_score_grad  x_uij, loss, gradient coefficients, scatter-add into g, W for dE
-//   grad_E        gE_part = F[rows]^T * W                   (fvx_project.cu, VBPR only)
-//   k_adam_rows x2 / k_adam_sweep x2   Adam on touched rows / on whole tables (DENSE)
-//   k_adam_E      dense Adam on E_ext (+ its L2 term)       (VBPR only)
-//   k_finish      step += 1, reset lists
+//   grad_E        gE_part = F[rows]^T * W                    (fvx_project[_tc].cu, VBPR only)
+//   k_update      Adam on the touched rows (or whole tables: DENSE), dense Adam on E_ext,
+//                 step += 1 and list reset by the last block
 #include <cuda_bf16.h>
 
 #include "fvx_common.cuh"
 #include "fvx_kernels.cuh"
-
-// ---------------------------------------------------------------------------------
-__device__ __forceinline__ void touch_row(const FvxTable& T, int32_t r, int32_t t) {
-  const int32_t old = atomicMax(&T.mark[r], t);
-  if (old < t) {
-    const int32_t idx = atomicAdd(T.count, 1);
-    if (idx < T.list_cap) T.list[idx] = r;
-  }
-}
-
-__global__ void k_mark(FvxModel M, const int32_t* __restrict__ user, const int32_t* __restrict__ pos,
-                       const int32_t* __restrict__ neg, int B) {
-  const int32_t t = (int32_t)(*M.step) + 1;
-  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
-    const int32_t u = user[b];
-    if (b == 0 || user[b - 1] != u) touch_row(M.users, u, t);
-    int32_t li = pos[b] - M.item_lo, lj = neg[b] - M.item_lo;
-    if (li < 0 || li >= M.item_cnt) li = -1;
-    if (lj < 0 || lj >= M.item_cnt) lj = -1;
-    M.rows[b] = li;
-    M.rows[B + b] = lj;
-    if (li >= 0) touch_row(M.items, li, t);
-    if (lj >= 0) touch_row(M.items, lj, t);
-  }
-}
 
 // ---------------------------------------------------------------------------------
 // DEFERRED Adam catch-up: a row last brought up to step `last` has, under the
@@ -81,15 +55,76 @@ __device__ __forceinline__ void replay_row(const FvxTable& T, int32_t r, int32_t
   if (lane == 0) T.last[r] = target;
 }
 
-// rows in T.list -> step (*step); one warp per row
-__global__ void k_catchup_list(FvxTable T, const int64_t* __restrict__ step, float lr) {
-  const int32_t target = (int32_t)(*step);
+// Claims row r of table T for step t.  The winning lanes of the warp append their rows to
+// T.list with ONE atomic on the counter; returns the ballot of winners.
+__device__ __forceinline__ uint32_t claim_rows(const FvxTable& T, int32_t r, bool want, int32_t t, int lane) {
+  bool win = false;
+  if (want) win = atomicMax(&T.mark[r], t) < t;
+  const uint32_t b = __ballot_sync(0xffffffffu, win);
+  if (b) {
+    const int leader = __ffs(b) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(T.count, __popc(b));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (win) {
+      const int idx = base + __popc(b & ((1u << lane) - 1u));
+      if (idx < T.list_cap) T.list[idx] = r;
+    }
+  }
+  return b;
+}
+
+#define PREP_TPW 4
+// blocks [0, nb_mark): PREP_TPW triples per warp pass; blocks beyond: bf16 planes of E_ext^T
+__global__ void __launch_bounds__(256)
+k_prep(FvxModel M, const int32_t* __restrict__ user, const int32_t* __restrict__ pos,
+       const int32_t* __restrict__ neg, int B, int nb_mark, int NP) {
   const int lane = threadIdx.x & 31;
-  int n = *T.count;
-  if (n > T.list_cap) n = T.list_cap;
-  const int warps = (gridDim.x * blockDim.x) >> 5;
-  for (int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < n; e += warps)
-    replay_row(T, T.list[e], target, lr, lane);
+  if ((int)blockIdx.x >= nb_mark) {
+    __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(M.ET_hi);
+    __nv_bfloat16* lo = reinterpret_cast<__nv_bfloat16*>(M.ET_lo);
+    const int total = NP * M.D;
+    for (int i = (blockIdx.x - nb_mark) * blockDim.x + threadIdx.x; i < total;
+         i += (gridDim.x - nb_mark) * blockDim.x) {
+      const int n = i / M.D, f = i - n * M.D;
+      const float x = n < M.de ? M.E[(size_t)f * M.de + n] : 0.0f;
+      const __nv_bfloat16 h = __float2bfloat16_rn(x);
+      hi[i] = h;
+      lo[i] = __float2bfloat16_rn(x - __bfloat162float(h));
+    }
+    return;
+  }
+  const int32_t done = (int32_t)(*M.step);
+  const int32_t t = done + 1;
+  const bool deferred = M.adam_mode == FVX_ADAM_DEFERRED;
+  // a warp takes PREP_TPW triples at a time (lanes 0..PREP_TPW-1 claim their three rows), then
+  // replays the claimed rows one after the other with all 32 lanes on the row's columns
+  const int warp_g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (nb_mark * blockDim.x) >> 5;
+  for (int b0 = warp_g * PREP_TPW; b0 < B; b0 += nwarps * PREP_TPW) {
+    const int b = b0 + lane;
+    const bool live = lane < PREP_TPW && b < B;
+    int32_t u = -1, li = -1, lj = -1;
+    bool ustart = false;
+    if (live) {
+      u = user[b];
+      ustart = (b == 0 || user[b - 1] != u);
+      li = pos[b] - M.item_lo;
+      lj = neg[b] - M.item_lo;
+      if (li < 0 || li >= M.item_cnt) li = -1;
+      if (lj < 0 || lj >= M.item_cnt) lj = -1;
+      M.rows[b] = li;
+      M.rows[B + b] = lj;
+    }
+    uint32_t wu = claim_rows(M.users, u, live && ustart && u >= 0 && u < M.num_users, t, lane);
+    uint32_t wi = claim_rows(M.items, li, li >= 0, t, lane);
+    uint32_t wj = claim_rows(M.items, lj, lj >= 0, t, lane);
+    if (deferred) {
+      while (wu) { const int L = __ffs(wu) - 1; wu &= wu - 1; replay_row(M.users, __shfl_sync(0xffffffffu, u, L), done, M.lr, lane); }
+      while (wi) { const int L = __ffs(wi) - 1; wi &= wi - 1; replay_row(M.items, __shfl_sync(0xffffffffu, li, L), done, M.lr, lane); }
+      while (wj) { const int L = __ffs(wj) - 1; wj &= wj - 1; replay_row(M.items, __shfl_sync(0xffffffffu, lj, L), done, M.lr, lane); }
+    }
+  }
 }
 
 // every row -> step (*step)  (fvx_adam_flush)
@@ -102,13 +137,14 @@ __global__ void k_catchup_all(FvxTable T, const int64_t* __restrict__ step, floa
 }
 
 // ---------------------------------------------------------------------------------
-// Scores, loss and gradients of one batch.  One warp walks TPW consecutive triples so
-// that the run of equal users the reference's sampler produces (dataset.py:96-99) is
-// reduced in shared memory and leaves as ONE atomic row update.
-#define SG_TPW 8
+// Scores, loss and gradients of one batch: one warp per triple, every row of the triple
+// in flight at once (user row, two item rows, two theta rows).  Gradients leave as
+// red.global.add into the zero-initialised accumulators g (duplicates of a row inside a
+// batch - the reference's sampler emits runs of one user, dataset.py:96-99 - are summed
+// there, which is the dedup-sum TF's sparse Adam does before squaring).
 #define SG_WARPS 8
 
-// TH layout: row stride th_np, th_ks K-split partials th_ss floats apart (summed here).
+// TH layout: row stride np, ks K-split partials ss floats apart (summed on read).
 struct SgTheta {
   const float* p;
   int np, ks;
@@ -121,107 +157,98 @@ struct SgTheta {
   }
 };
 
+template <int MAXV>
 __global__ void __launch_bounds__(SG_WARPS * 32)
 k_score_grad(FvxModel M, const int32_t* __restrict__ user, int B, int loss_slot, SgTheta T, int wnp) {
-  extern __shared__ float sg_smem[];
+  __shared__ double loss_sh[SG_WARPS];
   const int Su = M.users.stride, Si = M.items.stride, K = M.K, d = M.d, de = M.de;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* urow = sg_smem + (size_t)warp * 2 * Su;  // current user's row
-  float* uacc = urow + Su;                        // its gradient accumulator
   const float reg = M.reg, reg2 = 2.0f * M.reg;
   const bool vis = M.D > 0;
   const long long gw = (long long)blockIdx.x * SG_WARPS + warp;
   const long long nw = (long long)gridDim.x * SG_WARPS;
   double loss_acc = 0.0;
+  __nv_bfloat16* wh = reinterpret_cast<__nv_bfloat16*>(M.W_hi);
+  __nv_bfloat16* wl = reinterpret_cast<__nv_bfloat16*>(M.W_lo);
 
-  for (long long b0 = gw * SG_TPW; b0 < B; b0 += nw * SG_TPW) {
-    int32_t cur_u = -1;
-    const int bend = (int)((b0 + SG_TPW < B) ? b0 + SG_TPW : B);
-    for (int b = (int)b0; b < bend; ++b) {
-      const int32_t u = user[b];
-      if (u != cur_u) {
-        if (cur_u >= 0) {
-          float* g = M.users.g + (size_t)cur_u * Su;
-          for (int c = lane; c < Su; c += 32) fvx_red_add(g + c, uacc[c]);
-        }
-        const float* src = M.users.w + (size_t)u * Su;
-        for (int c = lane; c < Su; c += 32) { urow[c] = src[c]; uacc[c] = 0.0f; }
-        cur_u = u;
-        __syncwarp();
-      }
-      const int32_t li = M.rows[b], lj = M.rows[B + b];
-      if (li < 0 || lj < 0) {  // item id outside the catalog: triple ignored (no gradient to E either)
-        if (vis && wnp > 0) {
-          for (int n = lane; n < wnp; n += 32) {
+  for (long long b = gw; b < B; b += nw) {
+    const int32_t u = user[b];
+    const int32_t li = M.rows[b], lj = M.rows[B + b];
+    if (li < 0 || lj < 0 || u < 0 || u >= M.num_users) {
+      // item id outside the catalog: triple ignored (and no gradient to E either)
+      if (vis) {
+        const int nw_ = wnp > 0 ? wnp : de;
+        for (int n = lane; n < nw_; n += 32) {
+          if (wnp > 0) {
             const __nv_bfloat16 z = __float2bfloat16_rn(0.0f);
-            reinterpret_cast<__nv_bfloat16*>(M.W_hi)[(size_t)b * wnp + n] = z;
-            reinterpret_cast<__nv_bfloat16*>(M.W_lo)[(size_t)b * wnp + n] = z;
-            reinterpret_cast<__nv_bfloat16*>(M.W_hi)[(size_t)(B + b) * wnp + n] = z;
-            reinterpret_cast<__nv_bfloat16*>(M.W_lo)[(size_t)(B + b) * wnp + n] = z;
+            wh[(size_t)b * wnp + n] = z; wl[(size_t)b * wnp + n] = z;
+            wh[(size_t)(B + b) * wnp + n] = z; wl[(size_t)(B + b) * wnp + n] = z;
+          } else {
+            M.W[(size_t)b * de + n] = 0.0f; M.W[(size_t)(B + b) * de + n] = 0.0f;
           }
-        } else if (vis) {
-          for (int n = lane; n < de; n += 32) { M.W[(size_t)b * de + n] = 0.0f; M.W[(size_t)(B + b) * de + n] = 0.0f; }
         }
-        continue;
       }
-      const float* gi = M.items.w + (size_t)li * Si;
-      const float* gj = M.items.w + (size_t)lj * Si;
-      float part = 0.0f, sq = 0.0f;
-      for (int c = lane; c < K; c += 32) {
-        const float a = urow[c], x = gi[c], y = gj[c];
-        part = fmaf(a, x - y, part);
-        sq += a * a + x * x + y * y;
+      continue;
+    }
+    const float* ur = M.users.w + (size_t)u * Su;
+    const float* gi = M.items.w + (size_t)li * Si;
+    const float* gj = M.items.w + (size_t)lj * Si;
+    float a[MAXV], x[MAXV], y[MAXV], tu[MAXV], dt[MAXV];
+#pragma unroll
+    for (int q = 0; q < MAXV; ++q) {
+      const int c = lane + 32 * q;
+      const bool in = c < K;
+      a[q] = in ? ur[c] : 0.0f;
+      x[q] = in ? gi[c] : 0.0f;
+      y[q] = in ? gj[c] : 0.0f;
+      const bool iv = vis && c < d;
+      tu[q] = iv ? ur[K + c] : 0.0f;
+      dt[q] = iv ? T.at(b, c) - T.at(B + b, c) : 0.0f;
+    }
+    const float bi = gi[K], bj = gj[K];
+    const float vb = vis ? T.at(b, d) - T.at(B + b, d) : 0.0f;
+    float part = 0.0f, sq = 0.0f;
+#pragma unroll
+    for (int q = 0; q < MAXV; ++q) {
+      part = fmaf(a[q], x[q] - y[q], part);
+      part = fmaf(tu[q], dt[q], part);
+      sq += a[q] * a[q] + x[q] * x[q] + y[q] * y[q] + tu[q] * tu[q];
+    }
+    const float xs = fvx_warp_sum(part) + (bi - bj) + vb;
+    const float sqs = fvx_warp_sum(sq);
+    const bool inside = (xs >= FVX_CLIP_LO) && (xs <= FVX_CLIP_HI);
+    const float coef = inside ? -1.0f / (1.0f + expf(xs)) : 0.0f;  // d softplus(-x)/dx
+    const float z = -fminf(fmaxf(xs, FVX_CLIP_LO), FVX_CLIP_HI);
+    const float sp = z > 13.942385f ? z : (z < -13.942385f ? expf(z) : log1pf(expf(z)));
+    if (lane == 0) loss_acc += (double)sp + (double)(reg * sqs) + (double)(reg * bi * bi) +
+                               (double)(reg * bj * bj / 10.0f);
+    float* gu = M.users.g + (size_t)u * Su;
+    float* ggi = M.items.g + (size_t)li * Si;
+    float* ggj = M.items.g + (size_t)lj * Si;
+#pragma unroll
+    for (int q = 0; q < MAXV; ++q) {
+      const int c = lane + 32 * q;
+      if (c < K) {
+        fvx_red_add(gu + c, coef * (x[q] - y[q]) + reg2 * a[q]);
+        fvx_red_add(ggi + c, coef * a[q] + reg2 * x[q]);
+        fvx_red_add(ggj + c, -coef * a[q] + reg2 * y[q]);
       }
-      const float bi = gi[K], bj = gj[K];
-      float vb = 0.0f;
-      float dth0 = 0.0f;   // (theta_i - theta_j)[lane]; further columns are re-read below when d > 32
-      if (vis) {
-        for (int n = lane; n < d; n += 32) {
-          const float a = urow[K + n];
-          const float dt = T.at(b, n) - T.at(B + b, n);
-          if (n < 32) dth0 = dt;
-          part = fmaf(a, dt, part);
-          sq += a * a;
-        }
-        vb = T.at(b, d) - T.at(B + b, d);
-      }
-      const float x = fvx_warp_sum(part) + (bi - bj) + vb;
-      const float sqs = fvx_warp_sum(sq);
-      const bool inside = (x >= FVX_CLIP_LO) && (x <= FVX_CLIP_HI);
-      const float coef = inside ? -1.0f / (1.0f + expf(x)) : 0.0f;  // d softplus(-x)/dx
-      const float z = -fminf(fmaxf(x, FVX_CLIP_LO), FVX_CLIP_HI);
-      const float sp = z > 13.942385f ? z : (z < -13.942385f ? expf(z) : log1pf(expf(z)));
-      if (lane == 0) loss_acc += (double)sp + (double)(reg * sqs) + (double)(reg * bi * bi) +
-                                 (double)(reg * bj * bj / 10.0f);
-      float* ggi = M.items.g + (size_t)li * Si;
-      float* ggj = M.items.g + (size_t)lj * Si;
-      for (int c = lane; c < K; c += 32) {
-        const float a = urow[c], xg = gi[c], yg = gj[c];
-        uacc[c] += coef * (xg - yg) + reg2 * a;
-        fvx_red_add(ggi + c, coef * a + reg2 * xg);
-        fvx_red_add(ggj + c, -coef * a + reg2 * yg);
-      }
-      if (lane == 0) {
-        fvx_red_add(ggi + K, coef + reg2 * bi);
-        fvx_red_add(ggj + K, -coef + (reg2 / 10.0f) * bj);
-      }
-      if (vis) {
-        const int nw = wnp > 0 ? wnp : de;
-        for (int n = lane; n < nw; n += 32) {
-          float wv = 0.0f;
-          if (n < d) {
-            const float a = urow[K + n];
-            const float dt = n < 32 ? dth0 : T.at(b, n) - T.at(B + b, n);
-            uacc[K + n] += coef * dt + reg2 * a;
-            wv = coef * a;
-          } else if (n == d) {
-            wv = coef;
-          }
+      if (vis && c < d) fvx_red_add(gu + K + c, coef * dt[q] + reg2 * tu[q]);
+    }
+    if (lane == 0) {
+      fvx_red_add(ggi + K, coef + reg2 * bi);
+      fvx_red_add(ggj + K, -coef + (reg2 / 10.0f) * bj);
+    }
+    if (vis) {
+      const int nw_ = wnp > 0 ? wnp : de;
+#pragma unroll
+      for (int q = 0; q < MAXV; ++q) {
+        const int n = lane + 32 * q;
+        if (n < nw_) {
+          const float wv = n < d ? coef * tu[q] : (n == d ? coef : 0.0f);
           if (wnp > 0) {   // bf16 hi/lo planes for the tensor-core backward
             const __nv_bfloat16 h = __float2bfloat16_rn(wv);
             const __nv_bfloat16 l = __float2bfloat16_rn(wv - __bfloat162float(h));
-            __nv_bfloat16* wh = reinterpret_cast<__nv_bfloat16*>(M.W_hi);
-            __nv_bfloat16* wl = reinterpret_cast<__nv_bfloat16*>(M.W_lo);
             wh[(size_t)b * wnp + n] = h;
             wl[(size_t)b * wnp + n] = l;
             wh[(size_t)(B + b) * wnp + n] = __hneg(h);
@@ -232,96 +259,114 @@ k_score_grad(FvxModel M, const int32_t* __restrict__ user, int B, int loss_slot,
           }
         }
       }
-      __syncwarp();
     }
-    if (cur_u >= 0) {
-      float* g = M.users.g + (size_t)cur_u * Su;
-      for (int c = lane; c < Su; c += 32) fvx_red_add(g + c, uacc[c]);
-    }
-    __syncwarp();
   }
-  if (lane == 0 && loss_acc != 0.0) atomicAdd(M.loss + loss_slot, loss_acc);
+  // one atomic per block
+  if (lane == 0) loss_sh[warp] = loss_acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < SG_WARPS; ++w) s += loss_sh[w];
+    if (s != 0.0) atomicAdd(M.loss + loss_slot, s);
+  }
 }
 
 // ---------------------------------------------------------------------------------
-// Adam on the touched rows (DEFERRED / LAZY): one warp per row of T.list.
-__global__ void k_adam_rows(FvxTable T, const int64_t* __restrict__ step, float lr) {
-  const long long t = *step + 1;
-  const float a = fvx_alpha(lr, t);
-  const int lane = threadIdx.x & 31;
-  int n = *T.count;
-  if (n > T.list_cap) n = T.list_cap;
-  const int warps = (gridDim.x * blockDim.x) >> 5;
-  for (int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < n; e += warps) {
-    const int32_t r = T.list[e];
-    const size_t o = (size_t)r * T.stride;
-    for (int c = lane; c < T.stride; c += 32) {
-      const float g = T.g[o + c];
-      const float m = FVX_BETA1 * T.m[o + c] + (1.0f - FVX_BETA1) * g;
-      const float v = FVX_BETA2 * T.v[o + c] + (1.0f - FVX_BETA2) * (g * g);
-      T.m[o + c] = m;
-      T.v[o + c] = v;
-      T.w[o + c] -= a * m / (sqrtf(v) + FVX_EPS);
-      T.g[o + c] = 0.0f;
-    }
-    if (lane == 0) T.last[r] = (int32_t)t;
-  }
-}
+// One launch for the whole parameter update.  Blocks [0, nb_u): user rows, [nb_u, nb_u+nb_i):
+// item rows, the rest: E_ext.  The last block to finish advances the step counter.
+struct UpdParams {
+  int nb_u, nb_i, nb_e;
+  int parts, gnp;       // gE_part: `parts` row-group partials with row stride gnp
+  int loss_slot;
+  int dense;            // DENSE: sweep the whole tables
+  int32_t* sync;        // [1] blocks-done counter (zero between launches)
+};
 
-// Adam on every element of the table (DENSE: the reference's literal behaviour).
-__global__ void k_adam_sweep(FvxTable T, const int64_t* __restrict__ step, float lr) {
-  const long long t = *step + 1;
-  const float a = fvx_alpha(lr, t);
-  const long long n4 = (T.rows * T.stride) >> 2;
-  float4* __restrict__ W = reinterpret_cast<float4*>(T.w);
-  float4* __restrict__ Mo = reinterpret_cast<float4*>(T.m);
-  float4* __restrict__ V = reinterpret_cast<float4*>(T.v);
-  float4* __restrict__ G = reinterpret_cast<float4*>(T.g);
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
-       i += (long long)gridDim.x * blockDim.x) {
-    float4 g = G[i], m = Mo[i], v = V[i], w = W[i];
+__device__ __forceinline__ void adam4(float4& w, float4& m, float4& v, const float4 g, float a) {
 #define FVX_ADAM1(f)                                            \
   m.f = FVX_BETA1 * m.f + (1.0f - FVX_BETA1) * g.f;             \
   v.f = FVX_BETA2 * v.f + (1.0f - FVX_BETA2) * (g.f * g.f);     \
   w.f -= a * m.f / (sqrtf(v.f) + FVX_EPS);
-    FVX_ADAM1(x) FVX_ADAM1(y) FVX_ADAM1(z) FVX_ADAM1(w)
+  FVX_ADAM1(x) FVX_ADAM1(y) FVX_ADAM1(z) FVX_ADAM1(w)
 #undef FVX_ADAM1
-    Mo[i] = m; V[i] = v; W[i] = w;
-    if (g.x != 0.0f || g.y != 0.0f || g.z != 0.0f || g.w != 0.0f) G[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+__device__ __forceinline__ void adam_table_part(const FvxTable& T, int blk, int nblk, float a, int32_t t, bool dense) {
+  float4* __restrict__ W = reinterpret_cast<float4*>(T.w);
+  float4* __restrict__ Mo = reinterpret_cast<float4*>(T.m);
+  float4* __restrict__ V = reinterpret_cast<float4*>(T.v);
+  float4* __restrict__ G = reinterpret_cast<float4*>(T.g);
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (dense) {   // the reference's literal behaviour: every element of the table moves
+    const long long n4 = (T.rows * T.stride) >> 2;
+    for (long long i = (long long)blk * blockDim.x + threadIdx.x; i < n4; i += (long long)nblk * blockDim.x) {
+      float4 g = G[i], m = Mo[i], v = V[i], w = W[i];
+      adam4(w, m, v, g, a);
+      Mo[i] = m; V[i] = v; W[i] = w;
+      if (g.x != 0.0f || g.y != 0.0f || g.z != 0.0f || g.w != 0.0f) G[i] = z4;
+    }
+    return;
+  }
+  const int lane = threadIdx.x & 31;
+  int n = *T.count;
+  if (n > T.list_cap) n = T.list_cap;
+  const int s4 = T.stride >> 2;
+  const int warps = (nblk * blockDim.x) >> 5;
+  for (int e = (blk * blockDim.x + threadIdx.x) >> 5; e < n; e += warps) {
+    const int32_t r = T.list[e];
+    const size_t o = (size_t)r * s4;
+    for (int c = lane; c < s4; c += 32) {
+      float4 g = G[o + c], m = Mo[o + c], v = V[o + c], w = W[o + c];
+      adam4(w, m, v, g, a);
+      Mo[o + c] = m; V[o + c] = v; W[o + c] = w; G[o + c] = z4;
+    }
+    if (lane == 0) T.last[r] = t;
   }
 }
 
-// Dense Adam on E_ext [D,de]: gradient = sum of the per-group partials + 2*reg*E
-// (VBPR.py:129 puts reg*(|E|^2+|Bp|^2) into the loss); adds that loss term as well.
-// gE_part rows have stride gnp floats (de on the fp32 path, NP on the tensor-core path).
-__global__ void k_adam_E(FvxModel M, int parts, int loss_slot, const float* __restrict__ extra_grad, int gnp) {
+__global__ void __launch_bounds__(256)
+k_update(FvxModel M, UpdParams U) {
   const long long t = *M.step + 1;
   const float a = fvx_alpha(M.lr, t);
-  const int n = M.D * M.de;
-  const float reg = M.reg;
-  float sq = 0.0f;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    float g = extra_grad ? extra_grad[i] : 0.0f;
-    const int f = i / M.de, c = i - f * M.de;
-    for (int p = 0; p < parts; ++p) g += M.gE_part[((size_t)p * M.D + f) * gnp + c];
-    const float e = M.E[i];
-    sq += e * e;
-    g += 2.0f * reg * e;
-    const float m = FVX_BETA1 * M.mE[i] + (1.0f - FVX_BETA1) * g;
-    const float v = FVX_BETA2 * M.vE[i] + (1.0f - FVX_BETA2) * (g * g);
-    M.mE[i] = m;
-    M.vE[i] = v;
-    M.E[i] = e - a * m / (sqrtf(v) + FVX_EPS);
+  const int b = blockIdx.x;
+  if (b < U.nb_u) {
+    adam_table_part(M.users, b, U.nb_u, a, (int32_t)t, U.dense);
+  } else if (b < U.nb_u + U.nb_i) {
+    adam_table_part(M.items, b - U.nb_u, U.nb_i, a, (int32_t)t, U.dense);
+  } else {
+    // dense Adam on E_ext [D,de]: gradient = sum of the row-group partials + 2*reg*E
+    // (VBPR.py:129 puts reg*(|E|^2+|Bp|^2) into the loss); adds that loss term as well.
+    const int n = M.D * M.de;
+    const float reg = M.reg;
+    float sq = 0.0f;
+    for (int i = (b - U.nb_u - U.nb_i) * blockDim.x + threadIdx.x; i < n; i += U.nb_e * blockDim.x) {
+      const int f = i / M.de, c = i - f * M.de;
+      float g = 0.0f;
+      for (int p = 0; p < U.parts; ++p) g += M.gE_part[((size_t)p * M.D + f) * U.gnp + c];
+      const float e = M.E[i];
+      sq += e * e;
+      g += 2.0f * reg * e;
+      const float m = FVX_BETA1 * M.mE[i] + (1.0f - FVX_BETA1) * g;
+      const float v = FVX_BETA2 * M.vE[i] + (1.0f - FVX_BETA2) * (g * g);
+      M.mE[i] = m;
+      M.vE[i] = v;
+      M.E[i] = e - a * m / (sqrtf(v) + FVX_EPS);
+    }
+    sq = fvx_warp_sum(sq);
+    if ((threadIdx.x & 31) == 0 && sq != 0.0f) atomicAdd(M.loss + U.loss_slot, (double)(reg * sq));
   }
-  sq = fvx_warp_sum(sq);
-  if ((threadIdx.x & 31) == 0 && sq != 0.0f && loss_slot >= 0) atomicAdd(M.loss + loss_slot, (double)(reg * sq));
-}
-
-__global__ void k_finish(FvxModel M) {
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    *M.step += 1;
-    *M.users.count = 0;
-    *M.items.count = 0;
+  // last block: the step is complete
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const int prev = atomicAdd(U.sync, 1);
+    if (prev == (int)gridDim.x - 1) {
+      *U.sync = 0;
+      *M.step += 1;
+      *M.users.count = 0;
+      *M.items.count = 0;
+      __threadfence();
+    }
   }
 }
 
@@ -350,10 +395,7 @@ static inline int warp_grid(long long rows, int block = 256, int per_sm = 8) {
 }
 
 int fvx_launch_score_grad(const FvxModel* m, const int32_t* user, int B, int loss_slot, int th_ks, cudaStream_t st) {
-  const size_t smem = (size_t)SG_WARPS * 2 * m->users.stride * sizeof(float);
-  FVX_CHECK_ARG(smem <= 48 * 1024, "fvx_bpr_step: K+d too large for the score kernel (%zu B smem)", smem);
-  long long groups = ((long long)B + SG_TPW - 1) / SG_TPW;
-  long long g = (groups + SG_WARPS - 1) / SG_WARPS;
+  long long g = ((long long)B + SG_WARPS - 1) / SG_WARPS;
   long long cap = (long long)fvx_num_sms() * 8;
   if (g > cap) g = cap;
   SgTheta T;
@@ -362,13 +404,20 @@ int fvx_launch_score_grad(const FvxModel* m, const int32_t* user, int B, int los
   T.np = tc ? fvx_tc_np(m->de) : m->de;
   T.ks = tc ? th_ks : 1;
   T.ss = 2LL * B * T.np;
-  k_score_grad<<<(int)g, SG_WARPS * 32, smem, st>>>(*m, user, B, loss_slot, T, tc ? T.np : 0);
+  const int wnp = tc ? T.np : 0;
+  const int need = (m->K > m->d + 1 ? m->K : m->d + 1);
+  FVX_CHECK_ARG(need <= 256 && (wnp == 0 || wnp <= 256), "fvx_bpr_step: K=%d / d=%d too large for the score kernel",
+                m->K, m->d);
+  if (need <= 64 && wnp <= 64)
+    k_score_grad<2><<<(int)g, SG_WARPS * 32, 0, st>>>(*m, user, B, loss_slot, T, wnp);
+  else
+    k_score_grad<8><<<(int)g, SG_WARPS * 32, 0, st>>>(*m, user, B, loss_slot, T, wnp);
   FVX_CHECK_LAUNCH("k_score_grad");
   return 0;
 }
 
 // phases of one step, in launch order (FVX_N_PHASES entries; see fvx.h)
-enum { PH_MARK = 0, PH_CATCHUP, PH_PROJECT, PH_SCORE_GRAD, PH_GRAD_E, PH_ADAM_ROWS, PH_ADAM_E, PH_FINISH, PH_COUNT };
+enum { PH_PREP = 0, PH_PROJECT, PH_SCORE_GRAD, PH_GRAD_E, PH_UPDATE, PH_COUNT };
 
 static int bpr_step_impl(const FvxModel* model, const int32_t* user, const int32_t* pos, const int32_t* neg,
                          int32_t B, int32_t loss_slot, cudaStream_t st, cudaEvent_t* ev) {
@@ -380,35 +429,34 @@ static int bpr_step_impl(const FvxModel* model, const int32_t* user, const int32
                 "fvx_bpr_step: model is item-sharded; use the sharded entry points");
   FVX_CHECK_ARG(loss_slot >= 0 && loss_slot < M.loss_slots, "fvx_bpr_step: loss_slot out of range");
   FVX_CHECK_ARG(M.users.list_cap >= B && M.items.list_cap >= 2 * B, "fvx_bpr_step: touched-row lists too small");
-  FVX_CHECK_ARG(M.rows != nullptr && M.loss != nullptr, "fvx_bpr_step: null scratch");
+  FVX_CHECK_ARG(M.rows != nullptr && M.loss != nullptr && M.sync != nullptr, "fvx_bpr_step: null scratch");
   const bool vis = M.D > 0;
   const bool tc = vis && M.use_tensor_cores;
+  const int NP = tc ? fvx_tc_np(M.de) : M.de;
   int th_ks = 1;
   if (vis) FVX_CHECK_ARG(M.TH && M.gE_part && M.ge_parts > 0 && (tc || M.W), "fvx_bpr_step: VBPR scratch missing");
   if (tc) {
     FVX_CHECK_ARG(M.F_pl && M.ET_hi && M.ET_lo && M.W_hi && M.W_lo,
                   "fvx_bpr_step: use_tensor_cores=1 needs the bf16 planes (F_pl, ET_*, W_*)");
     th_ks = fvx_tc_ksplit(&M, 2LL * B);
-    while (th_ks > 1 && (long long)th_ks * 2 * B * fvx_tc_np(M.de) > M.th_cap) th_ks >>= 1;
-    FVX_CHECK_ARG((long long)th_ks * 2 * B * fvx_tc_np(M.de) <= M.th_cap, "fvx_bpr_step: TH scratch too small");
+    while (th_ks > 1 && (long long)th_ks * 2 * B * NP > M.th_cap) th_ks >>= 1;
+    FVX_CHECK_ARG((long long)th_ks * 2 * B * NP <= M.th_cap, "fvx_bpr_step: TH scratch too small");
   } else if (vis) {
     FVX_CHECK_ARG(M.F != nullptr, "fvx_bpr_step: fp32 projection needs F");
     FVX_CHECK_ARG(2LL * B * M.de <= M.th_cap, "fvx_bpr_step: TH scratch too small");
   }
 #define PHASE(i) do { if (ev) cudaEventRecord(ev[i], st); } while (0)
 
-  PHASE(PH_MARK);
-  k_mark<<<warp_grid((B + 31) / 32), 256, 0, st>>>(M, user, pos, neg, B);
-  FVX_CHECK_LAUNCH("k_mark");
-  PHASE(PH_CATCHUP);
-  if (M.adam_mode == FVX_ADAM_DEFERRED) {
-    k_catchup_list<<<warp_grid(B), 256, 0, st>>>(M.users, M.step, M.lr);
-    k_catchup_list<<<warp_grid(2LL * B), 256, 0, st>>>(M.items, M.step, M.lr);
-    FVX_CHECK_LAUNCH("k_catchup_list");
+  PHASE(PH_PREP);
+  {
+    int nb_mark = (B + 8 * PREP_TPW - 1) / (8 * PREP_TPW);     // 8 warps per block
+    if (nb_mark > fvx_num_sms() * 8) nb_mark = fvx_num_sms() * 8;
+    const int nb_e = tc ? 32 : 0;
+    k_prep<<<nb_mark + nb_e, 256, 0, st>>>(M, user, pos, neg, B, nb_mark, NP);
+    FVX_CHECK_LAUNCH("k_prep");
   }
   PHASE(PH_PROJECT);
   if (tc) {
-    if (int rc = fvx_launch_split_E(&M, st)) return rc;
     if (int rc = fvx_launch_project_tc(&M, M.rows, 0, 2 * B, th_ks, M.TH, st)) return rc;
   } else if (vis) {
     if (int rc = fvx_launch_project(&M, M.rows, 2 * B, M.TH, st)) return rc;
@@ -422,27 +470,23 @@ static int bpr_step_impl(const FvxModel* model, const int32_t* user, const int32
   } else if (vis) {
     if (int rc = fvx_launch_grad_E(&M, M.rows, 2 * B, &parts, st)) return rc;
   }
-  PHASE(PH_ADAM_ROWS);
-  if (M.adam_mode == FVX_ADAM_DENSE) {
-    k_adam_sweep<<<fvx_num_sms() * 8, 256, 0, st>>>(M.users, M.step, M.lr);
-    k_adam_sweep<<<fvx_num_sms() * 8, 256, 0, st>>>(M.items, M.step, M.lr);
-    FVX_CHECK_LAUNCH("k_adam_sweep");
-  } else {
-    k_adam_rows<<<warp_grid(B), 256, 0, st>>>(M.users, M.step, M.lr);
-    k_adam_rows<<<warp_grid(2LL * B), 256, 0, st>>>(M.items, M.step, M.lr);
-    FVX_CHECK_LAUNCH("k_adam_rows");
+  PHASE(PH_UPDATE);
+  {
+    UpdParams U;
+    U.dense = M.adam_mode == FVX_ADAM_DENSE;
+    if (U.dense) {
+      U.nb_u = fvx_num_sms() * 4;
+      U.nb_i = fvx_num_sms() * 4;
+    } else {
+      U.nb_u = warp_grid(B, 256, 2);
+      U.nb_i = warp_grid(2LL * B, 256, 6);
+    }
+    U.nb_e = vis ? (M.D * M.de + 255) / 256 : 0;
+    if (U.nb_e > fvx_num_sms() * 2) U.nb_e = fvx_num_sms() * 2;
+    U.parts = parts; U.gnp = NP; U.loss_slot = loss_slot; U.sync = M.sync;
+    k_update<<<U.nb_u + U.nb_i + U.nb_e, 256, 0, st>>>(M, U);
+    FVX_CHECK_LAUNCH("k_update");
   }
-  PHASE(PH_ADAM_E);
-  if (vis) {
-    const int n = M.D * M.de;
-    int g = (n + 255) / 256;
-    if (g > fvx_num_sms() * 4) g = fvx_num_sms() * 4;
-    k_adam_E<<<g, 256, 0, st>>>(M, parts, loss_slot, nullptr, tc ? fvx_tc_np(M.de) : M.de);
-    FVX_CHECK_LAUNCH("k_adam_E");
-  }
-  PHASE(PH_FINISH);
-  k_finish<<<1, 32, 0, st>>>(M);
-  FVX_CHECK_LAUNCH("k_finish");
   PHASE(PH_COUNT);
 #undef PHASE
   return 0;

@@ -197,25 +197,24 @@ class DataLoader(object):
 
     def device_epoch(self, epoch, device="cuda:0"):
         """(user, pos, neg) int32 CUDA tensors of one whole epoch (N triples), generated on
-        the device: Philox permutation keys -> stable argsort -> CSR expansion -> negatives."""
+        the device with no host synchronisation: Feistel/Philox user permutation ->
+        prefix sum of the list lengths -> CSR expansion with the negatives drawn in the same pass."""
         import torch
         from .. import _lib
         st = self.device_state(device)
         dv = torch.device(device)
         U, N = self.num_users, self.num_train
-        keys = torch.empty(U, dtype=torch.int32, device=dv)
-        _lib.call("fvx_perm_keys", _lib.ptr(keys), U, self.seed, epoch, _lib.stream_ptr())
-        perm = torch.argsort(keys.to(torch.int64) & 0xFFFFFFFF, stable=True)
-        lens = st["lens"][perm]
-        offs = torch.cumsum(lens, 0) - lens
-        perm32 = perm.to(torch.int32)
+        perm = torch.empty(U, dtype=torch.int32, device=dv)
+        lens = torch.empty(U, dtype=torch.int64, device=dv)
+        _lib.call("fvx_epoch_perm", _lib.ptr(perm), _lib.ptr(lens), _lib.ptr(st["row_ptr"]), U, self.seed, epoch,
+                  _lib.stream_ptr())
+        offs_incl = torch.cumsum(lens, 0)
         users = torch.empty(N, dtype=torch.int32, device=dv)
         pos = torch.empty(N, dtype=torch.int32, device=dv)
         neg = torch.empty(N, dtype=torch.int32, device=dv)
-        _lib.call("fvx_enumerate_epoch", _lib.ptr(st["row_ptr"]), _lib.ptr(st["col_file"]), _lib.ptr(perm32),
-                  _lib.ptr(offs.contiguous()), U, _lib.ptr(users), _lib.ptr(pos), _lib.stream_ptr())
-        _lib.call("fvx_sample_negatives", _lib.ptr(st["row_ptr"]), _lib.ptr(st["col_sorted"]), _lib.ptr(users),
-                  _lib.ptr(neg), N, self.num_items, self.seed, epoch * N, _lib.stream_ptr())
+        _lib.call("fvx_epoch_triples", _lib.ptr(st["row_ptr"]), _lib.ptr(st["col_file"]), _lib.ptr(st["col_sorted"]),
+                  _lib.ptr(perm), _lib.ptr(offs_incl), U, self.num_items, self.seed, epoch * N, _lib.ptr(users),
+                  _lib.ptr(pos), _lib.ptr(neg), _lib.stream_ptr())
         return users, pos, neg
 
     def next_triple_batch(self, device="cuda:0"):

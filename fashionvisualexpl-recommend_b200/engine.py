@@ -63,6 +63,7 @@ class Engine:
         self.step_t = torch.zeros(1, dtype=torch.int64, device=dev)
         self.loss_t = torch.zeros(self.loss_slots, dtype=torch.float64, device=dev)
         self.rows_t = torch.zeros(2 * self.max_batch, **i32)
+        self.sync_t = torch.zeros(4, **i32)
         self.F = self.F_pl = None
         self.ET_hi = self.ET_lo = self.W_hi = self.W_lo = None
         self.use_tensor_cores = bool(use_tensor_cores) and self.D > 0
@@ -192,6 +193,7 @@ class Engine:
             m.step, m.loss, m.loss_slots = ptr(self.step_t), ptr(self.loss_t), self.loss_slots
             m.TH, m.W, m.rows = ptr(self.TH), ptr(self.W), ptr(self.rows_t)
             m.th_cap = self.TH.numel() if self.TH is not None else 0
+            m.sync = ptr(self.sync_t)
             m.max_batch, m.use_tensor_cores = self.max_batch, int(self.use_tensor_cores)
             self._struct = m
         return self._struct

@@ -99,6 +99,7 @@ typedef struct FvxModel {
   float* W;             /* [2*max_batch, de] backward coefficients (fp32 path)      */
   int32_t* rows;        /* [2*max_batch] local item row of each (triple, side) slot,
                            -1 when the item belongs to another rank                 */
+  int32_t* sync;        /* [4] zero-initialised inter-block counters of the step kernels */
   int32_t max_batch;
   int32_t use_tensor_cores; /* 0: fp32 SIMT projection; 1: tcgen05 (needs the planes) */
 } FvxModel;
@@ -119,10 +120,19 @@ int fvx_enumerate_epoch(const int64_t* row_ptr, const int32_t* col_file, const i
                         const int64_t* offs, int32_t num_users, int32_t* out_user,
                         int32_t* out_pos, fvx_stream_t stream);
 
-/* One 32-bit Philox key per user for the epoch permutation (stable argsort of the
- * keys = user order of that epoch); replaces random.shuffle (dataset.py:95). */
-int fvx_perm_keys(uint32_t* keys, int32_t num_users, uint64_t seed, uint32_t epoch,
-                  fvx_stream_t stream);
+/* User order of one epoch, replacing random.shuffle (dataset.py:95): perm[p] = user at
+ * position p, computed per position by a 4-round Feistel network keyed by Philox(seed,
+ * epoch) with cycle walking (no sort, no host synchronisation).  lens (optional) receives
+ * the train-list length of perm[p]; its inclusive prefix sum is offs_incl below. */
+int fvx_epoch_perm(int32_t* perm, int64_t* lens, const int64_t* row_ptr, int32_t num_users,
+                   uint64_t seed, uint32_t epoch, fvx_stream_t stream);
+
+/* fvx_enumerate_epoch + fvx_sample_negatives in one pass (offs_incl = INCLUSIVE prefix sum of
+ * the train-list lengths in perm order): triple n of the epoch uses counter offset+n. */
+int fvx_epoch_triples(const int64_t* row_ptr, const int32_t* col_file, const int32_t* col_sorted,
+                      const int32_t* perm, const int64_t* offs_incl, int32_t num_users,
+                      int32_t num_items, uint64_t seed, uint64_t offset, int32_t* out_user,
+                      int32_t* out_pos, int32_t* out_neg, fvx_stream_t stream);
 
 /* Uniform negatives with rejection against the user's TRAIN items
  * (dataset.py:100-103); counter-based: triple n uses counter offset+n. */
@@ -139,9 +149,9 @@ int fvx_bpr_step(const FvxModel* model, const int32_t* user, const int32_t* pos,
 
 /* Profiling variant of fvx_bpr_step: same work, CUDA events between the phases, and a
  * host synchronisation at the end (so it cannot be graph-captured).  phase_ms_host
- * receives FVX_N_PHASES durations in launch order: mark, catch-up, projection,
- * score+grad, grad_E, Adam rows, Adam E, finish. */
-#define FVX_N_PHASES 8
+ * receives FVX_N_PHASES durations in launch order: prep (touched-row lists + deferred-Adam
+ * catch-up + E planes), projection, score+grad, grad_E, update (Adam rows + Adam E + step). */
+#define FVX_N_PHASES 5
 int fvx_bpr_step_timed(const FvxModel* model, const int32_t* user, const int32_t* pos,
                        const int32_t* neg, int32_t B, int32_t loss_slot, float* phase_ms_host,
                        fvx_stream_t stream);

@@ -10,7 +10,7 @@ Two generators over the same enumeration order and rejection rule
   reference; small cases only.
 * ``philox_*`` - the counter-based generator of the device path: Philox4x32-10
   keyed by ``seed``, counter = (global triple index, attempt block).  The user
-  permutation of an epoch is the stable argsort of one Philox word per user.
+  permutation of an epoch is a Philox-keyed Feistel network with cycle walking.
 """
 from __future__ import annotations
 
@@ -116,12 +116,32 @@ def philox_negatives(row_ptr, col_sorted, users, num_items, seed, offset):
     return out
 
 
-def philox_user_permutation(num_users, seed, epoch):
-    """Epoch user order of the device path: stable argsort of one Philox word per user."""
-    u = np.arange(num_users, dtype=np.uint64)
-    w = philox4x32(u & _MASK, u >> np.uint64(32), np.full(num_users, epoch), STREAM_PERM,
-                   seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)[0]
-    return np.argsort(w, kind="stable").astype(np.int64), w
+def feistel_user_permutation(num_users, seed, epoch):
+    """Epoch user order of the device path (fvx_epoch_perm): perm[p] = user at position p.
+
+    A 4-round Feistel network over 2h bits (h = ceil(bits(U) / 2), so 2^(2h) >= U) with the
+    round function F(R, r) = word 0 of Philox(ctr=(R, r, epoch, STREAM_PERM), key=seed) masked
+    to h bits, (L, R) <- (R, L ^ F(R, r)); positions that land outside [0, U) walk the cycle
+    again.  A bijection of [0, U) computed independently per position - no sort."""
+    bits = 1
+    while bits < 31 and (1 << bits) < num_users:
+        bits += 1
+    h = (bits + 1) // 2
+    mask = np.uint64((1 << h) - 1)
+    k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
+    x = np.arange(num_users, dtype=np.uint64)
+    out = np.empty(num_users, dtype=np.int64)
+    pending = np.arange(num_users)
+    while pending.size:
+        L, R = x[pending] >> np.uint64(h), x[pending] & mask
+        for r in range(4):
+            f = philox4x32(R, np.full(R.shape, r), np.full(R.shape, epoch), STREAM_PERM, k0, k1)[0]
+            L, R = R, L ^ (f.astype(np.uint64) & mask)
+        x[pending] = (L << np.uint64(h)) | R
+        ok = x[pending] < num_users
+        out[pending[ok]] = x[pending[ok]].astype(np.int64)
+        pending = pending[~ok]
+    return out
 
 
 def enumerate_epoch(row_ptr, col_file, perm):

@@ -109,8 +109,12 @@ def test_philox_known_answer():
 def test_philox_negatives_never_in_train_and_deterministic():
     U, I, tr, _, _, _ = tiny_dataset()
     row_ptr, col_file, col_sorted = csr(tr)
-    perm, _ = sampler.philox_user_permutation(U, seed=5, epoch=0)
+    perm = sampler.feistel_user_permutation(U, seed=5, epoch=0)
     assert sorted(perm.tolist()) == list(range(U))
+    for n in (1, 2, 3, 17, 1000, 4097):                      # a bijection for every domain size, every epoch
+        p0, p1 = sampler.feistel_user_permutation(n, 9, 0), sampler.feistel_user_permutation(n, 9, 1)
+        assert sorted(p0.tolist()) == list(range(n)) and sorted(p1.tolist()) == list(range(n))
+        assert n < 17 or (p0 != p1).any()
     users, pos = sampler.enumerate_epoch(row_ptr, col_file, perm)
     neg = sampler.philox_negatives(row_ptr, col_sorted, users, I, seed=5, offset=100)
     assert all(int(j) not in tr[int(u)] for u, j in zip(users, neg))
