@@ -195,30 +195,38 @@ class DataLoader(object):
             }
         return self._dev
 
-    def device_epoch(self, epoch, device="cuda:0"):
+    def device_epoch(self, epoch, device="cuda:0", out=None):
         """(user, pos, neg) int32 CUDA tensors of one whole epoch (N triples), generated on
         the device with no host synchronisation: Feistel/Philox user permutation ->
-        prefix sum of the list lengths -> CSR expansion with the negatives drawn in the same pass."""
+        prefix sum of the list lengths -> CSR expansion with the negatives drawn in the same
+        pass.  ``out``: optional (user, pos, neg) tensors of N elements to write into."""
         import torch
         from .. import _lib
         st = self.device_state(device)
         dv = torch.device(device)
         U, N = self.num_users, self.num_train
-        perm = torch.empty(U, dtype=torch.int32, device=dv)
-        lens = torch.empty(U, dtype=torch.int64, device=dv)
+        ws = st.get("epoch_ws")
+        if ws is None:
+            ws = st["epoch_ws"] = (torch.empty(U, dtype=torch.int32, device=dv),
+                                   torch.empty(U, dtype=torch.int64, device=dv),
+                                   torch.empty(U, dtype=torch.int64, device=dv))
+        perm, lens, offs_incl = ws
         _lib.call("fvx_epoch_perm", _lib.ptr(perm), _lib.ptr(lens), _lib.ptr(st["row_ptr"]), U, self.seed, epoch,
                   _lib.stream_ptr())
-        offs_incl = torch.cumsum(lens, 0)
-        users = torch.empty(N, dtype=torch.int32, device=dv)
-        pos = torch.empty(N, dtype=torch.int32, device=dv)
-        neg = torch.empty(N, dtype=torch.int32, device=dv)
+        torch.cumsum(lens, 0, out=offs_incl)
+        if out is None:
+            out = tuple(torch.empty(N, dtype=torch.int32, device=dv) for _ in range(3))
+        users, pos, neg = out
         _lib.call("fvx_epoch_triples", _lib.ptr(st["row_ptr"]), _lib.ptr(st["col_file"]), _lib.ptr(st["col_sorted"]),
                   _lib.ptr(perm), _lib.ptr(offs_incl), U, self.num_items, self.seed, epoch * N, _lib.ptr(users),
                   _lib.ptr(pos), _lib.ptr(neg), _lib.stream_ptr())
         return users, pos, neg
 
-    def next_triple_batch(self, device="cuda:0"):
-        """Iterator over ``(user, pos, neg)`` int32 CUDA tensors of ``batch_size`` triples."""
+    def next_triple_batch(self, device="cuda:0", reuse=True):
+        """Iterator over ``(user, pos, neg)`` int32 CUDA tensors of ``batch_size`` triples.
+        With the device sampler the batches are views into two alternating epoch buffers: a
+        batch stays valid until the epoch after the next one is generated (``reuse=False``
+        allocates a fresh buffer per epoch for callers that keep every batch)."""
         import torch
         B = self.params.batch_size
         total = self._total_triples()
@@ -231,16 +239,27 @@ class DataLoader(object):
             return
         if self.sampler != "device":
             raise ValueError("unknown sampler %r (host_ref | device)" % self.sampler)
-        carry, done, epoch = None, 0, 0
+        # two fixed buffers of N + B triples: the tail of one epoch that does not fill a batch is
+        # copied to the front of the other buffer and the next epoch is generated behind it, so
+        # batches are consecutive slices across epoch boundaries and nothing is allocated per epoch
+        N = self.num_train
+        dv = torch.device(device)
+        bufs = [tuple(torch.empty(N + B, dtype=torch.int32, device=dv) for _ in range(3)) for _ in range(2)]
+        done, epoch, carry = 0, 0, 0
+        prev, prev_s = None, 0
         while done < total:
-            cur = self.device_epoch(epoch, device)
+            if not reuse and epoch >= 2:
+                bufs[epoch & 1] = tuple(torch.empty(N + B, dtype=torch.int32, device=dv) for _ in range(3))
+            cur = bufs[epoch & 1]
+            if carry:
+                for c, x in zip(cur, prev):
+                    c[:carry].copy_(x[prev_s:prev_s + carry])
+            self.device_epoch(epoch, device, out=tuple(c[carry:carry + N] for c in cur))
             epoch += 1
-            if carry is not None:
-                cur = tuple(torch.cat([c, x]) for c, x in zip(carry, cur))
-            n_av = cur[0].numel()
+            n_av = carry + N
             s = 0
             while s + B <= n_av and done < total:
                 yield tuple(x[s:s + B] for x in cur)
                 s += B
                 done += B
-            carry = tuple(x[s:] for x in cur) if s < n_av else None
+            prev, prev_s, carry = cur, s, n_av - s
