@@ -1,29 +1,38 @@
 // Full-catalog top-k on the 5th-generation tensor cores (tcgen05 + TMEM + TMA).
 //
 // predict_all (BPRMF.py:85, VBPR.py:95-97) is the contraction
-//     S[u,i] = <[Gu|Tu|1][u,:], [Gi|theta|Bi+vbias][i,:]>
+//     S[u,i] = <[Gu|Tu|1|1][u,:], [Gi|theta|b_hi|b_lo][i,:]>,   b = Bi + vbias
 // and Evaluator.store_recommendation (Evaluator.py:231-237) wants, per user, the k best
 // non-train items.  The sweep below never writes S:
 //
-//   1. k_pack_users / k_pack_items   bf16 operands (K+d+1 padded to KP), fp32 row norms
-//   2. k_topk_tc (persistent, warp-specialised)
-//        warp 0  TMA producer : item tiles [256 x KP] -> 64B-swizzled smem ring
-//        warp 1  UMMA issuer  : D[128 x 256] (TMEM, fp32) = A_users[128 x KP] * B_items^T
-//        warps 2-5 epilogue   : tcgen05.ld 32 columns at a time, one thread per user
-//                               row; a 3-input max tree tests the 32 scores against the
-//                               row's running threshold; survivors go to the row's
-//                               candidate list; a warp-cooperative radix select tightens
-//                               the threshold when the list fills up
-//   3. k_rescore_select              exact fp32 re-scoring of the candidates with the
-//                                    same fvx_score_one() the fp32 path uses, train-item
-//                                    mask, sort, top-k.
+//   1. k_pack_users / k_pack_items   bf16 operands (K+d+2 padded to KP), fp32 row norms;
+//                                    the item bias rides in two columns (bf16 hi + lo) so
+//                                    that it enters the score almost exactly
+//   2. k_topk_tc (persistent, warp-specialised, one CTA per SM)
+//        warp 0    TMA producer : item tiles [128 x KP] -> 64B-swizzled smem ring; the two
+//                                 user tiles [128 x KP] of the work unit
+//        warp 1    UMMA issuer  : D[ut][128 x 128] (TMEM, fp32) = A_ut * B_tile^T for both user
+//                                 tiles of the unit (the item tile is read from smem once for
+//                                 256 users), 4 accumulators = 2 user tiles x double buffer
+//        warps 2-9 epilogue     : one thread per user row (single owner): tcgen05.ld 32
+//                                 columns at a time (next chunk in flight while this one is
+//                                 tested), a 3-input max tree against the row's running
+//                                 threshold; survivors are appended to the row's candidate
+//                                 list; a warp-cooperative radix select tightens the threshold
+//                                 when the list grows past k + slack; thresholds are shared
+//                                 between the item splits of a row through global memory
+//   3. k_rescore_select              exact fp32 re-scoring of the surviving candidates with the
+//                                    same fvx_score_one() the fp32 path uses, train-item mask,
+//                                    sort, top-k.
 //
-// Exactness: bf16 rounding of both operands bounds |s_bf16 - s_fp32| by
-// eps_u = 1.01 * 2^-7 * |a_u| * max_i |b_i| (Cauchy-Schwarz).  A row keeps every item with
-// s_bf16 >= tau - 2*eps_u, tau = the k-th best bf16 score among its non-train items so
-// far, so the true top-k is always among the candidates and the output equals the fp32
-// kernel's bit for bit.  If a row's list overflows (more than CAP items inside the
-// margin) the row is flagged and the caller re-runs it through the fp32 kernel.
+// Exactness: with a = [Gu|Tu][u], b = [Gi|theta][i] rounded to bf16 (relative error 2^-9 each)
+//   |s_bf16 - s_fp32| <= eps_u = 1.002 * 2^-8 * |a| * max_i|b_i|              (Cauchy-Schwarz)
+//                              + 2^-17 * max_i|bias_i|                         (hi+lo residual)
+//                              + KP * 2^-21 * (|a| * max|b| + max|bias|)       (fp32 accumulation)
+// A row keeps every item with s_bf16 >= tau - 2*eps_u, tau = the (k + #train items)-th best bf16
+// score seen so far (a lower bound of the k-th best over the non-train items), so the true top-k
+// is always among the candidates and the output equals the fp32 kernel's bit for bit.  A row whose
+// list overflows is flagged and the caller re-runs it through the fp32 kernel.
 #include <cuda_bf16.h>
 #include <math_constants.h>
 
@@ -32,22 +41,27 @@
 #include "fvx_tc.cuh"
 
 #define TCK_BM 128          // users per tile  (UMMA M)
-#define TCK_BN 256          // items per tile  (UMMA N)
+#define TCK_BN 128          // items per tile  (UMMA N)
 #define TCK_KB 32           // bf16 elements per K block (64-byte swizzle rows)
 #define TCK_CAP 512         // candidate slots per (user, split)
-#define TCK_THREADS 192
+#define TCK_SLACK 96        // a list is compacted once it holds k + #train + TCK_SLACK entries
+#define TCK_THREADS 320     // warp 0 producer, warp 1 UMMA, warps 2-9 epilogue
+#define TCK_RS_MAX 512      // candidates per user the final selection can take
 #define KEY_PAD 0xFFFFFFFFFFFFFFFFull
 
-__device__ __forceinline__ unsigned long long tck_key(float s, int32_t id) {
+// order-preserving float <-> uint (ascending uint == ascending float)
+__device__ __forceinline__ uint32_t tck_mono(float s) {
   const uint32_t b = __float_as_uint(s);
-  const uint32_t mono = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
-  return ((unsigned long long)(~mono) << 32) | (uint32_t)id;
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
-__device__ __forceinline__ float tck_score_of_hi(uint32_t hi) {
-  const uint32_t mono = ~hi;
-  const uint32_t b = (mono & 0x80000000u) ? (mono ^ 0x80000000u) : ~mono;
-  return __uint_as_float(b);
+__device__ __forceinline__ float tck_unmono(uint32_t m) {
+  return __uint_as_float((m & 0x80000000u) ? (m ^ 0x80000000u) : ~m);
 }
+// list key: ascending key == descending score, then ascending item id
+__device__ __forceinline__ unsigned long long tck_key(float s, int32_t id) {
+  return ((unsigned long long)(~tck_mono(s)) << 32) | (uint32_t)id;
+}
+__device__ __forceinline__ float tck_score_of_hi(uint32_t hi) { return tck_unmono(~hi); }
 __device__ __forceinline__ float max3(float a, float b, float c) {
   float r;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
@@ -56,7 +70,7 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
 
 // ---------------------------------------------------------------------------------
 __global__ void k_pack_users(FvxModel M, int u0, int u1, __nv_bfloat16* __restrict__ A, float* __restrict__ unorm,
-                             int KP) {
+                             uint32_t* __restrict__ thr_g, int KP) {
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   const int kd = M.K + M.d;
@@ -64,37 +78,51 @@ __global__ void k_pack_users(FvxModel M, int u0, int u1, __nv_bfloat16* __restri
     const float* src = M.users.w + (size_t)u * M.users.stride;
     float sq = 0.0f;
     for (int c = lane; c < KP; c += 32) {
-      const float v = c < kd ? src[c] : (c == kd ? 1.0f : 0.0f);
-      sq += v * v;
+      float v = 0.0f;
+      if (c < kd) { v = src[c]; sq += v * v; }
+      else if (c == kd || c == kd + 1) v = 1.0f;       // multiplies bias_hi and bias_lo
       A[(size_t)(u - u0) * KP + c] = __float2bfloat16_rn(v);
     }
     sq = fvx_warp_sum(sq);
-    if (lane == 0) unorm[u - u0] = sqrtf(sq);
+    if (lane == 0) {
+      unorm[u - u0] = sqrtf(sq);
+      thr_g[u - u0] = tck_mono(-CUDART_INF_F);
+    }
   }
 }
 
+// stat[0] = max |[Gi|theta]| (as uint bits of a non-negative float), stat[1] = max |bias|
 __global__ void k_pack_items(FvxModel M, const float* __restrict__ theta, __nv_bfloat16* __restrict__ Bm,
-                             uint32_t* __restrict__ bmax_bits, int KP) {
+                             uint32_t* __restrict__ stat, int KP) {
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   const int K = M.K, d = M.d, kd = K + d;
-  float wmax = 0.0f;
+  float wmax = 0.0f, bmax = 0.0f;
   for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < M.item_cnt; i += warps) {
     const float* row = M.items.w + (size_t)i * M.items.stride;
     const float* th = d > 0 ? theta + (size_t)i * M.de : nullptr;
+    const float bias = row[K] + (d > 0 ? th[d] : 0.0f);
+    const __nv_bfloat16 bh = __float2bfloat16_rn(bias);
+    const __nv_bfloat16 bl = __float2bfloat16_rn(bias - __bfloat162float(bh));
     float sq = 0.0f;
     for (int c = lane; c < KP; c += 32) {
-      float v = 0.0f;
-      if (c < K) v = row[c];
-      else if (c < kd) v = th[c - K];
-      else if (c == kd) v = row[K] + (d > 0 ? th[d] : 0.0f);
-      sq += v * v;
-      Bm[(size_t)i * KP + c] = __float2bfloat16_rn(v);
+      __nv_bfloat16 o = __float2bfloat16_rn(0.0f);
+      if (c < kd) {
+        const float v = c < K ? row[c] : th[c - K];
+        sq += v * v;
+        o = __float2bfloat16_rn(v);
+      } else if (c == kd) o = bh;
+      else if (c == kd + 1) o = bl;
+      Bm[(size_t)i * KP + c] = o;
     }
     sq = fvx_warp_sum(sq);
     wmax = fmaxf(wmax, sqrtf(sq));
+    bmax = fmaxf(bmax, fabsf(bias));
   }
-  if (lane == 0) atomicMax(bmax_bits, __float_as_uint(wmax));   // non-negative floats order like uints
+  if (lane == 0) {   // non-negative floats order like uints
+    atomicMax(stat, __float_as_uint(wmax));
+    atomicMax(stat + 1, __float_as_uint(bmax));
+  }
 }
 
 // ---------------------------------------------------------------------------------
@@ -103,68 +131,103 @@ struct TckParams {
   int item_cnt, item_lo;
   int nkb;              // K blocks of 32
   int stages;
-  int splits, tiles_per_split, n_item_tiles, n_user_tiles;
+  int splits, tiles_per_split, n_item_tiles, n_pairs;
   int k;
   int u0;
+  float acc_c;          // KP * 2^-21: fp32 accumulation error per unit of magnitude
   const float* unorm;
-  const uint32_t* bmax_bits;
+  const uint32_t* stat; // [0] max item norm, [1] max |bias|  (float bits)
   const int64_t* mask_row_ptr;
-  const int32_t* mask_col;
   unsigned long long* cand;   // [n_users * splits * CAP]
   int32_t* ccount;            // [n_users * splits]
   int32_t* flags;             // [n_users]
+  uint32_t* thr_g;            // [n_users] best known row threshold (tck_mono encoding), shared by the splits
 };
 
 // warp-cooperative: tighten the threshold of lane `L`'s row and prune its candidate list
 __device__ __forceinline__ void tck_compact_row(const TckParams& P, int L, int lane, int my_row, int split,
-                                                float my_margin, int& cnt, float& thr) {
+                                                float my_margin, int my_kk, int& cnt, float& thr) {
   const int row = __shfl_sync(0xffffffffu, my_row, L);
   const int n = __shfl_sync(0xffffffffu, cnt, L);
+  const int kk = __shfl_sync(0xffffffffu, my_kk, L);
   const float margin = __shfl_sync(0xffffffffu, my_margin, L);
+  const float old_thr = __shfl_sync(0xffffffffu, thr, L);
   unsigned long long* buf = P.cand + ((size_t)row * P.splits + split) * TCK_CAP;
-  const int gu = P.u0 + row;
-  const long long mlo = P.mask_row_ptr[gu], mhi = P.mask_row_ptr[gu + 1];
-  unsigned long long e[TCK_CAP / 32];
+  // The train-item mask is NOT consulted here: the (k + #train items)-th best score over ALL
+  // items is a lower bound of the k-th best over the non-train items.  k_rescore_select applies
+  // the mask exactly.
+  uint32_t e[TCK_CAP / 32];
+  uint32_t kmin = 0xFFFFFFFFu, kmax = 0u;
 #pragma unroll
   for (int q = 0; q < TCK_CAP / 32; ++q) {
     const int idx = q * 32 + lane;
-    unsigned long long key = idx < n ? buf[idx] : KEY_PAD;
-    if (key != KEY_PAD && fvx_in_sorted(P.mask_col, mlo, mhi, (int32_t)(key & 0xFFFFFFFFu))) key = KEY_PAD;
-    e[q] = key;
+    e[q] = idx < n ? (uint32_t)(buf[idx] >> 32) : 0xFFFFFFFFu;
+    if (idx < n) { kmin = min(kmin, e[q]); kmax = max(kmax, e[q]); }
   }
-  int valid = 0;
-#pragma unroll
-  for (int q = 0; q < TCK_CAP / 32; ++q) valid += (e[q] != KEY_PAD) ? 1 : 0;
-  valid = __reduce_add_sync(0xffffffffu, valid);
-  float new_thr = -CUDART_INF_F;
-  if (valid >= P.k) {
-    // smallest 32-bit score key T with #(hi32 <= T) >= k  == key of the k-th best score
-    uint32_t lo = 0u, hi = 0xFFFFFFFEu;
+  float new_thr = fmaxf(old_thr, tck_unmono(__ldcg(P.thr_g + row)));
+  if (n >= kk) {
+    // a 32-bit score key T with  kk <= #(key <= T) <= kk + 8  (or exactly the kk-th best)
+    uint32_t lo = __reduce_min_sync(0xffffffffu, kmin), hi = __reduce_max_sync(0xffffffffu, kmax);
     while (lo < hi) {
       const uint32_t mid = lo + ((hi - lo) >> 1);
       int c = 0;
 #pragma unroll
-      for (int q = 0; q < TCK_CAP / 32; ++q) c += ((uint32_t)(e[q] >> 32) <= mid) ? 1 : 0;
+      for (int q = 0; q < TCK_CAP / 32; ++q) c += (e[q] <= mid) ? 1 : 0;
       c = __reduce_add_sync(0xffffffffu, c);
-      if (c >= P.k) hi = mid; else lo = mid + 1;
+      if (c >= kk) { hi = mid; if (c <= kk + 8) break; } else lo = mid + 1;
     }
-    new_thr = tck_score_of_hi(lo) - margin;
+    new_thr = fmaxf(new_thr, tck_score_of_hi(hi) - margin);
   }
+  const uint32_t cut = ~tck_mono(new_thr);          // keep keys <= cut  <=>  score >= new_thr
   int out = 0;
-  __syncwarp();
 #pragma unroll
   for (int q = 0; q < TCK_CAP / 32; ++q) {
-    const bool keep = e[q] != KEY_PAD && tck_score_of_hi((uint32_t)(e[q] >> 32)) >= new_thr;
+    const int idx = q * 32 + lane;
+    const bool keep = idx < n && e[q] <= cut;
+    const unsigned long long full = keep ? buf[idx] : 0ull;
+    __syncwarp();
     const uint32_t b = __ballot_sync(0xffffffffu, keep);
-    if (keep) buf[out + __popc(b & ((1u << lane) - 1u))] = e[q];
+    if (keep) buf[out + __popc(b & ((1u << lane) - 1u))] = full;
     out += __popc(b);
   }
   __syncwarp();
-  if (out > TCK_CAP - 64) {          // too many items inside the margin: row is re-run in fp32
+  if (out > TCK_CAP - 40) {            // too many items inside the margin: row is re-run in fp32
     if (lane == 0) P.flags[row] = 1;
-    out = TCK_CAP - 64;
+    out = TCK_CAP - 40;
   }
-  if (lane == L) { cnt = out; thr = new_thr; }
+  if (lane == L) {
+    cnt = out;
+    thr = new_thr;
+    atomicMax(P.thr_g + row, tck_mono(new_thr));
+  }
+}
+
+// one 32-column chunk of one row: group maxima first, then only the groups that can hold a survivor
+__device__ __forceinline__ void tck_scan_chunk(const uint32_t (&v)[32], float thr, int ibase, int item_cnt,
+                                               int item_lo, unsigned long long* buf, int& cnt) {
+  float g[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float a0 = max3(__uint_as_float(v[8 * q]), __uint_as_float(v[8 * q + 1]), __uint_as_float(v[8 * q + 2]));
+    const float a1 = max3(__uint_as_float(v[8 * q + 3]), __uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5]));
+    g[q] = max3(a0, a1, fmaxf(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7])));
+  }
+  const float m = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
+  if (m >= thr) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (g[q] >= thr) {
+#pragma unroll
+        for (int j = 8 * q; j < 8 * q + 8; ++j) {
+          const float s = __uint_as_float(v[j]);
+          if (s >= thr && ibase + j < item_cnt && cnt < TCK_CAP) {
+            buf[cnt] = tck_key(s, item_lo + ibase + j);
+            ++cnt;
+          }
+        }
+      }
+    }
+  }
 }
 
 __global__ void __launch_bounds__(TCK_THREADS, 1)
@@ -173,24 +236,24 @@ k_topk_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   // swizzled TMA / UMMA tiles need their base aligned to the swizzle repeat: round up by hand
   uint8_t* smem = smem_raw + ((1024u - (tc_smem_u32(smem_raw) & 1023u)) & 1023u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t a_bytes = (uint32_t)P.nkb * TCK_BM * 64u;
+  const uint32_t a_bytes = (uint32_t)P.nkb * TCK_BM * 64u;      // one user tile
   const uint32_t b_bytes = (uint32_t)P.nkb * TCK_BN * 64u;
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + a_bytes;
+  uint8_t* sA = smem;                                            // [2][a_bytes]
+  uint8_t* sB = smem + 2 * a_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)P.stages * b_bytes);
   uint64_t* full_b = bars;                  // [stages]
   uint64_t* empty_b = bars + P.stages;      // [stages]
   uint64_t* a_full = bars + 2 * P.stages;   // [1]
   uint64_t* a_empty = a_full + 1;           // [1]
-  uint64_t* t_full = a_empty + 1;           // [2]
-  uint64_t* t_empty = t_full + 2;           // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+  uint64_t* t_full = a_empty + 1;           // [4]  accumulator = ut * 2 + buffer
+  uint64_t* t_empty = t_full + 4;           // [4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 4);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < P.stages; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
     mbar_init(a_full, 1);
     mbar_init(a_empty, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 4); }
+    for (int s = 0; s < 4; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 4); }
     mbar_fence_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -200,18 +263,20 @@ k_topk_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int n_units = P.n_user_tiles * P.splits;
+  const int n_units = P.n_pairs * P.splits;
 
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
       uint32_t stage = 0, phase = 0, unit_i = 0;
       for (int w = blockIdx.x; w < n_units; w += gridDim.x, ++unit_i) {
-        const int ut = w / P.splits, sp = w - ut * P.splits;
+        const int pair = w / P.splits, sp = w - pair * P.splits;
         mbar_wait(a_empty, (unit_i & 1) ^ 1);
-        mbar_expect_tx(a_full, a_bytes);
-        for (int kb = 0; kb < P.nkb; ++kb)
-          tma_load_2d(sA + (size_t)kb * TCK_BM * 64, &tmA, a_full, kb * TCK_KB, ut * TCK_BM);
+        mbar_expect_tx(a_full, 2 * a_bytes);
+        for (int ut = 0; ut < 2; ++ut)
+          for (int kb = 0; kb < P.nkb; ++kb)
+            tma_load_2d(sA + (size_t)ut * a_bytes + (size_t)kb * TCK_BM * 64, &tmA, a_full, kb * TCK_KB,
+                        (pair * 2 + ut) * TCK_BM);
         const int t0 = sp * P.tiles_per_split;
         const int t1 = min(P.n_item_tiles, t0 + P.tiles_per_split);
         for (int t = t0; t < t1; ++t) {
@@ -228,92 +293,106 @@ k_topk_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     // ===== UMMA issuer (one elected thread) =====
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(TCK_BM, TCK_BN, 0, 0);
-      uint32_t stage = 0, phase = 0, unit_i = 0, acc = 0, acc_phase = 0;
+      uint32_t stage = 0, phase = 0, unit_i = 0, buf = 0, buf_phase = 0;
       for (int w = blockIdx.x; w < n_units; w += gridDim.x, ++unit_i) {
         const int sp = w % P.splits;
         mbar_wait(a_full, unit_i & 1);
         const int t0 = sp * P.tiles_per_split;
         const int t1 = min(P.n_item_tiles, t0 + P.tiles_per_split);
         for (int t = t0; t < t1; ++t) {
-          mbar_wait(&t_empty[acc], acc_phase ^ 1);
           mbar_wait(&full_b[stage], phase);
           tc_fence_after();
-          const uint32_t a0 = tc_smem_u32(sA), b0 = tc_smem_u32(sB + (size_t)stage * b_bytes);
-          const uint32_t d = tmem_base + acc * TCK_BN;
-          for (int kb = 0; kb < P.nkb; ++kb) {
+          const uint32_t b0 = tc_smem_u32(sB + (size_t)stage * b_bytes);
+          for (int ut = 0; ut < 2; ++ut) {
+            const uint32_t acc = ut * 2 + buf;
+            mbar_wait(&t_empty[acc], buf_phase ^ 1);
+            tc_fence_after();
+            const uint32_t a0 = tc_smem_u32(sA + (size_t)ut * a_bytes);
+            const uint32_t d = tmem_base + acc * TCK_BN;
+            for (int kb = 0; kb < P.nkb; ++kb) {
 #pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-              const uint64_t ad = umma_smem_desc(a0 + kb * TCK_BM * 64 + ks * 32, 16, 512, TC_SWZ_64B);
-              const uint64_t bd = umma_smem_desc(b0 + kb * TCK_BN * 64 + ks * 32, 16, 512, TC_SWZ_64B);
-              umma_f16(d, ad, bd, idesc, (kb | ks) ? 1u : 0u);
+              for (int ks = 0; ks < 2; ++ks) {
+                const uint64_t ad = umma_smem_desc(a0 + kb * TCK_BM * 64 + ks * 32, 16, 512, TC_SWZ_64B);
+                const uint64_t bd = umma_smem_desc(b0 + kb * TCK_BN * 64 + ks * 32, 16, 512, TC_SWZ_64B);
+                umma_f16(d, ad, bd, idesc, (kb | ks) ? 1u : 0u);
+              }
             }
+            umma_commit(&t_full[acc]);     // accumulator ready for its epilogue warps
           }
           umma_commit(&empty_b[stage]);    // smem stage may be refilled once these UMMAs retire
-          umma_commit(&t_full[acc]);       // accumulator ready for the epilogue
           if (++stage == (uint32_t)P.stages) { stage = 0; phase ^= 1; }
-          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+          if (++buf == 2) { buf = 0; buf_phase ^= 1; }
         }
-        umma_commit(a_empty);              // user tile may be overwritten
+        umma_commit(a_empty);              // user tiles may be overwritten
       }
     }
   } else {
-    // ===== epilogue: one thread per user row =====
-    const int quad = warp & 3;
-    const float bmax = __uint_as_float(*P.bmax_bits);
-    uint32_t acc = 0, acc_phase = 0;
+    // ===== epilogue: warps 2-5 own user tile 0, warps 6-9 user tile 1; thread = user row =====
+    const int ew = warp - 2;
+    const int ut = ew >> 2;
+    const int quad = warp & 3;            // TMEM lanes this warp may read: [32*quad, 32*quad+32)
+    const int rit = quad * 32 + lane;     // row in tile
+    const float bmax = __uint_as_float(P.stat[0]), biasmax = __uint_as_float(P.stat[1]);
+    uint32_t buf = 0, buf_phase = 0;
     for (int w = blockIdx.x; w < n_units; w += gridDim.x) {
-      const int ut = w / P.splits, sp = w - ut * P.splits;
-      const int row = ut * TCK_BM + quad * 32 + lane;
+      const int pair = w / P.splits, sp = w - pair * P.splits;
+      const int row = (pair * 2 + ut) * TCK_BM + rit;
       const bool live = row < P.n_users;
-      const float margin = live ? 2.0f * 1.01f * 0.0078125f * P.unorm[row] * bmax + 1e-30f : 0.0f;
+      float margin = 0.0f;
+      int kk = P.k;
+      if (live) {
+        const float an = P.unorm[row];
+        const float eps = 1.002f * 0.00390625f * an * bmax + 7.6294e-6f * biasmax + P.acc_c * (an * bmax + biasmax);
+        margin = 2.0f * eps + 1e-30f;
+        const int gu = P.u0 + row;
+        kk = P.k + (int)(P.mask_row_ptr[gu + 1] - P.mask_row_ptr[gu]);
+        if (kk > TCK_CAP - TCK_SLACK - 40) {   // cannot bound this row's list: exact fp32 sweep instead
+          kk = TCK_CAP - TCK_SLACK - 40;
+          P.flags[row] = 1;
+        }
+      }
+      const int trig = kk + TCK_SLACK;
       float thr = live ? -CUDART_INF_F : CUDART_INF_F;
       int cnt = 0;
-      unsigned long long* buf = P.cand + ((size_t)(live ? row : 0) * P.splits + sp) * TCK_CAP;
+      unsigned long long* lbuf = P.cand + ((size_t)(live ? row : 0) * P.splits + sp) * TCK_CAP;
       const int t0 = sp * P.tiles_per_split;
       const int t1 = min(P.n_item_tiles, t0 + P.tiles_per_split);
       for (int t = t0; t < t1; ++t) {
-        mbar_wait(&t_full[acc], acc_phase);
+        const uint32_t acc = ut * 2 + buf;
+        if (live) thr = fmaxf(thr, tck_unmono(__ldcg(P.thr_g + row)));   // bounds found by the row's other splits (L2)
+        mbar_wait(&t_full[acc], buf_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TCK_BN;
         const int item0 = t * TCK_BN;
-#pragma unroll 1
-        for (int c = 0; c < TCK_BN / 32; ++c) {
-          uint32_t v[32];
-          tmem_ld_32x32(taddr + c * 32, v);
+        uint32_t va[32], vb[32];
+        tmem_ld_32x32(taddr, va);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
           tmem_ld_wait();
-          float m = max3(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]));
-#pragma unroll
-          for (int j = 3; j < 31; j += 2) m = max3(m, __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
-          m = fmaxf(m, __uint_as_float(v[31]));
-          if (m >= thr) {
-            const int ibase = item0 + c * 32;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float s = __uint_as_float(v[j]);
-              if (s >= thr && ibase + j < P.item_cnt && cnt < TCK_CAP) {
-                buf[cnt] = tck_key(s, P.item_lo + ibase + j);
-                ++cnt;
-              }
-            }
-          }
-          uint32_t need = __ballot_sync(0xffffffffu, cnt > TCK_CAP - 32);
+          // next chunk in flight while this one is tested
+          if (c == 0) tmem_ld_32x32(taddr + 32, vb);
+          if (c == 1) tmem_ld_32x32(taddr + 64, va);
+          if (c == 2) tmem_ld_32x32(taddr + 96, vb);
+          if ((c & 1) == 0) tck_scan_chunk(va, thr, item0 + c * 32, P.item_cnt, P.item_lo, lbuf, cnt);
+          else tck_scan_chunk(vb, thr, item0 + c * 32, P.item_cnt, P.item_lo, lbuf, cnt);
+          uint32_t need = __ballot_sync(0xffffffffu, cnt >= trig);
           while (need) {
             const int L = __ffs(need) - 1;
             need &= need - 1;
-            tck_compact_row(P, L, lane, row, sp, margin, cnt, thr);
+            tck_compact_row(P, L, lane, row, sp, margin, kk, cnt, thr);
           }
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&t_empty[acc]);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (++buf == 2) { buf = 0; buf_phase ^= 1; }
       }
-      // final prune of every live row, then publish the list length
-      uint32_t need = __ballot_sync(0xffffffffu, live);
+      // publish this split's bound for the rows that hold at least kk candidates, then the length
+      uint32_t need = __ballot_sync(0xffffffffu, live && cnt >= kk);
       while (need) {
         const int L = __ffs(need) - 1;
         need &= need - 1;
-        tck_compact_row(P, L, lane, row, sp, margin, cnt, thr);
+        tck_compact_row(P, L, lane, row, sp, margin, kk, cnt, thr);
       }
       if (live) P.ccount[(size_t)row * P.splits + sp] = cnt;
     }
@@ -345,37 +424,56 @@ __device__ __forceinline__ void rs_bitonic(unsigned long long* keys, int n, int 
 __global__ void __launch_bounds__(RS_WARPS * 32)
 k_rescore_select(FvxModel M, const float* __restrict__ theta, int u0, int n_users, int splits,
                  const unsigned long long* __restrict__ cand, const int32_t* __restrict__ ccount,
-                 const int64_t* __restrict__ mask_row_ptr, const int32_t* __restrict__ mask_col, int k, int npad,
+                 const uint32_t* __restrict__ thr_g, int32_t* __restrict__ flags,
+                 const int64_t* __restrict__ mask_row_ptr, const int32_t* __restrict__ mask_col, int k,
                  int32_t* __restrict__ out_ids, float* __restrict__ out_scores) {
-  extern __shared__ __align__(16) unsigned char rs_smem[];
+  __shared__ unsigned long long rs_keys[RS_WARPS][TCK_RS_MAX];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  unsigned long long* kk = reinterpret_cast<unsigned long long*>(rs_smem) + (size_t)warp * npad;
+  unsigned long long* kk = rs_keys[warp];
   for (int r = blockIdx.x * RS_WARPS + warp; r < n_users; r += gridDim.x * RS_WARPS) {
     const int gu = u0 + r;
     const float* urow = M.users.w + (size_t)gu * M.users.stride;
     const long long mlo = mask_row_ptr[gu], mhi = mask_row_ptr[gu + 1];
+    // survivors of the row's final bound (already includes the rounding margin)
+    const uint32_t cut = ~thr_g[r];
     int total = 0;
     for (int sp = 0; sp < splits; ++sp) {
       const int n = ccount[(size_t)r * splits + sp];
       const unsigned long long* src = cand + ((size_t)r * splits + sp) * TCK_CAP;
-      for (int i = lane; i < n; i += 32) {
-        const int32_t gid = (int32_t)(src[i] & 0xFFFFFFFFu);
-        unsigned long long key = KEY_PAD;
-        if (!fvx_in_sorted(mask_col, mlo, mhi, gid)) {
-          const int32_t li = gid - M.item_lo;
-          const float* th = M.d > 0 ? theta + (size_t)li * M.de : nullptr;
-          const float s = fvx_score_one(urow, M.items.w + (size_t)li * M.items.stride, th, M.K, M.d);
-          key = tck_key(s, gid);
-        }
-        kk[total + i] = key;
+      for (int i0 = 0; i0 < n; i0 += 32) {
+        const int i = i0 + lane;
+        const unsigned long long key = i < n ? src[i] : KEY_PAD;
+        const bool keep = i < n && (uint32_t)(key >> 32) <= cut;
+        const uint32_t b = __ballot_sync(0xffffffffu, keep);
+        const int pos = total + __popc(b & ((1u << lane) - 1u));
+        if (keep && pos < TCK_RS_MAX) kk[pos] = key;
+        total += __popc(b);
       }
-      total += n;
     }
+    if (total > TCK_RS_MAX) {
+      if (lane == 0) flags[r] = 1;
+      total = TCK_RS_MAX;
+    }
+    __syncwarp();
+    // exact fp32 scores (the fp32 kernel's arithmetic) and the train mask
+    for (int i = lane; i < total; i += 32) {
+      const int32_t gid = (int32_t)(kk[i] & 0xFFFFFFFFu);
+      unsigned long long key = KEY_PAD;
+      if (!fvx_in_sorted(mask_col, mlo, mhi, gid)) {
+        const int32_t li = gid - M.item_lo;
+        const float* th = M.d > 0 ? theta + (size_t)li * M.de : nullptr;
+        const float s = fvx_score_one(urow, M.items.w + (size_t)li * M.items.stride, th, M.K, M.d);
+        key = tck_key(s, gid);
+      }
+      kk[i] = key;
+    }
+    int npad = 32;
+    while (npad < total) npad <<= 1;
     for (int i = total + lane; i < npad; i += 32) kk[i] = KEY_PAD;
     __syncwarp();
     rs_bitonic(kk, npad, lane);
     for (int i = lane; i < k; i += 32) {
-      const bool ok = kk[i] != KEY_PAD;
+      const bool ok = i < npad && kk[i] != KEY_PAD;
       out_ids[(size_t)r * k + i] = ok ? (int32_t)(kk[i] & 0xFFFFFFFFu) : -1;
       out_scores[(size_t)r * k + i] = ok ? tck_score_of_hi((uint32_t)(kk[i] >> 32)) : -CUDART_INF_F;
     }
@@ -417,13 +515,15 @@ extern "C" {
 
 int fvx_eval_ws_query(const FvxModel* model, int32_t n_users, FvxEvalWs* ws) {
   FVX_CHECK_ARG(model && ws && n_users > 0, "fvx_eval_ws_query: bad arguments");
-  const int kd1 = model->K + model->d + 1;
-  const int KP = (kd1 + TCK_KB - 1) / TCK_KB * TCK_KB;
-  const int n_user_tiles = (n_users + TCK_BM - 1) / TCK_BM;
-  int splits = (2 * fvx_num_sms() + n_user_tiles - 1) / n_user_tiles;
+  const int kd2 = model->K + model->d + 2;
+  const int KP = (kd2 + TCK_KB - 1) / TCK_KB * TCK_KB;
+  const int n_pairs = (n_users + 2 * TCK_BM - 1) / (2 * TCK_BM);
   const int n_item_tiles = (model->item_cnt + TCK_BN - 1) / TCK_BN;
-  if (splits > 4) splits = 4;
-  if (splits > n_item_tiles) splits = n_item_tiles;
+  // work units = user-tile pairs x item splits; aim at >= 4 units per SM to keep the tail short
+  // (the splits of a row share their thresholds, so a split costs little extra candidate traffic)
+  int splits = (4 * fvx_num_sms() + n_pairs - 1) / n_pairs;
+  if (splits > 8) splits = 8;
+  if (splits > n_item_tiles / 8) splits = n_item_tiles / 8;
   if (splits < 1) splits = 1;
   ws->KP = KP;
   ws->splits = splits;
@@ -445,21 +545,22 @@ int fvx_score_topk_tc(const FvxModel* model, const float* theta_ext, int32_t u0,
   fvx_eval_ws_query(model, n_users, &q);
   FVX_CHECK_ARG(ws->KP == q.KP && ws->splits == q.splits && ws->cap == TCK_CAP && ws->u_cap >= n_users &&
                 ws->i_cap >= model->item_cnt, "fvx_score_topk_tc: workspace does not match fvx_eval_ws_query");
-  FVX_CHECK_ARG(ws->A && ws->Bm && ws->unorm && ws->bmax && ws->cand && ws->ccount && ws->flags,
+  FVX_CHECK_ARG(ws->A && ws->Bm && ws->unorm && ws->stat && ws->cand && ws->ccount && ws->flags && ws->thr,
                 "fvx_score_topk_tc: null workspace buffer");
   const int KP = q.KP, nkb = KP / TCK_KB;
-  FVX_CHECK_ARG(KP <= 128, "fvx_score_topk_tc: K+d+1=%d too large for the tensor-core sweep (use fvx_score_topk)",
-                model->K + model->d + 1);
+  FVX_CHECK_ARG(KP <= 128, "fvx_score_topk_tc: K+d+2=%d too large for the tensor-core sweep (use fvx_score_topk)",
+                model->K + model->d + 2);
   cudaStream_t st = fvx_cu(stream);
 
-  cudaMemsetAsync(ws->bmax, 0, 4, st);
+  cudaMemsetAsync(ws->stat, 0, 8, st);
   cudaMemsetAsync(ws->flags, 0, sizeof(int32_t) * n_users, st);
   int g = (n_users * 32 + 255) / 256;
   if (g > fvx_num_sms() * 8) g = fvx_num_sms() * 8;
-  k_pack_users<<<g, 256, 0, st>>>(*model, u0, u1, reinterpret_cast<__nv_bfloat16*>(ws->A), ws->unorm, KP);
+  k_pack_users<<<g, 256, 0, st>>>(*model, u0, u1, reinterpret_cast<__nv_bfloat16*>(ws->A), ws->unorm,
+                                  reinterpret_cast<uint32_t*>(ws->thr), KP);
   g = fvx_num_sms() * 8;
   k_pack_items<<<g, 256, 0, st>>>(*model, theta_ext, reinterpret_cast<__nv_bfloat16*>(ws->Bm),
-                                  reinterpret_cast<uint32_t*>(ws->bmax), KP);
+                                  reinterpret_cast<uint32_t*>(ws->stat), KP);
   FVX_CHECK_LAUNCH("k_pack");
 
   CUtensorMap tmA, tmB;
@@ -469,43 +570,37 @@ int fvx_score_topk_tc(const FvxModel* model, const float* theta_ext, int32_t u0,
 
   TckParams P;
   P.n_users = n_users; P.item_cnt = model->item_cnt; P.item_lo = model->item_lo; P.nkb = nkb;
-  P.n_user_tiles = (n_users + TCK_BM - 1) / TCK_BM;
+  P.n_pairs = (n_users + 2 * TCK_BM - 1) / (2 * TCK_BM);
   P.n_item_tiles = (model->item_cnt + TCK_BN - 1) / TCK_BN;
   P.splits = q.splits;
   P.tiles_per_split = (P.n_item_tiles + P.splits - 1) / P.splits;
-  P.k = k; P.u0 = u0; P.unorm = ws->unorm; P.bmax_bits = reinterpret_cast<const uint32_t*>(ws->bmax);
-  P.mask_row_ptr = mask_row_ptr; P.mask_col = mask_col;
+  P.k = k; P.u0 = u0; P.unorm = ws->unorm; P.stat = reinterpret_cast<const uint32_t*>(ws->stat);
+  P.acc_c = (float)KP * 4.76837158e-7f;
+  P.mask_row_ptr = mask_row_ptr;
   P.cand = reinterpret_cast<unsigned long long*>(ws->cand); P.ccount = ws->ccount; P.flags = ws->flags;
+  P.thr_g = reinterpret_cast<uint32_t*>(ws->thr);
   const size_t a_bytes = (size_t)nkb * TCK_BM * 64, b_bytes = (size_t)nkb * TCK_BN * 64;
-  int stages = (int)((220 * 1024 - a_bytes) / b_bytes);
-  if (stages > 4) stages = 4;
+  int stages = (int)((200 * 1024 - 2 * a_bytes) / b_bytes);
+  if (stages > 6) stages = 6;
   FVX_CHECK_ARG(stages >= 2, "fvx_score_topk_tc: tile does not fit shared memory");
   P.stages = stages;
-  const size_t smem = a_bytes + stages * b_bytes + (2 * stages + 6) * 8 + 16 + 1024;
+  const size_t smem = 2 * a_bytes + stages * b_bytes + (2 * stages + 10) * 8 + 16 + 1024;
   static size_t configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(k_topk_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) FVX_FAIL(-3, "fvx_score_topk_tc: cannot set %zu B smem: %s", smem, cudaGetErrorString(e));
     configured = smem;
   }
-  int grid = P.n_user_tiles * P.splits;
+  int grid = P.n_pairs * P.splits;   // work units; persistent CTAs, one per SM
   if (grid > fvx_num_sms()) grid = fvx_num_sms();
   k_topk_tc<<<grid, TCK_THREADS, smem, st>>>(tmA, tmB, P);
   FVX_CHECK_LAUNCH("k_topk_tc");
 
-  int npad = 32;
-  while (npad < q.splits * TCK_CAP) npad <<= 1;
-  const size_t rs_smem = (size_t)RS_WARPS * npad * 8;
-  static bool rs_conf = false;
-  if (rs_smem > 48 * 1024 && !rs_conf) {
-    cudaFuncSetAttribute(k_rescore_select, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    rs_conf = true;
-  }
   long long rg = ((long long)n_users + RS_WARPS - 1) / RS_WARPS;
   if (rg > (long long)fvx_num_sms() * 8) rg = (long long)fvx_num_sms() * 8;
-  k_rescore_select<<<(int)rg, RS_WARPS * 32, rs_smem, st>>>(*model, theta_ext, u0, n_users, q.splits, P.cand,
-                                                            P.ccount, mask_row_ptr, mask_col, k, npad, out_ids,
-                                                            out_scores);
+  k_rescore_select<<<(int)rg, RS_WARPS * 32, 0, st>>>(*model, theta_ext, u0, n_users, q.splits, P.cand, P.ccount,
+                                                      P.thr_g, ws->flags, mask_row_ptr, mask_col, k, out_ids,
+                                                      out_scores);
   FVX_CHECK_LAUNCH("k_rescore_select");
   return 0;
 }

@@ -54,6 +54,7 @@ struct ProjFwdParams {
   int chunks;           // 64-feature chunks per split
   int n_tiles;          // 128-row tiles
   int stages;
+  int nacc;             // independent accumulators per buffer (one per UMMA K step of a chunk)
   float* out;           // [ksplit][nrows][NP]
 };
 
@@ -80,8 +81,10 @@ k_proj_fwd_tc(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant_
     mbar_fence_init();
     tma_prefetch_desc(&tmB_hi); tma_prefetch_desc(&tmB_lo);
   }
+  // A UMMA that accumulates into the columns its predecessor wrote waits for it; each K step of
+  // a chunk therefore owns its own accumulator and the epilogue adds them.
   uint32_t tcols = 32;
-  while (tcols < 2u * P.NP) tcols <<= 1;
+  while (tcols < 2u * P.nacc * P.NP) tcols <<= 1;
   if (warp == 4) tmem_alloc(tmem_slot, tcols);
   tc_fence_before();
   __syncthreads();
@@ -136,22 +139,24 @@ k_proj_fwd_tc(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant_
       for (int w = blockIdx.x; w < n_units; w += gridDim.x) {
         mbar_wait(&t_empty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d = tmem_base + acc * P.NP;
+        const uint32_t d0 = tmem_base + acc * P.nacc * P.NP;
         for (int c = 0; c < P.chunks; ++c) {
           mbar_wait(&full_b[stage], phase);
           fence_proxy_async_smem();           // cp.async (generic proxy) writes -> UMMA (async proxy) reads
           tc_fence_after();
           const uint32_t a_hi = tc_smem_u32(smem + (size_t)stage * stage_bytes);
           const uint32_t a_lo = a_hi + a_bytes, b_hi = a_lo + a_bytes, b_lo = b_hi + b_bytes;
+          // pass-major, K-step-minor: consecutive UMMAs target different accumulators
 #pragma unroll
-          for (int k = 0; k < PT_KC / 16; ++k) {
-            const uint64_t dah = umma_smem_desc(a_hi + k * 32, 16, 1024, TC_SWZ_128B);
-            const uint64_t dal = umma_smem_desc(a_lo + k * 32, 16, 1024, TC_SWZ_128B);
-            const uint64_t dbh = umma_smem_desc(b_hi + k * 32, 16, 1024, TC_SWZ_128B);
-            const uint64_t dbl = umma_smem_desc(b_lo + k * 32, 16, 1024, TC_SWZ_128B);
-            umma_f16(d, dah, dbh, idesc, (c | k) ? 1u : 0u);
-            umma_f16(d, dal, dbh, idesc, 1u);
-            umma_f16(d, dah, dbl, idesc, 1u);
+          for (int pass = 0; pass < 3; ++pass) {
+#pragma unroll
+            for (int k = 0; k < PT_KC / 16; ++k) {
+              const uint32_t d = d0 + (uint32_t)(k % P.nacc) * P.NP;
+              const uint64_t da = umma_smem_desc((pass == 1 ? a_lo : a_hi) + k * 32, 16, 1024, TC_SWZ_128B);
+              const uint64_t db = umma_smem_desc((pass == 2 ? b_lo : b_hi) + k * 32, 16, 1024, TC_SWZ_128B);
+              const bool first = c == 0 && pass == 0 && k < P.nacc;
+              umma_f16(d, da, db, idesc, first ? 0u : 1u);
+            }
           }
           umma_commit(&empty_b[stage]);
           if (++stage == (uint32_t)P.stages) { stage = 0; phase ^= 1; }
@@ -171,15 +176,18 @@ k_proj_fwd_tc(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant_
       tc_fence_after();
       float* dst = P.out + ((size_t)ks * P.nrows + (size_t)(row < P.nrows ? row : 0)) * P.NP;
       for (int n0 = 0; n0 < P.NP; n0 += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * P.NP + n0, v);
-        tmem_ld_wait();
+        float sum[32];
+        for (int a = 0; a < P.nacc; ++a) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (acc * P.nacc + a) * P.NP + n0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sum[j] = a == 0 ? __uint_as_float(v[j]) : sum[j] + __uint_as_float(v[j]);
+        }
         if (row < P.nrows) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(dst + n0 + j) =
-                make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                            __uint_as_float(v[j + 3]));
+            *reinterpret_cast<float4*>(dst + n0 + j) = make_float4(sum[j], sum[j + 1], sum[j + 2], sum[j + 3]);
         }
       }
       tc_fence_before();
@@ -302,18 +310,18 @@ k_grad_E_tc(const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ 
         tc_fence_after();
         const uint32_t a_hi = tc_smem_u32(smem + (size_t)stage * stage_bytes);
         const uint32_t a_lo = a_hi + a_bytes, w_hi = a_lo + a_bytes, w_lo = w_hi + w_bytes;
-        for (int mb = 0; mb < nmb; ++mb) {
-          const uint32_t d = tmem_base + mb * P.NP;
+        // (K step, pass)-major, M-block-minor: consecutive UMMAs target different accumulators
 #pragma unroll
-          for (int k = 0; k < GE_RT / 16; ++k) {
-            const uint32_t aoff = (uint32_t)(2 * mb) * chunk_bytes + k * 16 * 128;
-            const uint64_t dah = umma_smem_desc(a_hi + aoff, chunk_bytes, 1024, TC_SWZ_128B);
-            const uint64_t dal = umma_smem_desc(a_lo + aoff, chunk_bytes, 1024, TC_SWZ_128B);
-            const uint64_t dwh = umma_smem_desc(w_hi + k * 16 * wrow_bytes, watom_bytes, w_sbo, P.w_sw);
-            const uint64_t dwl = umma_smem_desc(w_lo + k * 16 * wrow_bytes, watom_bytes, w_sbo, P.w_sw);
-            umma_f16(d, dah, dwh, idesc, (t | k) ? 1u : 0u);
-            umma_f16(d, dal, dwh, idesc, 1u);
-            umma_f16(d, dah, dwl, idesc, 1u);
+        for (int k = 0; k < GE_RT / 16; ++k) {
+#pragma unroll
+          for (int pass = 0; pass < 3; ++pass) {
+            const uint64_t dw = umma_smem_desc((pass == 2 ? w_lo : w_hi) + k * 16 * wrow_bytes, watom_bytes, w_sbo,
+                                               P.w_sw);
+            for (int mb = 0; mb < nmb; ++mb) {
+              const uint32_t aoff = (uint32_t)(2 * mb) * chunk_bytes + k * 16 * 128;
+              const uint64_t da = umma_smem_desc((pass == 1 ? a_lo : a_hi) + aoff, chunk_bytes, 1024, TC_SWZ_128B);
+              umma_f16(tmem_base + mb * P.NP, da, dw, idesc, (t | k | pass) ? 1u : 0u);
+            }
           }
         }
         umma_commit(&empty_b[stage]);
@@ -433,6 +441,7 @@ int fvx_launch_project_tc(const FvxModel* m, const int32_t* rows, int row0, int6
   P.rows = rows; P.row0 = row0; P.nrows = nrows; P.NP = NP; P.ksplit = ksplit; P.chunks = chunks_total / ksplit;
   P.n_tiles = (int)((nrows + PT_BM - 1) / PT_BM);
   P.out = out;
+  P.nacc = 256 / NP < 4 ? (256 / NP < 1 ? 1 : 256 / NP) : 4;
   const size_t stage_bytes = 2 * PT_BM * 128 + 2 * (size_t)NP * 128;
   int stages = (int)((220 * 1024) / stage_bytes);
   if (stages > 6) stages = 6;

@@ -21,38 +21,43 @@
 //   m <- b1*m ; v <- b2*v ; w <- w - alpha_tau * m / (sqrt(v) + eps).
 // The loop is truncated after FVX_REPLAY_MAX iterations (the remaining updates are
 // below 2e-9 of the first one); m and v then take their closed-form decay.
-__device__ __forceinline__ void replay_row(const FvxTable& T, int32_t r, int32_t target, float lr, int lane) {
+// `nl` lanes (lane index li) cooperate on one row, 4 columns at a time.
+__device__ __forceinline__ void replay_row(const FvxTable& T, int32_t r, int32_t target, float lr, int li, int nl) {
   const int32_t last = T.last[r];
   const int32_t gap = target - last;
-  if (gap <= 0) return;
-  if (last > 0) {  // rows never updated have m = v = 0: nothing moves
+  if (gap > 0 && last > 0) {  // rows never updated have m = v = 0: nothing moves
     const int n = gap < FVX_REPLAY_MAX ? gap : FVX_REPLAY_MAX;
     const int rem = gap - n;
-    const float p1_0 = (float)pow(0.9, (double)(last + 1));
-    const float p2_0 = (float)pow(0.999, (double)(last + 1));
-    const float d1 = rem > 0 ? (float)pow(0.9, (double)rem) : 1.0f;
-    const float d2 = rem > 0 ? (float)pow(0.999, (double)rem) : 1.0f;
-    float* __restrict__ w = T.w + (size_t)r * T.stride;
-    float* __restrict__ m = T.m + (size_t)r * T.stride;
-    float* __restrict__ v = T.v + (size_t)r * T.stride;
-    for (int c = lane; c < T.stride; c += 32) {
-      float wc = w[c], mc = m[c], vc = v[c];
-      float p1 = p1_0, p2 = p2_0;
+    // q1 = 1 - b1^tau, q2 = 1 - b2^tau for tau = last+1, then q <- (1-b) + b*q (no cancellation)
+    const float q1_0 = (float)(-expm1((double)(last + 1) * -0.10536051565782628));    // ln 0.9
+    const float q2_0 = (float)(-expm1((double)(last + 1) * -0.0010005003335835335)); // ln 0.999
+    const float d1 = rem > 0 ? (float)exp((double)rem * -0.10536051565782628) : 1.0f;
+    const float d2 = rem > 0 ? (float)exp((double)rem * -0.0010005003335835335) : 1.0f;
+    float4* __restrict__ w = reinterpret_cast<float4*>(T.w + (size_t)r * T.stride);
+    float4* __restrict__ m = reinterpret_cast<float4*>(T.m + (size_t)r * T.stride);
+    float4* __restrict__ v = reinterpret_cast<float4*>(T.v + (size_t)r * T.stride);
+    for (int c = li; c < (T.stride >> 2); c += nl) {
+      float4 wc = w[c], mc = m[c], vc = v[c];
+      float q1 = q1_0, q2 = q2_0;
       for (int k = 0; k < n; ++k) {
-        const float a = lr * fvx_sqrt_approx(1.0f - p2) * fvx_rcp_approx(1.0f - p1);
-        mc *= FVX_BETA1;
-        vc *= FVX_BETA2;
-        wc -= a * mc * fvx_rcp_approx(fvx_sqrt_approx(vc) + FVX_EPS);
-        p1 *= FVX_BETA1;
-        p2 *= FVX_BETA2;
+        const float a = lr * fvx_sqrt_approx(q2) * fvx_rcp_approx(q1);
+#define FVX_RP1(f)                                                        \
+        mc.f *= FVX_BETA1;                                                \
+        vc.f *= FVX_BETA2;                                                \
+        wc.f -= a * mc.f * fvx_rcp_approx(fvx_sqrt_approx(vc.f) + FVX_EPS);
+        FVX_RP1(x) FVX_RP1(y) FVX_RP1(z) FVX_RP1(w)
+#undef FVX_RP1
+        q1 = fmaf(FVX_BETA1, q1, 1.0f - FVX_BETA1);
+        q2 = fmaf(FVX_BETA2, q2, 1.0f - FVX_BETA2);
       }
-      w[c] = wc;
-      m[c] = mc * d1;
-      v[c] = vc * d2;
+      mc.x *= d1; mc.y *= d1; mc.z *= d1; mc.w *= d1;
+      vc.x *= d2; vc.y *= d2; vc.z *= d2; vc.w *= d2;
+      w[c] = wc; m[c] = mc; v[c] = vc;
     }
   }
-  __syncwarp();
-  if (lane == 0) T.last[r] = target;
+  // every lane of the group has read T.last[r] before it is advanced
+  __syncwarp(nl == 32 ? 0xffffffffu : (0xFFu << ((threadIdx.x & 31) & ~7)));
+  if (li == 0 && gap > 0) T.last[r] = target;
 }
 
 // Claims row r of table T for step t.  The winning lanes of the warp append their rows to
@@ -74,7 +79,7 @@ __device__ __forceinline__ uint32_t claim_rows(const FvxTable& T, int32_t r, boo
   return b;
 }
 
-#define PREP_TPW 4
+#define PREP_TPW 8
 // blocks [0, nb_mark): PREP_TPW triples per warp pass; blocks beyond: bf16 planes of E_ext^T
 __global__ void __launch_bounds__(256)
 k_prep(FvxModel M, const int32_t* __restrict__ user, const int32_t* __restrict__ pos,
@@ -104,25 +109,42 @@ k_prep(FvxModel M, const int32_t* __restrict__ user, const int32_t* __restrict__
   for (int b0 = warp_g * PREP_TPW; b0 < B; b0 += nwarps * PREP_TPW) {
     const int b = b0 + lane;
     const bool live = lane < PREP_TPW && b < B;
-    int32_t u = -1, li = -1, lj = -1;
+    int32_t u = -1, li_ = -1, lj = -1;
     bool ustart = false;
     if (live) {
       u = user[b];
       ustart = (b == 0 || user[b - 1] != u);
-      li = pos[b] - M.item_lo;
+      li_ = pos[b] - M.item_lo;
       lj = neg[b] - M.item_lo;
-      if (li < 0 || li >= M.item_cnt) li = -1;
+      if (li_ < 0 || li_ >= M.item_cnt) li_ = -1;
       if (lj < 0 || lj >= M.item_cnt) lj = -1;
-      M.rows[b] = li;
+      M.rows[b] = li_;
       M.rows[B + b] = lj;
     }
     uint32_t wu = claim_rows(M.users, u, live && ustart && u >= 0 && u < M.num_users, t, lane);
-    uint32_t wi = claim_rows(M.items, li, li >= 0, t, lane);
+    uint32_t wi = claim_rows(M.items, li_, li_ >= 0, t, lane);
     uint32_t wj = claim_rows(M.items, lj, lj >= 0, t, lane);
     if (deferred) {
-      while (wu) { const int L = __ffs(wu) - 1; wu &= wu - 1; replay_row(M.users, __shfl_sync(0xffffffffu, u, L), done, M.lr, lane); }
-      while (wi) { const int L = __ffs(wi) - 1; wi &= wi - 1; replay_row(M.items, __shfl_sync(0xffffffffu, li, L), done, M.lr, lane); }
-      while (wj) { const int L = __ffs(wj) - 1; wj &= wj - 1; replay_row(M.items, __shfl_sync(0xffffffffu, lj, L), done, M.lr, lane); }
+      // the claimed rows of this pass (<= 3 * PREP_TPW), four at a time: 8 lanes per row
+      const int grp = lane >> 3, li = lane & 7;
+      const int nu_ = __popc(wu), ni_ = __popc(wi), total = nu_ + ni_ + __popc(wj);
+      for (int base = 0; base < total; base += 4) {
+        const int k = base + grp;
+        // k-th claimed row: users first, then pos items, then neg items
+        int32_t row = -1;
+        int which = 0;
+        {
+          uint32_t msk = wu; int kk = k;
+          if (kk >= nu_) { kk -= nu_; msk = wi; which = 1; if (kk >= ni_) { kk -= ni_; msk = wj; which = 2; } }
+          int src = -1;
+          if (k < total) { for (int q = 0; q < kk; ++q) msk &= msk - 1; src = __ffs(msk) - 1; }
+          const int32_t vu = __shfl_sync(0xffffffffu, u, src < 0 ? 0 : src);
+          const int32_t vi = __shfl_sync(0xffffffffu, li_, src < 0 ? 0 : src);
+          const int32_t vj = __shfl_sync(0xffffffffu, lj, src < 0 ? 0 : src);
+          if (src >= 0) row = which == 0 ? vu : (which == 1 ? vi : vj);
+        }
+        if (row >= 0) replay_row(which == 0 ? M.users : M.items, row, done, M.lr, li, 8);
+      }
     }
   }
 }
@@ -133,7 +155,7 @@ __global__ void k_catchup_all(FvxTable T, const int64_t* __restrict__ step, floa
   const int lane = threadIdx.x & 31;
   const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
   for (long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < T.rows; r += warps)
-    replay_row(T, (int32_t)r, target, lr, lane);
+    replay_row(T, (int32_t)r, target, lr, lane, 32);
 }
 
 // ---------------------------------------------------------------------------------

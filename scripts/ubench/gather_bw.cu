@@ -122,6 +122,73 @@ k_gather(const __grid_constant__ CUtensorMap tm, const __nv_bfloat16* F, const i
   }
 }
 
+
+// fwd-like: stage = 128 rows x 256 B (interleaved hi|lo planes), NST stages, each of the 128 producer threads keeps
+// 16 source pointers and issues 16 cp.async per stage; consumer waits `delay` cycles before releasing the stage.
+template <int NST>
+__global__ void __launch_bounds__(192, 1)
+k_fwdlike(const uint8_t* F, const int* rows, int nrows, int row_bytes, int chunks_per_unit, int delay, int swz, unsigned* sink) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (tc_smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int SB = 32768;
+  uint64_t* full_b = reinterpret_cast<uint64_t*>(smem + NST * SB);
+  uint64_t* empty_b = full_b + NST;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) { for (int s = 0; s < NST; ++s) { mbar_init(&full_b[s], 128); mbar_init(&empty_b[s], 1); } mbar_fence_init(); }
+  __syncthreads();
+  const int chunks_total = row_bytes / 256;
+  const int ksplit = chunks_total / chunks_per_unit;
+  const int n_units = (nrows / 128) * ksplit;
+  if (warp < 4) {
+    const int tid = threadIdx.x, sub = tid >> 4, e = tid & 15, plane = e >> 3, c16 = e & 7;
+    uint32_t stage = 0, phase = 0;
+    for (int w = blockIdx.x; w < n_units; w += gridDim.x) {
+      const int tile = w / ksplit, ks = w - tile * ksplit;
+      const uint8_t* src[16];
+#pragma unroll
+      for (int it = 0; it < 16; ++it) src[it] = F + (size_t)rows[tile * 128 + it * 8 + sub] * row_bytes + e * 16;
+      for (int c = 0; c < chunks_per_unit; ++c) {
+        const int chunk = ks * chunks_per_unit + c;
+        mbar_wait(&empty_b[stage], phase ^ 1);
+        const uint32_t sA = tc_smem_u32(smem + stage * SB) + plane * 16384;
+#pragma unroll
+        for (int it = 0; it < 16; ++it) {
+          const int r = it * 8 + sub;
+          cpasync16(sA + r * 128 + (((swz ? (c16 ^ (r & 7)) : c16)) << 4), src[it] + (size_t)chunk * 256);
+        }
+        cpasync_arrive_noinc(&full_b[stage]);
+        if (++stage == NST) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 4) {
+    uint32_t stage = 0, phase = 0; unsigned acc = 0;
+    for (int w = blockIdx.x; w < n_units; w += gridDim.x)
+      for (int c = 0; c < chunks_per_unit; ++c) {
+        mbar_wait(&full_b[stage], phase);
+        acc += reinterpret_cast<const unsigned*>(smem + stage * SB)[lane * 37];
+        if (delay) { const long long t0 = clock64(); while (clock64() - t0 < delay) {} }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_b[stage]);
+        if (++stage == NST) { stage = 0; phase ^= 1; }
+      }
+    if (acc == 0x12345678u) sink[0] = acc;
+  }
+}
+
+template <int NST>
+static void run_fwdlike(const char* name, const uint8_t* F, const int* rows, int nrows, int D, int cpu, int delay, int swz, unsigned* sink) {
+  const size_t smem = NST * 32768 + 2 * NST * 8 + 1024;
+  cudaFuncSetAttribute(k_fwdlike<NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  for (int w = 0; w < 2; ++w) k_fwdlike<NST><<<148, 192, smem>>>(F, rows, nrows, D * 4, cpu, delay, swz, sink);
+  cudaEventRecord(e0);
+  for (int w = 0; w < 5; ++w) k_fwdlike<NST><<<148, 192, smem>>>(F, rows, nrows, D * 4, cpu, delay, swz, sink);
+  cudaEventRecord(e1);
+  cudaError_t err = cudaDeviceSynchronize();
+  float ms; cudaEventElapsedTime(&ms, e0, e1);
+  printf("%-60s %8.1f us  %8.1f GB/s  %s\n", name, ms / 5 * 1e3, (double)nrows * D * 4 / (ms / 5) / 1e6, err == cudaSuccess ? "" : cudaGetErrorString(err));
+}
+
 int main(int argc, char** argv) {
   const int I = 100000, D = 2048, nrows = 32768;
   __nv_bfloat16* F; int* rows; unsigned* sink;
@@ -145,6 +212,19 @@ int main(int argc, char** argv) {
       {"bulk1d 2 KB pieces", 8, 1, 1, 1},
       {"bulk1d 4 KB rows", 9, 1, 1, 1},
   };
+  {
+    // fwd-like study on a full 8 KB-per-row plane pair (F2: 100000 x 8192 B)
+    uint8_t* F2; cudaMalloc(&F2, (size_t)I * D * 4); cudaMemset(F2, 0, (size_t)I * D * 4);
+    const uint8_t* f = F2;
+    run_fwdlike<5>("fwdlike 5x32KB, 8 chunks/unit (ksplit 4), no delay", f, rows, nrows, D, 8, 0, 1, sink);
+    run_fwdlike<5>("fwdlike 5x32KB, 32 chunks/unit (ksplit 1), no delay", f, rows, nrows, D, 32, 0, 1, sink);
+    run_fwdlike<5>("fwdlike 5x32KB, 8 chunks/unit, delay 500 cyc", f, rows, nrows, D, 8, 500, 1, sink);
+    run_fwdlike<5>("fwdlike 5x32KB, 8 chunks/unit, delay 1000 cyc", f, rows, nrows, D, 8, 1000, 1, sink);
+    run_fwdlike<5>("fwdlike 5x32KB, 8 chunks/unit, no swizzle", f, rows, nrows, D, 8, 0, 0, sink);
+    run_fwdlike<6>("fwdlike 6x32KB, 8 chunks/unit, no delay", f, rows, nrows, D, 8, 0, 1, sink);
+    run_fwdlike<3>("fwdlike 3x32KB, 8 chunks/unit, no delay", f, rows, nrows, D, 8, 0, 1, sink);
+    cudaFree(F2);
+  }
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   for (auto& c : cfgs) {
     CUtensorMap tm = make_map(F, I, D, 64, c.br, c.sw, c.promo);
