@@ -38,8 +38,8 @@ class FvxModel(C.Structure):
 
 
 class FvxEvalWs(C.Structure):
-    _fields_ = [("A", _p), ("Bm", _p), ("unorm", _p), ("stat", _p), ("cand", _p), ("ccount", _p), ("flags", _p),
-                ("thr", _p),
+    _fields_ = [("A", _p), ("Bm", _p), ("epsa", _p), ("nb", _p), ("stat", _p), ("cand", _p), ("ccount", _p),
+                ("flags", _p), ("thr", _p), ("lists", C.c_int64),
                 ("u_cap", C.c_int32), ("i_cap", C.c_int32), ("KP", C.c_int32), ("splits", C.c_int32),
                 ("cap", C.c_int32), ("_pad", C.c_int32)]
 

@@ -5,9 +5,9 @@
 // and Evaluator.store_recommendation (Evaluator.py:231-237) wants, per user, the k best
 // non-train items.  The sweep below never writes S:
 //
-//   1. k_pack_users / k_pack_items   bf16 operands (K+d+2 padded to KP), fp32 row norms;
-//                                    the item bias rides in two columns (bf16 hi + lo) so
-//                                    that it enters the score almost exactly
+//   1. k_pack_users / k_pack_items   bf16 operands (K+d+3 padded to KP); the item bias rides in
+//                                    two columns (bf16 hi + lo) so that it enters the score
+//                                    almost exactly, the rounding bound in a third
 //   2. k_topk_tc (persistent, warp-specialised, one CTA per SM)
 //        warp 0    TMA producer : item tiles [128 x KP] -> 64B-swizzled smem ring; the two
 //                                 user tiles [128 x KP] of the work unit
@@ -25,14 +25,16 @@
 //                                    same fvx_score_one() the fp32 path uses, train-item mask,
 //                                    sort, top-k.
 //
-// Exactness: with a = [Gu|Tu][u], b = [Gi|theta][i] rounded to bf16 (relative error 2^-9 each)
-//   |s_bf16 - s_fp32| <= eps_u = 1.002 * 2^-8 * |a| * max_i|b_i|              (Cauchy-Schwarz)
-//                              + 2^-17 * max_i|bias_i|                         (hi+lo residual)
-//                              + KP * 2^-21 * (|a| * max|b| + max|bias|)       (fp32 accumulation)
-// A row keeps every item with s_bf16 >= tau - 2*eps_u, tau = the (k + #train items)-th best bf16
-// score seen so far (a lower bound of the k-th best over the non-train items), so the true top-k
-// is always among the candidates and the output equals the fp32 kernel's bit for bit.  A row whose
-// list overflows is flagged and the caller re-runs it through the fp32 kernel.
+// Exactness.  With a = [Gu|Tu][u], b = [Gi|theta][i] rounded to bf16 (relative error 2^-9 each)
+//   |s_bf16 - s_fp32| <= c * |a| * |b_i| + beta0,   c = 1.003 * 2^-8 + KP * 2^-21  (rounding + fp32
+//   accumulation),  beta0 = (2^-17 + KP * 2^-21) * max_i |bias_i|                (hi+lo residual).
+// The bound is PER ITEM and costs nothing: one more K column holds eps_u = c*|a_u| (rounded up to
+// bf16) on the user side and |b_i| (rounded up) on the item side, so the UMMA itself delivers the
+// upper bound s_ub = s_bf16 + eps_u * |b_i|; the lower bound is s_lb = s_ub - 2.001 * eps_u * |b_i|
+// - beta0.  A row keeps every item with s_ub >= tau - beta0, tau = the (k + #train items)-th best
+// s_lb seen so far (a lower bound of the k-th best true score over the non-train items), so the
+// true top-k is always among the candidates and the output equals the fp32 kernel's bit for bit.
+// A row whose list overflows is flagged and the caller re-runs it through the fp32 kernel.
 #include <cuda_bf16.h>
 #include <math_constants.h>
 
@@ -44,9 +46,9 @@
 #define TCK_BN 128          // items per tile  (UMMA N)
 #define TCK_KB 32           // bf16 elements per K block (64-byte swizzle rows)
 #define TCK_CAP 512         // candidate slots per (user, split)
-#define TCK_SLACK 96        // a list is compacted once it holds k + #train + TCK_SLACK entries
+#define TCK_SLACK 192       // a list is compacted once it holds k + #train + TCK_SLACK entries
 #define TCK_THREADS 320     // warp 0 producer, warp 1 UMMA, warps 2-9 epilogue
-#define TCK_RS_MAX 512      // candidates per user the final selection can take
+#define TCK_RS_MAX 1024     // candidates per user the final selection can take
 #define KEY_PAD 0xFFFFFFFFFFFFFFFFull
 
 // order-preserving float <-> uint (ascending uint == ascending float)
@@ -69,31 +71,40 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
 }
 
 // ---------------------------------------------------------------------------------
-__global__ void k_pack_users(FvxModel M, int u0, int u1, __nv_bfloat16* __restrict__ A, float* __restrict__ unorm,
-                             uint32_t* __restrict__ thr_g, int KP) {
+__device__ __forceinline__ __nv_bfloat16 bf16_up(float x) {   // smallest bf16 >= x (x >= 0)
+  __nv_bfloat16 h = __float2bfloat16_rn(x);
+  if (__bfloat162float(h) < x) h = __ushort_as_bfloat16((unsigned short)(__bfloat16_as_ushort(h) + 1));
+  return h;
+}
+
+__global__ void k_pack_users(FvxModel M, int u0, int u1, __nv_bfloat16* __restrict__ A, float* __restrict__ epsa,
+                             uint32_t* __restrict__ thr_g, int KP, float c_rel) {
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   const int kd = M.K + M.d;
   for (int u = u0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); u < u1; u += warps) {
     const float* src = M.users.w + (size_t)u * M.users.stride;
     float sq = 0.0f;
-    for (int c = lane; c < KP; c += 32) {
-      float v = 0.0f;
-      if (c < kd) { v = src[c]; sq += v * v; }
-      else if (c == kd || c == kd + 1) v = 1.0f;       // multiplies bias_hi and bias_lo
-      A[(size_t)(u - u0) * KP + c] = __float2bfloat16_rn(v);
-    }
+    for (int c = lane; c < kd; c += 32) { const float v = src[c]; sq += v * v; }
     sq = fvx_warp_sum(sq);
+    const __nv_bfloat16 eh = bf16_up(c_rel * sqrtf(sq) * 1.0001f);
+    for (int c = lane; c < KP; c += 32) {
+      __nv_bfloat16 o = __float2bfloat16_rn(0.0f);
+      if (c < kd) o = __float2bfloat16_rn(src[c]);
+      else if (c == kd || c == kd + 1) o = __float2bfloat16_rn(1.0f);   // multiplies bias_hi and bias_lo
+      else if (c == kd + 2) o = eh;                                     // multiplies |b_i|
+      A[(size_t)(u - u0) * KP + c] = o;
+    }
     if (lane == 0) {
-      unorm[u - u0] = sqrtf(sq);
+      epsa[u - u0] = __bfloat162float(eh);
       thr_g[u - u0] = tck_mono(-CUDART_INF_F);
     }
   }
 }
 
-// stat[0] = max |[Gi|theta]| (as uint bits of a non-negative float), stat[1] = max |bias|
+// nb[i] = |[Gi|theta][i]| rounded up to bf16; stat[1] = max |bias| (uint bits of a non-negative float)
 __global__ void k_pack_items(FvxModel M, const float* __restrict__ theta, __nv_bfloat16* __restrict__ Bm,
-                             uint32_t* __restrict__ stat, int KP) {
+                             float* __restrict__ nb, uint32_t* __restrict__ stat, int KP) {
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   const int K = M.K, d = M.d, kd = K + d;
@@ -105,17 +116,18 @@ __global__ void k_pack_items(FvxModel M, const float* __restrict__ theta, __nv_b
     const __nv_bfloat16 bh = __float2bfloat16_rn(bias);
     const __nv_bfloat16 bl = __float2bfloat16_rn(bias - __bfloat162float(bh));
     float sq = 0.0f;
+    for (int c = lane; c < kd; c += 32) { const float v = c < K ? row[c] : th[c - K]; sq += v * v; }
+    sq = fvx_warp_sum(sq);
+    const __nv_bfloat16 nh = bf16_up(sqrtf(sq) * 1.0001f);
     for (int c = lane; c < KP; c += 32) {
       __nv_bfloat16 o = __float2bfloat16_rn(0.0f);
-      if (c < kd) {
-        const float v = c < K ? row[c] : th[c - K];
-        sq += v * v;
-        o = __float2bfloat16_rn(v);
-      } else if (c == kd) o = bh;
+      if (c < kd) o = __float2bfloat16_rn(c < K ? row[c] : th[c - K]);
+      else if (c == kd) o = bh;
       else if (c == kd + 1) o = bl;
+      else if (c == kd + 2) o = nh;
       Bm[(size_t)i * KP + c] = o;
     }
-    sq = fvx_warp_sum(sq);
+    if (lane == 0) nb[i] = __bfloat162float(nh);
     wmax = fmaxf(wmax, sqrtf(sq));
     bmax = fmaxf(bmax, fabsf(bias));
   }
@@ -131,54 +143,82 @@ struct TckParams {
   int item_cnt, item_lo;
   int nkb;              // K blocks of 32
   int stages;
-  int splits, tiles_per_split, n_item_tiles, n_pairs;
+  // work units: the first n_full user-tile pairs (a multiple of the grid size) sweep the whole
+  // catalog each (one list per row, no threshold restart); the remaining pairs are cut into
+  // `splits` item ranges so that the last wave still fills the machine
+  int splits, tiles_per_split, n_item_tiles, n_pairs, n_full;
   int k;
   int u0;
-  float acc_c;          // KP * 2^-21: fp32 accumulation error per unit of magnitude
-  const float* unorm;
+  float beta_c;         // 2^-17 + KP * 2^-21: bias residual + fp32 accumulation, per unit of max|bias|
+  const float* epsa;    // [n_users] eps_u as multiplied by the UMMA (bf16 value)
+  const float* nb;      // [item_cnt] |b_i| as multiplied by the UMMA (bf16 value)
   const uint32_t* stat; // [0] max item norm, [1] max |bias|  (float bits)
   const int64_t* mask_row_ptr;
-  unsigned long long* cand;   // [n_users * splits * CAP]
-  int32_t* ccount;            // [n_users * splits]
+  unsigned long long* cand;   // [lists * CAP]
+  int32_t* ccount;            // [lists]
   int32_t* flags;             // [n_users]
-  uint32_t* thr_g;            // [n_users] best known row threshold (tck_mono encoding), shared by the splits
+  uint32_t* thr_g;            // [n_users] best known row threshold on s_ub (tck_mono encoding)
 };
+
+// list index of (row, split): rows of the full pairs own one list, tail rows `splits` lists
+__device__ __forceinline__ size_t tck_list(const TckParams& P, int row, int sp) {
+  const int full_rows = P.n_full * 2 * TCK_BM;
+  return row < full_rows ? (size_t)row : (size_t)full_rows + (size_t)(row - full_rows) * P.splits + sp;
+}
+// unit w of the global enumeration -> (pair, split, tile range)
+__device__ __forceinline__ void tck_unit(const TckParams& P, int w, int& pair, int& sp, int& t0, int& t1) {
+  if (w < P.n_full) { pair = w; sp = 0; t0 = 0; t1 = P.n_item_tiles; return; }
+  const int x = w - P.n_full;
+  pair = P.n_full + x / P.splits;
+  sp = x - (x / P.splits) * P.splits;
+  t0 = sp * P.tiles_per_split;
+  t1 = min(P.n_item_tiles, t0 + P.tiles_per_split);
+}
 
 // warp-cooperative: tighten the threshold of lane `L`'s row and prune its candidate list
 __device__ __forceinline__ void tck_compact_row(const TckParams& P, int L, int lane, int my_row, int split,
-                                                float my_margin, int my_kk, int& cnt, float& thr) {
+                                                float my_eps2, float beta0, int my_kk, int& cnt, float& thr) {
   const int row = __shfl_sync(0xffffffffu, my_row, L);
   const int n = __shfl_sync(0xffffffffu, cnt, L);
   const int kk = __shfl_sync(0xffffffffu, my_kk, L);
-  const float margin = __shfl_sync(0xffffffffu, my_margin, L);
+  const float eps2 = __shfl_sync(0xffffffffu, my_eps2, L);     // 2.001 * eps_u
   const float old_thr = __shfl_sync(0xffffffffu, thr, L);
-  unsigned long long* buf = P.cand + ((size_t)row * P.splits + split) * TCK_CAP;
+  unsigned long long* buf = P.cand + tck_list(P, row, split) * TCK_CAP;
   // The train-item mask is NOT consulted here: the (k + #train items)-th best score over ALL
   // items is a lower bound of the k-th best over the non-train items.  k_rescore_select applies
   // the mask exactly.
-  uint32_t e[TCK_CAP / 32];
+  uint32_t e[TCK_CAP / 32];     // ~mono(s_ub): the list key (ascending = best first)
+  uint32_t lbk[TCK_CAP / 32];   // ~mono(s_lb)
   uint32_t kmin = 0xFFFFFFFFu, kmax = 0u;
 #pragma unroll
   for (int q = 0; q < TCK_CAP / 32; ++q) {
     const int idx = q * 32 + lane;
-    e[q] = idx < n ? (uint32_t)(buf[idx] >> 32) : 0xFFFFFFFFu;
-    if (idx < n) { kmin = min(kmin, e[q]); kmax = max(kmax, e[q]); }
+    e[q] = 0xFFFFFFFFu;
+    lbk[q] = 0xFFFFFFFFu;
+    if (idx < n) {
+      const unsigned long long key = buf[idx];
+      e[q] = (uint32_t)(key >> 32);
+      const float lb = tck_score_of_hi(e[q]) - eps2 * P.nb[(uint32_t)key - (uint32_t)P.item_lo] - beta0;
+      lbk[q] = ~tck_mono(lb);
+      kmin = min(kmin, lbk[q]);
+      kmax = max(kmax, lbk[q]);
+    }
   }
   float new_thr = fmaxf(old_thr, tck_unmono(__ldcg(P.thr_g + row)));
   if (n >= kk) {
-    // a 32-bit score key T with  kk <= #(key <= T) <= kk + 8  (or exactly the kk-th best)
+    // a 32-bit key T with  kk <= #(lb key <= T) <= kk + 16  (or exactly the kk-th best lower bound)
     uint32_t lo = __reduce_min_sync(0xffffffffu, kmin), hi = __reduce_max_sync(0xffffffffu, kmax);
     while (lo < hi) {
       const uint32_t mid = lo + ((hi - lo) >> 1);
       int c = 0;
 #pragma unroll
-      for (int q = 0; q < TCK_CAP / 32; ++q) c += (e[q] <= mid) ? 1 : 0;
+      for (int q = 0; q < TCK_CAP / 32; ++q) c += (lbk[q] <= mid) ? 1 : 0;
       c = __reduce_add_sync(0xffffffffu, c);
-      if (c >= kk) { hi = mid; if (c <= kk + 8) break; } else lo = mid + 1;
+      if (c >= kk) { hi = mid; if (c <= kk + 16) break; } else lo = mid + 1;
     }
-    new_thr = fmaxf(new_thr, tck_score_of_hi(hi) - margin);
+    new_thr = fmaxf(new_thr, tck_score_of_hi(hi) - beta0);
   }
-  const uint32_t cut = ~tck_mono(new_thr);          // keep keys <= cut  <=>  score >= new_thr
+  const uint32_t cut = ~tck_mono(new_thr);          // keep keys <= cut  <=>  s_ub >= new_thr
   int out = 0;
 #pragma unroll
   for (int q = 0; q < TCK_CAP / 32; ++q) {
@@ -263,22 +303,21 @@ k_topk_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int n_units = P.n_pairs * P.splits;
+  const int n_units = P.n_full + (P.n_pairs - P.n_full) * P.splits;
 
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
       uint32_t stage = 0, phase = 0, unit_i = 0;
       for (int w = blockIdx.x; w < n_units; w += gridDim.x, ++unit_i) {
-        const int pair = w / P.splits, sp = w - pair * P.splits;
+        int pair, sp, t0, t1;
+        tck_unit(P, w, pair, sp, t0, t1);
         mbar_wait(a_empty, (unit_i & 1) ^ 1);
         mbar_expect_tx(a_full, 2 * a_bytes);
         for (int ut = 0; ut < 2; ++ut)
           for (int kb = 0; kb < P.nkb; ++kb)
             tma_load_2d(sA + (size_t)ut * a_bytes + (size_t)kb * TCK_BM * 64, &tmA, a_full, kb * TCK_KB,
                         (pair * 2 + ut) * TCK_BM);
-        const int t0 = sp * P.tiles_per_split;
-        const int t1 = min(P.n_item_tiles, t0 + P.tiles_per_split);
         for (int t = t0; t < t1; ++t) {
           mbar_wait(&empty_b[stage], phase ^ 1);
           mbar_expect_tx(&full_b[stage], b_bytes);
@@ -295,10 +334,9 @@ k_topk_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       constexpr uint32_t idesc = umma_idesc_bf16(TCK_BM, TCK_BN, 0, 0);
       uint32_t stage = 0, phase = 0, unit_i = 0, buf = 0, buf_phase = 0;
       for (int w = blockIdx.x; w < n_units; w += gridDim.x, ++unit_i) {
-        const int sp = w % P.splits;
+        int pair, sp, t0, t1;
+        tck_unit(P, w, pair, sp, t0, t1);
         mbar_wait(a_full, unit_i & 1);
-        const int t0 = sp * P.tiles_per_split;
-        const int t1 = min(P.n_item_tiles, t0 + P.tiles_per_split);
         for (int t = t0; t < t1; ++t) {
           mbar_wait(&full_b[stage], phase);
           tc_fence_after();
@@ -332,18 +370,18 @@ k_topk_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const int ut = ew >> 2;
     const int quad = warp & 3;            // TMEM lanes this warp may read: [32*quad, 32*quad+32)
     const int rit = quad * 32 + lane;     // row in tile
-    const float bmax = __uint_as_float(P.stat[0]), biasmax = __uint_as_float(P.stat[1]);
+    const float beta0 = P.beta_c * __uint_as_float(P.stat[1]) + 1e-30f;
     uint32_t buf = 0, buf_phase = 0;
     for (int w = blockIdx.x; w < n_units; w += gridDim.x) {
-      const int pair = w / P.splits, sp = w - pair * P.splits;
+      int pair, sp, t0, t1;
+      tck_unit(P, w, pair, sp, t0, t1);
+      const bool shared = w >= P.n_full;    // the row's other splits run elsewhere: exchange bounds
       const int row = (pair * 2 + ut) * TCK_BM + rit;
       const bool live = row < P.n_users;
-      float margin = 0.0f;
+      float eps2 = 0.0f;
       int kk = P.k;
       if (live) {
-        const float an = P.unorm[row];
-        const float eps = 1.002f * 0.00390625f * an * bmax + 7.6294e-6f * biasmax + P.acc_c * (an * bmax + biasmax);
-        margin = 2.0f * eps + 1e-30f;
+        eps2 = 2.001f * P.epsa[row];
         const int gu = P.u0 + row;
         kk = P.k + (int)(P.mask_row_ptr[gu + 1] - P.mask_row_ptr[gu]);
         if (kk > TCK_CAP - TCK_SLACK - 40) {   // cannot bound this row's list: exact fp32 sweep instead
@@ -354,12 +392,13 @@ k_topk_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       const int trig = kk + TCK_SLACK;
       float thr = live ? -CUDART_INF_F : CUDART_INF_F;
       int cnt = 0;
-      unsigned long long* lbuf = P.cand + ((size_t)(live ? row : 0) * P.splits + sp) * TCK_CAP;
-      const int t0 = sp * P.tiles_per_split;
-      const int t1 = min(P.n_item_tiles, t0 + P.tiles_per_split);
+      unsigned long long* lbuf = P.cand + tck_list(P, live ? row : 0, sp) * TCK_CAP;
       for (int t = t0; t < t1; ++t) {
         const uint32_t acc = ut * 2 + buf;
-        if (live) thr = fmaxf(thr, tck_unmono(__ldcg(P.thr_g + row)));   // bounds found by the row's other splits (L2)
+        // bounds found by the row's other splits (L2), fetched now and applied after this tile
+        uint32_t peer = 0u;
+        const bool refresh = shared && live && ((t - t0) & 7) == 0;
+        if (refresh) peer = __ldcg(P.thr_g + row);
         mbar_wait(&t_full[acc], buf_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TCK_BN;
@@ -379,22 +418,23 @@ k_topk_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           while (need) {
             const int L = __ffs(need) - 1;
             need &= need - 1;
-            tck_compact_row(P, L, lane, row, sp, margin, kk, cnt, thr);
+            tck_compact_row(P, L, lane, row, sp, eps2, beta0, kk, cnt, thr);
           }
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&t_empty[acc]);
         if (++buf == 2) { buf = 0; buf_phase ^= 1; }
+        if (refresh) thr = fmaxf(thr, tck_unmono(peer));
       }
-      // publish this split's bound for the rows that hold at least kk candidates, then the length
+      // publish this unit's bound for the rows that hold at least kk candidates, then the length
       uint32_t need = __ballot_sync(0xffffffffu, live && cnt >= kk);
       while (need) {
         const int L = __ffs(need) - 1;
         need &= need - 1;
-        tck_compact_row(P, L, lane, row, sp, margin, kk, cnt, thr);
+        tck_compact_row(P, L, lane, row, sp, eps2, beta0, kk, cnt, thr);
       }
-      if (live) P.ccount[(size_t)row * P.splits + sp] = cnt;
+      if (live) P.ccount[tck_list(P, row, sp)] = cnt;
     }
   }
   tc_fence_before();
@@ -421,25 +461,62 @@ __device__ __forceinline__ void rs_bitonic(unsigned long long* keys, int n, int 
     }
 }
 
+// x_ui with the fp32 kernel's arithmetic (fvx_score_one: K latent terms, d visual terms, item
+// bias, visual bias, one fmaf chain in index order) but 16-byte loads of the item row
+__device__ __forceinline__ float rs_score(const float* __restrict__ urow, const float* __restrict__ irow,
+                                          const float* __restrict__ th, int K, int d) {
+  float s = 0.0f;
+  int c = 0;
+  for (; c + 4 <= K; c += 4) {
+    const float4 x = *reinterpret_cast<const float4*>(irow + c);
+    s = fmaf(urow[c], x.x, s);
+    s = fmaf(urow[c + 1], x.y, s);
+    s = fmaf(urow[c + 2], x.z, s);
+    s = fmaf(urow[c + 3], x.w, s);
+  }
+  for (; c < K; ++c) s = fmaf(urow[c], irow[c], s);
+  if (d > 0) {
+    int n = 0;
+    for (; n + 4 <= d; n += 4) {
+      const float4 x = *reinterpret_cast<const float4*>(th + n);
+      s = fmaf(urow[K + n], x.x, s);
+      s = fmaf(urow[K + n + 1], x.y, s);
+      s = fmaf(urow[K + n + 2], x.z, s);
+      s = fmaf(urow[K + n + 3], x.w, s);
+    }
+    for (; n < d; ++n) s = fmaf(urow[K + n], th[n], s);
+    s += irow[K];
+    s += th[d];
+  } else {
+    s += irow[K];
+  }
+  return s;
+}
+
 __global__ void __launch_bounds__(RS_WARPS * 32)
-k_rescore_select(FvxModel M, const float* __restrict__ theta, int u0, int n_users, int splits,
-                 const unsigned long long* __restrict__ cand, const int32_t* __restrict__ ccount,
-                 const uint32_t* __restrict__ thr_g, int32_t* __restrict__ flags,
+k_rescore_select(FvxModel M, const float* __restrict__ theta, TckParams P,
                  const int64_t* __restrict__ mask_row_ptr, const int32_t* __restrict__ mask_col, int k,
                  int32_t* __restrict__ out_ids, float* __restrict__ out_scores) {
   __shared__ unsigned long long rs_keys[RS_WARPS][TCK_RS_MAX];
+  __shared__ float rs_user[RS_WARPS][128];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned long long* kk = rs_keys[warp];
-  for (int r = blockIdx.x * RS_WARPS + warp; r < n_users; r += gridDim.x * RS_WARPS) {
-    const int gu = u0 + r;
+  float* us = rs_user[warp];
+  const int full_rows = P.n_full * 2 * TCK_BM;
+  const int kd = M.K + M.d;
+  for (int r = blockIdx.x * RS_WARPS + warp; r < P.n_users; r += gridDim.x * RS_WARPS) {
+    const int gu = P.u0 + r;
     const float* urow = M.users.w + (size_t)gu * M.users.stride;
+    for (int c = lane; c < kd; c += 32) us[c] = urow[c];
     const long long mlo = mask_row_ptr[gu], mhi = mask_row_ptr[gu + 1];
-    // survivors of the row's final bound (already includes the rounding margin)
-    const uint32_t cut = ~thr_g[r];
+    // survivors of the row's final bound on s_ub
+    const uint32_t cut = ~P.thr_g[r];
+    const int nlists = r < full_rows ? 1 : P.splits;
     int total = 0;
-    for (int sp = 0; sp < splits; ++sp) {
-      const int n = ccount[(size_t)r * splits + sp];
-      const unsigned long long* src = cand + ((size_t)r * splits + sp) * TCK_CAP;
+    for (int sp = 0; sp < nlists; ++sp) {
+      const size_t li = tck_list(P, r, sp);
+      const int n = P.ccount[li];
+      const unsigned long long* src = P.cand + li * TCK_CAP;
       for (int i0 = 0; i0 < n; i0 += 32) {
         const int i = i0 + lane;
         const unsigned long long key = i < n ? src[i] : KEY_PAD;
@@ -451,7 +528,7 @@ k_rescore_select(FvxModel M, const float* __restrict__ theta, int u0, int n_user
       }
     }
     if (total > TCK_RS_MAX) {
-      if (lane == 0) flags[r] = 1;
+      if (lane == 0) P.flags[r] = 1;
       total = TCK_RS_MAX;
     }
     __syncwarp();
@@ -462,8 +539,7 @@ k_rescore_select(FvxModel M, const float* __restrict__ theta, int u0, int n_user
       if (!fvx_in_sorted(mask_col, mlo, mhi, gid)) {
         const int32_t li = gid - M.item_lo;
         const float* th = M.d > 0 ? theta + (size_t)li * M.de : nullptr;
-        const float s = fvx_score_one(urow, M.items.w + (size_t)li * M.items.stride, th, M.K, M.d);
-        key = tck_key(s, gid);
+        key = tck_key(rs_score(us, M.items.w + (size_t)li * M.items.stride, th, M.K, M.d), gid);
       }
       kk[i] = key;
     }
@@ -513,23 +589,41 @@ int tc_make_tensor_map_bf16(CUtensorMap* out, const void* base, uint64_t rows, u
 
 extern "C" {
 
+// geometry shared by the query and the launch
+static void tck_geometry(const FvxModel* m, int n_users, int* KP, int* n_pairs, int* n_full, int* splits, int* grid,
+                         long long* lists) {
+  const int kd3 = m->K + m->d + 3;
+  *KP = (kd3 + TCK_KB - 1) / TCK_KB * TCK_KB;
+  *n_pairs = (n_users + 2 * TCK_BM - 1) / (2 * TCK_BM);
+  const int n_item_tiles = (m->item_cnt + TCK_BN - 1) / TCK_BN;
+  const int G = fvx_num_sms();
+  *n_full = (*n_pairs / G) * G;
+  const int tail = *n_pairs - *n_full;
+  int s = 1;
+  if (tail > 0) {
+    s = (G + tail - 1) / tail;          // the tail pairs are cut so that their units still fill the machine
+    if (s > 8) s = 8;
+    if (s > n_item_tiles / 8) s = n_item_tiles / 8;
+    if (s < 1) s = 1;
+  }
+  *splits = s;
+  const long long units = (long long)*n_full + (long long)tail * s;
+  *grid = (int)(units < G ? units : G);
+  *lists = (long long)*n_full * 2 * TCK_BM + ((long long)n_users - (long long)*n_full * 2 * TCK_BM > 0
+                                               ? ((long long)n_users - (long long)*n_full * 2 * TCK_BM) * s : 0);
+}
+
 int fvx_eval_ws_query(const FvxModel* model, int32_t n_users, FvxEvalWs* ws) {
   FVX_CHECK_ARG(model && ws && n_users > 0, "fvx_eval_ws_query: bad arguments");
-  const int kd2 = model->K + model->d + 2;
-  const int KP = (kd2 + TCK_KB - 1) / TCK_KB * TCK_KB;
-  const int n_pairs = (n_users + 2 * TCK_BM - 1) / (2 * TCK_BM);
-  const int n_item_tiles = (model->item_cnt + TCK_BN - 1) / TCK_BN;
-  // work units = user-tile pairs x item splits; aim at >= 4 units per SM to keep the tail short
-  // (the splits of a row share their thresholds, so a split costs little extra candidate traffic)
-  int splits = (4 * fvx_num_sms() + n_pairs - 1) / n_pairs;
-  if (splits > 8) splits = 8;
-  if (splits > n_item_tiles / 8) splits = n_item_tiles / 8;
-  if (splits < 1) splits = 1;
+  int KP, n_pairs, n_full, splits, grid;
+  long long lists;
+  tck_geometry(model, n_users, &KP, &n_pairs, &n_full, &splits, &grid, &lists);
   ws->KP = KP;
   ws->splits = splits;
   ws->cap = TCK_CAP;
   ws->u_cap = n_users;
   ws->i_cap = model->item_cnt;
+  ws->lists = lists;
   return 0;
 }
 
@@ -541,25 +635,30 @@ int fvx_score_topk_tc(const FvxModel* model, const float* theta_ext, int32_t u0,
   FVX_CHECK_ARG(0 <= u0 && u0 < u1 && u1 <= model->num_users, "fvx_score_topk_tc: bad user range");
   FVX_CHECK_ARG(k >= 1 && k <= 128, "fvx_score_topk_tc: k=%d outside [1,128]", k);
   const int n_users = u1 - u0;
-  FvxEvalWs q;
-  fvx_eval_ws_query(model, n_users, &q);
-  FVX_CHECK_ARG(ws->KP == q.KP && ws->splits == q.splits && ws->cap == TCK_CAP && ws->u_cap >= n_users &&
-                ws->i_cap >= model->item_cnt, "fvx_score_topk_tc: workspace does not match fvx_eval_ws_query");
-  FVX_CHECK_ARG(ws->A && ws->Bm && ws->unorm && ws->stat && ws->cand && ws->ccount && ws->flags && ws->thr,
+  int KP, n_pairs, n_full, splits, grid;
+  long long lists;
+  tck_geometry(model, n_users, &KP, &n_pairs, &n_full, &splits, &grid, &lists);
+  FVX_CHECK_ARG(ws->KP == KP && ws->splits == splits && ws->cap == TCK_CAP && ws->u_cap >= n_users &&
+                ws->i_cap >= model->item_cnt && ws->lists >= lists,
+                "fvx_score_topk_tc: workspace does not match fvx_eval_ws_query");
+  FVX_CHECK_ARG(ws->A && ws->Bm && ws->epsa && ws->nb && ws->stat && ws->cand && ws->ccount && ws->flags && ws->thr,
                 "fvx_score_topk_tc: null workspace buffer");
-  const int KP = q.KP, nkb = KP / TCK_KB;
-  FVX_CHECK_ARG(KP <= 128, "fvx_score_topk_tc: K+d+2=%d too large for the tensor-core sweep (use fvx_score_topk)",
-                model->K + model->d + 2);
+  const int nkb = KP / TCK_KB;
+  FVX_CHECK_ARG(KP <= 128 && model->K + model->d <= 128,
+                "fvx_score_topk_tc: K+d+3=%d too large for the tensor-core sweep (use fvx_score_topk)",
+                model->K + model->d + 3);
   cudaStream_t st = fvx_cu(stream);
 
   cudaMemsetAsync(ws->stat, 0, 8, st);
   cudaMemsetAsync(ws->flags, 0, sizeof(int32_t) * n_users, st);
+  cudaMemsetAsync(ws->ccount, 0, sizeof(int32_t) * lists, st);
+  const float c_rel = 1.003f * 0.00390625f + (float)KP * 4.76837158e-7f;
   int g = (n_users * 32 + 255) / 256;
   if (g > fvx_num_sms() * 8) g = fvx_num_sms() * 8;
-  k_pack_users<<<g, 256, 0, st>>>(*model, u0, u1, reinterpret_cast<__nv_bfloat16*>(ws->A), ws->unorm,
-                                  reinterpret_cast<uint32_t*>(ws->thr), KP);
+  k_pack_users<<<g, 256, 0, st>>>(*model, u0, u1, reinterpret_cast<__nv_bfloat16*>(ws->A), ws->epsa,
+                                  reinterpret_cast<uint32_t*>(ws->thr), KP, c_rel);
   g = fvx_num_sms() * 8;
-  k_pack_items<<<g, 256, 0, st>>>(*model, theta_ext, reinterpret_cast<__nv_bfloat16*>(ws->Bm),
+  k_pack_items<<<g, 256, 0, st>>>(*model, theta_ext, reinterpret_cast<__nv_bfloat16*>(ws->Bm), ws->nb,
                                   reinterpret_cast<uint32_t*>(ws->stat), KP);
   FVX_CHECK_LAUNCH("k_pack");
 
@@ -570,12 +669,12 @@ int fvx_score_topk_tc(const FvxModel* model, const float* theta_ext, int32_t u0,
 
   TckParams P;
   P.n_users = n_users; P.item_cnt = model->item_cnt; P.item_lo = model->item_lo; P.nkb = nkb;
-  P.n_pairs = (n_users + 2 * TCK_BM - 1) / (2 * TCK_BM);
+  P.n_pairs = n_pairs; P.n_full = n_full;
   P.n_item_tiles = (model->item_cnt + TCK_BN - 1) / TCK_BN;
-  P.splits = q.splits;
+  P.splits = splits;
   P.tiles_per_split = (P.n_item_tiles + P.splits - 1) / P.splits;
-  P.k = k; P.u0 = u0; P.unorm = ws->unorm; P.stat = reinterpret_cast<const uint32_t*>(ws->stat);
-  P.acc_c = (float)KP * 4.76837158e-7f;
+  P.k = k; P.u0 = u0; P.epsa = ws->epsa; P.nb = ws->nb; P.stat = reinterpret_cast<const uint32_t*>(ws->stat);
+  P.beta_c = 7.6294e-6f + (float)KP * 4.76837158e-7f;
   P.mask_row_ptr = mask_row_ptr;
   P.cand = reinterpret_cast<unsigned long long*>(ws->cand); P.ccount = ws->ccount; P.flags = ws->flags;
   P.thr_g = reinterpret_cast<uint32_t*>(ws->thr);
@@ -591,15 +690,12 @@ int fvx_score_topk_tc(const FvxModel* model, const float* theta_ext, int32_t u0,
     if (e != cudaSuccess) FVX_FAIL(-3, "fvx_score_topk_tc: cannot set %zu B smem: %s", smem, cudaGetErrorString(e));
     configured = smem;
   }
-  int grid = P.n_pairs * P.splits;   // work units; persistent CTAs, one per SM
-  if (grid > fvx_num_sms()) grid = fvx_num_sms();
   k_topk_tc<<<grid, TCK_THREADS, smem, st>>>(tmA, tmB, P);
   FVX_CHECK_LAUNCH("k_topk_tc");
 
   long long rg = ((long long)n_users + RS_WARPS - 1) / RS_WARPS;
   if (rg > (long long)fvx_num_sms() * 8) rg = (long long)fvx_num_sms() * 8;
-  k_rescore_select<<<(int)rg, RS_WARPS * 32, 0, st>>>(*model, theta_ext, u0, n_users, q.splits, P.cand, P.ccount,
-                                                      P.thr_g, ws->flags, mask_row_ptr, mask_col, k, out_ids,
+  k_rescore_select<<<(int)rg, RS_WARPS * 32, 0, st>>>(*model, theta_ext, P, mask_row_ptr, mask_col, k, out_ids,
                                                       out_scores);
   FVX_CHECK_LAUNCH("k_rescore_select");
   return 0;

@@ -286,7 +286,7 @@ class Engine:
         ids = torch.empty(n, k, dtype=torch.int32, device=self.device)
         sc = torch.empty(n, k, dtype=torch.float32, device=self.device)
         tc = self.use_tensor_cores if tc is None else tc
-        if tc and thr_scores is None and self.K + self.d + 2 <= 128 and n > 0:
+        if tc and thr_scores is None and self.K + self.d + 3 <= 128 and n > 0:
             ws = self._eval_ws(n)
             call("fvx_score_topk_tc", C.byref(self.struct()), ptr(self.theta()), u0, u1, ptr(mask_row_ptr),
                  ptr(mask_col), k, ptr(ids), ptr(sc), C.byref(ws["struct"]), stream_ptr())
@@ -312,16 +312,17 @@ class Engine:
         call("fvx_eval_ws_query", C.byref(self.struct()), n_users, C.byref(q))
         if ws is None or ws["n"] != n_users or ws["KP"] != q.KP or ws["splits"] != q.splits:
             dv = self.device
-            ws = {"n": n_users, "KP": q.KP, "splits": q.splits,
+            ws = {"n": n_users, "KP": q.KP, "splits": q.splits, "lists": q.lists,
                   "A": torch.empty(n_users * q.KP, dtype=torch.uint16, device=dv),
                   "Bm": torch.empty(self.Ic * q.KP, dtype=torch.uint16, device=dv),
-                  "unorm": torch.empty(n_users, dtype=torch.float32, device=dv),
+                  "epsa": torch.empty(n_users, dtype=torch.float32, device=dv),
+                  "nb": torch.empty(self.Ic, dtype=torch.float32, device=dv),
                   "stat": torch.zeros(2, dtype=torch.float32, device=dv),
                   "thr": torch.zeros(n_users, dtype=torch.int32, device=dv),
-                  "cand": torch.empty(n_users * q.splits * q.cap, dtype=torch.int64, device=dv),
-                  "ccount": torch.zeros(n_users * q.splits, dtype=torch.int32, device=dv),
+                  "cand": torch.empty(q.lists * q.cap, dtype=torch.int64, device=dv),
+                  "ccount": torch.zeros(q.lists, dtype=torch.int32, device=dv),
                   "flags": torch.zeros(n_users, dtype=torch.int32, device=dv)}
-            q.A, q.Bm, q.unorm, q.stat = ptr(ws["A"]), ptr(ws["Bm"]), ptr(ws["unorm"]), ptr(ws["stat"])
+            q.A, q.Bm, q.epsa, q.nb, q.stat = ptr(ws["A"]), ptr(ws["Bm"]), ptr(ws["epsa"]), ptr(ws["nb"]), ptr(ws["stat"])
             q.cand, q.ccount, q.flags, q.thr = ptr(ws["cand"]), ptr(ws["ccount"]), ptr(ws["flags"]), ptr(ws["thr"])
             ws["struct"] = q
             self._ws = ws

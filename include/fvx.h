@@ -188,20 +188,22 @@ int fvx_score_topk(const FvxModel* model, const float* theta_ext, int32_t u0, in
  * bound of the running k-th best, then the candidates are re-scored in fp32 with the
  * same arithmetic as fvx_score_topk, so both return identical ids and scores.
  * The caller owns the workspace: fill KP / splits / cap with fvx_eval_ws_query() and
- * allocate A [u_cap*KP] bf16, Bm [i_cap*KP] bf16, unorm [u_cap] f32, stat [2] f32,
- * cand [u_cap*splits*cap] u64, ccount [u_cap*splits] i32, flags [u_cap] i32, thr [u_cap] u32.
+ * allocate A [u_cap*KP] bf16, Bm [i_cap*KP] bf16, epsa [u_cap] f32, nb [i_cap] f32, stat [2] f32,
+ * cand [lists*cap] u64, ccount [lists] i32, flags [u_cap] i32, thr [u_cap] u32.
  * On return flags[u-u0] != 0 marks a user whose candidate list overflowed (or who has more
- * than ~270 train items): its output row is not valid and must be recomputed with
- * fvx_score_topk.  Needs K+d+2 <= 128. */
+ * than ~180 train items): its output row is not valid and must be recomputed with
+ * fvx_score_topk.  Needs K+d+3 <= 128. */
 typedef struct FvxEvalWs {
   uint16_t* A;
   uint16_t* Bm;
-  float* unorm;
+  float* epsa;
+  float* nb;
   float* stat;
   uint64_t* cand;
   int32_t* ccount;
   int32_t* flags;
   uint32_t* thr;
+  int64_t lists;
   int32_t u_cap, i_cap, KP, splits, cap, _pad;
 } FvxEvalWs;
 int fvx_eval_ws_query(const FvxModel* model, int32_t n_users, FvxEvalWs* ws);
