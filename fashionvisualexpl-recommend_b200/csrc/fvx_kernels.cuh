@@ -24,6 +24,12 @@ int fvx_launch_split_W(const FvxModel* m, const float* W, const int32_t* rows, l
 int fvx_launch_reduce_gE(const FvxModel* m, int parts, int gnp, float* out, cudaStream_t st);
 int fvx_launch_grad_E_tc(const FvxModel* m, const int32_t* rows, int64_t nrows, int* parts_out, cudaStream_t st);
 
+// pieces of the optimiser step shared with the item-sharded path (fvx_train_sharded.cu)
+int fvx_check_model(const FvxModel* m, const char* who);
+int fvx_launch_prep(const FvxModel* m, const int32_t* user, const int32_t* pos, const int32_t* neg, int B,
+                    cudaStream_t st);
+int fvx_launch_update(const FvxModel* m, int B, int parts, int gnp, const float* gE_src, int loss_slot,
+                      cudaStream_t st);
 int fvx_launch_score_grad(const FvxModel* m, const int32_t* user, int B, int loss_slot, int th_ks, cudaStream_t st);
 
 // x_ui for one (user row, item row, theta row): the single definition every scoring

@@ -302,6 +302,7 @@ struct UpdParams {
   int loss_slot;
   int dense;            // DENSE: sweep the whole tables
   int32_t* sync;        // [1] blocks-done counter (zero between launches)
+  const float* gE_src;  // partial gradients of E_ext (model->gE_part, or an all-reduced [D, de] buffer)
 };
 
 __device__ __forceinline__ void adam4(float4& w, float4& m, float4& v, const float4 g, float a) {
@@ -364,7 +365,7 @@ k_update(FvxModel M, UpdParams U) {
     for (int i = (b - U.nb_u - U.nb_i) * blockDim.x + threadIdx.x; i < n; i += U.nb_e * blockDim.x) {
       const int f = i / M.de, c = i - f * M.de;
       float g = 0.0f;
-      for (int p = 0; p < U.parts; ++p) g += M.gE_part[((size_t)p * M.D + f) * U.gnp + c];
+      for (int p = 0; p < U.parts; ++p) g += U.gE_src[((size_t)p * M.D + f) * U.gnp + c];
       const float e = M.E[i];
       sq += e * e;
       g += 2.0f * reg * e;
@@ -375,7 +376,7 @@ k_update(FvxModel M, UpdParams U) {
       M.E[i] = e - a * m / (sqrtf(v) + FVX_EPS);
     }
     sq = fvx_warp_sum(sq);
-    if ((threadIdx.x & 31) == 0 && sq != 0.0f) atomicAdd(M.loss + U.loss_slot, (double)(reg * sq));
+    if ((threadIdx.x & 31) == 0 && sq != 0.0f && U.loss_slot >= 0) atomicAdd(M.loss + U.loss_slot, (double)(reg * sq));
   }
   // last block: the step is complete
   __syncthreads();
@@ -438,6 +439,38 @@ int fvx_launch_score_grad(const FvxModel* m, const int32_t* user, int B, int los
   return 0;
 }
 
+int fvx_launch_prep(const FvxModel* m, const int32_t* user, const int32_t* pos, const int32_t* neg, int B,
+                    cudaStream_t st) {
+  const bool tc = m->D > 0 && m->use_tensor_cores;
+  int nb_mark = (B + 8 * PREP_TPW - 1) / (8 * PREP_TPW);     // 8 warps per block
+  if (nb_mark > fvx_num_sms() * 8) nb_mark = fvx_num_sms() * 8;
+  const int nb_e = tc ? 32 : 0;
+  k_prep<<<nb_mark + nb_e, 256, 0, st>>>(*m, user, pos, neg, B, nb_mark, tc ? fvx_tc_np(m->de) : m->de);
+  FVX_CHECK_LAUNCH("k_prep");
+  return 0;
+}
+
+int fvx_launch_update(const FvxModel* m, int B, int parts, int gnp, const float* gE_src, int loss_slot,
+                      cudaStream_t st) {
+  UpdParams U;
+  U.dense = m->adam_mode == FVX_ADAM_DENSE;
+  if (U.dense) {
+    U.nb_u = fvx_num_sms() * 4;
+    U.nb_i = fvx_num_sms() * 4;
+  } else {
+    U.nb_u = warp_grid(B, 256, 2);
+    U.nb_i = warp_grid(2LL * B, 256, 6);
+  }
+  U.nb_e = m->D > 0 ? (m->D * m->de + 255) / 256 : 0;
+  if (U.nb_e > fvx_num_sms() * 2) U.nb_e = fvx_num_sms() * 2;
+  U.parts = parts; U.gnp = gnp; U.loss_slot = loss_slot; U.sync = m->sync; U.gE_src = gE_src;
+  k_update<<<U.nb_u + U.nb_i + U.nb_e, 256, 0, st>>>(*m, U);
+  FVX_CHECK_LAUNCH("k_update");
+  return 0;
+}
+
+int fvx_check_model(const FvxModel* m, const char* who) { return check_model(m, who); }
+
 // phases of one step, in launch order (FVX_N_PHASES entries; see fvx.h)
 enum { PH_PREP = 0, PH_PROJECT, PH_SCORE_GRAD, PH_GRAD_E, PH_UPDATE, PH_COUNT };
 
@@ -470,13 +503,7 @@ static int bpr_step_impl(const FvxModel* model, const int32_t* user, const int32
 #define PHASE(i) do { if (ev) cudaEventRecord(ev[i], st); } while (0)
 
   PHASE(PH_PREP);
-  {
-    int nb_mark = (B + 8 * PREP_TPW - 1) / (8 * PREP_TPW);     // 8 warps per block
-    if (nb_mark > fvx_num_sms() * 8) nb_mark = fvx_num_sms() * 8;
-    const int nb_e = tc ? 32 : 0;
-    k_prep<<<nb_mark + nb_e, 256, 0, st>>>(M, user, pos, neg, B, nb_mark, NP);
-    FVX_CHECK_LAUNCH("k_prep");
-  }
+  if (int rc = fvx_launch_prep(&M, user, pos, neg, B, st)) return rc;
   PHASE(PH_PROJECT);
   if (tc) {
     if (int rc = fvx_launch_project_tc(&M, M.rows, 0, 2 * B, th_ks, M.TH, st)) return rc;
@@ -493,22 +520,7 @@ static int bpr_step_impl(const FvxModel* model, const int32_t* user, const int32
     if (int rc = fvx_launch_grad_E(&M, M.rows, 2 * B, &parts, st)) return rc;
   }
   PHASE(PH_UPDATE);
-  {
-    UpdParams U;
-    U.dense = M.adam_mode == FVX_ADAM_DENSE;
-    if (U.dense) {
-      U.nb_u = fvx_num_sms() * 4;
-      U.nb_i = fvx_num_sms() * 4;
-    } else {
-      U.nb_u = warp_grid(B, 256, 2);
-      U.nb_i = warp_grid(2LL * B, 256, 6);
-    }
-    U.nb_e = vis ? (M.D * M.de + 255) / 256 : 0;
-    if (U.nb_e > fvx_num_sms() * 2) U.nb_e = fvx_num_sms() * 2;
-    U.parts = parts; U.gnp = NP; U.loss_slot = loss_slot; U.sync = M.sync;
-    k_update<<<U.nb_u + U.nb_i + U.nb_e, 256, 0, st>>>(M, U);
-    FVX_CHECK_LAUNCH("k_update");
-  }
+  if (int rc = fvx_launch_update(&M, B, parts, NP, M.gE_part, loss_slot, st)) return rc;
   PHASE(PH_COUNT);
 #undef PHASE
   return 0;

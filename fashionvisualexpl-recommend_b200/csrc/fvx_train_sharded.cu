@@ -1,0 +1,274 @@
+// The BPR optimiser step with the item catalog row-sharded over R ranks (one process per GPU).
+//
+// x_uij = s_ui - s_uj is linear in the item-side quantities, s_ui = Bi[i] + <Gu[u],Gi[i]> +
+// <Tu[u], F[i]E> + F[i]Bp (BPRMF.py:74, VBPR.py:82-84), so each rank scores the (triple, side)
+// slots whose item it owns and one small all-reduce assembles every x.  Every rank sees the same
+// batch; user tables and E are replicated, Gi / Bi / F and their Adam state live on the owner.
+//
+//   phase A (fvx_bpr_step_sharded_a)  prep (touched rows, catch-up, E planes) -> projection of the
+//                                     owned slots -> partial scores S[2B] (0 for foreign slots)
+//        -- host: all-reduce(S) --
+//   phase B (fvx_bpr_step_sharded_b)  x, loss and gradient coefficients from S; gradients of the
+//                                     owned item rows; this rank's share of the user-row gradients
+//                                     into the packed run buffer RU; W of the owned slots; grad_E
+//                                     of the owned slots reduced to dE[D, de]
+//        -- host: all-reduce(RU), all-reduce(dE) --
+//   phase C (fvx_bpr_step_sharded_c)  RU rows -> user gradient accumulators; Adam on users (every
+//                                     rank, identical), owned items, E (identical)
+//
+// RU is indexed by RUN: the reference's sampler emits runs of one user (dataset.py:96-99), run_id[b]
+// = number of positions <= b where user[b] != user[b-1], minus one.  The layout depends only on the
+// batch, so it is the same on every rank and the all-reduce needs no index exchange.  Ownership of
+// the per-triple terms that are not tied to an item (softplus loss, user-side L2): the rank that
+// owns the POSITIVE item.
+#include <cuda_bf16.h>
+
+#include "fvx_common.cuh"
+#include "fvx_kernels.cuh"
+
+#define SS_WARPS 8
+
+struct SsTheta {
+  const float* p;
+  int np, ks;
+  long long ss;
+  __device__ __forceinline__ float at(long long slot, int n) const {
+    const float* q = p + slot * np + n;
+    float v = q[0];
+    for (int s = 1; s < ks; ++s) v += q[s * ss];
+    return v;
+  }
+};
+
+// phase A: one warp per (triple, side) slot this rank owns
+__global__ void __launch_bounds__(SS_WARPS * 32)
+k_partial_scores(FvxModel M, const int32_t* __restrict__ user, int B, SsTheta T, float* __restrict__ S) {
+  const int Su = M.users.stride, Si = M.items.stride, K = M.K, d = M.d;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool vis = M.D > 0;
+  const long long nw = (long long)gridDim.x * SS_WARPS;
+  for (long long slot = (long long)blockIdx.x * SS_WARPS + warp; slot < 2LL * B; slot += nw) {
+    const int32_t li = M.rows[slot];
+    const int b = (int)(slot < B ? slot : slot - B);
+    const int32_t u = user[b];
+    float s = 0.0f;
+    if (li >= 0 && u >= 0 && u < M.num_users) {
+      const float* ur = M.users.w + (size_t)u * Su;
+      const float* gi = M.items.w + (size_t)li * Si;
+      float part = 0.0f;
+      for (int c = lane; c < K; c += 32) part = fmaf(ur[c], gi[c], part);
+      if (vis)
+        for (int n = lane; n < d; n += 32) part = fmaf(ur[K + n], T.at(slot, n), part);
+      s = fvx_warp_sum(part) + gi[K] + (vis ? T.at(slot, d) : 0.0f);
+    }
+    if (lane == 0) S[slot] = s;
+  }
+}
+
+// phase B: one warp per triple; each side only if its item is owned
+__global__ void __launch_bounds__(SS_WARPS * 32)
+k_grads_sharded(FvxModel M, const int32_t* __restrict__ user, int B, int loss_slot, SsTheta T, int wnp,
+                const float* __restrict__ S, const int32_t* __restrict__ run_id, float* __restrict__ RU) {
+  __shared__ double loss_sh[SS_WARPS];
+  const int Su = M.users.stride, Si = M.items.stride, K = M.K, d = M.d, de = M.de;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float reg = M.reg, reg2 = 2.0f * M.reg;
+  const bool vis = M.D > 0;
+  const long long nw = (long long)gridDim.x * SS_WARPS;
+  double loss_acc = 0.0;
+  __nv_bfloat16* wh = reinterpret_cast<__nv_bfloat16*>(M.W_hi);
+  __nv_bfloat16* wl = reinterpret_cast<__nv_bfloat16*>(M.W_lo);
+  for (long long b = (long long)blockIdx.x * SS_WARPS + warp; b < B; b += nw) {
+    const int32_t u = user[b];
+    const float xs = S[b] - S[B + b];
+    const bool inside = (xs >= FVX_CLIP_LO) && (xs <= FVX_CLIP_HI);
+    const float coef = inside ? -1.0f / (1.0f + expf(xs)) : 0.0f;
+    const float* ur = M.users.w + (size_t)u * Su;
+    float* ru = RU + (size_t)run_id[b] * Su;
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+      const long long slot = side ? B + b : b;
+      const int32_t li = M.rows[slot];
+      const float cs = side ? -coef : coef;
+      const int nw_ = wnp > 0 ? wnp : de;
+      if (li < 0) {                 // foreign slot: no gradient from here, and a zero W row
+        if (vis)
+          for (int n = lane; n < nw_; n += 32) {
+            if (wnp > 0) { wh[slot * wnp + n] = __float2bfloat16_rn(0.0f); wl[slot * wnp + n] = __float2bfloat16_rn(0.0f); }
+            else M.W[slot * de + n] = 0.0f;
+          }
+        continue;
+      }
+      const float* gi = M.items.w + (size_t)li * Si;
+      float* gg = M.items.g + (size_t)li * Si;
+      float sq = 0.0f;
+      for (int c = lane; c < K; c += 32) {
+        const float a = ur[c], x = gi[c];
+        fvx_red_add(gg + c, cs * a + reg2 * x);
+        // the user row's data term from this side; its L2 term once per triple (positive side)
+        fvx_red_add(ru + c, cs * x + (side == 0 ? reg2 * a : 0.0f));
+        sq += x * x + (side == 0 ? a * a : 0.0f);
+      }
+      const float bi = gi[K];
+      if (lane == 0) fvx_red_add(gg + K, cs + (side == 0 ? reg2 : reg2 / 10.0f) * bi);
+      if (vis) {
+        for (int n = lane; n < nw_; n += 32) {
+          float wv = 0.0f;
+          if (n < d) {
+            const float tu = ur[K + n];
+            fvx_red_add(ru + K + n, cs * T.at(slot, n) + (side == 0 ? reg2 * tu : 0.0f));
+            if (side == 0) sq += tu * tu;
+            wv = cs * tu;
+          } else if (n == d) {
+            wv = cs;
+          }
+          if (wnp > 0) {
+            const __nv_bfloat16 h = __float2bfloat16_rn(wv);
+            wh[slot * wnp + n] = h;
+            wl[slot * wnp + n] = __float2bfloat16_rn(wv - __bfloat162float(h));
+          } else {
+            M.W[slot * de + n] = wv;
+          }
+        }
+      }
+      const float sqs = fvx_warp_sum(sq);
+      if (lane == 0) {
+        loss_acc += (double)(reg * sqs) + (double)(reg * bi * bi / (side == 0 ? 1.0f : 10.0f));
+        if (side == 0) {
+          const float z = -fminf(fmaxf(xs, FVX_CLIP_LO), FVX_CLIP_HI);
+          loss_acc += (double)(z > 13.942385f ? z : (z < -13.942385f ? expf(z) : log1pf(expf(z))));
+        }
+      }
+    }
+  }
+  if (lane == 0) loss_sh[warp] = loss_acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < SS_WARPS; ++w) s += loss_sh[w];
+    if (s != 0.0) atomicAdd(M.loss + loss_slot, s);
+  }
+}
+
+// phase C: one warp per run start adds the all-reduced run gradient into the user's accumulator
+__global__ void k_scatter_runs(FvxModel M, const int32_t* __restrict__ user, int B,
+                               const int32_t* __restrict__ run_id, const float* __restrict__ RU) {
+  const int lane = threadIdx.x & 31;
+  const int Su = M.users.stride;
+  const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long b = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < B; b += nw) {
+    const int32_t u = user[b];
+    if (b > 0 && user[b - 1] == u) continue;          // not a run start
+    const float* src = RU + (size_t)run_id[b] * Su;
+    float* g = M.users.g + (size_t)u * Su;
+    for (int c = lane; c < Su; c += 32) fvx_red_add(g + c, src[c]);   // a user may own several runs
+  }
+}
+
+static int sharded_common(const FvxModel* m, const int32_t* user, int B, const char* who) {
+  if (int rc = fvx_check_model(m, who)) return rc;
+  FVX_CHECK_ARG(user != nullptr && B >= 1 && B <= m->max_batch, "%s: bad batch", who);
+  FVX_CHECK_ARG(m->users.list_cap >= B && m->items.list_cap >= 2 * B, "%s: touched-row lists too small", who);
+  FVX_CHECK_ARG(m->rows && m->loss && m->sync, "%s: null scratch", who);
+  if (m->D > 0) {
+    FVX_CHECK_ARG(m->TH && m->gE_part && m->ge_parts > 0, "%s: VBPR scratch missing", who);
+    if (m->use_tensor_cores) FVX_CHECK_ARG(m->F_pl && m->ET_hi && m->ET_lo && m->W_hi && m->W_lo, "%s: bf16 planes missing", who);
+    else FVX_CHECK_ARG(m->F && m->W, "%s: fp32 projection needs F and W", who);
+  }
+  return 0;
+}
+
+static int sharded_ks(const FvxModel* m, int B) {
+  if (!(m->D > 0 && m->use_tensor_cores)) return 1;
+  const int NP = fvx_tc_np(m->de);
+  int ks = fvx_tc_ksplit(m, 2LL * B);
+  while (ks > 1 && (long long)ks * 2 * B * NP > m->th_cap) ks >>= 1;
+  return ks;
+}
+
+static SsTheta make_theta(const FvxModel* m, int B, int ks) {
+  SsTheta T;
+  const bool tc = m->D > 0 && m->use_tensor_cores;
+  T.p = m->TH;
+  T.np = tc ? fvx_tc_np(m->de) : m->de;
+  T.ks = tc ? ks : 1;
+  T.ss = 2LL * B * T.np;
+  return T;
+}
+
+static inline int ss_grid(long long warps_needed) {
+  long long g = (warps_needed + SS_WARPS - 1) / SS_WARPS;
+  const long long cap = (long long)fvx_num_sms() * 8;
+  if (g > cap) g = cap;
+  return g < 1 ? 1 : (int)g;
+}
+
+extern "C" {
+
+int fvx_bpr_step_sharded_a(const FvxModel* model, const int32_t* user, const int32_t* pos, const int32_t* neg,
+                           int32_t B, float* S, fvx_stream_t stream) {
+  if (int rc = sharded_common(model, user, B, "fvx_bpr_step_sharded_a")) return rc;
+  FVX_CHECK_ARG(pos && neg && S, "fvx_bpr_step_sharded_a: null pointer");
+  const FvxModel& M = *model;
+  cudaStream_t st = fvx_cu(stream);
+  if (int rc = fvx_launch_prep(&M, user, pos, neg, B, st)) return rc;
+  const int ks = sharded_ks(&M, B);
+  if (M.D > 0) {
+    if (M.use_tensor_cores) {
+      FVX_CHECK_ARG((long long)ks * 2 * B * fvx_tc_np(M.de) <= M.th_cap, "fvx_bpr_step_sharded_a: TH scratch too small");
+      if (int rc = fvx_launch_project_tc(&M, M.rows, 0, 2 * B, ks, M.TH, st)) return rc;
+    } else {
+      FVX_CHECK_ARG(2LL * B * M.de <= M.th_cap, "fvx_bpr_step_sharded_a: TH scratch too small");
+      if (int rc = fvx_launch_project(&M, M.rows, 2 * B, M.TH, st)) return rc;
+    }
+  }
+  k_partial_scores<<<ss_grid(2LL * B), SS_WARPS * 32, 0, st>>>(M, user, B, make_theta(&M, B, ks), S);
+  FVX_CHECK_LAUNCH("k_partial_scores");
+  return 0;
+}
+
+int fvx_bpr_step_sharded_b(const FvxModel* model, const int32_t* user, int32_t B, const float* S,
+                           const int32_t* run_id, float* RU, int64_t ru_rows, float* dE, int32_t loss_slot,
+                           fvx_stream_t stream) {
+  if (int rc = sharded_common(model, user, B, "fvx_bpr_step_sharded_b")) return rc;
+  FVX_CHECK_ARG(S && run_id && RU && ru_rows >= 1, "fvx_bpr_step_sharded_b: null pointer");
+  FVX_CHECK_ARG(loss_slot >= 0 && loss_slot < model->loss_slots, "fvx_bpr_step_sharded_b: loss_slot out of range");
+  const FvxModel& M = *model;
+  FVX_CHECK_ARG(M.D == 0 || dE != nullptr, "fvx_bpr_step_sharded_b: VBPR needs the dE buffer");
+  cudaStream_t st = fvx_cu(stream);
+  if (cudaMemsetAsync(RU, 0, sizeof(float) * ru_rows * M.users.stride, st) != cudaSuccess)
+    FVX_FAIL(-3, "fvx_bpr_step_sharded_b: memset failed");
+  const int ks = sharded_ks(&M, B);
+  const bool tc = M.D > 0 && M.use_tensor_cores;
+  k_grads_sharded<<<ss_grid(B), SS_WARPS * 32, 0, st>>>(M, user, B, loss_slot, make_theta(&M, B, ks),
+                                                        tc ? fvx_tc_np(M.de) : 0, S, run_id, RU);
+  FVX_CHECK_LAUNCH("k_grads_sharded");
+  if (M.D > 0) {
+    int parts = 0;
+    if (tc) {
+      if (int rc = fvx_launch_grad_E_tc(&M, M.rows, 2 * B, &parts, st)) return rc;
+    } else {
+      if (int rc = fvx_launch_grad_E(&M, M.rows, 2 * B, &parts, st)) return rc;
+    }
+    if (int rc = fvx_launch_reduce_gE(&M, parts, tc ? fvx_tc_np(M.de) : M.de, dE, st)) return rc;
+  }
+  return 0;
+}
+
+int fvx_bpr_step_sharded_c(const FvxModel* model, const int32_t* user, int32_t B, const int32_t* run_id,
+                           const float* RU, const float* dE, int32_t loss_slot, fvx_stream_t stream) {
+  if (int rc = sharded_common(model, user, B, "fvx_bpr_step_sharded_c")) return rc;
+  FVX_CHECK_ARG(run_id && RU, "fvx_bpr_step_sharded_c: null pointer");
+  const FvxModel& M = *model;
+  FVX_CHECK_ARG(M.D == 0 || dE != nullptr, "fvx_bpr_step_sharded_c: VBPR needs the reduced dE");
+  cudaStream_t st = fvx_cu(stream);
+  long long g = ((long long)B * 32 + 255) / 256;
+  if (g > (long long)fvx_num_sms() * 8) g = (long long)fvx_num_sms() * 8;
+  k_scatter_runs<<<(int)g, 256, 0, st>>>(M, user, B, run_id, RU);
+  FVX_CHECK_LAUNCH("k_scatter_runs");
+  // loss_slot < 0: the E term of the loss (VBPR.py:129) is not added (ranks other than 0, so that
+  // the per-rank losses sum to the batch loss)
+  return fvx_launch_update(&M, B, M.D > 0 ? 1 : 0, M.de, dE, loss_slot, st);
+}
+
+}  // extern "C"

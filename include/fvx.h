@@ -156,6 +156,24 @@ int fvx_bpr_step_timed(const FvxModel* model, const int32_t* user, const int32_t
                        const int32_t* neg, int32_t B, int32_t loss_slot, float* phase_ms_host,
                        fvx_stream_t stream);
 
+/* ---- the same step with the item catalog row-sharded over R ranks ----------------------
+ * Every rank calls the three phases with the SAME batch (global item ids); `model` holds the
+ * rank's shard (item_lo, item_cnt), replicated user tables and E.  x_uij = s_ui - s_uj is linear
+ * in the item-side terms, so the ranks exchange only: S (2B floats, sum), the packed user-row
+ * gradients RU and the dense dE (sums).  The host performs the three all-reduces (NCCL) between
+ * the phases.  Item ids must lie inside the catalog.
+ *   run_id[b] = index of the run of equal users that triple b belongs to (runs counted from 0
+ *   in batch order); RU has ru_rows >= number of runs rows of users.stride floats. */
+int fvx_bpr_step_sharded_a(const FvxModel* model, const int32_t* user, const int32_t* pos,
+                           const int32_t* neg, int32_t B, float* S, fvx_stream_t stream);
+int fvx_bpr_step_sharded_b(const FvxModel* model, const int32_t* user, int32_t B, const float* S,
+                           const int32_t* run_id, float* RU, int64_t ru_rows, float* dE,
+                           int32_t loss_slot, fvx_stream_t stream);
+/* loss_slot < 0: the reg*(|E|^2+|Bp|^2) loss term is not added (use on ranks other than 0) */
+int fvx_bpr_step_sharded_c(const FvxModel* model, const int32_t* user, int32_t B,
+                           const int32_t* run_id, const float* RU, const float* dE,
+                           int32_t loss_slot, fvx_stream_t stream);
+
 /* DEFERRED mode: bring every row of both tables up to the current step (call
  * before reading parameters: evaluation, checkpoint, predict_all). */
 int fvx_adam_flush(const FvxModel* model, fvx_stream_t stream);

@@ -1,0 +1,93 @@
+"""GPU: the item-sharded paths (fvx_bpr_step_sharded_a/b/c, per-shard top-k + merge) against the
+single-rank path and the oracle.  The R ranks are EMULATED on one GPU (fvx.parallel.LocalGroup:
+R engines in one process, collectives = tensor sums), because mutually waiting ranks must not be
+separate launches on one GPU; the real NCCL path is exercised by bench.py --gpus N."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import rel_err
+from oracle import bpr, evaluator as oe
+from test_gpu_parity import REL, _dev, _engine, _oracle_pair, _random_problem, _user_contiguous_batches
+
+pytestmark = pytest.mark.gpu
+
+
+def _shards(U, I, K, d, D, R, P, F, **kw):
+    from fvx.parallel import shard_bounds
+    es = []
+    for r in range(R):
+        lo, cnt = shard_bounds(I, R, r)
+        e = _engine(U, I, K, d=d, D=D, item_lo=lo, item_cnt=cnt, **kw)
+        if D:
+            e.set_features(F[lo:lo + cnt])
+        e.load_params(P)
+        es.append(e)
+    return es
+
+
+def _gather_params(es):
+    Ps = [e.params() for e in es]
+    out = {k: Ps[0][k] for k in Ps[0] if k not in ("Gi", "Bi")}
+    out["Gi"] = np.concatenate([p["Gi"] for p in Ps], 0)
+    out["Bi"] = np.concatenate([p["Bi"] for p in Ps], 0)
+    return out, Ps
+
+
+@pytest.mark.parametrize("tc", [False, True])
+@pytest.mark.parametrize("R", [2, 3])
+@pytest.mark.parametrize("K,d,D,B,mode", [(64, 20, 256, 512, "deferred"), (16, 0, 0, 256, "dense"),
+                                            (32, 20, 128, 200, "dense")])
+def test_sharded_step_matches_oracle_and_single_rank(K, d, D, B, mode, R, tc):
+    from fvx.parallel import LocalGroup, ShardedStep
+    if tc and D == 0:
+        pytest.skip("BPRMF has no projection")
+    U, I, steps, lr, reg = 500, 701, 12, 0.001, 1e-3
+    P, F, rng = _random_problem(U, I, K, d, D, seed=K + d + R)
+    es = _shards(U, I, K, d, D, R, P, F, lr=lr, reg=reg, adam_mode=mode, max_batch=B, use_tensor_cores=tc)
+    step = ShardedStep(es, LocalGroup(R))
+    # runs of distinct users, as the reference's sampler emits them (a user has at most two runs in a
+    # batch, across an epoch boundary): the sum of <= 2 run gradients per user is order-independent,
+    # which is what keeps the replicated user state bit-identical on every rank
+    batches = []
+    for _ in range(steps):
+        u = np.repeat(rng.permutation(U)[:B // 6 + 1], 6)[:B]
+        batches.append((u, rng.integers(0, I, B), rng.integers(0, I, B)))
+    P32, P64, l32, l64 = _oracle_pair(P, F, batches, reg, lr)
+    for s, b in enumerate(batches):
+        step.step(*(_dev(x) for x in b), loss_slot=s % 5)
+        got = step.read_loss(s % 5)
+        assert got == pytest.approx(l64[s], rel=REL), (s, mode, R)
+    Q, Ps = _gather_params(es)
+    for k in P64:
+        ref = P64[k]
+        dlt = np.abs(Q[k].reshape(ref.shape) - ref) / np.abs(ref).max()
+        assert (dlt > REL).mean() <= 2e-3, (k, float((dlt > REL).mean()))
+        assert dlt.max() <= max(20 * REL, 3 * rel_err(P32[k], ref)), (k, float(dlt.max()))
+    for name in ("Gu",) + (("Tu", "E", "Bp") if D else ()):       # replicated state is bit-identical on every rank
+        for p in Ps[1:]:
+            assert np.array_equal(p[name], Ps[0][name]), name
+
+
+@pytest.mark.parametrize("R", [2, 4])
+def test_sharded_topk_equals_single_rank(R):
+    from fvx.parallel import LocalGroup, sharded_topk, user_slices
+    U, I, K, d, D, k = 300, 2000, 32, 12, 64, 20
+    P, F, rng = _random_problem(U, I, K, d, D, seed=9)
+    one = _engine(U, I, K, d=d, D=D, max_batch=64)
+    one.set_features(F)
+    one.load_params(P)
+    tr = [sorted(rng.choice(I, int(rng.integers(1, 9)), replace=False).tolist()) for _ in range(U)]
+    rp = torch.as_tensor(np.concatenate([[0], np.cumsum([len(t) for t in tr])]), dtype=torch.int64).cuda()
+    cs = torch.as_tensor(np.concatenate(tr), dtype=torch.int32).cuda()
+    ids1, sc1 = one.score_topk(rp, cs, k)
+    es = _shards(U, I, K, d, D, R, P, F, max_batch=64)
+    merged = sharded_topk(es, LocalGroup(R), rp, cs, k)
+    per, _ = user_slices(U, R)
+    ids = torch.cat([m[0] for m in merged])[:U]
+    sc = torch.cat([m[1] for m in merged])[:U]
+    assert torch.equal(ids, ids1) and torch.equal(sc, sc1)
+    o_ids, o_sc = oe.masked_topk(bpr.predict_all(P, F), tr, k)
+    for u in range(U):
+        ok, msg = oe.topk_matches(ids[u].cpu().numpy(), sc[u].cpu().numpy(), o_ids[u], o_sc[u])
+        assert ok, (u, msg)
