@@ -53,6 +53,15 @@ def bytes_per_triple(K, d, D, B):
     return 24 * (3 * K + d + 2) + 8 * D + 12 + 24.0 * (D * d + D) / B
 
 
+def load_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/traffic.json)."""
+    try:
+        with open(os.path.join(REPO, "profiles", "traffic.json")) as f:
+            return json.load(f).get(kernel)
+    except Exception:
+        return None
+
+
 def load_peaks():
     try:
         with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as f:
@@ -74,7 +83,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                          "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -200,12 +209,14 @@ def run_reference(args):
 
 def workload_config(args, n):
     return {"workload": "VBPR train step, K=%d d=%d D=%d, %d users x %d items (BASELINE configs[1]), "
-                        "B=%d triples/step, on-device Philox sampler, %s Adam"
+                        "B=%d triples/step per GPU, on-device Philox sampler, %s Adam"
                         % (args.embed_k, args.embed_d, args.feat_dim, args.users, args.items, args.batch,
                            args.adam_mode),
             "users": args.users, "items": args.items, "K": args.embed_k, "d": args.embed_d, "D": args.feat_dim,
-            "batch": args.batch, "adam_mode": args.adam_mode, "tensor_cores": bool(args.tensor_cores),
-            "parallelism": "1 GPU" if n == 1 else "%d independent replicas" % n,
+            "batch": args.batch * n, "adam_mode": args.adam_mode, "tensor_cores": bool(args.tensor_cores),
+            "parallelism": "1 GPU" if n == 1 else
+            "item catalog row-sharded over %d GPUs (users, E replicated); NCCL all-reduce of partial scores, "
+            "user-row gradients and dE; eval: per-shard top-k + all-to-all merge" % n,
             "l2": "F (%.2f GB) and the tables exceed the 126 MB L2; rows are gathered at random, no flush needed"
                   % (args.items * args.feat_dim * 4 / 1e9)}
 
@@ -216,131 +227,177 @@ def run_fvx(args):
     from fvx.build import build
     from fvx.dataset.dataset import DataLoader
     from fvx.engine import Engine
+    from fvx import parallel
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.init_process_group("nccl", device_id=dev)
     if rank == 0:
         build()
     if world > 1:
         dist.barrier()
-    dev = torch.device("cuda", local)
-    torch.cuda.set_device(dev)
-    B, K, d, D = args.batch, args.embed_k, args.embed_d, args.feat_dim
+    # weak scaling: the per-GPU batch is fixed, the global batch grows with the number of ranks;
+    # the item catalog (Gi, Bi, F + Adam state) is row-sharded, users and E are replicated
+    B, K, d, D = args.batch * world, args.embed_k, args.embed_d, args.feat_dim
 
     inter = make_problem(args)
-    p = argparse.Namespace(dataset="synthetic", batch_size=B, epochs=10 ** 6, sampler="device", seed=rank)
+    p = argparse.Namespace(dataset="synthetic", batch_size=B, epochs=10 ** 6, sampler="device", seed=0)
     data = DataLoader(p, interactions=inter)
+    lo, cnt = parallel.shard_bounds(args.items, world, rank)
     e = Engine(args.users, args.items, K, d=d, D=D, lr=1e-3, reg=1e-5, adam_mode=args.adam_mode,
-               max_batch=B, device=str(dev), seed=0, use_tensor_cores=bool(args.tensor_cores))
+               max_batch=B, device=str(dev), seed=0, use_tensor_cores=bool(args.tensor_cores),
+               item_lo=lo, item_cnt=cnt)
     if D:
-        e.set_features(make_features_device(args.items, D, dev))
+        F = make_features_device(args.items, D, dev)          # same generator seed on every rank
+        e.set_features(F[lo:lo + cnt].contiguous(), keep_fp32=not args.tensor_cores)
+        del F
+    sharded = parallel.ShardedStep([e], parallel.DistGroup()) if world > 1 else None
     batches = data.next_triple_batch(str(dev))
+
+    def do_step(b, slot=0):
+        if sharded is not None:
+            sharded.step(*b, loss_slot=slot)
+        else:
+            e.step(*b, loss_slot=slot)
+
+    def loss(slot=0):
+        return sharded.read_loss(slot) if sharded is not None else e.read_loss(slot)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
     for _ in range(args.warmup):
-        e.step(*next(batches))
-    launches_per_step = 5 if D else 3      # prep, projection, score+grad, grad_E, update
+        do_step(next(batches))
     clocks = ClockSampler(local)
     barrier()
     clocks.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ep0 = data_epochs = 0
     ev0.record()
     for _ in range(args.steps):
-        e.step(*next(batches))
+        do_step(next(batches))
     ev1.record()
     barrier()
-    ms = ev0.elapsed_time(ev1)
+    ms = max_over_ranks(ev0.elapsed_time(ev1))
+    # the timed region can be shorter than one nvidia-smi sampling period: keep the identical load
+    # running (untimed) until the sampler has seen it for ~0.5 s
+    t_load = time.perf_counter()
+    while time.perf_counter() - t_load < 0.5:
+        for _ in range(20):
+            do_step(next(batches))
+        torch.cuda.synchronize()
     clk = clocks.stop()
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    value = world * args.steps * B / ms * 1e3
+    clk["note"] = "sampled during the timed steps and %.1f s of the same steps run untimed right after" % 0.5
+    value = args.steps * B / ms * 1e3
+    # kernels of the timed region: 5 per step (prep, projection, score+grad, grad_E, update), 8 on the
+    # sharded path (+ partial scores, reduce, scatter), 2 per generated epoch
     epochs_in_region = (args.steps * B) / max(data.num_train, 1)
-    gpu_launches = args.steps * launches_per_step + int(np.ceil(epochs_in_region)) * 3
+    per_step = (5 if D else 3) if world == 1 else (8 if D else 5)
+    gpu_launches = args.steps * per_step + int(np.ceil(epochs_in_region)) * 2
 
     # ---- end to end through the reference-facing call: host batches in, float loss out ----
     hb = [tuple(x.cpu().pin_memory() for x in next(batches)) for _ in range(min(args.steps, 20))]
     barrier()
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
     for b in hb[:2]:
-        e.step(*(x.to(dev, non_blocking=True) for x in b)); e.read_loss(0)
+        do_step(tuple(x.to(dev, non_blocking=True) for x in b)); loss(0)
     barrier()
     t0.record()
     for b in hb:
-        e.step(*(x.to(dev, non_blocking=True) for x in b), loss_slot=0)
-        e.read_loss(0)                                   # D2H of the batch loss (BPRMF.py:125)
+        do_step(tuple(x.to(dev, non_blocking=True) for x in b), 0)
+        loss(0)                                          # D2H of the batch loss (BPRMF.py:125)
     t1.record()
     barrier()
-    e2e_ms = t0.elapsed_time(t1)
-    if world > 1:
-        t = torch.tensor([e2e_ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
-    e2e_value = world * len(hb) * B / e2e_ms * 1e3
+    e2e_ms = max_over_ranks(t0.elapsed_time(t1))
+    e2e_value = len(hb) * B / e2e_ms * 1e3
 
-    # ---- per-kernel shares (profiling entry point; separate from the timed region) ----------
-    phases = {}
-    for _ in range(8):
-        for k_, v in e.step_timed(*next(batches)).items():
-            phases[k_] = phases.get(k_, 0.0) + v / 8
     hbm, tf_burst, tf_sus, src = load_peaks()
     step_ms = ms / args.steps
     bpt = bytes_per_triple(K, d, D, B)
-    dom = max(phases, key=phases.get)
-    rows_bytes = 2 * B * D * 4.0
-    tbl = 4.0 * (3 * K + d + 2)                      # floats of the three rows of a triple, once
-    kern_bytes = {"project": rows_bytes + 2 * B * e.de * 4.0, "grad_E": rows_bytes + 2 * B * e.de * 4.0,
-                  "score_grad": B * 2 * tbl, "update": B * 4 * tbl + (28.0 * D * e.de if D else 0),
-                  "prep": B * (12.0 + 3 * tbl)}
-    ach = kern_bytes.get(dom, 0.0) / (phases[dom] * 1e-3) / 1e9 if phases[dom] > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm, "unit": "GB/s",
-                "frac": ach / hbm, "traffic": None, "peak_source": src,
-                "kernel_ms": phases[dom], "phase_ms": phases}
-    step_roof = {"achieved": B * bpt / (step_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
-                 "bytes_per_triple": bpt}
-    step_roof["frac"] = step_roof["achieved"] / hbm
-
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
             "clocks": clk, "gpu_launches": gpu_launches,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 12 * B, "d2h_bytes_per_step": 8,
-                    "steps": len(hb)},
-            "roofline": roofline, "step_roofline": step_roof}
+                    "steps": len(hb)}}
 
-    # ---- evaluation: users/s full-catalog top-k, train items masked -------------------------
+    # ---- per-kernel shares (profiling entry point; single rank; separate from the timed region) ----
+    if world == 1:
+        phases = {}
+        for _ in range(8):
+            for k_, v in e.step_timed(*next(batches)).items():
+                phases[k_] = phases.get(k_, 0.0) + v / 8
+        dom = max(phases, key=phases.get)
+        rows_bytes = 2 * B * D * 4.0
+        tbl = 4.0 * (3 * K + d + 2)                      # floats of the three rows of a triple, once
+        kern_bytes = {"project": rows_bytes + 2 * B * e.de * 4.0, "grad_E": rows_bytes + 2 * B * e.de * 4.0,
+                      "score_grad": B * 2 * tbl, "update": B * 4 * tbl + (28.0 * D * e.de if D else 0),
+                      "prep": B * (12.0 + 3 * tbl)}
+        kname = {"project": "k_proj_fwd_tc" if args.tensor_cores else "k_project",
+                 "grad_E": "k_grad_E_tc" if args.tensor_cores else "k_grad_E", "score_grad": "k_score_grad",
+                 "update": "k_update", "prep": "k_prep"}[dom]
+        ach = kern_bytes.get(dom, 0.0) / (phases[dom] * 1e-3) / 1e9 if phases[dom] > 0 else 0.0
+        line["roofline"] = {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": hbm, "unit": "GB/s",
+                            "frac": ach / hbm, "traffic": load_traffic(kname), "peak_source": src,
+                            "algorithmic_bytes_per_launch": kern_bytes.get(dom, 0.0),
+                            "kernel_ms": phases[dom], "phase_ms": phases}
+    step_roof = {"achieved": B * bpt / world / (step_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                 "bytes_per_triple": bpt, "note": "algorithmic bytes of the whole step per GPU / step time"}
+    step_roof["frac"] = step_roof["achieved"] / hbm
+    line["step_roofline"] = step_roof
+
+    # ---- evaluation: users/s full-catalog top-k, train items masked (all users) --------------------
     if not args.no_eval:
         st = data.device_state(str(dev))
         e.flush()
         torch.cuda.synchronize()
-        nu = min(args.users, 8192)
-        e.score_topk(st["row_ptr"], st["col_sorted"], args.top_k, u0=0, u1=256)      # warm-up
+
+        def sweep():
+            e.theta(refresh=True)
+            if world > 1:
+                return parallel.sharded_topk([e], parallel.DistGroup(), st["row_ptr"], st["col_sorted"], args.top_k)
+            return e.score_topk(st["row_ptr"], st["col_sorted"], args.top_k)
+
+        for _ in range(2):
+            sweep()                                       # warm-up (workspace allocation)
         barrier()
-        a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        e.theta(refresh=True)
-        ids, sc = e.score_topk(st["row_ptr"], st["col_sorted"], args.top_k, u0=0, u1=nu)
-        b2.record()
-        barrier()
-        ems = a.elapsed_time(b2)
+        best = 1e30
+        for _ in range(3):
+            a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            sweep()
+            b2.record()
+            barrier()
+            best = min(best, max_over_ranks(a.elapsed_time(b2)))
+        nu = args.users
         flops_user = 2.0 * args.items * (K + d) + 2.0 * args.items
-        line["eval"] = {"metric": "users/s full-catalog top-%d eval" % args.top_k, "value": nu / ems * 1e3,
-                        "unit": "users/s", "users": nu, "ms": ems, "kernel": "k_score_topk (fp32 CUDA cores)",
-                        "roofline": {"bound": "tensor", "achieved": nu * flops_user / (ems * 1e-3) / 1e12,
-                                     "peak": tf_burst, "unit": "TFLOP/s",
-                                     "frac": nu * flops_user / (ems * 1e-3) / 1e12 / tf_burst}}
+        tfl = nu * flops_user / (best * 1e-3) / 1e12
+        line["eval"] = {"metric": "users/s full-catalog top-%d eval" % args.top_k, "value": nu / best * 1e3,
+                        "unit": "users/s", "users": nu, "ms": best,
+                        "kernel": "k_topk_tc (tcgen05 bf16 filter + exact fp32 re-scoring)" if args.tensor_cores
+                        else "k_score_topk (fp32 CUDA cores)",
+                        "fallback_rows": getattr(e, "tc_overflow_rows", 0),
+                        "includes": "theta = F*E projection of the catalog, score sweep, mask, top-k"
+                                    + (", all-to-all exchange + merge" if world > 1 else ""),
+                        "roofline": {"bound": "tensor", "achieved": tfl, "peak": tf_burst * world, "unit": "TFLOP/s",
+                                     "frac": tfl / (tf_burst * world)}}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        F_host = e.F.cpu().numpy() if D else None
+        F_host = None
+        if D:
+            F_host = make_features_device(args.items, D, dev).cpu().numpy()
         v, n, el = cpu_oracle_rate(args, inter, F_host, args.cpu_seconds, B)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": len(os.sched_getaffinity(0)), "kind": "port",
                                 "sample": "%d steps of B=%d in %.1f s on the full tables (NumPy oracle of the "
