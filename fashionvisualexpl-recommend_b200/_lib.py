@@ -33,7 +33,7 @@ class FvxModel(C.Structure):
                 ("vE", _p), ("gE_part", _p), ("ge_parts", C.c_int32), ("_pad0", C.c_int32), ("F", _p),
                 ("F_pl", _p), ("ET_hi", _p), ("ET_lo", _p), ("W_hi", _p), ("W_lo", _p),
                 ("step", _p), ("loss", _p), ("loss_slots", C.c_int32), ("_pad1", C.c_int32), ("TH", _p),
-                ("th_cap", C.c_int64), ("W", _p), ("rows", _p), ("sync", _p), ("max_batch", C.c_int32),
+                ("th_cap", C.c_int64), ("W", _p), ("rows", _p), ("sync", _p), ("cmap", _p), ("max_batch", C.c_int32),
                 ("use_tensor_cores", C.c_int32)]
 
 
@@ -65,6 +65,7 @@ PROTOTYPES = {
     "fvx_project": (C.c_int, [_MP, _p, _p]),
     "fvx_predict_all": (C.c_int, [_MP, _p, _i32, _i32, _p, _p]),
     "fvx_score_topk": (C.c_int, [_MP, _p, _i32, _i32, _p, _p, _i32, _p, _p, _i32, _p, _p, _p]),
+    "fvx_score_topk_users": (C.c_int, [_MP, _p, _p, _i32, _p, _p, _i32, _p, _p, _p]),
     "fvx_eval_ws_query": (C.c_int, [_MP, _i32, C.POINTER(FvxEvalWs)]),
     "fvx_score_topk_tc": (C.c_int, [_MP, _p, _i32, _i32, _p, _p, _i32, _p, _p, C.POINTER(FvxEvalWs), _p]),
     "fvx_score_pairs": (C.c_int, [_MP, _p, _p, _p, _i64, _p, _p]),

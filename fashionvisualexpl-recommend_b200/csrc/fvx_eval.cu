@@ -78,7 +78,8 @@ __global__ void __launch_bounds__(TK_TILE)
 k_score_topk(FvxModel M, const float* __restrict__ theta, int u0, int u1,
              const int64_t* __restrict__ mask_row_ptr, const int32_t* __restrict__ mask_col, int k,
              int32_t* __restrict__ out_ids, float* __restrict__ out_scores, int n_thr,
-             const float* __restrict__ thr_scores, int32_t* __restrict__ out_counts) {
+             const float* __restrict__ thr_scores, int32_t* __restrict__ out_counts,
+             const int32_t* __restrict__ ulist) {   // ulist: user of local index j (nullptr: j itself)
   extern __shared__ __align__(16) unsigned char tk_smem[];
   const int Su = M.users.stride, Si = M.items.stride, K = M.K, d = M.d, de = M.de;
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(tk_smem);          // [UB][CAP]
@@ -94,7 +95,7 @@ k_score_topk(FvxModel M, const float* __restrict__ theta, int u0, int u1,
     __syncthreads();
     for (int e = tid; e < TK_UB * Su; e += TK_TILE) {
       const int u = e / Su, c = e - u * Su;
-      us[e] = (u < nu) ? M.users.w[(size_t)(ub + u) * Su + c] : 0.0f;
+      us[e] = (u < nu) ? M.users.w[(size_t)(ulist ? ulist[ub + u] : ub + u) * Su + c] : 0.0f;
     }
     if (tid < TK_UB) { tau[tid] = -CUDART_INF_F; cnt[tid] = 0; }
     if (tid < TK_UB * TK_MAXTHR) {
@@ -158,7 +159,7 @@ k_score_topk(FvxModel M, const float* __restrict__ theta, int u0, int u1,
 #pragma unroll
           for (int t = 0; t < TK_MAXTHR; ++t) cl[u][t] += (s >= thr[u * TK_MAXTHR + t]) ? 1 : 0;
           if (s > tau[u]) {
-            const int gu = ub + u;
+            const int gu = ulist ? ulist[ub + u] : ub + u;
             if (!fvx_in_sorted(mask_col, mask_row_ptr[gu], mask_row_ptr[gu + 1], gid)) {
               const int p = atomicAdd(&cnt[u], 1);
               if (p < TK_CAP) keys[u * TK_CAP + p] = topk_key(s, gid);
@@ -208,7 +209,7 @@ k_score_topk(FvxModel M, const float* __restrict__ theta, int u0, int u1,
         }
       __syncthreads();
       if (warp < nu) {
-        const int gu = ub + warp;
+        const int gu = ulist ? ulist[ub + warp] : ub + warp;
         const int64_t a = mask_row_ptr[gu], b = mask_row_ptr[gu + 1];
         int sub[TK_MAXTHR] = {0, 0, 0, 0};
         for (int64_t e = a + lane; e < b; e += 32) {
@@ -224,7 +225,7 @@ k_score_topk(FvxModel M, const float* __restrict__ theta, int u0, int u1,
           int v = sub[t];
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-          if (lane == 0 && t < n_thr) out_counts[(size_t)(gu - u0) * n_thr + t] = cge[warp * TK_MAXTHR + t] - v;
+          if (lane == 0 && t < n_thr) out_counts[(size_t)(ub + warp - u0) * n_thr + t] = cge[warp * TK_MAXTHR + t] - v;
         }
       }
     }
@@ -293,12 +294,12 @@ int fvx_score_pairs(const FvxModel* model, const float* theta_ext, const int32_t
   return 0;
 }
 
-int fvx_score_topk(const FvxModel* model, const float* theta_ext, int32_t u0, int32_t u1,
-                   const int64_t* mask_row_ptr, const int32_t* mask_col, int32_t k, int32_t* out_ids,
-                   float* out_scores, int32_t n_thr, const float* thr_scores, int32_t* out_counts,
-                   fvx_stream_t stream) {
+static int score_topk_impl(const FvxModel* model, const float* theta_ext, int32_t u0, int32_t u1,
+                           const int32_t* ulist, const int64_t* mask_row_ptr, const int32_t* mask_col, int32_t k,
+                           int32_t* out_ids, float* out_scores, int32_t n_thr, const float* thr_scores,
+                           int32_t* out_counts, fvx_stream_t stream) {
   if (int rc = check_eval_model(model, theta_ext, "fvx_score_topk")) return rc;
-  FVX_CHECK_ARG(0 <= u0 && u0 <= u1 && u1 <= model->num_users, "fvx_score_topk: bad user range");
+  FVX_CHECK_ARG(0 <= u0 && u0 <= u1 && (ulist != nullptr || u1 <= model->num_users), "fvx_score_topk: bad user range");
   FVX_CHECK_ARG(k >= 1 && k <= 128, "fvx_score_topk: k=%d outside [1,128]", k);
   FVX_CHECK_ARG(mask_row_ptr && mask_col && out_ids && out_scores, "fvx_score_topk: null pointer");
   FVX_CHECK_ARG(n_thr >= 0 && n_thr <= TK_MAXTHR, "fvx_score_topk: n_thr=%d outside [0,%d]", n_thr, TK_MAXTHR);
@@ -316,9 +317,25 @@ int fvx_score_topk(const FvxModel* model, const float* theta_ext, int32_t u0, in
   long long g = ((long long)(u1 - u0) + TK_UB - 1) / TK_UB;
   if (g > (long long)fvx_num_sms() * 4) g = (long long)fvx_num_sms() * 4;
   k_score_topk<<<(int)g, TK_TILE, smem, fvx_cu(stream)>>>(*model, theta_ext, u0, u1, mask_row_ptr, mask_col, k,
-                                                          out_ids, out_scores, n_thr, thr_scores, out_counts);
+                                                          out_ids, out_scores, n_thr, thr_scores, out_counts, ulist);
   FVX_CHECK_LAUNCH("k_score_topk");
   return 0;
+}
+
+int fvx_score_topk(const FvxModel* model, const float* theta_ext, int32_t u0, int32_t u1,
+                   const int64_t* mask_row_ptr, const int32_t* mask_col, int32_t k, int32_t* out_ids,
+                   float* out_scores, int32_t n_thr, const float* thr_scores, int32_t* out_counts,
+                   fvx_stream_t stream) {
+  return score_topk_impl(model, theta_ext, u0, u1, nullptr, mask_row_ptr, mask_col, k, out_ids, out_scores, n_thr,
+                         thr_scores, out_counts, stream);
+}
+
+int fvx_score_topk_users(const FvxModel* model, const float* theta_ext, const int32_t* users, int32_t n,
+                         const int64_t* mask_row_ptr, const int32_t* mask_col, int32_t k, int32_t* out_ids,
+                         float* out_scores, fvx_stream_t stream) {
+  FVX_CHECK_ARG(users != nullptr && n >= 0, "fvx_score_topk_users: bad user list");
+  return score_topk_impl(model, theta_ext, 0, n, users, mask_row_ptr, mask_col, k, out_ids, out_scores, 0, nullptr,
+                         nullptr, stream);
 }
 
 int fvx_topk_merge(const int32_t* ids, const float* scores, int64_t n_users, int32_t R, int32_t k,

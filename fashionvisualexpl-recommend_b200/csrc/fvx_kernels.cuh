@@ -17,12 +17,13 @@ int fvx_tc_ksplit(const FvxModel* m, long long nrows);
 int fvx_launch_split_E(const FvxModel* m, cudaStream_t st);
 int fvx_launch_split_planes(const float* src, uint16_t* dst, long long n_rows, int D, cudaStream_t st);
 int fvx_launch_project_tc(const FvxModel* m, const int32_t* rows, int row0, int64_t nrows, int ksplit, float* out,
-                          cudaStream_t st);
+                          cudaStream_t st, const int32_t* nrows_dev = nullptr);
 int fvx_launch_reduce_partials(const float* part, long long nrows, int NP, int ks, int de, float* out,
                                cudaStream_t st);
 int fvx_launch_split_W(const FvxModel* m, const float* W, const int32_t* rows, long long nrows, cudaStream_t st);
 int fvx_launch_reduce_gE(const FvxModel* m, int parts, int gnp, float* out, cudaStream_t st);
-int fvx_launch_grad_E_tc(const FvxModel* m, const int32_t* rows, int64_t nrows, int* parts_out, cudaStream_t st);
+int fvx_launch_grad_E_tc(const FvxModel* m, const int32_t* rows, int64_t nrows, int* parts_out, cudaStream_t st,
+                         const int32_t* nrows_dev = nullptr);
 
 // pieces of the optimiser step shared with the item-sharded path (fvx_train_sharded.cu)
 int fvx_check_model(const FvxModel* m, const char* who);

@@ -46,7 +46,8 @@ __device__ __forceinline__ void pt_cp_arrive(uint64_t* bar) {   // arrives when 
 struct ProjFwdParams {
   const uint8_t* Fpl;   // interleaved planes
   const int32_t* rows;  // nullptr: identity (catalog row row0 + r)
-  long long nrows;
+  long long nrows;      // rows the buffers are laid out for
+  const int32_t* nrows_dev;   // optional: the number of valid rows lives on the device (<= nrows)
   int row0;
   int D;
   int NP;               // padded output width (multiple of 32)
@@ -90,7 +91,9 @@ k_proj_fwd_tc(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int n_units = P.n_tiles * P.ksplit;
+  long long nvalid = P.nrows;
+  if (P.nrows_dev) { const long long v = *P.nrows_dev; nvalid = v < nvalid ? v : nvalid; }
+  const int n_units = (int)((nvalid + PT_BM - 1) / PT_BM) * P.ksplit;
 
   if (warp < 4) {
     // ===== producers: 16 lanes copy the 256 bytes (hi | lo) of one (row, chunk); a round of the
@@ -108,7 +111,7 @@ k_proj_fwd_tc(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant_
       for (int it = 0; it < 16; ++it) {
         const long long r = (long long)tile * PT_BM + it * 8 + sub;
         long long item = 0;
-        if (r < P.nrows) item = P.rows ? (long long)P.rows[r] : (long long)P.row0 + r;
+        if (r < nvalid) item = P.rows ? (long long)P.rows[r] : (long long)P.row0 + r;
         if (item < 0) item = 0;               // slot of another rank's item: any valid row, result unused
         src[it] = P.Fpl + (size_t)item * row_bytes + e * 16;
       }
@@ -174,7 +177,7 @@ k_proj_fwd_tc(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant_
       const long long row = (long long)tile * PT_BM + quad * 32 + lane;
       mbar_wait(&t_full[acc], acc_phase);
       tc_fence_after();
-      float* dst = P.out + ((size_t)ks * P.nrows + (size_t)(row < P.nrows ? row : 0)) * P.NP;
+      float* dst = P.out + ((size_t)ks * P.nrows + (size_t)(row < nvalid ? row : 0)) * P.NP;
       for (int n0 = 0; n0 < P.NP; n0 += 32) {
         float sum[32];
         for (int a = 0; a < P.nacc; ++a) {
@@ -184,7 +187,7 @@ k_proj_fwd_tc(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < 32; ++j) sum[j] = a == 0 ? __uint_as_float(v[j]) : sum[j] + __uint_as_float(v[j]);
         }
-        if (row < P.nrows) {
+        if (row < nvalid) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4)
             *reinterpret_cast<float4*>(dst + n0 + j) = make_float4(sum[j], sum[j + 1], sum[j + 2], sum[j + 3]);
@@ -209,10 +212,12 @@ struct GradEParams {
   const uint8_t* Fpl;
   const int32_t* rows;
   long long nrows;
+  const int32_t* nrows_dev;   // optional: the number of valid rows lives on the device (<= nrows)
+  int n_groups;         // row groups of the launch
   int D, NP;
   int fgs;              // features per CTA (multiple of 128)
   int nfg;              // feature groups = D / fgs
-  int rows_per_group;   // multiple of GE_RT
+  int rows_per_group;   // multiple of GE_RT (recomputed on the device when nrows_dev is set)
   int stages;
   int w_atoms;          // 64-column sub-tiles of the W tile (1 for NP <= 64)
   int w_sw;             // swizzle of the W tile: TC_SWZ_64B (NP == 32) or TC_SWZ_128B
@@ -254,9 +259,18 @@ k_grad_E_tc(const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
 
   const int rg = blockIdx.x / P.nfg, fg = blockIdx.x - rg * P.nfg;
-  const long long r_begin = (long long)rg * P.rows_per_group;
-  long long r_end = r_begin + P.rows_per_group;
-  if (r_end > P.nrows) r_end = P.nrows;
+  long long nvalid = P.nrows;
+  long long rpg = P.rows_per_group;
+  if (P.nrows_dev) {
+    const long long v = *P.nrows_dev;
+    nvalid = v < nvalid ? v : nvalid;
+    rpg = (nvalid + P.n_groups - 1) / P.n_groups;
+    rpg = (rpg + GE_RT - 1) / GE_RT * GE_RT;
+    if (rpg < GE_RT) rpg = GE_RT;
+  }
+  const long long r_begin = (long long)rg * rpg;
+  long long r_end = r_begin + rpg;
+  if (r_end > nvalid) r_end = nvalid;
   const int n_tiles = r_end > r_begin ? (int)((r_end - r_begin + GE_RT - 1) / GE_RT) : 0;
 
   if (warp < 4) {
@@ -272,7 +286,7 @@ k_grad_E_tc(const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ 
       for (int j = 0; j < GE_RT / 4; ++j) {
         const long long r = r0 + j * 4 + warp;
         long long item = 0;
-        if (r < P.nrows) item = P.rows ? (long long)P.rows[r] : r;
+        if (r < nvalid) item = P.rows ? (long long)P.rows[r] : r;
         if (item < 0) item = 0;
         src[j] = P.Fpl + (size_t)item * row_bytes + (size_t)fg * P.fgs * 4;
       }
@@ -422,7 +436,7 @@ int fvx_launch_split_E(const FvxModel* m, cudaStream_t st) {
 
 // out: [ksplit][nrows][NP] fp32 partials (ksplit from fvx_tc_ksplit)
 int fvx_launch_project_tc(const FvxModel* m, const int32_t* rows, int row0, int64_t nrows, int ksplit, float* out,
-                          cudaStream_t st) {
+                          cudaStream_t st, const int32_t* nrows_dev) {
   FVX_CHECK_ARG(m->F_pl && m->ET_hi && m->ET_lo, "tensor-core projection: bf16 planes missing");
   FVX_CHECK_ARG(m->D % PT_KC == 0, "tensor-core projection: D=%d must be a multiple of %d", m->D, PT_KC);
   const int NP = fvx_tc_np(m->de);
@@ -438,7 +452,7 @@ int fvx_launch_project_tc(const FvxModel* m, const int32_t* rows, int row0, int6
   if (rc != 0) FVX_FAIL(-4, "tensor-core projection: cuTensorMapEncodeTiled failed");
   ProjFwdParams P;
   P.Fpl = reinterpret_cast<const uint8_t*>(m->F_pl); P.D = m->D;
-  P.rows = rows; P.row0 = row0; P.nrows = nrows; P.NP = NP; P.ksplit = ksplit; P.chunks = chunks_total / ksplit;
+  P.rows = rows; P.row0 = row0; P.nrows = nrows; P.nrows_dev = nrows_dev; P.NP = NP; P.ksplit = ksplit; P.chunks = chunks_total / ksplit;
   P.n_tiles = (int)((nrows + PT_BM - 1) / PT_BM);
   P.out = out;
   P.nacc = 256 / NP < 4 ? (256 / NP < 1 ? 1 : 256 / NP) : 4;
@@ -461,7 +475,8 @@ int fvx_launch_project_tc(const FvxModel* m, const int32_t* rows, int row0, int6
 }
 
 // gE_part[p][D][NP] = partial sums; W planes [nrows][NP] bf16.  *parts_out = row groups written.
-int fvx_launch_grad_E_tc(const FvxModel* m, const int32_t* rows, int64_t nrows, int* parts_out, cudaStream_t st) {
+int fvx_launch_grad_E_tc(const FvxModel* m, const int32_t* rows, int64_t nrows, int* parts_out, cudaStream_t st,
+                         const int32_t* nrows_dev) {
   FVX_CHECK_ARG(m->F_pl && m->W_hi && m->W_lo && m->gE_part, "tensor-core grad_E: buffers missing");
   FVX_CHECK_ARG(m->D % 128 == 0, "tensor-core grad_E: D=%d must be a multiple of 128", m->D);
   const int NP = fvx_tc_np(m->de);
@@ -487,7 +502,7 @@ int fvx_launch_grad_E_tc(const FvxModel* m, const int32_t* rows, int64_t nrows, 
   if (rc != 0) FVX_FAIL(-4, "tensor-core grad_E: cuTensorMapEncodeTiled failed");
   GradEParams P;
   P.Fpl = reinterpret_cast<const uint8_t*>(m->F_pl);
-  P.rows = rows; P.nrows = nrows; P.D = m->D; P.NP = NP; P.fgs = fgs; P.nfg = nfg; P.rows_per_group = (int)rpg;
+  P.rows = rows; P.nrows = nrows; P.nrows_dev = nrows_dev; P.n_groups = parts; P.D = m->D; P.NP = NP; P.fgs = fgs; P.nfg = nfg; P.rows_per_group = (int)rpg;
   P.w_atoms = NP <= 64 ? 1 : NP / 64;
   P.w_sw = NP == 32 ? TC_SWZ_64B : TC_SWZ_128B;
   P.out = m->gE_part;

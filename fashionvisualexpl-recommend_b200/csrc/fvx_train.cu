@@ -384,7 +384,8 @@ k_update(FvxModel M, UpdParams U) {
     __threadfence();
     const int prev = atomicAdd(U.sync, 1);
     if (prev == (int)gridDim.x - 1) {
-      *U.sync = 0;
+      U.sync[0] = 0;
+      U.sync[1] = 0;                     // owned-slot counter of the sharded step
       *M.step += 1;
       *M.users.count = 0;
       *M.items.count = 0;

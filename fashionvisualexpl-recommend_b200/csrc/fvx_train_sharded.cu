@@ -40,27 +40,58 @@ struct SsTheta {
   }
 };
 
-// phase A: one warp per (triple, side) slot this rank owns
+// The slots whose item this rank owns, compacted (order arbitrary): crow[j] = local item row,
+// cslot[j] = slot, cpos[slot] = j (or -1); *count = number of owned slots.  The projection and
+// grad_E kernels then touch only owned rows (2B/R of them), indexed by j.
+__global__ void k_compact_owned(FvxModel M, int B, int32_t* __restrict__ count) {
+  int32_t* crow = M.cmap;
+  int32_t* cslot = M.cmap + 2 * (size_t)M.max_batch;
+  int32_t* cpos = M.cmap + 4 * (size_t)M.max_batch;
+  const int lane = threadIdx.x & 31;
+  const long long n = 2LL * B, npad = (n + 31) & ~31LL;
+  for (long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x; slot < npad;
+       slot += (long long)gridDim.x * blockDim.x) {
+    const int32_t li = slot < n ? M.rows[slot] : -1;
+    const uint32_t b = __ballot_sync(0xffffffffu, li >= 0);
+    int base = 0;
+    if (b) {
+      const int leader = __ffs(b) - 1;
+      if (lane == leader) base = atomicAdd(count, __popc(b));
+      base = __shfl_sync(0xffffffffu, base, leader);
+    }
+    if (li >= 0) {
+      const int j = base + __popc(b & ((1u << lane) - 1u));
+      crow[j] = li;
+      cslot[j] = (int32_t)slot;
+      cpos[slot] = j;
+    } else if (slot < n) {
+      cpos[slot] = -1;
+    }
+  }
+}
+
+// phase A: one warp per owned slot
 __global__ void __launch_bounds__(SS_WARPS * 32)
-k_partial_scores(FvxModel M, const int32_t* __restrict__ user, int B, SsTheta T, float* __restrict__ S) {
+k_partial_scores(FvxModel M, const int32_t* __restrict__ user, int B, SsTheta T, float* __restrict__ S,
+                 const int32_t* __restrict__ count) {
   const int Su = M.users.stride, Si = M.items.stride, K = M.K, d = M.d;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool vis = M.D > 0;
+  const int32_t* crow = M.cmap;
+  const int32_t* cslot = M.cmap + 2 * (size_t)M.max_batch;
   const long long nw = (long long)gridDim.x * SS_WARPS;
-  for (long long slot = (long long)blockIdx.x * SS_WARPS + warp; slot < 2LL * B; slot += nw) {
-    const int32_t li = M.rows[slot];
-    const int b = (int)(slot < B ? slot : slot - B);
+  const long long n_owned = *count;
+  for (long long j = (long long)blockIdx.x * SS_WARPS + warp; j < n_owned; j += nw) {
+    const int32_t li = crow[j], slot = cslot[j];
+    const int b = slot < B ? slot : slot - B;
     const int32_t u = user[b];
-    float s = 0.0f;
-    if (li >= 0 && u >= 0 && u < M.num_users) {
-      const float* ur = M.users.w + (size_t)u * Su;
-      const float* gi = M.items.w + (size_t)li * Si;
-      float part = 0.0f;
-      for (int c = lane; c < K; c += 32) part = fmaf(ur[c], gi[c], part);
-      if (vis)
-        for (int n = lane; n < d; n += 32) part = fmaf(ur[K + n], T.at(slot, n), part);
-      s = fvx_warp_sum(part) + gi[K] + (vis ? T.at(slot, d) : 0.0f);
-    }
+    const float* ur = M.users.w + (size_t)u * Su;
+    const float* gi = M.items.w + (size_t)li * Si;
+    float part = 0.0f;
+    for (int c = lane; c < K; c += 32) part = fmaf(ur[c], gi[c], part);
+    if (vis)
+      for (int n = lane; n < d; n += 32) part = fmaf(ur[K + n], T.at(j, n), part);
+    const float s = fvx_warp_sum(part) + gi[K] + (vis ? T.at(j, d) : 0.0f);
     if (lane == 0) S[slot] = s;
   }
 }
@@ -78,6 +109,8 @@ k_grads_sharded(FvxModel M, const int32_t* __restrict__ user, int B, int loss_sl
   double loss_acc = 0.0;
   __nv_bfloat16* wh = reinterpret_cast<__nv_bfloat16*>(M.W_hi);
   __nv_bfloat16* wl = reinterpret_cast<__nv_bfloat16*>(M.W_lo);
+  const int32_t* crow = M.cmap;
+  const int32_t* cpos = M.cmap + 4 * (size_t)M.max_batch;
   for (long long b = (long long)blockIdx.x * SS_WARPS + warp; b < B; b += nw) {
     const int32_t u = user[b];
     const float xs = S[b] - S[B + b];
@@ -88,17 +121,11 @@ k_grads_sharded(FvxModel M, const int32_t* __restrict__ user, int B, int loss_sl
 #pragma unroll
     for (int side = 0; side < 2; ++side) {
       const long long slot = side ? B + b : b;
-      const int32_t li = M.rows[slot];
+      const long long j = cpos[slot];           // position in the compact list; < 0: foreign slot
+      if (j < 0) continue;
+      const int32_t li = crow[j];
       const float cs = side ? -coef : coef;
       const int nw_ = wnp > 0 ? wnp : de;
-      if (li < 0) {                 // foreign slot: no gradient from here, and a zero W row
-        if (vis)
-          for (int n = lane; n < nw_; n += 32) {
-            if (wnp > 0) { wh[slot * wnp + n] = __float2bfloat16_rn(0.0f); wl[slot * wnp + n] = __float2bfloat16_rn(0.0f); }
-            else M.W[slot * de + n] = 0.0f;
-          }
-        continue;
-      }
       const float* gi = M.items.w + (size_t)li * Si;
       float* gg = M.items.g + (size_t)li * Si;
       float sq = 0.0f;
@@ -116,7 +143,7 @@ k_grads_sharded(FvxModel M, const int32_t* __restrict__ user, int B, int loss_sl
           float wv = 0.0f;
           if (n < d) {
             const float tu = ur[K + n];
-            fvx_red_add(ru + K + n, cs * T.at(slot, n) + (side == 0 ? reg2 * tu : 0.0f));
+            fvx_red_add(ru + K + n, cs * T.at(j, n) + (side == 0 ? reg2 * tu : 0.0f));
             if (side == 0) sq += tu * tu;
             wv = cs * tu;
           } else if (n == d) {
@@ -124,10 +151,10 @@ k_grads_sharded(FvxModel M, const int32_t* __restrict__ user, int B, int loss_sl
           }
           if (wnp > 0) {
             const __nv_bfloat16 h = __float2bfloat16_rn(wv);
-            wh[slot * wnp + n] = h;
-            wl[slot * wnp + n] = __float2bfloat16_rn(wv - __bfloat162float(h));
+            wh[j * wnp + n] = h;
+            wl[j * wnp + n] = __float2bfloat16_rn(wv - __bfloat162float(h));
           } else {
-            M.W[slot * de + n] = wv;
+            M.W[j * de + n] = wv;
           }
         }
       }
@@ -169,7 +196,7 @@ static int sharded_common(const FvxModel* m, const int32_t* user, int B, const c
   if (int rc = fvx_check_model(m, who)) return rc;
   FVX_CHECK_ARG(user != nullptr && B >= 1 && B <= m->max_batch, "%s: bad batch", who);
   FVX_CHECK_ARG(m->users.list_cap >= B && m->items.list_cap >= 2 * B, "%s: touched-row lists too small", who);
-  FVX_CHECK_ARG(m->rows && m->loss && m->sync, "%s: null scratch", who);
+  FVX_CHECK_ARG(m->rows && m->loss && m->sync && m->cmap, "%s: null scratch (rows / loss / sync / cmap)", who);
   if (m->D > 0) {
     FVX_CHECK_ARG(m->TH && m->gE_part && m->ge_parts > 0, "%s: VBPR scratch missing", who);
     if (m->use_tensor_cores) FVX_CHECK_ARG(m->F_pl && m->ET_hi && m->ET_lo && m->W_hi && m->W_lo, "%s: bf16 planes missing", who);
@@ -212,17 +239,30 @@ int fvx_bpr_step_sharded_a(const FvxModel* model, const int32_t* user, const int
   const FvxModel& M = *model;
   cudaStream_t st = fvx_cu(stream);
   if (int rc = fvx_launch_prep(&M, user, pos, neg, B, st)) return rc;
+  // compact list of the owned slots; foreign entries of crow stay -1 (the fp32 kernels skip them)
+  int32_t* count = M.sync + 1;
+  cudaMemsetAsync(M.cmap, 0xFF, sizeof(int32_t) * 2 * (size_t)M.max_batch, st);
+  cudaMemsetAsync(S, 0, sizeof(float) * 2 * (size_t)B, st);
+  {
+    long long g = (2LL * B + 255) / 256;
+    if (g > (long long)fvx_num_sms() * 8) g = (long long)fvx_num_sms() * 8;
+    k_compact_owned<<<(int)g, 256, 0, st>>>(M, B, count);
+    FVX_CHECK_LAUNCH("k_compact_owned");
+  }
   const int ks = sharded_ks(&M, B);
   if (M.D > 0) {
     if (M.use_tensor_cores) {
       FVX_CHECK_ARG((long long)ks * 2 * B * fvx_tc_np(M.de) <= M.th_cap, "fvx_bpr_step_sharded_a: TH scratch too small");
-      if (int rc = fvx_launch_project_tc(&M, M.rows, 0, 2 * B, ks, M.TH, st)) return rc;
+      // W rows past the owned ones must read as zero in the last backward tile
+      cudaMemsetAsync(M.W_hi, 0, sizeof(uint16_t) * 2 * (size_t)B * fvx_tc_np(M.de), st);
+      cudaMemsetAsync(M.W_lo, 0, sizeof(uint16_t) * 2 * (size_t)B * fvx_tc_np(M.de), st);
+      if (int rc = fvx_launch_project_tc(&M, M.cmap, 0, 2 * B, ks, M.TH, st, count)) return rc;
     } else {
       FVX_CHECK_ARG(2LL * B * M.de <= M.th_cap, "fvx_bpr_step_sharded_a: TH scratch too small");
-      if (int rc = fvx_launch_project(&M, M.rows, 2 * B, M.TH, st)) return rc;
+      if (int rc = fvx_launch_project(&M, M.cmap, 2 * B, M.TH, st)) return rc;
     }
   }
-  k_partial_scores<<<ss_grid(2LL * B), SS_WARPS * 32, 0, st>>>(M, user, B, make_theta(&M, B, ks), S);
+  k_partial_scores<<<ss_grid(2LL * B), SS_WARPS * 32, 0, st>>>(M, user, B, make_theta(&M, B, ks), S, count);
   FVX_CHECK_LAUNCH("k_partial_scores");
   return 0;
 }
@@ -246,9 +286,9 @@ int fvx_bpr_step_sharded_b(const FvxModel* model, const int32_t* user, int32_t B
   if (M.D > 0) {
     int parts = 0;
     if (tc) {
-      if (int rc = fvx_launch_grad_E_tc(&M, M.rows, 2 * B, &parts, st)) return rc;
+      if (int rc = fvx_launch_grad_E_tc(&M, M.cmap, 2 * B, &parts, st, M.sync + 1)) return rc;
     } else {
-      if (int rc = fvx_launch_grad_E(&M, M.rows, 2 * B, &parts, st)) return rc;
+      if (int rc = fvx_launch_grad_E(&M, M.cmap, 2 * B, &parts, st)) return rc;
     }
     if (int rc = fvx_launch_reduce_gE(&M, parts, tc ? fvx_tc_np(M.de) : M.de, dE, st)) return rc;
   }

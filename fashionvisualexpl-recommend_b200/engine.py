@@ -64,6 +64,7 @@ class Engine:
         self.loss_t = torch.zeros(self.loss_slots, dtype=torch.float64, device=dev)
         self.rows_t = torch.zeros(2 * self.max_batch, **i32)
         self.sync_t = torch.zeros(4, **i32)
+        self.cmap_t = torch.zeros(6 * self.max_batch, **i32) if (self.item_lo or self.Ic != self.I) else None
         self.F = self.F_pl = None
         self.ET_hi = self.ET_lo = self.W_hi = self.W_lo = None
         self.use_tensor_cores = bool(use_tensor_cores) and self.D > 0
@@ -194,6 +195,7 @@ class Engine:
             m.TH, m.W, m.rows = ptr(self.TH), ptr(self.W), ptr(self.rows_t)
             m.th_cap = self.TH.numel() if self.TH is not None else 0
             m.sync = ptr(self.sync_t)
+            m.cmap = ptr(self.cmap_t)
             m.max_batch, m.use_tensor_cores = self.max_batch, int(self.use_tensor_cores)
             self._struct = m
         return self._struct
@@ -276,13 +278,17 @@ class Engine:
              ptr(out), stream_ptr())
         return out
 
-    def score_topk(self, mask_row_ptr, mask_col, k, u0=0, u1=None, thr_scores=None, tc=None):
+    def score_topk(self, mask_row_ptr, mask_col, k, u0=0, u1=None, thr_scores=None, tc=None, view=None):
         """Masked top-k (+ optional rank counts) for users [u0,u1): (ids, scores[, counts]).
         ``tc``: use the tcgen05 sweep (default: the engine's ``use_tensor_cores``); it returns
-        the same ids / scores as the fp32 kernel and is only available without rank counts."""
+        the same ids / scores as the fp32 kernel and is only available without rank counts.
+        ``view``: an item-side view other than this engine's own shard (parallel.gathered_view):
+        dict(struct=FvxModel, theta=tensor, Ic=rows, keep=[tensors kept alive])."""
         u1 = self.U if u1 is None else u1
         self.flush()
         n = u1 - u0
+        if view is not None:
+            return self._score_topk_view(view, mask_row_ptr, mask_col, k, u0, u1, tc)
         ids = torch.empty(n, k, dtype=torch.int32, device=self.device)
         sc = torch.empty(n, k, dtype=torch.float32, device=self.device)
         tc = self.use_tensor_cores if tc is None else tc
@@ -290,12 +296,15 @@ class Engine:
             ws = self._eval_ws(n)
             call("fvx_score_topk_tc", C.byref(self.struct()), ptr(self.theta()), u0, u1, ptr(mask_row_ptr),
                  ptr(mask_col), k, ptr(ids), ptr(sc), C.byref(ws["struct"]), stream_ptr())
-            bad = torch.nonzero(ws["flags"][:n]).reshape(-1)
+            bad = torch.nonzero(ws["flags"][:n]).reshape(-1)       # (synchronises: the list length is needed)
             self.tc_overflow_rows = int(bad.numel())
-            for r in bad.tolist():          # candidate list overflowed: exact fp32 sweep for that user
-                call("fvx_score_topk", C.byref(self.struct()), ptr(self.theta()), u0 + r, u0 + r + 1,
-                     ptr(mask_row_ptr), ptr(mask_col), k, ptr(ids[r:r + 1]), ptr(sc[r:r + 1]), 0, None, None,
-                     stream_ptr())
+            if bad.numel():                 # candidate lists overflowed: one exact fp32 sweep for those users
+                ul = (bad + u0).to(torch.int32).contiguous()
+                fi = torch.empty(bad.numel(), k, dtype=torch.int32, device=self.device)
+                fs = torch.empty(bad.numel(), k, dtype=torch.float32, device=self.device)
+                call("fvx_score_topk_users", C.byref(self.struct()), ptr(self.theta()), ptr(ul), ul.numel(),
+                     ptr(mask_row_ptr), ptr(mask_col), k, ptr(fi), ptr(fs), stream_ptr())
+                ids[bad], sc[bad] = fi, fs
             return ids, sc
         n_thr, counts = 0, None
         if thr_scores is not None:
@@ -305,18 +314,46 @@ class Engine:
              ptr(mask_col), k, ptr(ids), ptr(sc), n_thr, ptr(thr_scores), ptr(counts), stream_ptr())
         return (ids, sc, counts) if thr_scores is not None else (ids, sc)
 
-    def _eval_ws(self, n_users):
+    def _score_topk_view(self, view, mask_row_ptr, mask_col, k, u0, u1, tc):
+        n = u1 - u0
+        m, th = view["struct"], view["theta"]
+        ids = torch.empty(n, k, dtype=torch.int32, device=self.device)
+        sc = torch.empty(n, k, dtype=torch.float32, device=self.device)
+        tc = self.use_tensor_cores if tc is None else tc
+        if n <= 0:
+            return ids, sc
+        if tc and self.K + self.d + 3 <= 128:
+            ws = self._eval_ws(n, struct=m, Ic=view["Ic"], key="_ws_view")
+            call("fvx_score_topk_tc", C.byref(m), ptr(th), u0, u1, ptr(mask_row_ptr), ptr(mask_col), k, ptr(ids),
+                 ptr(sc), C.byref(ws["struct"]), stream_ptr())
+            bad = torch.nonzero(ws["flags"][:n]).reshape(-1)
+            self.tc_overflow_rows = int(bad.numel())
+            if bad.numel():
+                ul = (bad + u0).to(torch.int32).contiguous()
+                fi = torch.empty(bad.numel(), k, dtype=torch.int32, device=self.device)
+                fs = torch.empty(bad.numel(), k, dtype=torch.float32, device=self.device)
+                call("fvx_score_topk_users", C.byref(m), ptr(th), ptr(ul), ul.numel(), ptr(mask_row_ptr),
+                     ptr(mask_col), k, ptr(fi), ptr(fs), stream_ptr())
+                ids[bad], sc[bad] = fi, fs
+            return ids, sc
+        call("fvx_score_topk", C.byref(m), ptr(th), u0, u1, ptr(mask_row_ptr), ptr(mask_col), k, ptr(ids), ptr(sc),
+             0, None, None, stream_ptr())
+        return ids, sc
+
+    def _eval_ws(self, n_users, struct=None, Ic=None, key="_ws"):
         """Caller-owned workspace of fvx_score_topk_tc, sized by fvx_eval_ws_query and cached."""
-        ws = getattr(self, "_ws", None)
+        ws = getattr(self, key, None)
         q = _lib.FvxEvalWs()
-        call("fvx_eval_ws_query", C.byref(self.struct()), n_users, C.byref(q))
-        if ws is None or ws["n"] != n_users or ws["KP"] != q.KP or ws["splits"] != q.splits:
+        struct = self.struct() if struct is None else struct
+        Ic = self.Ic if Ic is None else Ic
+        call("fvx_eval_ws_query", C.byref(struct), n_users, C.byref(q))
+        if ws is None or ws["n"] != n_users or ws["KP"] != q.KP or ws["splits"] != q.splits or ws["Ic"] != Ic:
             dv = self.device
-            ws = {"n": n_users, "KP": q.KP, "splits": q.splits, "lists": q.lists,
+            ws = {"n": n_users, "KP": q.KP, "splits": q.splits, "lists": q.lists, "Ic": Ic,
                   "A": torch.empty(n_users * q.KP, dtype=torch.uint16, device=dv),
-                  "Bm": torch.empty(self.Ic * q.KP, dtype=torch.uint16, device=dv),
+                  "Bm": torch.empty(Ic * q.KP, dtype=torch.uint16, device=dv),
                   "epsa": torch.empty(n_users, dtype=torch.float32, device=dv),
-                  "nb": torch.empty(self.Ic, dtype=torch.float32, device=dv),
+                  "nb": torch.empty(Ic, dtype=torch.float32, device=dv),
                   "stat": torch.zeros(2, dtype=torch.float32, device=dv),
                   "thr": torch.zeros(n_users, dtype=torch.int32, device=dv),
                   "cand": torch.empty(q.lists * q.cap, dtype=torch.int64, device=dv),
@@ -325,7 +362,7 @@ class Engine:
             q.A, q.Bm, q.epsa, q.nb, q.stat = ptr(ws["A"]), ptr(ws["Bm"]), ptr(ws["epsa"]), ptr(ws["nb"]), ptr(ws["stat"])
             q.cand, q.ccount, q.flags, q.thr = ptr(ws["cand"]), ptr(ws["ccount"]), ptr(ws["flags"]), ptr(ws["thr"])
             ws["struct"] = q
-            self._ws = ws
+            setattr(self, key, ws)
         return ws
 
 

@@ -52,6 +52,10 @@ class DistGroup:
     def all_to_all(self, outs, ins):
         self.dist.all_to_all_single(outs[0], ins[0], group=self.group)
 
+    def all_gather(self, outs, ins):
+        """outs[0]: [R, ...] receives ins[0] of every rank."""
+        self.dist.all_gather_into_tensor(outs[0], ins[0], group=self.group)
+
 
 class LocalGroup:
     """R emulated ranks in one process: ``tensors[r]`` is rank r's buffer."""
@@ -63,6 +67,11 @@ class LocalGroup:
         total = torch.stack(list(tensors)).sum(0)
         for t in tensors:
             t.copy_(total)
+
+    def all_gather(self, outs, ins):
+        full = torch.stack(list(ins))
+        for o in outs:
+            o.copy_(full)
 
     def all_to_all(self, outs, ins):
         R = self.world
@@ -150,3 +159,52 @@ def sharded_topk(engines, group, mask_row_ptr, mask_col, k, tc=None):
         scores.append(s_)
     xi, xs = exchange_topk(ids, scores, group)
     return [topk_merge(a, b) for a, b in zip(xi, xs)]
+
+
+def gathered_view(engines, group):
+    """Evaluation with the USERS split over the ranks instead of the items: the item-side operands of
+    the score (Gi | Bi rows and theta = F*E of every shard: (Si + de) * 4 bytes per item - F itself
+    stays sharded) are all-gathered once per sweep, then every rank scores its own user slice against
+    the whole catalog and no merge is needed.  Returns one view per local engine for
+    ``Engine.score_topk(view=...)``."""
+    R = group.world
+    e0 = engines[0]
+    I = e0.I
+    cnts = [shard_bounds(I, R, r)[1] for r in range(R)]
+    mx = max(cnts)
+    views, ins_w, ins_t, outs_w, outs_t = [], [], [], [], []
+    for e in engines:
+        e.flush()
+        w = torch.zeros(mx, e.Si, dtype=torch.float32, device=e.device)
+        w[:e.Ic] = e.items["w"]
+        ins_w.append(w)
+        outs_w.append(torch.empty(R, mx, e.Si, dtype=torch.float32, device=e.device))
+        if e.D:
+            t = torch.zeros(mx, e.de, dtype=torch.float32, device=e.device)
+            t[:e.Ic] = e.theta()
+            ins_t.append(t)
+            outs_t.append(torch.empty(R, mx, e.de, dtype=torch.float32, device=e.device))
+    group.all_gather(outs_w, ins_w)
+    if ins_t:
+        group.all_gather(outs_t, ins_t)
+    for i, e in enumerate(engines):
+        W = torch.cat([outs_w[i][r, :cnts[r]] for r in range(R)]).contiguous()
+        T = torch.cat([outs_t[i][r, :cnts[r]] for r in range(R)]).contiguous() if e.D else None
+        m = _lib.FvxModel()
+        C.pointer(m)[0] = e.struct()
+        m.item_lo, m.item_cnt = 0, I
+        m.items.w, m.items.rows = ptr(W), I
+        views.append({"struct": m, "theta": T, "Ic": I, "keep": [W, T]})
+    return views
+
+
+def user_sliced_topk(engines, group, mask_row_ptr, mask_col, k, tc=None):
+    """(ids, scores) of each local rank's user slice [U/R (last slice shorter), k]; see gathered_view."""
+    views = gathered_view(engines, group)
+    out = []
+    for i, (e, v) in enumerate(zip(engines, views)):
+        r = group.rank if group.rank is not None else i
+        per, _ = user_slices(e.U, group.world)
+        u0, u1 = min(e.U, r * per), min(e.U, (r + 1) * per)
+        out.append(e.score_topk(mask_row_ptr, mask_col, k, u0=u0, u1=u1, tc=tc, view=v))
+    return out

@@ -100,6 +100,8 @@ typedef struct FvxModel {
   int32_t* rows;        /* [2*max_batch] local item row of each (triple, side) slot,
                            -1 when the item belongs to another rank                 */
   int32_t* sync;        /* [4] zero-initialised inter-block counters of the step kernels */
+  int32_t* cmap;        /* [6*max_batch] sharded step only: compact list of the slots this rank
+                           owns - local item row [2B] | slot [2B] | position of a slot [2B] */
   int32_t max_batch;
   int32_t use_tensor_cores; /* 0: fp32 SIMT projection; 1: tcgen05 (needs the planes) */
 } FvxModel;
@@ -200,6 +202,12 @@ int fvx_score_topk(const FvxModel* model, const float* theta_ext, int32_t u0, in
                    const int64_t* mask_row_ptr, const int32_t* mask_col, int32_t k,
                    int32_t* out_ids, float* out_scores, int32_t n_thr, const float* thr_scores,
                    int32_t* out_counts, fvx_stream_t stream);
+
+/* fvx_score_topk for an explicit list of n users (each in [0, num_users)): row j of the outputs
+ * belongs to users[j].  The exact path for the rows fvx_score_topk_tc flags. */
+int fvx_score_topk_users(const FvxModel* model, const float* theta_ext, const int32_t* users, int32_t n,
+                         const int64_t* mask_row_ptr, const int32_t* mask_col, int32_t k,
+                         int32_t* out_ids, float* out_scores, fvx_stream_t stream);
 
 /* Tensor-core variant of fvx_score_topk (tcgen05 + TMA; top-k only, no rank counts):
  * a bf16 sweep selects, per user, every item whose bf16 score is within the rounding

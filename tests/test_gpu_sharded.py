@@ -91,3 +91,10 @@ def test_sharded_topk_equals_single_rank(R):
     for u in range(U):
         ok, msg = oe.topk_matches(ids[u].cpu().numpy(), sc[u].cpu().numpy(), o_ids[u], o_sc[u])
         assert ok, (u, msg)
+    # the other decomposition: users split over the ranks, item operands all-gathered
+    from fvx.parallel import user_sliced_topk
+    for tc in (False, True):
+        sl = user_sliced_topk(es, LocalGroup(R), rp, cs, k, tc=tc)
+        ids2 = torch.cat([a for a, _ in sl])
+        sc2 = torch.cat([b for _, b in sl])
+        assert ids2.shape[0] == U and torch.equal(ids2, ids1) and torch.equal(sc2, sc1), tc
