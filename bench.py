@@ -172,7 +172,9 @@ def run_reference(args):
         return
     from fvx import synth
     from oracle import bpr
-    B = args.batch
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    B = args.batch                      # one per-GPU batch per step: a bounded sample of the N-GPU workload
+    args.users = args.users * world     # the same problem size as the fvx arm at this N
     inter = make_problem(args)
     F = None
     if args.feat_dim:
@@ -198,10 +200,11 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, 1),
+            "config": workload_config(args, world),
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": "%d full steps of B=%d on the full tables (NumPy oracle, dense Keras-Adam "
-                                       "sweep like TF 2.3; TensorFlow itself not installable)" % (args.steps, B)},
+                             "sample": "%d steps of B=%d triples (one per-GPU batch) on the full tables (NumPy oracle, "
+                                       "dense Keras-Adam sweep like TF 2.3; TensorFlow itself not installable)"
+                                       % (args.steps, B)},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -209,9 +212,9 @@ def run_reference(args):
 
 def workload_config(args, n):
     return {"workload": "VBPR train step, K=%d d=%d D=%d, %d users x %d items (BASELINE configs[1]), "
-                        "B=%d triples/step per GPU, on-device Philox sampler, %s Adam"
+                        "B=%d triples/step per GPU, on-device Philox sampler, %s Adam%s"
                         % (args.embed_k, args.embed_d, args.feat_dim, args.users, args.items, args.batch,
-                           args.adam_mode),
+                           args.adam_mode, "" if n == 1 else "; weak scaling: 40 000 users and one batch per GPU"),
             "users": args.users, "items": args.items, "K": args.embed_k, "d": args.embed_d, "D": args.feat_dim,
             "batch": args.batch * n, "adam_mode": args.adam_mode, "tensor_cores": bool(args.tensor_cores),
             "parallelism": "1 GPU" if n == 1 else
@@ -244,6 +247,9 @@ def run_fvx(args):
     # the item catalog (Gi, Bi, F + Adam state) is row-sharded, users and E are replicated
     B, K, d, D = args.batch * world, args.embed_k, args.embed_d, args.feat_dim
 
+    # ... and so does the number of users (40 000 per GPU): training and evaluation work per GPU stay
+    # fixed while the catalog stays at `items` rows, sharded
+    args.users = args.users * world
     inter = make_problem(args)
     p = argparse.Namespace(dataset="synthetic", batch_size=B, epochs=10 ** 6, sampler="device", seed=0)
     data = DataLoader(p, interactions=inter)
@@ -255,7 +261,8 @@ def run_fvx(args):
         F = make_features_device(args.items, D, dev)          # same generator seed on every rank
         e.set_features(F[lo:lo + cnt].contiguous(), keep_fp32=not args.tensor_cores)
         del F
-    sharded = parallel.ShardedStep([e], parallel.DistGroup()) if world > 1 else None
+    min_len = int(np.diff(inter.row_ptr).min())
+    sharded = parallel.ShardedStep([e], parallel.DistGroup(), max_runs=B // max(min_len, 1) + 2) if world > 1 else None
     batches = data.next_triple_batch(str(dev))
 
     def do_step(b, slot=0):
@@ -364,33 +371,52 @@ def run_fvx(args):
         e.flush()
         torch.cuda.synchronize()
 
-        def sweep():
+        grp = parallel.DistGroup() if world > 1 else None
+
+        def sweep_item_shards():
+            # every rank: all users x its item shard -> all-to-all by user slice -> merge
             e.theta(refresh=True)
             if world > 1:
-                return parallel.sharded_topk([e], parallel.DistGroup(), st["row_ptr"], st["col_sorted"], args.top_k)
+                return parallel.sharded_topk([e], grp, st["row_ptr"], st["col_sorted"], args.top_k)
             return e.score_topk(st["row_ptr"], st["col_sorted"], args.top_k)
 
-        for _ in range(2):
-            sweep()                                       # warm-up (workspace allocation)
-        barrier()
-        best = 1e30
-        for _ in range(3):
-            a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            sweep()
-            b2.record()
+        def sweep_user_slices():
+            # theta of the own shard -> all-gather of (Gi|Bi, theta) -> every rank: its users x the catalog
+            e.theta(refresh=True)
+            return parallel.user_sliced_topk([e], grp, st["row_ptr"], st["col_sorted"], args.top_k)
+
+        def timed(fn):
+            for _ in range(2):
+                fn()                                      # warm-up (workspace allocation)
             barrier()
-            best = min(best, max_over_ranks(a.elapsed_time(b2)))
+            best = 1e30
+            for _ in range(3):
+                a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                fn()
+                b2.record()
+                barrier()
+                best = min(best, max_over_ranks(a.elapsed_time(b2)))
+            return best
+
         nu = args.users
         flops_user = 2.0 * args.items * (K + d) + 2.0 * args.items
+        modes = {"item_shards": timed(sweep_item_shards)}
+        if world > 1:
+            modes["user_slices"] = timed(sweep_user_slices)
+        mode = min(modes, key=modes.get)
+        best = modes[mode]
         tfl = nu * flops_user / (best * 1e-3) / 1e12
         line["eval"] = {"metric": "users/s full-catalog top-%d eval" % args.top_k, "value": nu / best * 1e3,
-                        "unit": "users/s", "users": nu, "ms": best,
+                        "unit": "users/s", "users": nu, "ms": best, "scaling": "weak (users per GPU fixed)",
                         "kernel": "k_topk_tc (tcgen05 bf16 filter + exact fp32 re-scoring)" if args.tensor_cores
                         else "k_score_topk (fp32 CUDA cores)",
                         "fallback_rows": getattr(e, "tc_overflow_rows", 0),
-                        "includes": "theta = F*E projection of the catalog, score sweep, mask, top-k"
-                                    + (", all-to-all exchange + merge" if world > 1 else ""),
+                        "decomposition": mode if world > 1 else "1 GPU",
+                        "ms_by_decomposition": modes,
+                        "includes": "theta = F*E projection of the catalog (F stays item-sharded), score sweep, "
+                                    "mask, top-k" + ("; item_shards: all-to-all exchange + merge of per-shard lists; "
+                                                     "user_slices: all-gather of the item operands" if world > 1 else ""),
                         "roofline": {"bound": "tensor", "achieved": tfl, "peak": tf_burst * world, "unit": "TFLOP/s",
                                      "frac": tfl / (tf_burst * world)}}
 

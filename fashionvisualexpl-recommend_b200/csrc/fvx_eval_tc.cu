@@ -48,7 +48,7 @@
 #define TCK_CAP 512         // candidate slots per (user, split)
 #define TCK_SLACK 192       // a list is compacted once it holds k + #train + TCK_SLACK entries
 #define TCK_THREADS 320     // warp 0 producer, warp 1 UMMA, warps 2-9 epilogue
-#define TCK_RS_MAX 1024     // candidates per user the final selection can take
+#define TCK_RS_MAX 2048     // candidates per user the final selection can take
 #define KEY_PAD 0xFFFFFFFFFFFFFFFFull
 
 // order-preserving float <-> uint (ascending uint == ascending float)
@@ -447,7 +447,7 @@ k_topk_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 
 // ---------------------------------------------------------------------------------
 // exact re-scoring + final selection: one warp per user
-#define RS_WARPS 4
+#define RS_WARPS 2
 __device__ __forceinline__ void rs_bitonic(unsigned long long* keys, int n, int lane) {
   for (int size = 2; size <= n; size <<= 1)
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
@@ -601,10 +601,16 @@ static void tck_geometry(const FvxModel* m, int n_users, int* KP, int* n_pairs, 
   const int tail = *n_pairs - *n_full;
   int s = 1;
   if (tail > 0) {
-    s = (G + tail - 1) / tail;          // the tail pairs are cut so that their units still fill the machine
-    if (s > 8) s = 8;
-    if (s > n_item_tiles / 8) s = n_item_tiles / 8;
-    if (s < 1) s = 1;
+    // the tail pairs are cut into s item ranges so that their units still fill the machine: the
+    // tail then takes ceil(tail*s/G) rounds of 1/s of a sweep; every extra split costs a threshold
+    // restart (~3 % of a sweep here), so the smallest s within 2 % of the best is taken
+    int smax = n_item_tiles / 8 < 16 ? n_item_tiles / 8 : 16;
+    if (smax < 1) smax = 1;
+    double best = 1e30;
+    for (int c = 1; c <= smax; ++c) {
+      const double t = (double)((tail * c + G - 1) / G) / c + 0.03 * c;
+      if (t < best * 0.98) { best = t; s = c; }
+    }
   }
   *splits = s;
   const long long units = (long long)*n_full + (long long)tail * s;

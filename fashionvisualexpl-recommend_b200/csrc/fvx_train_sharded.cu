@@ -99,7 +99,8 @@ k_partial_scores(FvxModel M, const int32_t* __restrict__ user, int B, SsTheta T,
 // phase B: one warp per triple; each side only if its item is owned
 __global__ void __launch_bounds__(SS_WARPS * 32)
 k_grads_sharded(FvxModel M, const int32_t* __restrict__ user, int B, int loss_slot, SsTheta T, int wnp,
-                const float* __restrict__ S, const int32_t* __restrict__ run_id, float* __restrict__ RU) {
+                const float* __restrict__ S, const int32_t* __restrict__ run_id, float* __restrict__ RU,
+                long long ru_rows) {
   __shared__ double loss_sh[SS_WARPS];
   const int Su = M.users.stride, Si = M.items.stride, K = M.K, d = M.d, de = M.de;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -117,6 +118,10 @@ k_grads_sharded(FvxModel M, const int32_t* __restrict__ user, int B, int loss_sl
     const bool inside = (xs >= FVX_CLIP_LO) && (xs <= FVX_CLIP_HI);
     const float coef = inside ? -1.0f / (1.0f + expf(xs)) : 0.0f;
     const float* ur = M.users.w + (size_t)u * Su;
+    if (run_id[b] >= ru_rows) {       // more runs than the caller sized RU for: reported through sync[2]
+      if (lane == 0) M.sync[2] = 1;
+      continue;
+    }
     float* ru = RU + (size_t)run_id[b] * Su;
 #pragma unroll
     for (int side = 0; side < 2; ++side) {
@@ -179,13 +184,14 @@ k_grads_sharded(FvxModel M, const int32_t* __restrict__ user, int B, int loss_sl
 
 // phase C: one warp per run start adds the all-reduced run gradient into the user's accumulator
 __global__ void k_scatter_runs(FvxModel M, const int32_t* __restrict__ user, int B,
-                               const int32_t* __restrict__ run_id, const float* __restrict__ RU) {
+                               const int32_t* __restrict__ run_id, const float* __restrict__ RU, long long ru_rows) {
   const int lane = threadIdx.x & 31;
   const int Su = M.users.stride;
   const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
   for (long long b = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < B; b += nw) {
     const int32_t u = user[b];
     if (b > 0 && user[b - 1] == u) continue;          // not a run start
+    if (run_id[b] >= ru_rows) continue;
     const float* src = RU + (size_t)run_id[b] * Su;
     float* g = M.users.g + (size_t)u * Su;
     for (int c = lane; c < Su; c += 32) fvx_red_add(g + c, src[c]);   // a user may own several runs
@@ -281,7 +287,7 @@ int fvx_bpr_step_sharded_b(const FvxModel* model, const int32_t* user, int32_t B
   const int ks = sharded_ks(&M, B);
   const bool tc = M.D > 0 && M.use_tensor_cores;
   k_grads_sharded<<<ss_grid(B), SS_WARPS * 32, 0, st>>>(M, user, B, loss_slot, make_theta(&M, B, ks),
-                                                        tc ? fvx_tc_np(M.de) : 0, S, run_id, RU);
+                                                        tc ? fvx_tc_np(M.de) : 0, S, run_id, RU, (long long)ru_rows);
   FVX_CHECK_LAUNCH("k_grads_sharded");
   if (M.D > 0) {
     int parts = 0;
@@ -296,7 +302,8 @@ int fvx_bpr_step_sharded_b(const FvxModel* model, const int32_t* user, int32_t B
 }
 
 int fvx_bpr_step_sharded_c(const FvxModel* model, const int32_t* user, int32_t B, const int32_t* run_id,
-                           const float* RU, const float* dE, int32_t loss_slot, fvx_stream_t stream) {
+                           const float* RU, int64_t ru_rows, const float* dE, int32_t loss_slot,
+                           fvx_stream_t stream) {
   if (int rc = sharded_common(model, user, B, "fvx_bpr_step_sharded_c")) return rc;
   FVX_CHECK_ARG(run_id && RU, "fvx_bpr_step_sharded_c: null pointer");
   const FvxModel& M = *model;
@@ -304,7 +311,7 @@ int fvx_bpr_step_sharded_c(const FvxModel* model, const int32_t* user, int32_t B
   cudaStream_t st = fvx_cu(stream);
   long long g = ((long long)B * 32 + 255) / 256;
   if (g > (long long)fvx_num_sms() * 8) g = (long long)fvx_num_sms() * 8;
-  k_scatter_runs<<<(int)g, 256, 0, st>>>(M, user, B, run_id, RU);
+  k_scatter_runs<<<(int)g, 256, 0, st>>>(M, user, B, run_id, RU, (long long)ru_rows);
   FVX_CHECK_LAUNCH("k_scatter_runs");
   // loss_slot < 0: the E term of the loss (VBPR.py:129) is not added (ranks other than 0, so that
   // the per-rank losses sum to the batch loss)

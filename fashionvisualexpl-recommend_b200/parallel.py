@@ -83,12 +83,16 @@ class LocalGroup:
 class ShardedStep:
     """``engines``: this process's engines - ONE with a ``DistGroup``, or all R with a ``LocalGroup``."""
 
-    def __init__(self, engines, group):
+    def __init__(self, engines, group, max_runs=None):
+        """``max_runs``: upper bound of the number of runs of equal users in a batch (default: the batch
+        size); the all-reduced user-gradient buffer has that many rows, so a tight bound - e.g.
+        B // (shortest train list) + 2 for batches of the reference's sampler - saves NVLink bytes."""
         self.engines, self.group = list(engines), group
         e = self.engines[0]
         B, dv = e.max_batch, e.device
+        self.max_runs = int(max_runs) if max_runs else B
         self.S = [torch.zeros(2 * B, dtype=torch.float32, device=dv) for _ in self.engines]
-        self.RU = [torch.zeros(B, e.Su, dtype=torch.float32, device=dv) for _ in self.engines]
+        self.RU = [torch.zeros(self.max_runs, e.Su, dtype=torch.float32, device=dv) for _ in self.engines]
         self.dE = [torch.zeros(e.D, e.de, dtype=torch.float32, device=dv) if e.D else None for _ in self.engines]
 
     def _rank_of(self, i):
@@ -108,11 +112,13 @@ class ShardedStep:
         if self.dE[0] is not None:
             self.group.all_reduce(self.dE)
         for i, (e, RU, dE) in enumerate(zip(self.engines, self.RU, self.dE)):
-            call("fvx_bpr_step_sharded_c", C.byref(e.struct()), ptr(user), B, ptr(rid), ptr(RU), ptr(dE),
-                 loss_slot if self._rank_of(i) == 0 else -1, stream_ptr())
+            call("fvx_bpr_step_sharded_c", C.byref(e.struct()), ptr(user), B, ptr(rid), ptr(RU), RU.shape[0],
+                 ptr(dE), loss_slot if self._rank_of(i) == 0 else -1, stream_ptr())
 
     def read_loss(self, slot=0, clear=True):
         """Batch loss = sum of the per-rank partial losses (synchronises)."""
+        if any(int(e.sync_t[2].item()) for e in self.engines):
+            raise _lib.FvxError("a batch had more runs of equal users than max_runs=%d" % self.max_runs)
         parts = [e.loss_t[slot:slot + 1].clone() for e in self.engines]
         if clear:
             for e in self.engines:

@@ -171,9 +171,10 @@ int fvx_bpr_step_sharded_a(const FvxModel* model, const int32_t* user, const int
 int fvx_bpr_step_sharded_b(const FvxModel* model, const int32_t* user, int32_t B, const float* S,
                            const int32_t* run_id, float* RU, int64_t ru_rows, float* dE,
                            int32_t loss_slot, fvx_stream_t stream);
-/* loss_slot < 0: the reg*(|E|^2+|Bp|^2) loss term is not added (use on ranks other than 0) */
+/* loss_slot < 0: the reg*(|E|^2+|Bp|^2) loss term is not added (use on ranks other than 0).
+ * A batch with more than ru_rows runs sets model->sync[2] = 1 (its surplus runs are dropped). */
 int fvx_bpr_step_sharded_c(const FvxModel* model, const int32_t* user, int32_t B,
-                           const int32_t* run_id, const float* RU, const float* dE,
+                           const int32_t* run_id, const float* RU, int64_t ru_rows, const float* dE,
                            int32_t loss_slot, fvx_stream_t stream);
 
 /* DEFERRED mode: bring every row of both tables up to the current step (call
