@@ -79,7 +79,9 @@ k_score_topk(FvxModel M, const float* __restrict__ theta, int u0, int u1,
              const int64_t* __restrict__ mask_row_ptr, const int32_t* __restrict__ mask_col, int k,
              int32_t* __restrict__ out_ids, float* __restrict__ out_scores, int n_thr,
              const float* __restrict__ thr_scores, int32_t* __restrict__ out_counts,
-             const int32_t* __restrict__ ulist) {   // ulist: user of local index j (nullptr: j itself)
+             const int32_t* __restrict__ ulist,     // ulist: user of local index j (nullptr: j itself)
+             const int32_t* __restrict__ n_dev,     // list mode: number of valid list entries lives on the device
+             int scatter_base) {                    // >= 0: output row of list entry j is ulist[j] - scatter_base
   extern __shared__ __align__(16) unsigned char tk_smem[];
   const int Su = M.users.stride, Si = M.items.stride, K = M.K, d = M.d, de = M.de;
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(tk_smem);          // [UB][CAP]
@@ -90,8 +92,13 @@ k_score_topk(FvxModel M, const float* __restrict__ theta, int u0, int u1,
   int* cge = cnt + TK_UB;                                                               // [UB][MAXTHR]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  for (int ub = u0 + blockIdx.x * TK_UB; ub < u1; ub += gridDim.x * TK_UB) {
-    const int nu = (u1 - ub < TK_UB) ? (u1 - ub) : TK_UB;
+  // device-counted lists (the rows fvx_score_topk_tc flags) are short: one user per CTA pass, so
+  // that a handful of users spread over the grid instead of queueing in one CTA
+  const bool spread = n_dev != nullptr;
+  if (spread) { const int nd = *n_dev; u1 = nd < u1 ? nd : u1; }
+  const int ub_step = spread ? 1 : TK_UB;
+  for (int ub = u0 + blockIdx.x * ub_step; ub < u1; ub += gridDim.x * ub_step) {
+    const int nu = spread ? 1 : ((u1 - ub < TK_UB) ? (u1 - ub) : TK_UB);
     __syncthreads();
     for (int e = tid; e < TK_UB * Su; e += TK_TILE) {
       const int u = e / Su, c = e - u * Su;
@@ -189,7 +196,7 @@ k_score_topk(FvxModel M, const float* __restrict__ theta, int u0, int u1,
       for (int i = c0 + lane; i < TK_CAP; i += 32) kk[i] = KEY_PAD;
       __syncwarp();
       warp_bitonic_sort(kk, TK_CAP, lane);
-      const size_t o = (size_t)(ub + warp - u0) * k;
+      const size_t o = (size_t)(scatter_base >= 0 ? ulist[ub + warp] - scatter_base : ub + warp - u0) * k;
       for (int i = lane; i < k; i += 32) {
         const bool ok = i < c0;
         out_ids[o + i] = ok ? (int32_t)(kk[i] & 0xFFFFFFFFu) : -1;
@@ -317,10 +324,47 @@ static int score_topk_impl(const FvxModel* model, const float* theta_ext, int32_
   long long g = ((long long)(u1 - u0) + TK_UB - 1) / TK_UB;
   if (g > (long long)fvx_num_sms() * 4) g = (long long)fvx_num_sms() * 4;
   k_score_topk<<<(int)g, TK_TILE, smem, fvx_cu(stream)>>>(*model, theta_ext, u0, u1, mask_row_ptr, mask_col, k,
-                                                          out_ids, out_scores, n_thr, thr_scores, out_counts, ulist);
+                                                          out_ids, out_scores, n_thr, thr_scores, out_counts, ulist,
+                                                          nullptr, -1);
   FVX_CHECK_LAUNCH("k_score_topk");
   return 0;
 }
+
+}  // extern "C"
+
+// users u0 + r with flags[r] != 0 -> list (order arbitrary), *count = its length
+__global__ void k_flag_list(const int32_t* __restrict__ flags, int n, int u0, int32_t* __restrict__ list,
+                            int32_t* __restrict__ count) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x)
+    if (flags[r] != 0) list[atomicAdd(count, 1)] = u0 + r;
+}
+
+// The exact sweep for the rows of [u0, u0+n) that carry a flag; results are written into the rows'
+// own slots of out_ids / out_scores.  No host synchronisation: the list and its length stay on the device.
+int fvx_launch_topk_flagged(const FvxModel* model, const float* theta_ext, const int32_t* flags, int n, int u0,
+                            const int64_t* mask_row_ptr, const int32_t* mask_col, int k, int32_t* out_ids,
+                            float* out_scores, int32_t* list_scratch, int32_t* count_scratch, cudaStream_t st) {
+  cudaMemsetAsync(count_scratch, 0, sizeof(int32_t), st);
+  int g = (n + 255) / 256;
+  if (g > fvx_num_sms() * 4) g = fvx_num_sms() * 4;
+  k_flag_list<<<g, 256, 0, st>>>(flags, n, u0, list_scratch, count_scratch);
+  const size_t smem = (size_t)TK_UB * TK_CAP * 8 + (size_t)TK_UB * model->users.stride * 4 +
+                      (size_t)TK_UB * 4 * (2 + 2 * TK_MAXTHR);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(k_score_topk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) FVX_FAIL(-3, "fvx_score_topk_tc: cannot set %zu B of shared memory: %s", smem,
+                                   cudaGetErrorString(e));
+    configured = smem;
+  }
+  k_score_topk<<<fvx_num_sms() * 2, TK_TILE, smem, st>>>(*model, theta_ext, 0, n, mask_row_ptr, mask_col, k, out_ids,
+                                                         out_scores, 0, nullptr, nullptr, list_scratch, count_scratch,
+                                                         u0);
+  FVX_CHECK_LAUNCH("k_score_topk (flagged rows)");
+  return 0;
+}
+
+extern "C" {
 
 int fvx_score_topk(const FvxModel* model, const float* theta_ext, int32_t u0, int32_t u1,
                    const int64_t* mask_row_ptr, const int32_t* mask_col, int32_t k, int32_t* out_ids,

@@ -704,7 +704,10 @@ int fvx_score_topk_tc(const FvxModel* model, const float* theta_ext, int32_t u0,
   k_rescore_select<<<(int)rg, RS_WARPS * 32, 0, st>>>(*model, theta_ext, P, mask_row_ptr, mask_col, k, out_ids,
                                                       out_scores);
   FVX_CHECK_LAUNCH("k_rescore_select");
-  return 0;
+  // rows whose candidate lists could not bound the result: exact fp32 sweep, written in place (the
+  // thresholds and the statistics are dead by now and serve as the list / its counter)
+  return fvx_launch_topk_flagged(model, theta_ext, ws->flags, n_users, u0, mask_row_ptr, mask_col, k, out_ids,
+                                 out_scores, reinterpret_cast<int32_t*>(ws->thr), reinterpret_cast<int32_t*>(ws->stat), st);
 }
 
 }  // extern "C"

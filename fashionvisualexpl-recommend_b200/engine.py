@@ -296,15 +296,7 @@ class Engine:
             ws = self._eval_ws(n)
             call("fvx_score_topk_tc", C.byref(self.struct()), ptr(self.theta()), u0, u1, ptr(mask_row_ptr),
                  ptr(mask_col), k, ptr(ids), ptr(sc), C.byref(ws["struct"]), stream_ptr())
-            bad = torch.nonzero(ws["flags"][:n]).reshape(-1)       # (synchronises: the list length is needed)
-            self.tc_overflow_rows = int(bad.numel())
-            if bad.numel():                 # candidate lists overflowed: one exact fp32 sweep for those users
-                ul = (bad + u0).to(torch.int32).contiguous()
-                fi = torch.empty(bad.numel(), k, dtype=torch.int32, device=self.device)
-                fs = torch.empty(bad.numel(), k, dtype=torch.float32, device=self.device)
-                call("fvx_score_topk_users", C.byref(self.struct()), ptr(self.theta()), ptr(ul), ul.numel(),
-                     ptr(mask_row_ptr), ptr(mask_col), k, ptr(fi), ptr(fs), stream_ptr())
-                ids[bad], sc[bad] = fi, fs
+            self._last_flags = ws["flags"][:n]      # rows the exact kernel recomputed (inside the call)
             return ids, sc
         n_thr, counts = 0, None
         if thr_scores is not None:
@@ -326,19 +318,17 @@ class Engine:
             ws = self._eval_ws(n, struct=m, Ic=view["Ic"], key="_ws_view")
             call("fvx_score_topk_tc", C.byref(m), ptr(th), u0, u1, ptr(mask_row_ptr), ptr(mask_col), k, ptr(ids),
                  ptr(sc), C.byref(ws["struct"]), stream_ptr())
-            bad = torch.nonzero(ws["flags"][:n]).reshape(-1)
-            self.tc_overflow_rows = int(bad.numel())
-            if bad.numel():
-                ul = (bad + u0).to(torch.int32).contiguous()
-                fi = torch.empty(bad.numel(), k, dtype=torch.int32, device=self.device)
-                fs = torch.empty(bad.numel(), k, dtype=torch.float32, device=self.device)
-                call("fvx_score_topk_users", C.byref(m), ptr(th), ptr(ul), ul.numel(), ptr(mask_row_ptr),
-                     ptr(mask_col), k, ptr(fi), ptr(fs), stream_ptr())
-                ids[bad], sc[bad] = fi, fs
+            self._last_flags = ws["flags"][:n]
             return ids, sc
         call("fvx_score_topk", C.byref(m), ptr(th), u0, u1, ptr(mask_row_ptr), ptr(mask_col), k, ptr(ids), ptr(sc),
              0, None, None, stream_ptr())
         return ids, sc
+
+    @property
+    def tc_overflow_rows(self):
+        """Rows of the last tensor-core sweep that went through the exact fp32 kernel (synchronises)."""
+        f = getattr(self, "_last_flags", None)
+        return 0 if f is None else int((f != 0).sum().item())
 
     def _eval_ws(self, n_users, struct=None, Ic=None, key="_ws"):
         """Caller-owned workspace of fvx_score_topk_tc, sized by fvx_eval_ws_query and cached."""

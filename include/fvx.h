@@ -217,9 +217,9 @@ int fvx_score_topk_users(const FvxModel* model, const float* theta_ext, const in
  * The caller owns the workspace: fill KP / splits / cap with fvx_eval_ws_query() and
  * allocate A [u_cap*KP] bf16, Bm [i_cap*KP] bf16, epsa [u_cap] f32, nb [i_cap] f32, stat [2] f32,
  * cand [lists*cap] u64, ccount [lists] i32, flags [u_cap] i32, thr [u_cap] u32.
- * On return flags[u-u0] != 0 marks a user whose candidate list overflowed (or who has more
- * than ~180 train items): its output row is not valid and must be recomputed with
- * fvx_score_topk.  Needs K+d+3 <= 128. */
+ * Rows whose candidate list overflows (or users with more than ~180 train items) are recomputed
+ * by the exact fp32 kernel inside the same call; flags[u-u0] != 0 tells which (diagnostics only).
+ * Needs K+d+3 <= 128. */
 typedef struct FvxEvalWs {
   uint16_t* A;
   uint16_t* Bm;
