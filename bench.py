@@ -36,7 +36,7 @@ def parse():
     ap.add_argument("--embed_k", type=int, default=64)
     ap.add_argument("--embed_d", type=int, default=20)
     ap.add_argument("--feat_dim", type=int, default=2048)
-    ap.add_argument("--batch", type=int, default=16384)
+    ap.add_argument("--batch", type=int, default=65536)   # per GPU; BASELINE C3 / SURVEY 8(d) batch
     ap.add_argument("--top_k", type=int, default=100)
     ap.add_argument("--adam_mode", default="deferred", choices=["deferred", "dense", "lazy"])
     ap.add_argument("--tensor_cores", type=int, default=1)

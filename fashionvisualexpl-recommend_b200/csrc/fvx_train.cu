@@ -293,6 +293,193 @@ k_score_grad(FvxModel M, const int32_t* __restrict__ user, int B, int loss_slot,
   }
 }
 
+// The same work with 16-byte loads and 16-byte reductions (red.global.add.v4.f32, sm_90+): a lane owns
+// four consecutive columns.  The scatter-add is what bounds this kernel (214 float reductions per
+// triple at K=64, d=20 through the L2 atomic units); vectors cut the operation count by four.
+// Requires K % 4 == 0 (user row: Tu starts 16-byte aligned).
+__device__ __forceinline__ void red_add4(float* addr, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ float4 sg_at4(const SgTheta& T, long long slot, int c4) {
+  const float4* q = reinterpret_cast<const float4*>(T.p + slot * T.np) + c4;
+  float4 v = q[0];
+  for (int s = 1; s < T.ks; ++s) {
+    const float4 w = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(q) + s * T.ss);
+    v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+  }
+  return v;
+}
+__device__ __forceinline__ float dot4(float4 a, float4 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w))); }
+__device__ __forceinline__ uint2 pack_bf16x4(float4 v) {
+  const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+  return make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+}
+__device__ __forceinline__ float4 unpack_bf16x4(uint2 p) {
+  const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&p.x), hi = *reinterpret_cast<const __nv_bfloat162*>(&p.y);
+  const float2 a = __bfloat1622float2(lo), b = __bfloat1622float2(hi);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+
+// 16 lanes per triple (two triples per warp in flight: the kernel is bound by the latency of the
+// index -> row -> theta load chain, not by bytes), chunk c of a row handled by lane c % 16.
+__device__ __forceinline__ float half_sum(float v) {
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int MQ, int MD>
+__global__ void __launch_bounds__(SG_WARPS * 32, 4)
+k_score_grad_v4(FvxModel M, const int32_t* __restrict__ user, int B, int loss_slot, SgTheta T, int wnp) {
+  __shared__ double loss_sh[SG_WARPS * 2];
+  const int Su = M.users.stride, Si = M.items.stride, K = M.K, d = M.d, de = M.de;
+  const int K4 = K >> 2, D4 = (d + 3) >> 2;
+  const int grp = threadIdx.x >> 4, sub = threadIdx.x & 15;
+  const float reg = M.reg, reg2 = 2.0f * M.reg;
+  const bool vis = M.D > 0;
+  const long long gg0 = (long long)blockIdx.x * (SG_WARPS * 2) + grp;
+  const long long ng = (long long)gridDim.x * (SG_WARPS * 2);
+  const int nw4 = (wnp > 0 ? wnp : de) >> 2;
+  double loss_acc = 0.0;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const long long Bpad = ((long long)B + 1) & ~1LL;       // both halves of a warp walk the loop together
+
+  for (long long b = gg0; b < Bpad; b += ng) {
+    const bool live = b < B;
+    const int32_t u = live ? user[b] : -1;
+    const int32_t li = live ? M.rows[b] : -1, lj = live ? M.rows[B + b] : -1;
+    const bool dead = li < 0 || lj < 0 || u < 0 || u >= M.num_users;   // id outside the catalog: triple ignored
+    float coef = 0.0f;
+    float4 tu[MD];
+#pragma unroll
+    for (int q = 0; q < MD; ++q) tu[q] = z4;
+    float4 a[MQ], x[MQ], y[MQ], dt[MD];
+    float bi = 0.f, bj = 0.f, vb = 0.f;
+    if (!dead) {
+      const float4* ur = reinterpret_cast<const float4*>(M.users.w + (size_t)u * Su);
+      const float4* gi = reinterpret_cast<const float4*>(M.items.w + (size_t)li * Si);
+      const float4* gj = reinterpret_cast<const float4*>(M.items.w + (size_t)lj * Si);
+#pragma unroll
+      for (int q = 0; q < MQ; ++q) {
+        const int c = sub + 16 * q;
+        a[q] = c < K4 ? ur[c] : z4;
+        x[q] = c < K4 ? gi[c] : z4;
+        y[q] = c < K4 ? gj[c] : z4;
+      }
+#pragma unroll
+      for (int q = 0; q < MD; ++q) {
+        const int c = sub + 16 * q;
+        dt[q] = z4;
+        if (vis && c < D4) {
+          tu[q] = ur[K4 + c];
+          const float4 ti = sg_at4(T, b, c), tj = sg_at4(T, B + b, c);
+          dt[q] = make_float4(ti.x - tj.x, ti.y - tj.y, ti.z - tj.z, ti.w - tj.w);
+          const int n0 = 4 * c;      // columns >= d of the chunk are not latent terms (column d: visual bias)
+          if (n0 + 1 >= d) { tu[q].y = 0.f; dt[q].y = 0.f; }
+          if (n0 + 2 >= d) { tu[q].z = 0.f; dt[q].z = 0.f; }
+          if (n0 + 3 >= d) { tu[q].w = 0.f; dt[q].w = 0.f; }
+        }
+      }
+      bi = M.items.w[(size_t)li * Si + K];
+      bj = M.items.w[(size_t)lj * Si + K];
+      vb = vis ? T.at(b, d) - T.at(B + b, d) : 0.0f;
+    } else {
+#pragma unroll
+      for (int q = 0; q < MQ; ++q) { a[q] = z4; x[q] = z4; y[q] = z4; }
+#pragma unroll
+      for (int q = 0; q < MD; ++q) dt[q] = z4;
+    }
+    float part = 0.0f, sq = 0.0f;
+#pragma unroll
+    for (int q = 0; q < MQ; ++q) {
+      const float4 df = make_float4(x[q].x - y[q].x, x[q].y - y[q].y, x[q].z - y[q].z, x[q].w - y[q].w);
+      part += dot4(a[q], df);
+      sq += dot4(a[q], a[q]) + dot4(x[q], x[q]) + dot4(y[q], y[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < MD; ++q) {
+      part += dot4(tu[q], dt[q]);
+      sq += dot4(tu[q], tu[q]);
+    }
+    const float xs = half_sum(part) + (bi - bj) + vb;
+    const float sqs = half_sum(sq);
+    if (!dead) {
+      const bool inside = (xs >= FVX_CLIP_LO) && (xs <= FVX_CLIP_HI);
+      coef = inside ? -1.0f / (1.0f + expf(xs)) : 0.0f;  // d softplus(-x)/dx
+      const float z = -fminf(fmaxf(xs, FVX_CLIP_LO), FVX_CLIP_HI);
+      const float sp = z > 13.942385f ? z : (z < -13.942385f ? expf(z) : log1pf(expf(z)));
+      if (sub == 0) loss_acc += (double)sp + (double)(reg * sqs) + (double)(reg * bi * bi) +
+                                (double)(reg * bj * bj / 10.0f);
+      float* gu = M.users.g + (size_t)u * Su;
+      float* ggi = M.items.g + (size_t)li * Si;
+      float* ggj = M.items.g + (size_t)lj * Si;
+#pragma unroll
+      for (int q = 0; q < MQ; ++q) {
+        const int c = sub + 16 * q;
+        if (c < K4) {
+          const float4 A = a[q], X = x[q], Y = y[q];
+          red_add4(gu + 4 * c, make_float4(coef * (X.x - Y.x) + reg2 * A.x, coef * (X.y - Y.y) + reg2 * A.y,
+                                           coef * (X.z - Y.z) + reg2 * A.z, coef * (X.w - Y.w) + reg2 * A.w));
+          red_add4(ggi + 4 * c, make_float4(coef * A.x + reg2 * X.x, coef * A.y + reg2 * X.y,
+                                            coef * A.z + reg2 * X.z, coef * A.w + reg2 * X.w));
+          red_add4(ggj + 4 * c, make_float4(-coef * A.x + reg2 * Y.x, -coef * A.y + reg2 * Y.y,
+                                            -coef * A.z + reg2 * Y.z, -coef * A.w + reg2 * Y.w));
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < MD; ++q) {
+        const int c = sub + 16 * q;
+        if (vis && c < D4) {
+          const float4 U4 = tu[q], Dt = dt[q];
+          red_add4(gu + K + 4 * c, make_float4(coef * Dt.x + reg2 * U4.x, coef * Dt.y + reg2 * U4.y,
+                                               coef * Dt.z + reg2 * U4.z, coef * Dt.w + reg2 * U4.w));
+        }
+      }
+      if (sub == 0) {
+        fvx_red_add(ggi + K, coef + reg2 * bi);
+        fvx_red_add(ggj + K, -coef + (reg2 / 10.0f) * bj);
+      }
+    }
+    if (vis && live) {
+      // W[slot, n] = +-coef * [Tu | 1 | 0...] (zero rows for an ignored triple)
+#pragma unroll
+      for (int q = 0; q < MD; ++q) {
+        const int c = sub + 16 * q;
+        if (c < nw4) {
+          const int n0 = 4 * c;
+          float4 wv = make_float4(coef * tu[q].x, coef * tu[q].y, coef * tu[q].z, coef * tu[q].w);
+          if (n0 == d) wv.x = coef;
+          if (n0 + 1 == d) wv.y = coef;
+          if (n0 + 2 == d) wv.z = coef;
+          if (n0 + 3 == d) wv.w = coef;
+          if (wnp > 0) {   // bf16 hi/lo planes for the tensor-core backward
+            const uint2 h = pack_bf16x4(wv);
+            const float4 hf = unpack_bf16x4(h);
+            const uint2 l = pack_bf16x4(make_float4(wv.x - hf.x, wv.y - hf.y, wv.z - hf.z, wv.w - hf.w));
+            uint2* wh = reinterpret_cast<uint2*>(M.W_hi);
+            uint2* wl = reinterpret_cast<uint2*>(M.W_lo);
+            wh[(size_t)b * nw4 + c] = h;
+            wl[(size_t)b * nw4 + c] = l;
+            wh[(size_t)(B + b) * nw4 + c] = make_uint2(h.x ^ 0x80008000u, h.y ^ 0x80008000u);   // negation
+            wl[(size_t)(B + b) * nw4 + c] = make_uint2(l.x ^ 0x80008000u, l.y ^ 0x80008000u);
+          } else {
+            reinterpret_cast<float4*>(M.W)[(size_t)b * nw4 + c] = wv;
+            reinterpret_cast<float4*>(M.W)[(size_t)(B + b) * nw4 + c] = make_float4(-wv.x, -wv.y, -wv.z, -wv.w);
+          }
+        }
+      }
+    }
+  }
+  if (sub == 0) loss_sh[grp] = loss_acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < SG_WARPS * 2; ++w) s += loss_sh[w];
+    if (s != 0.0) atomicAdd(M.loss + loss_slot, s);
+  }
+}
+
 // ---------------------------------------------------------------------------------
 // One launch for the whole parameter update.  Blocks [0, nb_u): user rows, [nb_u, nb_u+nb_i):
 // item rows, the rest: E_ext.  The last block to finish advances the step counter.
@@ -364,8 +551,17 @@ k_update(FvxModel M, UpdParams U) {
     float sq = 0.0f;
     for (int i = (b - U.nb_u - U.nb_i) * blockDim.x + threadIdx.x; i < n; i += U.nb_e * blockDim.x) {
       const int f = i / M.de, c = i - f * M.de;
+      // the row-group partials are summed in a fixed order (0, 1, 2, ...) four loads at a time
+      const float* gp = U.gE_src + (size_t)f * U.gnp + c;
+      const size_t pstride = (size_t)M.D * U.gnp;
       float g = 0.0f;
-      for (int p = 0; p < U.parts; ++p) g += U.gE_src[((size_t)p * M.D + f) * U.gnp + c];
+      int p = 0;
+      for (; p + 4 <= U.parts; p += 4) {
+        const float g0 = gp[(size_t)p * pstride], g1 = gp[(size_t)(p + 1) * pstride];
+        const float g2 = gp[(size_t)(p + 2) * pstride], g3 = gp[(size_t)(p + 3) * pstride];
+        g = (((g + g0) + g1) + g2) + g3;
+      }
+      for (; p < U.parts; ++p) g += gp[(size_t)p * pstride];
       const float e = M.E[i];
       sq += e * e;
       g += 2.0f * reg * e;
@@ -432,10 +628,21 @@ int fvx_launch_score_grad(const FvxModel* m, const int32_t* user, int B, int los
   const int need = (m->K > m->d + 1 ? m->K : m->d + 1);
   FVX_CHECK_ARG(need <= 256 && (wnp == 0 || wnp <= 256), "fvx_bpr_step: K=%d / d=%d too large for the score kernel",
                 m->K, m->d);
-  if (need <= 64 && wnp <= 64)
+  const int wcols = wnp > 0 ? wnp : m->de;
+  if (m->K % 4 == 0 && m->K <= 256 && m->d <= 252 && wcols <= 256) {
+    // vector path: a lane owns 4 columns, 16 lanes per triple
+    const long long g2 = (g + 1) / 2 > 0 ? (g + 1) / 2 : 1;
+    if (m->K <= 64 && wcols <= 64)
+      k_score_grad_v4<1, 1><<<(int)g2, SG_WARPS * 32, 0, st>>>(*m, user, B, loss_slot, T, wnp);
+    else if (m->K <= 128 && wcols <= 128)
+      k_score_grad_v4<2, 2><<<(int)g2, SG_WARPS * 32, 0, st>>>(*m, user, B, loss_slot, T, wnp);
+    else
+      k_score_grad_v4<4, 4><<<(int)g2, SG_WARPS * 32, 0, st>>>(*m, user, B, loss_slot, T, wnp);
+  } else if (need <= 64 && wnp <= 64) {
     k_score_grad<2><<<(int)g, SG_WARPS * 32, 0, st>>>(*m, user, B, loss_slot, T, wnp);
-  else
+  } else {
     k_score_grad<8><<<(int)g, SG_WARPS * 32, 0, st>>>(*m, user, B, loss_slot, T, wnp);
+  }
   FVX_CHECK_LAUNCH("k_score_grad");
   return 0;
 }
@@ -463,7 +670,7 @@ int fvx_launch_update(const FvxModel* m, int B, int parts, int gnp, const float*
     U.nb_i = warp_grid(2LL * B, 256, 6);
   }
   U.nb_e = m->D > 0 ? (m->D * m->de + 255) / 256 : 0;
-  if (U.nb_e > fvx_num_sms() * 2) U.nb_e = fvx_num_sms() * 2;
+  if (U.nb_e > fvx_num_sms() * 4) U.nb_e = fvx_num_sms() * 4;
   U.parts = parts; U.gnp = gnp; U.loss_slot = loss_slot; U.sync = m->sync; U.gE_src = gE_src;
   k_update<<<U.nb_u + U.nb_i + U.nb_e, 256, 0, st>>>(*m, U);
   FVX_CHECK_LAUNCH("k_update");
