@@ -117,7 +117,9 @@ k_proj_fwd_tc(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant_
       }
       for (int c = 0; c < P.chunks; ++c) {
         const int chunk = ks * P.chunks + c;
-        mbar_wait(&empty_b[stage], phase ^ 1);
+        // one poller per warp: 128 threads spinning on the barrier word starve the arrive that flips it
+        if (lane == 0) mbar_wait(&empty_b[stage], phase ^ 1);
+        __syncwarp();
         const uint32_t sA = tc_smem_u32(smem + (size_t)stage * stage_bytes) + plane * a_bytes;
 #pragma unroll
         for (int it = 0; it < 16; ++it) {
@@ -290,7 +292,8 @@ k_grad_E_tc(const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ 
         if (item < 0) item = 0;
         src[j] = P.Fpl + (size_t)item * row_bytes + (size_t)fg * P.fgs * 4;
       }
-      mbar_wait(&empty_b[stage], phase ^ 1);
+      if (lane == 0) mbar_wait(&empty_b[stage], phase ^ 1);   // one poller per warp
+      __syncwarp();
       const uint32_t sA = tc_smem_u32(smem + (size_t)stage * stage_bytes);
       for (int e = lane; e < per_row; e += 32) {
         const int c = e >> 4, plane = (e >> 3) & 1, c16 = e & 7;
