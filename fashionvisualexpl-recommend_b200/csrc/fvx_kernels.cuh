@@ -25,6 +25,12 @@ int fvx_launch_reduce_gE(const FvxModel* m, int parts, int gnp, float* out, cuda
 int fvx_launch_grad_E_tc(const FvxModel* m, const int32_t* rows, int64_t nrows, int* parts_out, cudaStream_t st,
                          const int32_t* nrows_dev = nullptr);
 
+// single-pass step kernel (fvx_step_fused.cu): projection + scoring + grad_E, every feature row read once.
+// Eligible: use_tensor_cores >= 2, one rank, d + 1 <= 32, D in {1024, 2048}, K % 4 == 0, K <= 64.
+bool fvx_fused_eligible(const FvxModel* m);
+int fvx_launch_step_fused(const FvxModel* m, const int32_t* user, int B, int loss_slot, int* parts_out,
+                          cudaStream_t st);
+
 // pieces of the optimiser step shared with the item-sharded path (fvx_train_sharded.cu)
 int fvx_check_model(const FvxModel* m, const char* who);
 int fvx_launch_prep(const FvxModel* m, const int32_t* user, const int32_t* pos, const int32_t* neg, int B,

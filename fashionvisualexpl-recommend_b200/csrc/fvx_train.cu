@@ -695,6 +695,7 @@ static int bpr_step_impl(const FvxModel* model, const int32_t* user, const int32
   FVX_CHECK_ARG(M.rows != nullptr && M.loss != nullptr && M.sync != nullptr, "fvx_bpr_step: null scratch");
   const bool vis = M.D > 0;
   const bool tc = vis && M.use_tensor_cores;
+  const bool fused = tc && fvx_fused_eligible(&M);   // single-pass kernel (fvx_step_fused.cu)
   const int NP = tc ? fvx_tc_np(M.de) : M.de;
   int th_ks = 1;
   if (vis) FVX_CHECK_ARG(M.TH && M.gE_part && M.ge_parts > 0 && (tc || M.W), "fvx_bpr_step: VBPR scratch missing");
@@ -713,16 +714,22 @@ static int bpr_step_impl(const FvxModel* model, const int32_t* user, const int32
   PHASE(PH_PREP);
   if (int rc = fvx_launch_prep(&M, user, pos, neg, B, st)) return rc;
   PHASE(PH_PROJECT);
-  if (tc) {
+  int parts = 0;
+  if (fused) {
+    // projection, scoring and grad_E in one launch; the two phases below are empty
+    if (int rc = fvx_launch_step_fused(&M, user, B, loss_slot, &parts, st)) return rc;
+  } else if (tc) {
     if (int rc = fvx_launch_project_tc(&M, M.rows, 0, 2 * B, th_ks, M.TH, st)) return rc;
   } else if (vis) {
     if (int rc = fvx_launch_project(&M, M.rows, 2 * B, M.TH, st)) return rc;
   }
   PHASE(PH_SCORE_GRAD);
-  if (int rc = fvx_launch_score_grad(&M, user, B, loss_slot, th_ks, st)) return rc;
+  if (!fused) {
+    if (int rc = fvx_launch_score_grad(&M, user, B, loss_slot, th_ks, st)) return rc;
+  }
   PHASE(PH_GRAD_E);
-  int parts = 0;
-  if (tc) {
+  if (fused) {
+  } else if (tc) {
     if (int rc = fvx_launch_grad_E_tc(&M, M.rows, 2 * B, &parts, st)) return rc;
   } else if (vis) {
     if (int rc = fvx_launch_grad_E(&M, M.rows, 2 * B, &parts, st)) return rc;

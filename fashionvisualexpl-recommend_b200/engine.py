@@ -30,7 +30,7 @@ def _r4(x):
 class Engine:
     def __init__(self, num_users, num_items, K, d=0, D=0, lr=1e-3, reg=0.0, adam_mode="deferred",
                  max_batch=4096, device="cuda:0", item_lo=0, item_cnt=None, loss_slots=4096,
-                 ge_parts=80, seed=0, use_tensor_cores=False):
+                 ge_parts=80, seed=0, use_tensor_cores=False, fused_step=True):
         if not torch.cuda.is_available():
             raise _lib.FvxError("no CUDA device: the fvx engine has no CPU path")
         _lib.load()
@@ -68,6 +68,9 @@ class Engine:
         self.F = self.F_pl = None
         self.ET_hi = self.ET_lo = self.W_hi = self.W_lo = None
         self.use_tensor_cores = bool(use_tensor_cores) and self.D > 0
+        # single-pass step kernel (fvx_step_fused.cu); the library falls back to the two-kernel
+        # path when the geometry is not eligible
+        self.fused_step = bool(fused_step) and self.use_tensor_cores
         if self.D:
             self.E = torch.zeros(self.D, self.de, **f32)
             self.mE, self.vE = torch.zeros_like(self.E), torch.zeros_like(self.E)
@@ -196,7 +199,8 @@ class Engine:
             m.th_cap = self.TH.numel() if self.TH is not None else 0
             m.sync = ptr(self.sync_t)
             m.cmap = ptr(self.cmap_t)
-            m.max_batch, m.use_tensor_cores = self.max_batch, int(self.use_tensor_cores)
+            m.max_batch = self.max_batch
+            m.use_tensor_cores = (2 if self.fused_step else 1) if self.use_tensor_cores else 0
             self._struct = m
         return self._struct
 

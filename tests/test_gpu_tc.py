@@ -83,12 +83,19 @@ def _perturbed_oracle(P, F, batches, reg, lr, rel=2.0 ** -16, seed=7):
 
 
 @pytest.mark.parametrize("mode", ["dense", "deferred"])
-@pytest.mark.parametrize("K,d,D,B", [(64, 20, 256, 512), (16, 64, 128, 96), (8, 5, 128, 33), (32, 20, 2048, 1024)])
-def test_train_steps_tensor_cores_match_oracle(K, d, D, B, mode):
+@pytest.mark.parametrize("K,d,D,B,fused", [(64, 20, 256, 512, False), (16, 64, 128, 96, False), (8, 5, 128, 33, False),
+                                             (32, 20, 2048, 1024, False),
+                                             # single-pass cluster kernel (fvx_step_fused.cu): whole tiles, a ragged
+                                             # last tile, fewer triples than one tile, the narrow slice (D = 1024)
+                                             (32, 20, 2048, 1024, True), (64, 20, 2048, 1000, True),
+                                             (64, 20, 2048, 7, True), (16, 8, 1024, 333, True), (64, 31, 2048, 97, True)])
+def test_train_steps_tensor_cores_match_oracle(K, d, D, B, fused, mode):
     U, I, steps, lr, reg = 700, 900, 20, 0.001, 1e-3
     P, F, rng = _random_problem(U, I, K, d, D, seed=K + d)
-    e = _engine(U, I, K, d=d, D=D, lr=lr, reg=reg, adam_mode=mode, max_batch=B, use_tensor_cores=True)
+    e = _engine(U, I, K, d=d, D=D, lr=lr, reg=reg, adam_mode=mode, max_batch=B, use_tensor_cores=True,
+                fused_step=fused)
     e.set_features(F, keep_fp32=False)                    # the step must not need the fp32 copy
+    assert e.struct().use_tensor_cores == (2 if fused else 1)
     e.load_params(P)
     batches = _user_contiguous_batches(rng, U, I, B, steps)
     P32, P64, l32, l64 = _oracle_pair(P, F, batches, reg, lr)
@@ -104,3 +111,46 @@ def test_train_steps_tensor_cores_match_oracle(K, d, D, B, mode):
         e_f32, e_pert = rel_err(P32[k], ref), rel_err(Pp[k], ref)
         assert dlt.max() <= max(REL, 3 * e_f32, e_pert), (mode, k, dlt.max(), e_f32, e_pert)
         assert (dlt > REL).mean() <= 1e-3, (mode, k, "elements beyond 1e-4", int((dlt > REL).sum()), dlt.size)
+
+
+@pytest.mark.parametrize("tile", ["64", "48"])
+def test_fused_step_equals_two_kernel_path(tile, monkeypatch):
+    """The single-pass kernel against the projection -> score -> grad_E kernels on the same batches,
+    including triples whose item id lies outside the catalog (ignored by both) and a user run that
+    crosses tile and cluster boundaries.  Run in a subprocess-free way for the default tile; the
+    48-row / 3-stage variant is selected by FVX_FUSED_TILE before the library first launches it."""
+    import os
+    import subprocess
+    import sys
+    if tile == "48":
+        # the tile shape is latched at the first fused launch of a process: use a fresh one
+        env = dict(os.environ, FVX_FUSED_TILE="48", FVX_FUSED_CHILD="1")
+        r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", __file__, "-k",
+                            "test_fused_step_equals_two_kernel_path and 64", "-m", "gpu"],
+                           env=env, capture_output=True, text=True, cwd=os.path.dirname(os.path.dirname(__file__)))
+        assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+        return
+    U, I, K, d, D, B, steps = 500, 700, 64, 20, 2048, 2500, 6
+    P, F, rng = _random_problem(U, I, K, d, D, seed=11)
+    es = []
+    for fused in (False, True):
+        e = _engine(U, I, K, d=d, D=D, lr=1e-3, reg=1e-4, max_batch=B, use_tensor_cores=True, fused_step=fused)
+        e.set_features(F, keep_fp32=False)
+        e.load_params(P)
+        es.append(e)
+    batches = _user_contiguous_batches(rng, U, I, B, steps)
+    for s, (u, i, j) in enumerate(batches):
+        i = i.copy(); j = j.copy()
+        i[5::97] = I + 3                                   # outside the catalog: triple ignored
+        j[11::89] = -1
+        losses = []
+        for e in es:
+            e.step(_dev(u), _dev(i), _dev(j), loss_slot=0)
+            losses.append(e.read_loss(0))
+        assert losses[1] == pytest.approx(losses[0], rel=2e-6), s
+    Qa, Qb = es[0].params(), es[1].params()
+    for k in Qa:
+        # same arithmetic up to the summation order of the projection; Adam turns a gradient that
+        # sits at rounding noise into an O(lr) move, so a handful of elements may differ more
+        dlt = np.abs(Qb[k] - Qa[k]) / np.abs(Qa[k]).max()
+        assert dlt.max() <= 5e-3 and (dlt > 2e-5).mean() <= 1e-3, (k, dlt.max(), (dlt > 2e-5).mean())
