@@ -311,7 +311,8 @@ def run_fvx(args):
     # kernels of the timed region: 5 per step (prep, projection, score+grad, grad_E, update), 8 on the
     # sharded path (+ partial scores, reduce, scatter), 2 per generated epoch
     epochs_in_region = (args.steps * B) / max(data.num_train, 1)
-    per_step = (5 if D else 3) if world == 1 else (8 if D else 5)
+    # 1 GPU, VBPR: rows+planes, claims/catch-up, projection, score+grad, row update, grad_E, E update
+    per_step = (7 if D else 3) if world == 1 else (8 if D else 5)
     gpu_launches = args.steps * per_step + int(np.ceil(epochs_in_region)) * 2
 
     # ---- end to end through the reference-facing call: host batches in, float loss out ----

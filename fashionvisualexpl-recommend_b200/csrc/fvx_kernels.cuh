@@ -33,10 +33,15 @@ int fvx_launch_step_fused(const FvxModel* m, const int32_t* user, int B, int los
 
 // pieces of the optimiser step shared with the item-sharded path (fvx_train_sharded.cu)
 int fvx_check_model(const FvxModel* m, const char* who);
+// what: ALL = one launch (rows, claims + catch-up, E planes); ROWS = only what the projection needs
+// (slot rows + E planes); CLAIMS = claims + deferred-Adam catch-up without the row / plane writes
+enum { FVX_PREP_ALL = 0, FVX_PREP_ROWS = 1, FVX_PREP_CLAIMS = 2 };
 int fvx_launch_prep(const FvxModel* m, const int32_t* user, const int32_t* pos, const int32_t* neg, int B,
-                    cudaStream_t st);
+                    cudaStream_t st, int what = FVX_PREP_ALL);
+// what: ALL = tables + E_ext + finalisation; TABLES = touched rows only; E = E_ext + finalisation
+enum { FVX_UPD_ALL = 0, FVX_UPD_TABLES = 1, FVX_UPD_E = 2 };
 int fvx_launch_update(const FvxModel* m, int B, int parts, int gnp, const float* gE_src, int loss_slot,
-                      cudaStream_t st);
+                      cudaStream_t st, int what = FVX_UPD_ALL);
 int fvx_launch_score_grad(const FvxModel* m, const int32_t* user, int B, int loss_slot, int th_ks, cudaStream_t st);
 
 // exact fp32 top-k for the flagged rows of [u0, u0+n), in place, no host synchronisation (fvx_eval.cu)

@@ -108,6 +108,7 @@ struct FusedParams {
   int n_tiles;          // ceil(B / (TR/2))
   int loss_slot;
   float* gE_out;        // [clusters][D][FS_NP]
+  long long* trace;     // optional [tiles of cluster 0][16] clock64 stamps of CTA 0 (profiling aid), else nullptr
 };
 
 // Shared-memory map of one CTA (offsets from the 1024-byte aligned base).
@@ -139,6 +140,8 @@ struct FusedSmem {
   static_assert(A_SUB % 1024 == 0 && W_PLANE % 512 == 0, "swizzle atoms");
   static_assert(2 * E_PLANE + NST * W_STAGE >= 16384, "forward M=128 over-read leaves the allocation");
 };
+
+#define FS_STAMP(it_, ev_) do { if (tracing) P.trace[(it_) * 16 + (ev_)] = clock64(); } while (0)
 
 // ------------------------------------------------------------------------------------------
 template <int TR, int NST, int SL>
@@ -186,6 +189,7 @@ k_step_fused(const __grid_constant__ CUtensorMap tmE_hi, const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
 
   const int B = P.B;
+  const bool tracing = P.trace != nullptr && cid == 0 && crank == 0 && lane == 0;
   const int cnt = cid < P.n_tiles ? (P.n_tiles - cid + ncl - 1) / ncl : 0;   // tiles of this cluster
 
   if (warp < 4) {
@@ -222,6 +226,7 @@ k_step_fused(const __grid_constant__ CUtensorMap tmE_hi, const __grid_constant__
       }
       if (lane == 0) mbar_wait(&free_b[s], ph ^ 1);
       __syncwarp();
+      if (warp == 0) FS_STAMP(it, 0);
       const uint32_t sA = sbase + L::OFF_A + s * L::A_STAGE + doff;
 #pragma unroll
       for (int j = 0; j < IT; ++j) {
@@ -229,6 +234,7 @@ k_step_fused(const __grid_constant__ CUtensorMap tmE_hi, const __grid_constant__
         fs_cp16(sA + r * 128 + ((c16 ^ (r & 7)) << 4), src[j]);
       }
       fs_cp_arrive(&full_b[s]);
+      if (warp == 0) FS_STAMP(it, 1);
     }
   } else if (warp == 4) {
     // ===== UMMA issuer: forward of tile nf and backward of tile nb, whichever is ready =====
@@ -244,6 +250,7 @@ k_step_fused(const __grid_constant__ CUtensorMap tmE_hi, const __grid_constant__
         if (nb < nf) {
           const uint32_t s = nb % NST, ph = (nb / NST) & 1;
           if (mbar_try_wait_cl(&w_full[s], ph)) {
+            FS_STAMP(nb, 4);
             fence_proxy_async_all();       // W rows were written through the generic proxy (remote stores)
             tc_fence_after();
             const uint32_t a_hi = sbase + L::OFF_A + s * L::A_STAGE, a_lo = a_hi + L::A_PLANE;
@@ -264,6 +271,7 @@ k_step_fused(const __grid_constant__ CUtensorMap tmE_hi, const __grid_constant__
               }
             }
             umma_commit(&free_b[s]);
+            FS_STAMP(nb, 5);
             ++nb;
             did = true;
           }
@@ -271,6 +279,7 @@ k_step_fused(const __grid_constant__ CUtensorMap tmE_hi, const __grid_constant__
         if (nf < cnt) {
           const uint32_t s = nf % NST, ph = (nf / NST) & 1, acc = nf & 1, aph = (nf >> 1) & 1;
           if (mbar_try_wait(&t_empty[acc], aph ^ 1) && mbar_try_wait(&full_b[s], ph)) {
+            FS_STAMP(nf, 2);
             fence_proxy_async_smem();      // cp.async (generic proxy) writes -> UMMA (async proxy) reads
             tc_fence_after();
             const uint32_t a_hi = sbase + L::OFF_A + s * L::A_STAGE, a_lo = a_hi + L::A_PLANE;
@@ -288,6 +297,7 @@ k_step_fused(const __grid_constant__ CUtensorMap tmE_hi, const __grid_constant__
               }
             }
             umma_commit(&t_full[acc]);
+            FS_STAMP(nf, 3);
             ++nf;
             did = true;
           }
@@ -340,6 +350,7 @@ k_step_fused(const __grid_constant__ CUtensorMap tmE_hi, const __grid_constant__
       // (B) forward partial rows -> the CTA that owns the row's triple
       if (quad < 2) {
         mbar_wait(&t_full[acc], aph);
+        if (warp == 5) FS_STAMP(it, 6);
         tc_fence_after();
         float sum[32];
 #pragma unroll
@@ -366,12 +377,14 @@ k_step_fused(const __grid_constant__ CUtensorMap tmE_hi, const __grid_constant__
                      __float_as_uint(sum[j + 3]));
           cl_arrive(cl_map(tc_smem_u32(&xb_full[s]), owner));
         }
+        if (warp == 5) FS_STAMP(it, 7);
       }
 
       // (C) score my triple
       if (widx < TPC) {
         if (lane == 0) mbar_wait_cl(&xb_full[s], ph);
         __syncwarp();
+        if (warp == 5) FS_STAMP(it, 8);
         float4 dt = z4;
         float vb_l = 0.f;
         if (cv >= 0 && cv < FS_NP / 4) {
@@ -452,6 +465,7 @@ k_step_fused(const __grid_constant__ CUtensorMap tmE_hi, const __grid_constant__
           sg[24 + cv] = make_uint2(l.x ^ 0x80008000u, l.y ^ 0x80008000u);
         }
         __syncwarp();
+        if (warp == 5) FS_STAMP(it, 9);
         {
           const uint32_t dest = (uint32_t)lane >> 2, piece = (uint32_t)lane & 3;
           const uint32_t wb = cl_map(sbase + L::OFF_W + s * L::W_STAGE, dest);
@@ -464,6 +478,7 @@ k_step_fused(const __grid_constant__ CUtensorMap tmE_hi, const __grid_constant__
           fence_proxy_async_all();
           cl_arrive(cl_map(tc_smem_u32(&w_full[s]), dest));
         }
+        if (warp == 5) FS_STAMP(it, 10);
         __syncwarp();                      // the staging buffer is rewritten by the next tile
       }
     }
@@ -507,6 +522,14 @@ k_step_fused(const __grid_constant__ CUtensorMap tmE_hi, const __grid_constant__
   }
 }
 
+static long long* g_fused_trace = nullptr;
+static long long g_fused_trace_cap = 0;
+extern "C" int fvx_debug_fused_trace(long long* buf, long long n) {   // profiling aid, not part of fvx.h
+  g_fused_trace = buf;
+  g_fused_trace_cap = n;
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------
 bool fvx_fused_eligible(const FvxModel* m) {
   if (!(m->D > 0 && m->use_tensor_cores >= 2)) return false;
@@ -546,10 +569,12 @@ static int launch_fused(const FvxModel* m, const int32_t* user, int B, int loss_
   P.Fpl = reinterpret_cast<const uint8_t*>(m->F_pl);
   P.user = user; P.B = B; P.loss_slot = loss_slot; P.gE_out = m->gE_part;
   P.n_tiles = (B + TR / 2 - 1) / (TR / 2);
+  P.trace = nullptr;
   int ncl = max_clusters < P.n_tiles ? max_clusters : P.n_tiles;
   if (ncl > m->ge_parts) ncl = m->ge_parts;
   FVX_CHECK_ARG(ncl >= 1, "k_step_fused: gE_part has no room");
   *parts_out = ncl;
+  if (g_fused_trace && (long long)((P.n_tiles + ncl - 1) / ncl) * 16 <= g_fused_trace_cap) P.trace = g_fused_trace;
   CUtensorMap e_hi, e_lo;
   int rc = 0;
   const uint64_t pitch = (uint64_t)m->D * 2;

@@ -11,6 +11,7 @@
 //   k_update      Adam on the touched rows (or whole tables: DENSE), dense Adam on E_ext,
 //                 step += 1 and list reset by the last block
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "fvx_common.cuh"
 #include "fvx_kernels.cuh"
@@ -81,22 +82,44 @@ __device__ __forceinline__ uint32_t claim_rows(const FvxTable& T, int32_t r, boo
 
 #define PREP_TPW 8
 // blocks [0, nb_mark): PREP_TPW triples per warp pass; blocks beyond: bf16 planes of E_ext^T
+// bf16 hi / lo planes of E_ext^T [NP, D] (rows >= de zero), blocks blk of nblk
+__device__ __forceinline__ void split_E_planes(const FvxModel& M, int NP, int blk, int nblk) {
+  __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(M.ET_hi);
+  __nv_bfloat16* lo = reinterpret_cast<__nv_bfloat16*>(M.ET_lo);
+  const int total = NP * M.D;
+  for (int i = blk * blockDim.x + threadIdx.x; i < total; i += nblk * blockDim.x) {
+    const int n = i / M.D, f = i - n * M.D;
+    const float x = n < M.de ? M.E[(size_t)f * M.de + n] : 0.0f;
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    hi[i] = h;
+    lo[i] = __float2bfloat16_rn(x - __bfloat162float(h));
+  }
+}
+
+// What the projection needs from the batch, and nothing else: the local item row of every
+// (triple, side) slot and the planes of E_ext^T.  Launched on the main stream while k_prep (claims +
+// deferred-Adam catch-up) runs beside the projection on the side stream.
+__global__ void __launch_bounds__(256)
+k_rows_et(FvxModel M, const int32_t* __restrict__ pos, const int32_t* __restrict__ neg, int B, int nb_rows, int NP) {
+  if ((int)blockIdx.x >= nb_rows) {
+    split_E_planes(M, NP, blockIdx.x - nb_rows, gridDim.x - nb_rows);
+    return;
+  }
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += nb_rows * blockDim.x) {
+    int32_t li = pos[b] - M.item_lo, lj = neg[b] - M.item_lo;
+    if (li < 0 || li >= M.item_cnt) li = -1;
+    if (lj < 0 || lj >= M.item_cnt) lj = -1;
+    M.rows[b] = li;
+    M.rows[B + b] = lj;
+  }
+}
+
 __global__ void __launch_bounds__(256)
 k_prep(FvxModel M, const int32_t* __restrict__ user, const int32_t* __restrict__ pos,
-       const int32_t* __restrict__ neg, int B, int nb_mark, int NP) {
+       const int32_t* __restrict__ neg, int B, int nb_mark, int NP, int write_rows) {
   const int lane = threadIdx.x & 31;
   if ((int)blockIdx.x >= nb_mark) {
-    __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(M.ET_hi);
-    __nv_bfloat16* lo = reinterpret_cast<__nv_bfloat16*>(M.ET_lo);
-    const int total = NP * M.D;
-    for (int i = (blockIdx.x - nb_mark) * blockDim.x + threadIdx.x; i < total;
-         i += (gridDim.x - nb_mark) * blockDim.x) {
-      const int n = i / M.D, f = i - n * M.D;
-      const float x = n < M.de ? M.E[(size_t)f * M.de + n] : 0.0f;
-      const __nv_bfloat16 h = __float2bfloat16_rn(x);
-      hi[i] = h;
-      lo[i] = __float2bfloat16_rn(x - __bfloat162float(h));
-    }
+    split_E_planes(M, NP, blockIdx.x - nb_mark, gridDim.x - nb_mark);
     return;
   }
   const int32_t done = (int32_t)(*M.step);
@@ -118,8 +141,10 @@ k_prep(FvxModel M, const int32_t* __restrict__ user, const int32_t* __restrict__
       lj = neg[b] - M.item_lo;
       if (li_ < 0 || li_ >= M.item_cnt) li_ = -1;
       if (lj < 0 || lj >= M.item_cnt) lj = -1;
-      M.rows[b] = li_;
-      M.rows[B + b] = lj;
+      if (write_rows) {
+        M.rows[b] = li_;
+        M.rows[B + b] = lj;
+      }
     }
     uint32_t wu = claim_rows(M.users, u, live && ustart && u >= 0 && u < M.num_users, t, lane);
     uint32_t wi = claim_rows(M.items, li_, li_ >= 0, t, lane);
@@ -488,6 +513,7 @@ struct UpdParams {
   int parts, gnp;       // gE_part: `parts` row-group partials with row stride gnp
   int loss_slot;
   int dense;            // DENSE: sweep the whole tables
+  int finalize;         // the last block advances the step counter and resets the lists
   int32_t* sync;        // [1] blocks-done counter (zero between launches)
   const float* gE_src;  // partial gradients of E_ext (model->gE_part, or an all-reduced [D, de] buffer)
 };
@@ -575,6 +601,7 @@ k_update(FvxModel M, UpdParams U) {
     if ((threadIdx.x & 31) == 0 && sq != 0.0f && U.loss_slot >= 0) atomicAdd(M.loss + U.loss_slot, (double)(reg * sq));
   }
   // last block: the step is complete
+  if (!U.finalize) return;
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
@@ -648,18 +675,27 @@ int fvx_launch_score_grad(const FvxModel* m, const int32_t* user, int B, int los
 }
 
 int fvx_launch_prep(const FvxModel* m, const int32_t* user, const int32_t* pos, const int32_t* neg, int B,
-                    cudaStream_t st) {
+                    cudaStream_t st, int what) {
   const bool tc = m->D > 0 && m->use_tensor_cores;
+  const int NP = tc ? fvx_tc_np(m->de) : m->de;
+  const int nb_e = tc ? 32 : 0;
+  if (what == FVX_PREP_ROWS) {
+    int nb_rows = (B + 255) / 256;
+    if (nb_rows > fvx_num_sms() * 4) nb_rows = fvx_num_sms() * 4;
+    k_rows_et<<<nb_rows + nb_e, 256, 0, st>>>(*m, pos, neg, B, nb_rows, NP);
+    FVX_CHECK_LAUNCH("k_rows_et");
+    return 0;
+  }
   int nb_mark = (B + 8 * PREP_TPW - 1) / (8 * PREP_TPW);     // 8 warps per block
   if (nb_mark > fvx_num_sms() * 8) nb_mark = fvx_num_sms() * 8;
-  const int nb_e = tc ? 32 : 0;
-  k_prep<<<nb_mark + nb_e, 256, 0, st>>>(*m, user, pos, neg, B, nb_mark, tc ? fvx_tc_np(m->de) : m->de);
+  const bool all = what == FVX_PREP_ALL;
+  k_prep<<<nb_mark + (all ? nb_e : 0), 256, 0, st>>>(*m, user, pos, neg, B, nb_mark, NP, all ? 1 : 0);
   FVX_CHECK_LAUNCH("k_prep");
   return 0;
 }
 
 int fvx_launch_update(const FvxModel* m, int B, int parts, int gnp, const float* gE_src, int loss_slot,
-                      cudaStream_t st) {
+                      cudaStream_t st, int what) {
   UpdParams U;
   U.dense = m->adam_mode == FVX_ADAM_DENSE;
   if (U.dense) {
@@ -671,6 +707,10 @@ int fvx_launch_update(const FvxModel* m, int B, int parts, int gnp, const float*
   }
   U.nb_e = m->D > 0 ? (m->D * m->de + 255) / 256 : 0;
   if (U.nb_e > fvx_num_sms() * 4) U.nb_e = fvx_num_sms() * 4;
+  // split launch: the table rows (no finalisation) beside grad_E, then E_ext + finalisation
+  if (what == FVX_UPD_TABLES) U.nb_e = 0;
+  if (what == FVX_UPD_E) { U.nb_u = 0; U.nb_i = 0; if (U.nb_e == 0) U.nb_e = 1; }
+  U.finalize = what != FVX_UPD_TABLES;
   U.parts = parts; U.gnp = gnp; U.loss_slot = loss_slot; U.sync = m->sync; U.gE_src = gE_src;
   k_update<<<U.nb_u + U.nb_i + U.nb_e, 256, 0, st>>>(*m, U);
   FVX_CHECK_LAUNCH("k_update");
@@ -678,6 +718,36 @@ int fvx_launch_update(const FvxModel* m, int B, int parts, int gnp, const float*
 }
 
 int fvx_check_model(const FvxModel* m, const char* who) { return check_model(m, who); }
+
+// Side stream of the two-stream step schedule: one per device, created on first use.
+// FVX_STEP_OVERLAP=0 keeps every kernel of the step on the caller's stream.
+struct SideStream {
+  cudaStream_t s;
+  cudaEvent_t fork, prep_done, score_done, upd_done;
+};
+static SideStream* side_stream() {
+  static SideStream pool[16];
+  static int state[16];   // 0: untried, 1: ready, -1: unavailable
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("FVX_STEP_OVERLAP");
+    enabled = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  if (!enabled) return nullptr;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  if (state[dev] == 0) {
+    SideStream& p = pool[dev];
+    bool ok = cudaStreamCreateWithFlags(&p.s, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&p.fork, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&p.prep_done, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&p.score_done, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&p.upd_done, cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) cudaGetLastError();
+    state[dev] = ok ? 1 : -1;
+  }
+  return state[dev] == 1 ? &pool[dev] : nullptr;
+}
 
 // phases of one step, in launch order (FVX_N_PHASES entries; see fvx.h)
 enum { PH_PREP = 0, PH_PROJECT, PH_SCORE_GRAD, PH_GRAD_E, PH_UPDATE, PH_COUNT };
@@ -710,6 +780,40 @@ static int bpr_step_impl(const FvxModel* model, const int32_t* user, const int32
     FVX_CHECK_ARG(2LL * B * M.de <= M.th_cap, "fvx_bpr_step: TH scratch too small");
   }
 #define PHASE(i) do { if (ev) cudaEventRecord(ev[i], st); } while (0)
+
+  // Two-stream schedule (VBPR, untimed calls): the claims + deferred-Adam catch-up touch only the
+  // embedding tables and run BESIDE the projection; the Adam update of the touched rows runs beside
+  // grad_E.  Both side kernels are latency-bound (atomics, dependent row loads), the projection
+  // kernels are bandwidth-bound, so the overlap is nearly free.  The timed entry point keeps
+  // everything on one stream so that each phase is measured alone.
+  SideStream* side = (vis && !ev && !fused) ? side_stream() : nullptr;
+  if (side) {
+    if (int rc = fvx_launch_prep(&M, user, pos, neg, B, st, FVX_PREP_ROWS)) return rc;
+    cudaEventRecord(side->fork, st);
+    cudaStreamWaitEvent(side->s, side->fork, 0);
+    if (int rc = fvx_launch_prep(&M, user, pos, neg, B, side->s, FVX_PREP_CLAIMS)) return rc;
+    cudaEventRecord(side->prep_done, side->s);
+    if (tc) {
+      if (int rc = fvx_launch_project_tc(&M, M.rows, 0, 2 * B, th_ks, M.TH, st)) return rc;
+    } else {
+      if (int rc = fvx_launch_project(&M, M.rows, 2 * B, M.TH, st)) return rc;
+    }
+    cudaStreamWaitEvent(st, side->prep_done, 0);
+    if (int rc = fvx_launch_score_grad(&M, user, B, loss_slot, th_ks, st)) return rc;
+    cudaEventRecord(side->score_done, st);
+    cudaStreamWaitEvent(side->s, side->score_done, 0);
+    if (int rc = fvx_launch_update(&M, B, 0, NP, M.gE_part, loss_slot, side->s, FVX_UPD_TABLES)) return rc;
+    cudaEventRecord(side->upd_done, side->s);
+    int parts = 0;
+    if (tc) {
+      if (int rc = fvx_launch_grad_E_tc(&M, M.rows, 2 * B, &parts, st)) return rc;
+    } else {
+      if (int rc = fvx_launch_grad_E(&M, M.rows, 2 * B, &parts, st)) return rc;
+    }
+    cudaStreamWaitEvent(st, side->upd_done, 0);      // join: the step is complete on `st`
+    if (int rc = fvx_launch_update(&M, B, parts, NP, M.gE_part, loss_slot, st, FVX_UPD_E)) return rc;
+    return 0;
+  }
 
   PHASE(PH_PREP);
   if (int rc = fvx_launch_prep(&M, user, pos, neg, B, st)) return rc;

@@ -30,7 +30,7 @@ def _r4(x):
 class Engine:
     def __init__(self, num_users, num_items, K, d=0, D=0, lr=1e-3, reg=0.0, adam_mode="deferred",
                  max_batch=4096, device="cuda:0", item_lo=0, item_cnt=None, loss_slots=4096,
-                 ge_parts=80, seed=0, use_tensor_cores=False, fused_step=True):
+                 ge_parts=80, seed=0, use_tensor_cores=False, fused_step=False):
         if not torch.cuda.is_available():
             raise _lib.FvxError("no CUDA device: the fvx engine has no CPU path")
         _lib.load()
@@ -68,7 +68,8 @@ class Engine:
         self.F = self.F_pl = None
         self.ET_hi = self.ET_lo = self.W_hi = self.W_lo = None
         self.use_tensor_cores = bool(use_tensor_cores) and self.D > 0
-        # single-pass step kernel (fvx_step_fused.cu); the library falls back to the two-kernel
+        # opt-in single-pass step kernel (fvx_step_fused.cu: correct, but measured slower than the
+        # two-kernel path in round 1 - DESIGN.md section 3); the library falls back to the two-kernel
         # path when the geometry is not eligible
         self.fused_step = bool(fused_step) and self.use_tensor_cores
         if self.D:
