@@ -104,17 +104,31 @@ k_proj_fwd_tc(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant_
     const int plane = e >> 3, c16 = e & 7;
     const size_t row_bytes = (size_t)P.D * 4;
     uint32_t stage = 0, phase = 0;
+    // The row indices of a unit are loaded one unit AHEAD: an index load issued behind a full
+    // pipeline of cp.async requests takes microseconds, and a producer that waits for it lets the
+    // stages run dry (36 % of the producers' samples in the round-1 v4 profile).
+    int32_t nxt[16];
+    auto load_idx = [&](int w) {
+      const int tile = w / P.ksplit;
+#pragma unroll
+      for (int it = 0; it < 16; ++it) {
+        const long long r = (long long)tile * PT_BM + it * 8 + sub;
+        int32_t item = 0;
+        if (r < nvalid) item = P.rows ? __ldg(P.rows + r) : (int32_t)(P.row0 + r);
+        nxt[it] = item;
+      }
+    };
+    if ((int)blockIdx.x < n_units) load_idx(blockIdx.x);
     for (int w = blockIdx.x; w < n_units; w += gridDim.x) {
       const int tile = w / P.ksplit, ks = w - tile * P.ksplit;
       const uint8_t* src[16];
 #pragma unroll
       for (int it = 0; it < 16; ++it) {
-        const long long r = (long long)tile * PT_BM + it * 8 + sub;
-        long long item = 0;
-        if (r < nvalid) item = P.rows ? (long long)P.rows[r] : (long long)P.row0 + r;
+        long long item = nxt[it];
         if (item < 0) item = 0;               // slot of another rank's item: any valid row, result unused
         src[it] = P.Fpl + (size_t)item * row_bytes + e * 16;
       }
+      if (w + (int)gridDim.x < n_units) load_idx(w + gridDim.x);
       for (int c = 0; c < P.chunks; ++c) {
         const int chunk = ks * P.chunks + c;
         // one poller per warp: 128 threads spinning on the barrier word starve the arrive that flips it
@@ -281,17 +295,30 @@ k_grad_E_tc(const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ 
     const size_t row_bytes = (size_t)P.D * 4;
     const int per_row = P.fgs / 4;            // 16-byte elements of one row slice (both planes)
     uint32_t stage = 0, phase = 0;
+    // row indices one tile ahead (see the forward kernel: an index load queued behind the cp.async
+    // traffic is slow, and here it used to sit in front of EVERY 32-row tile)
+    int32_t nxt[GE_RT / 4];
+    auto load_idx = [&](int t) {
+      const long long r0 = r_begin + (long long)t * GE_RT;
+#pragma unroll
+      for (int j = 0; j < GE_RT / 4; ++j) {
+        const long long r = r0 + j * 4 + warp;
+        int32_t item = 0;
+        if (r < nvalid) item = P.rows ? __ldg(P.rows + r) : (int32_t)r;
+        nxt[j] = item;
+      }
+    };
+    if (n_tiles > 0) load_idx(0);
     for (int t = 0; t < n_tiles; ++t) {
       const long long r0 = r_begin + (long long)t * GE_RT;
       const uint8_t* src[GE_RT / 4];
 #pragma unroll
       for (int j = 0; j < GE_RT / 4; ++j) {
-        const long long r = r0 + j * 4 + warp;
-        long long item = 0;
-        if (r < nvalid) item = P.rows ? (long long)P.rows[r] : r;
+        long long item = nxt[j];
         if (item < 0) item = 0;
         src[j] = P.Fpl + (size_t)item * row_bytes + (size_t)fg * P.fgs * 4;
       }
+      if (t + 1 < n_tiles) load_idx(t + 1);
       if (lane == 0) mbar_wait(&empty_b[stage], phase ^ 1);   // one poller per warp
       __syncwarp();
       const uint32_t sA = tc_smem_u32(smem + (size_t)stage * stage_bytes);
