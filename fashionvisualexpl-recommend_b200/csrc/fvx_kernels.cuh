@@ -13,6 +13,13 @@ int fvx_launch_grad_E(const FvxModel* m, const int32_t* rows, int64_t nrows, int
 // partials (NP = fvx_tc_np(de), ksplit = fvx_tc_ksplit(...)); the backward reads the bf16 planes
 // m->W_hi / m->W_lo [nrows][NP] and writes gE_part[parts][D][NP].
 int fvx_tc_np(int de);
+// Row pitch (bf16 elements) of the W planes: 2*NP when the two planes are interleaved row by row in
+// one allocation (W_lo == W_hi + NP: row r = [hi 0..NP | lo 0..NP], what the engine allocates - the
+// backward then reads [W_hi | W_lo] as ONE operand of N = 2*NP), else NP (two separate planes).
+static inline int fvx_w_pitch(const FvxModel* m) {
+  const int np = fvx_tc_np(m->de);
+  return (m->W_lo == m->W_hi + np) ? 2 * np : np;
+}
 int fvx_tc_ksplit(const FvxModel* m, long long nrows);
 int fvx_launch_split_E(const FvxModel* m, cudaStream_t st);
 int fvx_launch_split_planes(const float* src, uint16_t* dst, long long n_rows, int D, cudaStream_t st);

@@ -56,6 +56,8 @@ struct ProjFwdParams {
   int n_tiles;          // 128-row tiles
   int stages;
   int nacc;             // independent accumulators per buffer (one per UMMA K step of a chunk)
+  int cat;              // 1: B = [E_hi | E_lo] as ONE operand of N = 2*NP - two UMMAs per K step
+                        //    (A_hi, A_lo) instead of three; the epilogue adds the two column halves
   float* out;           // [ksplit][nrows][NP]
 };
 
@@ -84,8 +86,9 @@ k_proj_fwd_tc(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant_
   }
   // A UMMA that accumulates into the columns its predecessor wrote waits for it; each K step of
   // a chunk therefore owns its own accumulator and the epilogue adds them.
+  const uint32_t NW = P.cat ? 2u * P.NP : (uint32_t)P.NP;   // accumulator width in TMEM columns
   uint32_t tcols = 32;
-  while (tcols < 2u * P.nacc * P.NP) tcols <<= 1;
+  while (tcols < 2u * P.nacc * NW) tcols <<= 1;
   if (warp == 4) tmem_alloc(tmem_slot, tcols);
   tc_fence_before();
   __syncthreads();
@@ -153,12 +156,12 @@ k_proj_fwd_tc(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant_
   } else if (warp == 4) {
     // ===== UMMA issuer =====
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(PT_BM, P.NP, 0, 0);
+      const uint32_t idesc = umma_idesc_bf16(PT_BM, (int)NW, 0, 0);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       for (int w = blockIdx.x; w < n_units; w += gridDim.x) {
         mbar_wait(&t_empty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d0 = tmem_base + acc * P.nacc * P.NP;
+        const uint32_t d0 = tmem_base + acc * P.nacc * NW;
         for (int c = 0; c < P.chunks; ++c) {
           mbar_wait(&full_b[stage], phase);
           fence_proxy_async_smem();           // cp.async (generic proxy) writes -> UMMA (async proxy) reads
@@ -166,15 +169,32 @@ k_proj_fwd_tc(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant_
           const uint32_t a_hi = tc_smem_u32(smem + (size_t)stage * stage_bytes);
           const uint32_t a_lo = a_hi + a_bytes, b_hi = a_lo + a_bytes, b_lo = b_hi + b_bytes;
           // pass-major, K-step-minor: consecutive UMMAs target different accumulators
+          if (P.cat) {
+            // the hi and lo tiles of E_ext^T are adjacent in shared memory: one descriptor of 2*NP rows
+            // reads both, so A_hi and A_lo are fetched once each (the smem operand fetch, not the
+            // tensor pipe, paces these N = 32 products)
 #pragma unroll
-          for (int pass = 0; pass < 3; ++pass) {
+            for (int pass = 0; pass < 2; ++pass) {
 #pragma unroll
-            for (int k = 0; k < PT_KC / 16; ++k) {
-              const uint32_t d = d0 + (uint32_t)(k % P.nacc) * P.NP;
-              const uint64_t da = umma_smem_desc((pass == 1 ? a_lo : a_hi) + k * 32, 16, 1024, TC_SWZ_128B);
-              const uint64_t db = umma_smem_desc((pass == 2 ? b_lo : b_hi) + k * 32, 16, 1024, TC_SWZ_128B);
-              const bool first = c == 0 && pass == 0 && k < P.nacc;
-              umma_f16(d, da, db, idesc, first ? 0u : 1u);
+              for (int k = 0; k < PT_KC / 16; ++k) {
+                const uint32_t d = d0 + (uint32_t)(k % P.nacc) * NW;
+                const uint64_t da = umma_smem_desc((pass == 1 ? a_lo : a_hi) + k * 32, 16, 1024, TC_SWZ_128B);
+                const uint64_t db = umma_smem_desc(b_hi + k * 32, 16, 1024, TC_SWZ_128B);
+                const bool first = c == 0 && pass == 0 && k < P.nacc;
+                umma_f16(d, da, db, idesc, first ? 0u : 1u);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int pass = 0; pass < 3; ++pass) {
+#pragma unroll
+              for (int k = 0; k < PT_KC / 16; ++k) {
+                const uint32_t d = d0 + (uint32_t)(k % P.nacc) * P.NP;
+                const uint64_t da = umma_smem_desc((pass == 1 ? a_lo : a_hi) + k * 32, 16, 1024, TC_SWZ_128B);
+                const uint64_t db = umma_smem_desc((pass == 2 ? b_lo : b_hi) + k * 32, 16, 1024, TC_SWZ_128B);
+                const bool first = c == 0 && pass == 0 && k < P.nacc;
+                umma_f16(d, da, db, idesc, first ? 0u : 1u);
+              }
             }
           }
           umma_commit(&empty_b[stage]);
@@ -196,9 +216,12 @@ k_proj_fwd_tc(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant_
       float* dst = P.out + ((size_t)ks * P.nrows + (size_t)(row < nvalid ? row : 0)) * P.NP;
       for (int n0 = 0; n0 < P.NP; n0 += 32) {
         float sum[32];
-        for (int a = 0; a < P.nacc; ++a) {
+        const int nparts = P.cat ? 2 * P.nacc : P.nacc;   // cat: columns [0,NP) and [NP,2NP) of every accumulator
+        for (int a = 0; a < nparts; ++a) {
           uint32_t v[32];
-          tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (acc * P.nacc + a) * P.NP + n0, v);
+          const uint32_t col = P.cat ? (uint32_t)(acc * P.nacc + (a >> 1)) * NW + (uint32_t)(a & 1) * P.NP
+                                     : (uint32_t)(acc * P.nacc + a) * P.NP;
+          tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + col + n0, v);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) sum[j] = a == 0 ? __uint_as_float(v[j]) : sum[j] + __uint_as_float(v[j]);
@@ -237,6 +260,8 @@ struct GradEParams {
   int stages;
   int w_atoms;          // 64-column sub-tiles of the W tile (1 for NP <= 64)
   int w_sw;             // swizzle of the W tile: TC_SWZ_64B (NP == 32) or TC_SWZ_128B
+  int cat;              // 1 (NP == 32, interleaved W planes): the W tile is [32 rows x (hi 32 | lo 32)], ONE operand
+                        //    of N = 64 - two UMMAs per K step (F_hi^T, F_lo^T) instead of three
   float* out;           // [row groups][D][NP]
 };
 
@@ -249,10 +274,11 @@ k_grad_E_tc(const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ 
   const int nchunk = P.fgs / PT_KC;                          // 64-feature chunks per stage
   const uint32_t chunk_bytes = GE_RT * 128u;                 // [32 rows x 128 B]
   const uint32_t a_bytes = (uint32_t)nchunk * chunk_bytes;   // one plane
-  const uint32_t wrow_bytes = P.NP <= 64 ? (uint32_t)P.NP * 2u : 128u;
+  const uint32_t wrow_bytes = P.cat ? 128u : (P.NP <= 64 ? (uint32_t)P.NP * 2u : 128u);
   const uint32_t watom_bytes = GE_RT * wrow_bytes;
-  const uint32_t w_bytes = (uint32_t)P.w_atoms * watom_bytes;  // one plane
-  const uint32_t stage_bytes = 2 * a_bytes + 2 * w_bytes;
+  const uint32_t w_bytes = (uint32_t)P.w_atoms * watom_bytes;  // one plane (cat: both planes, one tile)
+  const uint32_t stage_bytes = 2 * a_bytes + (P.cat ? 1u : 2u) * w_bytes;
+  const uint32_t NW = P.cat ? 2u * P.NP : (uint32_t)P.NP;      // accumulator width in TMEM columns
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)P.stages * stage_bytes);
   uint64_t* full_b = bars;
   uint64_t* empty_b = bars + P.stages;
@@ -267,7 +293,7 @@ k_grad_E_tc(const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ 
   }
   const int nmb = P.fgs / 128;
   uint32_t tcols = 32;
-  while (tcols < (uint32_t)(nmb * P.NP)) tcols <<= 1;
+  while (tcols < (uint32_t)nmb * NW) tcols <<= 1;
   if (warp == 4) tmem_alloc(tmem_slot, tcols);
   tc_fence_before();
   __syncthreads();
@@ -334,7 +360,10 @@ k_grad_E_tc(const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ 
       pt_cp_arrive(&full_b[stage]);
       if (tid == 0) {
         uint8_t* sW_hi = smem + (size_t)stage * stage_bytes + 2 * a_bytes;
-        mbar_expect_tx(&full_b[stage], 2 * w_bytes);
+        mbar_expect_tx(&full_b[stage], (P.cat ? 1u : 2u) * w_bytes);
+        if (P.cat) {
+          tma_load_2d(sW_hi, &tmW_hi, &full_b[stage], 0, (int)r0);   // [32 rows x 128 B]: hi | lo of every row
+        } else
         for (int a = 0; a < P.w_atoms; ++a) {
           tma_load_2d(sW_hi + (size_t)a * watom_bytes, &tmW_hi, &full_b[stage], a * 64, (int)r0);
           tma_load_2d(sW_hi + w_bytes + (size_t)a * watom_bytes, &tmW_lo, &full_b[stage], a * 64, (int)r0);
@@ -345,7 +374,7 @@ k_grad_E_tc(const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ 
   } else if (warp == 4) {
     // ===== UMMA issuer: D[mb][128 features x NP] += F^T[128 x 16 rows] * W[16 rows x NP] =====
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(128, P.NP, 1, 1);
+      const uint32_t idesc = umma_idesc_bf16(128, (int)NW, 1, 1);
       const uint32_t w_sbo = 8u * wrow_bytes;
       uint32_t stage = 0, phase = 0;
       for (int t = 0; t < n_tiles; ++t) {
@@ -355,6 +384,20 @@ k_grad_E_tc(const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ 
         const uint32_t a_hi = tc_smem_u32(smem + (size_t)stage * stage_bytes);
         const uint32_t a_lo = a_hi + a_bytes, w_hi = a_lo + a_bytes, w_lo = w_hi + w_bytes;
         // (K step, pass)-major, M-block-minor: consecutive UMMAs target different accumulators
+        if (P.cat) {
+#pragma unroll
+          for (int k = 0; k < GE_RT / 16; ++k) {
+#pragma unroll
+            for (int pass = 0; pass < 2; ++pass) {
+              const uint64_t dw = umma_smem_desc(w_hi + k * 16 * wrow_bytes, watom_bytes, w_sbo, TC_SWZ_128B);
+              for (int mb = 0; mb < nmb; ++mb) {
+                const uint32_t aoff = (uint32_t)(2 * mb) * chunk_bytes + k * 16 * 128;
+                const uint64_t da = umma_smem_desc((pass == 1 ? a_lo : a_hi) + aoff, chunk_bytes, 1024, TC_SWZ_128B);
+                umma_f16(tmem_base + mb * NW, da, dw, idesc, (t | k | pass) ? 1u : 0u);
+              }
+            }
+          }
+        } else
 #pragma unroll
         for (int k = 0; k < GE_RT / 16; ++k) {
 #pragma unroll
@@ -386,8 +429,15 @@ k_grad_E_tc(const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ 
       for (int n0 = 0; n0 < P.NP; n0 += 32) {
         uint32_t v[32];
         if (n_tiles > 0) {
-          tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + mb * P.NP + n0, v);
+          tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + mb * NW + n0, v);
           tmem_ld_wait();
+          if (P.cat) {                      // columns [NP, 2NP): the products with W_lo
+            uint32_t v2[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + mb * NW + P.NP + n0, v2);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+          }
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = 0u;
@@ -485,7 +535,11 @@ int fvx_launch_project_tc(const FvxModel* m, const int32_t* rows, int row0, int6
   P.rows = rows; P.row0 = row0; P.nrows = nrows; P.nrows_dev = nrows_dev; P.NP = NP; P.ksplit = ksplit; P.chunks = chunks_total / ksplit;
   P.n_tiles = (int)((nrows + PT_BM - 1) / PT_BM);
   P.out = out;
-  P.nacc = 256 / NP < 4 ? (256 / NP < 1 ? 1 : 256 / NP) : 4;
+  P.cat = NP <= 64 ? 1 : 0;                       // N = 2*NP <= 128 and 2 buffers x nacc x 2*NP <= 512 columns
+  {
+    const int nw = P.cat ? 2 * NP : NP;
+    P.nacc = 256 / nw < 4 ? (256 / nw < 1 ? 1 : 256 / nw) : 4;
+  }
   const size_t stage_bytes = 2 * PT_BM * 128 + 2 * (size_t)NP * 128;
   int stages = (int)((220 * 1024) / stage_bytes);
   if (stages > 6) stages = 6;
@@ -525,19 +579,28 @@ int fvx_launch_grad_E_tc(const FvxModel* m, const int32_t* rows, int64_t nrows, 
   if (parts == 0) return 0;
   CUtensorMap w_hi, w_lo;
   int rc = 0;
+  const int wpitch = fvx_w_pitch(m);
+  const int cat = (NP == 32 && wpitch == 2 * NP) ? 1 : 0;
   const int wbox = NP <= 64 ? NP : 64;
   const int wsw = NP == 32 ? 2 : 3;
-  rc |= tc_make_tensor_map_bf16(&w_hi, m->W_hi, nrows, NP, (uint64_t)NP * 2, wbox, GE_RT, wsw);
-  rc |= tc_make_tensor_map_bf16(&w_lo, m->W_lo, nrows, NP, (uint64_t)NP * 2, wbox, GE_RT, wsw);
+  if (cat) {
+    // one map over the interleaved rows [nrows, hi 32 | lo 32]: 128-byte rows, 128B swizzle
+    rc |= tc_make_tensor_map_bf16(&w_hi, m->W_hi, nrows, 2 * NP, (uint64_t)wpitch * 2, 2 * NP, GE_RT, 3);
+    w_lo = w_hi;
+  } else {
+    rc |= tc_make_tensor_map_bf16(&w_hi, m->W_hi, nrows, NP, (uint64_t)wpitch * 2, wbox, GE_RT, wsw);
+    rc |= tc_make_tensor_map_bf16(&w_lo, m->W_lo, nrows, NP, (uint64_t)wpitch * 2, wbox, GE_RT, wsw);
+  }
   if (rc != 0) FVX_FAIL(-4, "tensor-core grad_E: cuTensorMapEncodeTiled failed");
   GradEParams P;
   P.Fpl = reinterpret_cast<const uint8_t*>(m->F_pl);
   P.rows = rows; P.nrows = nrows; P.nrows_dev = nrows_dev; P.n_groups = parts; P.D = m->D; P.NP = NP; P.fgs = fgs; P.nfg = nfg; P.rows_per_group = (int)rpg;
   P.w_atoms = NP <= 64 ? 1 : NP / 64;
   P.w_sw = NP == 32 ? TC_SWZ_64B : TC_SWZ_128B;
+  P.cat = cat;
   P.out = m->gE_part;
-  const size_t wrow = NP <= 64 ? (size_t)NP * 2 : 128;
-  const size_t stage_bytes = 2 * (size_t)(fgs / PT_KC) * GE_RT * 128 + 2 * (size_t)P.w_atoms * GE_RT * wrow;
+  const size_t wrow = cat ? 128 : (NP <= 64 ? (size_t)NP * 2 : 128);
+  const size_t stage_bytes = 2 * (size_t)(fgs / PT_KC) * GE_RT * 128 + (cat ? 1 : 2) * (size_t)P.w_atoms * GE_RT * wrow;
   int stages = (int)((220 * 1024) / stage_bytes);
   if (stages > 4) stages = 4;
   FVX_CHECK_ARG(stages >= 2, "tensor-core grad_E: tile does not fit shared memory");
@@ -579,7 +642,7 @@ int fvx_launch_reduce_partials(const float* part, long long nrows, int NP, int k
 
 // W fp32 [nrows, de] -> bf16 planes [nrows, NP] (rows with rows[r] < 0 and columns >= de: zero)
 __global__ void k_split_W(const float* __restrict__ W, const int32_t* __restrict__ rows, long long nrows, int de,
-                          int NP, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+                          int NP, int pitch, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
   const long long total = nrows * NP;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -588,8 +651,8 @@ __global__ void k_split_W(const float* __restrict__ W, const int32_t* __restrict
     float x = 0.0f;
     if (c < de && (rows == nullptr || rows[r] >= 0)) x = W[r * de + c];
     const __nv_bfloat16 h = __float2bfloat16_rn(x);
-    hi[i] = h;
-    lo[i] = __float2bfloat16_rn(x - __bfloat162float(h));
+    hi[r * pitch + c] = h;
+    lo[r * pitch + c] = __float2bfloat16_rn(x - __bfloat162float(h));
   }
 }
 
@@ -598,7 +661,7 @@ int fvx_launch_split_W(const FvxModel* m, const float* W, const int32_t* rows, l
   const int NP = fvx_tc_np(m->de);
   long long g = (nrows * NP + 255) / 256;
   if (g > (long long)fvx_num_sms() * 8) g = (long long)fvx_num_sms() * 8;
-  k_split_W<<<(int)g, 256, 0, st>>>(W, rows, nrows, m->de, NP, reinterpret_cast<__nv_bfloat16*>(m->W_hi),
+  k_split_W<<<(int)g, 256, 0, st>>>(W, rows, nrows, m->de, NP, fvx_w_pitch(m), reinterpret_cast<__nv_bfloat16*>(m->W_hi),
                                     reinterpret_cast<__nv_bfloat16*>(m->W_lo));
   FVX_CHECK_LAUNCH("k_split_W");
   return 0;

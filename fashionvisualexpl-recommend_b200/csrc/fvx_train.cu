@@ -206,7 +206,7 @@ struct SgTheta {
 
 template <int MAXV>
 __global__ void __launch_bounds__(SG_WARPS * 32)
-k_score_grad(FvxModel M, const int32_t* __restrict__ user, int B, int loss_slot, SgTheta T, int wnp) {
+k_score_grad(FvxModel M, const int32_t* __restrict__ user, int B, int loss_slot, SgTheta T, int wnp, int wpitch) {
   __shared__ double loss_sh[SG_WARPS];
   const int Su = M.users.stride, Si = M.items.stride, K = M.K, d = M.d, de = M.de;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -228,8 +228,8 @@ k_score_grad(FvxModel M, const int32_t* __restrict__ user, int B, int loss_slot,
         for (int n = lane; n < nw_; n += 32) {
           if (wnp > 0) {
             const __nv_bfloat16 z = __float2bfloat16_rn(0.0f);
-            wh[(size_t)b * wnp + n] = z; wl[(size_t)b * wnp + n] = z;
-            wh[(size_t)(B + b) * wnp + n] = z; wl[(size_t)(B + b) * wnp + n] = z;
+            wh[(size_t)b * wpitch + n] = z; wl[(size_t)b * wpitch + n] = z;
+            wh[(size_t)(B + b) * wpitch + n] = z; wl[(size_t)(B + b) * wpitch + n] = z;
           } else {
             M.W[(size_t)b * de + n] = 0.0f; M.W[(size_t)(B + b) * de + n] = 0.0f;
           }
@@ -296,10 +296,10 @@ k_score_grad(FvxModel M, const int32_t* __restrict__ user, int B, int loss_slot,
           if (wnp > 0) {   // bf16 hi/lo planes for the tensor-core backward
             const __nv_bfloat16 h = __float2bfloat16_rn(wv);
             const __nv_bfloat16 l = __float2bfloat16_rn(wv - __bfloat162float(h));
-            wh[(size_t)b * wnp + n] = h;
-            wl[(size_t)b * wnp + n] = l;
-            wh[(size_t)(B + b) * wnp + n] = __hneg(h);
-            wl[(size_t)(B + b) * wnp + n] = __hneg(l);
+            wh[(size_t)b * wpitch + n] = h;
+            wl[(size_t)b * wpitch + n] = l;
+            wh[(size_t)(B + b) * wpitch + n] = __hneg(h);
+            wl[(size_t)(B + b) * wpitch + n] = __hneg(l);
           } else {
             M.W[(size_t)b * de + n] = wv;
             M.W[(size_t)(B + b) * de + n] = -wv;
@@ -356,7 +356,7 @@ __device__ __forceinline__ float half_sum(float v) {
 
 template <int MQ, int MD>
 __global__ void __launch_bounds__(SG_WARPS * 32, 4)
-k_score_grad_v4(FvxModel M, const int32_t* __restrict__ user, int B, int loss_slot, SgTheta T, int wnp) {
+k_score_grad_v4(FvxModel M, const int32_t* __restrict__ user, int B, int loss_slot, SgTheta T, int wnp, int wpitch) {
   __shared__ double loss_sh[SG_WARPS * 2];
   const int Su = M.users.stride, Si = M.items.stride, K = M.K, d = M.d, de = M.de;
   const int K4 = K >> 2, D4 = (d + 3) >> 2;
@@ -484,10 +484,11 @@ k_score_grad_v4(FvxModel M, const int32_t* __restrict__ user, int B, int loss_sl
             const uint2 l = pack_bf16x4(make_float4(wv.x - hf.x, wv.y - hf.y, wv.z - hf.z, wv.w - hf.w));
             uint2* wh = reinterpret_cast<uint2*>(M.W_hi);
             uint2* wl = reinterpret_cast<uint2*>(M.W_lo);
-            wh[(size_t)b * nw4 + c] = h;
-            wl[(size_t)b * nw4 + c] = l;
-            wh[(size_t)(B + b) * nw4 + c] = make_uint2(h.x ^ 0x80008000u, h.y ^ 0x80008000u);   // negation
-            wl[(size_t)(B + b) * nw4 + c] = make_uint2(l.x ^ 0x80008000u, l.y ^ 0x80008000u);
+            const size_t wp4 = (size_t)(wpitch >> 2);
+            wh[(size_t)b * wp4 + c] = h;
+            wl[(size_t)b * wp4 + c] = l;
+            wh[(size_t)(B + b) * wp4 + c] = make_uint2(h.x ^ 0x80008000u, h.y ^ 0x80008000u);   // negation
+            wl[(size_t)(B + b) * wp4 + c] = make_uint2(l.x ^ 0x80008000u, l.y ^ 0x80008000u);
           } else {
             reinterpret_cast<float4*>(M.W)[(size_t)b * nw4 + c] = wv;
             reinterpret_cast<float4*>(M.W)[(size_t)(B + b) * nw4 + c] = make_float4(-wv.x, -wv.y, -wv.z, -wv.w);
@@ -652,6 +653,7 @@ int fvx_launch_score_grad(const FvxModel* m, const int32_t* user, int B, int los
   T.ks = tc ? th_ks : 1;
   T.ss = 2LL * B * T.np;
   const int wnp = tc ? T.np : 0;
+  const int wpitch = tc ? fvx_w_pitch(m) : 0;
   const int need = (m->K > m->d + 1 ? m->K : m->d + 1);
   FVX_CHECK_ARG(need <= 256 && (wnp == 0 || wnp <= 256), "fvx_bpr_step: K=%d / d=%d too large for the score kernel",
                 m->K, m->d);
@@ -660,15 +662,15 @@ int fvx_launch_score_grad(const FvxModel* m, const int32_t* user, int B, int los
     // vector path: a lane owns 4 columns, 16 lanes per triple
     const long long g2 = (g + 1) / 2 > 0 ? (g + 1) / 2 : 1;
     if (m->K <= 64 && wcols <= 64)
-      k_score_grad_v4<1, 1><<<(int)g2, SG_WARPS * 32, 0, st>>>(*m, user, B, loss_slot, T, wnp);
+      k_score_grad_v4<1, 1><<<(int)g2, SG_WARPS * 32, 0, st>>>(*m, user, B, loss_slot, T, wnp, wpitch);
     else if (m->K <= 128 && wcols <= 128)
-      k_score_grad_v4<2, 2><<<(int)g2, SG_WARPS * 32, 0, st>>>(*m, user, B, loss_slot, T, wnp);
+      k_score_grad_v4<2, 2><<<(int)g2, SG_WARPS * 32, 0, st>>>(*m, user, B, loss_slot, T, wnp, wpitch);
     else
-      k_score_grad_v4<4, 4><<<(int)g2, SG_WARPS * 32, 0, st>>>(*m, user, B, loss_slot, T, wnp);
+      k_score_grad_v4<4, 4><<<(int)g2, SG_WARPS * 32, 0, st>>>(*m, user, B, loss_slot, T, wnp, wpitch);
   } else if (need <= 64 && wnp <= 64) {
-    k_score_grad<2><<<(int)g, SG_WARPS * 32, 0, st>>>(*m, user, B, loss_slot, T, wnp);
+    k_score_grad<2><<<(int)g, SG_WARPS * 32, 0, st>>>(*m, user, B, loss_slot, T, wnp, wpitch);
   } else {
-    k_score_grad<8><<<(int)g, SG_WARPS * 32, 0, st>>>(*m, user, B, loss_slot, T, wnp);
+    k_score_grad<8><<<(int)g, SG_WARPS * 32, 0, st>>>(*m, user, B, loss_slot, T, wnp, wpitch);
   }
   FVX_CHECK_LAUNCH("k_score_grad");
   return 0;

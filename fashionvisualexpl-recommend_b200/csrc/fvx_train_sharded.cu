@@ -98,7 +98,7 @@ k_partial_scores(FvxModel M, const int32_t* __restrict__ user, int B, SsTheta T,
 
 // phase B: one warp per triple; each side only if its item is owned
 __global__ void __launch_bounds__(SS_WARPS * 32)
-k_grads_sharded(FvxModel M, const int32_t* __restrict__ user, int B, int loss_slot, SsTheta T, int wnp,
+k_grads_sharded(FvxModel M, const int32_t* __restrict__ user, int B, int loss_slot, SsTheta T, int wnp, int wpitch,
                 const float* __restrict__ S, const int32_t* __restrict__ run_id, float* __restrict__ RU,
                 long long ru_rows) {
   __shared__ double loss_sh[SS_WARPS];
@@ -156,8 +156,8 @@ k_grads_sharded(FvxModel M, const int32_t* __restrict__ user, int B, int loss_sl
           }
           if (wnp > 0) {
             const __nv_bfloat16 h = __float2bfloat16_rn(wv);
-            wh[j * wnp + n] = h;
-            wl[j * wnp + n] = __float2bfloat16_rn(wv - __bfloat162float(h));
+            wh[j * wpitch + n] = h;
+            wl[j * wpitch + n] = __float2bfloat16_rn(wv - __bfloat162float(h));
           } else {
             M.W[j * de + n] = wv;
           }
@@ -260,8 +260,12 @@ int fvx_bpr_step_sharded_a(const FvxModel* model, const int32_t* user, const int
     if (M.use_tensor_cores) {
       FVX_CHECK_ARG((long long)ks * 2 * B * fvx_tc_np(M.de) <= M.th_cap, "fvx_bpr_step_sharded_a: TH scratch too small");
       // W rows past the owned ones must read as zero in the last backward tile
-      cudaMemsetAsync(M.W_hi, 0, sizeof(uint16_t) * 2 * (size_t)B * fvx_tc_np(M.de), st);
-      cudaMemsetAsync(M.W_lo, 0, sizeof(uint16_t) * 2 * (size_t)B * fvx_tc_np(M.de), st);
+      if (fvx_w_pitch(&M) == 2 * fvx_tc_np(M.de)) {   // interleaved planes: one allocation
+        cudaMemsetAsync(M.W_hi, 0, sizeof(uint16_t) * 2 * (size_t)B * fvx_w_pitch(&M), st);
+      } else {
+        cudaMemsetAsync(M.W_hi, 0, sizeof(uint16_t) * 2 * (size_t)B * fvx_tc_np(M.de), st);
+        cudaMemsetAsync(M.W_lo, 0, sizeof(uint16_t) * 2 * (size_t)B * fvx_tc_np(M.de), st);
+      }
       if (int rc = fvx_launch_project_tc(&M, M.cmap, 0, 2 * B, ks, M.TH, st, count)) return rc;
     } else {
       FVX_CHECK_ARG(2LL * B * M.de <= M.th_cap, "fvx_bpr_step_sharded_a: TH scratch too small");
@@ -287,7 +291,8 @@ int fvx_bpr_step_sharded_b(const FvxModel* model, const int32_t* user, int32_t B
   const int ks = sharded_ks(&M, B);
   const bool tc = M.D > 0 && M.use_tensor_cores;
   k_grads_sharded<<<ss_grid(B), SS_WARPS * 32, 0, st>>>(M, user, B, loss_slot, make_theta(&M, B, ks),
-                                                        tc ? fvx_tc_np(M.de) : 0, S, run_id, RU, (long long)ru_rows);
+                                                        tc ? fvx_tc_np(M.de) : 0, tc ? fvx_w_pitch(&M) : 0, S, run_id, RU,
+                                                        (long long)ru_rows);
   FVX_CHECK_LAUNCH("k_grads_sharded");
   if (M.D > 0) {
     int parts = 0;

@@ -83,8 +83,11 @@ class Engine:
                 u16 = dict(dtype=torch.uint16, device=dev)
                 self.ET_hi = torch.zeros(self.NP, self.D, **u16)
                 self.ET_lo = torch.zeros(self.NP, self.D, **u16)
-                self.W_hi = torch.zeros(2 * self.max_batch, self.NP, **u16)
-                self.W_lo = torch.zeros(2 * self.max_batch, self.NP, **u16)
+                # backward coefficients: the two bf16 planes interleaved row by row, [hi NP | lo NP]
+                # (W_lo = W_hi + NP elements): the backward reads a row pair as one N = 2*NP operand
+                self.W_il = torch.zeros(2 * self.max_batch, 2 * self.NP, **u16)
+                self.W_hi = self.W_il
+                self.W_lo = self.W_il.view(-1)[self.NP:]
                 self.ge_parts = max(self.ge_parts, 148)
                 th_rows = max(4 * 2 * self.max_batch, 1 << 17)
                 self.TH = torch.zeros(th_rows, self.NP, **f32)

@@ -85,8 +85,8 @@ typedef struct FvxModel {
                            bf16(F - hi); 4*D bytes per row (fvx_split_planes)       */
   uint16_t* ET_hi;      /* [NP, D] bf16 planes of E_ext^T (NP = fvx_tc_width(de)),  */
   uint16_t* ET_lo;      /*   scratch refreshed by every call that projects          */
-  uint16_t* W_hi;       /* [2*max_batch, NP] bf16 planes of the backward            */
-  uint16_t* W_lo;       /*   coefficients (tensor-core path)                        */
+  uint16_t* W_hi;       /* [2*max_batch, NP] bf16 planes of the backward coefficients (tensor-core path), row pitch NP; or */
+  uint16_t* W_lo;       /* interleaved: W_lo == W_hi + NP, row pitch 2*NP ([hi NP | lo NP] per row) - the faster layout */
   int64_t* step;        /* [1] number of optimiser steps applied so far             */
   double* loss;         /* [loss_slots] per-step loss accumulators                  */
   int32_t loss_slots;
