@@ -44,7 +44,7 @@ int fvx_check_model(const FvxModel* m, const char* who);
 // (slot rows + E planes); CLAIMS = claims + deferred-Adam catch-up without the row / plane writes
 enum { FVX_PREP_ALL = 0, FVX_PREP_ROWS = 1, FVX_PREP_CLAIMS = 2 };
 int fvx_launch_prep(const FvxModel* m, const int32_t* user, const int32_t* pos, const int32_t* neg, int B,
-                    cudaStream_t st, int what = FVX_PREP_ALL);
+                    cudaStream_t st, int what = FVX_PREP_ALL, int H0 = 0);   // H0: k_rows_et half split (0: none)
 // what: ALL = tables + E_ext + finalisation; TABLES = touched rows only; E = E_ext + finalisation
 enum { FVX_UPD_ALL = 0, FVX_UPD_TABLES = 1, FVX_UPD_E = 2 };
 int fvx_launch_update(const FvxModel* m, int B, int parts, int gnp, const float* gE_src, int loss_slot,

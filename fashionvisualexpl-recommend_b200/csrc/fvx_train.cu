@@ -99,18 +99,29 @@ __device__ __forceinline__ void split_E_planes(const FvxModel& M, int NP, int bl
 // What the projection needs from the batch, and nothing else: the local item row of every
 // (triple, side) slot and the planes of E_ext^T.  Launched on the main stream while k_prep (claims +
 // deferred-Adam catch-up) runs beside the projection on the side stream.
+// Slot layout: [pos(H0) | neg(H0)] of the first H0 triples, then [pos(B-H0) | neg(B-H0)] of the rest
+// (H0 = B: the plain [pos(B) | neg(B)] layout).  With H0 = B/2 each half of the batch is a
+// self-contained [pos | neg] block, so the two halves can flow through projection -> scoring ->
+// grad_E as separate launches that overlap each other.
 __global__ void __launch_bounds__(256)
-k_rows_et(FvxModel M, const int32_t* __restrict__ pos, const int32_t* __restrict__ neg, int B, int nb_rows, int NP) {
+k_rows_et(FvxModel M, const int32_t* __restrict__ pos, const int32_t* __restrict__ neg, int B, int H0, int nb_rows,
+          int NP) {
   if ((int)blockIdx.x >= nb_rows) {
     split_E_planes(M, NP, blockIdx.x - nb_rows, gridDim.x - nb_rows);
     return;
   }
+  const int H1 = B - H0;
   for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += nb_rows * blockDim.x) {
     int32_t li = pos[b] - M.item_lo, lj = neg[b] - M.item_lo;
     if (li < 0 || li >= M.item_cnt) li = -1;
     if (lj < 0 || lj >= M.item_cnt) lj = -1;
-    M.rows[b] = li;
-    M.rows[B + b] = lj;
+    if (b < H0) {
+      M.rows[b] = li;
+      M.rows[H0 + b] = lj;
+    } else {
+      M.rows[2 * H0 + (b - H0)] = li;
+      M.rows[2 * H0 + H1 + (b - H0)] = lj;
+    }
   }
 }
 
@@ -370,10 +381,18 @@ k_score_grad_v4(FvxModel M, const int32_t* __restrict__ user, int B, int loss_sl
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
   const long long Bpad = ((long long)B + 1) & ~1LL;       // both halves of a warp walk the loop together
 
+  // the indices of the NEXT triple are loaded while this one is processed: one level less in the
+  // dependent load chain (index -> rows -> reductions) that bounds the kernel
+  int32_t u_n = -1, li_n = -1, lj_n = -1;
+  if (gg0 < B) { u_n = __ldg(user + gg0); li_n = __ldg(M.rows + gg0); lj_n = __ldg(M.rows + B + gg0); }
   for (long long b = gg0; b < Bpad; b += ng) {
     const bool live = b < B;
-    const int32_t u = live ? user[b] : -1;
-    const int32_t li = live ? M.rows[b] : -1, lj = live ? M.rows[B + b] : -1;
+    const int32_t u = u_n, li = li_n, lj = lj_n;
+    {
+      const long long bn = b + ng;
+      u_n = li_n = lj_n = -1;
+      if (bn < B) { u_n = __ldg(user + bn); li_n = __ldg(M.rows + bn); lj_n = __ldg(M.rows + B + bn); }
+    }
     const bool dead = li < 0 || lj < 0 || u < 0 || u >= M.num_users;   // id outside the catalog: triple ignored
     float coef = 0.0f;
     float4 tu[MD];
@@ -677,14 +696,14 @@ int fvx_launch_score_grad(const FvxModel* m, const int32_t* user, int B, int los
 }
 
 int fvx_launch_prep(const FvxModel* m, const int32_t* user, const int32_t* pos, const int32_t* neg, int B,
-                    cudaStream_t st, int what) {
+                    cudaStream_t st, int what, int H0) {
   const bool tc = m->D > 0 && m->use_tensor_cores;
   const int NP = tc ? fvx_tc_np(m->de) : m->de;
   const int nb_e = tc ? 32 : 0;
   if (what == FVX_PREP_ROWS) {
     int nb_rows = (B + 255) / 256;
     if (nb_rows > fvx_num_sms() * 4) nb_rows = fvx_num_sms() * 4;
-    k_rows_et<<<nb_rows + nb_e, 256, 0, st>>>(*m, pos, neg, B, nb_rows, NP);
+    k_rows_et<<<nb_rows + nb_e, 256, 0, st>>>(*m, pos, neg, B, (H0 > 0 && H0 < B) ? H0 : B, nb_rows, NP);
     FVX_CHECK_LAUNCH("k_rows_et");
     return 0;
   }
@@ -721,11 +740,21 @@ int fvx_launch_update(const FvxModel* m, int B, int parts, int gnp, const float*
 
 int fvx_check_model(const FvxModel* m, const char* who) { return check_model(m, who); }
 
+// Two-half pipelined schedule: OFF by default (measured 425 us vs 408 us per step at B = 65536: the
+// 128-register projection CTA leaves room for one 256-thread block per SM, so the scoring kernel
+// crawls beside it and grad_E of the second half waits).  Tests enable it through the hook below.
+static int g_pipe_min_batch = 0x7fffffff;
+extern "C" int fvx_debug_set_pipe_min_batch(int b) {   // test hook, not part of fvx.h
+  const int old = g_pipe_min_batch;
+  if (b >= 2) g_pipe_min_batch = b;
+  return old;
+}
+
 // Side stream of the two-stream step schedule: one per device, created on first use.
 // FVX_STEP_OVERLAP=0 keeps every kernel of the step on the caller's stream.
 struct SideStream {
   cudaStream_t s;
-  cudaEvent_t fork, prep_done, score_done, upd_done;
+  cudaEvent_t fork, prep_done, score_done, upd_done, fwd_done[2], sc_done[2];
 };
 static SideStream* side_stream() {
   static SideStream pool[16];
@@ -745,6 +774,10 @@ static SideStream* side_stream() {
     ok = ok && cudaEventCreateWithFlags(&p.prep_done, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&p.score_done, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&p.upd_done, cudaEventDisableTiming) == cudaSuccess;
+    for (int h = 0; h < 2; ++h) {
+      ok = ok && cudaEventCreateWithFlags(&p.fwd_done[h], cudaEventDisableTiming) == cudaSuccess;
+      ok = ok && cudaEventCreateWithFlags(&p.sc_done[h], cudaEventDisableTiming) == cudaSuccess;
+    }
     if (!ok) cudaGetLastError();
     state[dev] = ok ? 1 : -1;
   }
@@ -789,6 +822,58 @@ static int bpr_step_impl(const FvxModel* model, const int32_t* user, const int32
   // kernels are bandwidth-bound, so the overlap is nearly free.  The timed entry point keeps
   // everything on one stream so that each phase is measured alone.
   SideStream* side = (vis && !ev && !fused) ? side_stream() : nullptr;
+  if (side && tc && B >= g_pipe_min_batch) {
+    // Two half-batches in flight: the main stream runs fwd(h0) fwd(h1) grad_E(h0) grad_E(h1) back
+    // to back (the bandwidth-bound kernels); the side stream runs claims/catch-up, score(h0),
+    // score(h1) and the row update beside them (the latency-bound ones).  Each half is a
+    // self-contained [pos | neg] slot block (k_rows_et), so the existing kernels run on it unchanged
+    // through a copy of the model whose scratch pointers are offset.
+    const int H[2] = {B / 2, B - B / 2};
+    const int pitch = fvx_w_pitch(&M);
+    FvxModel Mh[2];
+    int ks[2];
+    long long th_off = 0;
+    for (int h = 0; h < 2; ++h) {
+      const long long slot0 = h ? 2LL * H[0] : 0;
+      ks[h] = fvx_tc_ksplit(&M, 2LL * H[h]);
+      while (ks[h] > 1 && th_off + (long long)ks[h] * 2 * H[h] * NP > M.th_cap) ks[h] >>= 1;
+      FVX_CHECK_ARG(th_off + (long long)ks[h] * 2 * H[h] * NP <= M.th_cap, "fvx_bpr_step: TH scratch too small");
+      Mh[h] = M;
+      Mh[h].rows = M.rows + slot0;
+      Mh[h].W_hi = M.W_hi + slot0 * pitch;
+      Mh[h].W_lo = M.W_lo + slot0 * pitch;
+      Mh[h].TH = M.TH + th_off;
+      Mh[h].th_cap = M.th_cap - th_off;
+      th_off += (long long)ks[h] * 2 * H[h] * NP;
+    }
+    if (int rc = fvx_launch_prep(&M, user, pos, neg, B, st, FVX_PREP_ROWS, H[0])) return rc;
+    cudaEventRecord(side->fork, st);
+    cudaStreamWaitEvent(side->s, side->fork, 0);
+    if (int rc = fvx_launch_prep(&M, user, pos, neg, B, side->s, FVX_PREP_CLAIMS)) return rc;
+    for (int h = 0; h < 2; ++h) {
+      if (int rc = fvx_launch_project_tc(&Mh[h], Mh[h].rows, 0, 2 * H[h], ks[h], Mh[h].TH, st)) return rc;
+      cudaEventRecord(side->fwd_done[h], st);
+    }
+    for (int h = 0; h < 2; ++h) {
+      cudaStreamWaitEvent(side->s, side->fwd_done[h], 0);
+      if (int rc = fvx_launch_score_grad(&Mh[h], user + (h ? H[0] : 0), H[h], loss_slot, ks[h], side->s)) return rc;
+      cudaEventRecord(side->sc_done[h], side->s);
+    }
+    if (int rc = fvx_launch_update(&M, B, 0, NP, M.gE_part, loss_slot, side->s, FVX_UPD_TABLES)) return rc;
+    cudaEventRecord(side->upd_done, side->s);
+    int parts_total = 0;
+    for (int h = 0; h < 2; ++h) {
+      Mh[h].gE_part = M.gE_part + (size_t)parts_total * M.D * NP;
+      Mh[h].ge_parts = M.ge_parts - parts_total;
+      int parts_h = 0;
+      cudaStreamWaitEvent(st, side->sc_done[h], 0);
+      if (int rc = fvx_launch_grad_E_tc(&Mh[h], Mh[h].rows, 2 * H[h], &parts_h, st)) return rc;
+      parts_total += parts_h;
+    }
+    cudaStreamWaitEvent(st, side->upd_done, 0);      // join: the step is complete on `st`
+    if (int rc = fvx_launch_update(&M, B, parts_total, NP, M.gE_part, loss_slot, st, FVX_UPD_E)) return rc;
+    return 0;
+  }
   if (side) {
     if (int rc = fvx_launch_prep(&M, user, pos, neg, B, st, FVX_PREP_ROWS)) return rc;
     cudaEventRecord(side->fork, st);

@@ -154,3 +154,41 @@ def test_fused_step_equals_two_kernel_path(tile, monkeypatch):
         # sits at rounding noise into an O(lr) move, so a handful of elements may differ more
         dlt = np.abs(Qb[k] - Qa[k]) / np.abs(Qa[k]).max()
         assert dlt.max() <= 5e-3 and (dlt > 2e-5).mean() <= 1e-3, (k, dlt.max(), (dlt > 2e-5).mean())
+
+
+@pytest.mark.parametrize("K,d,D,B", [(64, 20, 2048, 1000), (32, 20, 256, 513), (16, 40, 512, 300)])
+def test_two_half_pipelined_schedule_matches_oracle(K, d, D, B):
+    """fvx_bpr_step's large-batch schedule (two half-batches on two streams)
+    forced at a small batch: losses and parameters against the fp64 oracle, and against the
+    single-stream timed entry point on a twin engine (same kernels, plain slot layout)."""
+    from fvx import _lib
+    lib = _lib.load()
+    old = lib.fvx_debug_set_pipe_min_batch(64)
+    try:
+        U, I, steps, lr, reg = 700, 900, 12, 0.001, 1e-3
+        P, F, rng = _random_problem(U, I, K, d, D, seed=K + d + 1)
+        es = []
+        for _ in range(2):
+            e = _engine(U, I, K, d=d, D=D, lr=lr, reg=reg, max_batch=B, use_tensor_cores=True)
+            e.set_features(F, keep_fp32=False)
+            e.load_params(P)
+            es.append(e)
+        batches = _user_contiguous_batches(rng, U, I, B, steps)
+        P32, P64, l32, l64 = _oracle_pair(P, F, batches, reg, lr)
+        for s, b in enumerate(batches):
+            db = [_dev(x) for x in b]
+            es[0].step(*db, loss_slot=0)
+            es[1].step_timed(*db, loss_slot=0)
+            la, lb = es[0].read_loss(0), es[1].read_loss(0)
+            assert la == pytest.approx(l64[s], rel=REL), s
+            assert la == pytest.approx(lb, rel=2e-6), s
+        Qa, Qb = es[0].params(), es[1].params()
+        Pp = _perturbed_oracle(P, F, batches, reg, lr)
+        for k in P64:
+            ref = P64[k]
+            dlt = np.abs(Qa[k].reshape(ref.shape) - ref) / np.abs(ref).max()
+            assert dlt.max() <= max(REL, 3 * rel_err(P32[k], ref), rel_err(Pp[k], ref)), (k, dlt.max())
+            d2 = np.abs(Qa[k] - Qb[k]) / np.abs(Qb[k]).max()
+            assert d2.max() <= 5e-3 and (d2 > 2e-5).mean() <= 1e-3, (k, d2.max())
+    finally:
+        lib.fvx_debug_set_pipe_min_batch(old)
