@@ -261,8 +261,14 @@ def run_fvx(args):
         F = make_features_device(args.items, D, dev)          # same generator seed on every rank
         e.set_features(F[lo:lo + cnt].contiguous(), keep_fp32=not args.tensor_cores)
         del F
-    min_len = int(np.diff(inter.row_ptr).min())
-    sharded = parallel.ShardedStep([e], parallel.DistGroup(), max_runs=B // max(min_len, 1) + 2) if world > 1 else None
+    # rows of the all-reduced user-gradient buffer: runs of equal users in a batch.  The hard bound is
+    # B / (shortest train list); the batches hold B / (mean list) runs with a relative spread of a few
+    # per mille at this size, so 1.3 x the mean + 1024 is used (an overflow is detected on the device and
+    # raised by read_loss - it cannot pass silently)
+    lens = np.diff(inter.row_ptr)
+    min_len, mean_len = int(lens.min()), float(lens.mean())
+    max_runs = min(B // max(min_len, 1) + 2, int(1.3 * B / mean_len) + 1024)
+    sharded = parallel.ShardedStep([e], parallel.DistGroup(), max_runs=max_runs) if world > 1 else None
     batches = data.next_triple_batch(str(dev))
 
     def do_step(b, slot=0):

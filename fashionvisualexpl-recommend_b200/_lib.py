@@ -60,6 +60,8 @@ PROTOTYPES = {
     "fvx_bpr_step_timed": (C.c_int, [_MP, _p, _p, _p, _i32, _i32, C.POINTER(C.c_float), _p]),
     "fvx_bpr_step_sharded_a": (C.c_int, [_MP, _p, _p, _p, _i32, _p, _p]),
     "fvx_bpr_step_sharded_b": (C.c_int, [_MP, _p, _i32, _p, _p, _p, _i64, _p, _i32, _p]),
+    "fvx_bpr_step_sharded_b1": (C.c_int, [_MP, _p, _i32, _p, _p, _p, _i64, _i32, _p]),
+    "fvx_bpr_step_sharded_b2": (C.c_int, [_MP, _i32, _p, _p]),
     "fvx_bpr_step_sharded_c": (C.c_int, [_MP, _p, _i32, _p, _p, _i64, _p, _i32, _p]),
     "fvx_adam_flush": (C.c_int, [_MP, _p]),
     "fvx_project": (C.c_int, [_MP, _p, _p]),

@@ -38,6 +38,11 @@ bool fvx_fused_eligible(const FvxModel* m);
 int fvx_launch_step_fused(const FvxModel* m, const int32_t* user, int B, int loss_slot, int* parts_out,
                           cudaStream_t st);
 
+// Side stream of the step (one per device, FVX_STEP_OVERLAP=0 disables it): begin() makes it wait for the
+// work queued on `main_stream` and returns it (nullptr: unavailable); join() makes `main_stream` wait for it.
+cudaStream_t fvx_side_begin(cudaStream_t main_stream);
+void fvx_side_join(cudaStream_t main_stream);
+
 // pieces of the optimiser step shared with the item-sharded path (fvx_train_sharded.cu)
 int fvx_check_model(const FvxModel* m, const char* who);
 // what: ALL = one launch (rows, claims + catch-up, E planes); ROWS = only what the projection needs

@@ -127,7 +127,7 @@ k_rows_et(FvxModel M, const int32_t* __restrict__ pos, const int32_t* __restrict
 
 __global__ void __launch_bounds__(256)
 k_prep(FvxModel M, const int32_t* __restrict__ user, const int32_t* __restrict__ pos,
-       const int32_t* __restrict__ neg, int B, int nb_mark, int NP, int write_rows) {
+       const int32_t* __restrict__ neg, int B, int nb_mark, int NP, int write_rows, int tpw) {
   const int lane = threadIdx.x & 31;
   if ((int)blockIdx.x >= nb_mark) {
     split_E_planes(M, NP, blockIdx.x - nb_mark, gridDim.x - nb_mark);
@@ -140,9 +140,9 @@ k_prep(FvxModel M, const int32_t* __restrict__ user, const int32_t* __restrict__
   // replays the claimed rows one after the other with all 32 lanes on the row's columns
   const int warp_g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (nb_mark * blockDim.x) >> 5;
-  for (int b0 = warp_g * PREP_TPW; b0 < B; b0 += nwarps * PREP_TPW) {
+  for (int b0 = warp_g * tpw; b0 < B; b0 += nwarps * tpw) {
     const int b = b0 + lane;
-    const bool live = lane < PREP_TPW && b < B;
+    const bool live = lane < tpw && b < B;
     int32_t u = -1, li_ = -1, lj = -1;
     bool ustart = false;
     if (live) {
@@ -707,10 +707,12 @@ int fvx_launch_prep(const FvxModel* m, const int32_t* user, const int32_t* pos, 
     FVX_CHECK_LAUNCH("k_rows_et");
     return 0;
   }
-  int nb_mark = (B + 8 * PREP_TPW - 1) / (8 * PREP_TPW);     // 8 warps per block
+  // item-sharded ranks own few of the slots they scan: a full warp of triples per pass there
+  const int tpw = (m->item_cnt < m->num_items) ? 32 : PREP_TPW;
+  int nb_mark = (B + 8 * tpw - 1) / (8 * tpw);     // 8 warps per block
   if (nb_mark > fvx_num_sms() * 8) nb_mark = fvx_num_sms() * 8;
   const bool all = what == FVX_PREP_ALL;
-  k_prep<<<nb_mark + (all ? nb_e : 0), 256, 0, st>>>(*m, user, pos, neg, B, nb_mark, NP, all ? 1 : 0);
+  k_prep<<<nb_mark + (all ? nb_e : 0), 256, 0, st>>>(*m, user, pos, neg, B, nb_mark, NP, all ? 1 : 0, tpw);
   FVX_CHECK_LAUNCH("k_prep");
   return 0;
 }
@@ -782,6 +784,21 @@ static SideStream* side_stream() {
     state[dev] = ok ? 1 : -1;
   }
   return state[dev] == 1 ? &pool[dev] : nullptr;
+}
+
+// fork / join of the side stream for the other translation units (fvx_train_sharded.cu)
+cudaStream_t fvx_side_begin(cudaStream_t main_stream) {
+  SideStream* p = side_stream();
+  if (!p) return nullptr;
+  cudaEventRecord(p->fork, main_stream);
+  cudaStreamWaitEvent(p->s, p->fork, 0);
+  return p->s;
+}
+void fvx_side_join(cudaStream_t main_stream) {
+  SideStream* p = side_stream();
+  if (!p) return;
+  cudaEventRecord(p->prep_done, p->s);
+  cudaStreamWaitEvent(main_stream, p->prep_done, 0);
 }
 
 // phases of one step, in launch order (FVX_N_PHASES entries; see fvx.h)

@@ -70,6 +70,64 @@ __global__ void k_compact_owned(FvxModel M, int B, int32_t* __restrict__ count) 
   }
 }
 
+// phase A: 16 lanes per owned slot, 16-byte loads (K % 4 == 0; the scalar kernel below otherwise)
+__device__ __forceinline__ float ss_half_sum(float v) {
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float4 ss_theta4(const SsTheta& T, long long slot, int c4) {
+  const float4* q = reinterpret_cast<const float4*>(T.p + slot * T.np) + c4;
+  float4 v = q[0];
+  for (int s = 1; s < T.ks; ++s) {
+    const float4 w = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(q) + s * T.ss);
+    v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+  }
+  return v;
+}
+
+__global__ void __launch_bounds__(SS_WARPS * 32)
+k_partial_scores_v4(FvxModel M, const int32_t* __restrict__ user, int B, SsTheta T, float* __restrict__ S,
+                    const int32_t* __restrict__ count) {
+  const int Su = M.users.stride, Si = M.items.stride, K = M.K, d = M.d;
+  const int K4 = K >> 2, D4 = (d + 3) >> 2;
+  const int grp = threadIdx.x >> 4, sub = threadIdx.x & 15;
+  const bool vis = M.D > 0;
+  const int32_t* crow = M.cmap;
+  const int32_t* cslot = M.cmap + 2 * (size_t)M.max_batch;
+  const long long ng = (long long)gridDim.x * (SS_WARPS * 2);
+  const long long n_owned = *count, npad = (n_owned + 1) & ~1LL;   // both halves of a warp iterate together
+  for (long long j = (long long)blockIdx.x * (SS_WARPS * 2) + grp; j < npad; j += ng) {
+    const bool live = j < n_owned;
+    float part = 0.0f, tail = 0.0f;
+    int32_t slot = 0;
+    if (live) {
+      const int32_t li = crow[j];
+      slot = cslot[j];
+      const int b = slot < B ? slot : slot - B;
+      const int32_t u = user[b];
+      const float4* ur = reinterpret_cast<const float4*>(M.users.w + (size_t)u * Su);
+      const float4* gi = reinterpret_cast<const float4*>(M.items.w + (size_t)li * Si);
+      for (int c = sub; c < K4; c += 16) {
+        const float4 a = ur[c], x = gi[c];
+        part = fmaf(a.x, x.x, fmaf(a.y, x.y, fmaf(a.z, x.z, fmaf(a.w, x.w, part))));
+      }
+      if (vis)
+        for (int c = sub; c < D4; c += 16) {
+          const float4 tu = ur[K4 + c], th = ss_theta4(T, j, c);
+          const int n0 = 4 * c;
+          part = fmaf(tu.x, th.x, part);
+          if (n0 + 1 < d) part = fmaf(tu.y, th.y, part);
+          if (n0 + 2 < d) part = fmaf(tu.z, th.z, part);
+          if (n0 + 3 < d) part = fmaf(tu.w, th.w, part);
+        }
+      if (sub == 0) tail = M.items.w[(size_t)li * Si + K] + (vis ? T.at(j, d) : 0.0f);
+    }
+    const float s = ss_half_sum(part);
+    if (live && sub == 0) S[slot] = s + tail;
+  }
+}
+
 // phase A: one warp per owned slot
 __global__ void __launch_bounds__(SS_WARPS * 32)
 k_partial_scores(FvxModel M, const int32_t* __restrict__ user, int B, SsTheta T, float* __restrict__ S,
@@ -182,19 +240,175 @@ k_grads_sharded(FvxModel M, const int32_t* __restrict__ user, int B, int loss_sl
   }
 }
 
+
+// phase B, scalable form: one warp per OWNED slot (the compact list of phase A), 16-byte loads and
+// reductions.  The work of a rank is 2B/R slots however many triples the global batch holds; the
+// per-triple terms that are not tied to an item (softplus loss, user-side L2) belong to the slot
+// of the POSITIVE item.  Requires K % 4 == 0.
+__device__ __forceinline__ void ss_red_add4(float* addr, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ float4 ss_at4(const SsTheta& T, long long slot, int c4) {
+  const float4* q = reinterpret_cast<const float4*>(T.p + slot * T.np) + c4;
+  float4 v = q[0];
+  for (int s = 1; s < T.ks; ++s) {
+    const float4 w = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(q) + s * T.ss);
+    v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+  }
+  return v;
+}
+__device__ __forceinline__ uint2 ss_pack_bf16x4(float4 v) {
+  const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+  return make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+}
+__device__ __forceinline__ float4 ss_unpack_bf16x4(uint2 p) {
+  const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&p.x);
+  const __nv_bfloat162 hi = *reinterpret_cast<const __nv_bfloat162*>(&p.y);
+  const float2 a = __bfloat1622float2(lo), b = __bfloat1622float2(hi);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+
+__global__ void __launch_bounds__(SS_WARPS * 32)
+k_grads_owned(FvxModel M, const int32_t* __restrict__ user, int B, int loss_slot, SsTheta T, int wnp, int wpitch,
+              const float* __restrict__ S, const int32_t* __restrict__ run_id, float* __restrict__ RU,
+              long long ru_rows, const int32_t* __restrict__ count) {
+  __shared__ double loss_sh[SS_WARPS * 2];
+  const int Su = M.users.stride, Si = M.items.stride, K = M.K, d = M.d, de = M.de;
+  const int K4 = K >> 2, D4 = (d + 3) >> 2;
+  const int grp = threadIdx.x >> 4, sub = threadIdx.x & 15;     // 16 lanes per slot
+  const float reg = M.reg, reg2 = 2.0f * M.reg;
+  const bool vis = M.D > 0;
+  const long long ng = (long long)gridDim.x * (SS_WARPS * 2);
+  const long long n_owned = *count, npad = (n_owned + 1) & ~1LL;
+  const int nw4 = (wnp > 0 ? wnp : de) >> 2;
+  const int32_t* crow = M.cmap;
+  const int32_t* cslot = M.cmap + 2 * (size_t)M.max_batch;
+  double loss_acc = 0.0;
+  if (blockIdx.x == 0 && wnp > 0) {
+    // the last 32-row tile of the backward reads W rows past the owned ones: they must be zero
+    const long long cap = 2LL * M.max_batch;
+    for (long long i = threadIdx.x; i < 32LL * (wpitch >> 2); i += blockDim.x) {
+      const long long r = n_owned + i / (wpitch >> 2);
+      if (r < cap) reinterpret_cast<uint2*>(M.W_hi)[(size_t)r * (wpitch >> 2) + i % (wpitch >> 2)] = make_uint2(0u, 0u);
+      if (r < cap && wpitch == wnp) reinterpret_cast<uint2*>(M.W_lo)[(size_t)r * (wpitch >> 2) + i % (wpitch >> 2)] = make_uint2(0u, 0u);
+    }
+  }
+  for (long long j = (long long)blockIdx.x * (SS_WARPS * 2) + grp; j < npad; j += ng) {
+    bool live = j < n_owned;
+    float sq = 0.0f, xs = 0.0f, bi = 0.0f;
+    int side = 0;
+    if (live) {
+      const int32_t li = crow[j], slot = cslot[j];
+      side = slot >= B ? 1 : 0;
+      const int b = slot - side * B;
+      const int32_t u = user[b];
+      const int32_t run = run_id[b];
+      xs = S[b] - S[B + b];
+      const bool inside = (xs >= FVX_CLIP_LO) && (xs <= FVX_CLIP_HI);
+      const float coef = inside ? -1.0f / (1.0f + expf(xs)) : 0.0f;
+      if (run >= ru_rows) {           // more runs than the caller sized RU for: reported through sync[2]
+        if (sub == 0) M.sync[2] = 1;
+        live = false;
+      } else {
+        const float cs = side ? -coef : coef;
+        const float ul2 = side ? 0.0f : reg2;       // the user row's L2 term once per triple
+        const float4* ur = reinterpret_cast<const float4*>(M.users.w + (size_t)u * Su);
+        const float4* gi = reinterpret_cast<const float4*>(M.items.w + (size_t)li * Si);
+        float* gg = M.items.g + (size_t)li * Si;
+        float* ru = RU + (size_t)run * Su;
+        for (int c = sub; c < K4; c += 16) {
+          const float4 a = ur[c], x = gi[c];
+          ss_red_add4(gg + 4 * c, make_float4(cs * a.x + reg2 * x.x, cs * a.y + reg2 * x.y, cs * a.z + reg2 * x.z,
+                                              cs * a.w + reg2 * x.w));
+          ss_red_add4(ru + 4 * c, make_float4(cs * x.x + ul2 * a.x, cs * x.y + ul2 * a.y, cs * x.z + ul2 * a.z,
+                                              cs * x.w + ul2 * a.w));
+          sq += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+          if (!side) sq += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+        }
+        bi = M.items.w[(size_t)li * Si + K];
+        if (sub == 0) fvx_red_add(gg + K, cs + (side == 0 ? reg2 : reg2 / 10.0f) * bi);
+        if (vis) {
+          for (int c = sub; c < nw4; c += 16) {
+            const int n0 = 4 * c;
+            float4 tu = make_float4(0.f, 0.f, 0.f, 0.f), wv = tu;
+            if (c < D4) {
+              tu = ur[K4 + c];
+              if (n0 + 1 >= d) tu.y = 0.f;
+              if (n0 + 2 >= d) tu.z = 0.f;
+              if (n0 + 3 >= d) tu.w = 0.f;
+              float4 th = ss_at4(T, j, c);
+              if (n0 + 1 >= d) th.y = 0.f;
+              if (n0 + 2 >= d) th.z = 0.f;
+              if (n0 + 3 >= d) th.w = 0.f;
+              ss_red_add4(ru + K + 4 * c, make_float4(cs * th.x + ul2 * tu.x, cs * th.y + ul2 * tu.y,
+                                                      cs * th.z + ul2 * tu.z, cs * th.w + ul2 * tu.w));
+              if (!side) sq += tu.x * tu.x + tu.y * tu.y + tu.z * tu.z + tu.w * tu.w;
+              wv = make_float4(cs * tu.x, cs * tu.y, cs * tu.z, cs * tu.w);
+            }
+            if (n0 == d) wv.x = cs;
+            if (n0 + 1 == d) wv.y = cs;
+            if (n0 + 2 == d) wv.z = cs;
+            if (n0 + 3 == d) wv.w = cs;
+            if (wnp > 0) {
+              const uint2 h = ss_pack_bf16x4(wv);
+              const float4 hf = ss_unpack_bf16x4(h);
+              const uint2 l = ss_pack_bf16x4(make_float4(wv.x - hf.x, wv.y - hf.y, wv.z - hf.z, wv.w - hf.w));
+              reinterpret_cast<uint2*>(M.W_hi)[(size_t)j * (wpitch >> 2) + c] = h;
+              reinterpret_cast<uint2*>(M.W_lo)[(size_t)j * (wpitch >> 2) + c] = l;
+            } else {
+              reinterpret_cast<float4*>(M.W)[(size_t)j * nw4 + c] = wv;
+            }
+          }
+        }
+      }
+    }
+    const float sqs = ss_half_sum(sq);
+    if (live && sub == 0) {
+      loss_acc += (double)(reg * sqs) + (double)(reg * bi * bi / (side == 0 ? 1.0f : 10.0f));
+      if (side == 0) {
+        const float z = -fminf(fmaxf(xs, FVX_CLIP_LO), FVX_CLIP_HI);
+        loss_acc += (double)(z > 13.942385f ? z : (z < -13.942385f ? expf(z) : log1pf(expf(z))));
+      }
+    }
+  }
+  if (sub == 0) loss_sh[grp] = loss_acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < SS_WARPS * 2; ++w) s += loss_sh[w];
+    if (s != 0.0) atomicAdd(M.loss + loss_slot, s);
+  }
+}
+
 // phase C: one warp per run start adds the all-reduced run gradient into the user's accumulator
 __global__ void k_scatter_runs(FvxModel M, const int32_t* __restrict__ user, int B,
                                const int32_t* __restrict__ run_id, const float* __restrict__ RU, long long ru_rows) {
+  // a warp looks at 32 triples at once, then adds the rows of the run starts among them (a global
+  // batch of R*B triples holds ~R*B/6 runs: most triples are not a run start)
   const int lane = threadIdx.x & 31;
-  const int Su = M.users.stride;
+  const int Su = M.users.stride, S4 = Su >> 2;
   const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
-  for (long long b = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < B; b += nw) {
-    const int32_t u = user[b];
-    if (b > 0 && user[b - 1] == u) continue;          // not a run start
-    if (run_id[b] >= ru_rows) continue;
-    const float* src = RU + (size_t)run_id[b] * Su;
-    float* g = M.users.g + (size_t)u * Su;
-    for (int c = lane; c < Su; c += 32) fvx_red_add(g + c, src[c]);   // a user may own several runs
+  const long long npass = ((long long)B + 31) >> 5;
+  for (long long p = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; p < npass; p += nw) {
+    const long long b = p * 32 + lane;
+    int32_t u = -1, run = 0;
+    bool start = false;
+    if (b < B) {
+      u = user[b];
+      run = run_id[b];
+      start = (b == 0 || user[b - 1] != u) && run < ru_rows;
+    }
+    uint32_t msk = __ballot_sync(0xffffffffu, start);
+    while (msk) {
+      const int src = __ffs(msk) - 1;
+      msk &= msk - 1;
+      const int32_t uu = __shfl_sync(0xffffffffu, u, src);
+      const int32_t rr = __shfl_sync(0xffffffffu, run, src);
+      const float4* s4 = reinterpret_cast<const float4*>(RU + (size_t)rr * Su);
+      float* g = M.users.g + (size_t)uu * Su;
+      for (int c = lane; c < S4; c += 32) ss_red_add4(g + 4 * c, s4[c]);   // a user may own several runs
+    }
   }
 }
 
@@ -244,7 +458,16 @@ int fvx_bpr_step_sharded_a(const FvxModel* model, const int32_t* user, const int
   FVX_CHECK_ARG(pos && neg && S, "fvx_bpr_step_sharded_a: null pointer");
   const FvxModel& M = *model;
   cudaStream_t st = fvx_cu(stream);
-  if (int rc = fvx_launch_prep(&M, user, pos, neg, B, st)) return rc;
+  // The projection needs only the slot rows and the planes of E_ext^T: the claims and the
+  // deferred-Adam catch-up of the touched rows run beside it on the side stream (joined before the
+  // partial scores read the tables).
+  cudaStream_t side = M.D > 0 ? fvx_side_begin(st) : nullptr;
+  if (side) {
+    if (int rc = fvx_launch_prep(&M, user, pos, neg, B, side, FVX_PREP_CLAIMS)) return rc;
+    if (int rc = fvx_launch_prep(&M, user, pos, neg, B, st, FVX_PREP_ROWS)) return rc;
+  } else {
+    if (int rc = fvx_launch_prep(&M, user, pos, neg, B, st)) return rc;
+  }
   // compact list of the owned slots; foreign entries of crow stay -1 (the fp32 kernels skip them)
   int32_t* count = M.sync + 1;
   cudaMemsetAsync(M.cmap, 0xFF, sizeof(int32_t) * 2 * (size_t)M.max_batch, st);
@@ -259,51 +482,76 @@ int fvx_bpr_step_sharded_a(const FvxModel* model, const int32_t* user, const int
   if (M.D > 0) {
     if (M.use_tensor_cores) {
       FVX_CHECK_ARG((long long)ks * 2 * B * fvx_tc_np(M.de) <= M.th_cap, "fvx_bpr_step_sharded_a: TH scratch too small");
-      // W rows past the owned ones must read as zero in the last backward tile
-      if (fvx_w_pitch(&M) == 2 * fvx_tc_np(M.de)) {   // interleaved planes: one allocation
-        cudaMemsetAsync(M.W_hi, 0, sizeof(uint16_t) * 2 * (size_t)B * fvx_w_pitch(&M), st);
-      } else {
-        cudaMemsetAsync(M.W_hi, 0, sizeof(uint16_t) * 2 * (size_t)B * fvx_tc_np(M.de), st);
-        cudaMemsetAsync(M.W_lo, 0, sizeof(uint16_t) * 2 * (size_t)B * fvx_tc_np(M.de), st);
-      }
+      // (the W rows past the owned ones, read by the last backward tile, are zeroed by phase B)
       if (int rc = fvx_launch_project_tc(&M, M.cmap, 0, 2 * B, ks, M.TH, st, count)) return rc;
     } else {
       FVX_CHECK_ARG(2LL * B * M.de <= M.th_cap, "fvx_bpr_step_sharded_a: TH scratch too small");
       if (int rc = fvx_launch_project(&M, M.cmap, 2 * B, M.TH, st)) return rc;
     }
   }
-  k_partial_scores<<<ss_grid(2LL * B), SS_WARPS * 32, 0, st>>>(M, user, B, make_theta(&M, B, ks), S, count);
+  if (side) fvx_side_join(st);
+  if (M.K % 4 == 0)
+    k_partial_scores_v4<<<ss_grid(B), SS_WARPS * 32, 0, st>>>(M, user, B, make_theta(&M, B, ks), S, count);
+  else
+    k_partial_scores<<<ss_grid(2LL * B), SS_WARPS * 32, 0, st>>>(M, user, B, make_theta(&M, B, ks), S, count);
   FVX_CHECK_LAUNCH("k_partial_scores");
   return 0;
 }
 
-int fvx_bpr_step_sharded_b(const FvxModel* model, const int32_t* user, int32_t B, const float* S,
-                           const int32_t* run_id, float* RU, int64_t ru_rows, float* dE, int32_t loss_slot,
-                           fvx_stream_t stream) {
+int fvx_bpr_step_sharded_b1(const FvxModel* model, const int32_t* user, int32_t B, const float* S,
+                            const int32_t* run_id, float* RU, int64_t ru_rows, int32_t loss_slot,
+                            fvx_stream_t stream) {
   if (int rc = sharded_common(model, user, B, "fvx_bpr_step_sharded_b")) return rc;
   FVX_CHECK_ARG(S && run_id && RU && ru_rows >= 1, "fvx_bpr_step_sharded_b: null pointer");
   FVX_CHECK_ARG(loss_slot >= 0 && loss_slot < model->loss_slots, "fvx_bpr_step_sharded_b: loss_slot out of range");
   const FvxModel& M = *model;
-  FVX_CHECK_ARG(M.D == 0 || dE != nullptr, "fvx_bpr_step_sharded_b: VBPR needs the dE buffer");
   cudaStream_t st = fvx_cu(stream);
   if (cudaMemsetAsync(RU, 0, sizeof(float) * ru_rows * M.users.stride, st) != cudaSuccess)
     FVX_FAIL(-3, "fvx_bpr_step_sharded_b: memset failed");
   const int ks = sharded_ks(&M, B);
   const bool tc = M.D > 0 && M.use_tensor_cores;
-  k_grads_sharded<<<ss_grid(B), SS_WARPS * 32, 0, st>>>(M, user, B, loss_slot, make_theta(&M, B, ks),
-                                                        tc ? fvx_tc_np(M.de) : 0, tc ? fvx_w_pitch(&M) : 0, S, run_id, RU,
-                                                        (long long)ru_rows);
-  FVX_CHECK_LAUNCH("k_grads_sharded");
-  if (M.D > 0) {
-    int parts = 0;
-    if (tc) {
-      if (int rc = fvx_launch_grad_E_tc(&M, M.cmap, 2 * B, &parts, st, M.sync + 1)) return rc;
-    } else {
-      if (int rc = fvx_launch_grad_E(&M, M.cmap, 2 * B, &parts, st)) return rc;
+  if (M.K % 4 == 0) {
+    // one warp per owned slot: the work does not grow with the number of ranks
+    k_grads_owned<<<ss_grid(B), SS_WARPS * 32, 0, st>>>(M, user, B, loss_slot, make_theta(&M, B, ks),
+                                                              tc ? fvx_tc_np(M.de) : 0, tc ? fvx_w_pitch(&M) : 0, S,
+                                                              run_id, RU, (long long)ru_rows, M.sync + 1);
+    FVX_CHECK_LAUNCH("k_grads_owned");
+  } else {
+    if (tc) {   // W rows past the owned ones must read as zero in the last backward tile
+      const int np = fvx_tc_np(M.de), pitch = fvx_w_pitch(&M);
+      cudaMemsetAsync(M.W_hi, 0, sizeof(uint16_t) * 2 * (size_t)B * pitch, st);
+      if (pitch == np) cudaMemsetAsync(M.W_lo, 0, sizeof(uint16_t) * 2 * (size_t)B * np, st);
     }
-    if (int rc = fvx_launch_reduce_gE(&M, parts, tc ? fvx_tc_np(M.de) : M.de, dE, st)) return rc;
+    k_grads_sharded<<<ss_grid(B), SS_WARPS * 32, 0, st>>>(M, user, B, loss_slot, make_theta(&M, B, ks),
+                                                          tc ? fvx_tc_np(M.de) : 0, tc ? fvx_w_pitch(&M) : 0, S, run_id,
+                                                          RU, (long long)ru_rows);
+    FVX_CHECK_LAUNCH("k_grads_sharded");
   }
   return 0;
+}
+
+int fvx_bpr_step_sharded_b2(const FvxModel* model, int32_t B, float* dE, fvx_stream_t stream) {
+  FVX_CHECK_ARG(model != nullptr, "fvx_bpr_step_sharded_b: null model");
+  const FvxModel& M = *model;
+  if (M.D == 0) return 0;
+  FVX_CHECK_ARG(dE != nullptr && B >= 1 && B <= M.max_batch, "fvx_bpr_step_sharded_b: VBPR needs the dE buffer");
+  cudaStream_t st = fvx_cu(stream);
+  const bool tc = M.use_tensor_cores;
+  int parts = 0;
+  if (tc) {
+    if (int rc = fvx_launch_grad_E_tc(&M, M.cmap, 2 * B, &parts, st, M.sync + 1)) return rc;
+  } else {
+    if (int rc = fvx_launch_grad_E(&M, M.cmap, 2 * B, &parts, st)) return rc;
+  }
+  return fvx_launch_reduce_gE(&M, parts, tc ? fvx_tc_np(M.de) : M.de, dE, st);
+}
+
+int fvx_bpr_step_sharded_b(const FvxModel* model, const int32_t* user, int32_t B, const float* S,
+                           const int32_t* run_id, float* RU, int64_t ru_rows, float* dE, int32_t loss_slot,
+                           fvx_stream_t stream) {
+  FVX_CHECK_ARG(model != nullptr && (model->D == 0 || dE != nullptr), "fvx_bpr_step_sharded_b: VBPR needs the dE buffer");
+  if (int rc = fvx_bpr_step_sharded_b1(model, user, B, S, run_id, RU, ru_rows, loss_slot, stream)) return rc;
+  return fvx_bpr_step_sharded_b2(model, B, dE, stream);
 }
 
 int fvx_bpr_step_sharded_c(const FvxModel* model, const int32_t* user, int32_t B, const int32_t* run_id,

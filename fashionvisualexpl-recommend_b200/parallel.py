@@ -49,6 +49,15 @@ class DistGroup:
         for t in tensors:
             self.dist.all_reduce(t, group=self.group)
 
+    def all_reduce_start(self, tensors):
+        """Starts the all-reduce on NCCL's own stream (it waits for the work already queued on the
+        current stream); ``all_reduce_finish`` makes the current stream wait for the result."""
+        return [self.dist.all_reduce(t, group=self.group, async_op=True) for t in tensors]
+
+    def all_reduce_finish(self, works):
+        for w in works:
+            w.wait()
+
     def all_to_all(self, outs, ins):
         self.dist.all_to_all_single(outs[0], ins[0], group=self.group)
 
@@ -67,6 +76,13 @@ class LocalGroup:
         total = torch.stack(list(tensors)).sum(0)
         for t in tensors:
             t.copy_(total)
+
+    def all_reduce_start(self, tensors):
+        self.all_reduce(tensors)
+        return []
+
+    def all_reduce_finish(self, works):
+        pass
 
     def all_gather(self, outs, ins):
         full = torch.stack(list(ins))
@@ -94,6 +110,7 @@ class ShardedStep:
         self.S = [torch.zeros(2 * B, dtype=torch.float32, device=dv) for _ in self.engines]
         self.RU = [torch.zeros(self.max_runs, e.Su, dtype=torch.float32, device=dv) for _ in self.engines]
         self.dE = [torch.zeros(e.D, e.de, dtype=torch.float32, device=dv) if e.D else None for _ in self.engines]
+        self._side = None
 
     def _rank_of(self, i):
         return self.group.rank if self.group.rank is not None else i
@@ -101,16 +118,29 @@ class ShardedStep:
     def step(self, user, pos, neg, loss_slot=0):
         """One optimiser step on every (local) rank; asynchronous apart from the collectives."""
         B = user.numel()
-        rid = run_ids(user)
+        # the run ids (a handful of small torch kernels) are needed from phase B on: computed on a
+        # side stream while phase A runs
+        cur = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=user.device)
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):
+            rid = run_ids(user)
         for e, S in zip(self.engines, self.S):
             call("fvx_bpr_step_sharded_a", C.byref(e.struct()), ptr(user), ptr(pos), ptr(neg), B, ptr(S), stream_ptr())
         self.group.all_reduce(self.S)
-        for e, S, RU, dE in zip(self.engines, self.S, self.RU, self.dE):
-            call("fvx_bpr_step_sharded_b", C.byref(e.struct()), ptr(user), B, ptr(S), ptr(rid), ptr(RU), RU.shape[0],
-                 ptr(dE), loss_slot, stream_ptr())
-        self.group.all_reduce(self.RU)
+        cur.wait_stream(self._side)
+        rid.record_stream(cur)
+        for e, S, RU in zip(self.engines, self.S, self.RU):
+            call("fvx_bpr_step_sharded_b1", C.byref(e.struct()), ptr(user), B, ptr(S), ptr(rid), ptr(RU), RU.shape[0],
+                 loss_slot, stream_ptr())
+        # the all-reduce of the user-row gradients (the only large message) travels while grad_E runs
+        pending = self.group.all_reduce_start(self.RU)
         if self.dE[0] is not None:
+            for e, dE in zip(self.engines, self.dE):
+                call("fvx_bpr_step_sharded_b2", C.byref(e.struct()), B, ptr(dE), stream_ptr())
             self.group.all_reduce(self.dE)
+        self.group.all_reduce_finish(pending)
         for i, (e, RU, dE) in enumerate(zip(self.engines, self.RU, self.dE)):
             call("fvx_bpr_step_sharded_c", C.byref(e.struct()), ptr(user), B, ptr(rid), ptr(RU), RU.shape[0],
                  ptr(dE), loss_slot if self._rank_of(i) == 0 else -1, stream_ptr())

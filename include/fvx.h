@@ -171,6 +171,12 @@ int fvx_bpr_step_sharded_a(const FvxModel* model, const int32_t* user, const int
 int fvx_bpr_step_sharded_b(const FvxModel* model, const int32_t* user, int32_t B, const float* S,
                            const int32_t* run_id, float* RU, int64_t ru_rows, float* dE,
                            int32_t loss_slot, fvx_stream_t stream);
+/* Phase B in two calls (b = b1 then b2), so that the host can start the all-reduce of RU while
+ * grad_E runs: b1 = gradients of the owned slots (item rows, RU, W, loss); b2 = dE of the owned slots. */
+int fvx_bpr_step_sharded_b1(const FvxModel* model, const int32_t* user, int32_t B, const float* S,
+                            const int32_t* run_id, float* RU, int64_t ru_rows, int32_t loss_slot,
+                            fvx_stream_t stream);
+int fvx_bpr_step_sharded_b2(const FvxModel* model, int32_t B, float* dE, fvx_stream_t stream);
 /* loss_slot < 0: the reg*(|E|^2+|Bp|^2) loss term is not added (use on ranks other than 0).
  * A batch with more than ru_rows runs sets model->sync[2] = 1 (its surplus runs are dropped). */
 int fvx_bpr_step_sharded_c(const FvxModel* model, const int32_t* user, int32_t B,
