@@ -9,7 +9,7 @@ from fvx.engine import Engine
 
 U, I, K, d, D, B = 40000, 100000, 64, 20, 2048, int(os.environ.get("B", 65536))
 dev = "cuda:0"
-e = Engine(U, I, K, d=d, D=D, max_batch=B, use_tensor_cores=True, device=dev)
+e = Engine(U, I, K, d=d, D=D, max_batch=B, use_tensor_cores=True, device=dev, fused_step=True)
 g = torch.Generator(device=dev).manual_seed(1)
 F = torch.rand(I, D, device=dev, generator=g)
 e.set_features(F, keep_fp32=False); del F
