@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--top_k", type=int, default=100)
     ap.add_argument("--adam_mode", default="deferred", choices=["deferred", "dense", "lazy"])
     ap.add_argument("--tensor_cores", type=int, default=1)
+    ap.add_argument("--unique_rows", type=int, default=1)  # 0: one projection per (triple, side) slot
     ap.add_argument("--no_eval", action="store_true")
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--cpu_seconds", type=float, default=12.0)
@@ -214,7 +215,9 @@ def workload_config(args, n):
     return {"workload": "VBPR train step, K=%d d=%d D=%d, %d users x %d items (BASELINE configs[1]), "
                         "B=%d triples/step per GPU, on-device Philox sampler, %s Adam%s"
                         % (args.embed_k, args.embed_d, args.feat_dim, args.users, args.items, args.batch,
-                           args.adam_mode, "" if n == 1 else "; weak scaling: 40 000 users and one batch per GPU"),
+                           args.adam_mode + (", unique-row projection" if n == 1 and args.tensor_cores and args.unique_rows
+                                             else ""),
+                           "" if n == 1 else "; weak scaling: 40 000 users and one batch per GPU"),
             "users": args.users, "items": args.items, "K": args.embed_k, "d": args.embed_d, "D": args.feat_dim,
             "batch": args.batch * n, "adam_mode": args.adam_mode, "tensor_cores": bool(args.tensor_cores),
             "parallelism": "1 GPU" if n == 1 else
@@ -256,7 +259,8 @@ def run_fvx(args):
     lo, cnt = parallel.shard_bounds(args.items, world, rank)
     e = Engine(args.users, args.items, K, d=d, D=D, lr=1e-3, reg=1e-5, adam_mode=args.adam_mode,
                max_batch=B, device=str(dev), seed=0, use_tensor_cores=bool(args.tensor_cores),
-               item_lo=lo, item_cnt=cnt)
+               item_lo=lo, item_cnt=cnt, unique_rows=bool(args.unique_rows))
+    uniq = e.upos_t is not None and os.environ.get("FVX_STEP_DEDUP", "1") != "0"   # unique-row step in use
     if D:
         F = make_features_device(args.items, D, dev)          # same generator seed on every rank
         e.set_features(F[lo:lo + cnt].contiguous(), keep_fp32=not args.tensor_cores)
@@ -317,8 +321,9 @@ def run_fvx(args):
     # kernels of the timed region: 5 per step (prep, projection, score+grad, grad_E, update), 8 on the
     # sharded path (+ partial scores, reduce, scatter), 2 per generated epoch
     epochs_in_region = (args.steps * B) / max(data.num_train, 1)
-    # 1 GPU, VBPR: rows+planes, claims/catch-up, projection, score+grad, row update, grad_E, E update
-    per_step = (7 if D else 3) if world == 1 else (8 if D else 5)
+    # 1 GPU, VBPR: rows+planes(+item claims), claims/catch-up, projection, score+grad, row update,
+    # (coefficient planes: unique-row step), grad_E, E update
+    per_step = ((8 if uniq else 7) if D else 3) if world == 1 else (8 if D else 5)
     gpu_launches = args.steps * per_step + int(np.ceil(epochs_in_region)) * 2
 
     # ---- end to end through the reference-facing call: host batches in, float loss out ----
@@ -350,17 +355,24 @@ def run_fvx(args):
     # ---- per-kernel shares (profiling entry point; single rank; separate from the timed region) ----
     if world == 1:
         phases = {}
+        n_rows = []
         for _ in range(8):
-            for k_, v in e.step_timed(*next(batches)).items():
+            b_ = next(batches)
+            # rows one launch of the projection kernels gathers: every slot, or (unique-row step) the
+            # distinct catalog rows of the batch
+            n_rows.append(int(torch.unique(torch.cat([b_[1], b_[2]])).numel()) if uniq else 2 * B)
+            for k_, v in e.step_timed(*b_).items():
                 phases[k_] = phases.get(k_, 0.0) + v / 8
         dom = max(phases, key=phases.get)
-        rows_bytes = 2 * B * D * 4.0
+        rows_launch = float(np.mean(n_rows))
+        rows_bytes = rows_launch * D * 4.0
         tbl = 4.0 * (3 * K + d + 2)                      # floats of the three rows of a triple, once
-        kern_bytes = {"project": rows_bytes + 2 * B * e.de * 4.0, "grad_E": rows_bytes + 2 * B * e.de * 4.0,
+        kern_bytes = {"project": rows_bytes + rows_launch * e.de * 4.0, "grad_E": rows_bytes + rows_launch * e.de * 4.0,
                       "score_grad": B * 2 * tbl, "update": B * 4 * tbl + (28.0 * D * e.de if D else 0),
                       "prep": B * (12.0 + 3 * tbl)}
         kname = {"project": "k_proj_fwd_tc" if args.tensor_cores else "k_project",
-                 "grad_E": "k_grad_E_tc" if args.tensor_cores else "k_grad_E", "score_grad": "k_score_grad",
+                 "grad_E": "k_grad_E_tc" if args.tensor_cores else "k_grad_E",
+                 "score_grad": "k_score_grad_v4" if K % 4 == 0 else "k_score_grad",
                  "update": "k_update", "prep": "k_prep"}[dom]
         ach = kern_bytes.get(dom, 0.0) / (phases[dom] * 1e-3) / 1e9 if phases[dom] > 0 else 0.0
         traffic = load_traffic(kname)
@@ -368,12 +380,19 @@ def run_fvx(args):
                             "frac": ach / hbm, "traffic": traffic, "peak_source": src,
                             "algorithmic_bytes_per_launch": kern_bytes.get(dom, 0.0),
                             "kernel_ms": phases[dom], "phase_ms": phases,
+                            "phase_gbs": {k_: (kern_bytes.get(k_, 0.0) / (v * 1e-3) / 1e9 if v > 0 else None)
+                                          for k_, v in phases.items()},
+                            "rows_per_projection_launch": rows_launch, "slots_per_step": 2 * B,
+                            "unique_row_step": bool(uniq),
                             # the algorithmic count gives no credit for duplicate rows; popular items repeat
                             # inside a batch and hit L2, so the kernel's DRAM traffic (ncu) is lower and
                             # `frac` can exceed what the DRAM pins actually carried
                             "dram_achieved": (traffic / (phases[dom] * 1e-3) / 1e9) if traffic and phases[dom] > 0 else None,
-                            "note": "achieved = algorithmic bytes / CUDA-event kernel time (single-stream timed entry "
-                                    "point); dram_achieved = ncu DRAM bytes of the same launch / the same time"}
+                            "note": "achieved = bytes the launch is asked to move (projection kernels: gathered rows x 4D "
+                                    "- with the unique-row step the DISTINCT catalog rows of the batch, not the 2B slots; "
+                                    "the per-triple accounting of step_roofline gives no such credit) / CUDA-event kernel "
+                                    "time (single-stream timed entry point); dram_achieved = ncu DRAM bytes of the same "
+                                    "launch / the same time"}
     step_roof = {"achieved": B * bpt / world / (step_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
                  "bytes_per_triple": bpt, "note": "algorithmic bytes of the whole step per GPU / step time"}
     step_roof["frac"] = step_roof["achieved"] / hbm

@@ -11,7 +11,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libfvx.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 ADAM_DENSE, ADAM_DEFERRED, ADAM_LAZY = 0, 1, 2
 N_PHASES = 5
 PHASES = ("prep", "project", "score_grad", "grad_E", "update")
@@ -34,7 +34,7 @@ class FvxModel(C.Structure):
                 ("F_pl", _p), ("ET_hi", _p), ("ET_lo", _p), ("W_hi", _p), ("W_lo", _p),
                 ("step", _p), ("loss", _p), ("loss_slots", C.c_int32), ("_pad1", C.c_int32), ("TH", _p),
                 ("th_cap", C.c_int64), ("W", _p), ("rows", _p), ("sync", _p), ("cmap", _p), ("max_batch", C.c_int32),
-                ("use_tensor_cores", C.c_int32)]
+                ("use_tensor_cores", C.c_int32), ("upos", _p), ("W_sum", _p)]
 
 
 class FvxEvalWs(C.Structure):

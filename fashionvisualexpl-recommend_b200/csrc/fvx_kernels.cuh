@@ -21,10 +21,20 @@ static inline int fvx_w_pitch(const FvxModel* m) {
   return (m->W_lo == m->W_hi + np) ? 2 * np : np;
 }
 int fvx_tc_ksplit(const FvxModel* m, long long nrows);
+// K split of the forward projection for `tiles` 128-row tiles of `chunks` 64-feature chunks: aim at >= 6 work
+// units per SM so that the last wave is short; a split keeps >= 4 chunks.  Host and device evaluate the
+// same rule (the unique-row step knows its row count only on the device).
+FVX_HD int fvx_tc_ksplit_rule(long long tiles, int chunks, int nsm, int ks_cap) {
+  int ks = 1;
+  while (tiles * ks < 6LL * nsm && ks * 2 <= chunks / 4 && chunks % (ks * 2) == 0 && ks * 2 <= ks_cap) ks *= 2;
+  return ks;
+}
 int fvx_launch_split_E(const FvxModel* m, cudaStream_t st);
 int fvx_launch_split_planes(const float* src, uint16_t* dst, long long n_rows, int D, cudaStream_t st);
+// dyn_ks = 1: `ksplit` is only the cap; the kernel derives the split from *nrows_dev (fvx_tc_ksplit_rule) and
+// lays the partials out [split][nrows][NP] with the HOST-side nrows as the row capacity.
 int fvx_launch_project_tc(const FvxModel* m, const int32_t* rows, int row0, int64_t nrows, int ksplit, float* out,
-                          cudaStream_t st, const int32_t* nrows_dev = nullptr);
+                          cudaStream_t st, const int32_t* nrows_dev = nullptr, int dyn_ks = 0);
 int fvx_launch_reduce_partials(const float* part, long long nrows, int NP, int ks, int de, float* out,
                                cudaStream_t st);
 int fvx_launch_split_W(const FvxModel* m, const float* W, const int32_t* rows, long long nrows, cudaStream_t st);
@@ -47,14 +57,21 @@ void fvx_side_join(cudaStream_t main_stream);
 int fvx_check_model(const FvxModel* m, const char* who);
 // what: ALL = one launch (rows, claims + catch-up, E planes); ROWS = only what the projection needs
 // (slot rows + E planes); CLAIMS = claims + deferred-Adam catch-up without the row / plane writes
-enum { FVX_PREP_ALL = 0, FVX_PREP_ROWS = 1, FVX_PREP_CLAIMS = 2 };
+// UNIQ = slot rows + E planes + claims of the item rows with their list positions (unique-row step);
+// CLAIMS_LISTED = user claims + catch-up, item catch-up driven by the list UNIQ built
+enum { FVX_PREP_ALL = 0, FVX_PREP_ROWS = 1, FVX_PREP_CLAIMS = 2, FVX_PREP_UNIQ = 3, FVX_PREP_CLAIMS_LISTED = 4 };
 int fvx_launch_prep(const FvxModel* m, const int32_t* user, const int32_t* pos, const int32_t* neg, int B,
                     cudaStream_t st, int what = FVX_PREP_ALL, int H0 = 0);   // H0: k_rows_et half split (0: none)
 // what: ALL = tables + E_ext + finalisation; TABLES = touched rows only; E = E_ext + finalisation
 enum { FVX_UPD_ALL = 0, FVX_UPD_TABLES = 1, FVX_UPD_E = 2 };
 int fvx_launch_update(const FvxModel* m, int B, int parts, int gnp, const float* gE_src, int loss_slot,
                       cudaStream_t st, int what = FVX_UPD_ALL);
-int fvx_launch_score_grad(const FvxModel* m, const int32_t* user, int B, int loss_slot, int th_ks, cudaStream_t st);
+// dedup = 1 (unique-row step): theta rows / coefficient sums are addressed through upos, th_ks is the CAP of
+// the K split (the kernel derives the split from the list length like the projection does)
+int fvx_launch_score_grad(const FvxModel* m, const int32_t* user, int B, int loss_slot, int th_ks, cudaStream_t st,
+                          int dedup = 0);
+// W_sum -> bf16 planes of the listed rows (unique-row step)
+int fvx_launch_w_planes(const FvxModel* m, int B, cudaStream_t st);
 
 // exact fp32 top-k for the flagged rows of [u0, u0+n), in place, no host synchronisation (fvx_eval.cu)
 int fvx_launch_topk_flagged(const FvxModel* model, const float* theta_ext, const int32_t* flags, int n, int u0,

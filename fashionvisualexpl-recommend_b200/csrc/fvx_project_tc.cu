@@ -58,6 +58,10 @@ struct ProjFwdParams {
   int nacc;             // independent accumulators per buffer (one per UMMA K step of a chunk)
   int cat;              // 1: B = [E_hi | E_lo] as ONE operand of N = 2*NP - two UMMAs per K step
                         //    (A_hi, A_lo) instead of three; the epilogue adds the two column halves
+  int dyn_ks;           // 1: the K split follows the DEVICE-side row count (fvx_tc_ksplit_rule on *nrows_dev,
+                        //    at most `ksplit`): the unique-row step learns its row count on the device
+  int chunks_total;     // D / 64
+  int nsm;
   float* out;           // [ksplit][nrows][NP]
 };
 
@@ -96,7 +100,12 @@ k_proj_fwd_tc(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
   long long nvalid = P.nrows;
   if (P.nrows_dev) { const long long v = *P.nrows_dev; nvalid = v < nvalid ? v : nvalid; }
-  const int n_units = (int)((nvalid + PT_BM - 1) / PT_BM) * P.ksplit;
+  int ksplit = P.ksplit, chunks = P.chunks;
+  if (P.dyn_ks) {
+    ksplit = fvx_tc_ksplit_rule((nvalid + PT_BM - 1) / PT_BM, P.chunks_total, P.nsm, P.ksplit);
+    chunks = P.chunks_total / ksplit;
+  }
+  const int n_units = (int)((nvalid + PT_BM - 1) / PT_BM) * ksplit;
 
   if (warp < 4) {
     // ===== producers: 16 lanes copy the 256 bytes (hi | lo) of one (row, chunk); a round of the
@@ -112,7 +121,7 @@ k_proj_fwd_tc(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant_
     // stages run dry (36 % of the producers' samples in the round-1 v4 profile).
     int32_t nxt[16];
     auto load_idx = [&](int w) {
-      const int tile = w / P.ksplit;
+      const int tile = w / ksplit;
 #pragma unroll
       for (int it = 0; it < 16; ++it) {
         const long long r = (long long)tile * PT_BM + it * 8 + sub;
@@ -123,7 +132,7 @@ k_proj_fwd_tc(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant_
     };
     if ((int)blockIdx.x < n_units) load_idx(blockIdx.x);
     for (int w = blockIdx.x; w < n_units; w += gridDim.x) {
-      const int tile = w / P.ksplit, ks = w - tile * P.ksplit;
+      const int tile = w / ksplit, ks = w - tile * ksplit;
       const uint8_t* src[16];
 #pragma unroll
       for (int it = 0; it < 16; ++it) {
@@ -132,8 +141,8 @@ k_proj_fwd_tc(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant_
         src[it] = P.Fpl + (size_t)item * row_bytes + e * 16;
       }
       if (w + (int)gridDim.x < n_units) load_idx(w + gridDim.x);
-      for (int c = 0; c < P.chunks; ++c) {
-        const int chunk = ks * P.chunks + c;
+      for (int c = 0; c < chunks; ++c) {
+        const int chunk = ks * chunks + c;
         // one poller per warp: 128 threads spinning on the barrier word starve the arrive that flips it
         if (lane == 0) mbar_wait(&empty_b[stage], phase ^ 1);
         __syncwarp();
@@ -162,7 +171,7 @@ k_proj_fwd_tc(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant_
         mbar_wait(&t_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d0 = tmem_base + acc * P.nacc * NW;
-        for (int c = 0; c < P.chunks; ++c) {
+        for (int c = 0; c < chunks; ++c) {
           mbar_wait(&full_b[stage], phase);
           fence_proxy_async_smem();           // cp.async (generic proxy) writes -> UMMA (async proxy) reads
           tc_fence_after();
@@ -209,7 +218,7 @@ k_proj_fwd_tc(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant_
     const int quad = warp & 3;
     uint32_t acc = 0, acc_phase = 0;
     for (int w = blockIdx.x; w < n_units; w += gridDim.x) {
-      const int tile = w / P.ksplit, ks = w - tile * P.ksplit;
+      const int tile = w / ksplit, ks = w - tile * ksplit;
       const long long row = (long long)tile * PT_BM + quad * 32 + lane;
       mbar_wait(&t_full[acc], acc_phase);
       tc_fence_after();
@@ -491,12 +500,7 @@ __global__ void k_split_E(const float* __restrict__ E, int D, int de, int NP, __
 int fvx_tc_np(int de) { return de <= 32 ? 32 : (de + 63) / 64 * 64; }
 
 int fvx_tc_ksplit(const FvxModel* m, long long nrows) {
-  const long long tiles = (nrows + PT_BM - 1) / PT_BM;
-  const int chunks = m->D / PT_KC;
-  int ks = 1;
-  // aim at >= 6 work units per SM so that the last wave is short; a split keeps >= 4 chunks
-  while (tiles * ks < 6LL * fvx_num_sms() && ks * 2 <= chunks / 4 && chunks % (ks * 2) == 0) ks *= 2;
-  return ks;
+  return fvx_tc_ksplit_rule((nrows + PT_BM - 1) / PT_BM, m->D / PT_KC, fvx_num_sms(), 1 << 30);
 }
 
 static int set_smem(const void* fn, size_t bytes, const char* who) {
@@ -516,14 +520,15 @@ int fvx_launch_split_E(const FvxModel* m, cudaStream_t st) {
 
 // out: [ksplit][nrows][NP] fp32 partials (ksplit from fvx_tc_ksplit)
 int fvx_launch_project_tc(const FvxModel* m, const int32_t* rows, int row0, int64_t nrows, int ksplit, float* out,
-                          cudaStream_t st, const int32_t* nrows_dev) {
+                          cudaStream_t st, const int32_t* nrows_dev, int dyn_ks) {
   FVX_CHECK_ARG(m->F_pl && m->ET_hi && m->ET_lo, "tensor-core projection: bf16 planes missing");
   FVX_CHECK_ARG(m->D % PT_KC == 0, "tensor-core projection: D=%d must be a multiple of %d", m->D, PT_KC);
   const int NP = fvx_tc_np(m->de);
   FVX_CHECK_ARG(NP <= 256, "tensor-core projection: d+1=%d too wide", m->de);
   if (nrows <= 0) return 0;
   const int chunks_total = m->D / PT_KC;
-  FVX_CHECK_ARG(ksplit >= 1 && chunks_total % ksplit == 0, "tensor-core projection: bad K split %d", ksplit);
+  FVX_CHECK_ARG(ksplit >= 1 && (dyn_ks || chunks_total % ksplit == 0), "tensor-core projection: bad K split %d", ksplit);
+  FVX_CHECK_ARG(!dyn_ks || nrows_dev != nullptr, "tensor-core projection: a device-side K split needs nrows_dev");
   CUtensorMap b_hi, b_lo;
   int rc = 0;
   const uint64_t pitch = (uint64_t)m->D * 2;
@@ -532,7 +537,9 @@ int fvx_launch_project_tc(const FvxModel* m, const int32_t* rows, int row0, int6
   if (rc != 0) FVX_FAIL(-4, "tensor-core projection: cuTensorMapEncodeTiled failed");
   ProjFwdParams P;
   P.Fpl = reinterpret_cast<const uint8_t*>(m->F_pl); P.D = m->D;
-  P.rows = rows; P.row0 = row0; P.nrows = nrows; P.nrows_dev = nrows_dev; P.NP = NP; P.ksplit = ksplit; P.chunks = chunks_total / ksplit;
+  P.rows = rows; P.row0 = row0; P.nrows = nrows; P.nrows_dev = nrows_dev; P.NP = NP; P.ksplit = ksplit;
+  P.chunks = dyn_ks ? chunks_total : chunks_total / ksplit;
+  P.dyn_ks = dyn_ks; P.chunks_total = chunks_total; P.nsm = fvx_num_sms();
   P.n_tiles = (int)((nrows + PT_BM - 1) / PT_BM);
   P.out = out;
   P.cat = NP <= 64 ? 1 : 0;                       // N = 2*NP <= 128 and 2 buffers x nacc x 2*NP <= 512 columns
@@ -552,7 +559,7 @@ int fvx_launch_project_tc(const FvxModel* m, const int32_t* rows, int row0, int6
     configured = smem;
   }
   long long grid = (long long)P.n_tiles * ksplit;
-  if (grid > fvx_num_sms()) grid = fvx_num_sms();
+  if (grid > fvx_num_sms() || dyn_ks) grid = fvx_num_sms();
   k_proj_fwd_tc<<<(int)grid, PT_THREADS, smem, st>>>(b_hi, b_lo, P);
   FVX_CHECK_LAUNCH("k_proj_fwd_tc");
   return 0;

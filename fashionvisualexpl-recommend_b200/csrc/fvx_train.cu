@@ -80,6 +80,25 @@ __device__ __forceinline__ uint32_t claim_rows(const FvxTable& T, int32_t r, boo
   return b;
 }
 
+// claim_rows that also records WHERE in the list a row went: upos[r] = its index.  Every slot of the
+// batch that refers to row r finds the row's projection / coefficient sum through upos[r].
+__device__ __forceinline__ void claim_rows_pos(const FvxTable& T, int32_t* __restrict__ upos, int32_t r, bool want,
+                                               int32_t t, int lane) {
+  bool win = false;
+  if (want) win = atomicMax(&T.mark[r], t) < t;
+  const uint32_t b = __ballot_sync(0xffffffffu, win);
+  if (b) {
+    const int leader = __ffs(b) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(T.count, __popc(b));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (win) {
+      const int idx = base + __popc(b & ((1u << lane) - 1u));
+      if (idx < T.list_cap) { T.list[idx] = r; upos[r] = idx; }
+    }
+  }
+}
+
 #define PREP_TPW 8
 // blocks [0, nb_mark): PREP_TPW triples per warp pass; blocks beyond: bf16 planes of E_ext^T
 // bf16 hi / lo planes of E_ext^T [NP, D] (rows >= de zero), blocks blk of nblk
@@ -125,9 +144,37 @@ k_rows_et(FvxModel M, const int32_t* __restrict__ pos, const int32_t* __restrict
   }
 }
 
+// Unique-row step: the slot rows AND the claims of the item rows in one pass, on the main stream ahead of
+// the projection - items.list (the distinct catalog rows of the batch, in claim order) is the row list of
+// the projection and of grad_E, upos[row] the list position every slot of that row refers to.  The
+// deferred-Adam catch-up of the listed rows follows on the side stream (k_prep, items_listed = 1).
+__global__ void __launch_bounds__(256)
+k_uniq_rows(FvxModel M, const int32_t* __restrict__ pos, const int32_t* __restrict__ neg, int B, int nb_rows, int NP) {
+  if ((int)blockIdx.x >= nb_rows) {
+    split_E_planes(M, NP, blockIdx.x - nb_rows, gridDim.x - nb_rows);
+    return;
+  }
+  const int32_t t = (int32_t)(*M.step) + 1;
+  const int lane = threadIdx.x & 31;
+  for (int b0 = blockIdx.x * blockDim.x; b0 < B; b0 += nb_rows * blockDim.x) {   // warp-uniform trip count
+    const int b = b0 + threadIdx.x;
+    int32_t li = -1, lj = -1;
+    if (b < B) {
+      li = pos[b] - M.item_lo;
+      lj = neg[b] - M.item_lo;
+      if (li < 0 || li >= M.item_cnt) li = -1;
+      if (lj < 0 || lj >= M.item_cnt) lj = -1;
+      M.rows[b] = li;
+      M.rows[B + b] = lj;
+    }
+    claim_rows_pos(M.items, M.upos, li, li >= 0, t, lane);
+    claim_rows_pos(M.items, M.upos, lj, lj >= 0, t, lane);
+  }
+}
+
 __global__ void __launch_bounds__(256)
 k_prep(FvxModel M, const int32_t* __restrict__ user, const int32_t* __restrict__ pos,
-       const int32_t* __restrict__ neg, int B, int nb_mark, int NP, int write_rows, int tpw) {
+       const int32_t* __restrict__ neg, int B, int nb_mark, int NP, int write_rows, int tpw, int items_listed) {
   const int lane = threadIdx.x & 31;
   if ((int)blockIdx.x >= nb_mark) {
     split_E_planes(M, NP, blockIdx.x - nb_mark, gridDim.x - nb_mark);
@@ -148,8 +195,10 @@ k_prep(FvxModel M, const int32_t* __restrict__ user, const int32_t* __restrict__
     if (live) {
       u = user[b];
       ustart = (b == 0 || user[b - 1] != u);
-      li_ = pos[b] - M.item_lo;
-      lj = neg[b] - M.item_lo;
+      if (!items_listed) {
+        li_ = pos[b] - M.item_lo;
+        lj = neg[b] - M.item_lo;
+      }
       if (li_ < 0 || li_ >= M.item_cnt) li_ = -1;
       if (lj < 0 || lj >= M.item_cnt) lj = -1;
       if (write_rows) {
@@ -183,6 +232,15 @@ k_prep(FvxModel M, const int32_t* __restrict__ user, const int32_t* __restrict__
       }
     }
   }
+  if (items_listed && deferred) {
+    // the item rows were claimed by k_uniq_rows: catch up the listed rows, 8 lanes per row
+    int n = *M.items.count;
+    if (n > M.items.list_cap) n = M.items.list_cap;
+    const int li = lane & 7;
+    const int ngrp = (nb_mark * blockDim.x) >> 3;
+    for (int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; e < n; e += ngrp)
+      replay_row(M.items, M.items.list[e], done, M.lr, li, 8);
+  }
 }
 
 // every row -> step (*step)  (fvx_adam_flush)
@@ -207,6 +265,7 @@ struct SgTheta {
   const float* p;
   int np, ks;
   long long ss;
+  int chunks, nsm;      // unique-row step: ks is a cap, the split follows the device-side row count
   __device__ __forceinline__ float at(long long slot, int n) const {
     const float* q = p + slot * np + n;
     float v = q[0];
@@ -365,10 +424,17 @@ __device__ __forceinline__ float half_sum(float v) {
   return v;
 }
 
-template <int MQ, int MD>
+// DEDUP (unique-row step): theta of slot (b, side) is row upos[item row] of TH, and the backward
+// coefficients are ADDED into W_sum[upos[item row]] (fp32; k_w_planes turns the sums into bf16 planes).
+template <int MQ, int MD, bool DEDUP>
 __global__ void __launch_bounds__(SG_WARPS * 32, 4)
 k_score_grad_v4(FvxModel M, const int32_t* __restrict__ user, int B, int loss_slot, SgTheta T, int wnp, int wpitch) {
   __shared__ double loss_sh[SG_WARPS * 2];
+  if (DEDUP) {
+    int nv = *M.items.count;
+    if (nv > M.items.list_cap) nv = M.items.list_cap;
+    T.ks = fvx_tc_ksplit_rule((nv + 127) / 128, T.chunks, T.nsm, T.ks);
+  }
   const int Su = M.users.stride, Si = M.items.stride, K = M.K, d = M.d, de = M.de;
   const int K4 = K >> 2, D4 = (d + 3) >> 2;
   const int grp = threadIdx.x >> 4, sub = threadIdx.x & 15;
@@ -384,10 +450,16 @@ k_score_grad_v4(FvxModel M, const int32_t* __restrict__ user, int B, int loss_sl
   // the indices of the NEXT triple are loaded while this one is processed: one level less in the
   // dependent load chain (index -> rows -> reductions) that bounds the kernel
   int32_t u_n = -1, li_n = -1, lj_n = -1;
+  int32_t pi_n = 0, pj_n = 0;            // DEDUP: list positions of the two item rows, resolved one triple ahead
   if (gg0 < B) { u_n = __ldg(user + gg0); li_n = __ldg(M.rows + gg0); lj_n = __ldg(M.rows + B + gg0); }
+  if (DEDUP) {
+    pi_n = li_n >= 0 ? __ldg(M.upos + li_n) : 0;
+    pj_n = lj_n >= 0 ? __ldg(M.upos + lj_n) : 0;
+  }
   for (long long b = gg0; b < Bpad; b += ng) {
     const bool live = b < B;
     const int32_t u = u_n, li = li_n, lj = lj_n;
+    const long long si = DEDUP ? (long long)pi_n : b, sj = DEDUP ? (long long)pj_n : (long long)B + b;
     {
       const long long bn = b + ng;
       u_n = li_n = lj_n = -1;
@@ -417,7 +489,7 @@ k_score_grad_v4(FvxModel M, const int32_t* __restrict__ user, int B, int loss_sl
         dt[q] = z4;
         if (vis && c < D4) {
           tu[q] = ur[K4 + c];
-          const float4 ti = sg_at4(T, b, c), tj = sg_at4(T, B + b, c);
+          const float4 ti = sg_at4(T, si, c), tj = sg_at4(T, sj, c);
           dt[q] = make_float4(ti.x - tj.x, ti.y - tj.y, ti.z - tj.z, ti.w - tj.w);
           const int n0 = 4 * c;      // columns >= d of the chunk are not latent terms (column d: visual bias)
           if (n0 + 1 >= d) { tu[q].y = 0.f; dt[q].y = 0.f; }
@@ -427,7 +499,7 @@ k_score_grad_v4(FvxModel M, const int32_t* __restrict__ user, int B, int loss_sl
       }
       bi = M.items.w[(size_t)li * Si + K];
       bj = M.items.w[(size_t)lj * Si + K];
-      vb = vis ? T.at(b, d) - T.at(B + b, d) : 0.0f;
+      vb = vis ? T.at(si, d) - T.at(sj, d) : 0.0f;
     } else {
 #pragma unroll
       for (int q = 0; q < MQ; ++q) { a[q] = z4; x[q] = z4; y[q] = z4; }
@@ -485,7 +557,7 @@ k_score_grad_v4(FvxModel M, const int32_t* __restrict__ user, int B, int loss_sl
         fvx_red_add(ggj + K, -coef + (reg2 / 10.0f) * bj);
       }
     }
-    if (vis && live) {
+    if (vis && live && !(DEDUP && dead)) {
       // W[slot, n] = +-coef * [Tu | 1 | 0...] (zero rows for an ignored triple)
 #pragma unroll
       for (int q = 0; q < MD; ++q) {
@@ -497,7 +569,12 @@ k_score_grad_v4(FvxModel M, const int32_t* __restrict__ user, int B, int loss_sl
           if (n0 + 1 == d) wv.y = coef;
           if (n0 + 2 == d) wv.z = coef;
           if (n0 + 3 == d) wv.w = coef;
-          if (wnp > 0) {   // bf16 hi/lo planes for the tensor-core backward
+          if (DEDUP) {     // the slots of one catalog row are summed: one row of the backward operand per row
+            if (n0 <= d) {
+              red_add4(M.W_sum + (size_t)si * wnp + n0, wv);
+              red_add4(M.W_sum + (size_t)sj * wnp + n0, make_float4(-wv.x, -wv.y, -wv.z, -wv.w));
+            }
+          } else if (wnp > 0) {   // bf16 hi/lo planes for the tensor-core backward
             const uint2 h = pack_bf16x4(wv);
             const float4 hf = unpack_bf16x4(h);
             const uint2 l = pack_bf16x4(make_float4(wv.x - hf.x, wv.y - hf.y, wv.z - hf.z, wv.w - hf.w));
@@ -515,6 +592,10 @@ k_score_grad_v4(FvxModel M, const int32_t* __restrict__ user, int B, int loss_sl
         }
       }
     }
+    if (DEDUP) {   // the next triple's indices arrived long ago: resolve its list positions now
+      pi_n = li_n >= 0 ? __ldg(M.upos + li_n) : 0;
+      pj_n = lj_n >= 0 ? __ldg(M.upos + lj_n) : 0;
+    }
   }
   if (sub == 0) loss_sh[grp] = loss_acc;
   __syncthreads();
@@ -522,6 +603,38 @@ k_score_grad_v4(FvxModel M, const int32_t* __restrict__ user, int B, int loss_sl
     double s = 0.0;
     for (int w = 0; w < SG_WARPS * 2; ++w) s += loss_sh[w];
     if (s != 0.0) atomicAdd(M.loss + loss_slot, s);
+  }
+}
+
+// Unique-row step: W_sum[r, 0:NP) (fp32 sums over the slots of listed row r) -> the bf16 hi | lo planes the
+// tensor-core backward reads; the sums are zeroed for the next step, and the rows between the list length
+// and the next multiple of the backward's 32-row stage are cleared (they hold an older step's planes).
+__global__ void __launch_bounds__(256)
+k_w_planes(FvxModel M, int NP, int wpitch) {
+  int n = *M.items.count;
+  if (n > M.items.list_cap) n = M.items.list_cap;
+  long long npad = ((long long)n + 31) & ~31LL;
+  if (npad > 2LL * M.max_batch) npad = 2LL * M.max_batch;
+  const int np4 = NP >> 2;
+  const size_t wp4 = (size_t)(wpitch >> 2);
+  float4* ws = reinterpret_cast<float4*>(M.W_sum);
+  uint2* wh = reinterpret_cast<uint2*>(M.W_hi);
+  uint2* wl = reinterpret_cast<uint2*>(M.W_lo);
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npad * np4;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / np4;
+    const int c = (int)(i - r * np4);
+    float4 wv = z4;
+    if (r < n) {
+      wv = ws[i];
+      if (wv.x != 0.f || wv.y != 0.f || wv.z != 0.f || wv.w != 0.f) ws[i] = z4;
+    }
+    const uint2 h = pack_bf16x4(wv);
+    const float4 hf = unpack_bf16x4(h);
+    const uint2 l = pack_bf16x4(make_float4(wv.x - hf.x, wv.y - hf.y, wv.z - hf.z, wv.w - hf.w));
+    wh[(size_t)r * wp4 + c] = h;
+    wl[(size_t)r * wp4 + c] = l;
   }
 }
 
@@ -661,7 +774,8 @@ static inline int warp_grid(long long rows, int block = 256, int per_sm = 8) {
   return g < 1 ? 1 : (int)g;
 }
 
-int fvx_launch_score_grad(const FvxModel* m, const int32_t* user, int B, int loss_slot, int th_ks, cudaStream_t st) {
+int fvx_launch_score_grad(const FvxModel* m, const int32_t* user, int B, int loss_slot, int th_ks, cudaStream_t st,
+                          int dedup) {
   long long g = ((long long)B + SG_WARPS - 1) / SG_WARPS;
   long long cap = (long long)fvx_num_sms() * 8;
   if (g > cap) g = cap;
@@ -671,6 +785,8 @@ int fvx_launch_score_grad(const FvxModel* m, const int32_t* user, int B, int los
   T.np = tc ? fvx_tc_np(m->de) : m->de;
   T.ks = tc ? th_ks : 1;
   T.ss = 2LL * B * T.np;
+  T.chunks = m->D > 0 ? m->D / 64 : 1;
+  T.nsm = fvx_num_sms();
   const int wnp = tc ? T.np : 0;
   const int wpitch = tc ? fvx_w_pitch(m) : 0;
   const int need = (m->K > m->d + 1 ? m->K : m->d + 1);
@@ -680,12 +796,22 @@ int fvx_launch_score_grad(const FvxModel* m, const int32_t* user, int B, int los
   if (m->K % 4 == 0 && m->K <= 256 && m->d <= 252 && wcols <= 256) {
     // vector path: a lane owns 4 columns, 16 lanes per triple
     const long long g2 = (g + 1) / 2 > 0 ? (g + 1) / 2 : 1;
-    if (m->K <= 64 && wcols <= 64)
-      k_score_grad_v4<1, 1><<<(int)g2, SG_WARPS * 32, 0, st>>>(*m, user, B, loss_slot, T, wnp, wpitch);
+    if (dedup) {
+      FVX_CHECK_ARG(tc && m->upos && m->W_sum, "fvx_bpr_step: unique-row step without upos / W_sum");
+      if (m->K <= 64 && wcols <= 64)
+        k_score_grad_v4<1, 1, true><<<(int)g2, SG_WARPS * 32, 0, st>>>(*m, user, B, loss_slot, T, wnp, wpitch);
+      else if (m->K <= 128 && wcols <= 128)
+        k_score_grad_v4<2, 2, true><<<(int)g2, SG_WARPS * 32, 0, st>>>(*m, user, B, loss_slot, T, wnp, wpitch);
+      else
+        k_score_grad_v4<4, 4, true><<<(int)g2, SG_WARPS * 32, 0, st>>>(*m, user, B, loss_slot, T, wnp, wpitch);
+    } else if (m->K <= 64 && wcols <= 64)
+      k_score_grad_v4<1, 1, false><<<(int)g2, SG_WARPS * 32, 0, st>>>(*m, user, B, loss_slot, T, wnp, wpitch);
     else if (m->K <= 128 && wcols <= 128)
-      k_score_grad_v4<2, 2><<<(int)g2, SG_WARPS * 32, 0, st>>>(*m, user, B, loss_slot, T, wnp, wpitch);
+      k_score_grad_v4<2, 2, false><<<(int)g2, SG_WARPS * 32, 0, st>>>(*m, user, B, loss_slot, T, wnp, wpitch);
     else
-      k_score_grad_v4<4, 4><<<(int)g2, SG_WARPS * 32, 0, st>>>(*m, user, B, loss_slot, T, wnp, wpitch);
+      k_score_grad_v4<4, 4, false><<<(int)g2, SG_WARPS * 32, 0, st>>>(*m, user, B, loss_slot, T, wnp, wpitch);
+  } else if (dedup) {
+    FVX_FAIL(-2, "fvx_bpr_step: the unique-row step needs K %% 4 == 0");
   } else if (need <= 64 && wnp <= 64) {
     k_score_grad<2><<<(int)g, SG_WARPS * 32, 0, st>>>(*m, user, B, loss_slot, T, wnp, wpitch);
   } else {
@@ -707,12 +833,21 @@ int fvx_launch_prep(const FvxModel* m, const int32_t* user, const int32_t* pos, 
     FVX_CHECK_LAUNCH("k_rows_et");
     return 0;
   }
+  if (what == FVX_PREP_UNIQ) {
+    FVX_CHECK_ARG(m->upos != nullptr, "fvx_bpr_step: unique-row step without upos");
+    int nb_rows = (B + 255) / 256;
+    if (nb_rows > fvx_num_sms() * 4) nb_rows = fvx_num_sms() * 4;
+    k_uniq_rows<<<nb_rows + nb_e, 256, 0, st>>>(*m, pos, neg, B, nb_rows, NP);
+    FVX_CHECK_LAUNCH("k_uniq_rows");
+    return 0;
+  }
   // item-sharded ranks own few of the slots they scan: a full warp of triples per pass there
   const int tpw = (m->item_cnt < m->num_items) ? 32 : PREP_TPW;
   int nb_mark = (B + 8 * tpw - 1) / (8 * tpw);     // 8 warps per block
   if (nb_mark > fvx_num_sms() * 8) nb_mark = fvx_num_sms() * 8;
   const bool all = what == FVX_PREP_ALL;
-  k_prep<<<nb_mark + (all ? nb_e : 0), 256, 0, st>>>(*m, user, pos, neg, B, nb_mark, NP, all ? 1 : 0, tpw);
+  k_prep<<<nb_mark + (all ? nb_e : 0), 256, 0, st>>>(*m, user, pos, neg, B, nb_mark, NP, all ? 1 : 0, tpw,
+                                                     what == FVX_PREP_CLAIMS_LISTED ? 1 : 0);
   FVX_CHECK_LAUNCH("k_prep");
   return 0;
 }
@@ -740,7 +875,32 @@ int fvx_launch_update(const FvxModel* m, int B, int parts, int gnp, const float*
   return 0;
 }
 
+int fvx_launch_w_planes(const FvxModel* m, int B, cudaStream_t st) {
+  const int NP = fvx_tc_np(m->de);
+  long long g = (2LL * B * (NP >> 2) + 255) / 256;
+  if (g > (long long)fvx_num_sms() * 8) g = (long long)fvx_num_sms() * 8;
+  k_w_planes<<<(int)(g < 1 ? 1 : g), 256, 0, st>>>(*m, NP, fvx_w_pitch(m));
+  FVX_CHECK_LAUNCH("k_w_planes");
+  return 0;
+}
+
 int fvx_check_model(const FvxModel* m, const char* who) { return check_model(m, who); }
+
+// Unique-row step: ON by default where the model carries upos / W_sum;
+// FVX_STEP_DEDUP=0 or the hook below (tests compare the two paths in one process) turn it off.
+static int g_dedup = -1;
+extern "C" int fvx_debug_set_dedup(int on) {   // test hook, not part of fvx.h
+  const int old = g_dedup;
+  g_dedup = on ? 1 : 0;
+  return old;
+}
+static bool dedup_enabled() {
+  if (g_dedup < 0) {
+    const char* e = getenv("FVX_STEP_DEDUP");
+    g_dedup = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return g_dedup == 1;
+}
 
 // Two-half pipelined schedule: OFF by default (measured 425 us vs 408 us per step at B = 65536: the
 // 128-register projection CTA leaves room for one 256-thread block per SM, so the scoring kernel
@@ -839,6 +999,53 @@ static int bpr_step_impl(const FvxModel* model, const int32_t* user, const int32
   // kernels are bandwidth-bound, so the overlap is nearly free.  The timed entry point keeps
   // everything on one stream so that each phase is measured alone.
   SideStream* side = (vis && !ev && !fused) ? side_stream() : nullptr;
+
+  // Unique-row step: k_uniq_rows lists the distinct catalog rows of the batch (items.list / upos) ahead of
+  // the projection; the projection and grad_E run over that list (its length stays on the device), the
+  // scoring kernel reads theta through upos and sums the backward coefficients per listed row, k_w_planes
+  // turns the sums into the bf16 planes grad_E reads.  At B = 65 536 on a 100 k catalog 2B slots are
+  // ~58 k distinct rows: both contractions shrink by more than half.
+  const bool dedup = tc && !fused && M.upos && M.W_sum && M.K % 4 == 0 && M.K <= 256 && M.d <= 252 && NP <= 256 &&
+                     dedup_enabled() && !(side && B >= g_pipe_min_batch);
+  if (dedup) {
+    int ks_cap = 8;
+    while (ks_cap > 1 && (long long)ks_cap * 2 * B * NP > M.th_cap) ks_cap >>= 1;
+    const int32_t* cnt = M.items.count;
+    PHASE(PH_PREP);
+    if (int rc = fvx_launch_prep(&M, user, pos, neg, B, st, FVX_PREP_UNIQ)) return rc;
+    cudaStream_t ps = st;
+    if (side) {
+      cudaEventRecord(side->fork, st);
+      cudaStreamWaitEvent(side->s, side->fork, 0);
+      ps = side->s;
+    }
+    if (int rc = fvx_launch_prep(&M, user, pos, neg, B, ps, FVX_PREP_CLAIMS_LISTED)) return rc;
+    if (side) cudaEventRecord(side->prep_done, side->s);
+    PHASE(PH_PROJECT);
+    if (int rc = fvx_launch_project_tc(&M, M.items.list, 0, 2 * B, ks_cap, M.TH, st, cnt, 1)) return rc;
+    if (side) cudaStreamWaitEvent(st, side->prep_done, 0);
+    PHASE(PH_SCORE_GRAD);
+    if (int rc = fvx_launch_score_grad(&M, user, B, loss_slot, ks_cap, st, 1)) return rc;
+    if (side) {
+      cudaEventRecord(side->score_done, st);
+      cudaStreamWaitEvent(side->s, side->score_done, 0);
+      if (int rc = fvx_launch_update(&M, B, 0, NP, M.gE_part, loss_slot, side->s, FVX_UPD_TABLES)) return rc;
+      cudaEventRecord(side->upd_done, side->s);
+    }
+    PHASE(PH_GRAD_E);
+    if (int rc = fvx_launch_w_planes(&M, B, st)) return rc;
+    int parts = 0;
+    if (int rc = fvx_launch_grad_E_tc(&M, M.items.list, 2 * B, &parts, st, cnt)) return rc;
+    PHASE(PH_UPDATE);
+    if (side) {
+      cudaStreamWaitEvent(st, side->upd_done, 0);      // join: the step is complete on `st`
+      if (int rc = fvx_launch_update(&M, B, parts, NP, M.gE_part, loss_slot, st, FVX_UPD_E)) return rc;
+    } else {
+      if (int rc = fvx_launch_update(&M, B, parts, NP, M.gE_part, loss_slot, st)) return rc;
+    }
+    PHASE(PH_COUNT);
+    return 0;
+  }
   if (side && tc && B >= g_pipe_min_batch) {
     // Two half-batches in flight: the main stream runs fwd(h0) fwd(h1) grad_E(h0) grad_E(h1) back
     // to back (the bandwidth-bound kernels); the side stream runs claims/catch-up, score(h0),

@@ -30,7 +30,7 @@ def _r4(x):
 class Engine:
     def __init__(self, num_users, num_items, K, d=0, D=0, lr=1e-3, reg=0.0, adam_mode="deferred",
                  max_batch=4096, device="cuda:0", item_lo=0, item_cnt=None, loss_slots=4096,
-                 ge_parts=80, seed=0, use_tensor_cores=False, fused_step=False):
+                 ge_parts=80, seed=0, use_tensor_cores=False, fused_step=False, unique_rows=True):
         if not torch.cuda.is_available():
             raise _lib.FvxError("no CUDA device: the fvx engine has no CPU path")
         _lib.load()
@@ -67,6 +67,7 @@ class Engine:
         self.cmap_t = torch.zeros(6 * self.max_batch, **i32) if (self.item_lo or self.Ic != self.I) else None
         self.F = self.F_pl = None
         self.ET_hi = self.ET_lo = self.W_hi = self.W_lo = None
+        self.upos_t = self.W_sum = None
         self.use_tensor_cores = bool(use_tensor_cores) and self.D > 0
         # opt-in single-pass step kernel (fvx_step_fused.cu: correct, but measured slower than the
         # two-kernel path in round 1 - DESIGN.md section 3); the library falls back to the two-kernel
@@ -92,6 +93,12 @@ class Engine:
                 th_rows = max(4 * 2 * self.max_batch, 1 << 17)
                 self.TH = torch.zeros(th_rows, self.NP, **f32)
                 self.W = None
+                # unique-row step (one rank): each distinct catalog row of a batch is projected once;
+                # upos = position of a row in the touched-row list, W_sum = per-row sums of the
+                # backward coefficients (zero between steps).  unique_rows=False: one projection per slot.
+                if unique_rows and not self.item_lo and self.Ic == self.I:
+                    self.upos_t = torch.zeros(self.Ic, **i32)
+                    self.W_sum = torch.zeros(2 * self.max_batch, self.NP, **f32)
             else:
                 self.TH = torch.zeros(2 * self.max_batch, self.de, **f32)
                 self.W = torch.zeros(2 * self.max_batch, self.de, **f32)
@@ -205,6 +212,7 @@ class Engine:
             m.cmap = ptr(self.cmap_t)
             m.max_batch = self.max_batch
             m.use_tensor_cores = (2 if self.fused_step else 1) if self.use_tensor_cores else 0
+            m.upos, m.W_sum = ptr(self.upos_t), ptr(self.W_sum)
             self._struct = m
         return self._struct
 

@@ -30,7 +30,7 @@ extern "C" {
 
 typedef void* fvx_stream_t; /* cudaStream_t */
 
-#define FVX_ABI_VERSION 2
+#define FVX_ABI_VERSION 3
 
 /* Adam semantics.  The reference's Keras Adam moves
  * EVERY row of an embedding table on every step (rows without gradient keep
@@ -104,6 +104,15 @@ typedef struct FvxModel {
                            owns - local item row [2B] | slot [2B] | position of a slot [2B] */
   int32_t max_batch;
   int32_t use_tensor_cores; /* 0: fp32 SIMT projection; 1: tcgen05 (needs the planes) */
+  /* unique-row step (tensor-core path, one rank; both NULL: every slot is projected on its own).
+   * A batch of B triples touches far fewer than 2B distinct catalog rows (popular positives repeat,
+   * and 2B draws from I items collide): the step projects each distinct row ONCE - the touched-row
+   * list items.list doubles as the row list of the projection and of grad_E - and the backward
+   * coefficients of all slots of a row are summed before the contraction.                      */
+  int32_t* upos;        /* [item_cnt] position of the row in items.list (valid while
+                           items.mark[row] == step + 1)                                      */
+  float* W_sum;         /* [2*max_batch, NP] fp32 sums of the backward coefficients per listed
+                           row; all-zero between steps                                        */
 } FvxModel;
 
 /* ---- library ------------------------------------------------------------------ */

@@ -192,3 +192,79 @@ def test_two_half_pipelined_schedule_matches_oracle(K, d, D, B):
             assert d2.max() <= 5e-3 and (d2 > 2e-5).mean() <= 1e-3, (k, d2.max())
     finally:
         lib.fvx_debug_set_pipe_min_batch(old)
+
+
+@pytest.mark.parametrize("mode", ["deferred", "dense"])
+@pytest.mark.parametrize("K,d,D,B,I", [(64, 20, 2048, 3000, 400),     # ~every catalog row repeats 15 times
+                                        (64, 20, 256, 4097, 50000),    # hardly any duplicates, ragged batch
+                                        (32, 63, 512, 777, 300),       # NP = 64
+                                        (16, 100, 256, 500, 200)])     # NP = 128 (three-pass operands)
+def test_unique_row_step_equals_per_slot_step(K, d, D, B, I, mode):
+    """fvx_bpr_step projects each DISTINCT catalog row of the batch once (k_uniq_rows / upos / W_sum,
+    DESIGN.md section 3).  Against the per-slot path on the same batches - including triples whose
+    item id lies outside the catalog - and against the fp64 oracle; the scratch the unique-row step
+    leaves behind (row list, coefficient sums) must be clean after every step."""
+    U, steps, lr, reg = 600, 8, 1e-3, 1e-4
+    P, F, rng = _random_problem(U, I, K, d, D, seed=K + d + 5)
+    es = []
+    for uniq in (False, True):
+        e = _engine(U, I, K, d=d, D=D, lr=lr, reg=reg, adam_mode=mode, max_batch=B, use_tensor_cores=True,
+                    unique_rows=uniq)
+        e.set_features(F, keep_fp32=False)
+        e.load_params(P)
+        es.append(e)
+    assert es[0].struct().upos is None and es[1].struct().upos is not None
+    batches = _user_contiguous_batches(rng, U, I, B, steps)
+    clean = [(u, i, j) for (u, i, j) in batches]
+    P32, P64, l32, l64 = _oracle_pair(P, F, clean[:4], reg, lr)
+    for s, (u, i, j) in enumerate(batches):
+        i = i.copy(); j = j.copy()
+        if s >= 4:
+            i[5::97] = I + 3                               # outside the catalog: triple ignored
+            j[11::89] = -1
+        losses = []
+        for e in es:
+            e.step(_dev(u), _dev(i), _dev(j), loss_slot=0)
+            losses.append(e.read_loss(0))
+        assert losses[1] == pytest.approx(losses[0], rel=2e-6), s
+        if s < 4:
+            assert losses[1] == pytest.approx(l64[s], rel=REL), s
+        assert int(es[1].items["count"].item()) == 0
+        assert float(es[1].W_sum.abs().max()) == 0.0
+    Qa, Qb = es[0].params(), es[1].params()
+    for k in Qa:
+        dlt = np.abs(Qb[k] - Qa[k]) / np.abs(Qa[k]).max()
+        assert dlt.max() <= 5e-3 and (dlt > 2e-5).mean() <= 1e-3, (k, dlt.max(), (dlt > 2e-5).mean())
+
+
+def test_unique_row_step_timed_entry_point_and_hook():
+    """The profiling entry point runs the same unique-row kernels on one stream; the debug hook
+    (FVX_STEP_DEDUP=0 equivalent) selects the per-slot path on an engine that carries upos."""
+    from fvx import _lib
+    lib = _lib.load()
+    U, I, K, d, D, B, steps = 300, 500, 64, 20, 2048, 2048, 5
+    P, F, rng = _random_problem(U, I, K, d, D, seed=3)
+    es = []
+    for _ in range(3):
+        e = _engine(U, I, K, d=d, D=D, lr=1e-3, reg=1e-4, max_batch=B, use_tensor_cores=True)
+        e.set_features(F, keep_fp32=False)
+        e.load_params(P)
+        es.append(e)
+    batches = _user_contiguous_batches(rng, U, I, B, steps)
+    for s, b in enumerate(batches):
+        db = [_dev(x) for x in b]
+        es[0].step(*db, loss_slot=0)
+        ph = es[1].step_timed(*db, loss_slot=0)
+        assert set(ph) == set(_lib.PHASES) and all(v >= 0 for v in ph.values())
+        old = lib.fvx_debug_set_dedup(0)
+        try:
+            es[2].step(*db, loss_slot=0)
+        finally:
+            lib.fvx_debug_set_dedup(1 if old != 0 else 0)
+        la, lb, lc = (e.read_loss(0) for e in es)
+        assert la == pytest.approx(lb, rel=2e-6) and la == pytest.approx(lc, rel=2e-6), s
+    Qa, Qb, Qc = (e.params() for e in es)
+    for k in Qa:
+        for Q in (Qb, Qc):
+            dlt = np.abs(Q[k] - Qa[k]) / np.abs(Qa[k]).max()
+            assert dlt.max() <= 5e-3 and (dlt > 2e-5).mean() <= 1e-3, (k, dlt.max())
