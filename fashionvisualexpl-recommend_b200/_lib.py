@@ -34,7 +34,7 @@ class FvxModel(C.Structure):
                 ("F_pl", _p), ("ET_hi", _p), ("ET_lo", _p), ("W_hi", _p), ("W_lo", _p),
                 ("step", _p), ("loss", _p), ("loss_slots", C.c_int32), ("_pad1", C.c_int32), ("TH", _p),
                 ("th_cap", C.c_int64), ("W", _p), ("rows", _p), ("sync", _p), ("cmap", _p), ("max_batch", C.c_int32),
-                ("use_tensor_cores", C.c_int32), ("upos", _p), ("W_sum", _p)]
+                ("use_tensor_cores", C.c_int32), ("upos", _p), ("W_sum", _p), ("uslot", _p)]
 
 
 class FvxEvalWs(C.Structure):

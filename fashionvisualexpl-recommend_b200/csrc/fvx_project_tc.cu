@@ -66,7 +66,10 @@ struct ProjFwdParams {
 };
 
 // ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(PT_THREADS, 1)
+// min-blocks 2 is a REGISTER cap (112 per thread), not an occupancy claim - shared memory admits one CTA per
+// SM: the claims / catch-up kernel of the step runs beside this one on the side stream and can only use the
+// registers this kernel leaves (148 per thread left room for ONE 256-thread block per SM).
+__global__ void __launch_bounds__(PT_THREADS, 2)
 k_proj_fwd_tc(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
               const ProjFwdParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];

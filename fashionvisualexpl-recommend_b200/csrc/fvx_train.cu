@@ -17,28 +17,44 @@
 #include "fvx_kernels.cuh"
 
 // ---------------------------------------------------------------------------------
-// DEFERRED Adam catch-up: a row last brought up to step `last` has, under the
-// reference's dense-semantics Adam, taken zero-gradient steps last+1 .. target:
-//   m <- b1*m ; v <- b2*v ; w <- w - alpha_tau * m / (sqrt(v) + eps).
-// The loop is truncated after FVX_REPLAY_MAX iterations (the remaining updates are
+// DEFERRED Adam catch-up.  A row current to step `last` is brought to step `target`:
+//   step last+1 is a FULL Adam step with the row's pending gradient g (the gradient of the step at
+//     which the row was last touched stays in g until the row is needed again - the single-rank step
+//     has no separate row-update kernel; g is zero when k_update already applied it, or the row was
+//     never touched, and the step degenerates to a zero-gradient one);
+//   steps last+2 .. target are the zero-gradient steps the reference's dense-semantics Adam takes on
+//     rows without gradient:  m <- b1*m ; v <- b2*v ; w <- w - alpha_tau * m / (sqrt(v) + eps).
+// The zero-gradient loop is truncated after FVX_REPLAY_MAX iterations (the remaining updates are
 // below 2e-9 of the first one); m and v then take their closed-form decay.
 // `nl` lanes (lane index li) cooperate on one row, 4 columns at a time.
 __device__ __forceinline__ void replay_row(const FvxTable& T, int32_t r, int32_t target, float lr, int li, int nl) {
   const int32_t last = T.last[r];
   const int32_t gap = target - last;
-  if (gap > 0 && last > 0) {  // rows never updated have m = v = 0: nothing moves
-    const int n = gap < FVX_REPLAY_MAX ? gap : FVX_REPLAY_MAX;
-    const int rem = gap - n;
+  if (gap > 0) {
+    const int nz = gap - 1;
+    const int n = nz < FVX_REPLAY_MAX ? nz : FVX_REPLAY_MAX;
+    const int rem = nz - n;
     // q1 = 1 - b1^tau, q2 = 1 - b2^tau for tau = last+1, then q <- (1-b) + b*q (no cancellation)
-    const float q1_0 = (float)(-expm1((double)(last + 1) * -0.10536051565782628));    // ln 0.9
-    const float q2_0 = (float)(-expm1((double)(last + 1) * -0.0010005003335835335)); // ln 0.999
+    const double q1d = -expm1((double)(last + 1) * -0.10536051565782628);    // ln 0.9
+    const double q2d = -expm1((double)(last + 1) * -0.0010005003335835335); // ln 0.999
+    const float a0 = (float)((double)lr * sqrt(q2d) / q1d);                  // alpha of step last+1 (fvx_alpha)
+    const float q1_0 = fmaf(FVX_BETA1, (float)q1d, 1.0f - FVX_BETA1);
+    const float q2_0 = fmaf(FVX_BETA2, (float)q2d, 1.0f - FVX_BETA2);
     const float d1 = rem > 0 ? (float)exp((double)rem * -0.10536051565782628) : 1.0f;
     const float d2 = rem > 0 ? (float)exp((double)rem * -0.0010005003335835335) : 1.0f;
     float4* __restrict__ w = reinterpret_cast<float4*>(T.w + (size_t)r * T.stride);
     float4* __restrict__ m = reinterpret_cast<float4*>(T.m + (size_t)r * T.stride);
     float4* __restrict__ v = reinterpret_cast<float4*>(T.v + (size_t)r * T.stride);
+    float4* __restrict__ g = reinterpret_cast<float4*>(T.g + (size_t)r * T.stride);
     for (int c = li; c < (T.stride >> 2); c += nl) {
       float4 wc = w[c], mc = m[c], vc = v[c];
+      const float4 gc = g[c];
+#define FVX_RP0(f)                                                        \
+      mc.f = FVX_BETA1 * mc.f + (1.0f - FVX_BETA1) * gc.f;                \
+      vc.f = FVX_BETA2 * vc.f + (1.0f - FVX_BETA2) * (gc.f * gc.f);       \
+      wc.f -= a0 * mc.f / (sqrtf(vc.f) + FVX_EPS);
+      FVX_RP0(x) FVX_RP0(y) FVX_RP0(z) FVX_RP0(w)
+#undef FVX_RP0
       float q1 = q1_0, q2 = q2_0;
       for (int k = 0; k < n; ++k) {
         const float a = lr * fvx_sqrt_approx(q2) * fvx_rcp_approx(q1);
@@ -54,6 +70,7 @@ __device__ __forceinline__ void replay_row(const FvxTable& T, int32_t r, int32_t
       mc.x *= d1; mc.y *= d1; mc.z *= d1; mc.w *= d1;
       vc.x *= d2; vc.y *= d2; vc.z *= d2; vc.w *= d2;
       w[c] = wc; m[c] = mc; v[c] = vc;
+      if (gc.x != 0.0f || gc.y != 0.0f || gc.z != 0.0f || gc.w != 0.0f) g[c] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
   // every lane of the group has read T.last[r] before it is advanced
@@ -80,21 +97,28 @@ __device__ __forceinline__ uint32_t claim_rows(const FvxTable& T, int32_t r, boo
   return b;
 }
 
-// claim_rows that also records WHERE in the list a row went: upos[r] = its index.  Every slot of the
-// batch that refers to row r finds the row's projection / coefficient sum through upos[r].
-__device__ __forceinline__ void claim_rows_pos(const FvxTable& T, int32_t* __restrict__ upos, int32_t r, bool want,
+// The two item rows of a triple claimed together: both atomicMax stamps in flight at once, then ONE
+// warp-aggregated append for all winners of the warp.  upos[r] records where in the list row r went:
+// every slot of the batch that refers to row r finds its projection / coefficient sum through it.
+__device__ __forceinline__ void claim_pair_pos(const FvxTable& T, int32_t* __restrict__ upos, int32_t ri, int32_t rj,
                                                int32_t t, int lane) {
-  bool win = false;
-  if (want) win = atomicMax(&T.mark[r], t) < t;
-  const uint32_t b = __ballot_sync(0xffffffffu, win);
-  if (b) {
-    const int leader = __ffs(b) - 1;
+  bool wi = false, wj = false;
+  if (ri >= 0) wi = atomicMax(&T.mark[ri], t) < t;
+  if (rj >= 0) wj = atomicMax(&T.mark[rj], t) < t;      // rj == ri: the second stamp finds t and loses
+  const uint32_t bi = __ballot_sync(0xffffffffu, wi), bj = __ballot_sync(0xffffffffu, wj);
+  const int ni = __popc(bi), total = ni + __popc(bj);
+  if (total) {
     int base = 0;
-    if (lane == leader) base = atomicAdd(T.count, __popc(b));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (win) {
-      const int idx = base + __popc(b & ((1u << lane) - 1u));
-      if (idx < T.list_cap) { T.list[idx] = r; upos[r] = idx; }
+    if (lane == 0) base = atomicAdd(T.count, total);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    const uint32_t lt = (1u << lane) - 1u;
+    if (wi) {
+      const int idx = base + __popc(bi & lt);
+      if (idx < T.list_cap) { T.list[idx] = ri; upos[ri] = idx; }
+    }
+    if (wj) {
+      const int idx = base + ni + __popc(bj & lt);
+      if (idx < T.list_cap) { T.list[idx] = rj; upos[rj] = idx; }
     }
   }
 }
@@ -167,8 +191,7 @@ k_uniq_rows(FvxModel M, const int32_t* __restrict__ pos, const int32_t* __restri
       M.rows[b] = li;
       M.rows[B + b] = lj;
     }
-    claim_rows_pos(M.items, M.upos, li, li >= 0, t, lane);
-    claim_rows_pos(M.items, M.upos, lj, lj >= 0, t, lane);
+    claim_pair_pos(M.items, M.upos, li, lj, t, lane);
   }
 }
 
@@ -183,6 +206,14 @@ k_prep(FvxModel M, const int32_t* __restrict__ user, const int32_t* __restrict__
   const int32_t done = (int32_t)(*M.step);
   const int32_t t = done + 1;
   const bool deferred = M.adam_mode == FVX_ADAM_DEFERRED;
+  if (items_listed) {
+    // list position of every slot's row (k_uniq_rows has finished): the scoring kernel reads it with its
+    // other indices instead of chasing rows -> upos
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < 2 * B; s += nb_mark * blockDim.x) {
+      const int32_t r = M.rows[s];
+      M.uslot[s] = r >= 0 ? M.upos[r] : 0;
+    }
+  }
   // a warp takes PREP_TPW triples at a time (lanes 0..PREP_TPW-1 claim their three rows), then
   // replays the claimed rows one after the other with all 32 lanes on the row's columns
   const int warp_g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -450,12 +481,9 @@ k_score_grad_v4(FvxModel M, const int32_t* __restrict__ user, int B, int loss_sl
   // the indices of the NEXT triple are loaded while this one is processed: one level less in the
   // dependent load chain (index -> rows -> reductions) that bounds the kernel
   int32_t u_n = -1, li_n = -1, lj_n = -1;
-  int32_t pi_n = 0, pj_n = 0;            // DEDUP: list positions of the two item rows, resolved one triple ahead
+  int32_t pi_n = 0, pj_n = 0;            // DEDUP: list positions of the two item rows (k_prep: uslot)
   if (gg0 < B) { u_n = __ldg(user + gg0); li_n = __ldg(M.rows + gg0); lj_n = __ldg(M.rows + B + gg0); }
-  if (DEDUP) {
-    pi_n = li_n >= 0 ? __ldg(M.upos + li_n) : 0;
-    pj_n = lj_n >= 0 ? __ldg(M.upos + lj_n) : 0;
-  }
+  if (DEDUP && gg0 < B) { pi_n = __ldg(M.uslot + gg0); pj_n = __ldg(M.uslot + B + gg0); }
   for (long long b = gg0; b < Bpad; b += ng) {
     const bool live = b < B;
     const int32_t u = u_n, li = li_n, lj = lj_n;
@@ -464,6 +492,10 @@ k_score_grad_v4(FvxModel M, const int32_t* __restrict__ user, int B, int loss_sl
       const long long bn = b + ng;
       u_n = li_n = lj_n = -1;
       if (bn < B) { u_n = __ldg(user + bn); li_n = __ldg(M.rows + bn); lj_n = __ldg(M.rows + B + bn); }
+      if (DEDUP) {
+        pi_n = pj_n = 0;
+        if (bn < B) { pi_n = __ldg(M.uslot + bn); pj_n = __ldg(M.uslot + B + bn); }
+      }
     }
     const bool dead = li < 0 || lj < 0 || u < 0 || u >= M.num_users;   // id outside the catalog: triple ignored
     float coef = 0.0f;
@@ -592,10 +624,6 @@ k_score_grad_v4(FvxModel M, const int32_t* __restrict__ user, int B, int loss_sl
         }
       }
     }
-    if (DEDUP) {   // the next triple's indices arrived long ago: resolve its list positions now
-      pi_n = li_n >= 0 ? __ldg(M.upos + li_n) : 0;
-      pj_n = lj_n >= 0 ? __ldg(M.upos + lj_n) : 0;
-    }
   }
   if (sub == 0) loss_sh[grp] = loss_acc;
   __syncthreads();
@@ -681,7 +709,8 @@ __device__ __forceinline__ void adam_table_part(const FvxTable& T, int blk, int 
   if (n > T.list_cap) n = T.list_cap;
   const int s4 = T.stride >> 2;
   const int warps = (nblk * blockDim.x) >> 5;
-  for (int e = (blk * blockDim.x + threadIdx.x) >> 5; e < n; e += warps) {
+  const int w0 = (blk * blockDim.x + threadIdx.x) >> 5;
+  for (int e = w0; e < n; e += warps) {
     const int32_t r = T.list[e];
     const size_t o = (size_t)r * s4;
     for (int c = lane; c < s4; c += 32) {
@@ -797,7 +826,7 @@ int fvx_launch_score_grad(const FvxModel* m, const int32_t* user, int B, int los
     // vector path: a lane owns 4 columns, 16 lanes per triple
     const long long g2 = (g + 1) / 2 > 0 ? (g + 1) / 2 : 1;
     if (dedup) {
-      FVX_CHECK_ARG(tc && m->upos && m->W_sum, "fvx_bpr_step: unique-row step without upos / W_sum");
+      FVX_CHECK_ARG(tc && m->upos && m->W_sum && m->uslot, "fvx_bpr_step: unique-row step without upos / W_sum / uslot");
       if (m->K <= 64 && wcols <= 64)
         k_score_grad_v4<1, 1, true><<<(int)g2, SG_WARPS * 32, 0, st>>>(*m, user, B, loss_slot, T, wnp, wpitch);
       else if (m->K <= 128 && wcols <= 128)
@@ -961,8 +990,52 @@ void fvx_side_join(cudaStream_t main_stream) {
   cudaStreamWaitEvent(main_stream, p->prep_done, 0);
 }
 
+// Two-stream timeline of the unique-row step (debug hooks, not part of fvx.h): with tracing on, the step
+// records a timing event after every kernel on the stream that kernel runs on; fvx_debug_trace_read
+// returns their times in microseconds relative to the first one.
+enum { TR_BEGIN = 0, TR_UNIQ, TR_FWD, TR_PREP0, TR_PREP1, TR_SCORE, TR_WPL, TR_GRADE, TR_UPD0, TR_UPD1, TR_END, TR_COUNT };
+static cudaEvent_t g_trace_ev[TR_COUNT];
+static int g_trace_on = 0;
+extern "C" int fvx_debug_trace(int on) {
+  if (on && !g_trace_ev[0])
+    for (int i = 0; i < TR_COUNT; ++i)
+      if (cudaEventCreate(&g_trace_ev[i]) != cudaSuccess) return -3;
+  g_trace_on = on ? 1 : 0;
+  return 0;
+}
+extern "C" int fvx_debug_trace_read(float* us_host) {   // [TR_COUNT]; synchronises
+  if (!g_trace_ev[0]) return -2;
+  if (cudaEventSynchronize(g_trace_ev[TR_END]) != cudaSuccess) return -3;
+  for (int i = 0; i < TR_COUNT; ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, g_trace_ev[TR_BEGIN], g_trace_ev[i]) != cudaSuccess) { cudaGetLastError(); ms = -1e-3f; }
+    us_host[i] = ms * 1e3f;
+  }
+  return 0;
+}
+#define TRACE(i, stream) do { if (g_trace_on) cudaEventRecord(g_trace_ev[i], (stream)); } while (0)
+
 // phases of one step, in launch order (FVX_N_PHASES entries; see fvx.h)
 enum { PH_PREP = 0, PH_PROJECT, PH_SCORE_GRAD, PH_GRAD_E, PH_UPDATE, PH_COUNT };
+
+// DEFERRED mode, one rank: the Adam step of the rows a batch touched is NOT applied at the end of the step.
+// The gradient stays in g and the row is brought up to date - pending step first, then the zero-gradient
+// steps - when it is next needed (replay_row: the catch-up of the next step that touches it, or
+// fvx_adam_flush).  One read-modify-write of (w, m, v, g) per touched row instead of two, and one
+// kernel less per step.  FVX_STEP_MERGED_UPDATE=0 restores the separate row update (A/B measurements).
+static bool merged_update_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("FVX_STEP_MERGED_UPDATE"); on = (e && atoi(e) == 0) ? 0 : 1; }
+  return on == 1;
+}
+static int step_update(const FvxModel* m, bool merged, int B, int parts, int gnp, int loss_slot, cudaStream_t st,
+                       int what) {
+  if (merged) {
+    if (what == FVX_UPD_TABLES) return 0;
+    what = FVX_UPD_E;
+  }
+  return fvx_launch_update(m, B, parts, gnp, m->gE_part, loss_slot, st, what);
+}
 
 static int bpr_step_impl(const FvxModel* model, const int32_t* user, const int32_t* pos, const int32_t* neg,
                          int32_t B, int32_t loss_slot, cudaStream_t st, cudaEvent_t* ev) {
@@ -977,6 +1050,7 @@ static int bpr_step_impl(const FvxModel* model, const int32_t* user, const int32
   FVX_CHECK_ARG(M.rows != nullptr && M.loss != nullptr && M.sync != nullptr, "fvx_bpr_step: null scratch");
   const bool vis = M.D > 0;
   const bool tc = vis && M.use_tensor_cores;
+  const bool merged = M.adam_mode == FVX_ADAM_DEFERRED && merged_update_enabled();
   const bool fused = tc && fvx_fused_eligible(&M);   // single-pass kernel (fvx_step_fused.cu)
   const int NP = tc ? fvx_tc_np(M.de) : M.de;
   int th_ks = 1;
@@ -1005,44 +1079,85 @@ static int bpr_step_impl(const FvxModel* model, const int32_t* user, const int32
   // scoring kernel reads theta through upos and sums the backward coefficients per listed row, k_w_planes
   // turns the sums into the bf16 planes grad_E reads.  At B = 65 536 on a 100 k catalog 2B slots are
   // ~58 k distinct rows: both contractions shrink by more than half.
-  const bool dedup = tc && !fused && M.upos && M.W_sum && M.K % 4 == 0 && M.K <= 256 && M.d <= 252 && NP <= 256 &&
+  const bool dedup = tc && !fused && M.upos && M.W_sum && M.uslot && M.K % 4 == 0 && M.K <= 256 && M.d <= 252 && NP <= 256 &&
                      dedup_enabled() && !(side && B >= g_pipe_min_batch);
   if (dedup) {
     int ks_cap = 8;
     while (ks_cap > 1 && (long long)ks_cap * 2 * B * NP > M.th_cap) ks_cap >>= 1;
     const int32_t* cnt = M.items.count;
     PHASE(PH_PREP);
+    TRACE(TR_BEGIN, st);
     if (int rc = fvx_launch_prep(&M, user, pos, neg, B, st, FVX_PREP_UNIQ)) return rc;
-    cudaStream_t ps = st;
+    TRACE(TR_UNIQ, st);
+    // Submission order matters: a kernel submitted first fills the SMs first.  The bandwidth-bound
+    // projection kernels (one CTA per SM) go in AHEAD of the latency-bound side kernels, which then
+    // run in the registers the projection CTAs leave; the other way round the side kernel's blocks
+    // occupy every SM and the projection starts only when they retire (measured: 27 of the 75 us
+    // of side work overlapped).
+    static int side_first = -1;          // FVX_STEP_SIDE_FIRST=1: the old submission order (A/B measurements)
+    if (side_first < 0) { const char* e_ = getenv("FVX_STEP_SIDE_FIRST"); side_first = (e_ && atoi(e_) == 1) ? 1 : 0; }
     if (side) {
       cudaEventRecord(side->fork, st);
-      cudaStreamWaitEvent(side->s, side->fork, 0);
-      ps = side->s;
+      if (side_first) {
+        cudaStreamWaitEvent(side->s, side->fork, 0);
+        TRACE(TR_PREP0, side->s);
+        if (int rc = fvx_launch_prep(&M, user, pos, neg, B, side->s, FVX_PREP_CLAIMS_LISTED)) return rc;
+        TRACE(TR_PREP1, side->s);
+      }
+    } else {
+      if (int rc = fvx_launch_prep(&M, user, pos, neg, B, st, FVX_PREP_CLAIMS_LISTED)) return rc;
     }
-    if (int rc = fvx_launch_prep(&M, user, pos, neg, B, ps, FVX_PREP_CLAIMS_LISTED)) return rc;
-    if (side) cudaEventRecord(side->prep_done, side->s);
     PHASE(PH_PROJECT);
     if (int rc = fvx_launch_project_tc(&M, M.items.list, 0, 2 * B, ks_cap, M.TH, st, cnt, 1)) return rc;
-    if (side) cudaStreamWaitEvent(st, side->prep_done, 0);
+    TRACE(TR_FWD, st);
+    if (side) {
+      if (!side_first) {
+        cudaStreamWaitEvent(side->s, side->fork, 0);
+        TRACE(TR_PREP0, side->s);
+        if (int rc = fvx_launch_prep(&M, user, pos, neg, B, side->s, FVX_PREP_CLAIMS_LISTED)) return rc;
+        TRACE(TR_PREP1, side->s);
+      }
+      cudaEventRecord(side->prep_done, side->s);
+      cudaStreamWaitEvent(st, side->prep_done, 0);
+    }
     PHASE(PH_SCORE_GRAD);
     if (int rc = fvx_launch_score_grad(&M, user, B, loss_slot, ks_cap, st, 1)) return rc;
+    TRACE(TR_SCORE, st);
     if (side) {
       cudaEventRecord(side->score_done, st);
-      cudaStreamWaitEvent(side->s, side->score_done, 0);
-      if (int rc = fvx_launch_update(&M, B, 0, NP, M.gE_part, loss_slot, side->s, FVX_UPD_TABLES)) return rc;
-      cudaEventRecord(side->upd_done, side->s);
+      if (side_first) {
+        cudaStreamWaitEvent(side->s, side->score_done, 0);
+        TRACE(TR_UPD0, side->s);
+        if (int rc = step_update(&M, merged, B, 0, NP, loss_slot, side->s, FVX_UPD_TABLES)) return rc;
+        TRACE(TR_UPD1, side->s);
+      }
     }
     PHASE(PH_GRAD_E);
     if (int rc = fvx_launch_w_planes(&M, B, st)) return rc;
+    TRACE(TR_WPL, st);
+    // The row update may not start before grad_E's CTAs are resident: released by score_done it fills every
+    // SM during k_w_planes and grad_E starts only when its whole grid has retired (measured: grad_E
+    // 198 -> 330 us of the step with the update at 192 -> 244).  It is released by k_w_planes instead;
+    // grad_E, next on the main stream, wins that race and the update runs in the registers it leaves.
+    if (side && !side_first) cudaEventRecord(side->score_done, st);
     int parts = 0;
     if (int rc = fvx_launch_grad_E_tc(&M, M.items.list, 2 * B, &parts, st, cnt)) return rc;
+    TRACE(TR_GRADE, st);
     PHASE(PH_UPDATE);
     if (side) {
+      if (!side_first) {
+        cudaStreamWaitEvent(side->s, side->score_done, 0);
+        TRACE(TR_UPD0, side->s);
+        if (int rc = step_update(&M, merged, B, 0, NP, loss_slot, side->s, FVX_UPD_TABLES)) return rc;
+        TRACE(TR_UPD1, side->s);
+      }
+      cudaEventRecord(side->upd_done, side->s);
       cudaStreamWaitEvent(st, side->upd_done, 0);      // join: the step is complete on `st`
-      if (int rc = fvx_launch_update(&M, B, parts, NP, M.gE_part, loss_slot, st, FVX_UPD_E)) return rc;
+      if (int rc = step_update(&M, merged, B, parts, NP, loss_slot, st, FVX_UPD_E)) return rc;
     } else {
-      if (int rc = fvx_launch_update(&M, B, parts, NP, M.gE_part, loss_slot, st)) return rc;
+      if (int rc = step_update(&M, merged, B, parts, NP, loss_slot, st, FVX_UPD_ALL)) return rc;
     }
+    TRACE(TR_END, st);
     PHASE(PH_COUNT);
     return 0;
   }
@@ -1083,7 +1198,7 @@ static int bpr_step_impl(const FvxModel* model, const int32_t* user, const int32
       if (int rc = fvx_launch_score_grad(&Mh[h], user + (h ? H[0] : 0), H[h], loss_slot, ks[h], side->s)) return rc;
       cudaEventRecord(side->sc_done[h], side->s);
     }
-    if (int rc = fvx_launch_update(&M, B, 0, NP, M.gE_part, loss_slot, side->s, FVX_UPD_TABLES)) return rc;
+    if (int rc = step_update(&M, merged, B, 0, NP, loss_slot, side->s, FVX_UPD_TABLES)) return rc;
     cudaEventRecord(side->upd_done, side->s);
     int parts_total = 0;
     for (int h = 0; h < 2; ++h) {
@@ -1095,7 +1210,7 @@ static int bpr_step_impl(const FvxModel* model, const int32_t* user, const int32
       parts_total += parts_h;
     }
     cudaStreamWaitEvent(st, side->upd_done, 0);      // join: the step is complete on `st`
-    if (int rc = fvx_launch_update(&M, B, parts_total, NP, M.gE_part, loss_slot, st, FVX_UPD_E)) return rc;
+    if (int rc = step_update(&M, merged, B, parts_total, NP, loss_slot, st, FVX_UPD_E)) return rc;
     return 0;
   }
   if (side) {
@@ -1113,7 +1228,7 @@ static int bpr_step_impl(const FvxModel* model, const int32_t* user, const int32
     if (int rc = fvx_launch_score_grad(&M, user, B, loss_slot, th_ks, st)) return rc;
     cudaEventRecord(side->score_done, st);
     cudaStreamWaitEvent(side->s, side->score_done, 0);
-    if (int rc = fvx_launch_update(&M, B, 0, NP, M.gE_part, loss_slot, side->s, FVX_UPD_TABLES)) return rc;
+    if (int rc = step_update(&M, merged, B, 0, NP, loss_slot, side->s, FVX_UPD_TABLES)) return rc;
     cudaEventRecord(side->upd_done, side->s);
     int parts = 0;
     if (tc) {
@@ -1122,7 +1237,7 @@ static int bpr_step_impl(const FvxModel* model, const int32_t* user, const int32
       if (int rc = fvx_launch_grad_E(&M, M.rows, 2 * B, &parts, st)) return rc;
     }
     cudaStreamWaitEvent(st, side->upd_done, 0);      // join: the step is complete on `st`
-    if (int rc = fvx_launch_update(&M, B, parts, NP, M.gE_part, loss_slot, st, FVX_UPD_E)) return rc;
+    if (int rc = step_update(&M, merged, B, parts, NP, loss_slot, st, FVX_UPD_E)) return rc;
     return 0;
   }
 
@@ -1150,7 +1265,7 @@ static int bpr_step_impl(const FvxModel* model, const int32_t* user, const int32
     if (int rc = fvx_launch_grad_E(&M, M.rows, 2 * B, &parts, st)) return rc;
   }
   PHASE(PH_UPDATE);
-  if (int rc = fvx_launch_update(&M, B, parts, NP, M.gE_part, loss_slot, st)) return rc;
+  if (int rc = step_update(&M, merged, B, parts, NP, loss_slot, st, FVX_UPD_ALL)) return rc;
   PHASE(PH_COUNT);
 #undef PHASE
   return 0;

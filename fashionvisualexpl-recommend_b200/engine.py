@@ -67,7 +67,7 @@ class Engine:
         self.cmap_t = torch.zeros(6 * self.max_batch, **i32) if (self.item_lo or self.Ic != self.I) else None
         self.F = self.F_pl = None
         self.ET_hi = self.ET_lo = self.W_hi = self.W_lo = None
-        self.upos_t = self.W_sum = None
+        self.upos_t = self.W_sum = self.uslot_t = None
         self.use_tensor_cores = bool(use_tensor_cores) and self.D > 0
         # opt-in single-pass step kernel (fvx_step_fused.cu: correct, but measured slower than the
         # two-kernel path in round 1 - DESIGN.md section 3); the library falls back to the two-kernel
@@ -99,6 +99,7 @@ class Engine:
                 if unique_rows and not self.item_lo and self.Ic == self.I:
                     self.upos_t = torch.zeros(self.Ic, **i32)
                     self.W_sum = torch.zeros(2 * self.max_batch, self.NP, **f32)
+                    self.uslot_t = torch.zeros(2 * self.max_batch, **i32)
             else:
                 self.TH = torch.zeros(2 * self.max_batch, self.de, **f32)
                 self.W = torch.zeros(2 * self.max_batch, self.de, **f32)
@@ -212,7 +213,7 @@ class Engine:
             m.cmap = ptr(self.cmap_t)
             m.max_batch = self.max_batch
             m.use_tensor_cores = (2 if self.fused_step else 1) if self.use_tensor_cores else 0
-            m.upos, m.W_sum = ptr(self.upos_t), ptr(self.W_sum)
+            m.upos, m.W_sum, m.uslot = ptr(self.upos_t), ptr(self.W_sum), ptr(self.uslot_t)
             self._struct = m
         return self._struct
 

@@ -104,7 +104,7 @@ typedef struct FvxModel {
                            owns - local item row [2B] | slot [2B] | position of a slot [2B] */
   int32_t max_batch;
   int32_t use_tensor_cores; /* 0: fp32 SIMT projection; 1: tcgen05 (needs the planes) */
-  /* unique-row step (tensor-core path, one rank; both NULL: every slot is projected on its own).
+  /* unique-row step (tensor-core path, one rank; all NULL: every slot is projected on its own).
    * A batch of B triples touches far fewer than 2B distinct catalog rows (popular positives repeat,
    * and 2B draws from I items collide): the step projects each distinct row ONCE - the touched-row
    * list items.list doubles as the row list of the projection and of grad_E - and the backward
@@ -113,6 +113,7 @@ typedef struct FvxModel {
                            items.mark[row] == step + 1)                                      */
   float* W_sum;         /* [2*max_batch, NP] fp32 sums of the backward coefficients per listed
                            row; all-zero between steps                                        */
+  int32_t* uslot;       /* [2*max_batch] list position of the row of each (triple, side) slot  */
 } FvxModel;
 
 /* ---- library ------------------------------------------------------------------ */
