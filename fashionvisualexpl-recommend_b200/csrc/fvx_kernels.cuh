@@ -29,6 +29,17 @@ FVX_HD int fvx_tc_ksplit_rule(long long tiles, int chunks, int nsm, int ks_cap) 
   while (tiles * ks < 6LL * nsm && ks * 2 <= chunks / 4 && chunks % (ks * 2) == 0 && ks * 2 <= ks_cap) ks *= 2;
   return ks;
 }
+// The split the unique-row step derives on the device from its row count (forward kernel AND scoring kernel
+// evaluate it): the plain rule, or - when that leaves the last wave of units more than 4 % short and there
+// is at least one tile per CTA - stream-K with two partials per row (returns 2, *streamk = 1).
+FVX_HD int fvx_tc_split_dyn(long long tiles, int chunks, int nsm, int ks_cap, int ctas, int* streamk) {
+  const int ks = fvx_tc_ksplit_rule(tiles, chunks, nsm, ks_cap);
+  const long long units = tiles * ks;
+  const long long rounds = (units + ctas - 1) / ctas;
+  *streamk = 0;
+  if (ks_cap >= 2 && tiles >= ctas && rounds * ctas * 25 > units * 26) { *streamk = 1; return 2; }
+  return ks;
+}
 int fvx_launch_split_E(const FvxModel* m, cudaStream_t st);
 int fvx_launch_split_planes(const float* src, uint16_t* dst, long long n_rows, int D, cudaStream_t st);
 // dyn_ks = 1: `ksplit` is only the cap; the kernel derives the split from *nrows_dev (fvx_tc_ksplit_rule) and

@@ -65,6 +65,40 @@ struct ProjFwdParams {
   float* out;           // [ksplit][nrows][NP]
 };
 
+// Work of one CTA of the forward kernel, walked identically by its three roles.
+//   units    : (tile, K split) pairs w = blockIdx.x, blockIdx.x + gridDim.x, ... - whole splits
+//   stream-K : the flattened (tile, chunk) space is cut into gridDim.x EQUAL contiguous ranges; a CTA's
+//              range covers whole tiles plus a head and a tail fragment.  Ranges are at least one tile long
+//              (tiles >= CTAs), so a tile is cut at most once: the fragment that starts at chunk 0 writes
+//              partial 0, the other one partial 1, and a tile that is not cut gets a zero partial 1.
+struct FwdWork {
+  int streamk, ksplit, chunks, C, n_units, w, step;
+  long long pos, hi;
+  __device__ __forceinline__ bool next(int& tile, int& cb, int& ce, int& slot, bool& whole) {
+    if (!streamk) {
+      if (w >= n_units) return false;
+      tile = w / ksplit;
+      slot = w - tile * ksplit;
+      cb = slot * chunks; ce = cb + chunks; whole = false;
+      w += step;
+      return true;
+    }
+    if (pos >= hi) return false;
+    tile = (int)(pos / C);
+    cb = (int)(pos - (long long)tile * C);
+    const long long rem = hi - pos;
+    ce = rem < (long long)(C - cb) ? cb + (int)rem : C;
+    slot = cb == 0 ? 0 : 1;
+    whole = cb == 0 && ce == C;
+    pos += ce - cb;
+    return true;
+  }
+  __device__ __forceinline__ int peek_tile() const {     // tile of the fragment next() would return, -1: none
+    if (!streamk) return w < n_units ? w / ksplit : -1;
+    return pos < hi ? (int)(pos / C) : -1;
+  }
+};
+
 // ---------------------------------------------------------------------------------
 // min-blocks 2 is a REGISTER cap (112 per thread), not an occupancy claim - shared memory admits one CTA per
 // SM: the claims / catch-up kernel of the step runs beside this one on the side stream and can only use the
@@ -103,12 +137,20 @@ k_proj_fwd_tc(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
   long long nvalid = P.nrows;
   if (P.nrows_dev) { const long long v = *P.nrows_dev; nvalid = v < nvalid ? v : nvalid; }
-  int ksplit = P.ksplit, chunks = P.chunks;
-  if (P.dyn_ks) {
-    ksplit = fvx_tc_ksplit_rule((nvalid + PT_BM - 1) / PT_BM, P.chunks_total, P.nsm, P.ksplit);
-    chunks = P.chunks_total / ksplit;
+  FwdWork work0;
+  {
+    const long long tiles = (nvalid + PT_BM - 1) / PT_BM;
+    int ksplit = P.ksplit, chunks = P.chunks, streamk = 0;
+    if (P.dyn_ks) {
+      ksplit = fvx_tc_split_dyn(tiles, P.chunks_total, P.nsm, P.ksplit, (int)gridDim.x, &streamk);
+      chunks = P.chunks_total / (streamk ? 1 : ksplit);
+    }
+    work0.streamk = streamk; work0.ksplit = ksplit; work0.chunks = chunks; work0.C = P.chunks_total;
+    work0.n_units = (int)tiles * ksplit; work0.w = blockIdx.x; work0.step = gridDim.x;
+    const long long total = tiles * P.chunks_total;
+    work0.pos = total * blockIdx.x / gridDim.x;
+    work0.hi = total * (blockIdx.x + 1) / gridDim.x;
   }
-  const int n_units = (int)((nvalid + PT_BM - 1) / PT_BM) * ksplit;
 
   if (warp < 4) {
     // ===== producers: 16 lanes copy the 256 bytes (hi | lo) of one (row, chunk); a round of the
@@ -123,8 +165,7 @@ k_proj_fwd_tc(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant_
     // pipeline of cp.async requests takes microseconds, and a producer that waits for it lets the
     // stages run dry (36 % of the producers' samples in the round-1 v4 profile).
     int32_t nxt[16];
-    auto load_idx = [&](int w) {
-      const int tile = w / ksplit;
+    auto load_idx = [&](int tile) {
 #pragma unroll
       for (int it = 0; it < 16; ++it) {
         const long long r = (long long)tile * PT_BM + it * 8 + sub;
@@ -133,9 +174,11 @@ k_proj_fwd_tc(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant_
         nxt[it] = item;
       }
     };
-    if ((int)blockIdx.x < n_units) load_idx(blockIdx.x);
-    for (int w = blockIdx.x; w < n_units; w += gridDim.x) {
-      const int tile = w / ksplit, ks = w - tile * ksplit;
+    FwdWork work = work0;
+    if (work.peek_tile() >= 0) load_idx(work.peek_tile());
+    int tile, cb, ce, slot;
+    bool whole;
+    while (work.next(tile, cb, ce, slot, whole)) {
       const uint8_t* src[16];
 #pragma unroll
       for (int it = 0; it < 16; ++it) {
@@ -143,9 +186,8 @@ k_proj_fwd_tc(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant_
         if (item < 0) item = 0;               // slot of another rank's item: any valid row, result unused
         src[it] = P.Fpl + (size_t)item * row_bytes + e * 16;
       }
-      if (w + (int)gridDim.x < n_units) load_idx(w + gridDim.x);
-      for (int c = 0; c < chunks; ++c) {
-        const int chunk = ks * chunks + c;
+      if (work.peek_tile() >= 0) load_idx(work.peek_tile());
+      for (int chunk = cb; chunk < ce; ++chunk) {
         // one poller per warp: 128 threads spinning on the barrier word starve the arrive that flips it
         if (lane == 0) mbar_wait(&empty_b[stage], phase ^ 1);
         __syncwarp();
@@ -170,11 +212,14 @@ k_proj_fwd_tc(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant_
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(PT_BM, (int)NW, 0, 0);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      for (int w = blockIdx.x; w < n_units; w += gridDim.x) {
+      FwdWork work = work0;
+      int tile, cb, ce, slot;
+      bool whole;
+      while (work.next(tile, cb, ce, slot, whole)) {
         mbar_wait(&t_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d0 = tmem_base + acc * P.nacc * NW;
-        for (int c = 0; c < chunks; ++c) {
+        for (int c = 0; c < ce - cb; ++c) {
           mbar_wait(&full_b[stage], phase);
           fence_proxy_async_smem();           // cp.async (generic proxy) writes -> UMMA (async proxy) reads
           tc_fence_after();
@@ -220,12 +265,18 @@ k_proj_fwd_tc(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant_
     // ===== epilogue: TMEM -> registers -> fp32 partial rows =====
     const int quad = warp & 3;
     uint32_t acc = 0, acc_phase = 0;
-    for (int w = blockIdx.x; w < n_units; w += gridDim.x) {
-      const int tile = w / ksplit, ks = w - tile * ksplit;
+    FwdWork work = work0;
+    int tile, cb, ce, slot;
+    bool whole;
+    while (work.next(tile, cb, ce, slot, whole)) {
       const long long row = (long long)tile * PT_BM + quad * 32 + lane;
       mbar_wait(&t_full[acc], acc_phase);
       tc_fence_after();
-      float* dst = P.out + ((size_t)ks * P.nrows + (size_t)(row < nvalid ? row : 0)) * P.NP;
+      float* dst = P.out + ((size_t)slot * P.nrows + (size_t)(row < nvalid ? row : 0)) * P.NP;
+      if (whole && row < nvalid) {            // stream-K: an uncut tile has no second fragment - its partial 1 is zero
+        float4* z = reinterpret_cast<float4*>(dst + (size_t)P.nrows * P.NP);
+        for (int n4 = 0; n4 < (P.NP >> 2); ++n4) z[n4] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
       for (int n0 = 0; n0 < P.NP; n0 += 32) {
         float sum[32];
         const int nparts = P.cat ? 2 * P.nacc : P.nacc;   // cat: columns [0,NP) and [NP,2NP) of every accumulator

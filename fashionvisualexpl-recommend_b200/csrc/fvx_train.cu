@@ -34,25 +34,27 @@ __device__ __forceinline__ void replay_row(const FvxTable& T, int32_t r, int32_t
     const int nz = gap - 1;
     const int n = nz < FVX_REPLAY_MAX ? nz : FVX_REPLAY_MAX;
     const int rem = nz - n;
-    // q1 = 1 - b1^tau, q2 = 1 - b2^tau for tau = last+1, then q <- (1-b) + b*q (no cancellation)
-    const double q1d = -expm1((double)(last + 1) * -0.10536051565782628);    // ln 0.9
-    const double q2d = -expm1((double)(last + 1) * -0.0010005003335835335); // ln 0.999
-    const float a0 = (float)((double)lr * sqrt(q2d) / q1d);                  // alpha of step last+1 (fvx_alpha)
-    const float q1_0 = fmaf(FVX_BETA1, (float)q1d, 1.0f - FVX_BETA1);
-    const float q2_0 = fmaf(FVX_BETA2, (float)q2d, 1.0f - FVX_BETA2);
-    const float d1 = rem > 0 ? (float)exp((double)rem * -0.10536051565782628) : 1.0f;
-    const float d2 = rem > 0 ? (float)exp((double)rem * -0.0010005003335835335) : 1.0f;
+    // q1 = 1 - b1^tau, q2 = 1 - b2^tau for tau = last+1 (expm1f: no cancellation for small tau), then
+    // q <- (1-b) + b*q.  Single precision throughout: the kernel was instruction-bound on the double
+    // expm1 / sqrt / divide every lane evaluated per row (28.5 M warp instructions per launch); alpha
+    // carries ~2 ulp, i.e. a relative error of 1e-7 on an update that is itself ~1e-2 of the weight.
+    const float tau = (float)(last + 1);
+    const float q1f = -expm1f(tau * -0.10536051565782628f);    // ln 0.9
+    const float q2f = -expm1f(tau * -0.0010005003335835335f);  // ln 0.999
+    const float a0 = lr * sqrtf(q2f) / q1f;                    // alpha of step last+1 (fvx_alpha)
+    const float q1_0 = fmaf(FVX_BETA1, q1f, 1.0f - FVX_BETA1);
+    const float q2_0 = fmaf(FVX_BETA2, q2f, 1.0f - FVX_BETA2);
+    const float d1 = rem > 0 ? expf((float)rem * -0.10536051565782628f) : 1.0f;
+    const float d2 = rem > 0 ? expf((float)rem * -0.0010005003335835335f) : 1.0f;
     float4* __restrict__ w = reinterpret_cast<float4*>(T.w + (size_t)r * T.stride);
     float4* __restrict__ m = reinterpret_cast<float4*>(T.m + (size_t)r * T.stride);
     float4* __restrict__ v = reinterpret_cast<float4*>(T.v + (size_t)r * T.stride);
     float4* __restrict__ g = reinterpret_cast<float4*>(T.g + (size_t)r * T.stride);
-    for (int c = li; c < (T.stride >> 2); c += nl) {
-      float4 wc = w[c], mc = m[c], vc = v[c];
-      const float4 gc = g[c];
+    auto advance = [&](float4& wc, float4& mc, float4& vc, const float4& gc) {
 #define FVX_RP0(f)                                                        \
       mc.f = FVX_BETA1 * mc.f + (1.0f - FVX_BETA1) * gc.f;                \
       vc.f = FVX_BETA2 * vc.f + (1.0f - FVX_BETA2) * (gc.f * gc.f);       \
-      wc.f -= a0 * mc.f / (sqrtf(vc.f) + FVX_EPS);
+      wc.f -= a0 * mc.f * fvx_rcp_approx(fvx_sqrt_approx(vc.f) + FVX_EPS);
       FVX_RP0(x) FVX_RP0(y) FVX_RP0(z) FVX_RP0(w)
 #undef FVX_RP0
       float q1 = q1_0, q2 = q2_0;
@@ -69,8 +71,27 @@ __device__ __forceinline__ void replay_row(const FvxTable& T, int32_t r, int32_t
       }
       mc.x *= d1; mc.y *= d1; mc.z *= d1; mc.w *= d1;
       vc.x *= d2; vc.y *= d2; vc.z *= d2; vc.w *= d2;
-      w[c] = wc; m[c] = mc; v[c] = vc;
-      if (gc.x != 0.0f || gc.y != 0.0f || gc.z != 0.0f || gc.w != 0.0f) g[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int s4 = T.stride >> 2;
+    // two column chunks per pass: the eight loads of a pass are in flight together (a row of K = 64 is
+    // 17 - 21 float4: with 8 lanes per row two passes instead of three dependent ones)
+    for (int c0 = 0; c0 < s4; c0 += 2 * nl) {
+      const int ca = c0 + li, cb = c0 + nl + li;
+      const bool ha = ca < s4, hb = cb < s4;
+      float4 wa = z4, ma = z4, va = z4, ga = z4, wb = z4, mb = z4, vb = z4, gb = z4;
+      if (ha) { wa = w[ca]; ma = m[ca]; va = v[ca]; ga = g[ca]; }
+      if (hb) { wb = w[cb]; mb = m[cb]; vb = v[cb]; gb = g[cb]; }
+      if (ha) {
+        advance(wa, ma, va, ga);
+        w[ca] = wa; m[ca] = ma; v[ca] = va;
+        if (ga.x != 0.0f || ga.y != 0.0f || ga.z != 0.0f || ga.w != 0.0f) g[ca] = z4;
+      }
+      if (hb) {
+        advance(wb, mb, vb, gb);
+        w[cb] = wb; m[cb] = mb; v[cb] = vb;
+        if (gb.x != 0.0f || gb.y != 0.0f || gb.z != 0.0f || gb.w != 0.0f) g[cb] = z4;
+      }
     }
   }
   // every lane of the group has read T.last[r] before it is advanced
@@ -195,7 +216,7 @@ k_uniq_rows(FvxModel M, const int32_t* __restrict__ pos, const int32_t* __restri
   }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 k_prep(FvxModel M, const int32_t* __restrict__ user, const int32_t* __restrict__ pos,
        const int32_t* __restrict__ neg, int B, int nb_mark, int NP, int write_rows, int tpw, int items_listed) {
   const int lane = threadIdx.x & 31;
@@ -464,7 +485,8 @@ k_score_grad_v4(FvxModel M, const int32_t* __restrict__ user, int B, int loss_sl
   if (DEDUP) {
     int nv = *M.items.count;
     if (nv > M.items.list_cap) nv = M.items.list_cap;
-    T.ks = fvx_tc_ksplit_rule((nv + 127) / 128, T.chunks, T.nsm, T.ks);
+    int streamk;
+    T.ks = fvx_tc_split_dyn((nv + 127) / 128, T.chunks, T.nsm, T.ks, T.nsm, &streamk);
   }
   const int Su = M.users.stride, Si = M.items.stride, K = M.K, d = M.d, de = M.de;
   const int K4 = K >> 2, D4 = (d + 3) >> 2;
@@ -744,6 +766,13 @@ k_update(FvxModel M, UpdParams U) {
       const size_t pstride = (size_t)M.D * U.gnp;
       float g = 0.0f;
       int p = 0;
+      for (; p + 16 <= U.parts; p += 16) {      // sixteen loads in flight, summed in the same fixed order
+        float t_[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) t_[q] = gp[(size_t)(p + q) * pstride];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) g += t_[q];
+      }
       for (; p + 4 <= U.parts; p += 4) {
         const float g0 = gp[(size_t)p * pstride], g1 = gp[(size_t)(p + 1) * pstride];
         const float g2 = gp[(size_t)(p + 2) * pstride], g3 = gp[(size_t)(p + 3) * pstride];
