@@ -18,6 +18,7 @@
 //   B = W tile [32 rows x NP] (MN-major), D[512 features x NP] stays in TMEM over all row
 //   tiles of the group and leaves once as a per-row-group partial of gE_ext.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "fvx_common.cuh"
 #include "fvx_kernels.cuh"
@@ -604,6 +605,15 @@ int fvx_launch_project_tc(const FvxModel* m, const int32_t* rows, int row0, int6
   const size_t stage_bytes = 2 * PT_BM * 128 + 2 * (size_t)NP * 128;
   int stages = (int)((220 * 1024) / stage_bytes);
   if (stages > 6) stages = 6;
+  {
+    static int cap = -1;                 // FVX_FWD_STAGES: cap on the pipeline depth (measurements)
+    if (cap < 0) { const char* e = getenv("FVX_FWD_STAGES"); cap = e ? atoi(e) : 0; }
+    if (cap >= 2 && stages > cap) stages = cap;
+    // the step's forward kernel shares the memory system with the catch-up kernel on the side stream:
+    // six 32 KB stages per SM keep ~28 MB of requests queued and the latency-bound neighbour waits behind
+    // them (its end moved from 146 to 138 us of the step with four stages; the projection itself did not slow)
+    if (cap < 2 && dyn_ks && stages > 4) stages = 4;
+  }
   FVX_CHECK_ARG(stages >= 2, "tensor-core projection: tile does not fit shared memory");
   P.stages = stages;
   const size_t smem = stages * stage_bytes + (2 * stages + 4) * 8 + 16 + 1024;
@@ -664,6 +674,11 @@ int fvx_launch_grad_E_tc(const FvxModel* m, const int32_t* rows, int64_t nrows, 
   const size_t stage_bytes = 2 * (size_t)(fgs / PT_KC) * GE_RT * 128 + (cat ? 1 : 2) * (size_t)P.w_atoms * GE_RT * wrow;
   int stages = (int)((220 * 1024) / stage_bytes);
   if (stages > 4) stages = 4;
+  {
+    static int cap = -1;                 // FVX_GE_STAGES: cap on the pipeline depth (measurements)
+    if (cap < 0) { const char* e = getenv("FVX_GE_STAGES"); cap = e ? atoi(e) : 0; }
+    if (cap >= 2 && stages > cap) stages = cap;
+  }
   FVX_CHECK_ARG(stages >= 2, "tensor-core grad_E: tile does not fit shared memory");
   P.stages = stages;
   const size_t smem = stages * stage_bytes + (2 * stages + 1) * 8 + 16 + 1024;

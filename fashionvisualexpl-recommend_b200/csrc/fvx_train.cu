@@ -457,6 +457,26 @@ __device__ __forceinline__ float4 sg_at4(const SgTheta& T, long long slot, int c
   }
   return v;
 }
+// theta chunk c4 of the positive and the negative slot, minus each other.  All loads of the common
+// splits (1 or 2 partials) are issued before the first use: written as a loop over the partials the
+// compiler emits load -> add -> load -> add, four dependent memory round trips per triple (31 % of the
+// kernel's stall samples sat on those adds in the round-1 v7 profile).
+__device__ __forceinline__ float4 sg_diff4(const SgTheta& T, long long si, long long sj, int c4) {
+  const float4* qi = reinterpret_cast<const float4*>(T.p + si * T.np) + c4;
+  const float4* qj = reinterpret_cast<const float4*>(T.p + sj * T.np) + c4;
+  if (T.ks <= 2) {
+    const float4 a0 = qi[0], b0 = qj[0];
+    float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = a1;
+    if (T.ks == 2) {
+      a1 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(qi) + T.ss);
+      b1 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(qj) + T.ss);
+    }
+    return make_float4((a0.x + a1.x) - (b0.x + b1.x), (a0.y + a1.y) - (b0.y + b1.y),
+                       (a0.z + a1.z) - (b0.z + b1.z), (a0.w + a1.w) - (b0.w + b1.w));
+  }
+  const float4 ti = sg_at4(T, si, c4), tj = sg_at4(T, sj, c4);
+  return make_float4(ti.x - tj.x, ti.y - tj.y, ti.z - tj.z, ti.w - tj.w);
+}
 __device__ __forceinline__ float dot4(float4 a, float4 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w))); }
 __device__ __forceinline__ uint2 pack_bf16x4(float4 v) {
   const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
@@ -489,7 +509,7 @@ k_score_grad_v4(FvxModel M, const int32_t* __restrict__ user, int B, int loss_sl
     T.ks = fvx_tc_split_dyn((nv + 127) / 128, T.chunks, T.nsm, T.ks, T.nsm, &streamk);
   }
   const int Su = M.users.stride, Si = M.items.stride, K = M.K, d = M.d, de = M.de;
-  const int K4 = K >> 2, D4 = (d + 3) >> 2;
+  const int K4 = K >> 2, D4 = (d + 3) >> 2, D4b = (d + 4) >> 2;
   const int grp = threadIdx.x >> 4, sub = threadIdx.x & 15;
   const float reg = M.reg, reg2 = 2.0f * M.reg;
   const bool vis = M.D > 0;
@@ -541,11 +561,15 @@ k_score_grad_v4(FvxModel M, const int32_t* __restrict__ user, int B, int loss_sl
       for (int q = 0; q < MD; ++q) {
         const int c = sub + 16 * q;
         dt[q] = z4;
-        if (vis && c < D4) {
-          tu[q] = ur[K4 + c];
-          const float4 ti = sg_at4(T, si, c), tj = sg_at4(T, sj, c);
-          dt[q] = make_float4(ti.x - tj.x, ti.y - tj.y, ti.z - tj.z, ti.w - tj.w);
-          const int n0 = 4 * c;      // columns >= d of the chunk are not latent terms (column d: visual bias)
+        if (vis && c < D4b) {                // chunks of columns 0 .. d: latent terms and the visual bias
+          if (c < D4) tu[q] = ur[K4 + c];
+          dt[q] = sg_diff4(T, si, sj, c);
+          if (c == (d >> 2)) {               // column d: theta_i[d] - theta_j[d] = the visual-bias difference
+            const int e_ = d & 3;
+            vb = e_ == 0 ? dt[q].x : (e_ == 1 ? dt[q].y : (e_ == 2 ? dt[q].z : dt[q].w));
+          }
+          const int n0 = 4 * c;      // columns >= d of the chunk are not latent terms
+          if (n0 >= d) { tu[q].x = 0.f; dt[q].x = 0.f; }
           if (n0 + 1 >= d) { tu[q].y = 0.f; dt[q].y = 0.f; }
           if (n0 + 2 >= d) { tu[q].z = 0.f; dt[q].z = 0.f; }
           if (n0 + 3 >= d) { tu[q].w = 0.f; dt[q].w = 0.f; }
@@ -553,7 +577,6 @@ k_score_grad_v4(FvxModel M, const int32_t* __restrict__ user, int B, int loss_sl
       }
       bi = M.items.w[(size_t)li * Si + K];
       bj = M.items.w[(size_t)lj * Si + K];
-      vb = vis ? T.at(si, d) - T.at(sj, d) : 0.0f;
     } else {
 #pragma unroll
       for (int q = 0; q < MQ; ++q) { a[q] = z4; x[q] = z4; y[q] = z4; }
@@ -572,7 +595,8 @@ k_score_grad_v4(FvxModel M, const int32_t* __restrict__ user, int B, int loss_sl
       part += dot4(tu[q], dt[q]);
       sq += dot4(tu[q], tu[q]);
     }
-    const float xs = half_sum(part) + (bi - bj) + vb;
+    // the lane that holds column d hands the visual-bias difference to its half-warp (0 elsewhere: a sum does it)
+    const float xs = half_sum(part) + (bi - bj) + half_sum(vb);
     const float sqs = half_sum(sq);
     if (!dead) {
       const bool inside = (xs >= FVX_CLIP_LO) && (xs <= FVX_CLIP_HI);
@@ -848,7 +872,7 @@ int fvx_launch_score_grad(const FvxModel* m, const int32_t* user, int B, int los
   const int wnp = tc ? T.np : 0;
   const int wpitch = tc ? fvx_w_pitch(m) : 0;
   const int need = (m->K > m->d + 1 ? m->K : m->d + 1);
-  FVX_CHECK_ARG(need <= 256 && (wnp == 0 || wnp <= 256), "fvx_bpr_step: K=%d / d=%d too large for the score kernel",
+  FVX_CHECK_ARG(need <= 288 && (wnp == 0 || wnp <= 256), "fvx_bpr_step: K=%d / d=%d too large for the score kernel",
                 m->K, m->d);
   const int wcols = wnp > 0 ? wnp : m->de;
   if (m->K % 4 == 0 && m->K <= 256 && m->d <= 252 && wcols <= 256) {
@@ -872,8 +896,10 @@ int fvx_launch_score_grad(const FvxModel* m, const int32_t* user, int B, int los
     FVX_FAIL(-2, "fvx_bpr_step: the unique-row step needs K %% 4 == 0");
   } else if (need <= 64 && wnp <= 64) {
     k_score_grad<2><<<(int)g, SG_WARPS * 32, 0, st>>>(*m, user, B, loss_slot, T, wnp, wpitch);
-  } else {
+  } else if (need <= 256) {
     k_score_grad<8><<<(int)g, SG_WARPS * 32, 0, st>>>(*m, user, B, loss_slot, T, wnp, wpitch);
+  } else {      // BASELINE configs[4] with embed_d = 256: d + 1 = 257 columns
+    k_score_grad<9><<<(int)g, SG_WARPS * 32, 0, st>>>(*m, user, B, loss_slot, T, wnp, wpitch);
   }
   FVX_CHECK_LAUNCH("k_score_grad");
   return 0;

@@ -85,6 +85,8 @@ def _perturbed_oracle(P, F, batches, reg, lr, rel=2.0 ** -16, seed=7):
 @pytest.mark.parametrize("mode", ["dense", "deferred"])
 @pytest.mark.parametrize("K,d,D,B,fused", [(64, 20, 256, 512, False), (16, 64, 128, 96, False), (8, 5, 128, 33, False),
                                              (32, 20, 2048, 1024, False),
+                                             (256, 20, 4096, 512, False),     # BASELINE configs[4]: K = 256, 4096-d features
+                                             (256, 255, 4096, 96, False),     # ... and the widest tensor-core operand (NP = 256)
                                              # single-pass cluster kernel (fvx_step_fused.cu): whole tiles, a ragged
                                              # last tile, fewer triples than one tile, the narrow slice (D = 1024)
                                              (32, 20, 2048, 1024, True), (64, 20, 2048, 1000, True),
