@@ -323,7 +323,8 @@ def run_fvx(args):
     epochs_in_region = (args.steps * B) / max(data.num_train, 1)
     # 1 GPU, VBPR: rows+planes(+item claims), claims/catch-up, projection, score+grad, row update,
     # (coefficient planes: unique-row step), grad_E, E update
-    per_step = ((8 if uniq else 7) if D else 3) if world == 1 else (8 if D else 5)
+    merged = args.adam_mode == "deferred" and os.environ.get("FVX_STEP_MERGED_UPDATE", "1") != "0"
+    per_step = (((8 if uniq else 7) if D else 3) - (1 if merged and D else 0)) if world == 1 else (8 if D else 5)
     gpu_launches = args.steps * per_step + int(np.ceil(epochs_in_region)) * 2
 
     # ---- end to end through the reference-facing call: host batches in, float loss out ----
@@ -452,6 +453,32 @@ def run_fvx(args):
                                                      "user_slices: all-gather of the item operands" if world > 1 else ""),
                         "roofline": {"bound": "tensor", "achieved": tfl, "peak": tf_burst * world, "unit": "TFLOP/s",
                                      "frac": tfl / (tf_burst * world)}}
+
+    # ---- Evaluator.eval's device work: rank counts of two held-out items per user (validation + test)
+    if not args.no_eval and world == 1:
+        held = torch.randint(0, args.items, (args.users, 2), device=dev, dtype=torch.int32)
+        who = torch.arange(args.users, device=dev, dtype=torch.int32).repeat_interleave(2)
+        thr = e.score_pairs(who, held.reshape(-1).contiguous()).reshape(args.users, 2).contiguous()
+
+        def t_ms(fn, reps):
+            fn(); torch.cuda.synchronize()
+            a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                out = fn()
+            b2.record(); torch.cuda.synchronize()
+            return a.elapsed_time(b2) / reps, out
+
+        ms_new, c_new = t_ms(lambda: e.rank_counts(st["row_ptr"], st["col_sorted"], thr), 3)
+        ms_old, c_old = t_ms(lambda: e.score_topk(st["row_ptr"], st["col_sorted"], 1, thr_scores=thr)[2], 1)
+        fl = 2.0 * args.users * args.items * (K + d)
+        fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12            # CUDA-core fp32 FMA peak at the boost clock
+        line["eval"]["rank_counts"] = {
+            "what": "Evaluator.eval device work: #items scoring >= each of 2 held-out items per user, train items "
+                    "excluded (fvx_rank_counts, exact fp32 register-tiled sweep)",
+            "ms": ms_new, "users_per_s": args.users / ms_new * 1e3, "tflops_fp32": fl / (ms_new * 1e-3) / 1e12,
+            "frac_of_fp32_fma_peak": fl / (ms_new * 1e-3) / 1e12 / fp32_peak,
+            "ms_list_kernel": ms_old, "identical_counts": bool(torch.equal(c_new, c_old))}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         F_host = None

@@ -67,6 +67,7 @@ PROTOTYPES = {
     "fvx_project": (C.c_int, [_MP, _p, _p]),
     "fvx_predict_all": (C.c_int, [_MP, _p, _i32, _i32, _p, _p]),
     "fvx_score_topk": (C.c_int, [_MP, _p, _i32, _i32, _p, _p, _i32, _p, _p, _i32, _p, _p, _p]),
+    "fvx_rank_counts": (C.c_int, [_MP, _p, _i32, _i32, _p, _p, _i32, _p, _p, _p]),
     "fvx_score_topk_users": (C.c_int, [_MP, _p, _p, _i32, _p, _p, _i32, _p, _p, _p]),
     "fvx_eval_ws_query": (C.c_int, [_MP, _i32, C.POINTER(FvxEvalWs)]),
     "fvx_score_topk_tc": (C.c_int, [_MP, _p, _i32, _i32, _p, _p, _i32, _p, _p, C.POINTER(FvxEvalWs), _p]),

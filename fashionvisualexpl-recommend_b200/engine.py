@@ -328,6 +328,22 @@ class Engine:
              ptr(mask_col), k, ptr(ids), ptr(sc), n_thr, ptr(thr_scores), ptr(counts), stream_ptr())
         return (ids, sc, counts) if thr_scores is not None else (ids, sc)
 
+    def rank_counts(self, mask_row_ptr, mask_col, thr_scores, u0=0, u1=None):
+        """counts[u, t] = number of owned, non-masked items scoring >= thr_scores[u, t] (NaN: unused) for
+        users [u0,u1): the register-tiled sweep of fvx_rank_counts (at most 4 thresholds per launch)."""
+        u1 = self.U if u1 is None else u1
+        self.flush()
+        n, T = u1 - u0, thr_scores.shape[1]
+        counts = torch.zeros(n, T, dtype=torch.int32, device=self.device)
+        theta = self.theta()
+        for c0 in range(0, T, 4):
+            thr = thr_scores[:, c0:c0 + 4].contiguous()
+            out = torch.empty(n, thr.shape[1], dtype=torch.int32, device=self.device)
+            call("fvx_rank_counts", C.byref(self.struct()), ptr(theta), u0, u1, ptr(mask_row_ptr), ptr(mask_col),
+                 thr.shape[1], ptr(thr), ptr(out), stream_ptr())
+            counts[:, c0:c0 + 4] = out
+        return counts
+
     def _score_topk_view(self, view, mask_row_ptr, mask_col, k, u0, u1, tc):
         n = u1 - u0
         m, th = view["struct"], view["theta"]

@@ -10,7 +10,7 @@ per-user Python loops.
 
 The reference's candidate lists (all items minus train items, held-out items last,
 :36-79) are never materialised: the sweep counts, per held-out item, how many non-train
-items score >= it (``fvx_score_topk`` rank counts), and the metrics of ``_eval_by_user``
+items score >= it (``fvx_rank_counts``: a register-tiled sweep that keeps no lists), and the metrics of ``_eval_by_user``
 (:82-128) follow from those counts - position (:96-98), AUC (:100), top-K membership
 under ``heapq.nlargest``'s tie rule (held-out items come last, :104-114), nDCG (:119),
 precision (:122), recall (:125).
@@ -66,11 +66,7 @@ class Evaluator:
         users = torch.arange(U, dtype=torch.int32, device=e.device).repeat_interleave(T)
         sc = e.score_pairs(users, torch.clamp(Hd.reshape(-1), min=0).contiguous()).reshape(U, T)
         sc = torch.where(Hd >= 0, sc, torch.full_like(sc, float("nan")))
-        counts = torch.zeros(U, T, dtype=torch.int32, device=e.device)
-        for c0 in range(0, T, 4):
-            thr = sc[:, c0:c0 + 4].contiguous()
-            _, _, cnt = e.score_topk(st["row_ptr"], st["col_sorted"], 1, thr_scores=thr)
-            counts[:, c0:c0 + 4] = cnt
+        counts = e.rank_counts(st["row_ptr"], st["col_sorted"], sc.contiguous())
         return sc.cpu().numpy(), counts.cpu().numpy().astype(np.int64)
 
     def user_metrics(self):

@@ -220,6 +220,15 @@ int fvx_score_topk(const FvxModel* model, const float* theta_ext, int32_t u0, in
                    int32_t* out_ids, float* out_scores, int32_t n_thr, const float* thr_scores,
                    int32_t* out_counts, fvx_stream_t stream);
 
+/* Rank counts alone (Evaluator.py:96-98) - all Evaluator.eval needs: AUC, HR@k, nDCG@k, precision and
+ * recall follow from the position of each held-out item.  out_counts[(u-u0)*n_thr + t] = number of owned,
+ * non-masked items whose score is >= thr_scores[(u-u0)*n_thr + t] (NaN = unused), the same value
+ * fvx_score_topk returns (same fmaf chain, bit for bit), from a register-tiled sweep that keeps no
+ * candidate lists: 128 users x 128 items per CTA.  1 <= n_thr <= 4. */
+int fvx_rank_counts(const FvxModel* model, const float* theta_ext, int32_t u0, int32_t u1,
+                    const int64_t* mask_row_ptr, const int32_t* mask_col, int32_t n_thr,
+                    const float* thr_scores, int32_t* out_counts, fvx_stream_t stream);
+
 /* fvx_score_topk for an explicit list of n users (each in [0, num_users)): row j of the outputs
  * belongs to users[j].  The exact path for the rows fvx_score_topk_tc flags. */
 int fvx_score_topk_users(const FvxModel* model, const float* theta_ext, const int32_t* users, int32_t n,

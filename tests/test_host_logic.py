@@ -89,6 +89,10 @@ class _MockEngine:
         return out + (torch.from_numpy(cnt),) if cnt is not None else out
 
 
+    def rank_counts(self, row_ptr, col, thr_scores, u0=0, u1=None):
+        return self.score_topk(row_ptr, col, 1, thr_scores=thr_scores)[2]
+
+
 class _MockModel:
     def __init__(self, engine):
         self.engine = engine
