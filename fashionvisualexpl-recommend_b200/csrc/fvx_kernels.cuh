@@ -81,6 +81,9 @@ int fvx_launch_update(const FvxModel* m, int B, int parts, int gnp, const float*
 // the K split (the kernel derives the split from the list length like the projection does)
 int fvx_launch_score_grad(const FvxModel* m, const int32_t* user, int B, int loss_slot, int th_ks, cudaStream_t st,
                           int dedup = 0);
+// switches of the step (environment: FVX_STEP_DEDUP, FVX_STEP_MERGED_UPDATE; test hook fvx_debug_set_dedup)
+bool fvx_dedup_enabled();
+bool fvx_merged_update(const FvxModel* m);   // DEFERRED mode without the row-update kernel
 // W_sum -> bf16 planes of the listed rows (unique-row step)
 int fvx_launch_w_planes(const FvxModel* m, int B, cudaStream_t st);
 

@@ -978,7 +978,7 @@ extern "C" int fvx_debug_set_dedup(int on) {   // test hook, not part of fvx.h
   g_dedup = on ? 1 : 0;
   return old;
 }
-static bool dedup_enabled() {
+bool fvx_dedup_enabled() {
   if (g_dedup < 0) {
     const char* e = getenv("FVX_STEP_DEDUP");
     g_dedup = (e && atoi(e) == 0) ? 0 : 1;
@@ -1083,6 +1083,7 @@ static bool merged_update_enabled() {
   if (on < 0) { const char* e = getenv("FVX_STEP_MERGED_UPDATE"); on = (e && atoi(e) == 0) ? 0 : 1; }
   return on == 1;
 }
+bool fvx_merged_update(const FvxModel* m) { return m->adam_mode == FVX_ADAM_DEFERRED && merged_update_enabled(); }
 static int step_update(const FvxModel* m, bool merged, int B, int parts, int gnp, int loss_slot, cudaStream_t st,
                        int what) {
   if (merged) {
@@ -1135,7 +1136,7 @@ static int bpr_step_impl(const FvxModel* model, const int32_t* user, const int32
   // turns the sums into the bf16 planes grad_E reads.  At B = 65 536 on a 100 k catalog 2B slots are
   // ~58 k distinct rows: both contractions shrink by more than half.
   const bool dedup = tc && !fused && M.upos && M.W_sum && M.uslot && M.K % 4 == 0 && M.K <= 256 && M.d <= 252 && NP <= 256 &&
-                     dedup_enabled() && !(side && B >= g_pipe_min_batch);
+                     fvx_dedup_enabled() && !(side && B >= g_pipe_min_batch);
   if (dedup) {
     int ks_cap = 8;
     while (ks_cap > 1 && (long long)ks_cap * 2 * B * NP > M.th_cap) ks_cap >>= 1;

@@ -32,6 +32,7 @@ struct SsTheta {
   const float* p;
   int np, ks;
   long long ss;
+  int chunks, nsm;      // unique-row step: ks is a cap, the split follows the device-side row count
   __device__ __forceinline__ float at(long long slot, int n) const {
     const float* q = p + slot * np + n;
     float v = q[0];
@@ -86,10 +87,16 @@ __device__ __forceinline__ float4 ss_theta4(const SsTheta& T, long long slot, in
   return v;
 }
 
+// uniq != 0 (unique-row step): theta of a slot is row uslot[slot] of TH (one projection per DISTINCT owned row)
 __global__ void __launch_bounds__(SS_WARPS * 32)
 k_partial_scores_v4(FvxModel M, const int32_t* __restrict__ user, int B, SsTheta T, float* __restrict__ S,
-                    const int32_t* __restrict__ count) {
+                    const int32_t* __restrict__ count, int uniq) {
   const int Su = M.users.stride, Si = M.items.stride, K = M.K, d = M.d;
+  if (uniq) {
+    int nv = *M.items.count, sk;
+    if (nv > M.items.list_cap) nv = M.items.list_cap;
+    T.ks = fvx_tc_split_dyn((nv + 127) / 128, T.chunks, T.nsm, T.ks, T.nsm, &sk);
+  }
   const int K4 = K >> 2, D4 = (d + 3) >> 2;
   const int grp = threadIdx.x >> 4, sub = threadIdx.x & 15;
   const bool vis = M.D > 0;
@@ -112,16 +119,17 @@ k_partial_scores_v4(FvxModel M, const int32_t* __restrict__ user, int B, SsTheta
         const float4 a = ur[c], x = gi[c];
         part = fmaf(a.x, x.x, fmaf(a.y, x.y, fmaf(a.z, x.z, fmaf(a.w, x.w, part))));
       }
+      const long long tj = uniq ? (long long)M.uslot[slot] : j;
       if (vis)
         for (int c = sub; c < D4; c += 16) {
-          const float4 tu = ur[K4 + c], th = ss_theta4(T, j, c);
+          const float4 tu = ur[K4 + c], th = ss_theta4(T, tj, c);
           const int n0 = 4 * c;
           part = fmaf(tu.x, th.x, part);
           if (n0 + 1 < d) part = fmaf(tu.y, th.y, part);
           if (n0 + 2 < d) part = fmaf(tu.z, th.z, part);
           if (n0 + 3 < d) part = fmaf(tu.w, th.w, part);
         }
-      if (sub == 0) tail = M.items.w[(size_t)li * Si + K] + (vis ? T.at(j, d) : 0.0f);
+      if (sub == 0) tail = M.items.w[(size_t)li * Si + K] + (vis ? T.at(tj, d) : 0.0f);
     }
     const float s = ss_half_sum(part);
     if (live && sub == 0) S[slot] = s + tail;
@@ -272,11 +280,16 @@ __device__ __forceinline__ float4 ss_unpack_bf16x4(uint2 p) {
 __global__ void __launch_bounds__(SS_WARPS * 32)
 k_grads_owned(FvxModel M, const int32_t* __restrict__ user, int B, int loss_slot, SsTheta T, int wnp, int wpitch,
               const float* __restrict__ S, const int32_t* __restrict__ run_id, float* __restrict__ RU,
-              long long ru_rows, const int32_t* __restrict__ count) {
+              long long ru_rows, const int32_t* __restrict__ count, int uniq) {
   __shared__ double loss_sh[SS_WARPS * 2];
   const int Su = M.users.stride, Si = M.items.stride, K = M.K, d = M.d, de = M.de;
   const int K4 = K >> 2, D4 = (d + 3) >> 2;
   const int grp = threadIdx.x >> 4, sub = threadIdx.x & 15;     // 16 lanes per slot
+  if (uniq) {
+    int nv = *M.items.count, sk;
+    if (nv > M.items.list_cap) nv = M.items.list_cap;
+    T.ks = fvx_tc_split_dyn((nv + 127) / 128, T.chunks, T.nsm, T.ks, T.nsm, &sk);
+  }
   const float reg = M.reg, reg2 = 2.0f * M.reg;
   const bool vis = M.D > 0;
   const long long ng = (long long)gridDim.x * (SS_WARPS * 2);
@@ -285,7 +298,7 @@ k_grads_owned(FvxModel M, const int32_t* __restrict__ user, int B, int loss_slot
   const int32_t* crow = M.cmap;
   const int32_t* cslot = M.cmap + 2 * (size_t)M.max_batch;
   double loss_acc = 0.0;
-  if (blockIdx.x == 0 && wnp > 0) {
+  if (blockIdx.x == 0 && wnp > 0 && !uniq) {   // (unique-row step: k_w_planes writes the planes and clears the tail)
     // the last 32-row tile of the backward reads W rows past the owned ones: they must be zero
     const long long cap = 2LL * M.max_batch;
     for (long long i = threadIdx.x; i < 32LL * (wpitch >> 2); i += blockDim.x) {
@@ -317,6 +330,7 @@ k_grads_owned(FvxModel M, const int32_t* __restrict__ user, int B, int loss_slot
         const float4* gi = reinterpret_cast<const float4*>(M.items.w + (size_t)li * Si);
         float* gg = M.items.g + (size_t)li * Si;
         float* ru = RU + (size_t)run * Su;
+        const long long tj = uniq ? (long long)M.uslot[slot] : j;   // row of TH / of the coefficient sums
         for (int c = sub; c < K4; c += 16) {
           const float4 a = ur[c], x = gi[c];
           ss_red_add4(gg + 4 * c, make_float4(cs * a.x + reg2 * x.x, cs * a.y + reg2 * x.y, cs * a.z + reg2 * x.z,
@@ -337,7 +351,7 @@ k_grads_owned(FvxModel M, const int32_t* __restrict__ user, int B, int loss_slot
               if (n0 + 1 >= d) tu.y = 0.f;
               if (n0 + 2 >= d) tu.z = 0.f;
               if (n0 + 3 >= d) tu.w = 0.f;
-              float4 th = ss_at4(T, j, c);
+              float4 th = ss_at4(T, tj, c);
               if (n0 + 1 >= d) th.y = 0.f;
               if (n0 + 2 >= d) th.z = 0.f;
               if (n0 + 3 >= d) th.w = 0.f;
@@ -350,7 +364,9 @@ k_grads_owned(FvxModel M, const int32_t* __restrict__ user, int B, int loss_slot
             if (n0 + 1 == d) wv.y = cs;
             if (n0 + 2 == d) wv.z = cs;
             if (n0 + 3 == d) wv.w = cs;
-            if (wnp > 0) {
+            if (uniq) {            // the slots of one catalog row are summed: one backward row per distinct row
+              if (n0 <= d) ss_red_add4(M.W_sum + (size_t)tj * wnp + n0, wv);
+            } else if (wnp > 0) {
               const uint2 h = ss_pack_bf16x4(wv);
               const float4 hf = ss_unpack_bf16x4(h);
               const uint2 l = ss_pack_bf16x4(make_float4(wv.x - hf.x, wv.y - hf.y, wv.z - hf.z, wv.w - hf.w));
@@ -440,7 +456,23 @@ static SsTheta make_theta(const FvxModel* m, int B, int ks) {
   T.np = tc ? fvx_tc_np(m->de) : m->de;
   T.ks = tc ? ks : 1;
   T.ss = 2LL * B * T.np;
+  T.chunks = m->D > 0 ? m->D / 64 : 1;
+  T.nsm = fvx_num_sms();
   return T;
+}
+
+// Unique-row step on a shard (see fvx_train.cu): with R ranks a rank owns I/R catalog rows but 2B_global/R
+// slots - at 8 ranks ~131 k slots over 12.5 k rows - so projecting each DISTINCT owned row once shrinks both
+// contractions by the duplication factor.  Needs the tensor-core path, K % 4 == 0 and the scratch
+// (upos, W_sum, uslot); FVX_STEP_DEDUP=0 turns it off.
+static bool sharded_uniq(const FvxModel* m) {
+  return m->D > 0 && m->use_tensor_cores && m->upos && m->W_sum && m->uslot && m->K % 4 == 0 &&
+         fvx_tc_np(m->de) <= 256 && fvx_dedup_enabled();
+}
+static int uniq_ks_cap(const FvxModel* m, int B) {
+  int ks_cap = 8;
+  while (ks_cap > 1 && (long long)ks_cap * 2 * B * fvx_tc_np(m->de) > m->th_cap) ks_cap >>= 1;
+  return ks_cap;
 }
 
 static inline int ss_grid(long long warps_needed) {
@@ -461,12 +493,22 @@ int fvx_bpr_step_sharded_a(const FvxModel* model, const int32_t* user, const int
   // The projection needs only the slot rows and the planes of E_ext^T: the claims and the
   // deferred-Adam catch-up of the touched rows run beside it on the side stream (joined before the
   // partial scores read the tables).
-  cudaStream_t side = M.D > 0 ? fvx_side_begin(st) : nullptr;
-  if (side) {
-    if (int rc = fvx_launch_prep(&M, user, pos, neg, B, side, FVX_PREP_CLAIMS)) return rc;
-    if (int rc = fvx_launch_prep(&M, user, pos, neg, B, st, FVX_PREP_ROWS)) return rc;
+  const bool uniq = sharded_uniq(&M);
+  cudaStream_t side = nullptr;
+  if (uniq) {
+    // slot rows + claims of the owned rows (list positions in upos) ahead of the projection; user claims,
+    // catch-up and the slots' list positions (uslot) beside it
+    if (int rc = fvx_launch_prep(&M, user, pos, neg, B, st, FVX_PREP_UNIQ)) return rc;
+    side = fvx_side_begin(st);
+    if (int rc = fvx_launch_prep(&M, user, pos, neg, B, side ? side : st, FVX_PREP_CLAIMS_LISTED)) return rc;
   } else {
-    if (int rc = fvx_launch_prep(&M, user, pos, neg, B, st)) return rc;
+    side = M.D > 0 ? fvx_side_begin(st) : nullptr;
+    if (side) {
+      if (int rc = fvx_launch_prep(&M, user, pos, neg, B, side, FVX_PREP_CLAIMS)) return rc;
+      if (int rc = fvx_launch_prep(&M, user, pos, neg, B, st, FVX_PREP_ROWS)) return rc;
+    } else {
+      if (int rc = fvx_launch_prep(&M, user, pos, neg, B, st)) return rc;
+    }
   }
   // compact list of the owned slots; foreign entries of crow stay -1 (the fp32 kernels skip them)
   int32_t* count = M.sync + 1;
@@ -478,8 +520,11 @@ int fvx_bpr_step_sharded_a(const FvxModel* model, const int32_t* user, const int
     k_compact_owned<<<(int)g, 256, 0, st>>>(M, B, count);
     FVX_CHECK_LAUNCH("k_compact_owned");
   }
-  const int ks = sharded_ks(&M, B);
-  if (M.D > 0) {
+  const int ks = uniq ? uniq_ks_cap(&M, B) : sharded_ks(&M, B);
+  if (uniq) {
+    FVX_CHECK_ARG(2LL * B * fvx_tc_np(M.de) <= M.th_cap, "fvx_bpr_step_sharded_a: TH scratch too small");
+    if (int rc = fvx_launch_project_tc(&M, M.items.list, 0, 2 * B, ks, M.TH, st, M.items.count, 1)) return rc;
+  } else if (M.D > 0) {
     if (M.use_tensor_cores) {
       FVX_CHECK_ARG((long long)ks * 2 * B * fvx_tc_np(M.de) <= M.th_cap, "fvx_bpr_step_sharded_a: TH scratch too small");
       // (the W rows past the owned ones, read by the last backward tile, are zeroed by phase B)
@@ -491,7 +536,7 @@ int fvx_bpr_step_sharded_a(const FvxModel* model, const int32_t* user, const int
   }
   if (side) fvx_side_join(st);
   if (M.K % 4 == 0)
-    k_partial_scores_v4<<<ss_grid(B), SS_WARPS * 32, 0, st>>>(M, user, B, make_theta(&M, B, ks), S, count);
+    k_partial_scores_v4<<<ss_grid(B), SS_WARPS * 32, 0, st>>>(M, user, B, make_theta(&M, B, ks), S, count, uniq ? 1 : 0);
   else
     k_partial_scores<<<ss_grid(2LL * B), SS_WARPS * 32, 0, st>>>(M, user, B, make_theta(&M, B, ks), S, count);
   FVX_CHECK_LAUNCH("k_partial_scores");
@@ -508,14 +553,18 @@ int fvx_bpr_step_sharded_b1(const FvxModel* model, const int32_t* user, int32_t 
   cudaStream_t st = fvx_cu(stream);
   if (cudaMemsetAsync(RU, 0, sizeof(float) * ru_rows * M.users.stride, st) != cudaSuccess)
     FVX_FAIL(-3, "fvx_bpr_step_sharded_b: memset failed");
-  const int ks = sharded_ks(&M, B);
+  const bool uniq = sharded_uniq(&M);
+  const int ks = uniq ? uniq_ks_cap(&M, B) : sharded_ks(&M, B);
   const bool tc = M.D > 0 && M.use_tensor_cores;
   if (M.K % 4 == 0) {
     // one warp per owned slot: the work does not grow with the number of ranks
     k_grads_owned<<<ss_grid(B), SS_WARPS * 32, 0, st>>>(M, user, B, loss_slot, make_theta(&M, B, ks),
                                                               tc ? fvx_tc_np(M.de) : 0, tc ? fvx_w_pitch(&M) : 0, S,
-                                                              run_id, RU, (long long)ru_rows, M.sync + 1);
+                                                              run_id, RU, (long long)ru_rows, M.sync + 1, uniq ? 1 : 0);
     FVX_CHECK_LAUNCH("k_grads_owned");
+    if (uniq) {
+      if (int rc = fvx_launch_w_planes(&M, B, st)) return rc;
+    }
   } else {
     if (tc) {   // W rows past the owned ones must read as zero in the last backward tile
       const int np = fvx_tc_np(M.de), pitch = fvx_w_pitch(&M);
@@ -538,7 +587,9 @@ int fvx_bpr_step_sharded_b2(const FvxModel* model, int32_t B, float* dE, fvx_str
   cudaStream_t st = fvx_cu(stream);
   const bool tc = M.use_tensor_cores;
   int parts = 0;
-  if (tc) {
+  if (tc && sharded_uniq(&M)) {
+    if (int rc = fvx_launch_grad_E_tc(&M, M.items.list, 2 * B, &parts, st, M.items.count)) return rc;
+  } else if (tc) {
     if (int rc = fvx_launch_grad_E_tc(&M, M.cmap, 2 * B, &parts, st, M.sync + 1)) return rc;
   } else {
     if (int rc = fvx_launch_grad_E(&M, M.cmap, 2 * B, &parts, st)) return rc;
@@ -568,7 +619,9 @@ int fvx_bpr_step_sharded_c(const FvxModel* model, const int32_t* user, int32_t B
   FVX_CHECK_LAUNCH("k_scatter_runs");
   // loss_slot < 0: the E term of the loss (VBPR.py:129) is not added (ranks other than 0, so that
   // the per-rank losses sum to the batch loss)
-  return fvx_launch_update(&M, B, M.D > 0 ? 1 : 0, M.de, dE, loss_slot, st);
+  // DEFERRED: the touched rows keep their gradient and take the step when they are next needed (replay_row)
+  return fvx_launch_update(&M, B, M.D > 0 ? 1 : 0, M.de, dE, loss_slot, st,
+                           fvx_merged_update(&M) ? FVX_UPD_E : FVX_UPD_ALL);
 }
 
 }  // extern "C"

@@ -98,10 +98,10 @@ class Engine:
                 th_rows = max(4 * 2 * self.max_batch, 1 << 17)
                 self.TH = torch.zeros(th_rows, self.NP, **f32)
                 self.W = None
-                # unique-row step (one rank): each distinct catalog row of a batch is projected once;
+                # unique-row step: each distinct (owned) catalog row of a batch is projected once;
                 # upos = position of a row in the touched-row list, W_sum = per-row sums of the
                 # backward coefficients (zero between steps).  unique_rows=False: one projection per slot.
-                if unique_rows and not self.item_lo and self.Ic == self.I:
+                if unique_rows:
                     self.upos_t = torch.zeros(self.Ic, **i32)
                     self.W_sum = torch.zeros(2 * self.max_batch, self.NP, **f32)
                     self.uslot_t = torch.zeros(2 * self.max_batch, **i32)
