@@ -113,6 +113,7 @@ class BPRMF(RecommenderModel):
             for k in ("w", "m", "v", "last"):
                 t[k].copy_(sd["%s.%s" % (name, k)])
             t["mark"].zero_()          # touch stamps are relative to the (restored) step counter
+            t["g"].zero_()             # a checkpoint is taken after a flush: no pending gradient goes with it
         if e.D:
             e.E.copy_(sd["E"]); e.mE.copy_(sd["mE"]); e.vE.copy_(sd["vE"])
         e._theta_step = -1

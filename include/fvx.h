@@ -35,9 +35,13 @@ typedef void* fvx_stream_t; /* cudaStream_t */
 /* Adam semantics.  The reference's Keras Adam moves
  * EVERY row of an embedding table on every step (rows without gradient keep
  * moving on momentum).  DENSE reproduces that literally with a whole-table sweep;
- * DEFERRED gives the same result (to fp32 rounding) by replaying the skipped
- * zero-gradient steps of a row when it is next touched; LAZY skips untouched rows
- * (NOT reference semantics - a labelled fast mode). */
+ * DEFERRED gives the same result (to fp32 rounding) lazily: a row is brought up to
+ * date only when it is next needed (the next step that touches it, or fvx_adam_flush).
+ * Up to date means: first the Adam step of the batch that last touched it - that
+ * batch's gradient stays in `g` until then, the step has no separate row-update
+ * kernel - then the zero-gradient steps it skipped since.  `w` of a touched row is
+ * therefore STALE between steps: call fvx_adam_flush before reading the tables.
+ * LAZY skips untouched rows (NOT reference semantics - a labelled fast mode). */
 enum { FVX_ADAM_DENSE = 0, FVX_ADAM_DEFERRED = 1, FVX_ADAM_LAZY = 2 };
 
 /* One embedding table with its optimiser state, row-major, row stride `stride`
@@ -48,7 +52,8 @@ typedef struct FvxTable {
   float* w;        /* [rows, stride] parameters                                   */
   float* m;        /* [rows, stride] Adam first moment                            */
   float* v;        /* [rows, stride] Adam second moment                           */
-  float* g;        /* [rows, stride] gradient accumulator, all-zero between steps */
+  float* g;        /* [rows, stride] gradient accumulator; DENSE / LAZY: all-zero between
+                      steps; DEFERRED: the pending gradient of step last+1 (zero after a flush) */
   int32_t* last;   /* [rows] step up to which the row is current (DEFERRED)       */
   int32_t* mark;   /* [rows] step at which the row was last marked as touched     */
   int32_t* list;   /* [list_cap] rows touched by the step in flight               */
@@ -193,8 +198,9 @@ int fvx_bpr_step_sharded_c(const FvxModel* model, const int32_t* user, int32_t B
                            const int32_t* run_id, const float* RU, int64_t ru_rows, const float* dE,
                            int32_t loss_slot, fvx_stream_t stream);
 
-/* DEFERRED mode: bring every row of both tables up to the current step (call
- * before reading parameters: evaluation, checkpoint, predict_all). */
+/* DEFERRED mode: bring every row of both tables up to the current step - pending
+ * gradient step, then the skipped zero-gradient steps (call before reading
+ * parameters: evaluation, checkpoint, predict_all).  Idempotent. */
 int fvx_adam_flush(const FvxModel* model, fvx_stream_t stream);
 
 /* ---- evaluation: replaces predict_all + the evaluator's host loops ------------- */
