@@ -58,6 +58,7 @@ PROTOTYPES = {
     "fvx_sample_negatives": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _u64, _u64, _p]),
     "fvx_bpr_step": (C.c_int, [_MP, _p, _p, _p, _i32, _i32, _p]),
     "fvx_bpr_step_timed": (C.c_int, [_MP, _p, _p, _p, _i32, _i32, C.POINTER(C.c_float), _p]),
+    "fvx_run_ids": (C.c_int, [_p, _i64, _p, _p, _p]),
     "fvx_bpr_step_sharded_a": (C.c_int, [_MP, _p, _p, _p, _i32, _p, _p]),
     "fvx_bpr_step_sharded_b": (C.c_int, [_MP, _p, _i32, _p, _p, _p, _i64, _p, _i32, _p]),
     "fvx_bpr_step_sharded_b1": (C.c_int, [_MP, _p, _i32, _p, _p, _p, _i64, _i32, _p]),

@@ -428,6 +428,79 @@ __global__ void k_scatter_runs(FvxModel M, const int32_t* __restrict__ user, int
   }
 }
 
+// run_id[b] = (number of positions <= b where user[b] != user[b-1]) - 1, i.e. the index of the run of
+// equal users triple b belongs to.  Two launches: run starts per 4096-element block, then every block
+// adds up the counts of the blocks before it (<= 256 values) and scans its own elements.
+#define RI_THREADS 256
+#define RI_PER 16
+__global__ void __launch_bounds__(RI_THREADS)
+k_run_count(const int32_t* __restrict__ user, long long n, int32_t* __restrict__ part) {
+  __shared__ int sh[RI_THREADS / 32];
+  const long long base = (long long)blockIdx.x * RI_THREADS * RI_PER;
+  int c = 0;
+  for (int e = 0; e < RI_PER; ++e) {
+    const long long b = base + (long long)e * RI_THREADS + threadIdx.x;      // coalesced
+    if (b < n) c += (b == 0 || user[b] != user[b - 1]) ? 1 : 0;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < RI_THREADS / 32; ++w) t += sh[w];
+    part[blockIdx.x] = t;
+  }
+}
+__global__ void __launch_bounds__(RI_THREADS)
+k_run_write(const int32_t* __restrict__ user, long long n, const int32_t* __restrict__ part,
+            int32_t* __restrict__ run_id) {
+  __shared__ int sh[RI_THREADS / 32];
+  __shared__ int carry;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int q = 0; q < (int)blockIdx.x; ++q) t += part[q];
+    carry = t;
+  }
+  __syncthreads();
+  const long long base = (long long)blockIdx.x * RI_THREADS * RI_PER;
+  for (int e = 0; e < RI_PER; ++e) {                      // 256 consecutive elements per round
+    const long long b = base + (long long)e * RI_THREADS + threadIdx.x;
+    const int f = (b < n && (b == 0 || user[b] != user[b - 1])) ? 1 : 0;
+    int x = f;                                            // inclusive scan of the round
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) sh[warp] = x;
+    __syncthreads();
+    int off = carry;
+    for (int w = 0; w < warp; ++w) off += sh[w];
+    if (b < n) run_id[b] = off + x - 1;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int t = carry;
+      for (int w = 0; w < RI_THREADS / 32; ++w) t += sh[w];
+      carry = t;
+    }
+    __syncthreads();
+  }
+}
+
+extern "C" int fvx_run_ids(const int32_t* user, int64_t n, int32_t* run_id, int32_t* scratch, fvx_stream_t stream) {
+  FVX_CHECK_ARG(user && run_id && scratch && n >= 0, "fvx_run_ids: bad arguments");
+  if (n == 0) return 0;
+  const long long nb = (n + RI_THREADS * RI_PER - 1) / (RI_THREADS * RI_PER);
+  FVX_CHECK_ARG(nb <= 4096, "fvx_run_ids: n=%lld too large", (long long)n);
+  cudaStream_t st = fvx_cu(stream);
+  k_run_count<<<(int)nb, RI_THREADS, 0, st>>>(user, n, scratch);
+  k_run_write<<<(int)nb, RI_THREADS, 0, st>>>(user, n, scratch, run_id);
+  FVX_CHECK_LAUNCH("k_run_ids");
+  return 0;
+}
+
 static int sharded_common(const FvxModel* m, const int32_t* user, int B, const char* who) {
   if (int rc = fvx_check_model(m, who)) return rc;
   FVX_CHECK_ARG(user != nullptr && B >= 1 && B <= m->max_batch, "%s: bad batch", who);

@@ -110,7 +110,8 @@ class ShardedStep:
         self.S = [torch.zeros(2 * B, dtype=torch.float32, device=dv) for _ in self.engines]
         self.RU = [torch.zeros(self.max_runs, e.Su, dtype=torch.float32, device=dv) for _ in self.engines]
         self.dE = [torch.zeros(e.D, e.de, dtype=torch.float32, device=dv) if e.D else None for _ in self.engines]
-        self._side = None
+        self.rid = torch.zeros(B, dtype=torch.int32, device=dv)
+        self.rid_scratch = torch.zeros(B // 4096 + 2, dtype=torch.int32, device=dv)
 
     def _rank_of(self, i):
         return self.group.rank if self.group.rank is not None else i
@@ -118,19 +119,13 @@ class ShardedStep:
     def step(self, user, pos, neg, loss_slot=0):
         """One optimiser step on every (local) rank; asynchronous apart from the collectives."""
         B = user.numel()
-        # the run ids (a handful of small torch kernels) are needed from phase B on: computed on a
-        # side stream while phase A runs
-        cur = torch.cuda.current_stream()
-        if self._side is None:
-            self._side = torch.cuda.Stream(device=user.device)
-        self._side.wait_stream(cur)
-        with torch.cuda.stream(self._side):
-            rid = run_ids(user)
+        # run ids of the batch (needed from phase B on): two small launches through the C ABI - the step is
+        # ~20 host calls and every torch op saved shortens the launch-bound tail on a busy host
+        rid = self.rid[:B]
+        call("fvx_run_ids", ptr(user), B, ptr(rid), ptr(self.rid_scratch), stream_ptr())
         for e, S in zip(self.engines, self.S):
             call("fvx_bpr_step_sharded_a", C.byref(e.struct()), ptr(user), ptr(pos), ptr(neg), B, ptr(S), stream_ptr())
         self.group.all_reduce(self.S)
-        cur.wait_stream(self._side)
-        rid.record_stream(cur)
         for e, S, RU in zip(self.engines, self.S, self.RU):
             call("fvx_bpr_step_sharded_b1", C.byref(e.struct()), ptr(user), B, ptr(S), ptr(rid), ptr(RU), RU.shape[0],
                  loss_slot, stream_ptr())

@@ -183,6 +183,8 @@ int fvx_bpr_step_timed(const FvxModel* model, const int32_t* user, const int32_t
  *   in batch order); RU has ru_rows >= number of runs rows of users.stride floats. */
 int fvx_bpr_step_sharded_a(const FvxModel* model, const int32_t* user, const int32_t* pos,
                            const int32_t* neg, int32_t B, float* S, fvx_stream_t stream);
+/* run_id of a batch (see above) in two small launches; scratch: >= n / 4096 + 1 int32. */
+int fvx_run_ids(const int32_t* user, int64_t n, int32_t* run_id, int32_t* scratch, fvx_stream_t stream);
 int fvx_bpr_step_sharded_b(const FvxModel* model, const int32_t* user, int32_t B, const float* S,
                            const int32_t* run_id, float* RU, int64_t ru_rows, float* dE,
                            int32_t loss_slot, fvx_stream_t stream);

@@ -98,3 +98,17 @@ def test_sharded_topk_equals_single_rank(R):
         ids2 = torch.cat([a for a, _ in sl])
         sc2 = torch.cat([b for _, b in sl])
         assert ids2.shape[0] == U and torch.equal(ids2, ids1) and torch.equal(sc2, sc1), tc
+
+
+@pytest.mark.parametrize("n", [1, 31, 256, 4096, 4097, 70001, 262144])
+def test_run_ids_kernel_equals_torch(n):
+    """fvx_run_ids (two launches) against the torch restatement the CPU test pins."""
+    from fvx import _lib
+    from fvx.parallel import run_ids
+    g = torch.Generator().manual_seed(n)
+    lens = torch.randint(1, 9, (n,), generator=g)
+    user = torch.repeat_interleave(torch.randint(0, 50, (n,), generator=g), lens)[:n].to(torch.int32).cuda()
+    out = torch.full((n,), -7, dtype=torch.int32, device="cuda")
+    scratch = torch.zeros(n // 4096 + 2, dtype=torch.int32, device="cuda")
+    _lib.call("fvx_run_ids", _lib.ptr(user), n, _lib.ptr(out), _lib.ptr(scratch), _lib.stream_ptr())
+    assert torch.equal(out, run_ids(user))
