@@ -260,6 +260,13 @@ class Engine:
             self.loss_t[slot] = 0
         return v
 
+    def take_loss(self, slot=0):
+        """The loss accumulated in ``slot`` as a 1-element device tensor; the accumulator is cleared
+        (all stream-ordered, no synchronisation)."""
+        out = self.loss_t[slot:slot + 1].clone()
+        self.loss_t[slot:slot + 1].zero_()
+        return out
+
     # ---- evaluation ----------------------------------------------------------------------
     def theta(self, refresh=False):
         """theta_ext = F * E_ext over the owned catalog rows, cached per optimiser step."""
@@ -392,6 +399,61 @@ class Engine:
             ws["struct"] = q
             setattr(self, key, ws)
         return ws
+
+
+class HostStepper:
+    """Host batches in, one loss per step out, with one step in flight.
+
+    The reference returns ``float(loss)`` from every ``train_step`` (BPRMF.py:125), i.e. the host waits
+    for the device once per step and the device then waits for the host to stage the next batch.  This
+    helper keeps that contract - one host batch uploaded and one loss read back per step - but
+    pipelines it: the upload of batch s+1 (copy stream, double-buffered device slots) and the launch of
+    step s+1 are issued before the host blocks on the loss of step s.
+
+        st = HostStepper(engine.step, loss_of, B, device)     # or ShardedStep.step
+        st.submit(batch)        # batch: pinned int32 [3, B] host tensor (user, pos, neg)
+        loss = st.collect()     # loss of the oldest uncollected step (blocks on that step only)
+
+    ``loss_of(slot)`` returns a 1-element device tensor with the step's loss (for an item-sharded step:
+    after the all-reduce of the per-rank parts) and may clear the accumulator."""
+
+    def __init__(self, step_fn, loss_of, max_batch, device, depth=2):
+        self.step_fn, self.loss_of, self.depth = step_fn, loss_of, int(depth)
+        self.device = torch.device(device)
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.dev = [torch.empty(3, max_batch, dtype=torch.int32, device=self.device) for _ in range(self.depth)]
+        self.loss_host = [torch.zeros(1, dtype=torch.float64).pin_memory() for _ in range(self.depth)]
+        self.copied = [torch.cuda.Event() for _ in range(self.depth)]
+        self.done = [torch.cuda.Event() for _ in range(self.depth)]
+        self.n_submitted = self.n_collected = 0
+
+    def pending(self):
+        return self.n_submitted - self.n_collected
+
+    def submit(self, host_batch):
+        if self.pending() >= self.depth:
+            raise RuntimeError("HostStepper: collect() before submitting more than %d steps" % self.depth)
+        i = self.n_submitted % self.depth
+        B = host_batch.shape[1]
+        cur = torch.cuda.current_stream(self.device)
+        buf = self.dev[i][:, :B]
+        with torch.cuda.stream(self.copy_stream):
+            # slot i was last read by step n_submitted - depth, whose `done` event the host has waited for
+            buf.copy_(host_batch, non_blocking=True)
+            self.copied[i].record(self.copy_stream)
+        cur.wait_event(self.copied[i])
+        self.step_fn(buf[0], buf[1], buf[2], loss_slot=i)
+        self.loss_host[i].copy_(self.loss_of(i), non_blocking=True)
+        self.done[i].record(cur)
+        self.n_submitted += 1
+
+    def collect(self):
+        if self.pending() <= 0:
+            raise RuntimeError("HostStepper: nothing to collect")
+        i = self.n_collected % self.depth
+        self.done[i].synchronize()
+        self.n_collected += 1
+        return float(self.loss_host[i].item())
 
 
 def topk_merge(ids, scores):

@@ -140,6 +140,18 @@ class ShardedStep:
             call("fvx_bpr_step_sharded_c", C.byref(e.struct()), ptr(user), B, ptr(rid), ptr(RU), RU.shape[0],
                  ptr(dE), loss_slot if self._rank_of(i) == 0 else -1, stream_ptr())
 
+    def take_loss(self, slot=0):
+        """Batch loss (sum of the per-rank parts) as a 1-element device tensor of the first local rank;
+        the accumulators are cleared.  Stream-ordered, no host synchronisation (run overflow is reported
+        by ``read_loss`` / ``check_runs``)."""
+        parts = [e.take_loss(slot) for e in self.engines]
+        self.group.all_reduce(parts)
+        return parts[0]
+
+    def check_runs(self):
+        if any(int(e.sync_t[2].item()) for e in self.engines):
+            raise _lib.FvxError("a batch had more runs of equal users than max_runs=%d" % self.max_runs)
+
     def read_loss(self, slot=0, clear=True):
         """Batch loss = sum of the per-rank partial losses (synchronises)."""
         if any(int(e.sync_t[2].item()) for e in self.engines):
