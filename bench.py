@@ -213,10 +213,10 @@ def run_reference(args):
 
 def workload_config(args, n):
     return {"workload": "VBPR train step, K=%d d=%d D=%d, %d users x %d items (BASELINE configs[1]), "
-                        "B=%d triples/step per GPU, on-device Philox sampler, %s Adam%s"
+                        "B=%d triples/step per GPU, on-device Philox sampler, %s Adam%s%s"
                         % (args.embed_k, args.embed_d, args.feat_dim, args.users, args.items, args.batch,
-                           args.adam_mode + (", unique-row projection" if n == 1 and args.tensor_cores and args.unique_rows
-                                             else ""),
+                           args.adam_mode,
+                           ", each distinct catalog row of a batch projected once" if args.tensor_cores and args.unique_rows else "",
                            "" if n == 1 else "; weak scaling: 40 000 users and one batch per GPU"),
             "users": args.users, "items": args.items, "K": args.embed_k, "d": args.embed_d, "D": args.feat_dim,
             "batch": args.batch * n, "adam_mode": args.adam_mode, "tensor_cores": bool(args.tensor_cores),
