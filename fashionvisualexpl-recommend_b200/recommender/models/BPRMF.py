@@ -64,13 +64,19 @@ class BPRMF(RecommenderModel):
         if D:
             self.engine.set_features(features)
 
-    # the reference's variables, as live views into the packed device tables
+    # the reference's variables, as live views into the packed device tables.  In the default DEFERRED
+    # Adam mode rows are brought up to date lazily, so every read flushes first:
+    # what the caller sees is what a tf.Variable of the reference would hold after the same steps
+    def _current(self):
+        self.engine.flush()
+        return self.engine
+
     @property
-    def Bi(self): return self.engine.Bi
+    def Bi(self): return self._current().Bi
     @property
-    def Gu(self): return self.engine.Gu
+    def Gu(self): return self._current().Gu
     @property
-    def Gi(self): return self.engine.Gi
+    def Gi(self): return self._current().Gi
 
     def _idx(self, x):
         return self.engine._i32(x, self.engine.device)

@@ -33,7 +33,7 @@ class VBPR(BPRMF, VisualLoader):
         self.optimizer = _Optimizer(self.engine)
 
     @property
-    def Tu(self): return self.engine.Tu
+    def Tu(self): return self._current().Tu
     @property
     def E(self): return self.engine.Ew
     @property
