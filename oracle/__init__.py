@@ -12,6 +12,9 @@ What it restates (all citations relative to the reference tree, see SURVEY.md §
 * ``oracle.bpr``       - BPRMF / VBPR forward, loss, closed-form gradients and the
                          Keras-Adam update (``src/recommender/models/BPRMF.py:55-125``,
                          ``src/recommender/models/VBPR.py:59-144``).
+* ``oracle.gradfashion`` - the GradFashion linear variant (two-stage visual projection of colour and edge
+                         descriptors, ``src/recommender/models/GradFashion.py:81-190,304-320``): the next
+                         model family on the path; pinned, no CUDA path yet.
 * ``oracle.sampler``   - the host triple sampler (``src/dataset/dataset.py:83-114``)
                          in the reference's own RNG streams, plus the counter-based
                          Philox sampler the device path implements.

@@ -93,6 +93,10 @@ def matmul(a, b, transpose_b=False):
     return TFTensor(_t(a) @ (b.t() if transpose_b else b))
 
 
+def concat(values, axis=0):
+    return TFTensor(torch.cat([_t(v) for v in values], dim=axis))
+
+
 def clip_by_value(x, lo, hi):
     return TFTensor(torch.clamp(_t(x), lo, hi))
 
@@ -222,6 +226,7 @@ def install():
     tf.reduce_sum = reduce_sum
     tf.matmul = matmul
     tf.clip_by_value = clip_by_value
+    tf.concat = concat
     tf.GradientTape = GradientTape
     tf.nn = types.SimpleNamespace(embedding_lookup=_embedding_lookup, softplus=_softplus,
                                   l2_loss=_l2_loss)

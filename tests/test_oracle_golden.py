@@ -121,3 +121,46 @@ def test_philox_negatives_never_in_train_and_deterministic():
     assert (0 <= neg).all() and (neg < I).all()
     again = sampler.philox_negatives(row_ptr, col_sorted, users[7:], I, seed=5, offset=107)
     assert (again == neg[7:]).all()
+
+
+def test_gradfashion_oracle_matches_reference_model_code():
+    """oracle/gradfashion.py against the reference's own GradFashion.py (call, train_step, predict_all)
+    run over the tensorflow shim (tests/golden/make_golden_gradfashion.py): the two-stage visual
+    projection v_i = [Fc Ec | Fe Ee], its regulariser (no /10 on the negative bias, unlike VBPR) and the
+    closed-form gradients of all eight variables."""
+    from oracle import gradfashion as gf
+    g = golden("gradfashion_ref.npz")
+    names = ["Bi", "Gu", "Gi", "Ec", "Ee", "Tu", "E", "Bp"]
+    lr, reg = float(g["hyper"][0]), float(g["hyper"][1])
+    Fc, Fe = g["Fc"].astype(np.float32), g["Fe"].astype(np.float32)
+    P = {k: g["init_" + k].astype(np.float32).copy() for k in names}
+    assert rel_err(gf.score(P, g["users"][0], g["pos"][0], Fc, Fe), g["call_x0"]) < 1e-5
+    S = bpr.init_adam(P)
+    for s in range(len(g["losses"])):
+        loss = gf.train_step(P, S, (g["users"][s], g["pos"][s], g["neg"][s]), reg, lr, Fc, Fe)
+        assert loss == pytest.approx(float(g["losses"][s]), rel=1e-5), s
+        if s == 0:
+            for k in names:
+                assert rel_err(P[k].reshape(g["step1_" + k].shape), g["step1_" + k]) < 1e-4, k
+    for k in names:
+        assert rel_err(P[k].reshape(g["final_" + k].shape), g["final_" + k]) < 1e-4, k
+    assert rel_err(gf.predict_all(P, Fc, Fe), g["predict_all_final"]) < 1e-4
+    # gradients against central differences in float64 on one batch (independent of the shim's autodiff)
+    P64 = {k: g["init_" + k].astype(np.float64).copy() for k in names}
+    b = (g["users"][0], g["pos"][0], g["neg"][0])
+    _, G, _ = gf.loss_and_grads(P64, b, reg, Fc.astype(np.float64), Fe.astype(np.float64))
+    rng = np.random.default_rng(0)
+    for k in ("Ec", "Ee", "E", "Bp", "Tu", "Gi"):
+        idx = tuple(rng.integers(0, n) for n in P64[k].shape)
+        if k in ("Tu",):
+            idx = (int(b[0][0]),) + idx[1:]
+        if k in ("Gi",):
+            idx = (int(b[1][0]),) + idx[1:]
+        h = 1e-6
+        old = P64[k][idx]
+        P64[k][idx] = old + h
+        lp = gf.loss_and_grads(P64, b, reg, Fc.astype(np.float64), Fe.astype(np.float64))[0]
+        P64[k][idx] = old - h
+        lm = gf.loss_and_grads(P64, b, reg, Fc.astype(np.float64), Fe.astype(np.float64))[0]
+        P64[k][idx] = old
+        assert G[k][idx] == pytest.approx((lp - lm) / (2 * h), rel=1e-5, abs=1e-8), (k, idx)
