@@ -46,6 +46,8 @@ k_rank_counts(FvxModel M, const float* __restrict__ theta, int u0, int u1, int n
   float4* As = reinterpret_cast<float4*>(rc_smem);                 // [RC_KQB][RC_PITCH]
   float4* Bs = As + RC_KQB * RC_PITCH;                             // [RC_KQB][RC_PITCH]
   float* bias = reinterpret_cast<float*>(Bs + RC_KQB * RC_PITCH);  // [2][RC_TI]: item bias (-inf: no such item), visual bias
+  float* thr_s = bias + 2 * RC_TI;                                 // [RC_TU][NT] thresholds of the unit's users (registers
+                                                                   // are what limits the main loop: see the b prefetch)
   const int K = M.K, d = M.d, de = M.de, Su = M.users.stride, Si = M.items.stride;
   const int KQ = (K + d + 3) >> 2;
   const int nkb = (KQ + RC_KQB - 1) / RC_KQB;
@@ -59,16 +61,16 @@ k_rank_counts(FvxModel M, const float* __restrict__ theta, int u0, int u1, int n
   for (int w = blockIdx.x; w < n_units; w += gridDim.x) {
     const int ub = w / n_slices, sl = w - ub * n_slices;
     const int ubase = u0 + ub * RC_TU;
-    float thr[8][NT];
     int cnt[8][NT];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int gu = ubase + tu + 16 * u;
+    for (int u = 0; u < 8; ++u)
 #pragma unroll
-      for (int t = 0; t < NT; ++t) {
-        thr[u][t] = (gu < u1 && t < n_thr) ? thr_scores[(size_t)(gu - u0) * n_thr + t] : CUDART_NAN_F;
-        cnt[u][t] = 0;
-      }
+      for (int t = 0; t < NT; ++t) cnt[u][t] = 0;
+    __syncthreads();                       // the previous unit has read its thresholds
+    for (int i = tid; i < RC_TU * NT; i += RC_THREADS) {
+      const int r = i / NT, t = i - r * NT;
+      const int gu = ubase + r;
+      thr_s[i] = (gu < u1 && t < n_thr) ? thr_scores[(size_t)(gu - u0) * n_thr + t] : CUDART_NAN_F;
     }
     auto fill_users = [&](int kb) {
       const int q0 = kb * RC_KQB, nq = (KQ - q0 < RC_KQB) ? (KQ - q0) : RC_KQB;
@@ -117,20 +119,29 @@ k_rank_counts(FvxModel M, const float* __restrict__ theta, int u0, int u1, int n
         }
         __syncthreads();
         for (int q = 0; q < nq; ++q) {
-          float4 a[8];
+          // Registers bound this loop (64 accumulators at two CTAs per SM): the user operand is held four
+          // users at a time, which leaves room to fetch the item operand of column block j + 1 BEFORE the
+          // FMAs of block j issue - with one register quad for b the first FMA after every LDS.128 waited
+          // out the shared-memory latency (27 % of the stall samples, profiles/r1_v8_rank_counts_full.txt).
 #pragma unroll
-          for (int u = 0; u < 8; ++u) a[u] = As[q * RC_PITCH + tu + 16 * u];
+          for (int uh = 0; uh < 2; ++uh) {
+            float4 a[4];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 b = Bs[q * RC_PITCH + ti + 16 * j];
+            for (int u = 0; u < 4; ++u) a[u] = As[q * RC_PITCH + tu + 16 * (4 * uh + u)];
+            float4 b_next = Bs[q * RC_PITCH + ti];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              float s = acc[u][j];
-              s = fmaf(a[u].x, b.x, s);
-              s = fmaf(a[u].y, b.y, s);
-              s = fmaf(a[u].z, b.z, s);
-              s = fmaf(a[u].w, b.w, s);
-              acc[u][j] = s;
+            for (int j = 0; j < 8; ++j) {
+              const float4 b = b_next;
+              if (j + 1 < 8) b_next = Bs[q * RC_PITCH + ti + 16 * (j + 1)];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                float s = acc[4 * uh + u][j];
+                s = fmaf(a[u].x, b.x, s);
+                s = fmaf(a[u].y, b.y, s);
+                s = fmaf(a[u].z, b.z, s);
+                s = fmaf(a[u].w, b.w, s);
+                acc[4 * uh + u][j] = s;
+              }
             }
           }
         }
@@ -144,7 +155,7 @@ k_rank_counts(FvxModel M, const float* __restrict__ theta, int u0, int u1, int n
           float s = acc[u][j] + b1;
           if (vis) s += b2;
 #pragma unroll
-          for (int t = 0; t < NT; ++t) cnt[u][t] += (s >= thr[u][t]) ? 1 : 0;
+          for (int t = 0; t < NT; ++t) cnt[u][t] += (s >= thr_s[(tu + 16 * u) * NT + t]) ? 1 : 0;
         }
       }
     }
@@ -217,7 +228,8 @@ extern "C" int fvx_rank_counts(const FvxModel* model, const float* theta_ext, in
   if (n_slices < 1) n_slices = 1;
   const int tiles_per_slice = (n_tiles + n_slices - 1) / n_slices;
   n_slices = (n_tiles + tiles_per_slice - 1) / tiles_per_slice;
-  const size_t smem = (size_t)2 * RC_KQB * RC_PITCH * sizeof(float4) + 2 * RC_TI * sizeof(float);
+  const size_t smem = (size_t)2 * RC_KQB * RC_PITCH * sizeof(float4) + 2 * RC_TI * sizeof(float) +
+                      (size_t)RC_TU * 4 * sizeof(float);
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(k_rank_counts<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
