@@ -15,6 +15,9 @@ What it restates (all citations relative to the reference tree, see SURVEY.md §
 * ``oracle.gradfashion`` - the GradFashion linear variant (two-stage visual projection of colour and edge
                          descriptors, ``src/recommender/models/GradFashion.py:81-190,304-320``): the next
                          model family on the path; pinned, no CUDA path yet.
+* ``oracle.sharded``   - the item-sharded step as the three phases of ``fvx_bpr_step_sharded_a/b/c`` (partial
+                         scores, per-rank gradient shares packed by run of equal users, ownership of the
+                         per-triple terms), run by tests/test_parallel_cpu.py in two gloo processes.
 * ``oracle.sampler``   - the host triple sampler (``src/dataset/dataset.py:83-114``)
                          in the reference's own RNG streams, plus the counter-based
                          Philox sampler the device path implements.

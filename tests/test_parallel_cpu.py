@@ -71,3 +71,63 @@ def test_topk_exchange_layout_gloo_world2():
         p.join(120)
         assert p.exitcode == 0
     assert out.get(timeout=5) == 2.0
+
+
+def _step_worker(rank, world, port, out):
+    """Two gloo ranks run the item-sharded step of oracle/sharded.py (the phases of
+    fvx_bpr_step_sharded_a/b/c) with real all-reduces; every rank must end with the parameters of the
+    single-rank oracle step, the item rows on their owner."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from fvx.parallel import shard_bounds
+    from oracle import bpr, sharded
+    U, I, K, d, D, B, steps, reg, lr = 40, 61, 8, 5, 12, 48, 4, 1e-3, 0.01
+    rng = np.random.default_rng(5)                                      # the same problem on every rank
+    P0 = bpr.init_params(U, I, K, d, D, seed=1, dtype=np.float64)
+    P0["Bi"] = rng.standard_normal(I) * 0.1
+    F = np.maximum(rng.standard_normal((I, D)), 0)
+    lo, cnt = shard_bounds(I, world, rank)
+    P = {k: v.copy() for k, v in P0.items()}                            # users, E replicated; items: own rows matter
+    Q = {k: v.copy() for k, v in P0.items()}                            # single-rank oracle
+    S_ad, SQ = bpr.init_adam(P), bpr.init_adam(Q)
+    ok = True
+    for s in range(steps):
+        u = np.repeat(rng.integers(0, U, B // 4), 4)
+        batch = (u, rng.integers(0, I, B), rng.integers(0, I, B))
+        want_loss = bpr.train_step(Q, SQ, batch, reg, lr, F)
+        St = torch.from_numpy(sharded.phase_a(P, lo, cnt, batch, F))
+        dist.all_reduce(St)
+        n_runs = int(sharded.run_ids(u)[-1]) + 1
+        G_items, RU, dE, dBp, loss = sharded.phase_b(P, lo, cnt, batch, St.numpy(), reg, n_runs, F)
+        RUt, dEt, dBt = torch.from_numpy(RU), torch.from_numpy(dE), torch.from_numpy(dBp)
+        for t in (RUt, dEt, dBt):
+            dist.all_reduce(t)
+        G, extra = sharded.phase_c_grads(P, batch, G_items, RUt.numpy(), dEt.numpy(), dBt.numpy(), reg,
+                                         add_e_reg=(rank == 0))
+        lt = torch.tensor([float(loss + extra)], dtype=torch.float64)
+        dist.all_reduce(lt)
+        ok = ok and abs(float(lt.item()) - want_loss) <= 1e-9 * abs(want_loss)
+        bpr.adam_apply(P, S_ad, G, lr)        # dense-semantics Adam: foreign item rows see a zero gradient here
+    own = slice(lo, lo + cnt)
+    for k in ("Gu", "Tu", "E", "Bp"):
+        ok = ok and np.allclose(P[k], Q[k], rtol=1e-10, atol=1e-13)
+    for k in ("Gi", "Bi"):
+        ok = ok and np.allclose(P[k][own], Q[k][own], rtol=1e-10, atol=1e-13)
+    t = torch.tensor([1.0 if ok else 0.0])
+    dist.all_reduce(t)
+    if rank == 0:
+        out.put(float(t.item()))
+    dist.destroy_process_group()
+
+
+def test_sharded_step_decomposition_gloo_world2():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_step_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    assert out.get(timeout=5) == 2.0
