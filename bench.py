@@ -506,6 +506,33 @@ def run_fvx(args):
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": len(os.sched_getaffinity(0)), "kind": "port",
                                 "sample": "%d steps of B=%d in %.1f s on the full tables (NumPy oracle of the "
                                           "reference step with TF-2.3 dense Keras-Adam)" % (n, B, el)}
+    # ---- the reference's evaluation on the host cores (port): predict_all + store_recommendation's
+    # mask / top-k (Evaluator.py:225-239) and _eval_by_user (:82-128) on a slice of users (the full [U, I]
+    # matrix of this config is 16 GB and the per-user Python loops take minutes) --------------------------
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.no_eval:
+        try:
+            from oracle import bpr as obpr, evaluator as oev
+            n_s = 256
+            Pq = {k_: v for k_, v in e.params().items()}
+            Fh = F_host if D else None
+            tr_ptr, tr_col = inter.row_ptr, inter.col_file
+            tr = [np.sort(tr_col[tr_ptr[u]:tr_ptr[u + 1]]).tolist() for u in range(n_s)]
+            held = [[int(inter.test[u])] if np.ndim(inter.test) == 1 else list(inter.test[u]) for u in range(n_s)]
+            t0_ = time.perf_counter()
+            Sc = obpr.predict_all(Pq, Fh, users=np.arange(n_s))
+            oev.masked_topk(Sc, tr, args.top_k)
+            t1_ = time.perf_counter()
+            for u in range(n_s):
+                oev.eval_by_user(Sc[u], args.items, tr[u], held[u], args.top_k)
+            t2_ = time.perf_counter()
+            line["eval"]["cpu_baseline"] = {
+                "kind": "port", "cores": len(os.sched_getaffinity(0)), "users": n_s,
+                "topk_users_per_s": n_s / (t1_ - t0_), "eval_users_per_s": n_s / (t2_ - t1_),
+                "sample": "%d users x %d items: NumPy predict_all + masked top-%d (store_recommendation), then "
+                          "_eval_by_user per user for one held-out item" % (n_s, args.items, args.top_k)}
+        except Exception as ex:  # a reported baseline must never cost the bench line
+            line["eval"]["cpu_baseline"] = {"kind": "port", "error": repr(ex)}
+
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
