@@ -1,81 +1,96 @@
-"""Command-line driver with the flags and defaults of the reference's src/train_rec.py
-(:17-46), restricted to the models on the hot path (``--rec bprmf | vbpr``).
+"""Command-line driver: the flag surface of the reference's src/train_rec.py (:17-46 - same names,
+same defaults, same per-regulariser loop and console block), for the models on the hot path
+(``--rec bprmf | vbpr``).
 
     cd src && python -m fvx.train_rec --dataset amazon_men --rec vbpr --gpu 0 ...
 
-Deviations, all documented in DESIGN.md: ``--validation`` parses real booleans (the
-reference's ``type=bool`` makes any non-empty string true, :29); ``--gpu`` selects the
-CUDA device (the reference's default -1 means CPU, which does not exist here);
-new optional flags ``--adam_mode``, ``--sampler``, ``--seed``, ``--tensor_cores``,
-``--data_root``, ``--results_root``.
+Deviations, all documented in DESIGN.md: ``--validation`` parses real booleans (the reference's
+``type=bool`` makes any non-empty string true, :29); ``--gpu`` selects the CUDA device (the
+reference's default -1 means CPU, which does not exist here, so the default is 0) and ``--rec``
+defaults to ``vbpr``; new optional flags ``--adam_mode``, ``--sampler``, ``--seed``,
+``--tensor_cores``, ``--data_root``, ``--results_root``.
 """
 import argparse
 
 from .config import configs
 
 
-def _bool(s):
-    return str(s).lower() not in ("0", "false", "no", "")
+def _flag(text):
+    return str(text).strip().lower() not in ("0", "false", "no", "off", "")
+
+
+# (name, type, default, extra argparse keywords).  The first block is the reference's surface.
+REFERENCE_FLAGS = (
+    ("gpu", int, 0, {}),
+    ("best_metric", str, "ndcg", {}),
+    ("dataset", None, "amazon_baby", {"nargs": "?"}),
+    ("rec", None, "vbpr", {"nargs": "?"}),
+    ("batch_size", int, 256, {}),
+    ("top_k", int, 20, {}),
+    ("epochs", int, 200, {}),
+    ("verbose", int, -1, {}),
+    ("batch_eval", int, 128, {}),
+    ("lr", float, 0.001, {}),
+    ("validation", _flag, True, {}),
+    ("restore_epochs", int, 1, {}),
+    ("list_of_regs", float, [0.0], {"nargs": "+"}),
+    ("cnn_model", None, "vgg19", {"nargs": "?"}),
+    ("output_layer", None, "fc2", {"nargs": "?"}),
+    ("embed_k", int, 128, {}),
+    ("embed_d", int, 20, {}),
+    ("reg", float, 0, {}),
+)
+ENGINE_FLAGS = (
+    ("adam_mode", None, "deferred", {"choices": ["deferred", "dense", "lazy"]}),
+    ("sampler", None, "host_ref", {"choices": ["host_ref", "device"]}),
+    ("seed", int, 0, {}),
+    ("tensor_cores", _flag, False, {}),
+    ("data_root", None, None, {}),
+    ("results_root", None, None, {}),
+)
 
 
 def parse_args(argv=None):
-    parser = argparse.ArgumentParser(description="Run train of the Recommender Model.")
-    parser.add_argument('--gpu', type=int, default=0)
-    parser.add_argument('--best_metric', type=str, default='ndcg')
-    parser.add_argument('--dataset', nargs='?', default='amazon_baby', help='dataset name')
-    parser.add_argument('--rec', nargs='?', default="vbpr", help="set recommendation model")
-    parser.add_argument('--batch_size', type=int, default=256, help='batch_size')
-    parser.add_argument('--top_k', type=int, default=20, help='top-k of recommendation.')
-    parser.add_argument('--epochs', type=int, default=200, help='Number of epochs.')
-    parser.add_argument('--verbose', type=int, default=-1, help='number of epochs to store model parameters.')
-    parser.add_argument('--batch_eval', type=int, default=128, help='batch size on items for evaluation.')
-    parser.add_argument('--lr', type=float, default=0.001, help='Learning rate.')
-    parser.add_argument('--validation', type=_bool, default=True, help='use the validation set')
-    parser.add_argument('--restore_epochs', type=int, default=1)
-    parser.add_argument('--list_of_regs', nargs='+', type=float, default=[0.0], help='list of regularization terms')
-    parser.add_argument('--cnn_model', nargs='?', default='vgg19', help='Model used for feature extraction.')
-    parser.add_argument('--output_layer', nargs='?', default='fc2', help='Output layer for feature extraction.')
-    parser.add_argument('--embed_k', type=int, default=128, help='Embedding size.')
-    parser.add_argument('--embed_d', type=int, default=20, help='size of low dimensionality for visual features')
-    parser.add_argument('--reg', type=float, default=0, help='regularization')
-    # additions
-    parser.add_argument('--adam_mode', default='deferred', choices=['deferred', 'dense', 'lazy'])
-    parser.add_argument('--sampler', default='host_ref', choices=['host_ref', 'device'])
-    parser.add_argument('--seed', type=int, default=0)
-    parser.add_argument('--tensor_cores', type=_bool, default=False)
-    parser.add_argument('--data_root', default=None)
-    parser.add_argument('--results_root', default=None)
-    return parser.parse_args(argv)
+    ap = argparse.ArgumentParser(description="BPRMF / VBPR training on the fvx engine (reference CLI surface)")
+    for name, kind, default, extra in REFERENCE_FLAGS + ENGINE_FLAGS:
+        kw = dict(extra, default=default)
+        if kind is not None:
+            kw["type"] = kind
+        ap.add_argument("--" + name, **kw)
+    return ap.parse_args(argv)
+
+
+def _model_class(rec):
+    from .recommender.models.BPRMF import BPRMF
+    from .recommender.models.VBPR import VBPR
+    table = {"bprmf": BPRMF, "vbpr": VBPR}
+    if rec not in table:
+        raise NotImplementedError('Not implemented or unknown Recommender Model.')
+    return table[rec]
 
 
 def train(argv=None):
+    """One full ``model.train()`` per entry of ``--list_of_regs`` (train_rec.py:60-90); returns the
+    list of results dicts."""
+    from .dataset.dataset import DataLoader
     args = parse_args(argv)
     configs.set_roots(data=args.data_root, results=args.results_root)
     args.device = "cuda:%d" % max(args.gpu, 0)
-    from .dataset.dataset import DataLoader
-    from .recommender.models.BPRMF import BPRMF
-    from .recommender.models.VBPR import VBPR
-    out = []
-    for it, current_reg in enumerate(list(args.list_of_regs)):
-        print('--------------------------------------------------------------------')
-        print('ITERATION %d/%d WITH REGULARIZATION: %f' % (it + 1, len(list(args.list_of_regs)), current_reg))
+    regs = list(args.list_of_regs)
+    rule = '-' * 68
+    runs = []
+    for n, reg in enumerate(regs, start=1):
+        print(rule)
+        print('ITERATION %d/%d WITH REGULARIZATION: %f' % (n, len(regs), reg))
         data = DataLoader(params=args)
         print("Training {0} on {1}".format(args.rec, args.dataset))
+        args.reg = reg
         print("Parameters:")
-        args.reg = current_reg
-        for arg in vars(args):
-            print("\t- " + str(arg) + " = " + str(getattr(args, arg)))
-        print("\n")
-        if args.rec == 'bprmf':
-            model = BPRMF(data, args)
-        elif args.rec == 'vbpr':
-            model = VBPR(data, args)
-        else:
-            raise NotImplementedError('Not implemented or unknown Recommender Model.')
-        out.append(model.train())
+        print("".join("\t- %s = %s\n" % (key, value) for key, value in vars(args).items()))
+        runs.append(_model_class(args.rec)(data, args).train())
         print('END REGULARIZATION')
-        print('--------------------------------------------------------------------')
-    return out
+        print(rule)
+    return runs
 
 
 if __name__ == '__main__':

@@ -177,3 +177,23 @@ def test_no_cpu_fallback():
         Engine(10, 10, 4)
     with pytest.raises(_lib.FvxError):
         _lib.ptr(torch.zeros(4))
+
+
+def test_cli_surface_matches_reference():
+    """fvx.train_rec keeps the flag names and defaults of the reference's train_rec.py:17-46 (listed here;
+    /root/reference is not read at run time).  Documented deviations: --gpu defaults to 0 (no CPU path),
+    --rec to vbpr (the reference's default model is out of scope), --validation parses real booleans."""
+    from fvx import train_rec
+    ref = {"best_metric": "ndcg", "dataset": "amazon_baby", "batch_size": 256, "top_k": 20, "epochs": 200,
+           "verbose": -1, "batch_eval": 128, "lr": 0.001, "validation": True, "restore_epochs": 1,
+           "list_of_regs": [0.0], "cnn_model": "vgg19", "output_layer": "fc2", "embed_k": 128, "embed_d": 20,
+           "reg": 0}
+    a = vars(train_rec.parse_args([]))
+    for k, v in ref.items():
+        assert a[k] == v, k
+    assert a["gpu"] == 0 and a["rec"] == "vbpr"
+    b = train_rec.parse_args(["--rec", "bprmf", "--list_of_regs", "0.1", "0.01", "--validation", "False",
+                              "--embed_k", "64", "--gpu", "1"])
+    assert b.rec == "bprmf" and b.list_of_regs == [0.1, 0.01] and b.validation is False and b.embed_k == 64
+    with pytest.raises(NotImplementedError):
+        train_rec._model_class("acf")
