@@ -403,6 +403,12 @@ def run_fvx(args):
                                           for k_, v in phases.items()},
                             "rows_per_projection_launch": rows_launch, "slots_per_step": 2 * B,
                             "unique_row_step": bool(uniq),
+                            # the same kernel under SURVEY 8(d)'s per-triple accounting (2 feature rows per triple,
+                            # no credit for rows a batch repeats): what the step "asked for", not what the kernel moved
+                            "survey_accounting": ({"bytes_per_launch": 2.0 * B * D * 4.0,
+                                                   "achieved": 2.0 * B * D * 4.0 / (phases[dom] * 1e-3) / 1e9,
+                                                   "frac": 2.0 * B * D * 4.0 / (phases[dom] * 1e-3) / 1e9 / hbm}
+                                                  if dom in ("project", "grad_E") and phases[dom] > 0 else None),
                             # the algorithmic count gives no credit for duplicate rows; popular items repeat
                             # inside a batch and hit L2, so the kernel's DRAM traffic (ncu) is lower and
                             # `frac` can exceed what the DRAM pins actually carried
