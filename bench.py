@@ -409,9 +409,7 @@ def run_fvx(args):
                                                    "achieved": 2.0 * B * D * 4.0 / (phases[dom] * 1e-3) / 1e9,
                                                    "frac": 2.0 * B * D * 4.0 / (phases[dom] * 1e-3) / 1e9 / hbm}
                                                   if dom in ("project", "grad_E") and phases[dom] > 0 else None),
-                            # the algorithmic count gives no credit for duplicate rows; popular items repeat
-                            # inside a batch and hit L2, so the kernel's DRAM traffic (ncu) is lower and
-                            # `frac` can exceed what the DRAM pins actually carried
+                            # DRAM bytes of the same launch from the committed ncu capture / the same time
                             "dram_achieved": (traffic / (phases[dom] * 1e-3) / 1e9) if traffic and phases[dom] > 0 else None,
                             "note": "achieved = bytes the launch is asked to move (projection kernels: gathered rows x 4D "
                                     "- with the unique-row step the DISTINCT catalog rows of the batch, not the 2B slots; "
