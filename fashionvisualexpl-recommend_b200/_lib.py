@@ -11,7 +11,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libfvx.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 ADAM_DENSE, ADAM_DEFERRED, ADAM_LAZY = 0, 1, 2
 N_PHASES = 5
 PHASES = ("prep", "project", "score_grad", "grad_E", "update")
@@ -34,14 +34,14 @@ class FvxModel(C.Structure):
                 ("F_pl", _p), ("ET_hi", _p), ("ET_lo", _p), ("W_hi", _p), ("W_lo", _p),
                 ("step", _p), ("loss", _p), ("loss_slots", C.c_int32), ("_pad1", C.c_int32), ("TH", _p),
                 ("th_cap", C.c_int64), ("W", _p), ("rows", _p), ("sync", _p), ("cmap", _p), ("max_batch", C.c_int32),
-                ("use_tensor_cores", C.c_int32), ("upos", _p), ("W_sum", _p), ("uslot", _p)]
+                ("use_tensor_cores", C.c_int32), ("upos", _p), ("W_sum", _p), ("uslot", _p), ("batch_stage", _p)]
 
 
 class FvxEvalWs(C.Structure):
     _fields_ = [("A", _p), ("Bm", _p), ("epsa", _p), ("nb", _p), ("stat", _p), ("cand", _p), ("ccount", _p),
-                ("flags", _p), ("thr", _p), ("lists", C.c_int64),
+                ("flags", _p), ("thr", _p), ("gmax", _p), ("lists", C.c_int64), ("gmax_elems", C.c_int64),
                 ("u_cap", C.c_int32), ("i_cap", C.c_int32), ("KP", C.c_int32), ("splits", C.c_int32),
-                ("cap", C.c_int32), ("_pad", C.c_int32)]
+                ("cap", C.c_int32), ("n_ut", C.c_int32), ("a_stride", C.c_int32), ("_pad", C.c_int32)]
 
 
 # name -> (restype, argtypes); exactly the prototypes of include/fvx.h
@@ -57,6 +57,7 @@ PROTOTYPES = {
     "fvx_epoch_triples": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _u64, _u64, _p, _p, _p, _p]),
     "fvx_sample_negatives": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _u64, _u64, _p]),
     "fvx_bpr_step": (C.c_int, [_MP, _p, _p, _p, _i32, _i32, _p]),
+    "fvx_bpr_steps": (C.c_int, [_MP, _p, _p, _p, _i64, _i32, _i32, _i32, _p]),
     "fvx_bpr_step_timed": (C.c_int, [_MP, _p, _p, _p, _i32, _i32, C.POINTER(C.c_float), _p]),
     "fvx_run_ids": (C.c_int, [_p, _i64, _p, _p, _p]),
     "fvx_bpr_step_sharded_a": (C.c_int, [_MP, _p, _p, _p, _i32, _p, _p]),
@@ -78,6 +79,9 @@ PROTOTYPES = {
     "fvx_tc_width": (C.c_int, [_i32]),
     "fvx_project_rows": (C.c_int, [_MP, _p, _i64, _p, _p]),
     "fvx_grad_e_rows": (C.c_int, [_MP, _p, _i64, _p, _p, _p]),
+    "fvx_debug_set_dedup": (C.c_int, [C.c_int]),
+    "fvx_debug_trace": (C.c_int, [C.c_int]),
+    "fvx_debug_trace_read": (C.c_int, [C.POINTER(C.c_float)]),
 }
 
 _lib = None

@@ -13,15 +13,30 @@ void fvx_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+int fvx_cur_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= FVX_MAX_DEV) dev = 0;
+  return dev;
+}
+
 int fvx_num_sms() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess ||
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
-      sms = 148;  // B200
+  static int sms[FVX_MAX_DEV];
+  const int dev = fvx_cur_device();
+  if (sms[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;  // B200
+    sms[dev] = n;
   }
-  return sms;
+  return sms[dev];
+}
+
+int fvx_ensure_smem(const void* func, FvxSmemMark* mark, size_t smem, const char* who) {
+  const int dev = fvx_cur_device();
+  if (smem <= 48 * 1024 || smem <= mark->v[dev]) return 0;
+  cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) FVX_FAIL(-3, "%s: cannot set %zu B of dynamic shared memory: %s", who, smem, cudaGetErrorString(e));
+  mark->v[dev] = smem;
+  return 0;
 }
 
 extern "C" {

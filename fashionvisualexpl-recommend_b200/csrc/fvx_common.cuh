@@ -30,7 +30,14 @@ void fvx_set_error(const char* fmt, ...);
   } while (0)
 
 static inline cudaStream_t fvx_cu(fvx_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
-int fvx_num_sms();
+int fvx_num_sms();      // SM count of the CURRENT device (cached per device)
+int fvx_cur_device();   // current CUDA device ordinal (0 on error)
+// Per-device state of a kernel's opt-in dynamic shared memory limit: a process may drive several GPUs
+// (one Engine per device), and cudaFuncSetAttribute applies to the current device's context only.
+#define FVX_MAX_DEV 64
+struct FvxSmemMark { size_t v[FVX_MAX_DEV]; };
+// Raises the limit of `func` on the current device when `smem` exceeds what was configured there before.
+int fvx_ensure_smem(const void* func, FvxSmemMark* mark, size_t smem, const char* who);
 
 // ---- Adam constants (Keras defaults; BPRMF.py:52, VBPR.py:56) --------------------
 #define FVX_BETA1 0.9f

@@ -8,6 +8,8 @@
 #include "fvx_common.cuh"
 #include "fvx_kernels.cuh"
 
+static FvxSmemMark g_topk_smem;   // k_score_topk: dynamic shared memory configured per device
+
 // ---- order-preserving key: ascending key == descending score, then ascending id ----
 __device__ __forceinline__ unsigned long long topk_key(float s, int32_t id) {
   const uint32_t b = __float_as_uint(s);
@@ -314,13 +316,7 @@ static int score_topk_impl(const FvxModel* model, const float* theta_ext, int32_
   if (u1 == u0) return 0;
   const size_t smem = (size_t)TK_UB * TK_CAP * 8 + (size_t)TK_UB * model->users.stride * 4 +
                       (size_t)TK_UB * 4 * (2 + 2 * TK_MAXTHR);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_score_topk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) FVX_FAIL(-3, "fvx_score_topk: cannot set %zu B of shared memory: %s", smem,
-                                   cudaGetErrorString(e));
-    configured = smem;
-  }
+  if (int r = fvx_ensure_smem((const void*)k_score_topk, &g_topk_smem, smem, "fvx_score_topk")) return r;
   long long g = ((long long)(u1 - u0) + TK_UB - 1) / TK_UB;
   if (g > (long long)fvx_num_sms() * 4) g = (long long)fvx_num_sms() * 4;
   k_score_topk<<<(int)g, TK_TILE, smem, fvx_cu(stream)>>>(*model, theta_ext, u0, u1, mask_row_ptr, mask_col, k,
@@ -350,13 +346,7 @@ int fvx_launch_topk_flagged(const FvxModel* model, const float* theta_ext, const
   k_flag_list<<<g, 256, 0, st>>>(flags, n, u0, list_scratch, count_scratch);
   const size_t smem = (size_t)TK_UB * TK_CAP * 8 + (size_t)TK_UB * model->users.stride * 4 +
                       (size_t)TK_UB * 4 * (2 + 2 * TK_MAXTHR);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_score_topk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) FVX_FAIL(-3, "fvx_score_topk_tc: cannot set %zu B of shared memory: %s", smem,
-                                   cudaGetErrorString(e));
-    configured = smem;
-  }
+  if (int r = fvx_ensure_smem((const void*)k_score_topk, &g_topk_smem, smem, "fvx_score_topk")) return r;
   k_score_topk<<<fvx_num_sms() * 2, TK_TILE, smem, st>>>(*model, theta_ext, 0, n, mask_row_ptr, mask_col, k, out_ids,
                                                          out_scores, 0, nullptr, nullptr, list_scratch, count_scratch,
                                                          u0);
@@ -391,11 +381,8 @@ int fvx_topk_merge(const int32_t* ids, const float* scores, int64_t n_users, int
   int npad = 32;
   while (npad < R * k) npad <<= 1;
   const size_t smem = (size_t)MG_WARPS * npad * 8;
-  static bool configured = false;
-  if (smem > 48 * 1024 && !configured) {
-    cudaFuncSetAttribute(k_topk_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    configured = true;
-  }
+  static FvxSmemMark merge_smem;
+  if (int r = fvx_ensure_smem((const void*)k_topk_merge, &merge_smem, smem, "fvx_topk_merge")) return r;
   long long g = (n_users + MG_WARPS - 1) / MG_WARPS;
   if (g > (long long)fvx_num_sms() * 8) g = (long long)fvx_num_sms() * 8;
   k_topk_merge<<<(int)g, MG_WARPS * 32, smem, fvx_cu(stream)>>>(ids, scores, n_users, R, k, npad, out_ids,

@@ -8,19 +8,27 @@
 //   1. k_pack_users / k_pack_items   bf16 operands (K+d+3 padded to KP); the item bias rides in
 //                                    two columns (bf16 hi + lo) so that it enters the score
 //                                    almost exactly, the rounding bound in a third
-//   2. k_topk_tc (persistent, warp-specialised, one CTA per SM)
-//        warp 0    TMA producer : item tiles [128 x KP] -> 64B-swizzled smem ring; the two
-//                                 user tiles [128 x KP] of the work unit
-//        warp 1    UMMA issuer  : D[ut][128 x 128] (TMEM, fp32) = A_ut * B_tile^T for both user
-//                                 tiles of the unit (the item tile is read from smem once for
-//                                 256 users), 4 accumulators = 2 user tiles x double buffer
-//        warps 2-9 epilogue     : one thread per user row (single owner): tcgen05.ld 32
-//                                 columns at a time (next chunk in flight while this one is
-//                                 tested), a 3-input max tree against the row's running
-//                                 threshold; survivors are appended to the row's candidate
-//                                 list; a warp-cooperative radix select tightens the threshold
-//                                 when the list grows past k + slack; thresholds are shared
-//                                 between the item splits of a row through global memory
+//   2. k_topk_tc (persistent, warp-specialised, one CTA per SM).  A work unit is (n_ut user tiles of
+//      128 rows, an item range); the unit sweeps its range TWICE:
+//        warp 0    TMA producer : item tiles [128 x KP] -> 128B-swizzled smem ring (both sweeps); the
+//                                 user tiles [128 x KP] of the unit once
+//        warp 1    UMMA issuer  : D[ut][128 x 128] (TMEM, fp32) = A_ut * B_tile^T for every user tile
+//                                 of the unit (the item tile is read from smem once for 256 users),
+//                                 2 * n_ut accumulators = user tiles x double buffer
+//        warps 2-9 epilogue     : one thread per user row (single owner), tcgen05.ld 32 columns at a
+//                                 time with the next chunk in flight.
+//          sweep A (bounds)     : nothing but a max tree - the maximum of every GROUP of columns
+//                                 (gchunks 32-column chunks; at most ~512 groups per range) goes to a
+//                                 per-CTA scratch [group][row].  The (k + #train)-th largest group
+//                                 maximum, minus the rounding margin, is a lower bound tau of the
+//                                 (k + #train)-th best true score of the range (distinct groups hold
+//                                 distinct items); each thread finds it for its row by bisection over
+//                                 its <= 512 group maxima (coalesced, L2-resident).
+//          sweep B (candidates) : the same max tree against the now FIXED tau; the few survivors
+//                                 (~1.2 (k + #train) per row) are appended to the row's list.
+//      No running threshold, no list compaction, no cross-CTA exchange: the first version of this
+//      kernel spent 3.4 of its 5.1 ms per 256 users on exactly that (round-2 ncu capture,
+//      profiles/r2a_*), whatever the size of the catalog.
 //   3. k_rescore_select              exact fp32 re-scoring of the surviving candidates with the
 //                                    same fvx_score_one() the fp32 path uses, train-item mask,
 //                                    sort, top-k.
@@ -28,13 +36,13 @@
 // Exactness.  With a = [Gu|Tu][u], b = [Gi|theta][i] rounded to bf16 (relative error 2^-9 each)
 //   |s_bf16 - s_fp32| <= c * |a| * |b_i| + beta0,   c = 1.003 * 2^-8 + KP * 2^-21  (rounding + fp32
 //   accumulation),  beta0 = (2^-17 + KP * 2^-21) * max_i |bias_i|                (hi+lo residual).
-// The bound is PER ITEM and costs nothing: one more K column holds eps_u = c*|a_u| (rounded up to
-// bf16) on the user side and |b_i| (rounded up) on the item side, so the UMMA itself delivers the
-// upper bound s_ub = s_bf16 + eps_u * |b_i|; the lower bound is s_lb = s_ub - 2.001 * eps_u * |b_i|
-// - beta0.  A row keeps every item with s_ub >= tau - beta0, tau = the (k + #train items)-th best
-// s_lb seen so far (a lower bound of the k-th best true score over the non-train items), so the
-// true top-k is always among the candidates and the output equals the fp32 kernel's bit for bit.
-// A row whose list overflows is flagged and the caller re-runs it through the fp32 kernel.
+// One more K column holds eps_u = c*|a_u| (rounded up to bf16) on the user side and |b_i| (rounded up) on
+// the item side, so the UMMA itself delivers an UPPER bound s_ub = s_bf16 + eps_u * |b_i| >= s_fp32, and
+// s_ub - margin_u <= s_fp32 with margin_u = 2.001 * eps_u * max_i |b_i| + beta0.  If theta is a value that
+// at least kk = k + #train group maxima (of s_ub) reach, kk distinct items have a true score >=
+// theta - margin_u =: tau, so every item of the true top-kk has s_ub >= s >= tau: keeping {s_ub >= tau}
+// loses nothing, and the output equals the fp32 kernel's bit for bit.  A row whose list overflows, or whose
+// range has fewer than kk groups, is flagged and re-run through the fp32 kernel inside the same call.
 #include <cuda_bf16.h>
 #include <math_constants.h>
 
@@ -43,12 +51,14 @@
 #include "fvx_tc.cuh"
 
 #define TCK_BM 128          // users per tile  (UMMA M)
-#define TCK_BN 128          // items per tile  (UMMA N)
-#define TCK_KB 32           // bf16 elements per K block (64-byte swizzle rows)
+#define TCK_BN 128          // items per tile  (UMMA N); wide operands (K = 256) take 64 (TckParams.bn)
+#define TCK_KB 64           // bf16 elements per K block: 128-byte rows, 128B swizzle (the 64-byte rows of the
+                            // first version cost ~2000 cycles per 256 x 128 tile - TMA rows and operand fetch)
 #define TCK_CAP 512         // candidate slots per (user, split)
-#define TCK_SLACK 192       // a list is compacted once it holds k + #train + TCK_SLACK entries
-#define TCK_THREADS 320     // warp 0 producer, warp 1 UMMA, warps 2-9 epilogue
-#define TCK_RS_MAX 2048     // candidates per user the final selection can take
+#define TCK_GMAX 512        // groups per (unit, range) the bounds sweep keeps
+#define TCK_THREADS 352     // warp 0 producer, warps 1 and 10 UMMA (one per user tile), warps 2-9 epilogue
+#define TCK_RS_MAX 1024     // candidates per user the final selection can take (<= 4 splits x ~200)
+#define TCK_MIN_SPLIT_ITEMS 16384 // an item split keeps at least this many items (>= 1.5 kk groups of one chunk)
 #define KEY_PAD 0xFFFFFFFFFFFFFFFFull
 
 // order-preserving float <-> uint (ascending uint == ascending float)
@@ -78,7 +88,7 @@ __device__ __forceinline__ __nv_bfloat16 bf16_up(float x) {   // smallest bf16 >
 }
 
 __global__ void k_pack_users(FvxModel M, int u0, int u1, __nv_bfloat16* __restrict__ A, float* __restrict__ epsa,
-                             uint32_t* __restrict__ thr_g, int KP, float c_rel) {
+                             int KP, float c_rel) {
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   const int kd = M.K + M.d;
@@ -95,14 +105,11 @@ __global__ void k_pack_users(FvxModel M, int u0, int u1, __nv_bfloat16* __restri
       else if (c == kd + 2) o = eh;                                     // multiplies |b_i|
       A[(size_t)(u - u0) * KP + c] = o;
     }
-    if (lane == 0) {
-      epsa[u - u0] = __bfloat162float(eh);
-      thr_g[u - u0] = tck_mono(-CUDART_INF_F);
-    }
+    if (lane == 0) epsa[u - u0] = __bfloat162float(eh);
   }
 }
 
-// nb[i] = |[Gi|theta][i]| rounded up to bf16; stat[1] = max |bias| (uint bits of a non-negative float)
+// nb[i] = |[Gi|theta][i]| rounded up to bf16; stat[0] = max_i nb[i], stat[1] = max |bias| (uint bits of non-negative floats)
 __global__ void k_pack_items(FvxModel M, const float* __restrict__ theta, __nv_bfloat16* __restrict__ Bm,
                              float* __restrict__ nb, uint32_t* __restrict__ stat, int KP) {
   const int lane = threadIdx.x & 31;
@@ -128,7 +135,7 @@ __global__ void k_pack_items(FvxModel M, const float* __restrict__ theta, __nv_b
       Bm[(size_t)i * KP + c] = o;
     }
     if (lane == 0) nb[i] = __bfloat162float(nh);
-    wmax = fmaxf(wmax, sqrtf(sq));
+    wmax = fmaxf(wmax, __bfloat162float(nh));
     bmax = fmaxf(bmax, fabsf(bias));
   }
   if (lane == 0) {   // non-negative floats order like uints
@@ -141,129 +148,77 @@ __global__ void k_pack_items(FvxModel M, const float* __restrict__ theta, __nv_b
 struct TckParams {
   int n_users;          // users in this call (rows of A)
   int item_cnt, item_lo;
-  int nkb;              // K blocks of 32
+  int nkb;              // K blocks of 64
+  int nk16;             // UMMA K steps that hold data: ceil((K+d+3) / 16) (the zero padding behind them is skipped)
   int stages;
-  // work units: the first n_full user-tile pairs (a multiple of the grid size) sweep the whole
-  // catalog each (one list per row, no threshold restart); the remaining pairs are cut into
-  // `splits` item ranges so that the last wave still fills the machine
-  int splits, tiles_per_split, n_item_tiles, n_pairs, n_full;
+  int n_ut;             // user tiles per work unit: 2, or 1 when two tiles + the item ring do not fit smem
+  int bn;               // items per tile: 128, or 64 for wide operands
+  // work units: the first n_full user groups (a multiple of the grid size) sweep the whole catalog each;
+  // the remaining groups are cut into `splits` item ranges so that the last wave still fills the machine
+  int splits, tiles_per_split, n_item_tiles, n_groups, n_full;
   int k;
   int u0;
+  int a_stride;         // the bounds sweep visits every a_stride-th tile of the range (1 or 2)
   float beta_c;         // 2^-17 + KP * 2^-21: bias residual + fp32 accumulation, per unit of max|bias|
   const float* epsa;    // [n_users] eps_u as multiplied by the UMMA (bf16 value)
-  const float* nb;      // [item_cnt] |b_i| as multiplied by the UMMA (bf16 value)
-  const uint32_t* stat; // [0] max item norm, [1] max |bias|  (float bits)
+  const uint32_t* stat; // [0] max_i |b_i| as multiplied by the UMMA, [1] max |bias|  (float bits)
   const int64_t* mask_row_ptr;
+  float* gmax;                // [grid][TCK_GMAX][n_ut * 128] group maxima of the unit in flight
   unsigned long long* cand;   // [lists * CAP]
   int32_t* ccount;            // [lists]
   int32_t* flags;             // [n_users]
-  uint32_t* thr_g;            // [n_users] best known row threshold on s_ub (tck_mono encoding)
 };
 
-// list index of (row, split): rows of the full pairs own one list, tail rows `splits` lists
+// list index of (row, split): rows of the full groups own one list, tail rows `splits` lists
 __device__ __forceinline__ size_t tck_list(const TckParams& P, int row, int sp) {
-  const int full_rows = P.n_full * 2 * TCK_BM;
+  const int full_rows = P.n_full * P.n_ut * TCK_BM;
   return row < full_rows ? (size_t)row : (size_t)full_rows + (size_t)(row - full_rows) * P.splits + sp;
 }
-// unit w of the global enumeration -> (pair, split, tile range)
-__device__ __forceinline__ void tck_unit(const TckParams& P, int w, int& pair, int& sp, int& t0, int& t1) {
-  if (w < P.n_full) { pair = w; sp = 0; t0 = 0; t1 = P.n_item_tiles; return; }
+// unit w of the global enumeration -> (user group, split, tile range)
+__device__ __forceinline__ void tck_unit(const TckParams& P, int w, int& grp, int& sp, int& t0, int& t1) {
+  if (w < P.n_full) { grp = w; sp = 0; t0 = 0; t1 = P.n_item_tiles; return; }
   const int x = w - P.n_full;
-  pair = P.n_full + x / P.splits;
+  grp = P.n_full + x / P.splits;
   sp = x - (x / P.splits) * P.splits;
   t0 = sp * P.tiles_per_split;
   t1 = min(P.n_item_tiles, t0 + P.tiles_per_split);
 }
-
-// warp-cooperative: tighten the threshold of lane `L`'s row and prune its candidate list
-__device__ __forceinline__ void tck_compact_row(const TckParams& P, int L, int lane, int my_row, int split,
-                                                float my_eps2, float beta0, int my_kk, int& cnt, float& thr) {
-  const int row = __shfl_sync(0xffffffffu, my_row, L);
-  const int n = __shfl_sync(0xffffffffu, cnt, L);
-  const int kk = __shfl_sync(0xffffffffu, my_kk, L);
-  const float eps2 = __shfl_sync(0xffffffffu, my_eps2, L);     // 2.001 * eps_u
-  const float old_thr = __shfl_sync(0xffffffffu, thr, L);
-  unsigned long long* buf = P.cand + tck_list(P, row, split) * TCK_CAP;
-  // The train-item mask is NOT consulted here: the (k + #train items)-th best score over ALL
-  // items is a lower bound of the k-th best over the non-train items.  k_rescore_select applies
-  // the mask exactly.
-  uint32_t e[TCK_CAP / 32];     // ~mono(s_ub): the list key (ascending = best first)
-  uint32_t lbk[TCK_CAP / 32];   // ~mono(s_lb)
-  uint32_t kmin = 0xFFFFFFFFu, kmax = 0u;
-#pragma unroll
-  for (int q = 0; q < TCK_CAP / 32; ++q) {
-    const int idx = q * 32 + lane;
-    e[q] = 0xFFFFFFFFu;
-    lbk[q] = 0xFFFFFFFFu;
-    if (idx < n) {
-      const unsigned long long key = buf[idx];
-      e[q] = (uint32_t)(key >> 32);
-      const float lb = tck_score_of_hi(e[q]) - eps2 * P.nb[(uint32_t)key - (uint32_t)P.item_lo] - beta0;
-      lbk[q] = ~tck_mono(lb);
-      kmin = min(kmin, lbk[q]);
-      kmax = max(kmax, lbk[q]);
-    }
-  }
-  float new_thr = fmaxf(old_thr, tck_unmono(__ldcg(P.thr_g + row)));
-  if (n >= kk) {
-    // a 32-bit key T with  kk <= #(lb key <= T) <= kk + 16  (or exactly the kk-th best lower bound)
-    uint32_t lo = __reduce_min_sync(0xffffffffu, kmin), hi = __reduce_max_sync(0xffffffffu, kmax);
-    while (lo < hi) {
-      const uint32_t mid = lo + ((hi - lo) >> 1);
-      int c = 0;
-#pragma unroll
-      for (int q = 0; q < TCK_CAP / 32; ++q) c += (lbk[q] <= mid) ? 1 : 0;
-      c = __reduce_add_sync(0xffffffffu, c);
-      if (c >= kk) { hi = mid; if (c <= kk + 16) break; } else lo = mid + 1;
-    }
-    new_thr = fmaxf(new_thr, tck_score_of_hi(hi) - beta0);
-  }
-  const uint32_t cut = ~tck_mono(new_thr);          // keep keys <= cut  <=>  s_ub >= new_thr
-  int out = 0;
-#pragma unroll
-  for (int q = 0; q < TCK_CAP / 32; ++q) {
-    const int idx = q * 32 + lane;
-    const bool keep = idx < n && e[q] <= cut;
-    const unsigned long long full = keep ? buf[idx] : 0ull;
-    __syncwarp();
-    const uint32_t b = __ballot_sync(0xffffffffu, keep);
-    if (keep) buf[out + __popc(b & ((1u << lane) - 1u))] = full;
-    out += __popc(b);
-  }
-  __syncwarp();
-  if (out > TCK_CAP - 40) {            // too many items inside the margin: row is re-run in fp32
-    if (lane == 0) P.flags[row] = 1;
-    out = TCK_CAP - 40;
-  }
-  if (lane == L) {
-    cnt = out;
-    thr = new_thr;
-    atomicMax(P.thr_g + row, tck_mono(new_thr));
-  }
+// 32-column chunks per group of a bounds sweep over `chunks` chunks (a power of two, so that a group is a
+// whole number of chunks of a tile or a whole number of tiles): at most TCK_GMAX groups
+__device__ __forceinline__ int tck_gchunks(int chunks) {
+  int g = 1;
+  while ((chunks + g - 1) / g > TCK_GMAX) g <<= 1;
+  return g;
 }
 
-// one 32-column chunk of one row: group maxima first, then only the groups that can hold a survivor
-__device__ __forceinline__ void tck_scan_chunk(const uint32_t (&v)[32], float thr, int ibase, int item_cnt,
-                                               int item_lo, unsigned long long* buf, int& cnt) {
-  float g[4];
+// maximum of a 32-column chunk: 11 three-input maxima, four 8-column sub-maxima on the way
+__device__ __forceinline__ float tck_chunk_max(const uint32_t (&v)[32], float (&g)[4]) {
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const float a0 = max3(__uint_as_float(v[8 * q]), __uint_as_float(v[8 * q + 1]), __uint_as_float(v[8 * q + 2]));
     const float a1 = max3(__uint_as_float(v[8 * q + 3]), __uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5]));
     g[q] = max3(a0, a1, fmaxf(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7])));
   }
-  const float m = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
-  if (m >= thr) {
+  return fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
+}
+
+// candidates sweep, one chunk of one row per lane: the 8-column sub-maxima decide warp-wide which octets
+// are looked at; inside an octet only the lanes that hold a survivor do anything
+__device__ __forceinline__ void tck_scan_chunk(const uint32_t (&v)[32], float thr, int ibase, int ilimit, int item_lo,
+                                               unsigned long long* buf, int& cnt) {
+  float g[4];
+  const float m = tck_chunk_max(v, g);
+  if (!__any_sync(0xffffffffu, m >= thr)) return;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      if (g[q] >= thr) {
+  for (int q = 0; q < 4; ++q) {
+    if (!__any_sync(0xffffffffu, g[q] >= thr)) continue;
+    if (g[q] >= thr) {
 #pragma unroll
-        for (int j = 8 * q; j < 8 * q + 8; ++j) {
-          const float s = __uint_as_float(v[j]);
-          if (s >= thr && ibase + j < item_cnt && cnt < TCK_CAP) {
-            buf[cnt] = tck_key(s, item_lo + ibase + j);
-            ++cnt;
-          }
+      for (int j = 8 * q; j < 8 * q + 8; ++j) {
+        const float s = __uint_as_float(v[j]);
+        if (s >= thr && ibase + j < ilimit) {
+          if (cnt < TCK_CAP) buf[cnt] = tck_key(s, item_lo + ibase + j);
+          ++cnt;                              // counts past the capacity: the row is flagged at the end
         }
       }
     }
@@ -276,10 +231,10 @@ k_topk_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   // swizzled TMA / UMMA tiles need their base aligned to the swizzle repeat: round up by hand
   uint8_t* smem = smem_raw + ((1024u - (tc_smem_u32(smem_raw) & 1023u)) & 1023u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t a_bytes = (uint32_t)P.nkb * TCK_BM * 64u;      // one user tile
-  const uint32_t b_bytes = (uint32_t)P.nkb * TCK_BN * 64u;
-  uint8_t* sA = smem;                                            // [2][a_bytes]
-  uint8_t* sB = smem + 2 * a_bytes;
+  const uint32_t a_bytes = (uint32_t)P.nkb * TCK_BM * 128u;     // one user tile
+  const uint32_t b_bytes = (uint32_t)P.nkb * (uint32_t)P.bn * 128u;
+  uint8_t* sA = smem;                                            // [n_ut][a_bytes]
+  uint8_t* sB = smem + (size_t)P.n_ut * a_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)P.stages * b_bytes);
   uint64_t* full_b = bars;                  // [stages]
   uint64_t* empty_b = bars + P.stages;      // [stages]
@@ -290,9 +245,10 @@ k_topk_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 4);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < P.stages; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
+    // every UMMA warp (one per user tile) releases an item stage / the user tiles with its own commit
+    for (int s = 0; s < P.stages; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], P.n_ut); }
     mbar_init(a_full, 1);
-    mbar_init(a_empty, 1);
+    mbar_init(a_empty, P.n_ut);
     for (int s = 0; s < 4; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 4); }
     mbar_fence_init();
     tma_prefetch_desc(&tmA);
@@ -303,138 +259,206 @@ k_topk_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int n_units = P.n_full + (P.n_pairs - P.n_full) * P.splits;
+  const int n_units = P.n_full + (P.n_groups - P.n_full) * P.splits;
+  // Every role walks the same sequence of item tiles per unit: the bounds sweep (every a_stride-th tile of
+  // [t0, t1)), then the candidates sweep (every tile).  seq -> tile:
+  //   seq <  na : t0 + seq * a_stride          (sweep A)
+  //   seq >= na : t0 + (seq - na)              (sweep B)
 
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
       uint32_t stage = 0, phase = 0, unit_i = 0;
       for (int w = blockIdx.x; w < n_units; w += gridDim.x, ++unit_i) {
-        int pair, sp, t0, t1;
-        tck_unit(P, w, pair, sp, t0, t1);
+        int grp, sp, t0, t1;
+        tck_unit(P, w, grp, sp, t0, t1);
+        const int nt = t1 - t0, na = (nt + P.a_stride - 1) / P.a_stride;
         mbar_wait(a_empty, (unit_i & 1) ^ 1);
-        mbar_expect_tx(a_full, 2 * a_bytes);
-        for (int ut = 0; ut < 2; ++ut)
+        mbar_expect_tx(a_full, (uint32_t)P.n_ut * a_bytes);
+        for (int ut = 0; ut < P.n_ut; ++ut)
           for (int kb = 0; kb < P.nkb; ++kb)
-            tma_load_2d(sA + (size_t)ut * a_bytes + (size_t)kb * TCK_BM * 64, &tmA, a_full, kb * TCK_KB,
-                        (pair * 2 + ut) * TCK_BM);
-        for (int t = t0; t < t1; ++t) {
+            tma_load_2d(sA + (size_t)ut * a_bytes + (size_t)kb * TCK_BM * 128, &tmA, a_full, kb * TCK_KB,
+                        (grp * P.n_ut + ut) * TCK_BM);
+        for (int seq = 0; seq < na + nt; ++seq) {
+          const int t = seq < na ? t0 + seq * P.a_stride : t0 + (seq - na);
           mbar_wait(&empty_b[stage], phase ^ 1);
           mbar_expect_tx(&full_b[stage], b_bytes);
           uint8_t* dst = sB + (size_t)stage * b_bytes;
           for (int kb = 0; kb < P.nkb; ++kb)
-            tma_load_2d(dst + (size_t)kb * TCK_BN * 64, &tmB, &full_b[stage], kb * TCK_KB, t * TCK_BN);
+            tma_load_2d(dst + (size_t)kb * P.bn * 128, &tmB, &full_b[stage], kb * TCK_KB, t * P.bn);
           if (++stage == (uint32_t)P.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
-  } else if (warp == 1) {
-    // ===== UMMA issuer (one elected thread) =====
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(TCK_BM, TCK_BN, 0, 0);
+  } else if (warp == 1 || warp == 10) {
+    // ===== UMMA issuers: warp 1 fills the accumulators of user tile 0, warp 10 those of user tile 1 =====
+    // The ISSUE of a UMMA, not the tensor pipe, paced the first versions of this kernel: one thread issuing all
+    // twelve UMMAs of a 256 x 128 tile pair needed ~190 cycles for each (descriptor arithmetic, R2UR moves and
+    // branches at ~15 cycles apiece on a lone warp; profiles/r2_eval_*) against 64 on the tensor pipe, and the
+    // epilogue warps slept on t_full.  Two measures: (1) one issuing warp PER USER TILE, on different schedulers,
+    // each with its own double-buffered accumulator pair - an item stage is released by both warps' commits
+    // (a warp per accumulator, four in all, was measured slower: 1.92 vs 1.59 ms); (2) the warp stays
+    // convergent, the descriptors' low words (start address >> 4) advance by adds (+2 per 32-byte K step inside
+    // a 128-byte K block, + rows * 8 per K block) and only the instruction itself is predicated on elect.sync
+    // (umma_f16_lohi_elect) - inside an `if (lane == 0)` region the compiler wraps every UMMA into an ELECT /
+    // BRA.U.ANY emulation loop.
+    const int ut = warp == 1 ? 0 : 1;
+    if (ut < P.n_ut) {
+      const uint32_t idesc = umma_idesc_bf16(TCK_BM, P.bn, 0, 0);
+      const int nk = P.nk16;
+      const uint64_t d0 = umma_smem_desc(0, 16, 1024, TC_SWZ_128B);
+      const uint32_t dlo = (uint32_t)d0, dhi = (uint32_t)(d0 >> 32);      // everything but the start address
+      const uint32_t a_base = dlo + ((tc_smem_u32(sA) + (uint32_t)ut * a_bytes) >> 4);
+      const uint32_t b_base = dlo + (tc_smem_u32(sB) >> 4), b_st = b_bytes >> 4;
+      const uint32_t a_kb = (TCK_BM * 128u) >> 4, b_kb = ((uint32_t)P.bn * 128u) >> 4;
       uint32_t stage = 0, phase = 0, unit_i = 0, buf = 0, buf_phase = 0;
       for (int w = blockIdx.x; w < n_units; w += gridDim.x, ++unit_i) {
-        int pair, sp, t0, t1;
-        tck_unit(P, w, pair, sp, t0, t1);
+        int grp, sp, t0, t1;
+        tck_unit(P, w, grp, sp, t0, t1);
+        const int nt = t1 - t0, na = (nt + P.a_stride - 1) / P.a_stride;
         mbar_wait(a_full, unit_i & 1);
-        for (int t = t0; t < t1; ++t) {
+        for (int seq = 0; seq < na + nt; ++seq) {
+          const uint32_t acc = ut * 2 + buf;
           mbar_wait(&full_b[stage], phase);
+          mbar_wait(&t_empty[acc], buf_phase ^ 1);
           tc_fence_after();
-          const uint32_t b0 = tc_smem_u32(sB + (size_t)stage * b_bytes);
-          for (int ut = 0; ut < 2; ++ut) {
-            const uint32_t acc = ut * 2 + buf;
-            mbar_wait(&t_empty[acc], buf_phase ^ 1);
-            tc_fence_after();
-            const uint32_t a0 = tc_smem_u32(sA + (size_t)ut * a_bytes);
-            const uint32_t d = tmem_base + acc * TCK_BN;
-            for (int kb = 0; kb < P.nkb; ++kb) {
+          const uint32_t d = tmem_base + acc * TCK_BN;
+          uint32_t alo = a_base, blo = b_base + stage * b_st;
+          for (int k = 0; k < nk; k += 4, alo += a_kb, blo += b_kb) {
 #pragma unroll
-              for (int ks = 0; ks < 2; ++ks) {
-                const uint64_t ad = umma_smem_desc(a0 + kb * TCK_BM * 64 + ks * 32, 16, 512, TC_SWZ_64B);
-                const uint64_t bd = umma_smem_desc(b0 + kb * TCK_BN * 64 + ks * 32, 16, 512, TC_SWZ_64B);
-                umma_f16(d, ad, bd, idesc, (kb | ks) ? 1u : 0u);
-              }
-            }
-            umma_commit(&t_full[acc]);     // accumulator ready for its epilogue warps
+            for (int ks = 0; ks < 4; ++ks)
+              if (k + ks < nk) umma_f16_lohi_elect(d, alo + 2u * ks, dhi, blo + 2u * ks, dhi, idesc, (k + ks) ? 1u : 0u);
           }
-          umma_commit(&empty_b[stage]);    // smem stage may be refilled once these UMMAs retire
+          umma_commit_elect(&t_full[acc]);       // accumulator ready for its epilogue warps
+          umma_commit_elect(&empty_b[stage]);    // this warp is done with the item stage
           if (++stage == (uint32_t)P.stages) { stage = 0; phase ^= 1; }
           if (++buf == 2) { buf = 0; buf_phase ^= 1; }
         }
-        umma_commit(a_empty);              // user tiles may be overwritten
+        umma_commit_elect(a_empty);              // this warp is done with the user tiles
       }
     }
-  } else {
+  } else if (warp < 10 && (warp - 2) >> 2 < P.n_ut) {
     // ===== epilogue: warps 2-5 own user tile 0, warps 6-9 user tile 1; thread = user row =====
-    const int ew = warp - 2;
-    const int ut = ew >> 2;
+    const int ut = (warp - 2) >> 2;
     const int quad = warp & 3;            // TMEM lanes this warp may read: [32*quad, 32*quad+32)
     const int rit = quad * 32 + lane;     // row in tile
+    const int rows_u = P.n_ut * TCK_BM;   // rows of a unit
     const float beta0 = P.beta_c * __uint_as_float(P.stat[1]) + 1e-30f;
+    const float nbmax = __uint_as_float(P.stat[0]);
+    float* gm = P.gmax + (size_t)blockIdx.x * TCK_GMAX * rows_u + ut * TCK_BM + rit;   // [group][rows_u], this row
     uint32_t buf = 0, buf_phase = 0;
     for (int w = blockIdx.x; w < n_units; w += gridDim.x) {
-      int pair, sp, t0, t1;
-      tck_unit(P, w, pair, sp, t0, t1);
-      const bool shared = w >= P.n_full;    // the row's other splits run elsewhere: exchange bounds
-      const int row = (pair * 2 + ut) * TCK_BM + rit;
+      int grp, sp, t0, t1;
+      tck_unit(P, w, grp, sp, t0, t1);
+      const int nt = t1 - t0, na = (nt + P.a_stride - 1) / P.a_stride;
+      const int row = (grp * P.n_ut + ut) * TCK_BM + rit;
       const bool live = row < P.n_users;
-      float eps2 = 0.0f;
       int kk = P.k;
+      float margin = 0.0f;
       if (live) {
-        eps2 = 2.001f * P.epsa[row];
         const int gu = P.u0 + row;
         kk = P.k + (int)(P.mask_row_ptr[gu + 1] - P.mask_row_ptr[gu]);
-        if (kk > TCK_CAP - TCK_SLACK - 40) {   // cannot bound this row's list: exact fp32 sweep instead
-          kk = TCK_CAP - TCK_SLACK - 40;
-          P.flags[row] = 1;
-        }
+        margin = 2.001f * P.epsa[row] * nbmax + beta0;
       }
-      const int trig = kk + TCK_SLACK;
-      float thr = live ? -CUDART_INF_F : CUDART_INF_F;
-      int cnt = 0;
-      unsigned long long* lbuf = P.cand + tck_list(P, live ? row : 0, sp) * TCK_CAP;
-      for (int t = t0; t < t1; ++t) {
+      // ---- sweep A: group maxima of s_ub -> gm[g * rows_u] ----
+      const int nch = P.bn >> 5;                // 32-column chunks per tile
+      const int gch = tck_gchunks(na * nch);    // chunks per group (power of two)
+      const int gsh = 31 - __clz(gch);
+      const int n_grp = (na * nch + gch - 1) >> gsh;
+      float run = -CUDART_INF_F, lo = CUDART_INF_F, hi = -CUDART_INF_F;
+      int cdone = 0;                            // chunks of the sweep consumed so far
+      int n_fin = 0;                            // groups that hold at least one catalog column
+      for (int seq = 0; seq < na; ++seq) {
+        const int t = t0 + seq * P.a_stride;
         const uint32_t acc = ut * 2 + buf;
-        // bounds found by the row's other splits (L2), fetched now and applied after this tile
-        uint32_t peer = 0u;
-        const bool refresh = shared && live && ((t - t0) & 7) == 0;
-        if (refresh) peer = __ldcg(P.thr_g + row);
         mbar_wait(&t_full[acc], buf_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TCK_BN;
-        const int item0 = t * TCK_BN;
+        const int ragged = (t + 1) * P.bn - P.item_cnt;       // > 0: the last tile holds columns past the catalog
         uint32_t va[32], vb[32];
         tmem_ld_32x32(taddr, va);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          tmem_ld_wait();
-          // next chunk in flight while this one is tested
-          if (c == 0) tmem_ld_32x32(taddr + 32, vb);
-          if (c == 1) tmem_ld_32x32(taddr + 64, va);
-          if (c == 2) tmem_ld_32x32(taddr + 96, vb);
-          if ((c & 1) == 0) tck_scan_chunk(va, thr, item0 + c * 32, P.item_cnt, P.item_lo, lbuf, cnt);
-          else tck_scan_chunk(vb, thr, item0 + c * 32, P.item_cnt, P.item_lo, lbuf, cnt);
-          uint32_t need = __ballot_sync(0xffffffffu, cnt >= trig);
-          while (need) {
-            const int L = __ffs(need) - 1;
-            need &= need - 1;
-            tck_compact_row(P, L, lane, row, sp, eps2, beta0, kk, cnt, thr);
+          if (c < nch) {
+            tmem_ld_wait();
+            if (c + 1 < nch) {                  // next chunk in flight while this one is reduced
+              if (c & 1) tmem_ld_32x32(taddr + (c + 1) * 32, va); else tmem_ld_32x32(taddr + (c + 1) * 32, vb);
+            }
+            uint32_t (&v)[32] = (c & 1) ? vb : va;
+            if (ragged > 0) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (t * P.bn + c * 32 + j >= P.item_cnt) v[j] = 0xFF800000u;     // -inf
+            }
+            float g4[4];
+            run = fmaxf(run, tck_chunk_max(v, g4));
+            if ((++cdone & (gch - 1)) == 0) {
+              gm[(size_t)((cdone >> gsh) - 1) * rows_u] = run;
+              if (run > -CUDART_INF_F) { lo = fminf(lo, run); hi = fmaxf(hi, run); ++n_fin; }
+              run = -CUDART_INF_F;
+            }
           }
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&t_empty[acc]);
         if (++buf == 2) { buf = 0; buf_phase ^= 1; }
-        if (refresh) thr = fmaxf(thr, tck_unmono(peer));
       }
-      // publish this unit's bound for the rows that hold at least kk candidates, then the length
-      uint32_t need = __ballot_sync(0xffffffffu, live && cnt >= kk);
-      while (need) {
-        const int L = __ffs(need) - 1;
-        need &= need - 1;
-        tck_compact_row(P, L, lane, row, sp, eps2, beta0, kk, cnt, thr);
+      if ((cdone & (gch - 1)) != 0) {           // the last, shorter group
+        gm[(size_t)(cdone >> gsh) * rows_u] = run;
+        if (run > -CUDART_INF_F) { lo = fminf(lo, run); hi = fmaxf(hi, run); ++n_fin; }
       }
-      if (live) P.ccount[tck_list(P, row, sp)] = cnt;
+      // ---- the row's bound: a value at least kk group maxima reach (bisection; counts in [kk, kk + kk/4]
+      //      stop it early - a looser value only lets a few more candidates through) ----
+      float thr = CUDART_INF_F;                 // dead rows keep nothing
+      bool unbounded = false;
+      if (live) {
+        if (n_fin < kk) {
+          unbounded = true;                     // fewer groups than kk (tiny range): the exact kernel takes the row
+        } else {
+          float a = lo, b = hi;                 // invariant: count(>= a) >= kk (lo: the smallest finite maximum)
+          for (int it = 0; it < 16 && a < b; ++it) {
+            const float mid = 0.5f * a + 0.5f * b;
+            if (!(mid > a) || !(mid < b)) break;
+            int c = 0;
+            for (int g = 0; g < n_grp; ++g) c += (__ldcg(gm + (size_t)g * rows_u) >= mid) ? 1 : 0;
+            if (c >= kk) { a = mid; if (c <= kk + (kk >> 2)) break; } else b = mid;
+          }
+          thr = a - margin;
+        }
+      }
+      // ---- sweep B: candidates with s_ub >= thr ----
+      int cnt = 0;
+      unsigned long long* lbuf = P.cand + tck_list(P, live ? row : 0, sp) * TCK_CAP;
+      for (int seq = 0; seq < nt; ++seq) {
+        const int t = t0 + seq;
+        const uint32_t acc = ut * 2 + buf;
+        mbar_wait(&t_full[acc], buf_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TCK_BN;
+        const int item0 = t * P.bn;
+        uint32_t va[32], vb[32];
+        tmem_ld_32x32(taddr, va);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (c < nch) {
+            tmem_ld_wait();
+            if (c + 1 < nch) {                  // next chunk in flight while this one is tested
+              if (c & 1) tmem_ld_32x32(taddr + (c + 1) * 32, va); else tmem_ld_32x32(taddr + (c + 1) * 32, vb);
+            }
+            if ((c & 1) == 0) tck_scan_chunk(va, thr, item0 + c * 32, P.item_cnt, P.item_lo, lbuf, cnt);
+            else tck_scan_chunk(vb, thr, item0 + c * 32, P.item_cnt, P.item_lo, lbuf, cnt);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&t_empty[acc]);
+        if (++buf == 2) { buf = 0; buf_phase ^= 1; }
+      }
+      if (live) {
+        if (unbounded || cnt > TCK_CAP) { P.flags[row] = 1; cnt = 0; }
+        P.ccount[tck_list(P, row, sp)] = cnt;
+      }
     }
   }
   tc_fence_before();
@@ -447,7 +471,7 @@ k_topk_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 
 // ---------------------------------------------------------------------------------
 // exact re-scoring + final selection: one warp per user
-#define RS_WARPS 2
+#define RS_WARPS 4
 __device__ __forceinline__ void rs_bitonic(unsigned long long* keys, int n, int lane) {
   for (int size = 2; size <= n; size <<= 1)
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
@@ -498,19 +522,18 @@ k_rescore_select(FvxModel M, const float* __restrict__ theta, TckParams P,
                  const int64_t* __restrict__ mask_row_ptr, const int32_t* __restrict__ mask_col, int k,
                  int32_t* __restrict__ out_ids, float* __restrict__ out_scores) {
   __shared__ unsigned long long rs_keys[RS_WARPS][TCK_RS_MAX];
-  __shared__ float rs_user[RS_WARPS][128];
+  __shared__ float rs_user[RS_WARPS][448];      // K + d <= 445 (KP <= 448)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned long long* kk = rs_keys[warp];
   float* us = rs_user[warp];
-  const int full_rows = P.n_full * 2 * TCK_BM;
+  const int full_rows = P.n_full * P.n_ut * TCK_BM;
   const int kd = M.K + M.d;
   for (int r = blockIdx.x * RS_WARPS + warp; r < P.n_users; r += gridDim.x * RS_WARPS) {
     const int gu = P.u0 + r;
     const float* urow = M.users.w + (size_t)gu * M.users.stride;
     for (int c = lane; c < kd; c += 32) us[c] = urow[c];
     const long long mlo = mask_row_ptr[gu], mhi = mask_row_ptr[gu + 1];
-    // survivors of the row's final bound on s_ub
-    const uint32_t cut = ~P.thr_g[r];
+    // the candidates of the row's lists (one per item split)
     const int nlists = r < full_rows ? 1 : P.splits;
     int total = 0;
     for (int sp = 0; sp < nlists; ++sp) {
@@ -520,7 +543,7 @@ k_rescore_select(FvxModel M, const float* __restrict__ theta, TckParams P,
       for (int i0 = 0; i0 < n; i0 += 32) {
         const int i = i0 + lane;
         const unsigned long long key = i < n ? src[i] : KEY_PAD;
-        const bool keep = i < n && (uint32_t)(key >> 32) <= cut;
+        const bool keep = i < n;
         const uint32_t b = __ballot_sync(0xffffffffu, keep);
         const int pos = total + __popc(b & ((1u << lane) - 1u));
         if (keep && pos < TCK_RS_MAX) kk[pos] = key;
@@ -590,46 +613,73 @@ int tc_make_tensor_map_bf16(CUtensorMap* out, const void* base, uint64_t rows, u
 extern "C" {
 
 // geometry shared by the query and the launch
-static void tck_geometry(const FvxModel* m, int n_users, int* KP, int* n_pairs, int* n_full, int* splits, int* grid,
-                         long long* lists) {
+struct TckGeom {
+  int KP, nkb, n_ut, bn, stages, n_groups, n_full, splits, grid;
+  long long lists, gmax_elems;
+  size_t smem;
+};
+static int tck_geometry(const FvxModel* m, int n_users, TckGeom* g) {
   const int kd3 = m->K + m->d + 3;
-  *KP = (kd3 + TCK_KB - 1) / TCK_KB * TCK_KB;
-  *n_pairs = (n_users + 2 * TCK_BM - 1) / (2 * TCK_BM);
-  const int n_item_tiles = (m->item_cnt + TCK_BN - 1) / TCK_BN;
+  g->KP = (kd3 + TCK_KB - 1) / TCK_KB * TCK_KB;
+  g->nkb = g->KP / TCK_KB;
+  // shared memory: n_ut user tiles + a ring of item tiles (each nkb * 8 KB).  Two user tiles per unit read
+  // every item tile once for 256 users; wide operands take one user tile.
+  // shared memory: n_ut user tiles (nkb * 16 KB each) + a ring of item tiles (nkb * bn * 128 B each).  Two user
+  // tiles per unit read every item tile once for 256 users; wide operands (K = 256: 5 K blocks) take one user
+  // tile and 64-item tiles.
+  const long long ut_bytes = (long long)g->nkb * TCK_BM * 128, budget = 224 * 1024;
+  static const int pref[6][3] = {{2, 128, 3}, {1, 128, 3}, {2, 128, 2}, {1, 64, 3}, {1, 128, 2}, {1, 64, 2}};
+  g->stages = 0;
+  for (int i = 0; i < 6 && g->stages == 0; ++i) {
+    const long long it_bytes = (long long)g->nkb * pref[i][1] * 128;
+    const long long st = (budget - pref[i][0] * ut_bytes) / it_bytes;
+    if (st >= pref[i][2]) { g->n_ut = pref[i][0]; g->bn = pref[i][1]; g->stages = st > 6 ? 6 : (int)st; }
+  }
+  if (g->stages == 0) return -1;
+  g->smem = (size_t)g->n_ut * ut_bytes + (size_t)g->stages * g->nkb * g->bn * 128 + (2 * g->stages + 10) * 8 + 16 + 1024;
+  const int rows_u = g->n_ut * TCK_BM;
+  g->n_groups = (n_users + rows_u - 1) / rows_u;
+  const int n_item_tiles = (m->item_cnt + g->bn - 1) / g->bn;
+  const int min_split = TCK_MIN_SPLIT_ITEMS / g->bn;
   const int G = fvx_num_sms();
-  *n_full = (*n_pairs / G) * G;
-  const int tail = *n_pairs - *n_full;
+  g->n_full = (g->n_groups / G) * G;
+  const int tail = g->n_groups - g->n_full;
   int s = 1;
   if (tail > 0) {
-    // the tail pairs are cut into s item ranges so that their units still fill the machine: the
-    // tail then takes ceil(tail*s/G) rounds of 1/s of a sweep; every extra split costs a threshold
-    // restart (~3 % of a sweep here), so the smallest s within 2 % of the best is taken
-    int smax = n_item_tiles / 8 < 16 ? n_item_tiles / 8 : 16;
+    // the tail groups are cut into s item ranges so that their units still fill the machine: the tail then
+    // takes ceil(tail*s/G) rounds of 1/s of a sweep.  A range keeps >= TCK_MIN_SPLIT_ITEMS items (its bound
+    // needs more groups than kk) and a row at most 4 lists; the smallest s within 2 % of the best is taken.
+    int smax = n_item_tiles / min_split < 4 ? n_item_tiles / min_split : 4;
     if (smax < 1) smax = 1;
     double best = 1e30;
     for (int c = 1; c <= smax; ++c) {
-      const double t = (double)((tail * c + G - 1) / G) / c + 0.03 * c;
+      const double t = (double)((tail * c + G - 1) / G) / c + 0.002 * c;
       if (t < best * 0.98) { best = t; s = c; }
     }
   }
-  *splits = s;
-  const long long units = (long long)*n_full + (long long)tail * s;
-  *grid = (int)(units < G ? units : G);
-  *lists = (long long)*n_full * 2 * TCK_BM + ((long long)n_users - (long long)*n_full * 2 * TCK_BM > 0
-                                               ? ((long long)n_users - (long long)*n_full * 2 * TCK_BM) * s : 0);
+  g->splits = s;
+  const long long units = (long long)g->n_full + (long long)tail * s;
+  g->grid = (int)(units < G ? units : G);
+  const long long full_rows = (long long)g->n_full * rows_u;
+  g->lists = full_rows + ((long long)n_users - full_rows > 0 ? ((long long)n_users - full_rows) * s : 0);
+  g->gmax_elems = (long long)G * TCK_GMAX * rows_u;
+  return 0;
 }
 
 int fvx_eval_ws_query(const FvxModel* model, int32_t n_users, FvxEvalWs* ws) {
   FVX_CHECK_ARG(model && ws && n_users > 0, "fvx_eval_ws_query: bad arguments");
-  int KP, n_pairs, n_full, splits, grid;
-  long long lists;
-  tck_geometry(model, n_users, &KP, &n_pairs, &n_full, &splits, &grid, &lists);
-  ws->KP = KP;
-  ws->splits = splits;
+  TckGeom g;
+  FVX_CHECK_ARG(tck_geometry(model, n_users, &g) == 0,
+                "fvx_eval_ws_query: K+d+3=%d too wide for the tensor-core sweep (use fvx_score_topk)",
+                model->K + model->d + 3);
+  ws->KP = g.KP;
+  ws->splits = g.splits;
   ws->cap = TCK_CAP;
   ws->u_cap = n_users;
   ws->i_cap = model->item_cnt;
-  ws->lists = lists;
+  ws->lists = g.lists;
+  ws->gmax_elems = g.gmax_elems;
+  ws->n_ut = g.n_ut;
   return 0;
 }
 
@@ -641,61 +691,54 @@ int fvx_score_topk_tc(const FvxModel* model, const float* theta_ext, int32_t u0,
   FVX_CHECK_ARG(0 <= u0 && u0 < u1 && u1 <= model->num_users, "fvx_score_topk_tc: bad user range");
   FVX_CHECK_ARG(k >= 1 && k <= 128, "fvx_score_topk_tc: k=%d outside [1,128]", k);
   const int n_users = u1 - u0;
-  int KP, n_pairs, n_full, splits, grid;
-  long long lists;
-  tck_geometry(model, n_users, &KP, &n_pairs, &n_full, &splits, &grid, &lists);
-  FVX_CHECK_ARG(ws->KP == KP && ws->splits == splits && ws->cap == TCK_CAP && ws->u_cap >= n_users &&
-                ws->i_cap >= model->item_cnt && ws->lists >= lists,
-                "fvx_score_topk_tc: workspace does not match fvx_eval_ws_query");
-  FVX_CHECK_ARG(ws->A && ws->Bm && ws->epsa && ws->nb && ws->stat && ws->cand && ws->ccount && ws->flags && ws->thr,
-                "fvx_score_topk_tc: null workspace buffer");
-  const int nkb = KP / TCK_KB;
-  FVX_CHECK_ARG(KP <= 128 && model->K + model->d <= 128,
-                "fvx_score_topk_tc: K+d+3=%d too large for the tensor-core sweep (use fvx_score_topk)",
+  TckGeom g;
+  FVX_CHECK_ARG(tck_geometry(model, n_users, &g) == 0,
+                "fvx_score_topk_tc: K+d+3=%d too wide for the tensor-core sweep (use fvx_score_topk)",
                 model->K + model->d + 3);
+  FVX_CHECK_ARG(ws->KP == g.KP && ws->splits == g.splits && ws->cap == TCK_CAP && ws->u_cap >= n_users &&
+                ws->i_cap >= model->item_cnt && ws->lists >= g.lists && ws->gmax_elems >= g.gmax_elems &&
+                ws->n_ut == g.n_ut,
+                "fvx_score_topk_tc: workspace does not match fvx_eval_ws_query");
+  FVX_CHECK_ARG(ws->A && ws->Bm && ws->epsa && ws->nb && ws->stat && ws->cand && ws->ccount && ws->flags && ws->thr &&
+                ws->gmax, "fvx_score_topk_tc: null workspace buffer");
+  const int KP = g.KP, nkb = g.nkb;
   cudaStream_t st = fvx_cu(stream);
 
   cudaMemsetAsync(ws->stat, 0, 8, st);
   cudaMemsetAsync(ws->flags, 0, sizeof(int32_t) * n_users, st);
-  cudaMemsetAsync(ws->ccount, 0, sizeof(int32_t) * lists, st);
+  cudaMemsetAsync(ws->ccount, 0, sizeof(int32_t) * g.lists, st);
   const float c_rel = 1.003f * 0.00390625f + (float)KP * 4.76837158e-7f;
-  int g = (n_users * 32 + 255) / 256;
-  if (g > fvx_num_sms() * 8) g = fvx_num_sms() * 8;
-  k_pack_users<<<g, 256, 0, st>>>(*model, u0, u1, reinterpret_cast<__nv_bfloat16*>(ws->A), ws->epsa,
-                                  reinterpret_cast<uint32_t*>(ws->thr), KP, c_rel);
-  g = fvx_num_sms() * 8;
-  k_pack_items<<<g, 256, 0, st>>>(*model, theta_ext, reinterpret_cast<__nv_bfloat16*>(ws->Bm), ws->nb,
-                                  reinterpret_cast<uint32_t*>(ws->stat), KP);
+  int gr = (n_users * 32 + 255) / 256;
+  if (gr > fvx_num_sms() * 8) gr = fvx_num_sms() * 8;
+  k_pack_users<<<gr, 256, 0, st>>>(*model, u0, u1, reinterpret_cast<__nv_bfloat16*>(ws->A), ws->epsa, KP, c_rel);
+  gr = fvx_num_sms() * 8;
+  k_pack_items<<<gr, 256, 0, st>>>(*model, theta_ext, reinterpret_cast<__nv_bfloat16*>(ws->Bm), ws->nb,
+                                   reinterpret_cast<uint32_t*>(ws->stat), KP);
   FVX_CHECK_LAUNCH("k_pack");
 
   CUtensorMap tmA, tmB;
-  int rc = tc_make_tensor_map_bf16(&tmA, ws->A, n_users, KP, (uint64_t)KP * 2, TCK_KB, TCK_BM, 2);
-  if (rc == 0) rc = tc_make_tensor_map_bf16(&tmB, ws->Bm, model->item_cnt, KP, (uint64_t)KP * 2, TCK_KB, TCK_BN, 2);
+  int rc = tc_make_tensor_map_bf16(&tmA, ws->A, n_users, KP, (uint64_t)KP * 2, TCK_KB, TCK_BM, 3);
+  if (rc == 0) rc = tc_make_tensor_map_bf16(&tmB, ws->Bm, model->item_cnt, KP, (uint64_t)KP * 2, TCK_KB, g.bn, 3);
   if (rc != 0) FVX_FAIL(-4, "fvx_score_topk_tc: cuTensorMapEncodeTiled failed (%d)", rc);
 
   TckParams P;
   P.n_users = n_users; P.item_cnt = model->item_cnt; P.item_lo = model->item_lo; P.nkb = nkb;
-  P.n_pairs = n_pairs; P.n_full = n_full;
-  P.n_item_tiles = (model->item_cnt + TCK_BN - 1) / TCK_BN;
-  P.splits = splits;
+  P.nk16 = (model->K + model->d + 3 + 15) / 16;
+  P.n_ut = g.n_ut; P.bn = g.bn; P.n_groups = g.n_groups; P.n_full = g.n_full;
+  P.n_item_tiles = (model->item_cnt + g.bn - 1) / g.bn;
+  P.splits = g.splits;
   P.tiles_per_split = (P.n_item_tiles + P.splits - 1) / P.splits;
-  P.k = k; P.u0 = u0; P.epsa = ws->epsa; P.nb = ws->nb; P.stat = reinterpret_cast<const uint32_t*>(ws->stat);
+  P.k = k; P.u0 = u0; P.epsa = ws->epsa; P.stat = reinterpret_cast<const uint32_t*>(ws->stat);
+  P.a_stride = ws->a_stride == 2 ? 2 : 1;
   P.beta_c = 7.6294e-6f + (float)KP * 4.76837158e-7f;
   P.mask_row_ptr = mask_row_ptr;
+  P.gmax = ws->gmax;
   P.cand = reinterpret_cast<unsigned long long*>(ws->cand); P.ccount = ws->ccount; P.flags = ws->flags;
-  P.thr_g = reinterpret_cast<uint32_t*>(ws->thr);
-  const size_t a_bytes = (size_t)nkb * TCK_BM * 64, b_bytes = (size_t)nkb * TCK_BN * 64;
-  int stages = (int)((200 * 1024 - 2 * a_bytes) / b_bytes);
-  if (stages > 6) stages = 6;
-  FVX_CHECK_ARG(stages >= 2, "fvx_score_topk_tc: tile does not fit shared memory");
-  P.stages = stages;
-  const size_t smem = 2 * a_bytes + stages * b_bytes + (2 * stages + 10) * 8 + 16 + 1024;
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_topk_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) FVX_FAIL(-3, "fvx_score_topk_tc: cannot set %zu B smem: %s", smem, cudaGetErrorString(e));
-    configured = smem;
-  }
+  P.stages = g.stages;
+  const size_t smem = g.smem;
+  const int grid = g.grid;
+  static FvxSmemMark topk_tc_smem;
+  if (int r = fvx_ensure_smem((const void*)k_topk_tc, &topk_tc_smem, smem, "fvx_score_topk_tc")) return r;
   k_topk_tc<<<grid, TCK_THREADS, smem, st>>>(tmA, tmB, P);
   FVX_CHECK_LAUNCH("k_topk_tc");
 
@@ -704,8 +747,8 @@ int fvx_score_topk_tc(const FvxModel* model, const float* theta_ext, int32_t u0,
   k_rescore_select<<<(int)rg, RS_WARPS * 32, 0, st>>>(*model, theta_ext, P, mask_row_ptr, mask_col, k, out_ids,
                                                       out_scores);
   FVX_CHECK_LAUNCH("k_rescore_select");
-  // rows whose candidate lists could not bound the result: exact fp32 sweep, written in place (the
-  // thresholds and the statistics are dead by now and serve as the list / its counter)
+  // rows whose candidate lists could not bound the result: exact fp32 sweep, written in place (ws->thr is
+  // the scratch for their list; the statistics are dead by now and serve as its counter)
   return fvx_launch_topk_flagged(model, theta_ext, ws->flags, n_users, u0, mask_row_ptr, mask_col, k, out_ids,
                                  out_scores, reinterpret_cast<int32_t*>(ws->thr), reinterpret_cast<int32_t*>(ws->stat), st);
 }

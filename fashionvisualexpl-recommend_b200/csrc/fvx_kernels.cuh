@@ -53,12 +53,6 @@ int fvx_launch_reduce_gE(const FvxModel* m, int parts, int gnp, float* out, cuda
 int fvx_launch_grad_E_tc(const FvxModel* m, const int32_t* rows, int64_t nrows, int* parts_out, cudaStream_t st,
                          const int32_t* nrows_dev = nullptr);
 
-// single-pass step kernel (fvx_step_fused.cu): projection + scoring + grad_E, every feature row read once.
-// Eligible: use_tensor_cores >= 2, one rank, d + 1 <= 32, D in {1024, 2048}, K % 4 == 0, K <= 64.
-bool fvx_fused_eligible(const FvxModel* m);
-int fvx_launch_step_fused(const FvxModel* m, const int32_t* user, int B, int loss_slot, int* parts_out,
-                          cudaStream_t st);
-
 // Side stream of the step (one per device, FVX_STEP_OVERLAP=0 disables it): begin() makes it wait for the
 // work queued on `main_stream` and returns it (nullptr: unavailable); join() makes `main_stream` wait for it.
 cudaStream_t fvx_side_begin(cudaStream_t main_stream);
@@ -72,7 +66,7 @@ int fvx_check_model(const FvxModel* m, const char* who);
 // CLAIMS_LISTED = user claims + catch-up, item catch-up driven by the list UNIQ built
 enum { FVX_PREP_ALL = 0, FVX_PREP_ROWS = 1, FVX_PREP_CLAIMS = 2, FVX_PREP_UNIQ = 3, FVX_PREP_CLAIMS_LISTED = 4 };
 int fvx_launch_prep(const FvxModel* m, const int32_t* user, const int32_t* pos, const int32_t* neg, int B,
-                    cudaStream_t st, int what = FVX_PREP_ALL, int H0 = 0);   // H0: k_rows_et half split (0: none)
+                    cudaStream_t st, int what = FVX_PREP_ALL);
 // what: ALL = tables + E_ext + finalisation; TABLES = touched rows only; E = E_ext + finalisation
 enum { FVX_UPD_ALL = 0, FVX_UPD_TABLES = 1, FVX_UPD_E = 2 };
 int fvx_launch_update(const FvxModel* m, int B, int parts, int gnp, const float* gE_src, int loss_slot,
@@ -81,7 +75,7 @@ int fvx_launch_update(const FvxModel* m, int B, int parts, int gnp, const float*
 // the K split (the kernel derives the split from the list length like the projection does)
 int fvx_launch_score_grad(const FvxModel* m, const int32_t* user, int B, int loss_slot, int th_ks, cudaStream_t st,
                           int dedup = 0);
-// switches of the step (environment: FVX_STEP_DEDUP, FVX_STEP_MERGED_UPDATE; test hook fvx_debug_set_dedup)
+// switches of the step (environment: FVX_STEP_DEDUP; test hook fvx_debug_set_dedup)
 bool fvx_dedup_enabled();
 bool fvx_merged_update(const FvxModel* m);   // DEFERRED mode without the row-update kernel
 // W_sum -> bf16 planes of the listed rows (unique-row step)

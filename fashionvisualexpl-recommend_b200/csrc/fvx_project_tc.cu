@@ -558,11 +558,6 @@ int fvx_tc_ksplit(const FvxModel* m, long long nrows) {
   return fvx_tc_ksplit_rule((nrows + PT_BM - 1) / PT_BM, m->D / PT_KC, fvx_num_sms(), 1 << 30);
 }
 
-static int set_smem(const void* fn, size_t bytes, const char* who) {
-  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-  if (e != cudaSuccess) FVX_FAIL(-3, "%s: cannot set %zu B of shared memory: %s", who, bytes, cudaGetErrorString(e));
-  return 0;
-}
 
 int fvx_launch_split_E(const FvxModel* m, cudaStream_t st) {
   FVX_CHECK_ARG(m->ET_hi && m->ET_lo, "tensor-core projection: ET planes missing");
@@ -617,11 +612,8 @@ int fvx_launch_project_tc(const FvxModel* m, const int32_t* rows, int row0, int6
   FVX_CHECK_ARG(stages >= 2, "tensor-core projection: tile does not fit shared memory");
   P.stages = stages;
   const size_t smem = stages * stage_bytes + (2 * stages + 4) * 8 + 16 + 1024;
-  static size_t configured = 0;
-  if (smem > configured) {
-    if (int r = set_smem((const void*)k_proj_fwd_tc, smem, "k_proj_fwd_tc")) return r;
-    configured = smem;
-  }
+  static FvxSmemMark fwd_smem;
+  if (int r = fvx_ensure_smem((const void*)k_proj_fwd_tc, &fwd_smem, smem, "k_proj_fwd_tc")) return r;
   long long grid = (long long)P.n_tiles * ksplit;
   if (grid > fvx_num_sms() || dyn_ks) grid = fvx_num_sms();
   k_proj_fwd_tc<<<(int)grid, PT_THREADS, smem, st>>>(b_hi, b_lo, P);
@@ -682,11 +674,8 @@ int fvx_launch_grad_E_tc(const FvxModel* m, const int32_t* rows, int64_t nrows, 
   FVX_CHECK_ARG(stages >= 2, "tensor-core grad_E: tile does not fit shared memory");
   P.stages = stages;
   const size_t smem = stages * stage_bytes + (2 * stages + 1) * 8 + 16 + 1024;
-  static size_t configured = 0;
-  if (smem > configured) {
-    if (int r = set_smem((const void*)k_grad_E_tc, smem, "k_grad_E_tc")) return r;
-    configured = smem;
-  }
+  static FvxSmemMark ge_smem;
+  if (int r = fvx_ensure_smem((const void*)k_grad_E_tc, &ge_smem, smem, "k_grad_E_tc")) return r;
   k_grad_E_tc<<<parts * nfg, PT_THREADS, smem, st>>>(w_hi, w_lo, P);
   FVX_CHECK_LAUNCH("k_grad_E_tc");
   return 0;

@@ -230,13 +230,9 @@ extern "C" int fvx_rank_counts(const FvxModel* model, const float* theta_ext, in
   n_slices = (n_tiles + tiles_per_slice - 1) / tiles_per_slice;
   const size_t smem = (size_t)2 * RC_KQB * RC_PITCH * sizeof(float4) + 2 * RC_TI * sizeof(float) +
                       (size_t)RC_TU * 4 * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_rank_counts<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_rank_counts<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) FVX_FAIL(-3, "fvx_rank_counts: cannot set %zu B of shared memory: %s", smem, cudaGetErrorString(e));
-    configured = true;
-  }
+  static FvxSmemMark rc2_smem, rc4_smem;
+  if (int r = fvx_ensure_smem((const void*)k_rank_counts<2>, &rc2_smem, smem, "fvx_rank_counts")) return r;
+  if (int r = fvx_ensure_smem((const void*)k_rank_counts<4>, &rc4_smem, smem, "fvx_rank_counts")) return r;
   long long grid = (long long)n_ublocks * n_slices;
   if (grid > slots) grid = slots;
   if (n_thr <= 2)

@@ -23,14 +23,19 @@ TC_D void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 TC_D void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem_u32(bar)) : "memory");
 }
+// try_wait with a suspend-time hint: a warp whose phase is not complete is PARKED by the hardware (it wakes when
+// the phase completes, or after the hint) instead of re-issuing the poll.  Without the hint the poll returns
+// after ~70 cycles; eight waiting epilogue warps then take two thirds of the issue slots of the scheduler
+// they share with the single UMMA-issuing thread, which paces the whole CTA (measured in k_topk_tc: 190 cycles
+// per UMMA against 64 on the tensor pipe).
 TC_D bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(tc_smem_u32(bar)), "r"(parity)
+      : "r"(tc_smem_u32(bar)), "r"(parity), "r"(2000u)
       : "memory");
   return ok != 0;
 }
@@ -91,6 +96,44 @@ TC_D void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t ide
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// the same with the descriptors handed over as (low, high) 32-bit words: an issue loop that advances the start
+// address with 32-bit adds keeps the per-UMMA instruction count of its single thread small
+TC_D void umma_f16_lohi(uint32_t tmem_d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc,
+                        uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Warp-convergent issue: EVERY lane of the issuing warp executes the call with the same operands and the
+// instruction itself is predicated on elect.sync.  Inside an `if (lane == 0)` region the compiler cannot prove
+// the operands warp-uniform and wraps each UMMA into an ELECT / BRA.U.ANY emulation loop (~25 dependent
+// instructions, ~140 cycles per UMMA for the lone thread: twice what the tensor pipe needs for M = N = 128);
+// in convergent code the descriptors sit in uniform registers and a UMMA costs a handful of instructions.
+TC_D void umma_f16_lohi_elect(uint32_t tmem_d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc,
+                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+TC_D void umma_commit_elect(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(tc_smem_u32(bar))
       : "memory");
 }
 // arrive on an mbarrier once all previously issued UMMAs of this thread have completed

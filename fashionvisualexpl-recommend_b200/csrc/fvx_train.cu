@@ -12,6 +12,7 @@
 //                 step += 1 and list reset by the last block
 #include <cuda_bf16.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "fvx_common.cuh"
 #include "fvx_kernels.cuh"
@@ -161,31 +162,20 @@ __device__ __forceinline__ void split_E_planes(const FvxModel& M, int NP, int bl
 }
 
 // What the projection needs from the batch, and nothing else: the local item row of every
-// (triple, side) slot and the planes of E_ext^T.  Launched on the main stream while k_prep (claims +
-// deferred-Adam catch-up) runs beside the projection on the side stream.
-// Slot layout: [pos(H0) | neg(H0)] of the first H0 triples, then [pos(B-H0) | neg(B-H0)] of the rest
-// (H0 = B: the plain [pos(B) | neg(B)] layout).  With H0 = B/2 each half of the batch is a
-// self-contained [pos | neg] block, so the two halves can flow through projection -> scoring ->
-// grad_E as separate launches that overlap each other.
+// (triple, side) slot ([pos(B) | neg(B)]) and the planes of E_ext^T.  Launched on the main stream while
+// k_prep (claims + deferred-Adam catch-up) runs beside the projection on the side stream.
 __global__ void __launch_bounds__(256)
-k_rows_et(FvxModel M, const int32_t* __restrict__ pos, const int32_t* __restrict__ neg, int B, int H0, int nb_rows,
-          int NP) {
+k_rows_et(FvxModel M, const int32_t* __restrict__ pos, const int32_t* __restrict__ neg, int B, int nb_rows, int NP) {
   if ((int)blockIdx.x >= nb_rows) {
     split_E_planes(M, NP, blockIdx.x - nb_rows, gridDim.x - nb_rows);
     return;
   }
-  const int H1 = B - H0;
   for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += nb_rows * blockDim.x) {
     int32_t li = pos[b] - M.item_lo, lj = neg[b] - M.item_lo;
     if (li < 0 || li >= M.item_cnt) li = -1;
     if (lj < 0 || lj >= M.item_cnt) lj = -1;
-    if (b < H0) {
-      M.rows[b] = li;
-      M.rows[H0 + b] = lj;
-    } else {
-      M.rows[2 * H0 + (b - H0)] = li;
-      M.rows[2 * H0 + H1 + (b - H0)] = lj;
-    }
+    M.rows[b] = li;
+    M.rows[B + b] = lj;
   }
 }
 
@@ -894,11 +884,8 @@ int fvx_launch_score_grad(const FvxModel* m, const int32_t* user, int B, int los
       k_score_grad_v4<4, 4, false><<<(int)g2, SG_WARPS * 32, 0, st>>>(*m, user, B, loss_slot, T, wnp, wpitch);
   } else if (dedup) {
     FVX_FAIL(-2, "fvx_bpr_step: the unique-row step needs K %% 4 == 0");
-  } else if (need <= 64 && wnp <= 64) {
-    k_score_grad<2><<<(int)g, SG_WARPS * 32, 0, st>>>(*m, user, B, loss_slot, T, wnp, wpitch);
-  } else if (need <= 256) {
-    k_score_grad<8><<<(int)g, SG_WARPS * 32, 0, st>>>(*m, user, B, loss_slot, T, wnp, wpitch);
-  } else {      // BASELINE configs[4] with embed_d = 256: d + 1 = 257 columns
+  } else {
+    // K % 4 != 0: the scalar kernel, a lane per column (up to 9 x 32 = 288 columns: configs[4] with embed_d = 256)
     k_score_grad<9><<<(int)g, SG_WARPS * 32, 0, st>>>(*m, user, B, loss_slot, T, wnp, wpitch);
   }
   FVX_CHECK_LAUNCH("k_score_grad");
@@ -906,14 +893,14 @@ int fvx_launch_score_grad(const FvxModel* m, const int32_t* user, int B, int los
 }
 
 int fvx_launch_prep(const FvxModel* m, const int32_t* user, const int32_t* pos, const int32_t* neg, int B,
-                    cudaStream_t st, int what, int H0) {
+                    cudaStream_t st, int what) {
   const bool tc = m->D > 0 && m->use_tensor_cores;
   const int NP = tc ? fvx_tc_np(m->de) : m->de;
   const int nb_e = tc ? 32 : 0;
   if (what == FVX_PREP_ROWS) {
     int nb_rows = (B + 255) / 256;
     if (nb_rows > fvx_num_sms() * 4) nb_rows = fvx_num_sms() * 4;
-    k_rows_et<<<nb_rows + nb_e, 256, 0, st>>>(*m, pos, neg, B, (H0 > 0 && H0 < B) ? H0 : B, nb_rows, NP);
+    k_rows_et<<<nb_rows + nb_e, 256, 0, st>>>(*m, pos, neg, B, nb_rows, NP);
     FVX_CHECK_LAUNCH("k_rows_et");
     return 0;
   }
@@ -973,7 +960,7 @@ int fvx_check_model(const FvxModel* m, const char* who) { return check_model(m, 
 // Unique-row step: ON by default where the model carries upos / W_sum;
 // FVX_STEP_DEDUP=0 or the hook below (tests compare the two paths in one process) turn it off.
 static int g_dedup = -1;
-extern "C" int fvx_debug_set_dedup(int on) {   // test hook, not part of fvx.h
+extern "C" int fvx_debug_set_dedup(int on) {
   const int old = g_dedup;
   g_dedup = on ? 1 : 0;
   return old;
@@ -986,33 +973,22 @@ bool fvx_dedup_enabled() {
   return g_dedup == 1;
 }
 
-// Two-half pipelined schedule: OFF by default (measured 425 us vs 408 us per step at B = 65536: the
-// 128-register projection CTA leaves room for one 256-thread block per SM, so the scoring kernel
-// crawls beside it and grad_E of the second half waits).  Tests enable it through the hook below.
-static int g_pipe_min_batch = 0x7fffffff;
-extern "C" int fvx_debug_set_pipe_min_batch(int b) {   // test hook, not part of fvx.h
-  const int old = g_pipe_min_batch;
-  if (b >= 2) g_pipe_min_batch = b;
-  return old;
-}
-
 // Side stream of the two-stream step schedule: one per device, created on first use.
 // FVX_STEP_OVERLAP=0 keeps every kernel of the step on the caller's stream.
 struct SideStream {
   cudaStream_t s;
-  cudaEvent_t fork, prep_done, score_done, upd_done, fwd_done[2], sc_done[2];
+  cudaEvent_t fork, prep_done, score_done, upd_done;
 };
 static SideStream* side_stream() {
-  static SideStream pool[16];
-  static int state[16];   // 0: untried, 1: ready, -1: unavailable
+  static SideStream pool[FVX_MAX_DEV];
+  static int state[FVX_MAX_DEV];   // 0: untried, 1: ready, -1: unavailable
   static int enabled = -1;
   if (enabled < 0) {
     const char* e = getenv("FVX_STEP_OVERLAP");
     enabled = (e && atoi(e) == 0) ? 0 : 1;
   }
   if (!enabled) return nullptr;
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  const int dev = fvx_cur_device();
   if (state[dev] == 0) {
     SideStream& p = pool[dev];
     bool ok = cudaStreamCreateWithFlags(&p.s, cudaStreamNonBlocking) == cudaSuccess;
@@ -1020,10 +996,6 @@ static SideStream* side_stream() {
     ok = ok && cudaEventCreateWithFlags(&p.prep_done, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&p.score_done, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&p.upd_done, cudaEventDisableTiming) == cudaSuccess;
-    for (int h = 0; h < 2; ++h) {
-      ok = ok && cudaEventCreateWithFlags(&p.fwd_done[h], cudaEventDisableTiming) == cudaSuccess;
-      ok = ok && cudaEventCreateWithFlags(&p.sc_done[h], cudaEventDisableTiming) == cudaSuccess;
-    }
     if (!ok) cudaGetLastError();
     state[dev] = ok ? 1 : -1;
   }
@@ -1045,7 +1017,7 @@ void fvx_side_join(cudaStream_t main_stream) {
   cudaStreamWaitEvent(main_stream, p->prep_done, 0);
 }
 
-// Two-stream timeline of the unique-row step (debug hooks, not part of fvx.h): with tracing on, the step
+// Two-stream timeline of the unique-row step (diagnostics, declared in fvx.h): with tracing on, the step
 // records a timing event after every kernel on the stream that kernel runs on; fvx_debug_trace_read
 // returns their times in microseconds relative to the first one.
 enum { TR_BEGIN = 0, TR_UNIQ, TR_FWD, TR_PREP0, TR_PREP1, TR_SCORE, TR_WPL, TR_GRADE, TR_UPD0, TR_UPD1, TR_END, TR_COUNT };
@@ -1073,28 +1045,24 @@ extern "C" int fvx_debug_trace_read(float* us_host) {   // [TR_COUNT]; synchroni
 // phases of one step, in launch order (FVX_N_PHASES entries; see fvx.h)
 enum { PH_PREP = 0, PH_PROJECT, PH_SCORE_GRAD, PH_GRAD_E, PH_UPDATE, PH_COUNT };
 
-// DEFERRED mode, one rank: the Adam step of the rows a batch touched is NOT applied at the end of the step.
-// The gradient stays in g and the row is brought up to date - pending step first, then the zero-gradient
+// DEFERRED mode: the Adam step of the rows a batch touched is NOT applied at the end of the step.  The
+// gradient stays in g and the row is brought up to date - pending step first, then the zero-gradient
 // steps - when it is next needed (replay_row: the catch-up of the next step that touches it, or
 // fvx_adam_flush).  One read-modify-write of (w, m, v, g) per touched row instead of two, and one
-// kernel less per step.  FVX_STEP_MERGED_UPDATE=0 restores the separate row update (A/B measurements).
-static bool merged_update_enabled() {
-  static int on = -1;
-  if (on < 0) { const char* e = getenv("FVX_STEP_MERGED_UPDATE"); on = (e && atoi(e) == 0) ? 0 : 1; }
-  return on == 1;
-}
-bool fvx_merged_update(const FvxModel* m) { return m->adam_mode == FVX_ADAM_DEFERRED && merged_update_enabled(); }
-static int step_update(const FvxModel* m, bool merged, int B, int parts, int gnp, int loss_slot, cudaStream_t st,
-                       int what) {
-  if (merged) {
+// kernel less per step; DENSE / LAZY keep the row update (k_update, tables part).
+bool fvx_merged_update(const FvxModel* m) { return m->adam_mode == FVX_ADAM_DEFERRED; }
+static int step_update(const FvxModel* m, int B, int parts, int gnp, int loss_slot, cudaStream_t st, int what) {
+  if (fvx_merged_update(m)) {
     if (what == FVX_UPD_TABLES) return 0;
     what = FVX_UPD_E;
   }
   return fvx_launch_update(m, B, parts, gnp, m->gE_part, loss_slot, st, what);
 }
 
+// use_side: 1 = two-stream schedule where it pays (VBPR), 0 = everything on `st` (timed entry point, and the
+// small batches of the graph-replayed loop, whose kernels are too short for a fork / join to pay)
 static int bpr_step_impl(const FvxModel* model, const int32_t* user, const int32_t* pos, const int32_t* neg,
-                         int32_t B, int32_t loss_slot, cudaStream_t st, cudaEvent_t* ev) {
+                         int32_t B, int32_t loss_slot, cudaStream_t st, cudaEvent_t* ev, int use_side) {
   if (int rc = check_model(model, "fvx_bpr_step")) return rc;
   const FvxModel& M = *model;
   FVX_CHECK_ARG(user && pos && neg, "fvx_bpr_step: null batch pointer");
@@ -1106,8 +1074,6 @@ static int bpr_step_impl(const FvxModel* model, const int32_t* user, const int32
   FVX_CHECK_ARG(M.rows != nullptr && M.loss != nullptr && M.sync != nullptr, "fvx_bpr_step: null scratch");
   const bool vis = M.D > 0;
   const bool tc = vis && M.use_tensor_cores;
-  const bool merged = M.adam_mode == FVX_ADAM_DEFERRED && merged_update_enabled();
-  const bool fused = tc && fvx_fused_eligible(&M);   // single-pass kernel (fvx_step_fused.cu)
   const int NP = tc ? fvx_tc_np(M.de) : M.de;
   int th_ks = 1;
   if (vis) FVX_CHECK_ARG(M.TH && M.gE_part && M.ge_parts > 0 && (tc || M.W), "fvx_bpr_step: VBPR scratch missing");
@@ -1123,20 +1089,18 @@ static int bpr_step_impl(const FvxModel* model, const int32_t* user, const int32
   }
 #define PHASE(i) do { if (ev) cudaEventRecord(ev[i], st); } while (0)
 
-  // Two-stream schedule (VBPR, untimed calls): the claims + deferred-Adam catch-up touch only the
-  // embedding tables and run BESIDE the projection; the Adam update of the touched rows runs beside
-  // grad_E.  Both side kernels are latency-bound (atomics, dependent row loads), the projection
-  // kernels are bandwidth-bound, so the overlap is nearly free.  The timed entry point keeps
-  // everything on one stream so that each phase is measured alone.
-  SideStream* side = (vis && !ev && !fused) ? side_stream() : nullptr;
+  // Two-stream schedule (VBPR): the claims + deferred-Adam catch-up touch only the embedding tables and run
+  // BESIDE the projection; in DENSE / LAZY mode the Adam update of the touched rows runs beside grad_E.  The
+  // timed entry point keeps everything on one stream so that each phase is measured alone.
+  SideStream* side = (vis && !ev && use_side) ? side_stream() : nullptr;
 
   // Unique-row step: k_uniq_rows lists the distinct catalog rows of the batch (items.list / upos) ahead of
   // the projection; the projection and grad_E run over that list (its length stays on the device), the
-  // scoring kernel reads theta through upos and sums the backward coefficients per listed row, k_w_planes
+  // scoring kernel reads theta through uslot and sums the backward coefficients per listed row, k_w_planes
   // turns the sums into the bf16 planes grad_E reads.  At B = 65 536 on a 100 k catalog 2B slots are
   // ~58 k distinct rows: both contractions shrink by more than half.
-  const bool dedup = tc && !fused && M.upos && M.W_sum && M.uslot && M.K % 4 == 0 && M.K <= 256 && M.d <= 252 && NP <= 256 &&
-                     fvx_dedup_enabled() && !(side && B >= g_pipe_min_batch);
+  const bool dedup = tc && M.upos && M.W_sum && M.uslot && M.K % 4 == 0 && M.K <= 256 && M.d <= 252 && NP <= 256 &&
+                     fvx_dedup_enabled();
   if (dedup) {
     int ks_cap = 8;
     while (ks_cap > 1 && (long long)ks_cap * 2 * B * NP > M.th_cap) ks_cap >>= 1;
@@ -1148,128 +1112,51 @@ static int bpr_step_impl(const FvxModel* model, const int32_t* user, const int32
     // Submission order matters: a kernel submitted first fills the SMs first.  The bandwidth-bound
     // projection kernels (one CTA per SM) go in AHEAD of the latency-bound side kernels, which then
     // run in the registers the projection CTAs leave; the other way round the side kernel's blocks
-    // occupy every SM and the projection starts only when they retire (measured: 27 of the 75 us
-    // of side work overlapped).
-    static int side_first = -1;          // FVX_STEP_SIDE_FIRST=1: the old submission order (A/B measurements)
-    if (side_first < 0) { const char* e_ = getenv("FVX_STEP_SIDE_FIRST"); side_first = (e_ && atoi(e_) == 1) ? 1 : 0; }
-    if (side) {
-      cudaEventRecord(side->fork, st);
-      if (side_first) {
-        cudaStreamWaitEvent(side->s, side->fork, 0);
-        TRACE(TR_PREP0, side->s);
-        if (int rc = fvx_launch_prep(&M, user, pos, neg, B, side->s, FVX_PREP_CLAIMS_LISTED)) return rc;
-        TRACE(TR_PREP1, side->s);
-      }
-    } else {
-      if (int rc = fvx_launch_prep(&M, user, pos, neg, B, st, FVX_PREP_CLAIMS_LISTED)) return rc;
-    }
+    // occupy every SM and the projection starts only when they retire.
+    if (side) cudaEventRecord(side->fork, st);
+    else if (int rc = fvx_launch_prep(&M, user, pos, neg, B, st, FVX_PREP_CLAIMS_LISTED)) return rc;
     PHASE(PH_PROJECT);
     if (int rc = fvx_launch_project_tc(&M, M.items.list, 0, 2 * B, ks_cap, M.TH, st, cnt, 1)) return rc;
     TRACE(TR_FWD, st);
     if (side) {
-      if (!side_first) {
-        cudaStreamWaitEvent(side->s, side->fork, 0);
-        TRACE(TR_PREP0, side->s);
-        if (int rc = fvx_launch_prep(&M, user, pos, neg, B, side->s, FVX_PREP_CLAIMS_LISTED)) return rc;
-        TRACE(TR_PREP1, side->s);
-      }
+      cudaStreamWaitEvent(side->s, side->fork, 0);
+      TRACE(TR_PREP0, side->s);
+      if (int rc = fvx_launch_prep(&M, user, pos, neg, B, side->s, FVX_PREP_CLAIMS_LISTED)) return rc;
+      TRACE(TR_PREP1, side->s);
       cudaEventRecord(side->prep_done, side->s);
       cudaStreamWaitEvent(st, side->prep_done, 0);
     }
     PHASE(PH_SCORE_GRAD);
     if (int rc = fvx_launch_score_grad(&M, user, B, loss_slot, ks_cap, st, 1)) return rc;
     TRACE(TR_SCORE, st);
-    if (side) {
-      cudaEventRecord(side->score_done, st);
-      if (side_first) {
-        cudaStreamWaitEvent(side->s, side->score_done, 0);
-        TRACE(TR_UPD0, side->s);
-        if (int rc = step_update(&M, merged, B, 0, NP, loss_slot, side->s, FVX_UPD_TABLES)) return rc;
-        TRACE(TR_UPD1, side->s);
-      }
-    }
     PHASE(PH_GRAD_E);
     if (int rc = fvx_launch_w_planes(&M, B, st)) return rc;
     TRACE(TR_WPL, st);
-    // The row update may not start before grad_E's CTAs are resident: released by score_done it fills every
-    // SM during k_w_planes and grad_E starts only when its whole grid has retired (measured: grad_E
-    // 198 -> 330 us of the step with the update at 192 -> 244).  It is released by k_w_planes instead;
-    // grad_E, next on the main stream, wins that race and the update runs in the registers it leaves.
-    if (side && !side_first) cudaEventRecord(side->score_done, st);
+    // (DENSE / LAZY) the row update may not start before grad_E's CTAs are resident: released by the scoring
+    // kernel it fills every SM during k_w_planes and grad_E starts only when its whole grid has retired.  It
+    // is released by k_w_planes instead; grad_E, next on the main stream, wins that race.
+    if (side) cudaEventRecord(side->score_done, st);
     int parts = 0;
     if (int rc = fvx_launch_grad_E_tc(&M, M.items.list, 2 * B, &parts, st, cnt)) return rc;
     TRACE(TR_GRADE, st);
     PHASE(PH_UPDATE);
-    if (side) {
-      if (!side_first) {
-        cudaStreamWaitEvent(side->s, side->score_done, 0);
-        TRACE(TR_UPD0, side->s);
-        if (int rc = step_update(&M, merged, B, 0, NP, loss_slot, side->s, FVX_UPD_TABLES)) return rc;
-        TRACE(TR_UPD1, side->s);
-      }
+    if (side && !fvx_merged_update(&M)) {
+      cudaStreamWaitEvent(side->s, side->score_done, 0);
+      TRACE(TR_UPD0, side->s);
+      if (int rc = step_update(&M, B, 0, NP, loss_slot, side->s, FVX_UPD_TABLES)) return rc;
+      TRACE(TR_UPD1, side->s);
       cudaEventRecord(side->upd_done, side->s);
       cudaStreamWaitEvent(st, side->upd_done, 0);      // join: the step is complete on `st`
-      if (int rc = step_update(&M, merged, B, parts, NP, loss_slot, st, FVX_UPD_E)) return rc;
+      if (int rc = step_update(&M, B, parts, NP, loss_slot, st, FVX_UPD_E)) return rc;
     } else {
-      if (int rc = step_update(&M, merged, B, parts, NP, loss_slot, st, FVX_UPD_ALL)) return rc;
+      if (int rc = step_update(&M, B, parts, NP, loss_slot, st, FVX_UPD_ALL)) return rc;
     }
     TRACE(TR_END, st);
     PHASE(PH_COUNT);
     return 0;
   }
-  if (side && tc && B >= g_pipe_min_batch) {
-    // Two half-batches in flight: the main stream runs fwd(h0) fwd(h1) grad_E(h0) grad_E(h1) back
-    // to back (the bandwidth-bound kernels); the side stream runs claims/catch-up, score(h0),
-    // score(h1) and the row update beside them (the latency-bound ones).  Each half is a
-    // self-contained [pos | neg] slot block (k_rows_et), so the existing kernels run on it unchanged
-    // through a copy of the model whose scratch pointers are offset.
-    const int H[2] = {B / 2, B - B / 2};
-    const int pitch = fvx_w_pitch(&M);
-    FvxModel Mh[2];
-    int ks[2];
-    long long th_off = 0;
-    for (int h = 0; h < 2; ++h) {
-      const long long slot0 = h ? 2LL * H[0] : 0;
-      ks[h] = fvx_tc_ksplit(&M, 2LL * H[h]);
-      while (ks[h] > 1 && th_off + (long long)ks[h] * 2 * H[h] * NP > M.th_cap) ks[h] >>= 1;
-      FVX_CHECK_ARG(th_off + (long long)ks[h] * 2 * H[h] * NP <= M.th_cap, "fvx_bpr_step: TH scratch too small");
-      Mh[h] = M;
-      Mh[h].rows = M.rows + slot0;
-      Mh[h].W_hi = M.W_hi + slot0 * pitch;
-      Mh[h].W_lo = M.W_lo + slot0 * pitch;
-      Mh[h].TH = M.TH + th_off;
-      Mh[h].th_cap = M.th_cap - th_off;
-      th_off += (long long)ks[h] * 2 * H[h] * NP;
-    }
-    if (int rc = fvx_launch_prep(&M, user, pos, neg, B, st, FVX_PREP_ROWS, H[0])) return rc;
-    cudaEventRecord(side->fork, st);
-    cudaStreamWaitEvent(side->s, side->fork, 0);
-    if (int rc = fvx_launch_prep(&M, user, pos, neg, B, side->s, FVX_PREP_CLAIMS)) return rc;
-    for (int h = 0; h < 2; ++h) {
-      if (int rc = fvx_launch_project_tc(&Mh[h], Mh[h].rows, 0, 2 * H[h], ks[h], Mh[h].TH, st)) return rc;
-      cudaEventRecord(side->fwd_done[h], st);
-    }
-    for (int h = 0; h < 2; ++h) {
-      cudaStreamWaitEvent(side->s, side->fwd_done[h], 0);
-      if (int rc = fvx_launch_score_grad(&Mh[h], user + (h ? H[0] : 0), H[h], loss_slot, ks[h], side->s)) return rc;
-      cudaEventRecord(side->sc_done[h], side->s);
-    }
-    if (int rc = step_update(&M, merged, B, 0, NP, loss_slot, side->s, FVX_UPD_TABLES)) return rc;
-    cudaEventRecord(side->upd_done, side->s);
-    int parts_total = 0;
-    for (int h = 0; h < 2; ++h) {
-      Mh[h].gE_part = M.gE_part + (size_t)parts_total * M.D * NP;
-      Mh[h].ge_parts = M.ge_parts - parts_total;
-      int parts_h = 0;
-      cudaStreamWaitEvent(st, side->sc_done[h], 0);
-      if (int rc = fvx_launch_grad_E_tc(&Mh[h], Mh[h].rows, 2 * H[h], &parts_h, st)) return rc;
-      parts_total += parts_h;
-    }
-    cudaStreamWaitEvent(st, side->upd_done, 0);      // join: the step is complete on `st`
-    if (int rc = step_update(&M, merged, B, parts_total, NP, loss_slot, st, FVX_UPD_E)) return rc;
-    return 0;
-  }
   if (side) {
+    // one projection per (triple, side) slot: fp32 CUDA-core kernels, or tensor cores without the row lists
     if (int rc = fvx_launch_prep(&M, user, pos, neg, B, st, FVX_PREP_ROWS)) return rc;
     cudaEventRecord(side->fork, st);
     cudaStreamWaitEvent(side->s, side->fork, 0);
@@ -1284,7 +1171,7 @@ static int bpr_step_impl(const FvxModel* model, const int32_t* user, const int32
     if (int rc = fvx_launch_score_grad(&M, user, B, loss_slot, th_ks, st)) return rc;
     cudaEventRecord(side->score_done, st);
     cudaStreamWaitEvent(side->s, side->score_done, 0);
-    if (int rc = step_update(&M, merged, B, 0, NP, loss_slot, side->s, FVX_UPD_TABLES)) return rc;
+    if (int rc = step_update(&M, B, 0, NP, loss_slot, side->s, FVX_UPD_TABLES)) return rc;
     cudaEventRecord(side->upd_done, side->s);
     int parts = 0;
     if (tc) {
@@ -1293,7 +1180,7 @@ static int bpr_step_impl(const FvxModel* model, const int32_t* user, const int32
       if (int rc = fvx_launch_grad_E(&M, M.rows, 2 * B, &parts, st)) return rc;
     }
     cudaStreamWaitEvent(st, side->upd_done, 0);      // join: the step is complete on `st`
-    if (int rc = step_update(&M, merged, B, parts, NP, loss_slot, st, FVX_UPD_E)) return rc;
+    if (int rc = step_update(&M, B, parts, NP, loss_slot, st, FVX_UPD_E)) return rc;
     return 0;
   }
 
@@ -1301,29 +1188,72 @@ static int bpr_step_impl(const FvxModel* model, const int32_t* user, const int32
   if (int rc = fvx_launch_prep(&M, user, pos, neg, B, st)) return rc;
   PHASE(PH_PROJECT);
   int parts = 0;
-  if (fused) {
-    // projection, scoring and grad_E in one launch; the two phases below are empty
-    if (int rc = fvx_launch_step_fused(&M, user, B, loss_slot, &parts, st)) return rc;
-  } else if (tc) {
+  if (tc) {
     if (int rc = fvx_launch_project_tc(&M, M.rows, 0, 2 * B, th_ks, M.TH, st)) return rc;
   } else if (vis) {
     if (int rc = fvx_launch_project(&M, M.rows, 2 * B, M.TH, st)) return rc;
   }
   PHASE(PH_SCORE_GRAD);
-  if (!fused) {
-    if (int rc = fvx_launch_score_grad(&M, user, B, loss_slot, th_ks, st)) return rc;
-  }
+  if (int rc = fvx_launch_score_grad(&M, user, B, loss_slot, th_ks, st)) return rc;
   PHASE(PH_GRAD_E);
-  if (fused) {
-  } else if (tc) {
+  if (tc) {
     if (int rc = fvx_launch_grad_E_tc(&M, M.rows, 2 * B, &parts, st)) return rc;
   } else if (vis) {
     if (int rc = fvx_launch_grad_E(&M, M.rows, 2 * B, &parts, st)) return rc;
   }
   PHASE(PH_UPDATE);
-  if (int rc = step_update(&M, merged, B, parts, NP, loss_slot, st, FVX_UPD_ALL)) return rc;
+  if (int rc = step_update(&M, B, parts, NP, loss_slot, st, FVX_UPD_ALL)) return rc;
   PHASE(PH_COUNT);
 #undef PHASE
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// Small-batch regime (the reference's default batch is 256, train_rec.py:23): a step is a handful of
+// microsecond kernels and the host's launch cost bounds it.  fvx_bpr_steps runs n consecutive steps on
+// batches that lie back to back in epoch-long index arrays: a one-block kernel copies batch `cursor` into the
+// model's staging area and advances the cursor, the step's kernels read the staging area - so the launch
+// sequence of GRAPH_STEPS steps is the same whatever the batch and is captured ONCE into a CUDA graph
+// (per device, keyed by the model struct, the array pointers and B), then replayed.
+#define GRAPH_STEPS 8
+__global__ void k_fetch_batch(const int32_t* __restrict__ user, const int32_t* __restrict__ pos,
+                              const int32_t* __restrict__ neg, int B, int32_t* __restrict__ stage,
+                              long long* __restrict__ cursor) {
+  const long long c = *cursor;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B; i += gridDim.x * blockDim.x) {
+    stage[i] = user[c * B + i];
+    stage[B + i] = pos[c * B + i];
+    stage[2 * B + i] = neg[c * B + i];
+  }
+}
+__global__ void k_cursor_set(long long* cursor, long long v, long long add) { *cursor = add ? *cursor + add : v; }
+
+// the cursor lives behind the three index arrays of the staging area, 8-byte aligned
+static inline long long* stage_cursor(const FvxModel* m) {
+  return reinterpret_cast<long long*>(m->batch_stage + ((3 * (size_t)m->max_batch + 1) & ~(size_t)1));
+}
+
+struct StepGraph {
+  FvxModel model;
+  const int32_t *user, *pos, *neg;
+  int B, loss_slot;
+  cudaGraphExec_t exec;
+};
+static StepGraph g_graphs[FVX_MAX_DEV][4];
+static int g_graph_next[FVX_MAX_DEV];
+
+static int one_staged_step(const FvxModel* m, const int32_t* user, const int32_t* pos, const int32_t* neg, int B,
+                           int loss_slot, cudaStream_t st) {
+  long long* cursor = stage_cursor(m);
+  int g = (B + 255) / 256;
+  if (g > fvx_num_sms()) g = fvx_num_sms();
+  k_fetch_batch<<<g, 256, 0, st>>>(user, pos, neg, B, m->batch_stage, cursor);
+  FVX_CHECK_LAUNCH("k_fetch_batch");
+  if (int rc = bpr_step_impl(m, m->batch_stage, m->batch_stage + B, m->batch_stage + 2 * B, B, loss_slot, st, nullptr,
+                             B >= 16384 ? 1 : 0))
+    return rc;
+  k_cursor_set<<<1, 1, 0, st>>>(cursor, 0, 1);
+  FVX_CHECK_LAUNCH("k_cursor_set");
   return 0;
 }
 
@@ -1331,7 +1261,58 @@ extern "C" {
 
 int fvx_bpr_step(const FvxModel* model, const int32_t* user, const int32_t* pos, const int32_t* neg,
                  int32_t B, int32_t loss_slot, fvx_stream_t stream) {
-  return bpr_step_impl(model, user, pos, neg, B, loss_slot, fvx_cu(stream), nullptr);
+  return bpr_step_impl(model, user, pos, neg, B, loss_slot, fvx_cu(stream), nullptr, 1);
+}
+
+int fvx_bpr_steps(const FvxModel* model, const int32_t* user, const int32_t* pos, const int32_t* neg,
+                  int64_t first, int32_t n_steps, int32_t B, int32_t loss_slot, fvx_stream_t stream) {
+  if (int rc = check_model(model, "fvx_bpr_steps")) return rc;
+  FVX_CHECK_ARG(user && pos && neg && first >= 0 && n_steps >= 0, "fvx_bpr_steps: bad arguments");
+  FVX_CHECK_ARG(model->batch_stage != nullptr, "fvx_bpr_steps: FvxModel.batch_stage is not allocated");
+  FVX_CHECK_ARG(B >= 1 && B <= model->max_batch, "fvx_bpr_steps: B=%d outside [1, max_batch=%d]", B, model->max_batch);
+  cudaStream_t st = fvx_cu(stream);
+  long long* cursor = stage_cursor(model);
+  k_cursor_set<<<1, 1, 0, st>>>(cursor, (long long)first, 0);
+  FVX_CHECK_LAUNCH("k_cursor_set");
+  int left = n_steps;
+  if (left >= GRAPH_STEPS) {
+    const int dev = fvx_cur_device();
+    StepGraph* G = nullptr;
+    for (int i = 0; i < 4; ++i) {
+      StepGraph& c = g_graphs[dev][i];
+      if (c.exec && c.user == user && c.pos == pos && c.neg == neg && c.B == B && c.loss_slot == loss_slot &&
+          memcmp(&c.model, model, sizeof(FvxModel)) == 0) { G = &c; break; }
+    }
+    if (!G) {
+      StepGraph& c = g_graphs[dev][g_graph_next[dev]++ & 3];
+      if (c.exec) { cudaGraphExecDestroy(c.exec); c.exec = nullptr; }
+      if (B >= 16384) side_stream();       // per-device helpers are created before the capture starts
+      // captured on a stream of our own (the caller's may be the legacy default stream, which cannot be
+      // captured) and launched on the caller's
+      static cudaStream_t cap[FVX_MAX_DEV];
+      if (!cap[dev] && cudaStreamCreateWithFlags(&cap[dev], cudaStreamNonBlocking) != cudaSuccess)
+        FVX_FAIL(-3, "fvx_bpr_steps: cannot create the capture stream: %s", cudaGetErrorString(cudaGetLastError()));
+      cudaGraph_t graph = nullptr;
+      if (cudaStreamBeginCapture(cap[dev], cudaStreamCaptureModeThreadLocal) != cudaSuccess)
+        FVX_FAIL(-3, "fvx_bpr_steps: cannot begin the capture: %s", cudaGetErrorString(cudaGetLastError()));
+      int rc = 0;
+      for (int s = 0; s < GRAPH_STEPS && rc == 0; ++s) rc = one_staged_step(model, user, pos, neg, B, loss_slot, cap[dev]);
+      cudaError_t ce = cudaStreamEndCapture(cap[dev], &graph);
+      if (rc != 0) { if (graph) cudaGraphDestroy(graph); return rc; }
+      if (ce != cudaSuccess || !graph) FVX_FAIL(-3, "fvx_bpr_steps: capture failed: %s", cudaGetErrorString(ce));
+      ce = cudaGraphInstantiate(&c.exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (ce != cudaSuccess) { c.exec = nullptr; FVX_FAIL(-3, "fvx_bpr_steps: instantiate failed: %s", cudaGetErrorString(ce)); }
+      c.model = *model; c.user = user; c.pos = pos; c.neg = neg; c.B = B; c.loss_slot = loss_slot;
+      G = &c;
+    }
+    for (; left >= GRAPH_STEPS; left -= GRAPH_STEPS)
+      if (cudaGraphLaunch(G->exec, st) != cudaSuccess)
+        FVX_FAIL(-3, "fvx_bpr_steps: graph launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+  }
+  for (; left > 0; --left)
+    if (int rc = one_staged_step(model, user, pos, neg, B, loss_slot, st)) return rc;
+  return 0;
 }
 
 int fvx_bpr_step_timed(const FvxModel* model, const int32_t* user, const int32_t* pos, const int32_t* neg,
@@ -1340,7 +1321,7 @@ int fvx_bpr_step_timed(const FvxModel* model, const int32_t* user, const int32_t
   cudaEvent_t ev[PH_COUNT + 1];
   for (int i = 0; i <= PH_COUNT; ++i)
     if (cudaEventCreate(&ev[i]) != cudaSuccess) FVX_FAIL(-3, "fvx_bpr_step_timed: cudaEventCreate failed");
-  int rc = bpr_step_impl(model, user, pos, neg, B, loss_slot, fvx_cu(stream), ev);
+  int rc = bpr_step_impl(model, user, pos, neg, B, loss_slot, fvx_cu(stream), ev, 0);
   if (rc == 0) {
     cudaError_t e = cudaEventSynchronize(ev[PH_COUNT]);
     if (e != cudaSuccess) {

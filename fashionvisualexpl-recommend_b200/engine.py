@@ -30,7 +30,7 @@ def _r4(x):
 class Engine:
     def __init__(self, num_users, num_items, K, d=0, D=0, lr=1e-3, reg=0.0, adam_mode="deferred",
                  max_batch=4096, device="cuda:0", item_lo=0, item_cnt=None, loss_slots=4096,
-                 ge_parts=80, seed=0, use_tensor_cores=False, fused_step=False, unique_rows=True):
+                 ge_parts=80, seed=0, use_tensor_cores=False, unique_rows=True):
         if not torch.cuda.is_available():
             raise _lib.FvxError("no CUDA device: the fvx engine has no CPU path")
         _lib.load()
@@ -64,6 +64,7 @@ class Engine:
         self.loss_t = torch.zeros(self.loss_slots, dtype=torch.float64, device=dev)
         self.rows_t = torch.zeros(2 * self.max_batch, **i32)
         self.sync_t = torch.zeros(4, **i32)
+        self.stage_t = torch.zeros(3 * self.max_batch + 4, **i32)     # fvx_bpr_steps: batch in flight + cursor
         self.cmap_t = torch.zeros(6 * self.max_batch, **i32) if (self.item_lo or self.Ic != self.I) else None
         self.F = self.F_pl = None
         self.ET_hi = self.ET_lo = self.W_hi = self.W_lo = None
@@ -74,10 +75,6 @@ class Engine:
             # wider / ragged models (BASELINE configs[4] with embed_d = 256) run on the exact fp32
             # CUDA-core kernels - still this library, still the GPU
             self.use_tensor_cores = False
-        # opt-in single-pass step kernel (fvx_step_fused.cu: correct, but measured slower than the
-        # two-kernel path in round 1 - DESIGN.md section 3); the library falls back to the two-kernel
-        # path when the geometry is not eligible
-        self.fused_step = bool(fused_step) and self.use_tensor_cores
         if self.D:
             self.E = torch.zeros(self.D, self.de, **f32)
             self.mE, self.vE = torch.zeros_like(self.E), torch.zeros_like(self.E)
@@ -120,23 +117,38 @@ class Engine:
     # ---- parameters ---------------------------------------------------------------------
     def init_glorot(self, seed=0):
         """GlorotUniform with the reference's 2-D shapes (BPRMF.py:35,48-50; VBPR.py:44-54);
-        Bi = 0.  TF's RNG stream is not reproducible, so values differ from a TF run."""
-        g = torch.Generator(device=self.device).manual_seed(int(seed))
+        Bi = 0.  TF's RNG stream is not reproducible, so values differ from a TF run.
 
-        def glorot(r, c, rows, cols):
-            lim = math.sqrt(6.0 / (r + c))
-            return (torch.rand(rows, cols, generator=g, device=self.device) * 2 - 1) * lim
+        One generator PER TABLE, keyed by (seed, table): every rank of an item-sharded job draws the
+        same replicated tables (Gu, Tu, E, Bp) whatever its shard size, and the item table is drawn as
+        the whole [I, K] matrix in fixed row chunks of which a rank keeps its own rows - the sharded
+        model starts as the single-GPU model does (tests/test_host_logic.py checks the slices)."""
+        dev = self.device
+
+        def gen(table):
+            return torch.Generator(device=dev).manual_seed(int(seed) * 1000003 + table)
+
+        def glorot(g, fan_r, fan_c, rows, cols):
+            lim = math.sqrt(6.0 / (fan_r + fan_c))
+            return (torch.rand(rows, cols, generator=g, device=dev) * 2 - 1) * lim
 
         uw, iw = self.users["w"], self.items["w"]
         uw.zero_()
         iw.zero_()
-        uw[:, :self.K] = glorot(self.U, self.K, self.U, self.K)
-        iw[:, :self.K] = glorot(self.I, self.K, self.Ic, self.K)
+        uw[:, :self.K] = glorot(gen(1), self.U, self.K, self.U, self.K)
+        g, chunk = gen(2), 65536
+        lo, hi = self.item_lo, self.item_lo + self.Ic
+        for s0 in range(0, self.I, chunk):                  # the same stream on every rank: all chunks are drawn
+            s1 = min(self.I, s0 + chunk)
+            blk = glorot(g, self.I, self.K, s1 - s0, self.K)
+            a, b = max(s0, lo), min(s1, hi)
+            if a < b:
+                iw[a - lo:b - lo, :self.K] = blk[a - s0:b - s0]
         if self.D:
-            uw[:, self.K:self.K + self.d] = glorot(self.U, self.d, self.U, self.d)
+            uw[:, self.K:self.K + self.d] = glorot(gen(3), self.U, self.d, self.U, self.d)
             self.E.zero_()
-            self.E[:, :self.d] = glorot(self.D, self.d, self.D, self.d)
-            self.E[:, self.d:self.d + 1] = glorot(self.D, 1, self.D, 1)
+            self.E[:, :self.d] = glorot(gen(4), self.D, self.d, self.D, self.d)
+            self.E[:, self.d:self.d + 1] = glorot(gen(5), self.D, 1, self.D, 1)
 
     # reference attribute names as views into the packed tables
     @property
@@ -217,12 +229,18 @@ class Engine:
             m.sync = ptr(self.sync_t)
             m.cmap = ptr(self.cmap_t)
             m.max_batch = self.max_batch
-            m.use_tensor_cores = (2 if self.fused_step else 1) if self.use_tensor_cores else 0
+            m.use_tensor_cores = 1 if self.use_tensor_cores else 0
             m.upos, m.W_sum, m.uslot = ptr(self.upos_t), ptr(self.W_sum), ptr(self.uslot_t)
+            m.batch_stage = ptr(self.stage_t)
             self._struct = m
         return self._struct
 
     def set_hyper(self, lr=None, reg=None):
+        """Changes lr / reg for the steps that follow.  In DEFERRED mode the last Adam step of the touched rows
+        (and their skipped zero-gradient steps) is still pending and would be replayed with the NEW lr, so the
+        tables are flushed first: steps already taken keep the lr they were taken with."""
+        if lr is not None and float(lr) != self.lr and self._struct is not None:
+            self.flush()
         if lr is not None:
             self.lr = float(lr)
         if reg is not None:
@@ -240,6 +258,14 @@ class Engine:
         """One optimiser step (fvx_bpr_step); asynchronous.  Index tensors: int32 CUDA."""
         B = user.numel()
         call("fvx_bpr_step", C.byref(self.struct()), ptr(user), ptr(pos), ptr(neg), B, loss_slot, stream_ptr())
+
+    def steps(self, user, pos, neg, first, n_steps, B, loss_slot=0):
+        """``n_steps`` consecutive optimiser steps on the batches ``[(first + s) * B, (first + s + 1) * B)`` of
+        epoch-long index tensors (fvx_bpr_steps: the launches of 8 steps replayed as one CUDA graph)."""
+        if (first + n_steps) * B > user.numel():
+            raise ValueError("steps(): batches run past the end of the index arrays")
+        call("fvx_bpr_steps", C.byref(self.struct()), ptr(user), ptr(pos), ptr(neg), int(first), int(n_steps), int(B),
+             loss_slot, stream_ptr())
 
     def step_timed(self, user, pos, neg, loss_slot=0):
         """Profiling step: returns {phase: ms} (synchronises)."""
@@ -321,7 +347,7 @@ class Engine:
         ids = torch.empty(n, k, dtype=torch.int32, device=self.device)
         sc = torch.empty(n, k, dtype=torch.float32, device=self.device)
         tc = self.use_tensor_cores if tc is None else tc
-        if tc and thr_scores is None and self.K + self.d + 3 <= 128 and n > 0:
+        if tc and thr_scores is None and self.K + self.d + 3 <= 448 and n > 0:
             ws = self._eval_ws(n)
             call("fvx_score_topk_tc", C.byref(self.struct()), ptr(self.theta()), u0, u1, ptr(mask_row_ptr),
                  ptr(mask_col), k, ptr(ids), ptr(sc), C.byref(ws["struct"]), stream_ptr())
@@ -359,7 +385,7 @@ class Engine:
         tc = self.use_tensor_cores if tc is None else tc
         if n <= 0:
             return ids, sc
-        if tc and self.K + self.d + 3 <= 128:
+        if tc and self.K + self.d + 3 <= 448:
             ws = self._eval_ws(n, struct=m, Ic=view["Ic"], key="_ws_view")
             call("fvx_score_topk_tc", C.byref(m), ptr(th), u0, u1, ptr(mask_row_ptr), ptr(mask_col), k, ptr(ids),
                  ptr(sc), C.byref(ws["struct"]), stream_ptr())
@@ -382,9 +408,13 @@ class Engine:
         struct = self.struct() if struct is None else struct
         Ic = self.Ic if Ic is None else Ic
         call("fvx_eval_ws_query", C.byref(struct), n_users, C.byref(q))
-        if ws is None or ws["n"] != n_users or ws["KP"] != q.KP or ws["splits"] != q.splits or ws["Ic"] != Ic:
+        if ws is None or ws["n"] != n_users or ws["KP"] != q.KP or ws["splits"] != q.splits or ws["Ic"] != Ic \
+                or ws["n_ut"] != q.n_ut:
             dv = self.device
-            ws = {"n": n_users, "KP": q.KP, "splits": q.splits, "lists": q.lists, "Ic": Ic,
+            gm = getattr(self, "_ws_gmax", None)            # per-CTA group maxima: shared by all workspaces
+            if gm is None or gm.numel() < q.gmax_elems:
+                gm = self._ws_gmax = torch.empty(q.gmax_elems, dtype=torch.float32, device=dv)
+            ws = {"n": n_users, "KP": q.KP, "splits": q.splits, "lists": q.lists, "Ic": Ic, "n_ut": q.n_ut,
                   "A": torch.empty(n_users * q.KP, dtype=torch.uint16, device=dv),
                   "Bm": torch.empty(Ic * q.KP, dtype=torch.uint16, device=dv),
                   "epsa": torch.empty(n_users, dtype=torch.float32, device=dv),
@@ -393,11 +423,13 @@ class Engine:
                   "thr": torch.zeros(n_users, dtype=torch.int32, device=dv),
                   "cand": torch.empty(q.lists * q.cap, dtype=torch.int64, device=dv),
                   "ccount": torch.zeros(q.lists, dtype=torch.int32, device=dv),
-                  "flags": torch.zeros(n_users, dtype=torch.int32, device=dv)}
+                  "flags": torch.zeros(n_users, dtype=torch.int32, device=dv), "gmax": gm}
             q.A, q.Bm, q.epsa, q.nb, q.stat = ptr(ws["A"]), ptr(ws["Bm"]), ptr(ws["epsa"]), ptr(ws["nb"]), ptr(ws["stat"])
             q.cand, q.ccount, q.flags, q.thr = ptr(ws["cand"]), ptr(ws["ccount"]), ptr(ws["flags"]), ptr(ws["thr"])
+            q.gmax = ptr(gm)
             ws["struct"] = q
             setattr(self, key, ws)
+        ws["struct"].a_stride = int(getattr(self, "eval_a_stride", 1))
         return ws
 
 

@@ -30,7 +30,7 @@ extern "C" {
 
 typedef void* fvx_stream_t; /* cudaStream_t */
 
-#define FVX_ABI_VERSION 3
+#define FVX_ABI_VERSION 4
 
 /* Adam semantics.  The reference's Keras Adam moves
  * EVERY row of an embedding table on every step (rows without gradient keep
@@ -119,6 +119,8 @@ typedef struct FvxModel {
   float* W_sum;         /* [2*max_batch, NP] fp32 sums of the backward coefficients per listed
                            row; all-zero between steps                                        */
   int32_t* uslot;       /* [2*max_batch] list position of the row of each (triple, side) slot  */
+  int32_t* batch_stage; /* [3*max_batch + 4] staging area of fvx_bpr_steps: the (user | pos | neg) indices of
+                           the batch in flight and the 64-bit batch cursor (may be NULL otherwise)     */
 } FvxModel;
 
 /* ---- library ------------------------------------------------------------------ */
@@ -163,6 +165,15 @@ int fvx_sample_negatives(const int64_t* row_ptr, const int32_t* col_sorted, cons
  * loss (BPRMF.py:104-115 / VBPR.py:117-130) into model->loss[loss_slot]. */
 int fvx_bpr_step(const FvxModel* model, const int32_t* user, const int32_t* pos,
                  const int32_t* neg, int32_t B, int32_t loss_slot, fvx_stream_t stream);
+
+/* n_steps consecutive optimiser steps on batches that lie back to back in epoch-long index arrays (what
+ * DataLoader.next_triple_batch yields as consecutive slices, dataset.py:116-122): step s trains on triples
+ * [(first + s) * B, (first + s + 1) * B).  The launch sequence of 8 steps is captured ONCE into a CUDA graph
+ * (per device, keyed by the model struct, the array pointers, B and loss_slot) and replayed: at the
+ * reference's default batch of 256 (train_rec.py:23) a step is a handful of microsecond kernels and the
+ * host's launch cost would bound it.  Needs FvxModel.batch_stage.  Losses add up in loss[loss_slot]. */
+int fvx_bpr_steps(const FvxModel* model, const int32_t* user, const int32_t* pos, const int32_t* neg,
+                  int64_t first, int32_t n_steps, int32_t B, int32_t loss_slot, fvx_stream_t stream);
 
 /* Profiling variant of fvx_bpr_step: same work, CUDA events between the phases, and a
  * host synchronisation at the end (so it cannot be graph-captured).  phase_ms_host
@@ -243,16 +254,16 @@ int fvx_score_topk_users(const FvxModel* model, const float* theta_ext, const in
                          const int64_t* mask_row_ptr, const int32_t* mask_col, int32_t k,
                          int32_t* out_ids, float* out_scores, fvx_stream_t stream);
 
-/* Tensor-core variant of fvx_score_topk (tcgen05 + TMA; top-k only, no rank counts):
- * a bf16 sweep selects, per user, every item whose bf16 score is within the rounding
- * bound of the running k-th best, then the candidates are re-scored in fp32 with the
- * same arithmetic as fvx_score_topk, so both return identical ids and scores.
- * The caller owns the workspace: fill KP / splits / cap with fvx_eval_ws_query() and
- * allocate A [u_cap*KP] bf16, Bm [i_cap*KP] bf16, epsa [u_cap] f32, nb [i_cap] f32, stat [2] f32,
- * cand [lists*cap] u64, ccount [lists] i32, flags [u_cap] i32, thr [u_cap] u32.
- * Rows whose candidate list overflows (or users with more than ~180 train items) are recomputed
- * by the exact fp32 kernel inside the same call; flags[u-u0] != 0 tells which (diagnostics only).
- * Needs K+d+3 <= 128. */
+/* Tensor-core variant of fvx_score_topk (tcgen05 + TMA; top-k only, no rank counts): a bf16 sweep over
+ * the catalog finds, per user, a lower bound of the (k + #train)-th best score from the maxima of column
+ * groups, a second sweep collects every item whose bf16 score (plus its rounding bound) reaches it, and the
+ * candidates are re-scored in fp32 with the same arithmetic as fvx_score_topk, so both return identical ids
+ * and scores.  The caller owns the workspace: fill KP / splits / cap / n_ut / lists / gmax_elems with
+ * fvx_eval_ws_query() and allocate A [u_cap*KP] bf16, Bm [i_cap*KP] bf16, epsa [u_cap] f32, nb [i_cap] f32,
+ * stat [2] f32, cand [lists*cap] u64, ccount [lists] i32, flags [u_cap] i32, thr [u_cap] u32,
+ * gmax [gmax_elems] f32.  a_stride (0 / 1: every tile, 2: every other tile) thins the bounds sweep.
+ * Rows whose candidate list overflows are recomputed by the exact fp32 kernel inside the same call;
+ * flags[u-u0] != 0 tells which (diagnostics only).  Needs K+d+3 <= 448. */
 typedef struct FvxEvalWs {
   uint16_t* A;
   uint16_t* Bm;
@@ -263,8 +274,10 @@ typedef struct FvxEvalWs {
   int32_t* ccount;
   int32_t* flags;
   uint32_t* thr;
+  float* gmax;
   int64_t lists;
-  int32_t u_cap, i_cap, KP, splits, cap, _pad;
+  int64_t gmax_elems;
+  int32_t u_cap, i_cap, KP, splits, cap, n_ut, a_stride, _pad;
 } FvxEvalWs;
 int fvx_eval_ws_query(const FvxModel* model, int32_t n_users, FvxEvalWs* ws);
 int fvx_score_topk_tc(const FvxModel* model, const float* theta_ext, int32_t u0, int32_t u1,
@@ -297,6 +310,16 @@ int fvx_grad_e_rows(const FvxModel* model, const int32_t* rows, int64_t nrows, c
 /* hi = bf16(F), lo = bf16(F - float(hi)) : 4 bytes/element like fp32, ~2^-17 relative.
  * src fp32 [n_rows, D] -> dst [n_rows, D/64, 2, 64] (the FvxModel.F_pl layout); D % 64 == 0. */
 int fvx_split_planes(const float* src, uint16_t* dst, int64_t n_rows, int32_t D, fvx_stream_t stream);
+
+/* ---- diagnostics (tests and profiling scripts; no product code calls them) ------------------------ */
+/* Unique-row step on (1) / off (0: one projection per slot) for this process; returns the previous value
+ * (-1: the FVX_STEP_DEDUP environment default was still in force). */
+int fvx_debug_set_dedup(int on);
+/* Two-stream timeline of fvx_bpr_step: with tracing on the step records a timing event after every kernel;
+ * fvx_debug_trace_read copies 11 times in microseconds (begin, uniq, fwd, prep0, prep1, score, w_planes,
+ * grad_E, upd0, upd1, end) relative to the first one and synchronises. */
+int fvx_debug_trace(int on);
+int fvx_debug_trace_read(float* us_host);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,70 @@
+#!/usr/bin/env python
+"""One full-catalog top-k sweep (BASELINE configs[1] shape by default) for profiling.
+
+    python scripts/eval_profile.py                     # CUDA-event time of the whole sweep (best of 3)
+    ncu --metrics gpu__time_duration.sum ... python scripts/eval_profile.py --sweeps 1    # per-kernel split
+    ncu --set full -k regex:'k_topk|k_rescore|k_pack|k_tile' ... python scripts/eval_profile.py --sweeps 1
+
+The model is trained for --train_steps steps first so that scores are not those of a random init.
+"""
+import argparse, json, os, sys
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from fvx.engine import Engine
+from fvx import synth
+from fvx.dataset.dataset import DataLoader
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--users", type=int, default=40000)
+ap.add_argument("--items", type=int, default=100000)
+ap.add_argument("--K", type=int, default=64)
+ap.add_argument("--d", type=int, default=20)
+ap.add_argument("--D", type=int, default=2048)
+ap.add_argument("--k", type=int, default=100)
+ap.add_argument("--train_steps", type=int, default=60)
+ap.add_argument("--batch", type=int, default=65536)
+ap.add_argument("--sweeps", type=int, default=3)
+ap.add_argument("--rank_counts", type=int, default=0)
+a = ap.parse_args()
+dev = torch.device("cuda:0")
+inter = synth.make_interactions(a.users, a.items, seed=1234)
+p = argparse.Namespace(dataset="x", batch_size=a.batch, epochs=10 ** 6, sampler="device", seed=0)
+data = DataLoader(p, interactions=inter)
+e = Engine(a.users, a.items, a.K, d=a.d, D=a.D, lr=1e-3, reg=1e-5, max_batch=a.batch, use_tensor_cores=True)
+if a.D:
+    g = torch.Generator(device=dev).manual_seed(4321)
+    F = torch.randn(a.items, a.D, generator=g, device=dev).clamp_(min=0) * torch.empty(a.items, a.D, device=dev).exponential_(1.0, generator=g)
+    F /= F.abs().max()
+    e.set_features(F, keep_fp32=False)
+    del F
+it = data.next_triple_batch(str(dev))
+for _ in range(a.train_steps):
+    e.step(*next(it))
+e.flush()
+st = data.device_state(str(dev))
+torch.cuda.synchronize()
+
+
+def sweep():
+    e.theta(refresh=True)
+    return e.score_topk(st["row_ptr"], st["col_sorted"], a.k)
+
+
+best = 1e30
+for i in range(a.sweeps + 1):          # the first sweep allocates the workspace
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record(); ids, sc = sweep(); t1.record(); torch.cuda.synchronize()
+    if i > 0 or a.sweeps == 0:
+        best = min(best, t0.elapsed_time(t1))
+out = {"users": a.users, "items": a.items, "K": a.K, "d": a.d, "k": a.k, "sweep_ms": best,
+       "users_per_s": a.users / best * 1e3, "fallback_rows": e.tc_overflow_rows,
+       "checksum": int(ids.to(torch.int64).sum().item())}
+if a.rank_counts:
+    held = torch.randint(0, a.items, (a.users, 2), device=dev, dtype=torch.int32)
+    who = torch.arange(a.users, device=dev, dtype=torch.int32).repeat_interleave(2)
+    thr = e.score_pairs(who, held.reshape(-1).contiguous()).reshape(a.users, 2).contiguous()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e.rank_counts(st["row_ptr"], st["col_sorted"], thr); torch.cuda.synchronize()
+    t0.record(); c = e.rank_counts(st["row_ptr"], st["col_sorted"], thr); t1.record(); torch.cuda.synchronize()
+    out["rank_counts_ms"] = t0.elapsed_time(t1)
+print(json.dumps(out))

@@ -83,21 +83,15 @@ def _perturbed_oracle(P, F, batches, reg, lr, rel=2.0 ** -16, seed=7):
 
 
 @pytest.mark.parametrize("mode", ["dense", "deferred"])
-@pytest.mark.parametrize("K,d,D,B,fused", [(64, 20, 256, 512, False), (16, 64, 128, 96, False), (8, 5, 128, 33, False),
-                                             (32, 20, 2048, 1024, False),
-                                             (256, 20, 4096, 512, False),     # BASELINE configs[4]: K = 256, 4096-d features
-                                             (256, 255, 4096, 96, False),     # ... and the widest tensor-core operand (NP = 256)
-                                             # single-pass cluster kernel (fvx_step_fused.cu): whole tiles, a ragged
-                                             # last tile, fewer triples than one tile, the narrow slice (D = 1024)
-                                             (32, 20, 2048, 1024, True), (64, 20, 2048, 1000, True),
-                                             (64, 20, 2048, 7, True), (16, 8, 1024, 333, True), (64, 31, 2048, 97, True)])
-def test_train_steps_tensor_cores_match_oracle(K, d, D, B, fused, mode):
+@pytest.mark.parametrize("K,d,D,B", [(64, 20, 256, 512), (16, 64, 128, 96), (8, 5, 128, 33), (32, 20, 2048, 1024),
+                                       (256, 20, 4096, 512),      # BASELINE configs[4]: K = 256, 4096-d features
+                                       (256, 255, 4096, 96)])     # ... and the widest tensor-core operand (NP = 256)
+def test_train_steps_tensor_cores_match_oracle(K, d, D, B, mode):
     U, I, steps, lr, reg = 700, 900, 20, 0.001, 1e-3
     P, F, rng = _random_problem(U, I, K, d, D, seed=K + d)
-    e = _engine(U, I, K, d=d, D=D, lr=lr, reg=reg, adam_mode=mode, max_batch=B, use_tensor_cores=True,
-                fused_step=fused)
+    e = _engine(U, I, K, d=d, D=D, lr=lr, reg=reg, adam_mode=mode, max_batch=B, use_tensor_cores=True)
     e.set_features(F, keep_fp32=False)                    # the step must not need the fp32 copy
-    assert e.struct().use_tensor_cores == (2 if fused else 1)
+    assert e.struct().use_tensor_cores == 1
     e.load_params(P)
     batches = _user_contiguous_batches(rng, U, I, B, steps)
     P32, P64, l32, l64 = _oracle_pair(P, F, batches, reg, lr)
@@ -115,85 +109,45 @@ def test_train_steps_tensor_cores_match_oracle(K, d, D, B, fused, mode):
         assert (dlt > REL).mean() <= 1e-3, (mode, k, "elements beyond 1e-4", int((dlt > REL).sum()), dlt.size)
 
 
-@pytest.mark.parametrize("tile", ["64", "48"])
-def test_fused_step_equals_two_kernel_path(tile, monkeypatch):
-    """The single-pass kernel against the projection -> score -> grad_E kernels on the same batches,
-    including triples whose item id lies outside the catalog (ignored by both) and a user run that
-    crosses tile and cluster boundaries.  Run in a subprocess-free way for the default tile; the
-    48-row / 3-stage variant is selected by FVX_FUSED_TILE before the library first launches it."""
-    import os
-    import subprocess
-    import sys
-    if tile == "48":
-        # the tile shape is latched at the first fused launch of a process: use a fresh one
-        env = dict(os.environ, FVX_FUSED_TILE="48", FVX_FUSED_CHILD="1")
-        r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", __file__, "-k",
-                            "test_fused_step_equals_two_kernel_path and 64", "-m", "gpu"],
-                           env=env, capture_output=True, text=True, cwd=os.path.dirname(os.path.dirname(__file__)))
-        assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
-        return
-    U, I, K, d, D, B, steps = 500, 700, 64, 20, 2048, 2500, 6
-    P, F, rng = _random_problem(U, I, K, d, D, seed=11)
+@pytest.mark.parametrize("K,d,D,B,tc", [(64, 20, 256, 256, True), (64, 20, 2048, 300, True), (32, 0, 0, 256, False),
+                                          (16, 8, 128, 64, False)])
+def test_graph_replayed_steps_equal_single_steps(K, d, D, B, tc):
+    """fvx_bpr_steps (small-batch regime: 8 steps captured once into a CUDA graph and replayed over batches
+    that lie back to back in epoch-long index arrays, plus ungraphed remainder steps) against the same
+    batches fed one fvx_bpr_step at a time: same losses, same parameters; and against the fp64 oracle."""
+    U, I, lr, reg, steps = 500, 800, 1e-3, 1e-4, 21            # 2 graph launches + 5 plain steps
+    P, F, rng = _random_problem(U, I, K, d, D, seed=K + B)
     es = []
-    for fused in (False, True):
-        e = _engine(U, I, K, d=d, D=D, lr=1e-3, reg=1e-4, max_batch=B, use_tensor_cores=True, fused_step=fused)
-        e.set_features(F, keep_fp32=False)
+    for _ in range(2):
+        e = _engine(U, I, K, d=d, D=D, lr=lr, reg=reg, max_batch=B, use_tensor_cores=tc)
+        if D:
+            e.set_features(F)
         e.load_params(P)
         es.append(e)
-    batches = _user_contiguous_batches(rng, U, I, B, steps)
-    for s, (u, i, j) in enumerate(batches):
-        i = i.copy(); j = j.copy()
-        i[5::97] = I + 3                                   # outside the catalog: triple ignored
-        j[11::89] = -1
-        losses = []
-        for e in es:
-            e.step(_dev(u), _dev(i), _dev(j), loss_slot=0)
-            losses.append(e.read_loss(0))
-        assert losses[1] == pytest.approx(losses[0], rel=2e-6), s
+    batches = _user_contiguous_batches(rng, U, I, B, steps + 3)
+    eu, ep, en = (_dev(np.concatenate([b[c] for b in batches])) for c in range(3))
+    first = 2                                                # the replay starts at batch 2 of the arrays
+    _, P64, _, l64 = _oracle_pair(P, F, batches[first:first + steps], reg, lr)
+    for s in range(steps):
+        es[0].step(*(_dev(x) for x in batches[first + s]), loss_slot=0)
+    es[1].steps(eu, ep, en, first, steps, B, loss_slot=0)
+    la, lb = es[0].read_loss(0), es[1].read_loss(0)
+    assert la == pytest.approx(float(np.sum(l64)), rel=REL)
+    assert lb == pytest.approx(la, rel=1e-6)
+    assert es[0].steps_done() == es[1].steps_done() == steps
+    # a second call replays the cached graph from another position
+    es[0].step(*(_dev(x) for x in batches[0]), loss_slot=1)
+    es[1].steps(eu, ep, en, 0, 1, B, loss_slot=1)
+    assert es[1].read_loss(1) == pytest.approx(es[0].read_loss(1), rel=1e-6)
+    for _ in range(2):
+        for s in range(8):
+            es[0].step(*(_dev(x) for x in batches[s]), loss_slot=0)
+        es[1].steps(eu, ep, en, 0, 8, B, loss_slot=0)
+    assert es[1].read_loss(0) == pytest.approx(es[0].read_loss(0), rel=1e-6)
     Qa, Qb = es[0].params(), es[1].params()
     for k in Qa:
-        # same arithmetic up to the summation order of the projection; Adam turns a gradient that
-        # sits at rounding noise into an O(lr) move, so a handful of elements may differ more
         dlt = np.abs(Qb[k] - Qa[k]) / np.abs(Qa[k]).max()
-        assert dlt.max() <= 5e-3 and (dlt > 2e-5).mean() <= 1e-3, (k, dlt.max(), (dlt > 2e-5).mean())
-
-
-@pytest.mark.parametrize("K,d,D,B", [(64, 20, 2048, 1000), (32, 20, 256, 513), (16, 40, 512, 300)])
-def test_two_half_pipelined_schedule_matches_oracle(K, d, D, B):
-    """fvx_bpr_step's large-batch schedule (two half-batches on two streams)
-    forced at a small batch: losses and parameters against the fp64 oracle, and against the
-    single-stream timed entry point on a twin engine (same kernels, plain slot layout)."""
-    from fvx import _lib
-    lib = _lib.load()
-    old = lib.fvx_debug_set_pipe_min_batch(64)
-    try:
-        U, I, steps, lr, reg = 700, 900, 12, 0.001, 1e-3
-        P, F, rng = _random_problem(U, I, K, d, D, seed=K + d + 1)
-        es = []
-        for _ in range(2):
-            e = _engine(U, I, K, d=d, D=D, lr=lr, reg=reg, max_batch=B, use_tensor_cores=True)
-            e.set_features(F, keep_fp32=False)
-            e.load_params(P)
-            es.append(e)
-        batches = _user_contiguous_batches(rng, U, I, B, steps)
-        P32, P64, l32, l64 = _oracle_pair(P, F, batches, reg, lr)
-        for s, b in enumerate(batches):
-            db = [_dev(x) for x in b]
-            es[0].step(*db, loss_slot=0)
-            es[1].step_timed(*db, loss_slot=0)
-            la, lb = es[0].read_loss(0), es[1].read_loss(0)
-            assert la == pytest.approx(l64[s], rel=REL), s
-            assert la == pytest.approx(lb, rel=2e-6), s
-        Qa, Qb = es[0].params(), es[1].params()
-        Pp = _perturbed_oracle(P, F, batches, reg, lr)
-        for k in P64:
-            ref = P64[k]
-            dlt = np.abs(Qa[k].reshape(ref.shape) - ref) / np.abs(ref).max()
-            assert dlt.max() <= max(REL, 3 * rel_err(P32[k], ref), rel_err(Pp[k], ref)), (k, dlt.max())
-            d2 = np.abs(Qa[k] - Qb[k]) / np.abs(Qb[k]).max()
-            assert d2.max() <= 5e-3 and (d2 > 2e-5).mean() <= 1e-3, (k, d2.max())
-    finally:
-        lib.fvx_debug_set_pipe_min_batch(old)
+        assert dlt.max() <= 5e-3 and (dlt > 2e-5).mean() <= 1e-3, (k, dlt.max())
 
 
 @pytest.mark.parametrize("mode", ["deferred", "dense"])
