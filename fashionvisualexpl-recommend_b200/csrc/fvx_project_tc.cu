@@ -1,5 +1,6 @@
 // The VBPR visual projection and its gradient on the 5th-generation tensor cores
-// (tcgen05 + TMEM), fed by TMA row gathers (cp.async.bulk.tensor ... tile::gather4).
+// (tcgen05 + TMEM).  The gathered F rows arrive by 16-byte cp.async (TMA tile::gather4 saturates at 1.67 TB/s,
+// profiles/r2_gather_bw.txt); the small operands (E_ext^T, W) by TMA tiles.
 //
 //   forward : TH[r,:]  = F[rows[r],:] * E_ext          (VBPR.py:83-84: matmul(feature_i, E / Bp))
 //   backward: gE_ext   = sum_r F[rows[r],:]^T * W[r,:]  (tape.gradient w.r.t. E, Bp; VBPR.py:141)
@@ -209,9 +210,16 @@ k_proj_fwd_tc(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant_
       }
     }
   } else if (warp == 4) {
-    // ===== UMMA issuer =====
-    if (lane == 0) {
+    // ===== UMMA issuer: the whole warp walks the loop, one elected lane issues =====
+    // (issued from an `if (lane == 0)` region a UMMA costs the lone thread ~150-190 cycles - descriptors
+    // rebuilt per instruction plus the compiler's ELECT / BRA.U.ANY emulation loop around it - and the eight
+    // N = 64 UMMAs of a 64-feature chunk then take as long as the chunk's 32 KB take to arrive from HBM; see
+    // fvx_eval_tc.cu and scripts/ubench/umma_chain.cu.  Convergent code, descriptor low words advanced by adds.)
+    {
       const uint32_t idesc = umma_idesc_bf16(PT_BM, (int)NW, 0, 0);
+      const uint64_t dsc0 = umma_smem_desc(0, 16, 1024, TC_SWZ_128B);
+      const uint32_t dlo = (uint32_t)dsc0, dhi = (uint32_t)(dsc0 >> 32);
+      const uint32_t s0 = tc_smem_u32(smem) >> 4, st16 = stage_bytes >> 4, a16 = a_bytes >> 4, b16 = b_bytes >> 4;
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       FwdWork work = work0;
       int tile, cb, ce, slot;
@@ -224,22 +232,19 @@ k_proj_fwd_tc(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant_
           mbar_wait(&full_b[stage], phase);
           fence_proxy_async_smem();           // cp.async (generic proxy) writes -> UMMA (async proxy) reads
           tc_fence_after();
-          const uint32_t a_hi = tc_smem_u32(smem + (size_t)stage * stage_bytes);
-          const uint32_t a_lo = a_hi + a_bytes, b_hi = a_lo + a_bytes, b_lo = b_hi + b_bytes;
+          const uint32_t a_hi = dlo + s0 + stage * st16;
+          const uint32_t a_lo = a_hi + a16, b_hi = a_lo + a16, b_lo = b_hi + b16;
           // pass-major, K-step-minor: consecutive UMMAs target different accumulators
           if (P.cat) {
             // the hi and lo tiles of E_ext^T are adjacent in shared memory: one descriptor of 2*NP rows
-            // reads both, so A_hi and A_lo are fetched once each (the smem operand fetch, not the
-            // tensor pipe, paces these N = 32 products)
+            // reads both, so A_hi and A_lo are fetched once each
 #pragma unroll
             for (int pass = 0; pass < 2; ++pass) {
 #pragma unroll
               for (int k = 0; k < PT_KC / 16; ++k) {
                 const uint32_t d = d0 + (uint32_t)(k % P.nacc) * NW;
-                const uint64_t da = umma_smem_desc((pass == 1 ? a_lo : a_hi) + k * 32, 16, 1024, TC_SWZ_128B);
-                const uint64_t db = umma_smem_desc(b_hi + k * 32, 16, 1024, TC_SWZ_128B);
                 const bool first = c == 0 && pass == 0 && k < P.nacc;
-                umma_f16(d, da, db, idesc, first ? 0u : 1u);
+                umma_f16_lohi_elect(d, (pass == 1 ? a_lo : a_hi) + 2u * k, dhi, b_hi + 2u * k, dhi, idesc, first ? 0u : 1u);
               }
             }
           } else {
@@ -248,17 +253,16 @@ k_proj_fwd_tc(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant_
 #pragma unroll
               for (int k = 0; k < PT_KC / 16; ++k) {
                 const uint32_t d = d0 + (uint32_t)(k % P.nacc) * P.NP;
-                const uint64_t da = umma_smem_desc((pass == 1 ? a_lo : a_hi) + k * 32, 16, 1024, TC_SWZ_128B);
-                const uint64_t db = umma_smem_desc((pass == 2 ? b_lo : b_hi) + k * 32, 16, 1024, TC_SWZ_128B);
                 const bool first = c == 0 && pass == 0 && k < P.nacc;
-                umma_f16(d, da, db, idesc, first ? 0u : 1u);
+                umma_f16_lohi_elect(d, (pass == 1 ? a_lo : a_hi) + 2u * k, dhi, (pass == 2 ? b_lo : b_hi) + 2u * k, dhi,
+                                    idesc, first ? 0u : 1u);
               }
             }
           }
-          umma_commit(&empty_b[stage]);
+          umma_commit_elect(&empty_b[stage]);
           if (++stage == (uint32_t)P.stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&t_full[acc]);
+        umma_commit_elect(&t_full[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -437,48 +441,51 @@ k_grad_E_tc(const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ 
     }
   } else if (warp == 4) {
     // ===== UMMA issuer: D[mb][128 features x NP] += F^T[128 x 16 rows] * W[16 rows x NP] =====
-    if (lane == 0) {
+    // (the whole warp walks the loop, one elected lane issues; descriptor low words advanced by adds - see the
+    // forward kernel)
+    {
       const uint32_t idesc = umma_idesc_bf16(128, (int)NW, 1, 1);
       const uint32_t w_sbo = 8u * wrow_bytes;
+      const uint64_t da0 = umma_smem_desc(0, chunk_bytes, 1024, TC_SWZ_128B);
+      const uint64_t dw0 = umma_smem_desc(0, watom_bytes, w_sbo, P.cat ? TC_SWZ_128B : P.w_sw);
+      const uint32_t alo0 = (uint32_t)da0, ahi = (uint32_t)(da0 >> 32), wlo0 = (uint32_t)dw0, whi = (uint32_t)(dw0 >> 32);
+      const uint32_t s0 = tc_smem_u32(smem) >> 4, st16 = stage_bytes >> 4, a16 = a_bytes >> 4, w16 = w_bytes >> 4;
+      const uint32_t mb16 = (2u * chunk_bytes) >> 4, k16a = (16u * 128u) >> 4, k16w = (16u * wrow_bytes) >> 4;
       uint32_t stage = 0, phase = 0;
       for (int t = 0; t < n_tiles; ++t) {
         mbar_wait(&full_b[stage], phase);
         fence_proxy_async_smem();
         tc_fence_after();
-        const uint32_t a_hi = tc_smem_u32(smem + (size_t)stage * stage_bytes);
-        const uint32_t a_lo = a_hi + a_bytes, w_hi = a_lo + a_bytes, w_lo = w_hi + w_bytes;
+        const uint32_t a_hi = s0 + stage * st16;
+        const uint32_t a_lo = a_hi + a16, w_hi = a_lo + a16, w_lo = w_hi + w16;
         // (K step, pass)-major, M-block-minor: consecutive UMMAs target different accumulators
         if (P.cat) {
 #pragma unroll
           for (int k = 0; k < GE_RT / 16; ++k) {
 #pragma unroll
             for (int pass = 0; pass < 2; ++pass) {
-              const uint64_t dw = umma_smem_desc(w_hi + k * 16 * wrow_bytes, watom_bytes, w_sbo, TC_SWZ_128B);
-              for (int mb = 0; mb < nmb; ++mb) {
-                const uint32_t aoff = (uint32_t)(2 * mb) * chunk_bytes + k * 16 * 128;
-                const uint64_t da = umma_smem_desc((pass == 1 ? a_lo : a_hi) + aoff, chunk_bytes, 1024, TC_SWZ_128B);
-                umma_f16(tmem_base + mb * NW, da, dw, idesc, (t | k | pass) ? 1u : 0u);
-              }
+              const uint32_t dw = wlo0 + w_hi + k * k16w;
+              uint32_t da = alo0 + (pass == 1 ? a_lo : a_hi) + k * k16a;
+              for (int mb = 0; mb < nmb; ++mb, da += mb16)
+                umma_f16_lohi_elect(tmem_base + mb * NW, da, ahi, dw, whi, idesc, (t | k | pass) ? 1u : 0u);
             }
           }
-        } else
+        } else {
 #pragma unroll
-        for (int k = 0; k < GE_RT / 16; ++k) {
+          for (int k = 0; k < GE_RT / 16; ++k) {
 #pragma unroll
-          for (int pass = 0; pass < 3; ++pass) {
-            const uint64_t dw = umma_smem_desc((pass == 2 ? w_lo : w_hi) + k * 16 * wrow_bytes, watom_bytes, w_sbo,
-                                               P.w_sw);
-            for (int mb = 0; mb < nmb; ++mb) {
-              const uint32_t aoff = (uint32_t)(2 * mb) * chunk_bytes + k * 16 * 128;
-              const uint64_t da = umma_smem_desc((pass == 1 ? a_lo : a_hi) + aoff, chunk_bytes, 1024, TC_SWZ_128B);
-              umma_f16(tmem_base + mb * P.NP, da, dw, idesc, (t | k | pass) ? 1u : 0u);
+            for (int pass = 0; pass < 3; ++pass) {
+              const uint32_t dw = wlo0 + (pass == 2 ? w_lo : w_hi) + k * k16w;
+              uint32_t da = alo0 + (pass == 1 ? a_lo : a_hi) + k * k16a;
+              for (int mb = 0; mb < nmb; ++mb, da += mb16)
+                umma_f16_lohi_elect(tmem_base + mb * P.NP, da, ahi, dw, whi, idesc, (t | k | pass) ? 1u : 0u);
             }
           }
         }
-        umma_commit(&empty_b[stage]);
+        umma_commit_elect(&empty_b[stage]);
         if (++stage == (uint32_t)P.stages) { stage = 0; phase ^= 1; }
       }
-      umma_commit(t_full);
+      umma_commit_elect(t_full);
     }
   } else {
     // ===== epilogue: the CTA's partial of gE_ext =====
