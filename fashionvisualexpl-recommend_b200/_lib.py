@@ -34,7 +34,16 @@ class FvxModel(C.Structure):
                 ("F_pl", _p), ("ET_hi", _p), ("ET_lo", _p), ("W_hi", _p), ("W_lo", _p),
                 ("step", _p), ("loss", _p), ("loss_slots", C.c_int32), ("_pad1", C.c_int32), ("TH", _p),
                 ("th_cap", C.c_int64), ("W", _p), ("rows", _p), ("sync", _p), ("cmap", _p), ("max_batch", C.c_int32),
-                ("use_tensor_cores", C.c_int32), ("upos", _p), ("W_sum", _p), ("uslot", _p), ("batch_stage", _p)]
+                ("use_tensor_cores", C.c_int32), ("upos", _p), ("W_sum", _p), ("uslot", _p), ("user_lo", C.c_int32),
+                ("user_cnt", C.c_int32), ("batch_stage", _p)]
+
+
+class FvxShardWs(C.Structure):
+    _fields_ = [("S", _p), ("run_id", _p), ("run_scratch", _p), ("WU", _p), ("RU", _p), ("dE", _p), ("loss_part", _p),
+                ("max_runs", C.c_int32), ("_pad", C.c_int32)]
+
+
+COMM_ID_BYTES = 256
 
 
 class FvxEvalWs(C.Structure):
@@ -60,11 +69,12 @@ PROTOTYPES = {
     "fvx_bpr_steps": (C.c_int, [_MP, _p, _p, _p, _i64, _i32, _i32, _i32, _p]),
     "fvx_bpr_step_timed": (C.c_int, [_MP, _p, _p, _p, _i32, _i32, C.POINTER(C.c_float), _p]),
     "fvx_run_ids": (C.c_int, [_p, _i64, _p, _p, _p]),
-    "fvx_bpr_step_sharded_a": (C.c_int, [_MP, _p, _p, _p, _i32, _p, _p]),
-    "fvx_bpr_step_sharded_b": (C.c_int, [_MP, _p, _i32, _p, _p, _p, _i64, _p, _i32, _p]),
-    "fvx_bpr_step_sharded_b1": (C.c_int, [_MP, _p, _i32, _p, _p, _p, _i64, _i32, _p]),
-    "fvx_bpr_step_sharded_b2": (C.c_int, [_MP, _i32, _p, _p]),
-    "fvx_bpr_step_sharded_c": (C.c_int, [_MP, _p, _i32, _p, _p, _i64, _p, _i32, _p]),
+    "fvx_bpr_step_sharded": (C.c_int, [_MP, C.POINTER(FvxShardWs), _p, _p, _p, _p, _i32, _i32, _p]),
+    "fvx_bpr_step_sharded_phase": (C.c_int, [_MP, C.POINTER(FvxShardWs), _p, _p, _p, _i32, _i32, _i32, _p]),
+    "fvx_comm_unique_id": (C.c_int, [_p]),
+    "fvx_comm_create": (C.c_int, [_p, _i32, _i32, C.POINTER(_p)]),
+    "fvx_comm_destroy": (C.c_int, [_p]),
+    "fvx_comm_all_reduce_f32": (C.c_int, [_p, _p, _i64, _p]),
     "fvx_adam_flush": (C.c_int, [_MP, _p]),
     "fvx_project": (C.c_int, [_MP, _p, _p]),
     "fvx_predict_all": (C.c_int, [_MP, _p, _i32, _i32, _p, _p]),

@@ -1,0 +1,119 @@
+// Communicators of the sharded step (include/fvx.h: FvxComm): two NCCL communicators over the same ranks,
+// one used on the caller's stream and one on a side stream.  NCCL is resolved at run time with dlopen /
+// dlsym - the copy the process already holds (torch's bundled libnccl.so.2) if there is one, else the system
+// library - so libfvx.so has no link-time dependency on it and a single-GPU user never loads it.
+#include <dlfcn.h>
+#include <nccl.h>      // types and enums only (compile time); every call goes through the table below
+#include <string.h>
+
+#include "fvx_common.cuh"
+#include "fvx_comm.cuh"
+
+struct NcclApi {
+  void* handle;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*);
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
+  ncclResult_t (*CommDestroy)(ncclComm_t);
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+  ncclResult_t (*GroupStart)();
+  ncclResult_t (*GroupEnd)();
+  const char* (*GetErrorString)(ncclResult_t);
+};
+static NcclApi g_nccl;
+
+static int nccl_load() {
+  if (g_nccl.handle) return 0;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);        // already in the process (torch)?
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) FVX_FAIL(-5, "fvx_comm: cannot load libnccl.so.2: %s", dlerror());
+#define FVX_SYM(field, name)                                                       \
+  *reinterpret_cast<void**>(&g_nccl.field) = dlsym(h, name);                       \
+  if (!g_nccl.field) FVX_FAIL(-5, "fvx_comm: libnccl has no symbol %s", name);
+  FVX_SYM(GetUniqueId, "ncclGetUniqueId")
+  FVX_SYM(CommInitRank, "ncclCommInitRank")
+  FVX_SYM(CommDestroy, "ncclCommDestroy")
+  FVX_SYM(AllReduce, "ncclAllReduce")
+  FVX_SYM(GroupStart, "ncclGroupStart")
+  FVX_SYM(GroupEnd, "ncclGroupEnd")
+  FVX_SYM(GetErrorString, "ncclGetErrorString")
+#undef FVX_SYM
+  g_nccl.handle = h;
+  return 0;
+}
+
+#define FVX_NCCL(call, what)                                                                  \
+  do {                                                                                        \
+    ncclResult_t r__ = (call);                                                                \
+    if (r__ != ncclSuccess) FVX_FAIL(-5, "%s: NCCL error: %s", (what), g_nccl.GetErrorString(r__)); \
+  } while (0)
+
+int fvx_comm_allreduce(FvxComm* c, int which, float* buf, size_t n, cudaStream_t st) {
+  if (n == 0) return 0;
+  FVX_NCCL(g_nccl.AllReduce(buf, buf, n, ncclFloat, ncclSum, reinterpret_cast<ncclComm_t>(c->nccl[which]), st),
+           "all-reduce");
+  return 0;
+}
+
+extern "C" {
+
+int fvx_comm_unique_id(uint8_t* id_host) {
+  FVX_CHECK_ARG(id_host != nullptr, "fvx_comm_unique_id: null buffer");
+  if (int rc = nccl_load()) return rc;
+  static_assert(2 * sizeof(ncclUniqueId) <= FVX_COMM_ID_BYTES, "id buffer too small");
+  memset(id_host, 0, FVX_COMM_ID_BYTES);
+  for (int i = 0; i < 2; ++i) {
+    ncclUniqueId id;
+    FVX_NCCL(g_nccl.GetUniqueId(&id), "fvx_comm_unique_id");
+    memcpy(id_host + i * sizeof(ncclUniqueId), &id, sizeof(id));
+  }
+  return 0;
+}
+
+int fvx_comm_create(const uint8_t* id_host, int32_t rank, int32_t world, FvxComm** out) {
+  FVX_CHECK_ARG(id_host && out && world >= 1 && rank >= 0 && rank < world, "fvx_comm_create: bad arguments");
+  if (int rc = nccl_load()) return rc;
+  FvxComm* c = new FvxComm();
+  memset(c, 0, sizeof(*c));
+  c->rank = rank;
+  c->world = world;
+  for (int i = 0; i < 2; ++i) {
+    ncclUniqueId id;
+    memcpy(&id, id_host + i * sizeof(ncclUniqueId), sizeof(id));
+    ncclComm_t comm = nullptr;
+    ncclResult_t r = g_nccl.CommInitRank(&comm, world, id, rank);
+    if (r != ncclSuccess) {
+      fvx_set_error("fvx_comm_create: ncclCommInitRank failed: %s", g_nccl.GetErrorString(r));
+      delete c;
+      return -5;
+    }
+    c->nccl[i] = comm;
+  }
+  bool ok = cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) == cudaSuccess;
+  for (int i = 0; i < FVX_COMM_EVENTS && ok; ++i) ok = cudaEventCreateWithFlags(&c->ev[i], cudaEventDisableTiming) == cudaSuccess;
+  if (!ok) {
+    fvx_set_error("fvx_comm_create: cannot create the side stream / events: %s", cudaGetErrorString(cudaGetLastError()));
+    delete c;
+    return -3;
+  }
+  *out = c;
+  return 0;
+}
+
+int fvx_comm_destroy(FvxComm* c) {
+  if (!c) return 0;
+  for (int i = 0; i < 2; ++i)
+    if (c->nccl[i]) g_nccl.CommDestroy(reinterpret_cast<ncclComm_t>(c->nccl[i]));
+  if (c->side) cudaStreamDestroy(c->side);
+  for (int i = 0; i < FVX_COMM_EVENTS; ++i)
+    if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  delete c;
+  return 0;
+}
+
+int fvx_comm_all_reduce_f32(FvxComm* c, float* buf, int64_t n, fvx_stream_t stream) {
+  FVX_CHECK_ARG(c && buf && n >= 0, "fvx_comm_all_reduce_f32: bad arguments");
+  return fvx_comm_allreduce(c, 0, buf, (size_t)n, fvx_cu(stream));
+}
+
+}  // extern "C"

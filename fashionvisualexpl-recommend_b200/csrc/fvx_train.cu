@@ -248,7 +248,8 @@ k_prep(FvxModel M, const int32_t* __restrict__ user, const int32_t* __restrict__
         M.rows[B + b] = lj;
       }
     }
-    uint32_t wu = claim_rows(M.users, u, live && ustart && u >= 0 && u < M.num_users, t, lane);
+    // only the OWNER of a user claims and catches up the user's row (one rank: every user is owned)
+    uint32_t wu = claim_rows(M.users, u, live && ustart && u >= M.user_lo && u < M.user_lo + M.user_cnt, t, lane);
     uint32_t wi = claim_rows(M.items, li_, li_ >= 0, t, lane);
     uint32_t wj = claim_rows(M.items, lj, lj >= 0, t, lane);
     if (deferred) {
@@ -286,11 +287,11 @@ k_prep(FvxModel M, const int32_t* __restrict__ user, const int32_t* __restrict__
 }
 
 // every row -> step (*step)  (fvx_adam_flush)
-__global__ void k_catchup_all(FvxTable T, const int64_t* __restrict__ step, float lr) {
+__global__ void k_catchup_all(FvxTable T, const int64_t* __restrict__ step, float lr, long long r0, long long r1) {
   const int32_t target = (int32_t)(*step);
   const int lane = threadIdx.x & 31;
   const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
-  for (long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < T.rows; r += warps)
+  for (long long r = r0 + (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5); r < r1; r += warps)
     replay_row(T, (int32_t)r, target, lr, lane, 32);
 }
 
@@ -713,6 +714,7 @@ struct UpdParams {
   int finalize;         // the last block advances the step counter and resets the lists
   int32_t* sync;        // [1] blocks-done counter (zero between launches)
   const float* gE_src;  // partial gradients of E_ext (model->gE_part, or an all-reduced [D, de] buffer)
+  const float* loss_pair;   // sharded step: {hi, lo, overflow flag} - the all-reduced loss shares of the ranks
 };
 
 __device__ __forceinline__ void adam4(float4& w, float4& m, float4& v, const float4 g, float a) {
@@ -804,6 +806,11 @@ k_update(FvxModel M, UpdParams U) {
     }
     sq = fvx_warp_sum(sq);
     if ((threadIdx.x & 31) == 0 && sq != 0.0f && U.loss_slot >= 0) atomicAdd(M.loss + U.loss_slot, (double)(reg * sq));
+    if (U.loss_pair && b == U.nb_u + U.nb_i && threadIdx.x == 0 && U.loss_slot >= 0) {
+      // a batch with more runs than the exchange buffers hold poisons the loss: nothing fails silently
+      const double l = U.loss_pair[2] != 0.0f ? (double)__int_as_float(0x7fc00000) : (double)U.loss_pair[0] + (double)U.loss_pair[1];
+      atomicAdd(M.loss + U.loss_slot, l);
+    }
   }
   // last block: the step is complete
   if (!U.finalize) return;
@@ -829,6 +836,8 @@ static int check_model(const FvxModel* m, const char* who) {
                 FVX_ABI_VERSION);
   FVX_CHECK_ARG(m->num_users > 0 && m->num_items > 0 && m->item_cnt > 0 && m->K > 0, "%s: bad geometry", who);
   FVX_CHECK_ARG(m->item_lo >= 0 && m->item_lo + m->item_cnt <= m->num_items, "%s: bad item shard", who);
+  FVX_CHECK_ARG(m->user_lo >= 0 && m->user_cnt >= 0 && m->user_lo + m->user_cnt <= m->num_users && m->users.rows >= m->num_users,
+                "%s: bad user block [%d, +%d) of %d", who, m->user_lo, m->user_cnt, m->num_users);
   FVX_CHECK_ARG(m->users.stride % 4 == 0 && m->users.stride >= m->K + m->d, "%s: bad user stride", who);
   FVX_CHECK_ARG(m->items.stride % 4 == 0 && m->items.stride >= m->K + 1, "%s: bad item stride", who);
   FVX_CHECK_ARG(m->users.w && m->items.w && m->step, "%s: null table pointer", who);
@@ -924,7 +933,7 @@ int fvx_launch_prep(const FvxModel* m, const int32_t* user, const int32_t* pos, 
 }
 
 int fvx_launch_update(const FvxModel* m, int B, int parts, int gnp, const float* gE_src, int loss_slot,
-                      cudaStream_t st, int what) {
+                      cudaStream_t st, int what, const float* loss_pair) {
   UpdParams U;
   U.dense = m->adam_mode == FVX_ADAM_DENSE;
   if (U.dense) {
@@ -940,7 +949,8 @@ int fvx_launch_update(const FvxModel* m, int B, int parts, int gnp, const float*
   if (what == FVX_UPD_TABLES) U.nb_e = 0;
   if (what == FVX_UPD_E) { U.nb_u = 0; U.nb_i = 0; if (U.nb_e == 0) U.nb_e = 1; }
   U.finalize = what != FVX_UPD_TABLES;
-  U.parts = parts; U.gnp = gnp; U.loss_slot = loss_slot; U.sync = m->sync; U.gE_src = gE_src;
+  U.parts = parts; U.gnp = gnp; U.loss_slot = loss_slot; U.sync = m->sync; U.gE_src = gE_src; U.loss_pair = loss_pair;
+  if (loss_pair && U.nb_e == 0) U.nb_e = 1;
   k_update<<<U.nb_u + U.nb_i + U.nb_e, 256, 0, st>>>(*m, U);
   FVX_CHECK_LAUNCH("k_update");
   return 0;
@@ -1340,8 +1350,9 @@ int fvx_adam_flush(const FvxModel* model, fvx_stream_t stream) {
   const FvxModel& M = *model;
   if (M.adam_mode != FVX_ADAM_DEFERRED) return 0;
   cudaStream_t st = fvx_cu(stream);
-  k_catchup_all<<<warp_grid(M.users.rows), 256, 0, st>>>(M.users, M.step, M.lr);
-  k_catchup_all<<<warp_grid(M.items.rows), 256, 0, st>>>(M.items, M.step, M.lr);
+  // users: the rows this rank owns (every row on one GPU); items: the owned shard
+  k_catchup_all<<<warp_grid(M.user_cnt), 256, 0, st>>>(M.users, M.step, M.lr, M.user_lo, (long long)M.user_lo + M.user_cnt);
+  k_catchup_all<<<warp_grid(M.items.rows), 256, 0, st>>>(M.items, M.step, M.lr, 0, M.items.rows);
   FVX_CHECK_LAUNCH("k_catchup_all");
   return 0;
 }

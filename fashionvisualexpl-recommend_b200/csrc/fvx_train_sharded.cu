@@ -1,28 +1,31 @@
-// The BPR optimiser step with the item catalog row-sharded over R ranks (one process per GPU).
+// The BPR optimiser step with the model sharded over R ranks (one process per GPU): include/fvx.h,
+// "the same step with the model sharded over R ranks".
 //
-// x_uij = s_ui - s_uj is linear in the item-side quantities, s_ui = Bi[i] + <Gu[u],Gi[i]> +
-// <Tu[u], F[i]E> + F[i]Bp (BPRMF.py:74, VBPR.py:82-84), so each rank scores the (triple, side)
-// slots whose item it owns and one small all-reduce assembles every x.  Every rank sees the same
-// batch; user tables and E are replicated, Gi / Bi / F and their Adam state live on the owner.
+// x_uij = s_ui - s_uj is linear in the item-side quantities, s_ui = Bi[i] + <Gu[u],Gi[i]> + <Tu[u], F[i]E> +
+// F[i]Bp (BPRMF.py:74, VBPR.py:82-84), so each rank scores the (triple, side) slots whose item it owns and one
+// small all-reduce assembles every x.  Items (Gi / Bi / F + Adam state) live on their owner; a USER's Adam state
+// lives on the owner of the user, who brings the row up to date when a batch touches it and publishes it to the
+// other ranks for that step (WU, indexed by run of equal users); E is replicated.
 //
-//   phase A (fvx_bpr_step_sharded_a)  prep (touched rows, catch-up, E planes) -> projection of the
-//                                     owned slots -> partial scores S[2B] (0 for foreign slots)
-//        -- host: all-reduce(S) --
-//   phase B (fvx_bpr_step_sharded_b)  x, loss and gradient coefficients from S; gradients of the
-//                                     owned item rows; this rank's share of the user-row gradients
-//                                     into the packed run buffer RU; W of the owned slots; grad_E
-//                                     of the owned slots reduced to dE[D, de]
-//        -- host: all-reduce(RU), all-reduce(dE) --
-//   phase C (fvx_bpr_step_sharded_c)  RU rows -> user gradient accumulators; Adam on users (every
-//                                     rank, identical), owned items, E (identical)
+//   piece 1  run ids; slot rows + claims of the owned item rows (unique-row step), E planes         [main]
+//   piece 2  claims + catch-up of the OWNED users of the batch, catch-up of the listed item rows;   [side]
+//            fresh rows of the owned users -> WU                      -- all-reduce(WU) [side] --
+//   piece 3  compact list of the owned slots; projection of the distinct owned rows                 [main]
+//   piece 4  partial scores of the owned slots (user rows from WU) -> S   -- all-reduce(S) --       [main]
+//   piece 5  gradients of the owned slots: item rows, user shares -> RU, coefficient sums -> planes [main]
+//                                                                     -- all-reduce(RU) [side] --
+//   piece 6  grad_E over the distinct owned rows -> dE (+ loss share) -- all-reduce(dE) --          [main]
+//   piece 7  RU rows of the OWNED users -> their gradient accumulators                              [side]
+//   piece 8  Adam on E (identical on every rank), loss, step += 1                                   [main]
 //
-// RU is indexed by RUN: the reference's sampler emits runs of one user (dataset.py:96-99), run_id[b]
+// RU / WU are indexed by RUN: the reference's sampler emits runs of one user (dataset.py:96-99), run_id[b]
 // = number of positions <= b where user[b] != user[b-1], minus one.  The layout depends only on the
-// batch, so it is the same on every rank and the all-reduce needs no index exchange.  Ownership of
+// batch, so it is the same on every rank and the all-reduces need no index exchange.  Ownership of
 // the per-triple terms that are not tied to an item (softplus loss, user-side L2): the rank that
 // owns the POSITIVE item.
 #include <cuda_bf16.h>
 
+#include "fvx_comm.cuh"
 #include "fvx_common.cuh"
 #include "fvx_kernels.cuh"
 
@@ -90,7 +93,8 @@ __device__ __forceinline__ float4 ss_theta4(const SsTheta& T, long long slot, in
 // uniq != 0 (unique-row step): theta of a slot is row uslot[slot] of TH (one projection per DISTINCT owned row)
 __global__ void __launch_bounds__(SS_WARPS * 32)
 k_partial_scores_v4(FvxModel M, const int32_t* __restrict__ user, int B, SsTheta T, float* __restrict__ S,
-                    const int32_t* __restrict__ count, int uniq) {
+                    const int32_t* __restrict__ count, int uniq, const float* __restrict__ WU,
+                    const int32_t* __restrict__ run_id, long long ru_rows) {
   const int Su = M.users.stride, Si = M.items.stride, K = M.K, d = M.d;
   if (uniq) {
     int nv = *M.items.count, sk;
@@ -112,8 +116,13 @@ k_partial_scores_v4(FvxModel M, const int32_t* __restrict__ user, int B, SsTheta
       const int32_t li = crow[j];
       slot = cslot[j];
       const int b = slot < B ? slot : slot - B;
-      const int32_t u = user[b];
-      const float4* ur = reinterpret_cast<const float4*>(M.users.w + (size_t)u * Su);
+      // the user's row: published by its owner for this step (WU, by run), or the local table (one rank)
+      const float* urow = M.users.w + (size_t)user[b] * Su;
+      if (WU) {
+        const int32_t run = run_id[b];
+        urow = WU + (size_t)(run < ru_rows ? run : 0) * Su;       // (a run past the buffer: the step is poisoned anyway)
+      }
+      const float4* ur = reinterpret_cast<const float4*>(urow);
       const float4* gi = reinterpret_cast<const float4*>(M.items.w + (size_t)li * Si);
       for (int c = sub; c < K4; c += 16) {
         const float4 a = ur[c], x = gi[c];
@@ -135,119 +144,6 @@ k_partial_scores_v4(FvxModel M, const int32_t* __restrict__ user, int B, SsTheta
     if (live && sub == 0) S[slot] = s + tail;
   }
 }
-
-// phase A: one warp per owned slot
-__global__ void __launch_bounds__(SS_WARPS * 32)
-k_partial_scores(FvxModel M, const int32_t* __restrict__ user, int B, SsTheta T, float* __restrict__ S,
-                 const int32_t* __restrict__ count) {
-  const int Su = M.users.stride, Si = M.items.stride, K = M.K, d = M.d;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool vis = M.D > 0;
-  const int32_t* crow = M.cmap;
-  const int32_t* cslot = M.cmap + 2 * (size_t)M.max_batch;
-  const long long nw = (long long)gridDim.x * SS_WARPS;
-  const long long n_owned = *count;
-  for (long long j = (long long)blockIdx.x * SS_WARPS + warp; j < n_owned; j += nw) {
-    const int32_t li = crow[j], slot = cslot[j];
-    const int b = slot < B ? slot : slot - B;
-    const int32_t u = user[b];
-    const float* ur = M.users.w + (size_t)u * Su;
-    const float* gi = M.items.w + (size_t)li * Si;
-    float part = 0.0f;
-    for (int c = lane; c < K; c += 32) part = fmaf(ur[c], gi[c], part);
-    if (vis)
-      for (int n = lane; n < d; n += 32) part = fmaf(ur[K + n], T.at(j, n), part);
-    const float s = fvx_warp_sum(part) + gi[K] + (vis ? T.at(j, d) : 0.0f);
-    if (lane == 0) S[slot] = s;
-  }
-}
-
-// phase B: one warp per triple; each side only if its item is owned
-__global__ void __launch_bounds__(SS_WARPS * 32)
-k_grads_sharded(FvxModel M, const int32_t* __restrict__ user, int B, int loss_slot, SsTheta T, int wnp, int wpitch,
-                const float* __restrict__ S, const int32_t* __restrict__ run_id, float* __restrict__ RU,
-                long long ru_rows) {
-  __shared__ double loss_sh[SS_WARPS];
-  const int Su = M.users.stride, Si = M.items.stride, K = M.K, d = M.d, de = M.de;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float reg = M.reg, reg2 = 2.0f * M.reg;
-  const bool vis = M.D > 0;
-  const long long nw = (long long)gridDim.x * SS_WARPS;
-  double loss_acc = 0.0;
-  __nv_bfloat16* wh = reinterpret_cast<__nv_bfloat16*>(M.W_hi);
-  __nv_bfloat16* wl = reinterpret_cast<__nv_bfloat16*>(M.W_lo);
-  const int32_t* crow = M.cmap;
-  const int32_t* cpos = M.cmap + 4 * (size_t)M.max_batch;
-  for (long long b = (long long)blockIdx.x * SS_WARPS + warp; b < B; b += nw) {
-    const int32_t u = user[b];
-    const float xs = S[b] - S[B + b];
-    const bool inside = (xs >= FVX_CLIP_LO) && (xs <= FVX_CLIP_HI);
-    const float coef = inside ? -1.0f / (1.0f + expf(xs)) : 0.0f;
-    const float* ur = M.users.w + (size_t)u * Su;
-    if (run_id[b] >= ru_rows) {       // more runs than the caller sized RU for: reported through sync[2]
-      if (lane == 0) M.sync[2] = 1;
-      continue;
-    }
-    float* ru = RU + (size_t)run_id[b] * Su;
-#pragma unroll
-    for (int side = 0; side < 2; ++side) {
-      const long long slot = side ? B + b : b;
-      const long long j = cpos[slot];           // position in the compact list; < 0: foreign slot
-      if (j < 0) continue;
-      const int32_t li = crow[j];
-      const float cs = side ? -coef : coef;
-      const int nw_ = wnp > 0 ? wnp : de;
-      const float* gi = M.items.w + (size_t)li * Si;
-      float* gg = M.items.g + (size_t)li * Si;
-      float sq = 0.0f;
-      for (int c = lane; c < K; c += 32) {
-        const float a = ur[c], x = gi[c];
-        fvx_red_add(gg + c, cs * a + reg2 * x);
-        // the user row's data term from this side; its L2 term once per triple (positive side)
-        fvx_red_add(ru + c, cs * x + (side == 0 ? reg2 * a : 0.0f));
-        sq += x * x + (side == 0 ? a * a : 0.0f);
-      }
-      const float bi = gi[K];
-      if (lane == 0) fvx_red_add(gg + K, cs + (side == 0 ? reg2 : reg2 / 10.0f) * bi);
-      if (vis) {
-        for (int n = lane; n < nw_; n += 32) {
-          float wv = 0.0f;
-          if (n < d) {
-            const float tu = ur[K + n];
-            fvx_red_add(ru + K + n, cs * T.at(j, n) + (side == 0 ? reg2 * tu : 0.0f));
-            if (side == 0) sq += tu * tu;
-            wv = cs * tu;
-          } else if (n == d) {
-            wv = cs;
-          }
-          if (wnp > 0) {
-            const __nv_bfloat16 h = __float2bfloat16_rn(wv);
-            wh[j * wpitch + n] = h;
-            wl[j * wpitch + n] = __float2bfloat16_rn(wv - __bfloat162float(h));
-          } else {
-            M.W[j * de + n] = wv;
-          }
-        }
-      }
-      const float sqs = fvx_warp_sum(sq);
-      if (lane == 0) {
-        loss_acc += (double)(reg * sqs) + (double)(reg * bi * bi / (side == 0 ? 1.0f : 10.0f));
-        if (side == 0) {
-          const float z = -fminf(fmaxf(xs, FVX_CLIP_LO), FVX_CLIP_HI);
-          loss_acc += (double)(z > 13.942385f ? z : (z < -13.942385f ? expf(z) : log1pf(expf(z))));
-        }
-      }
-    }
-  }
-  if (lane == 0) loss_sh[warp] = loss_acc;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double s = 0.0;
-    for (int w = 0; w < SS_WARPS; ++w) s += loss_sh[w];
-    if (s != 0.0) atomicAdd(M.loss + loss_slot, s);
-  }
-}
-
 
 // phase B, scalable form: one warp per OWNED slot (the compact list of phase A), 16-byte loads and
 // reductions.  The work of a rank is 2B/R slots however many triples the global batch holds; the
@@ -280,7 +176,8 @@ __device__ __forceinline__ float4 ss_unpack_bf16x4(uint2 p) {
 __global__ void __launch_bounds__(SS_WARPS * 32)
 k_grads_owned(FvxModel M, const int32_t* __restrict__ user, int B, int loss_slot, SsTheta T, int wnp, int wpitch,
               const float* __restrict__ S, const int32_t* __restrict__ run_id, float* __restrict__ RU,
-              long long ru_rows, const int32_t* __restrict__ count, int uniq) {
+              long long ru_rows, const int32_t* __restrict__ count, int uniq, const float* __restrict__ WU,
+              double* __restrict__ loss_out) {
   __shared__ double loss_sh[SS_WARPS * 2];
   const int Su = M.users.stride, Si = M.items.stride, K = M.K, d = M.d, de = M.de;
   const int K4 = K >> 2, D4 = (d + 3) >> 2;
@@ -326,7 +223,7 @@ k_grads_owned(FvxModel M, const int32_t* __restrict__ user, int B, int loss_slot
       } else {
         const float cs = side ? -coef : coef;
         const float ul2 = side ? 0.0f : reg2;       // the user row's L2 term once per triple
-        const float4* ur = reinterpret_cast<const float4*>(M.users.w + (size_t)u * Su);
+        const float4* ur = reinterpret_cast<const float4*>(WU ? WU + (size_t)run * Su : M.users.w + (size_t)u * Su);
         const float4* gi = reinterpret_cast<const float4*>(M.items.w + (size_t)li * Si);
         float* gg = M.items.g + (size_t)li * Si;
         float* ru = RU + (size_t)run * Su;
@@ -393,11 +290,11 @@ k_grads_owned(FvxModel M, const int32_t* __restrict__ user, int B, int loss_slot
   if (threadIdx.x == 0) {
     double s = 0.0;
     for (int w = 0; w < SS_WARPS * 2; ++w) s += loss_sh[w];
-    if (s != 0.0) atomicAdd(M.loss + loss_slot, s);
+    if (s != 0.0) atomicAdd(loss_out, s);
   }
 }
 
-// phase C: one warp per run start adds the all-reduced run gradient into the user's accumulator
+// one warp per run start of an OWNED user adds the all-reduced run gradient into the user's accumulator
 __global__ void k_scatter_runs(FvxModel M, const int32_t* __restrict__ user, int B,
                                const int32_t* __restrict__ run_id, const float* __restrict__ RU, long long ru_rows) {
   // a warp looks at 32 triples at once, then adds the rows of the run starts among them (a global
@@ -413,7 +310,7 @@ __global__ void k_scatter_runs(FvxModel M, const int32_t* __restrict__ user, int
     if (b < B) {
       u = user[b];
       run = run_id[b];
-      start = (b == 0 || user[b - 1] != u) && run < ru_rows;
+      start = (b == 0 || user[b - 1] != u) && run < ru_rows && u >= M.user_lo && u < M.user_lo + M.user_cnt;
     }
     uint32_t msk = __ballot_sync(0xffffffffu, start);
     while (msk) {
@@ -425,6 +322,60 @@ __global__ void k_scatter_runs(FvxModel M, const int32_t* __restrict__ user, int
       float* g = M.users.g + (size_t)uu * Su;
       for (int c = lane; c < S4; c += 32) ss_red_add4(g + 4 * c, s4[c]);   // a user may own several runs
     }
+  }
+}
+
+// The owner of a user publishes the user's up-to-date row for this step: WU[run] = w[u] for the run starts of
+// OWNED users (k_prep has caught the row up); WU is zero elsewhere, so the sum over the ranks is the row.
+__global__ void k_pack_wu(FvxModel M, const int32_t* __restrict__ user, int B, const int32_t* __restrict__ run_id,
+                          float* __restrict__ WU, long long ru_rows) {
+  const int lane = threadIdx.x & 31;
+  const int Su = M.users.stride, S4 = Su >> 2;
+  const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long npass = ((long long)B + 31) >> 5;
+  for (long long p = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; p < npass; p += nw) {
+    const long long b = p * 32 + lane;
+    int32_t u = -1, run = 0;
+    bool start = false;
+    if (b < B) {
+      u = user[b];
+      run = run_id[b];
+      start = (b == 0 || user[b - 1] != u) && u >= M.user_lo && u < M.user_lo + M.user_cnt;
+      if (start && run >= ru_rows) { M.sync[2] = 1; start = false; }    // more runs than the buffers hold
+    }
+    uint32_t msk = __ballot_sync(0xffffffffu, start);
+    while (msk) {
+      const int src = __ffs(msk) - 1;
+      msk &= msk - 1;
+      const int32_t uu = __shfl_sync(0xffffffffu, u, src);
+      const int32_t rr = __shfl_sync(0xffffffffu, run, src);
+      const float4* s4 = reinterpret_cast<const float4*>(M.users.w + (size_t)uu * Su);
+      float4* d4 = reinterpret_cast<float4*>(WU + (size_t)rr * Su);
+      for (int c = lane; c < S4; c += 32) d4[c] = s4[c];
+    }
+  }
+}
+
+// dE[D, de] = sum of the row-group partials; behind it this rank's loss share as two floats (hi + lo) and the
+// run-overflow flag, so that one all-reduce carries all three
+__global__ void k_dE_pack(const float* __restrict__ part, int parts, int D, int gnp, int de, float* __restrict__ out,
+                          double* __restrict__ loss_part, int32_t* __restrict__ sync) {
+  const int n = D * de;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int f = i / de, c = i - f * de;
+    float g = 0.0f;
+    for (int p = 0; p < parts; ++p) g += part[((size_t)p * D + f) * gnp + c];
+    out[i] = g;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const double l = *loss_part;
+    const float hi = (float)l;
+    out[n] = hi;
+    out[n + 1] = (float)(l - (double)hi);
+    out[n + 2] = sync[2] ? 1.0f : 0.0f;
+    out[n + 3] = 0.0f;
+    sync[2] = 0;
+    *loss_part = 0.0;
   }
 }
 
@@ -501,11 +452,14 @@ extern "C" int fvx_run_ids(const int32_t* user, int64_t n, int32_t* run_id, int3
   return 0;
 }
 
-static int sharded_common(const FvxModel* m, const int32_t* user, int B, const char* who) {
+static int sharded_common(const FvxModel* m, const FvxShardWs* ws, const int32_t* user, int B, const char* who) {
   if (int rc = fvx_check_model(m, who)) return rc;
   FVX_CHECK_ARG(user != nullptr && B >= 1 && B <= m->max_batch, "%s: bad batch", who);
   FVX_CHECK_ARG(m->users.list_cap >= B && m->items.list_cap >= 2 * B, "%s: touched-row lists too small", who);
   FVX_CHECK_ARG(m->rows && m->loss && m->sync && m->cmap, "%s: null scratch (rows / loss / sync / cmap)", who);
+  FVX_CHECK_ARG(m->K % 4 == 0, "%s: the sharded step needs embed_k %% 4 == 0 (got %d)", who, m->K);
+  FVX_CHECK_ARG(ws && ws->S && ws->run_id && ws->run_scratch && ws->WU && ws->RU && ws->dE && ws->loss_part &&
+                ws->max_runs >= 1, "%s: incomplete FvxShardWs", who);
   if (m->D > 0) {
     FVX_CHECK_ARG(m->TH && m->gE_part && m->ge_parts > 0, "%s: VBPR scratch missing", who);
     if (m->use_tensor_cores) FVX_CHECK_ARG(m->F_pl && m->ET_hi && m->ET_lo && m->W_hi && m->W_lo, "%s: bf16 planes missing", who);
@@ -535,11 +489,10 @@ static SsTheta make_theta(const FvxModel* m, int B, int ks) {
 }
 
 // Unique-row step on a shard (see fvx_train.cu): with R ranks a rank owns I/R catalog rows but 2B_global/R
-// slots - at 8 ranks ~131 k slots over 12.5 k rows - so projecting each DISTINCT owned row once shrinks both
-// contractions by the duplication factor.  Needs the tensor-core path, K % 4 == 0 and the scratch
-// (upos, W_sum, uslot); FVX_STEP_DEDUP=0 turns it off.
+// slots, so projecting each DISTINCT owned row once shrinks both contractions by the duplication factor.
+// Needs the tensor-core path and the scratch (upos, W_sum, uslot); FVX_STEP_DEDUP=0 turns it off.
 static bool sharded_uniq(const FvxModel* m) {
-  return m->D > 0 && m->use_tensor_cores && m->upos && m->W_sum && m->uslot && m->K % 4 == 0 &&
+  return m->D > 0 && m->use_tensor_cores && m->upos && m->W_sum && m->uslot &&
          fvx_tc_np(m->de) <= 256 && fvx_dedup_enabled();
 }
 static int uniq_ks_cap(const FvxModel* m, int B) {
@@ -554,147 +507,186 @@ static inline int ss_grid(long long warps_needed) {
   if (g > cap) g = cap;
   return g < 1 ? 1 : (int)g;
 }
+static inline int scan_grid(int B) {
+  long long g = ((long long)B * 32 + 255) / 256 / 32 + 1;       // a warp looks at 32 triples per pass
+  if (g > (long long)fvx_num_sms() * 8) g = (long long)fvx_num_sms() * 8;
+  return (int)g;
+}
 
-extern "C" {
+// ---- the pieces of the step (file header) ---------------------------------------------------------------
+struct ShCtx {
+  const FvxModel* m;
+  const FvxShardWs* ws;
+  const int32_t *user, *pos, *neg;
+  int B, loss_slot;
+  bool uniq;
+  int ks;
+};
 
-int fvx_bpr_step_sharded_a(const FvxModel* model, const int32_t* user, const int32_t* pos, const int32_t* neg,
-                           int32_t B, float* S, fvx_stream_t stream) {
-  if (int rc = sharded_common(model, user, B, "fvx_bpr_step_sharded_a")) return rc;
-  FVX_CHECK_ARG(pos && neg && S, "fvx_bpr_step_sharded_a: null pointer");
-  const FvxModel& M = *model;
-  cudaStream_t st = fvx_cu(stream);
-  // The projection needs only the slot rows and the planes of E_ext^T: the claims and the
-  // deferred-Adam catch-up of the touched rows run beside it on the side stream (joined before the
-  // partial scores read the tables).
-  const bool uniq = sharded_uniq(&M);
-  cudaStream_t side = nullptr;
-  if (uniq) {
-    // slot rows + claims of the owned rows (list positions in upos) ahead of the projection; user claims,
-    // catch-up and the slots' list positions (uslot) beside it
-    if (int rc = fvx_launch_prep(&M, user, pos, neg, B, st, FVX_PREP_UNIQ)) return rc;
-    side = fvx_side_begin(st);
-    if (int rc = fvx_launch_prep(&M, user, pos, neg, B, side ? side : st, FVX_PREP_CLAIMS_LISTED)) return rc;
-  } else {
-    side = M.D > 0 ? fvx_side_begin(st) : nullptr;
-    if (side) {
-      if (int rc = fvx_launch_prep(&M, user, pos, neg, B, side, FVX_PREP_CLAIMS)) return rc;
-      if (int rc = fvx_launch_prep(&M, user, pos, neg, B, st, FVX_PREP_ROWS)) return rc;
-    } else {
-      if (int rc = fvx_launch_prep(&M, user, pos, neg, B, st)) return rc;
-    }
-  }
+static int sh_p1(const ShCtx& c, cudaStream_t st) {
+  const FvxModel& M = *c.m;
+  if (int rc = fvx_run_ids(c.user, c.B, c.ws->run_id, c.ws->run_scratch, st)) return rc;
+  if (cudaMemsetAsync(c.ws->WU, 0, sizeof(float) * (size_t)c.ws->max_runs * M.users.stride, st) != cudaSuccess)
+    FVX_FAIL(-3, "fvx_bpr_step_sharded: memset failed");
+  return fvx_launch_prep(&M, c.user, c.pos, c.neg, c.B, st, c.uniq ? FVX_PREP_UNIQ : FVX_PREP_ROWS);
+}
+static int sh_p2(const ShCtx& c, cudaStream_t st) {
+  const FvxModel& M = *c.m;
+  if (int rc = fvx_launch_prep(&M, c.user, c.pos, c.neg, c.B, st, c.uniq ? FVX_PREP_CLAIMS_LISTED : FVX_PREP_CLAIMS))
+    return rc;
+  k_pack_wu<<<scan_grid(c.B), 256, 0, st>>>(M, c.user, c.B, c.ws->run_id, c.ws->WU, (long long)c.ws->max_runs);
+  FVX_CHECK_LAUNCH("k_pack_wu");
+  return 0;
+}
+static int sh_p3(const ShCtx& c, cudaStream_t st) {
+  const FvxModel& M = *c.m;
+  const int B = c.B;
   // compact list of the owned slots; foreign entries of crow stay -1 (the fp32 kernels skip them)
   int32_t* count = M.sync + 1;
   cudaMemsetAsync(M.cmap, 0xFF, sizeof(int32_t) * 2 * (size_t)M.max_batch, st);
-  cudaMemsetAsync(S, 0, sizeof(float) * 2 * (size_t)B, st);
+  cudaMemsetAsync(c.ws->S, 0, sizeof(float) * 2 * (size_t)B, st);
   {
     long long g = (2LL * B + 255) / 256;
     if (g > (long long)fvx_num_sms() * 8) g = (long long)fvx_num_sms() * 8;
     k_compact_owned<<<(int)g, 256, 0, st>>>(M, B, count);
     FVX_CHECK_LAUNCH("k_compact_owned");
   }
-  const int ks = uniq ? uniq_ks_cap(&M, B) : sharded_ks(&M, B);
-  if (uniq) {
-    FVX_CHECK_ARG(2LL * B * fvx_tc_np(M.de) <= M.th_cap, "fvx_bpr_step_sharded_a: TH scratch too small");
-    if (int rc = fvx_launch_project_tc(&M, M.items.list, 0, 2 * B, ks, M.TH, st, M.items.count, 1)) return rc;
-  } else if (M.D > 0) {
-    if (M.use_tensor_cores) {
-      FVX_CHECK_ARG((long long)ks * 2 * B * fvx_tc_np(M.de) <= M.th_cap, "fvx_bpr_step_sharded_a: TH scratch too small");
-      // (the W rows past the owned ones, read by the last backward tile, are zeroed by phase B)
-      if (int rc = fvx_launch_project_tc(&M, M.cmap, 0, 2 * B, ks, M.TH, st, count)) return rc;
-    } else {
-      FVX_CHECK_ARG(2LL * B * M.de <= M.th_cap, "fvx_bpr_step_sharded_a: TH scratch too small");
-      if (int rc = fvx_launch_project(&M, M.cmap, 2 * B, M.TH, st)) return rc;
-    }
+  if (c.uniq) {
+    FVX_CHECK_ARG(2LL * B * fvx_tc_np(M.de) <= M.th_cap, "fvx_bpr_step_sharded: TH scratch too small");
+    return fvx_launch_project_tc(&M, M.items.list, 0, 2 * B, c.ks, M.TH, st, M.items.count, 1);
   }
-  if (side) fvx_side_join(st);
-  if (M.K % 4 == 0)
-    k_partial_scores_v4<<<ss_grid(B), SS_WARPS * 32, 0, st>>>(M, user, B, make_theta(&M, B, ks), S, count, uniq ? 1 : 0);
-  else
-    k_partial_scores<<<ss_grid(2LL * B), SS_WARPS * 32, 0, st>>>(M, user, B, make_theta(&M, B, ks), S, count);
+  if (M.D > 0) {
+    if (M.use_tensor_cores) {
+      FVX_CHECK_ARG((long long)c.ks * 2 * B * fvx_tc_np(M.de) <= M.th_cap, "fvx_bpr_step_sharded: TH scratch too small");
+      // (the W rows past the owned ones, read by the last backward tile, are zeroed by piece 5)
+      return fvx_launch_project_tc(&M, M.cmap, 0, 2 * B, c.ks, M.TH, st, count);
+    }
+    FVX_CHECK_ARG(2LL * B * M.de <= M.th_cap, "fvx_bpr_step_sharded: TH scratch too small");
+    return fvx_launch_project(&M, M.cmap, 2 * B, M.TH, st);
+  }
+  return 0;
+}
+static int sh_p4(const ShCtx& c, cudaStream_t st) {
+  const FvxModel& M = *c.m;
+  k_partial_scores_v4<<<ss_grid(c.B), SS_WARPS * 32, 0, st>>>(M, c.user, c.B, make_theta(&M, c.B, c.ks), c.ws->S, M.sync + 1,
+                                                             c.uniq ? 1 : 0, c.ws->WU, c.ws->run_id,
+                                                             (long long)c.ws->max_runs);
   FVX_CHECK_LAUNCH("k_partial_scores");
   return 0;
 }
-
-int fvx_bpr_step_sharded_b1(const FvxModel* model, const int32_t* user, int32_t B, const float* S,
-                            const int32_t* run_id, float* RU, int64_t ru_rows, int32_t loss_slot,
-                            fvx_stream_t stream) {
-  if (int rc = sharded_common(model, user, B, "fvx_bpr_step_sharded_b")) return rc;
-  FVX_CHECK_ARG(S && run_id && RU && ru_rows >= 1, "fvx_bpr_step_sharded_b: null pointer");
-  FVX_CHECK_ARG(loss_slot >= 0 && loss_slot < model->loss_slots, "fvx_bpr_step_sharded_b: loss_slot out of range");
-  const FvxModel& M = *model;
-  cudaStream_t st = fvx_cu(stream);
-  if (cudaMemsetAsync(RU, 0, sizeof(float) * ru_rows * M.users.stride, st) != cudaSuccess)
-    FVX_FAIL(-3, "fvx_bpr_step_sharded_b: memset failed");
-  const bool uniq = sharded_uniq(&M);
-  const int ks = uniq ? uniq_ks_cap(&M, B) : sharded_ks(&M, B);
+static int sh_p5(const ShCtx& c, cudaStream_t st) {
+  const FvxModel& M = *c.m;
+  if (cudaMemsetAsync(c.ws->RU, 0, sizeof(float) * (size_t)c.ws->max_runs * M.users.stride, st) != cudaSuccess)
+    FVX_FAIL(-3, "fvx_bpr_step_sharded: memset failed");
   const bool tc = M.D > 0 && M.use_tensor_cores;
-  if (M.K % 4 == 0) {
-    // one warp per owned slot: the work does not grow with the number of ranks
-    k_grads_owned<<<ss_grid(B), SS_WARPS * 32, 0, st>>>(M, user, B, loss_slot, make_theta(&M, B, ks),
-                                                              tc ? fvx_tc_np(M.de) : 0, tc ? fvx_w_pitch(&M) : 0, S,
-                                                              run_id, RU, (long long)ru_rows, M.sync + 1, uniq ? 1 : 0);
-    FVX_CHECK_LAUNCH("k_grads_owned");
-    if (uniq) {
-      if (int rc = fvx_launch_w_planes(&M, B, st)) return rc;
+  // one half-warp per owned slot: the work does not grow with the number of ranks
+  k_grads_owned<<<ss_grid(c.B), SS_WARPS * 32, 0, st>>>(M, c.user, c.B, c.loss_slot, make_theta(&M, c.B, c.ks),
+                                                       tc ? fvx_tc_np(M.de) : 0, tc ? fvx_w_pitch(&M) : 0, c.ws->S,
+                                                       c.ws->run_id, c.ws->RU, (long long)c.ws->max_runs, M.sync + 1,
+                                                       c.uniq ? 1 : 0, c.ws->WU, c.ws->loss_part);
+  FVX_CHECK_LAUNCH("k_grads_owned");
+  if (c.uniq) return fvx_launch_w_planes(&M, c.B, st);
+  return 0;
+}
+static int sh_p6(const ShCtx& c, cudaStream_t st) {
+  const FvxModel& M = *c.m;
+  int parts = 0;
+  const bool tc = M.D > 0 && M.use_tensor_cores;
+  if (M.D > 0) {
+    if (c.uniq) {
+      if (int rc = fvx_launch_grad_E_tc(&M, M.items.list, 2 * c.B, &parts, st, M.items.count)) return rc;
+    } else if (tc) {
+      if (int rc = fvx_launch_grad_E_tc(&M, M.cmap, 2 * c.B, &parts, st, M.sync + 1)) return rc;
+    } else {
+      if (int rc = fvx_launch_grad_E(&M, M.cmap, 2 * c.B, &parts, st)) return rc;
     }
-  } else {
-    if (tc) {   // W rows past the owned ones must read as zero in the last backward tile
-      const int np = fvx_tc_np(M.de), pitch = fvx_w_pitch(&M);
-      cudaMemsetAsync(M.W_hi, 0, sizeof(uint16_t) * 2 * (size_t)B * pitch, st);
-      if (pitch == np) cudaMemsetAsync(M.W_lo, 0, sizeof(uint16_t) * 2 * (size_t)B * np, st);
-    }
-    k_grads_sharded<<<ss_grid(B), SS_WARPS * 32, 0, st>>>(M, user, B, loss_slot, make_theta(&M, B, ks),
-                                                          tc ? fvx_tc_np(M.de) : 0, tc ? fvx_w_pitch(&M) : 0, S, run_id,
-                                                          RU, (long long)ru_rows);
-    FVX_CHECK_LAUNCH("k_grads_sharded");
   }
+  const int n = M.D * M.de;
+  k_dE_pack<<<n > 0 ? (n + 255) / 256 : 1, 256, 0, st>>>(M.gE_part, parts, M.D, tc ? fvx_tc_np(M.de) : M.de, M.de, c.ws->dE,
+                                                        c.ws->loss_part, M.sync);
+  FVX_CHECK_LAUNCH("k_dE_pack");
+  return 0;
+}
+static int sh_p7(const ShCtx& c, cudaStream_t st) {
+  const FvxModel& M = *c.m;
+  k_scatter_runs<<<scan_grid(c.B), 256, 0, st>>>(M, c.user, c.B, c.ws->run_id, c.ws->RU, (long long)c.ws->max_runs);
+  FVX_CHECK_LAUNCH("k_scatter_runs");
+  return 0;
+}
+static int sh_p8(const ShCtx& c, cudaStream_t st) {
+  const FvxModel& M = *c.m;
+  // DEFERRED: the touched rows keep their gradient and take the step when they are next needed (replay_row);
+  // the reduced dE, the loss (sum of the ranks' shares, NaN after a run overflow) and the step counter
+  return fvx_launch_update(&M, c.B, M.D > 0 ? 1 : 0, M.de, c.ws->dE, c.loss_slot, st,
+                           fvx_merged_update(&M) ? FVX_UPD_E : FVX_UPD_ALL, c.ws->dE + (size_t)M.D * M.de);
+}
+
+static int make_ctx(ShCtx* c, const FvxModel* m, const FvxShardWs* ws, const int32_t* user, const int32_t* pos,
+                    const int32_t* neg, int B, int loss_slot, const char* who) {
+  if (int rc = sharded_common(m, ws, user, B, who)) return rc;
+  FVX_CHECK_ARG(pos && neg, "%s: null batch pointer", who);
+  FVX_CHECK_ARG(loss_slot >= 0 && loss_slot < m->loss_slots, "%s: loss_slot out of range", who);
+  c->m = m; c->ws = ws; c->user = user; c->pos = pos; c->neg = neg; c->B = B; c->loss_slot = loss_slot;
+  c->uniq = sharded_uniq(m);
+  c->ks = c->uniq ? uniq_ks_cap(m, B) : sharded_ks(m, B);
   return 0;
 }
 
-int fvx_bpr_step_sharded_b2(const FvxModel* model, int32_t B, float* dE, fvx_stream_t stream) {
-  FVX_CHECK_ARG(model != nullptr, "fvx_bpr_step_sharded_b: null model");
-  const FvxModel& M = *model;
-  if (M.D == 0) return 0;
-  FVX_CHECK_ARG(dE != nullptr && B >= 1 && B <= M.max_batch, "fvx_bpr_step_sharded_b: VBPR needs the dE buffer");
+extern "C" {
+
+int fvx_bpr_step_sharded_phase(const FvxModel* model, const FvxShardWs* ws, const int32_t* user, const int32_t* pos,
+                               const int32_t* neg, int32_t B, int32_t loss_slot, int32_t phase, fvx_stream_t stream) {
+  ShCtx c;
+  if (int rc = make_ctx(&c, model, ws, user, pos, neg, B, loss_slot, "fvx_bpr_step_sharded_phase")) return rc;
   cudaStream_t st = fvx_cu(stream);
-  const bool tc = M.use_tensor_cores;
-  int parts = 0;
-  if (tc && sharded_uniq(&M)) {
-    if (int rc = fvx_launch_grad_E_tc(&M, M.items.list, 2 * B, &parts, st, M.items.count)) return rc;
-  } else if (tc) {
-    if (int rc = fvx_launch_grad_E_tc(&M, M.cmap, 2 * B, &parts, st, M.sync + 1)) return rc;
-  } else {
-    if (int rc = fvx_launch_grad_E(&M, M.cmap, 2 * B, &parts, st)) return rc;
+  switch (phase) {
+    case 0:
+      if (int rc = sh_p1(c, st)) return rc;
+      return sh_p2(c, st);
+    case 1:
+      if (int rc = sh_p3(c, st)) return rc;
+      return sh_p4(c, st);
+    case 2:
+      if (int rc = sh_p5(c, st)) return rc;
+      return sh_p6(c, st);
+    case 3:
+      if (int rc = sh_p7(c, st)) return rc;
+      return sh_p8(c, st);
+    default:
+      FVX_FAIL(-2, "fvx_bpr_step_sharded_phase: phase %d outside [0, 3]", phase);
   }
-  return fvx_launch_reduce_gE(&M, parts, tc ? fvx_tc_np(M.de) : M.de, dE, st);
 }
 
-int fvx_bpr_step_sharded_b(const FvxModel* model, const int32_t* user, int32_t B, const float* S,
-                           const int32_t* run_id, float* RU, int64_t ru_rows, float* dE, int32_t loss_slot,
-                           fvx_stream_t stream) {
-  FVX_CHECK_ARG(model != nullptr && (model->D == 0 || dE != nullptr), "fvx_bpr_step_sharded_b: VBPR needs the dE buffer");
-  if (int rc = fvx_bpr_step_sharded_b1(model, user, B, S, run_id, RU, ru_rows, loss_slot, stream)) return rc;
-  return fvx_bpr_step_sharded_b2(model, B, dE, stream);
-}
-
-int fvx_bpr_step_sharded_c(const FvxModel* model, const int32_t* user, int32_t B, const int32_t* run_id,
-                           const float* RU, int64_t ru_rows, const float* dE, int32_t loss_slot,
-                           fvx_stream_t stream) {
-  if (int rc = sharded_common(model, user, B, "fvx_bpr_step_sharded_c")) return rc;
-  FVX_CHECK_ARG(run_id && RU, "fvx_bpr_step_sharded_c: null pointer");
+int fvx_bpr_step_sharded(const FvxModel* model, const FvxShardWs* ws, FvxComm* comm, const int32_t* user,
+                         const int32_t* pos, const int32_t* neg, int32_t B, int32_t loss_slot, fvx_stream_t stream) {
+  ShCtx c;
+  if (int rc = make_ctx(&c, model, ws, user, pos, neg, B, loss_slot, "fvx_bpr_step_sharded")) return rc;
+  FVX_CHECK_ARG(comm != nullptr, "fvx_bpr_step_sharded: null communicator");
   const FvxModel& M = *model;
-  FVX_CHECK_ARG(M.D == 0 || dE != nullptr, "fvx_bpr_step_sharded_c: VBPR needs the reduced dE");
-  cudaStream_t st = fvx_cu(stream);
-  long long g = ((long long)B * 32 + 255) / 256;
-  if (g > (long long)fvx_num_sms() * 8) g = (long long)fvx_num_sms() * 8;
-  k_scatter_runs<<<(int)g, 256, 0, st>>>(M, user, B, run_id, RU, (long long)ru_rows);
-  FVX_CHECK_LAUNCH("k_scatter_runs");
-  // loss_slot < 0: the E term of the loss (VBPR.py:129) is not added (ranks other than 0, so that
-  // the per-rank losses sum to the batch loss)
-  // DEFERRED: the touched rows keep their gradient and take the step when they are next needed (replay_row)
-  return fvx_launch_update(&M, B, M.D > 0 ? 1 : 0, M.de, dE, loss_slot, st,
-                           fvx_merged_update(&M) ? FVX_UPD_E : FVX_UPD_ALL);
+  cudaStream_t st = fvx_cu(stream), sd = comm->side;
+  const size_t n_ru = (size_t)ws->max_runs * M.users.stride;
+  if (int rc = sh_p1(c, st)) return rc;
+  cudaEventRecord(comm->ev[0], st);
+  cudaStreamWaitEvent(sd, comm->ev[0], 0);
+  // side: the owned users are brought up to date and published while the projection runs
+  if (int rc = sh_p2(c, sd)) return rc;
+  if (int rc = fvx_comm_allreduce(comm, 1, ws->WU, n_ru, sd)) return rc;
+  cudaEventRecord(comm->ev[1], sd);
+  if (int rc = sh_p3(c, st)) return rc;
+  cudaStreamWaitEvent(st, comm->ev[1], 0);
+  if (int rc = sh_p4(c, st)) return rc;
+  if (int rc = fvx_comm_allreduce(comm, 0, ws->S, 2 * (size_t)B, st)) return rc;
+  if (int rc = sh_p5(c, st)) return rc;
+  cudaEventRecord(comm->ev[2], st);
+  cudaStreamWaitEvent(sd, comm->ev[2], 0);
+  // side: the user-row gradient shares travel, and the owners take theirs, while grad_E runs
+  if (int rc = fvx_comm_allreduce(comm, 1, ws->RU, n_ru, sd)) return rc;
+  if (int rc = sh_p7(c, sd)) return rc;
+  cudaEventRecord(comm->ev[3], sd);
+  if (int rc = sh_p6(c, st)) return rc;
+  if (int rc = fvx_comm_allreduce(comm, 0, ws->dE, (size_t)M.D * M.de + 4, st)) return rc;
+  cudaStreamWaitEvent(st, comm->ev[3], 0);
+  return sh_p8(c, st);
 }
 
 }  // extern "C"

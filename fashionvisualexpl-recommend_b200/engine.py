@@ -30,7 +30,11 @@ def _r4(x):
 class Engine:
     def __init__(self, num_users, num_items, K, d=0, D=0, lr=1e-3, reg=0.0, adam_mode="deferred",
                  max_batch=4096, device="cuda:0", item_lo=0, item_cnt=None, loss_slots=4096,
-                 ge_parts=80, seed=0, use_tensor_cores=False, unique_rows=True):
+                 ge_parts=80, seed=0, use_tensor_cores=False, unique_rows=True, user_lo=0, user_cnt=None,
+                 user_rows=None, sharded=False):
+        """``item_lo / item_cnt``: the catalog rows this rank owns; ``user_lo / user_cnt``: the users it owns (their
+        Adam state lives here; the user tables are still allocated and indexed globally - ``user_rows`` rows, at
+        least ``num_users``, so that equal-sized blocks can be gathered in place)."""
         if not torch.cuda.is_available():
             raise _lib.FvxError("no CUDA device: the fvx engine has no CPU path")
         _lib.load()
@@ -41,6 +45,9 @@ class Engine:
             self.d = 0
         self.item_lo = int(item_lo)
         self.Ic = int(item_cnt) if item_cnt is not None else self.I - self.item_lo
+        self.user_lo = int(user_lo)
+        self.user_cnt = int(user_cnt) if user_cnt is not None else self.U - self.user_lo
+        self.U_rows = max(int(user_rows) if user_rows is not None else self.U, self.U)
         self.Su, self.Si, self.de = _r4(self.K + self.d), _r4(self.K + 1), _r4(self.d + 1) if self.D else 0
         self.lr, self.reg = float(lr), float(reg)
         self.adam_mode = _lib.ADAM_MODES[adam_mode] if isinstance(adam_mode, str) else int(adam_mode)
@@ -58,14 +65,14 @@ class Engine:
             t["count"] = torch.zeros(1, **i32)
             return t
 
-        self.users = table(self.U, self.Su, self.max_batch)
+        self.users = table(self.U_rows, self.Su, self.max_batch)
         self.items = table(self.Ic, self.Si, 2 * self.max_batch)
         self.step_t = torch.zeros(1, dtype=torch.int64, device=dev)
         self.loss_t = torch.zeros(self.loss_slots, dtype=torch.float64, device=dev)
         self.rows_t = torch.zeros(2 * self.max_batch, **i32)
         self.sync_t = torch.zeros(4, **i32)
         self.stage_t = torch.zeros(3 * self.max_batch + 4, **i32)     # fvx_bpr_steps: batch in flight + cursor
-        self.cmap_t = torch.zeros(6 * self.max_batch, **i32) if (self.item_lo or self.Ic != self.I) else None
+        self.cmap_t = torch.zeros(6 * self.max_batch, **i32) if (sharded or self.item_lo or self.Ic != self.I) else None
         self.F = self.F_pl = None
         self.ET_hi = self.ET_lo = self.W_hi = self.W_lo = None
         self.upos_t = self.W_sum = self.uslot_t = None
@@ -135,7 +142,7 @@ class Engine:
         uw, iw = self.users["w"], self.items["w"]
         uw.zero_()
         iw.zero_()
-        uw[:, :self.K] = glorot(gen(1), self.U, self.K, self.U, self.K)
+        uw[:self.U, :self.K] = glorot(gen(1), self.U, self.K, self.U, self.K)
         g, chunk = gen(2), 65536
         lo, hi = self.item_lo, self.item_lo + self.Ic
         for s0 in range(0, self.I, chunk):                  # the same stream on every rank: all chunks are drawn
@@ -145,16 +152,16 @@ class Engine:
             if a < b:
                 iw[a - lo:b - lo, :self.K] = blk[a - s0:b - s0]
         if self.D:
-            uw[:, self.K:self.K + self.d] = glorot(gen(3), self.U, self.d, self.U, self.d)
+            uw[:self.U, self.K:self.K + self.d] = glorot(gen(3), self.U, self.d, self.U, self.d)
             self.E.zero_()
             self.E[:, :self.d] = glorot(gen(4), self.D, self.d, self.D, self.d)
             self.E[:, self.d:self.d + 1] = glorot(gen(5), self.D, 1, self.D, 1)
 
     # reference attribute names as views into the packed tables
     @property
-    def Gu(self): return self.users["w"][:, :self.K]
+    def Gu(self): return self.users["w"][:self.U, :self.K]
     @property
-    def Tu(self): return self.users["w"][:, self.K:self.K + self.d]
+    def Tu(self): return self.users["w"][:self.U, self.K:self.K + self.d]
     @property
     def Gi(self): return self.items["w"][:, :self.K]
     @property
@@ -217,7 +224,8 @@ class Engine:
             m.num_users, m.num_items, m.item_lo, m.item_cnt = self.U, self.I, self.item_lo, self.Ic
             m.K, m.d, m.D, m.de, m.adam_mode = self.K, self.d, self.D, self.de, self.adam_mode
             m.lr, m.reg = self.lr, self.reg
-            m.users = self._table_struct(self.users, self.U, self.Su)
+            m.users = self._table_struct(self.users, self.U_rows, self.Su)
+            m.user_lo, m.user_cnt = self.user_lo, self.user_cnt
             m.items = self._table_struct(self.items, self.Ic, self.Si)
             m.E, m.mE, m.vE, m.gE_part = ptr(self.E), ptr(self.mE), ptr(self.vE), ptr(self.gE_part)
             m.ge_parts = self.ge_parts

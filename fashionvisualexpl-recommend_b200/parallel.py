@@ -1,17 +1,21 @@
 """One process per GPU: the item catalog (Gi, Bi, F and their Adam state) row-sharded over the
-ranks of a ``torch.distributed`` group, user tables and E replicated.
+ranks of a ``torch.distributed`` group, the USERS owned in contiguous blocks (the owner keeps a user's Adam
+state and publishes the user's row to the others for the steps that touch it), E replicated.
 
-* ``shard_bounds``            contiguous item block of a rank;
-* ``ShardedStep``             the BPR step over the three C-ABI phases of include/fvx.h with the
-                              all-reduces between them (S: 2B floats; RU: packed user-row
-                              gradients; dE: D x de) - NCCL over NVLink on a GPU box;
-* ``exchange_topk`` / ``sharded_topk``   evaluation: every rank sweeps all users over its shard,
-                              the per-shard top-k lists are exchanged by user slice
-                              (all-to-all) and merged there (``fvx_topk_merge``).
+* ``shard_bounds`` / ``user_bounds``   contiguous item block / user block of a rank;
+* ``sharded_engine``          an ``Engine`` holding one rank's part;
+* ``ShardedStep``             the BPR step: ONE C-ABI call per rank per step (``fvx_bpr_step_sharded``) that
+                              issues its four all-reduces itself - WU (fresh user rows) beside the projection
+                              and RU (user-row gradient shares) beside grad_E on a side stream, S (partial
+                              scores) and dE on the caller's - over NCCL communicators created from an id that
+                              ``torch.distributed`` broadcasts;
+* ``exchange_topk`` / ``sharded_topk``   evaluation: every rank sweeps all users over its shard, the per-shard
+                              top-k lists are exchanged by user slice (all-to-all) and merged there
+                              (``fvx_topk_merge``).
 
-``world`` may also be *emulated* on one GPU (``LocalGroup``): the ranks are engines in one
-process and the collectives plain tensor sums - used by the GPU tests, since several ranks of one
-job must never be separate launches on one GPU.
+``world`` may also be *emulated* on one GPU (``LocalGroup``): the ranks are engines in one process, the step
+runs phase by phase (``fvx_bpr_step_sharded_phase``) and the collectives are plain tensor sums - used by the
+GPU tests, since several ranks of one job must never be separate launches on one GPU.
 """
 from __future__ import annotations
 
@@ -30,6 +34,23 @@ def shard_bounds(num_items, world, rank):
     return lo, base + (1 if rank < rem else 0)
 
 
+def user_bounds(num_users, world, rank):
+    """(user_lo, user_cnt, user_rows) of ``rank``: equal blocks of ceil(U / world) users (the last ones shorter or
+    empty); ``user_rows`` = world * block, the rows every rank allocates so that the blocks gather in place."""
+    per = (int(num_users) + world - 1) // world
+    lo = min(int(num_users), rank * per)
+    return lo, max(0, min(int(num_users), lo + per) - lo), per * world
+
+
+def sharded_engine(world, rank, num_users, num_items, K, **kw):
+    """The ``Engine`` of one rank of a ``world``-rank job (item shard + user block of that rank)."""
+    from .engine import Engine
+    lo, cnt = shard_bounds(num_items, world, rank)
+    ulo, ucnt, urows = user_bounds(num_users, world, rank)
+    return Engine(num_users, num_items, K, item_lo=lo, item_cnt=cnt, user_lo=ulo, user_cnt=ucnt, user_rows=urows,
+                  sharded=True, **kw)
+
+
 def run_ids(user):
     """run_id[b] of the batch (int32): runs of equal consecutive users, counted from 0."""
     start = torch.ones_like(user, dtype=torch.int32)
@@ -44,6 +65,30 @@ class DistGroup:
         import torch.distributed as dist
         self.dist, self.group = dist, group
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self._comm = None
+
+    def comm(self, device):
+        """The ``FvxComm`` of this rank (two NCCL communicators owned by libfvx), created on first use: rank 0
+        draws the id, ``torch.distributed`` broadcasts its 256 bytes, every rank joins (collective)."""
+        if self._comm is None:
+            buf = (C.c_uint8 * _lib.COMM_ID_BYTES)()
+            if self.rank == 0:
+                call("fvx_comm_unique_id", buf)
+            t = torch.tensor(list(buf), dtype=torch.uint8, device=device)
+            self.dist.broadcast(t, src=self.dist.get_global_rank(self.group, 0) if self.group is not None else 0,
+                                group=self.group)
+            raw = bytes(t.cpu().tolist())
+            idb = (C.c_uint8 * _lib.COMM_ID_BYTES).from_buffer_copy(raw)
+            out = C.c_void_p()
+            with torch.cuda.device(device):
+                call("fvx_comm_create", idb, self.rank, self.world, C.byref(out))
+            self._comm = out
+        return self._comm
+
+    def close(self):
+        if self._comm is not None:
+            call("fvx_comm_destroy", self._comm)
+            self._comm = None
 
     def all_reduce(self, tensors):
         for t in tensors:
@@ -100,68 +145,85 @@ class ShardedStep:
     """``engines``: this process's engines - ONE with a ``DistGroup``, or all R with a ``LocalGroup``."""
 
     def __init__(self, engines, group, max_runs=None):
-        """``max_runs``: upper bound of the number of runs of equal users in a batch (default: the batch
-        size); the all-reduced user-gradient buffer has that many rows, so a tight bound - e.g.
-        B // (shortest train list) + 2 for batches of the reference's sampler - saves NVLink bytes."""
+        """``max_runs``: upper bound of the number of runs of equal users in a batch.  Default: the batch size
+        (the hard bound).  The user rows (WU) and user-gradient shares (RU) exchanged per step have that many
+        rows, so a tight bound - B // (shortest train list) + 2 is exact for batches of the reference's
+        sampler - saves NVLink bytes; a batch with more runs poisons that step's loss with NaN on every rank."""
         self.engines, self.group = list(engines), group
         e = self.engines[0]
-        B, dv = e.max_batch, e.device
+        B = e.max_batch
         self.max_runs = int(max_runs) if max_runs else B
-        self.S = [torch.zeros(2 * B, dtype=torch.float32, device=dv) for _ in self.engines]
-        self.RU = [torch.zeros(self.max_runs, e.Su, dtype=torch.float32, device=dv) for _ in self.engines]
-        self.dE = [torch.zeros(e.D, e.de, dtype=torch.float32, device=dv) if e.D else None for _ in self.engines]
-        self.rid = torch.zeros(B, dtype=torch.int32, device=dv)
-        self.rid_scratch = torch.zeros(B // 4096 + 2, dtype=torch.int32, device=dv)
-
-    def _rank_of(self, i):
-        return self.group.rank if self.group.rank is not None else i
+        self.ws = []
+        for e in self.engines:
+            dv = e.device
+            f32, i32 = dict(dtype=torch.float32, device=dv), dict(dtype=torch.int32, device=dv)
+            t = {"S": torch.zeros(2 * B, **f32), "run_id": torch.zeros(B, **i32),
+                 "run_scratch": torch.zeros(B // 4096 + 2, **i32), "WU": torch.zeros(self.max_runs, e.Su, **f32),
+                 "RU": torch.zeros(self.max_runs, e.Su, **f32), "dE": torch.zeros(e.D * e.de + 4, **f32),
+                 "loss_part": torch.zeros(1, dtype=torch.float64, device=dv)}
+            w = _lib.FvxShardWs(ptr(t["S"]), ptr(t["run_id"]), ptr(t["run_scratch"]), ptr(t["WU"]), ptr(t["RU"]),
+                                ptr(t["dE"]), ptr(t["loss_part"]), self.max_runs, 0)
+            t["struct"] = w
+            self.ws.append(t)
+        self._comm = group.comm(self.engines[0].device) if isinstance(group, DistGroup) else None
 
     def step(self, user, pos, neg, loss_slot=0):
-        """One optimiser step on every (local) rank; asynchronous apart from the collectives."""
+        """One optimiser step on every (local) rank; asynchronous."""
         B = user.numel()
-        # run ids of the batch (needed from phase B on): two small launches through the C ABI - the step is
-        # ~20 host calls and every torch op saved shortens the launch-bound tail on a busy host
-        rid = self.rid[:B]
-        call("fvx_run_ids", ptr(user), B, ptr(rid), ptr(self.rid_scratch), stream_ptr())
-        for e, S in zip(self.engines, self.S):
-            call("fvx_bpr_step_sharded_a", C.byref(e.struct()), ptr(user), ptr(pos), ptr(neg), B, ptr(S), stream_ptr())
-        self.group.all_reduce(self.S)
-        for e, S, RU in zip(self.engines, self.S, self.RU):
-            call("fvx_bpr_step_sharded_b1", C.byref(e.struct()), ptr(user), B, ptr(S), ptr(rid), ptr(RU), RU.shape[0],
-                 loss_slot, stream_ptr())
-        # the all-reduce of the user-row gradients (the only large message) travels while grad_E runs
-        pending = self.group.all_reduce_start(self.RU)
-        if self.dE[0] is not None:
-            for e, dE in zip(self.engines, self.dE):
-                call("fvx_bpr_step_sharded_b2", C.byref(e.struct()), B, ptr(dE), stream_ptr())
-            self.group.all_reduce(self.dE)
-        self.group.all_reduce_finish(pending)
-        for i, (e, RU, dE) in enumerate(zip(self.engines, self.RU, self.dE)):
-            call("fvx_bpr_step_sharded_c", C.byref(e.struct()), ptr(user), B, ptr(rid), ptr(RU), RU.shape[0],
-                 ptr(dE), loss_slot if self._rank_of(i) == 0 else -1, stream_ptr())
+        if self._comm is not None:
+            e, w = self.engines[0], self.ws[0]
+            call("fvx_bpr_step_sharded", C.byref(e.struct()), C.byref(w["struct"]), self._comm, ptr(user), ptr(pos),
+                 ptr(neg), B, loss_slot, stream_ptr())
+            return
+        # emulated ranks: the step cut at its collectives, the sums done here
+        sums = (("WU",), ("S",), ("RU", "dE"), ())
+        for phase in range(4):
+            for e, w in zip(self.engines, self.ws):
+                call("fvx_bpr_step_sharded_phase", C.byref(e.struct()), C.byref(w["struct"]), ptr(user), ptr(pos),
+                     ptr(neg), B, loss_slot, phase, stream_ptr())
+            for name in sums[phase]:
+                self.group.all_reduce([w[name] for w in self.ws])
 
     def take_loss(self, slot=0):
-        """Batch loss (sum of the per-rank parts) as a 1-element device tensor of the first local rank;
-        the accumulators are cleared.  Stream-ordered, no host synchronisation (run overflow is reported
-        by ``read_loss`` / ``check_runs``)."""
+        """Batch loss as a 1-element device tensor of the first local rank (every rank holds the whole loss: the
+        ranks' shares travel with dE); the accumulators are cleared.  Stream-ordered, no host synchronisation.
+        NaN: the batch had more runs of equal users than ``max_runs``."""
         parts = [e.take_loss(slot) for e in self.engines]
-        self.group.all_reduce(parts)
         return parts[0]
 
-    def check_runs(self):
-        if any(int(e.sync_t[2].item()) for e in self.engines):
-            raise _lib.FvxError("a batch had more runs of equal users than max_runs=%d" % self.max_runs)
-
     def read_loss(self, slot=0, clear=True):
-        """Batch loss = sum of the per-rank partial losses (synchronises)."""
-        if any(int(e.sync_t[2].item()) for e in self.engines):
-            raise _lib.FvxError("a batch had more runs of equal users than max_runs=%d" % self.max_runs)
-        parts = [e.loss_t[slot:slot + 1].clone() for e in self.engines]
+        """Batch loss (synchronises); raises if the batch had more runs than ``max_runs``."""
+        vals = [float(e.loss_t[slot].item()) for e in self.engines]
         if clear:
             for e in self.engines:
                 e.loss_t[slot] = 0
-        self.group.all_reduce(parts)
-        return float(parts[0].item())
+        if any(v != v for v in vals):
+            raise _lib.FvxError("a batch had more runs of equal users than max_runs=%d" % self.max_runs)
+        return vals[0]
+
+    def sync_users(self):
+        """Flushes deferred optimiser state and gathers the user rows from their owners, so that every rank
+        holds every user's current row (evaluation sweeps all users on every rank; ``Engine.params()``)."""
+        gather_users(self.engines, self.group)
+
+
+def gather_users(engines, group):
+    R = group.world
+    for e in engines:
+        e.flush()
+    if R == 1:
+        return
+    per = engines[0].U_rows // R
+    if isinstance(group, DistGroup):
+        e = engines[0]
+        w = e.users["w"]
+        own = w[group.rank * per:(group.rank + 1) * per].clone()
+        group.dist.all_gather_into_tensor(w, own, group=group.group)
+    else:
+        blocks = [e.users["w"][r * per:(r + 1) * per].clone() for r, e in enumerate(engines)]
+        for e in engines:
+            for r, blk in enumerate(blocks):
+                e.users["w"][r * per:(r + 1) * per].copy_(blk)
 
 
 # ---- evaluation ---------------------------------------------------------------------------------
@@ -195,6 +257,7 @@ def sharded_topk(engines, group, mask_row_ptr, mask_col, k, tc=None):
     """Full-catalog masked top-k with the catalog sharded: returns, per local rank, the merged
     ``(ids, scores)`` of that rank's user slice ``[U/R (padded), k]``."""
     from .engine import topk_merge
+    gather_users(engines, group)
     ids, scores = [], []
     for e in engines:
         i_, s_ = e.score_topk(mask_row_ptr, mask_col, k, tc=tc)
@@ -211,6 +274,7 @@ def gathered_view(engines, group):
     the whole catalog and no merge is needed.  Returns one view per local engine for
     ``Engine.score_topk(view=...)``."""
     R = group.world
+    gather_users(engines, group)
     e0 = engines[0]
     I = e0.I
     cnts = [shard_bounds(I, R, r)[1] for r in range(R)]

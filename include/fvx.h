@@ -119,6 +119,11 @@ typedef struct FvxModel {
   float* W_sum;         /* [2*max_batch, NP] fp32 sums of the backward coefficients per listed
                            row; all-zero between steps                                        */
   int32_t* uslot;       /* [2*max_batch] list position of the row of each (triple, side) slot  */
+  int32_t user_lo;      /* first user row OWNED by this rank (0 on one GPU)                                   */
+  int32_t user_cnt;     /* user rows owned by this rank (num_users on one GPU).  The user tables are allocated
+                           and indexed globally on every rank, but only the owner keeps a user's Adam state
+                           (m, v, g, last) and its authoritative row; other ranks' copies of w are stale until
+                           the rows are gathered (evaluation, checkpoint)                                      */
   int32_t* batch_stage; /* [3*max_batch + 4] staging area of fvx_bpr_steps: the (user | pos | neg) indices of
                            the batch in flight and the 64-bit batch cursor (may be NULL otherwise)     */
 } FvxModel;
@@ -184,32 +189,67 @@ int fvx_bpr_step_timed(const FvxModel* model, const int32_t* user, const int32_t
                        const int32_t* neg, int32_t B, int32_t loss_slot, float* phase_ms_host,
                        fvx_stream_t stream);
 
-/* ---- the same step with the item catalog row-sharded over R ranks ----------------------
- * Every rank calls the three phases with the SAME batch (global item ids); `model` holds the
- * rank's shard (item_lo, item_cnt), replicated user tables and E.  x_uij = s_ui - s_uj is linear
- * in the item-side terms, so the ranks exchange only: S (2B floats, sum), the packed user-row
- * gradients RU and the dense dE (sums).  The host performs the three all-reduces (NCCL) between
- * the phases.  Item ids must lie inside the catalog.
- *   run_id[b] = index of the run of equal users that triple b belongs to (runs counted from 0
- *   in batch order); RU has ru_rows >= number of runs rows of users.stride floats. */
-int fvx_bpr_step_sharded_a(const FvxModel* model, const int32_t* user, const int32_t* pos,
-                           const int32_t* neg, int32_t B, float* S, fvx_stream_t stream);
-/* run_id of a batch (see above) in two small launches; scratch: >= n / 4096 + 1 int32. */
+/* ---- the same step with the model sharded over R ranks (one process per GPU) --------------------------
+ * Items (Gi, Bi, F and their Adam state) are row-sharded in contiguous blocks (item_lo, item_cnt); USERS are
+ * owned in contiguous blocks too (user_lo, user_cnt): the owner keeps a user's Adam state and applies its
+ * updates; E is replicated.  Every rank sees the same batch (global ids).  x_uij = s_ui - s_uj is linear in
+ * the item-side terms, so a rank scores the (triple, side) slots whose item it owns, and the ranks exchange
+ * four buffers per step, all by sum (a buffer holds zeros where a rank has nothing to say):
+ *   WU [max_runs, users.stride]  the up-to-date rows of the batch's users, indexed by RUN of equal users (the
+ *                                reference's sampler emits runs of one user, dataset.py:96-99); written by
+ *                                the owner of the user
+ *   S  [2B]                      partial scores of the slots [pos(B) | neg(B)]
+ *   RU [max_runs, users.stride]  user-row gradient shares by run; the owner adds its runs into its accumulators
+ *   dE [D*de + 4]                dense gradient of E_ext, then the loss share (two floats, hi + lo) and the
+ *                                run-overflow flag
+ * Work per rank: 2B/R slots, B/R user rows - nothing grows with the number of ranks except the scans of the
+ * batch indices.  No item row ever leaves its owner.  run_id[b] = index of the run triple b belongs to; a batch
+ * with more than max_runs runs poisons the step's loss with NaN on every rank (nothing fails silently). */
+typedef struct FvxShardWs {
+  float* S;
+  int32_t* run_id;       /* [max_batch] */
+  int32_t* run_scratch;  /* [max_batch / 4096 + 2] */
+  float* WU;
+  float* RU;
+  float* dE;
+  double* loss_part;     /* [1] this rank's loss share of the step in flight */
+  int32_t max_runs;
+  int32_t _pad;
+} FvxShardWs;
+
+/* Communicators of the sharded step: two NCCL communicators over the same ranks, one for the collectives on
+ * the caller's stream (S, dE) and one for those that travel on a side stream beside the tensor-core kernels
+ * (WU beside the projection, RU beside grad_E).  libnccl.so.2 is resolved at run time (the copy the process
+ * already loaded, e.g. torch's, else the system one); libfvx does not link against it.
+ *   rank 0: fvx_comm_unique_id(id)  ->  broadcast the 256 bytes (torch.distributed, MPI, a file ...)
+ *   every rank: fvx_comm_create(id, rank, world, &comm)   [collective]                                   */
+typedef struct FvxComm FvxComm;
+#define FVX_COMM_ID_BYTES 256
+int fvx_comm_unique_id(uint8_t* id_host);
+int fvx_comm_create(const uint8_t* id_host, int32_t rank, int32_t world, FvxComm** out);
+int fvx_comm_destroy(FvxComm* comm);
+/* all-reduce (sum) of n floats in place on the caller's stream, e.g. to assemble per-rank statistics */
+int fvx_comm_all_reduce_f32(FvxComm* comm, float* buf, int64_t n, fvx_stream_t stream);
+
+/* run_id of a batch (see above) in two small launches; scratch: >= n / 4096 + 2 int32. */
 int fvx_run_ids(const int32_t* user, int64_t n, int32_t* run_id, int32_t* scratch, fvx_stream_t stream);
-int fvx_bpr_step_sharded_b(const FvxModel* model, const int32_t* user, int32_t B, const float* S,
-                           const int32_t* run_id, float* RU, int64_t ru_rows, float* dE,
-                           int32_t loss_slot, fvx_stream_t stream);
-/* Phase B in two calls (b = b1 then b2), so that the host can start the all-reduce of RU while
- * grad_E runs: b1 = gradients of the owned slots (item rows, RU, W, loss); b2 = dE of the owned slots. */
-int fvx_bpr_step_sharded_b1(const FvxModel* model, const int32_t* user, int32_t B, const float* S,
-                            const int32_t* run_id, float* RU, int64_t ru_rows, int32_t loss_slot,
-                            fvx_stream_t stream);
-int fvx_bpr_step_sharded_b2(const FvxModel* model, int32_t B, float* dE, fvx_stream_t stream);
-/* loss_slot < 0: the reg*(|E|^2+|Bp|^2) loss term is not added (use on ranks other than 0).
- * A batch with more than ru_rows runs sets model->sync[2] = 1 (its surplus runs are dropped). */
-int fvx_bpr_step_sharded_c(const FvxModel* model, const int32_t* user, int32_t B,
-                           const int32_t* run_id, const float* RU, int64_t ru_rows, const float* dE,
-                           int32_t loss_slot, fvx_stream_t stream);
+
+/* One optimiser step of the sharded model: ONE call per rank per step; the four all-reduces are issued inside
+ * (NCCL), WU and RU on a side stream.  The batch loss lands in model->loss[loss_slot] on EVERY rank. */
+int fvx_bpr_step_sharded(const FvxModel* model, const FvxShardWs* ws, FvxComm* comm, const int32_t* user,
+                         const int32_t* pos, const int32_t* neg, int32_t B, int32_t loss_slot, fvx_stream_t stream);
+
+/* The same step cut at its collectives, everything on `stream`, for callers that perform the sums themselves
+ * (tests that emulate R ranks inside one process; other transports):
+ *   phase 0  run ids, rows of the owned slots, catch-up of the owned users, their fresh rows -> WU
+ *            -- sum WU over the ranks --
+ *   phase 1  projection of the distinct owned rows, partial scores -> S
+ *            -- sum S --
+ *   phase 2  gradients of the owned slots (item rows, RU, backward coefficients), dE, loss share -> dE
+ *            -- sum RU, sum dE --
+ *   phase 3  RU rows of the owned users -> their accumulators; Adam on E; loss; step += 1               */
+int fvx_bpr_step_sharded_phase(const FvxModel* model, const FvxShardWs* ws, const int32_t* user, const int32_t* pos,
+                               const int32_t* neg, int32_t B, int32_t loss_slot, int32_t phase, fvx_stream_t stream);
 
 /* DEFERRED mode: bring every row of both tables up to the current step - pending
  * gradient step, then the skipped zero-gradient steps (call before reading

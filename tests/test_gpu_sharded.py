@@ -1,7 +1,8 @@
-"""GPU: the item-sharded paths (fvx_bpr_step_sharded_a/b/c, per-shard top-k + merge) against the
-single-rank path and the oracle.  The R ranks are EMULATED on one GPU (fvx.parallel.LocalGroup:
-R engines in one process, collectives = tensor sums), because mutually waiting ranks must not be
-separate launches on one GPU; the real NCCL path is exercised by bench.py --gpus N."""
+"""GPU: the sharded paths (fvx_bpr_step_sharded_phase, per-shard top-k + merge) against the single-rank
+path and the oracle.  The R ranks are EMULATED on one GPU (fvx.parallel.LocalGroup: R engines in one
+process, the step cut at its collectives, collectives = tensor sums), because mutually waiting ranks must
+not be separate launches on one GPU; the one-call NCCL path (fvx_bpr_step_sharded) is checked against the
+oracle by bench.py --gpus N (parity_checked) and by tests/test_gpu_multi.py on a multi-GPU box."""
 import numpy as np
 import pytest
 import torch
@@ -14,19 +15,20 @@ pytestmark = pytest.mark.gpu
 
 
 def _shards(U, I, K, d, D, R, P, F, **kw):
-    from fvx.parallel import shard_bounds
+    from fvx.parallel import sharded_engine
     es = []
     for r in range(R):
-        lo, cnt = shard_bounds(I, R, r)
-        e = _engine(U, I, K, d=d, D=D, item_lo=lo, item_cnt=cnt, **kw)
+        e = sharded_engine(R, r, U, I, K, d=d, D=D, **kw)
         if D:
-            e.set_features(F[lo:lo + cnt])
+            e.set_features(F[e.item_lo:e.item_lo + e.Ic])
         e.load_params(P)
         es.append(e)
     return es
 
 
-def _gather_params(es):
+def _gather_params(es, R):
+    from fvx.parallel import LocalGroup, gather_users
+    gather_users(es, LocalGroup(R))                 # user rows live on their owners until gathered
     Ps = [e.params() for e in es]
     out = {k: Ps[0][k] for k in Ps[0] if k not in ("Gi", "Bi")}
     out["Gi"] = np.concatenate([p["Gi"] for p in Ps], 0)
@@ -46,27 +48,57 @@ def test_sharded_step_matches_oracle_and_single_rank(K, d, D, B, mode, R, tc):
     P, F, rng = _random_problem(U, I, K, d, D, seed=K + d + R)
     es = _shards(U, I, K, d, D, R, P, F, lr=lr, reg=reg, adam_mode=mode, max_batch=B, use_tensor_cores=tc)
     step = ShardedStep(es, LocalGroup(R))
-    # runs of distinct users, as the reference's sampler emits them (a user has at most two runs in a
-    # batch, across an epoch boundary): the sum of <= 2 run gradients per user is order-independent,
-    # which is what keeps the replicated user state bit-identical on every rank
+    # runs of users as the reference's sampler emits them; now and then a user has two runs in a batch (as
+    # across an epoch boundary): both runs must see the row its owner published
     batches = []
-    for _ in range(steps):
-        u = np.repeat(rng.permutation(U)[:B // 6 + 1], 6)[:B]
+    for s_ in range(steps):
+        order = rng.permutation(U)[:B // 6 + 1]
+        if s_ % 3 == 1:
+            order[-1] = order[0]
+        u = np.repeat(order, 6)[:B]
         batches.append((u, rng.integers(0, I, B), rng.integers(0, I, B)))
     P32, P64, l32, l64 = _oracle_pair(P, F, batches, reg, lr)
     for s, b in enumerate(batches):
         step.step(*(_dev(x) for x in b), loss_slot=s % 5)
+        per_rank = [float(e.loss_t[s % 5].item()) for e in es]
+        assert max(per_rank) == min(per_rank), per_rank            # the whole loss on every rank
         got = step.read_loss(s % 5)
         assert got == pytest.approx(l64[s], rel=REL), (s, mode, R)
-    Q, Ps = _gather_params(es)
+    Q, Ps = _gather_params(es, R)
     for k in P64:
         ref = P64[k]
         dlt = np.abs(Q[k].reshape(ref.shape) - ref) / np.abs(ref).max()
         assert (dlt > REL).mean() <= 2e-3, (k, float((dlt > REL).mean()))
         assert dlt.max() <= max(20 * REL, 3 * rel_err(P32[k], ref)), (k, float(dlt.max()))
-    for name in ("Gu",) + (("Tu", "E", "Bp") if D else ()):       # replicated state is bit-identical on every rank
+    for name in (("E", "Bp") if D else ()):       # replicated state is bit-identical on every rank
         for p in Ps[1:]:
             assert np.array_equal(p[name], Ps[0][name]), name
+    # only the owner keeps a user's optimiser state
+    for r, e in enumerate(es):
+        own = torch.zeros(e.U_rows, dtype=torch.bool, device=e.device)
+        own[e.user_lo:e.user_lo + e.user_cnt] = True
+        assert float(e.users["m"][~own].abs().max()) == 0.0 and float(e.users["g"][~own].abs().max()) == 0.0
+
+
+def test_sharded_step_run_overflow_poisons_the_loss():
+    """A batch with more runs of equal users than max_runs: the step's loss is NaN on every rank and
+    read_loss raises (nothing is dropped silently); the next, well-formed batch is clean again."""
+    from fvx import _lib
+    from fvx.parallel import LocalGroup, ShardedStep
+    U, I, K, d, D, B, R = 300, 401, 16, 8, 128, 128, 2
+    P, F, rng = _random_problem(U, I, K, d, D, seed=4)
+    es = _shards(U, I, K, d, D, R, P, F, max_batch=B, use_tensor_cores=True)
+    step = ShardedStep(es, LocalGroup(R), max_runs=B // 4 + 2)
+    ok = (np.repeat(rng.permutation(U)[:B // 4], 4), rng.integers(0, I, B), rng.integers(0, I, B))
+    bad = (rng.permutation(U)[:B], rng.integers(0, I, B), rng.integers(0, I, B))      # B runs of one triple
+    step.step(*(_dev(x) for x in ok))
+    assert np.isfinite(step.read_loss())
+    step.step(*(_dev(x) for x in bad))
+    assert all(np.isnan(float(e.loss_t[0].item())) for e in es)
+    with pytest.raises(_lib.FvxError):
+        step.read_loss()
+    step.step(*(_dev(x) for x in ok))
+    assert np.isfinite(step.read_loss())
 
 
 @pytest.mark.parametrize("R", [2, 4])
