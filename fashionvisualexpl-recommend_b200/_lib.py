@@ -40,7 +40,7 @@ class FvxModel(C.Structure):
 
 class FvxShardWs(C.Structure):
     _fields_ = [("S", _p), ("run_id", _p), ("run_scratch", _p), ("WU", _p), ("RU", _p), ("dE", _p), ("loss_part", _p),
-                ("max_runs", C.c_int32), ("_pad", C.c_int32)]
+                ("max_runs", C.c_int32), ("run_cap", C.c_int32), ("owners", C.c_int32), ("users_per_owner", C.c_int32)]
 
 
 COMM_ID_BYTES = 256
@@ -69,6 +69,7 @@ PROTOTYPES = {
     "fvx_bpr_steps": (C.c_int, [_MP, _p, _p, _p, _i64, _i32, _i32, _i32, _p]),
     "fvx_bpr_step_timed": (C.c_int, [_MP, _p, _p, _p, _i32, _i32, C.POINTER(C.c_float), _p]),
     "fvx_run_ids": (C.c_int, [_p, _i64, _p, _p, _p]),
+    "fvx_run_slots": (C.c_int, [_p, _i64, _i32, _i32, _i32, _p, _p, _p]),
     "fvx_bpr_step_sharded": (C.c_int, [_MP, C.POINTER(FvxShardWs), _p, _p, _p, _p, _i32, _i32, _p]),
     "fvx_bpr_step_sharded_phase": (C.c_int, [_MP, C.POINTER(FvxShardWs), _p, _p, _p, _i32, _i32, _i32, _p]),
     "fvx_comm_unique_id": (C.c_int, [_p]),
@@ -92,6 +93,8 @@ PROTOTYPES = {
     "fvx_debug_set_dedup": (C.c_int, [C.c_int]),
     "fvx_debug_trace": (C.c_int, [C.c_int]),
     "fvx_debug_trace_read": (C.c_int, [C.POINTER(C.c_float)]),
+    "fvx_debug_trace_sharded": (C.c_int, [C.c_int]),
+    "fvx_debug_trace_sharded_read": (C.c_int, [C.POINTER(C.c_float)]),
 }
 
 _lib = None

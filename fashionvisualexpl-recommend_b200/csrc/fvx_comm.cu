@@ -15,6 +15,8 @@ struct NcclApi {
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
   ncclResult_t (*CommDestroy)(ncclComm_t);
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
+  ncclResult_t (*ReduceScatter)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
   ncclResult_t (*GroupStart)();
   ncclResult_t (*GroupEnd)();
   const char* (*GetErrorString)(ncclResult_t);
@@ -34,6 +36,8 @@ static int nccl_load() {
   FVX_SYM(CommInitRank, "ncclCommInitRank")
   FVX_SYM(CommDestroy, "ncclCommDestroy")
   FVX_SYM(AllReduce, "ncclAllReduce")
+  FVX_SYM(AllGather, "ncclAllGather")
+  FVX_SYM(ReduceScatter, "ncclReduceScatter")
   FVX_SYM(GroupStart, "ncclGroupStart")
   FVX_SYM(GroupEnd, "ncclGroupEnd")
   FVX_SYM(GetErrorString, "ncclGetErrorString")
@@ -52,6 +56,20 @@ int fvx_comm_allreduce(FvxComm* c, int which, float* buf, size_t n, cudaStream_t
   if (n == 0) return 0;
   FVX_NCCL(g_nccl.AllReduce(buf, buf, n, ncclFloat, ncclSum, reinterpret_cast<ncclComm_t>(c->nccl[which]), st),
            "all-reduce");
+  return 0;
+}
+
+// in place over R equal segments of `seg` floats at `buf`: rank r's segment is buf + r * seg
+int fvx_comm_allgather(FvxComm* c, int which, float* buf, size_t seg, cudaStream_t st) {
+  if (seg == 0) return 0;
+  FVX_NCCL(g_nccl.AllGather(buf + (size_t)c->rank * seg, buf, seg, ncclFloat, reinterpret_cast<ncclComm_t>(c->nccl[which]), st),
+           "all-gather");
+  return 0;
+}
+int fvx_comm_reducescatter(FvxComm* c, int which, float* buf, size_t seg, cudaStream_t st) {
+  if (seg == 0) return 0;
+  FVX_NCCL(g_nccl.ReduceScatter(buf, buf + (size_t)c->rank * seg, seg, ncclFloat, ncclSum,
+                                reinterpret_cast<ncclComm_t>(c->nccl[which]), st), "reduce-scatter");
   return 0;
 }
 

@@ -3,7 +3,7 @@
 #include <cuda_runtime.h>
 #include <stddef.h>
 
-#define FVX_COMM_EVENTS 4
+#define FVX_COMM_EVENTS 6
 struct FvxComm {
   void* nccl[2];          // [0]: collectives on the caller's stream (S, dE); [1]: on the side stream (WU, RU)
   int rank, world;
@@ -12,3 +12,6 @@ struct FvxComm {
 };
 // all-reduce (sum, fp32, in place) on communicator `which` (0 / 1), enqueued on `st`
 int fvx_comm_allreduce(FvxComm* c, int which, float* buf, size_t n, cudaStream_t st);
+// in place over `world` equal segments of `seg` floats at `buf` (rank r's segment: buf + r * seg)
+int fvx_comm_allgather(FvxComm* c, int which, float* buf, size_t seg, cudaStream_t st);
+int fvx_comm_reducescatter(FvxComm* c, int which, float* buf, size_t seg, cudaStream_t st);

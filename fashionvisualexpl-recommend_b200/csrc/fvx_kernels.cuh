@@ -44,14 +44,16 @@ int fvx_launch_split_E(const FvxModel* m, cudaStream_t st);
 int fvx_launch_split_planes(const float* src, uint16_t* dst, long long n_rows, int D, cudaStream_t st);
 // dyn_ks = 1: `ksplit` is only the cap; the kernel derives the split from *nrows_dev (fvx_tc_ksplit_rule) and
 // lays the partials out [split][nrows][NP] with the HOST-side nrows as the row capacity.
+// sm_reserve: SMs the launch leaves free (the sharded step keeps a few for the NCCL kernels that travel beside
+// the tensor-core kernels: a persistent one-CTA-per-SM grid would make them wait for its last CTA)
 int fvx_launch_project_tc(const FvxModel* m, const int32_t* rows, int row0, int64_t nrows, int ksplit, float* out,
-                          cudaStream_t st, const int32_t* nrows_dev = nullptr, int dyn_ks = 0);
+                          cudaStream_t st, const int32_t* nrows_dev = nullptr, int dyn_ks = 0, int sm_reserve = 0);
 int fvx_launch_reduce_partials(const float* part, long long nrows, int NP, int ks, int de, float* out,
                                cudaStream_t st);
 int fvx_launch_split_W(const FvxModel* m, const float* W, const int32_t* rows, long long nrows, cudaStream_t st);
 int fvx_launch_reduce_gE(const FvxModel* m, int parts, int gnp, float* out, cudaStream_t st);
 int fvx_launch_grad_E_tc(const FvxModel* m, const int32_t* rows, int64_t nrows, int* parts_out, cudaStream_t st,
-                         const int32_t* nrows_dev = nullptr);
+                         const int32_t* nrows_dev = nullptr, int sm_reserve = 0);
 
 // Side stream of the step (one per device, FVX_STEP_OVERLAP=0 disables it): begin() makes it wait for the
 // work queued on `main_stream` and returns it (nullptr: unavailable); join() makes `main_stream` wait for it.
@@ -64,7 +66,10 @@ int fvx_check_model(const FvxModel* m, const char* who);
 // (slot rows + E planes); CLAIMS = claims + deferred-Adam catch-up without the row / plane writes
 // UNIQ = slot rows + E planes + claims of the item rows with their list positions (unique-row step);
 // CLAIMS_LISTED = user claims + catch-up, item catch-up driven by the list UNIQ built
-enum { FVX_PREP_ALL = 0, FVX_PREP_ROWS = 1, FVX_PREP_CLAIMS = 2, FVX_PREP_UNIQ = 3, FVX_PREP_CLAIMS_LISTED = 4 };
+// USERS_ONLY / ITEMS_LISTED: the two halves of CLAIMS_LISTED (the sharded step publishes the user rows before
+// the item rows are caught up)
+enum { FVX_PREP_ALL = 0, FVX_PREP_ROWS = 1, FVX_PREP_CLAIMS = 2, FVX_PREP_UNIQ = 3, FVX_PREP_CLAIMS_LISTED = 4,
+       FVX_PREP_USERS_ONLY = 5, FVX_PREP_ITEMS_LISTED = 6 };
 int fvx_launch_prep(const FvxModel* m, const int32_t* user, const int32_t* pos, const int32_t* neg, int B,
                     cudaStream_t st, int what = FVX_PREP_ALL);
 // what: ALL = tables + E_ext + finalisation; TABLES = touched rows only; E = E_ext + finalisation

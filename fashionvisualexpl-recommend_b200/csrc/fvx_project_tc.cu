@@ -577,7 +577,7 @@ int fvx_launch_split_E(const FvxModel* m, cudaStream_t st) {
 
 // out: [ksplit][nrows][NP] fp32 partials (ksplit from fvx_tc_ksplit)
 int fvx_launch_project_tc(const FvxModel* m, const int32_t* rows, int row0, int64_t nrows, int ksplit, float* out,
-                          cudaStream_t st, const int32_t* nrows_dev, int dyn_ks) {
+                          cudaStream_t st, const int32_t* nrows_dev, int dyn_ks, int sm_reserve) {
   FVX_CHECK_ARG(m->F_pl && m->ET_hi && m->ET_lo, "tensor-core projection: bf16 planes missing");
   FVX_CHECK_ARG(m->D % PT_KC == 0, "tensor-core projection: D=%d must be a multiple of %d", m->D, PT_KC);
   const int NP = fvx_tc_np(m->de);
@@ -622,7 +622,10 @@ int fvx_launch_project_tc(const FvxModel* m, const int32_t* rows, int row0, int6
   static FvxSmemMark fwd_smem;
   if (int r = fvx_ensure_smem((const void*)k_proj_fwd_tc, &fwd_smem, smem, "k_proj_fwd_tc")) return r;
   long long grid = (long long)P.n_tiles * ksplit;
-  if (grid > fvx_num_sms() || dyn_ks) grid = fvx_num_sms();
+  int sms = fvx_num_sms() - sm_reserve;
+  if (sms < 8) sms = 8;
+  if (grid > sms || dyn_ks) grid = sms;
+  P.nsm = sms;
   k_proj_fwd_tc<<<(int)grid, PT_THREADS, smem, st>>>(b_hi, b_lo, P);
   FVX_CHECK_LAUNCH("k_proj_fwd_tc");
   return 0;
@@ -630,7 +633,7 @@ int fvx_launch_project_tc(const FvxModel* m, const int32_t* rows, int row0, int6
 
 // gE_part[p][D][NP] = partial sums; W planes [nrows][NP] bf16.  *parts_out = row groups written.
 int fvx_launch_grad_E_tc(const FvxModel* m, const int32_t* rows, int64_t nrows, int* parts_out, cudaStream_t st,
-                         const int32_t* nrows_dev) {
+                         const int32_t* nrows_dev, int sm_reserve) {
   FVX_CHECK_ARG(m->F_pl && m->W_hi && m->W_lo && m->gE_part, "tensor-core grad_E: buffers missing");
   FVX_CHECK_ARG(m->D % 128 == 0, "tensor-core grad_E: D=%d must be a multiple of 128", m->D);
   const int NP = fvx_tc_np(m->de);
@@ -638,7 +641,7 @@ int fvx_launch_grad_E_tc(const FvxModel* m, const int32_t* rows, int64_t nrows, 
   while (fgs > 128 && (m->D % fgs != 0 || (fgs / 128) * NP > 512)) fgs >>= 1;
   FVX_CHECK_ARG(m->D % fgs == 0 && (fgs / 128) * NP <= 512, "tensor-core grad_E: d+1=%d too wide", m->de);
   const int nfg = m->D / fgs;
-  int max_rg = fvx_num_sms() / nfg;
+  int max_rg = (fvx_num_sms() - sm_reserve) / nfg;
   if (max_rg < 1) max_rg = 1;
   if (max_rg > m->ge_parts) max_rg = m->ge_parts;
   long long rpg = (nrows + max_rg - 1) / max_rg;

@@ -208,7 +208,8 @@ k_uniq_rows(FvxModel M, const int32_t* __restrict__ pos, const int32_t* __restri
 
 __global__ void __launch_bounds__(256, 4)
 k_prep(FvxModel M, const int32_t* __restrict__ user, const int32_t* __restrict__ pos,
-       const int32_t* __restrict__ neg, int B, int nb_mark, int NP, int write_rows, int tpw, int items_listed) {
+       const int32_t* __restrict__ neg, int B, int nb_mark, int NP, int write_rows, int tpw, int items_listed,
+       int part) {     // part (items_listed only): 0 = everything, 1 = the user rows only, 2 = uslot + the listed item rows only
   const int lane = threadIdx.x & 31;
   if ((int)blockIdx.x >= nb_mark) {
     split_E_planes(M, NP, blockIdx.x - nb_mark, gridDim.x - nb_mark);
@@ -217,7 +218,7 @@ k_prep(FvxModel M, const int32_t* __restrict__ user, const int32_t* __restrict__
   const int32_t done = (int32_t)(*M.step);
   const int32_t t = done + 1;
   const bool deferred = M.adam_mode == FVX_ADAM_DEFERRED;
-  if (items_listed) {
+  if (items_listed && part != 1) {
     // list position of every slot's row (k_uniq_rows has finished): the scoring kernel reads it with its
     // other indices instead of chasing rows -> upos
     for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < 2 * B; s += nb_mark * blockDim.x) {
@@ -229,7 +230,7 @@ k_prep(FvxModel M, const int32_t* __restrict__ user, const int32_t* __restrict__
   // replays the claimed rows one after the other with all 32 lanes on the row's columns
   const int warp_g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (nb_mark * blockDim.x) >> 5;
-  for (int b0 = warp_g * tpw; b0 < B; b0 += nwarps * tpw) {
+  for (int b0 = warp_g * tpw; b0 < (part == 2 ? 0 : B); b0 += nwarps * tpw) {
     const int b = b0 + lane;
     const bool live = lane < tpw && b < B;
     int32_t u = -1, li_ = -1, lj = -1;
@@ -275,7 +276,7 @@ k_prep(FvxModel M, const int32_t* __restrict__ user, const int32_t* __restrict__
       }
     }
   }
-  if (items_listed && deferred) {
+  if (items_listed && deferred && part != 1) {
     // the item rows were claimed by k_uniq_rows: catch up the listed rows, 8 lanes per row
     int n = *M.items.count;
     if (n > M.items.list_cap) n = M.items.list_cap;
@@ -926,8 +927,9 @@ int fvx_launch_prep(const FvxModel* m, const int32_t* user, const int32_t* pos, 
   int nb_mark = (B + 8 * tpw - 1) / (8 * tpw);     // 8 warps per block
   if (nb_mark > fvx_num_sms() * 8) nb_mark = fvx_num_sms() * 8;
   const bool all = what == FVX_PREP_ALL;
-  k_prep<<<nb_mark + (all ? nb_e : 0), 256, 0, st>>>(*m, user, pos, neg, B, nb_mark, NP, all ? 1 : 0, tpw,
-                                                     what == FVX_PREP_CLAIMS_LISTED ? 1 : 0);
+  const int listed = (what == FVX_PREP_CLAIMS_LISTED || what == FVX_PREP_USERS_ONLY || what == FVX_PREP_ITEMS_LISTED) ? 1 : 0;
+  k_prep<<<nb_mark + (all ? nb_e : 0), 256, 0, st>>>(*m, user, pos, neg, B, nb_mark, NP, all ? 1 : 0, tpw, listed,
+                                                     what == FVX_PREP_USERS_ONLY ? 1 : (what == FVX_PREP_ITEMS_LISTED ? 2 : 0));
   FVX_CHECK_LAUNCH("k_prep");
   return 0;
 }

@@ -24,6 +24,7 @@
 // the per-triple terms that are not tied to an item (softplus loss, user-side L2): the rank that
 // owns the POSITIVE item.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "fvx_comm.cuh"
 #include "fvx_common.cuh"
@@ -326,7 +327,7 @@ __global__ void k_scatter_runs(FvxModel M, const int32_t* __restrict__ user, int
 }
 
 // The owner of a user publishes the user's up-to-date row for this step: WU[run] = w[u] for the run starts of
-// OWNED users (k_prep has caught the row up); WU is zero elsewhere, so the sum over the ranks is the row.
+// OWNED users (k_prep has caught the row up) - they all lie in the owner's segment of WU, which is then gathered.
 __global__ void k_pack_wu(FvxModel M, const int32_t* __restrict__ user, int B, const int32_t* __restrict__ run_id,
                           float* __restrict__ WU, long long ru_rows) {
   const int lane = threadIdx.x & 31;
@@ -363,8 +364,18 @@ __global__ void k_dE_pack(const float* __restrict__ part, int parts, int D, int 
   const int n = D * de;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int f = i / de, c = i - f * de;
+    const float* gp = part + (size_t)f * gnp + c;
+    const size_t ps = (size_t)D * gnp;
     float g = 0.0f;
-    for (int p = 0; p < parts; ++p) g += part[((size_t)p * D + f) * gnp + c];
+    int p = 0;
+    for (; p + 8 <= parts; p += 8) {             // eight loads in flight, summed in a fixed order
+      float t_[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) t_[q] = gp[(size_t)(p + q) * ps];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) g += t_[q];
+    }
+    for (; p < parts; ++p) g += gp[(size_t)p * ps];
     out[i] = g;
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -452,6 +463,100 @@ extern "C" int fvx_run_ids(const int32_t* user, int64_t n, int32_t* run_id, int3
   return 0;
 }
 
+// Run SLOTS: the same runs, but numbered per OWNER of the run's user: slot = owner * cap + (index of the run among
+// the runs of that owner, in batch order).  The rows of the exchanged buffers (WU, RU) are then grouped in one
+// contiguous segment of `cap` rows per owner, so the fresh user rows travel as an all-gather and the gradient
+// shares as a reduce-scatter - half the bytes of the all-reduces a run-ordered layout needs.  A run whose index
+// reaches cap gets slot 0x7fffffff (the kernels skip it and flag the step).  Up to 8 owners: the per-owner counts
+// of a 256-element round are scanned as eight 16-bit fields of two 64-bit words.
+#define RS_OWNERS 8
+#define RS_PER 4          // rounds of 256 elements per block: 1024 elements, so that a batch of 131 k triples fills the machine
+__device__ __forceinline__ int rs_owner(int32_t u, int per, int R) {
+  int o = per > 0 ? u / per : 0;
+  return o < 0 ? 0 : (o >= R ? R - 1 : o);
+}
+__global__ void __launch_bounds__(RI_THREADS)
+k_slot_count(const int32_t* __restrict__ user, long long n, int per, int R, int32_t* __restrict__ part) {
+  __shared__ int sh[RS_OWNERS];
+  if (threadIdx.x < RS_OWNERS) sh[threadIdx.x] = 0;
+  __syncthreads();
+  const long long base = (long long)blockIdx.x * RI_THREADS * RS_PER;
+  for (int e = 0; e < RS_PER; ++e) {
+    const long long b = base + (long long)e * RI_THREADS + threadIdx.x;
+    if (b < n && (b == 0 || user[b] != user[b - 1])) atomicAdd(&sh[rs_owner(user[b], per, R)], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x < RS_OWNERS) part[blockIdx.x * RS_OWNERS + threadIdx.x] = sh[threadIdx.x];
+}
+__global__ void __launch_bounds__(RI_THREADS)
+k_slot_write(const int32_t* __restrict__ user, long long n, int per, int R, int cap, const int32_t* __restrict__ part,
+             int32_t* __restrict__ run_id) {
+  __shared__ unsigned long long sh[RI_THREADS / 32][2];
+  __shared__ int carry[RS_OWNERS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x < RS_OWNERS) carry[threadIdx.x] = 0;
+  __syncthreads();
+  {                                   // runs of each owner in the blocks before this one: 32 threads per owner
+    const int o = threadIdx.x >> 5;
+    int t = 0;
+    for (int q = lane; q < (int)blockIdx.x; q += 32) t += part[q * RS_OWNERS + o];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
+    if (lane == 0) carry[o] = t;
+  }
+  __syncthreads();
+  const long long base = (long long)blockIdx.x * RI_THREADS * RS_PER;
+  for (int e = 0; e < RS_PER; ++e) {                      // 256 consecutive elements per round
+    const long long b = base + (long long)e * RI_THREADS + threadIdx.x;
+    int o = 0;
+    unsigned long long x0 = 0ull, x1 = 0ull;               // this element's contribution: a start of owner o
+    if (b < n) {
+      o = rs_owner(user[b], per, R);
+      if (b == 0 || user[b] != user[b - 1]) {
+        if (o < 4) x0 = 1ull << (16 * o); else x1 = 1ull << (16 * (o - 4));
+      }
+    }
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {                     // inclusive scan of the round's eight counters
+      const unsigned long long y0 = __shfl_up_sync(0xffffffffu, x0, d), y1 = __shfl_up_sync(0xffffffffu, x1, d);
+      if (lane >= d) { x0 += y0; x1 += y1; }
+    }
+    if (lane == 31) { sh[warp][0] = x0; sh[warp][1] = x1; }
+    __syncthreads();
+    unsigned long long off0 = 0ull, off1 = 0ull, tot0 = 0ull, tot1 = 0ull;
+    for (int w = 0; w < RI_THREADS / 32; ++w) {
+      if (w < warp) { off0 += sh[w][0]; off1 += sh[w][1]; }
+      tot0 += sh[w][0]; tot1 += sh[w][1];
+    }
+    if (b < n) {
+      const unsigned long long w_ = o < 4 ? (x0 + off0) >> (16 * o) : (x1 + off1) >> (16 * (o - 4));
+      const int idx = carry[o] + (int)(w_ & 0xFFFFull) - 1;   // runs of owner o that start at or before b, minus one
+      run_id[b] = idx < cap ? o * cap + idx : 0x7fffffff;
+    }
+    __syncthreads();
+    if (threadIdx.x < RS_OWNERS) {
+      const unsigned long long t_ = threadIdx.x < 4 ? tot0 >> (16 * threadIdx.x) : tot1 >> (16 * (threadIdx.x - 4));
+      carry[threadIdx.x] += (int)(t_ & 0xFFFFull);
+    }
+    __syncthreads();
+  }
+}
+
+extern "C" int fvx_run_slots(const int32_t* user, int64_t n, int32_t users_per_owner, int32_t owners, int32_t cap,
+                             int32_t* run_slot, int32_t* scratch, fvx_stream_t stream) {
+  FVX_CHECK_ARG(user && run_slot && scratch && n >= 0, "fvx_run_slots: bad arguments");
+  FVX_CHECK_ARG(owners >= 1 && owners <= RS_OWNERS && users_per_owner >= 1 && cap >= 1, "fvx_run_slots: owners=%d outside [1, %d]",
+                owners, RS_OWNERS);
+  if (n == 0) return 0;
+  const long long nb = (n + RI_THREADS * RS_PER - 1) / (RI_THREADS * RS_PER);
+  FVX_CHECK_ARG(nb <= 8192, "fvx_run_slots: n=%lld too large", (long long)n);
+  cudaStream_t st = fvx_cu(stream);
+  k_slot_count<<<(int)nb, RI_THREADS, 0, st>>>(user, n, users_per_owner, owners, scratch);
+  k_slot_write<<<(int)nb, RI_THREADS, 0, st>>>(user, n, users_per_owner, owners, cap, scratch, run_slot);
+  FVX_CHECK_LAUNCH("k_run_slots");
+  return 0;
+}
+
 static int sharded_common(const FvxModel* m, const FvxShardWs* ws, const int32_t* user, int B, const char* who) {
   if (int rc = fvx_check_model(m, who)) return rc;
   FVX_CHECK_ARG(user != nullptr && B >= 1 && B <= m->max_batch, "%s: bad batch", who);
@@ -459,7 +564,8 @@ static int sharded_common(const FvxModel* m, const FvxShardWs* ws, const int32_t
   FVX_CHECK_ARG(m->rows && m->loss && m->sync && m->cmap, "%s: null scratch (rows / loss / sync / cmap)", who);
   FVX_CHECK_ARG(m->K % 4 == 0, "%s: the sharded step needs embed_k %% 4 == 0 (got %d)", who, m->K);
   FVX_CHECK_ARG(ws && ws->S && ws->run_id && ws->run_scratch && ws->WU && ws->RU && ws->dE && ws->loss_part &&
-                ws->max_runs >= 1, "%s: incomplete FvxShardWs", who);
+                ws->run_cap >= 1 && ws->owners >= 1 && ws->max_runs == ws->owners * ws->run_cap && ws->users_per_owner >= 1,
+                "%s: incomplete FvxShardWs", who);
   if (m->D > 0) {
     FVX_CHECK_ARG(m->TH && m->gE_part && m->ge_parts > 0, "%s: VBPR scratch missing", who);
     if (m->use_tensor_cores) FVX_CHECK_ARG(m->F_pl && m->ET_hi && m->ET_lo && m->W_hi && m->W_lo, "%s: bf16 planes missing", who);
@@ -476,7 +582,7 @@ static int sharded_ks(const FvxModel* m, int B) {
   return ks;
 }
 
-static SsTheta make_theta(const FvxModel* m, int B, int ks) {
+static SsTheta make_theta(const FvxModel* m, int B, int ks, int sm_reserve = 0) {
   SsTheta T;
   const bool tc = m->D > 0 && m->use_tensor_cores;
   T.p = m->TH;
@@ -484,7 +590,8 @@ static SsTheta make_theta(const FvxModel* m, int B, int ks) {
   T.ks = tc ? ks : 1;
   T.ss = 2LL * B * T.np;
   T.chunks = m->D > 0 ? m->D / 64 : 1;
-  T.nsm = fvx_num_sms();
+  T.nsm = fvx_num_sms() - sm_reserve;      // what the projection was launched with (its K split follows it)
+  if (T.nsm < 8) T.nsm = 8;
   return T;
 }
 
@@ -521,22 +628,37 @@ struct ShCtx {
   int B, loss_slot;
   bool uniq;
   int ks;
+  int sm_reserve;       // SMs the tensor-core kernels leave to the NCCL kernels that travel beside them
 };
 
-static int sh_p1(const ShCtx& c, cudaStream_t st) {
-  const FvxModel& M = *c.m;
-  if (int rc = fvx_run_ids(c.user, c.B, c.ws->run_id, c.ws->run_scratch, st)) return rc;
-  if (cudaMemsetAsync(c.ws->WU, 0, sizeof(float) * (size_t)c.ws->max_runs * M.users.stride, st) != cudaSuccess)
-    FVX_FAIL(-3, "fvx_bpr_step_sharded: memset failed");
-  return fvx_launch_prep(&M, c.user, c.pos, c.neg, c.B, st, c.uniq ? FVX_PREP_UNIQ : FVX_PREP_ROWS);
+// piece 1 in two halves: (a) what the projection needs - slot rows, claims of the owned item rows, E planes;
+// (b) what only the user side needs - run ids, the cleared exchange buffers - which the full step runs on the side stream
+static int sh_p1a(const ShCtx& c, cudaStream_t st) {
+  return fvx_launch_prep(c.m, c.user, c.pos, c.neg, c.B, st, c.uniq ? FVX_PREP_UNIQ : FVX_PREP_ROWS);
 }
-static int sh_p2(const ShCtx& c, cudaStream_t st) {
+static int sh_p1b(const ShCtx& c, cudaStream_t st) {
+  // (WU needs no clearing: every row a kernel reads was written by the run's owner and gathered)
+  return fvx_run_slots(c.user, c.B, c.ws->users_per_owner, c.ws->owners, c.ws->run_cap, c.ws->run_id, c.ws->run_scratch, st);
+}
+static int sh_clear_ru(const ShCtx& c, cudaStream_t st) {
   const FvxModel& M = *c.m;
-  if (int rc = fvx_launch_prep(&M, c.user, c.pos, c.neg, c.B, st, c.uniq ? FVX_PREP_CLAIMS_LISTED : FVX_PREP_CLAIMS))
+  if (cudaMemsetAsync(c.ws->RU, 0, sizeof(float) * (size_t)c.ws->max_runs * M.users.stride, st) != cudaSuccess)
+    FVX_FAIL(-3, "fvx_bpr_step_sharded: memset failed");
+  return 0;
+}
+// piece 2 in two halves (unique-row step): (u) the owned users are caught up and published - the exchange of WU can
+// start; (i) the listed item rows are caught up, which nothing waits for before the partial scores
+static int sh_p2u(const ShCtx& c, cudaStream_t st) {
+  const FvxModel& M = *c.m;
+  if (int rc = fvx_launch_prep(&M, c.user, c.pos, c.neg, c.B, st, c.uniq ? FVX_PREP_USERS_ONLY : FVX_PREP_CLAIMS))
     return rc;
   k_pack_wu<<<scan_grid(c.B), 256, 0, st>>>(M, c.user, c.B, c.ws->run_id, c.ws->WU, (long long)c.ws->max_runs);
   FVX_CHECK_LAUNCH("k_pack_wu");
   return 0;
+}
+static int sh_p2i(const ShCtx& c, cudaStream_t st) {
+  if (!c.uniq) return 0;
+  return fvx_launch_prep(c.m, c.user, c.pos, c.neg, c.B, st, FVX_PREP_ITEMS_LISTED);
 }
 static int sh_p3(const ShCtx& c, cudaStream_t st) {
   const FvxModel& M = *c.m;
@@ -553,13 +675,13 @@ static int sh_p3(const ShCtx& c, cudaStream_t st) {
   }
   if (c.uniq) {
     FVX_CHECK_ARG(2LL * B * fvx_tc_np(M.de) <= M.th_cap, "fvx_bpr_step_sharded: TH scratch too small");
-    return fvx_launch_project_tc(&M, M.items.list, 0, 2 * B, c.ks, M.TH, st, M.items.count, 1);
+    return fvx_launch_project_tc(&M, M.items.list, 0, 2 * B, c.ks, M.TH, st, M.items.count, 1, c.sm_reserve);
   }
   if (M.D > 0) {
     if (M.use_tensor_cores) {
       FVX_CHECK_ARG((long long)c.ks * 2 * B * fvx_tc_np(M.de) <= M.th_cap, "fvx_bpr_step_sharded: TH scratch too small");
       // (the W rows past the owned ones, read by the last backward tile, are zeroed by piece 5)
-      return fvx_launch_project_tc(&M, M.cmap, 0, 2 * B, c.ks, M.TH, st, count);
+      return fvx_launch_project_tc(&M, M.cmap, 0, 2 * B, c.ks, M.TH, st, count, 0, c.sm_reserve);
     }
     FVX_CHECK_ARG(2LL * B * M.de <= M.th_cap, "fvx_bpr_step_sharded: TH scratch too small");
     return fvx_launch_project(&M, M.cmap, 2 * B, M.TH, st);
@@ -568,7 +690,7 @@ static int sh_p3(const ShCtx& c, cudaStream_t st) {
 }
 static int sh_p4(const ShCtx& c, cudaStream_t st) {
   const FvxModel& M = *c.m;
-  k_partial_scores_v4<<<ss_grid(c.B), SS_WARPS * 32, 0, st>>>(M, c.user, c.B, make_theta(&M, c.B, c.ks), c.ws->S, M.sync + 1,
+  k_partial_scores_v4<<<ss_grid(c.B), SS_WARPS * 32, 0, st>>>(M, c.user, c.B, make_theta(&M, c.B, c.ks, c.sm_reserve), c.ws->S, M.sync + 1,
                                                              c.uniq ? 1 : 0, c.ws->WU, c.ws->run_id,
                                                              (long long)c.ws->max_runs);
   FVX_CHECK_LAUNCH("k_partial_scores");
@@ -576,11 +698,9 @@ static int sh_p4(const ShCtx& c, cudaStream_t st) {
 }
 static int sh_p5(const ShCtx& c, cudaStream_t st) {
   const FvxModel& M = *c.m;
-  if (cudaMemsetAsync(c.ws->RU, 0, sizeof(float) * (size_t)c.ws->max_runs * M.users.stride, st) != cudaSuccess)
-    FVX_FAIL(-3, "fvx_bpr_step_sharded: memset failed");
   const bool tc = M.D > 0 && M.use_tensor_cores;
   // one half-warp per owned slot: the work does not grow with the number of ranks
-  k_grads_owned<<<ss_grid(c.B), SS_WARPS * 32, 0, st>>>(M, c.user, c.B, c.loss_slot, make_theta(&M, c.B, c.ks),
+  k_grads_owned<<<ss_grid(c.B), SS_WARPS * 32, 0, st>>>(M, c.user, c.B, c.loss_slot, make_theta(&M, c.B, c.ks, c.sm_reserve),
                                                        tc ? fvx_tc_np(M.de) : 0, tc ? fvx_w_pitch(&M) : 0, c.ws->S,
                                                        c.ws->run_id, c.ws->RU, (long long)c.ws->max_runs, M.sync + 1,
                                                        c.uniq ? 1 : 0, c.ws->WU, c.ws->loss_part);
@@ -594,9 +714,9 @@ static int sh_p6(const ShCtx& c, cudaStream_t st) {
   const bool tc = M.D > 0 && M.use_tensor_cores;
   if (M.D > 0) {
     if (c.uniq) {
-      if (int rc = fvx_launch_grad_E_tc(&M, M.items.list, 2 * c.B, &parts, st, M.items.count)) return rc;
+      if (int rc = fvx_launch_grad_E_tc(&M, M.items.list, 2 * c.B, &parts, st, M.items.count, c.sm_reserve)) return rc;
     } else if (tc) {
-      if (int rc = fvx_launch_grad_E_tc(&M, M.cmap, 2 * c.B, &parts, st, M.sync + 1)) return rc;
+      if (int rc = fvx_launch_grad_E_tc(&M, M.cmap, 2 * c.B, &parts, st, M.sync + 1, c.sm_reserve)) return rc;
     } else {
       if (int rc = fvx_launch_grad_E(&M, M.cmap, 2 * c.B, &parts, st)) return rc;
     }
@@ -629,10 +749,36 @@ static int make_ctx(ShCtx* c, const FvxModel* m, const FvxShardWs* ws, const int
   c->m = m; c->ws = ws; c->user = user; c->pos = pos; c->neg = neg; c->B = B; c->loss_slot = loss_slot;
   c->uniq = sharded_uniq(m);
   c->ks = c->uniq ? uniq_ks_cap(m, B) : sharded_ks(m, B);
+  c->sm_reserve = 0;
   return 0;
 }
 
+// Timeline of fvx_bpr_step_sharded (diagnostics, declared in fvx.h): with tracing on, the step records a timing
+// event after every piece / collective on the stream it runs on.
+enum { ST_BEGIN = 0, ST_P1, ST_P2, ST_AR_WU, ST_P3, ST_P4, ST_AR_S, ST_P5, ST_AR_RU, ST_P7, ST_P6, ST_AR_DE, ST_END, ST_COUNT };
+static cudaEvent_t g_st_ev[ST_COUNT];
+static int g_st_on = 0;
+#define STRACE(i, stream) do { if (g_st_on) cudaEventRecord(g_st_ev[i], (stream)); } while (0)
+
 extern "C" {
+
+int fvx_debug_trace_sharded(int on) {
+  if (on && !g_st_ev[0])
+    for (int i = 0; i < ST_COUNT; ++i)
+      if (cudaEventCreate(&g_st_ev[i]) != cudaSuccess) return -3;
+  g_st_on = on ? 1 : 0;
+  return 0;
+}
+int fvx_debug_trace_sharded_read(float* us_host) {   // [13]; synchronises
+  if (!g_st_ev[0]) return -2;
+  if (cudaEventSynchronize(g_st_ev[ST_END]) != cudaSuccess) return -3;
+  for (int i = 0; i < ST_COUNT; ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, g_st_ev[ST_BEGIN], g_st_ev[i]) != cudaSuccess) { cudaGetLastError(); ms = -1e-3f; }
+    us_host[i] = ms * 1e3f;
+  }
+  return 0;
+}
 
 int fvx_bpr_step_sharded_phase(const FvxModel* model, const FvxShardWs* ws, const int32_t* user, const int32_t* pos,
                                const int32_t* neg, int32_t B, int32_t loss_slot, int32_t phase, fvx_stream_t stream) {
@@ -641,8 +787,11 @@ int fvx_bpr_step_sharded_phase(const FvxModel* model, const FvxShardWs* ws, cons
   cudaStream_t st = fvx_cu(stream);
   switch (phase) {
     case 0:
-      if (int rc = sh_p1(c, st)) return rc;
-      return sh_p2(c, st);
+      if (int rc = sh_p1a(c, st)) return rc;
+      if (int rc = sh_p1b(c, st)) return rc;
+      if (int rc = sh_p2u(c, st)) return rc;
+      if (int rc = sh_clear_ru(c, st)) return rc;
+      return sh_p2i(c, st);
     case 1:
       if (int rc = sh_p3(c, st)) return rc;
       return sh_p4(c, st);
@@ -664,29 +813,63 @@ int fvx_bpr_step_sharded(const FvxModel* model, const FvxShardWs* ws, FvxComm* c
   FVX_CHECK_ARG(comm != nullptr, "fvx_bpr_step_sharded: null communicator");
   const FvxModel& M = *model;
   cudaStream_t st = fvx_cu(stream), sd = comm->side;
-  const size_t n_ru = (size_t)ws->max_runs * M.users.stride;
-  if (int rc = sh_p1(c, st)) return rc;
+  {
+    static int serial = -1;            // FVX_SH_SERIAL=1: every piece and collective on the caller's stream (measurements)
+    if (serial < 0) { const char* e_ = getenv("FVX_SH_SERIAL"); serial = (e_ && atoi(e_) == 1) ? 1 : 0; }
+    if (serial) sd = st;
+  }
+  const size_t seg = (size_t)ws->run_cap * M.users.stride;      // one owner's segment of WU / RU
+  FVX_CHECK_ARG(ws->owners == comm->world, "fvx_bpr_step_sharded: FvxShardWs.owners %d != communicator size %d", ws->owners,
+                comm->world);
+  {
+    // the persistent tensor-core kernels leave a few SMs to the NCCL kernels that run beside them (FVX_COMM_SMS,
+    // default 8): without them an all-reduce waits for the last CTA of the projection / grad_E to retire
+    static int reserve = -1;
+    if (reserve < 0) { const char* e_ = getenv("FVX_COMM_SMS"); reserve = e_ ? atoi(e_) : 8; if (reserve < 0 || reserve > 64) reserve = 8; }
+    c.sm_reserve = comm->world > 1 ? reserve : 0;
+  }
+  STRACE(ST_BEGIN, st);
+  // main: item claims, then the little the user side needs before its exchange can start - run slots, catch-up of
+  // the OWNED users of the batch, their rows packed into this rank's segment of WU (~30 us; beside the projection
+  // the same kernels took 100 us and the projection 60 us longer)
+  if (int rc = sh_p1a(c, st)) return rc;
+  if (int rc = sh_p1b(c, st)) return rc;
+  STRACE(ST_P1, st);
+  if (int rc = sh_p2u(c, st)) return rc;
+  STRACE(ST_P2, st);
   cudaEventRecord(comm->ev[0], st);
   cudaStreamWaitEvent(sd, comm->ev[0], 0);
-  // side: the owned users are brought up to date and published while the projection runs
-  if (int rc = sh_p2(c, sd)) return rc;
-  if (int rc = fvx_comm_allreduce(comm, 1, ws->WU, n_ru, sd)) return rc;
+  // side, beside the projection: the fresh user rows travel; the listed item rows are caught up
+  if (int rc = fvx_comm_allgather(comm, 1, ws->WU, seg, sd)) return rc;
+  STRACE(ST_AR_WU, sd);
+  if (int rc = sh_clear_ru(c, sd)) return rc;
+  if (int rc = sh_p2i(c, sd)) return rc;
   cudaEventRecord(comm->ev[1], sd);
   if (int rc = sh_p3(c, st)) return rc;
+  STRACE(ST_P3, st);
   cudaStreamWaitEvent(st, comm->ev[1], 0);
   if (int rc = sh_p4(c, st)) return rc;
+  STRACE(ST_P4, st);
   if (int rc = fvx_comm_allreduce(comm, 0, ws->S, 2 * (size_t)B, st)) return rc;
+  STRACE(ST_AR_S, st);
   if (int rc = sh_p5(c, st)) return rc;
+  STRACE(ST_P5, st);
   cudaEventRecord(comm->ev[2], st);
   cudaStreamWaitEvent(sd, comm->ev[2], 0);
   // side: the user-row gradient shares travel, and the owners take theirs, while grad_E runs
-  if (int rc = fvx_comm_allreduce(comm, 1, ws->RU, n_ru, sd)) return rc;
+  if (int rc = fvx_comm_reducescatter(comm, 1, ws->RU, seg, sd)) return rc;
+  STRACE(ST_AR_RU, sd);
   if (int rc = sh_p7(c, sd)) return rc;
+  STRACE(ST_P7, sd);
   cudaEventRecord(comm->ev[3], sd);
   if (int rc = sh_p6(c, st)) return rc;
+  STRACE(ST_P6, st);
   if (int rc = fvx_comm_allreduce(comm, 0, ws->dE, (size_t)M.D * M.de + 4, st)) return rc;
+  STRACE(ST_AR_DE, st);
   cudaStreamWaitEvent(st, comm->ev[3], 0);
-  return sh_p8(c, st);
+  if (int rc = sh_p8(c, st)) return rc;
+  STRACE(ST_END, st);
+  return 0;
 }
 
 }  // extern "C"

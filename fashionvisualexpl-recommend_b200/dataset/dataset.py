@@ -227,6 +227,16 @@ class DataLoader(object):
         With the device sampler the batches are views into two alternating epoch buffers: a
         batch stays valid until the epoch after the next one is generated (``reuse=False``
         allocates a fresh buffer per epoch for callers that keep every batch)."""
+        B = self.params.batch_size
+        for bufs, n in self.next_batch_run(device, reuse=reuse):
+            for s in range(n):
+                yield tuple(x[s * B:(s + 1) * B] for x in bufs)
+
+    def next_batch_run(self, device="cuda:0", reuse=True):
+        """Iterator over ``((user, pos, neg), n)``: index tensors holding ``n`` consecutive batches back to back
+        (batch s = elements [s*B, (s+1)*B)) - what ``Engine.steps`` replays as CUDA graphs.  The same triples, in
+        the same order, as ``next_triple_batch``: ``(N // B) * B * epochs`` in total, batches cut across epoch
+        boundaries (dataset.py:89-91,109-110,116-122)."""
         import torch
         B = self.params.batch_size
         total = self._total_triples()
@@ -234,8 +244,8 @@ class DataLoader(object):
             u, p, n = self.all_triple_batches()
             dv = torch.device(device)
             u, p, n = (torch.from_numpy(a.astype(np.int32)).to(dv) for a in (u, p, n))
-            for s in range(0, total, B):
-                yield u[s:s + B], p[s:s + B], n[s:s + B]
+            if total:
+                yield (u, p, n), total // B
             return
         if self.sampler != "device":
             raise ValueError("unknown sampler %r (host_ref | device)" % self.sampler)
@@ -257,9 +267,8 @@ class DataLoader(object):
             self.device_epoch(epoch, device, out=tuple(c[carry:carry + N] for c in cur))
             epoch += 1
             n_av = carry + N
-            s = 0
-            while s + B <= n_av and done < total:
-                yield tuple(x[s:s + B] for x in cur)
-                s += B
-                done += B
-            prev, prev_s, carry = cur, s, n_av - s
+            n = min(n_av // B, (total - done) // B)
+            if n > 0:
+                yield cur, n
+            done += n * B
+            prev, prev_s, carry = cur, n * B, n_av - n * B

@@ -146,23 +146,29 @@ class ShardedStep:
 
     def __init__(self, engines, group, max_runs=None):
         """``max_runs``: upper bound of the number of runs of equal users in a batch.  Default: the batch size
-        (the hard bound).  The user rows (WU) and user-gradient shares (RU) exchanged per step have that many
-        rows, so a tight bound - B // (shortest train list) + 2 is exact for batches of the reference's
-        sampler - saves NVLink bytes; a batch with more runs poisons that step's loss with NaN on every rank."""
+        (the hard bound).  The user rows (WU) and user-gradient shares (RU) exchanged per step are laid out in one
+        segment per owner of ``run_cap`` = max_runs / R (+ 15 % + 64 for the spread of the owners' shares) rows, so
+        a tight bound - B // (shortest train list) + 2 is exact for batches of the reference's sampler - saves
+        NVLink bytes; a batch in which an owner has more runs poisons that step's loss with NaN on every rank."""
         self.engines, self.group = list(engines), group
         e = self.engines[0]
-        B = e.max_batch
+        B, R = e.max_batch, group.world
+        if R > 8:
+            raise _lib.FvxError("the sharded step supports up to 8 ranks")
         self.max_runs = int(max_runs) if max_runs else B
+        self.run_cap = self.max_runs if R == 1 else min(self.max_runs, int(1.15 * self.max_runs / R) + 64)
+        rows = R * self.run_cap
+        per = e.U_rows // R
         self.ws = []
         for e in self.engines:
             dv = e.device
             f32, i32 = dict(dtype=torch.float32, device=dv), dict(dtype=torch.int32, device=dv)
             t = {"S": torch.zeros(2 * B, **f32), "run_id": torch.zeros(B, **i32),
-                 "run_scratch": torch.zeros(B // 4096 + 2, **i32), "WU": torch.zeros(self.max_runs, e.Su, **f32),
-                 "RU": torch.zeros(self.max_runs, e.Su, **f32), "dE": torch.zeros(e.D * e.de + 4, **f32),
+                 "run_scratch": torch.zeros(8 * (B // 1024 + 2), **i32), "WU": torch.zeros(rows, e.Su, **f32),
+                 "RU": torch.zeros(rows, e.Su, **f32), "dE": torch.zeros(e.D * e.de + 4, **f32),
                  "loss_part": torch.zeros(1, dtype=torch.float64, device=dv)}
             w = _lib.FvxShardWs(ptr(t["S"]), ptr(t["run_id"]), ptr(t["run_scratch"]), ptr(t["WU"]), ptr(t["RU"]),
-                                ptr(t["dE"]), ptr(t["loss_part"]), self.max_runs, 0)
+                                ptr(t["dE"]), ptr(t["loss_part"]), rows, self.run_cap, R, max(per, 1))
             t["struct"] = w
             self.ws.append(t)
         self._comm = group.comm(self.engines[0].device) if isinstance(group, DistGroup) else None
@@ -175,13 +181,19 @@ class ShardedStep:
             call("fvx_bpr_step_sharded", C.byref(e.struct()), C.byref(w["struct"]), self._comm, ptr(user), ptr(pos),
                  ptr(neg), B, loss_slot, stream_ptr())
             return
-        # emulated ranks: the step cut at its collectives, the sums done here
-        sums = (("WU",), ("S",), ("RU", "dE"), ())
+        # emulated ranks: the step cut at its collectives, which are done here
+        sums = ((), ("S",), ("RU", "dE"), ())
         for phase in range(4):
             for e, w in zip(self.engines, self.ws):
                 call("fvx_bpr_step_sharded_phase", C.byref(e.struct()), C.byref(w["struct"]), ptr(user), ptr(pos),
                      ptr(neg), B, loss_slot, phase, stream_ptr())
-            for name in sums[phase]:
+            if phase == 0:                       # all-gather: every rank receives every owner's segment of WU
+                c = self.run_cap
+                segs = [w["WU"][r * c:(r + 1) * c].clone() for r, w in enumerate(self.ws)]
+                for w in self.ws:
+                    for r, seg in enumerate(segs):
+                        w["WU"][r * c:(r + 1) * c].copy_(seg)
+            for name in sums[phase]:             # (the sum of RU over the ranks contains every owner's reduced segment)
                 self.group.all_reduce([w[name] for w in self.ws])
 
     def take_loss(self, slot=0):
@@ -198,7 +210,8 @@ class ShardedStep:
             for e in self.engines:
                 e.loss_t[slot] = 0
         if any(v != v for v in vals):
-            raise _lib.FvxError("a batch had more runs of equal users than max_runs=%d" % self.max_runs)
+            raise _lib.FvxError("a batch had more runs of equal users per owner than run_cap=%d (max_runs=%d)"
+                                % (self.run_cap, self.max_runs))
         return vals[0]
 
     def sync_users(self):

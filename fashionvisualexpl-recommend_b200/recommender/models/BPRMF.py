@@ -7,8 +7,9 @@ embed_k, learning_rate, reg, evaluator, directory_parameters, optimizer``; metho
 (:87-125) and ``train()`` (:127-192).  Every numeric operation runs in libfvx.so.
 
 Extra knobs read from ``params`` when present (all optional, defaults keep the
-reference behaviour): ``adam_mode`` (deferred | dense | lazy), ``sampler``
-(host_ref | device), ``device``, ``sync_loss``.
+reference behaviour): ``adam_mode`` (auto | deferred | dense | lazy; auto = dense for small batches on small tables), ``sampler``
+(host_ref | device), ``device``, ``sync_loss``, ``tensor_cores`` (default on), ``graph_steps``
+(default on: the steps of an epoch are replayed as CUDA graphs of 8, ``Engine.steps``).
 """
 from __future__ import annotations
 
@@ -58,9 +59,11 @@ class BPRMF(RecommenderModel):
     def _build_engine(self, d=0, D=0, features=None):
         p = self.params
         self.engine = Engine(self.num_users, self.num_items, self.embed_k, d=d, D=D, lr=p.lr, reg=p.reg,
-                             adam_mode=getattr(p, "adam_mode", "deferred"), max_batch=p.batch_size,
+                             adam_mode=getattr(p, "adam_mode", "auto"), max_batch=p.batch_size,
                              device=self.device, seed=getattr(p, "seed", 0),
-                             use_tensor_cores=bool(getattr(p, "tensor_cores", False)))
+                             # tcgen05 projections / evaluation sweep wherever the geometry is eligible (the
+                             # engine falls back to the exact fp32 CUDA-core kernels otherwise)
+                             use_tensor_cores=bool(getattr(p, "tensor_cores", True)))
         if D:
             self.engine.set_features(features)
 
@@ -93,12 +96,13 @@ class BPRMF(RecommenderModel):
         use it - it goes through the fused top-k sweep."""
         return DeviceArray(self.engine.predict_all())
 
-    def train_step(self, batch, sync=True):
+    def train_step(self, batch, sync=True, loss_slot=0):
         """One optimiser step on ``(user, pos, neg)``; returns the batch loss as a float
-        like the reference (BPRMF.py:125) - ``sync=False`` leaves it on the device."""
+        like the reference (BPRMF.py:125) - ``sync=False`` leaves it on the device, in
+        ``engine.loss_t[loss_slot]`` (``engine.take_loss``)."""
         user, pos, neg = (self._idx(a) for a in batch)
-        self.engine.step(user, pos, neg, loss_slot=0)
-        return self.engine.read_loss(0) if sync else None
+        self.engine.step(user, pos, neg, loss_slot=loss_slot)
+        return self.engine.read_loss(loss_slot) if sync else None
 
     # ---- checkpoints: tensors + optimiser state (the reference only ever saves) ----------
     def state_dict(self):
@@ -150,25 +154,36 @@ class BPRMF(RecommenderModel):
         os.makedirs(wdir, exist_ok=True)
         start_ep = time()
         print('Start training...')
-        for batch in self.data.next_triple_batch(self.device):
-            steps += 1
-            self.engine.step(*batch, loss_slot=0)
-            if sync_loss:
-                self.engine.loss_t[0].item()            # the reference syncs every step (:125)
-            if steps == steps_per_epoch:                  # epoch is over (:148)
-                loss = self.engine.read_loss(0)
-                epoch_text = 'Epoch {0}/{1} \tLoss: {2:.3f}'.format(it, p.epochs, loss / steps)
-                epoch_print = self.evaluator.eval(it, results, epoch_text, start_ep)
-                for metric in max_metrics.keys():
-                    if max_metrics[metric] <= results[it][metric + '_v']:
-                        max_metrics[metric] = results[it][metric + '_v']
-                        if metric == p.best_metric:
-                            best_epoch, best_state, best_epoch_print = it, self.state_dict(), epoch_print
-                if (it % self.verbose == 0 or it == 1) and self.verbose != -1:
-                    self.save_weights(f'{wdir}/weights-{it}-{self.directory_parameters}')
-                start_ep = time()
-                it += 1
-                steps = 0
+        graph = bool(getattr(p, "graph_steps", True)) and not sync_loss
+        for bufs, n_batches in self.data.next_batch_run(self.device):
+            first = 0
+            while first < n_batches:
+                # the steps up to the end of the epoch in one go (CUDA-graph replay), or one at a time when the
+                # reference's per-step loss synchronisation is asked for (:125)
+                n = min(n_batches - first, steps_per_epoch - steps) if graph else 1
+                if graph:
+                    self.engine.steps(bufs[0], bufs[1], bufs[2], first, n, p.batch_size, loss_slot=0)
+                else:
+                    B = p.batch_size
+                    self.engine.step(*(x[first * B:(first + 1) * B] for x in bufs), loss_slot=0)
+                    if sync_loss:
+                        self.engine.loss_t[0].item()
+                first += n
+                steps += n
+                if steps == steps_per_epoch:                  # epoch is over (:148)
+                    loss = self.engine.read_loss(0)
+                    epoch_text = 'Epoch {0}/{1} \tLoss: {2:.3f}'.format(it, p.epochs, loss / steps)
+                    epoch_print = self.evaluator.eval(it, results, epoch_text, start_ep)
+                    for metric in max_metrics.keys():
+                        if max_metrics[metric] <= results[it][metric + '_v']:
+                            max_metrics[metric] = results[it][metric + '_v']
+                            if metric == p.best_metric:
+                                best_epoch, best_state, best_epoch_print = it, self.state_dict(), epoch_print
+                    if (it % self.verbose == 0 or it == 1) and self.verbose != -1:
+                        self.save_weights(f'{wdir}/weights-{it}-{self.directory_parameters}')
+                    start_ep = time()
+                    it += 1
+                    steps = 0
         print('Training end...')
         self.evaluator.store_recommendation(path=f'{rdir}/recs-{it - 1}-{self.directory_parameters}.tsv')
         save_obj(results, f'{rdir}/results-metrics-{self.directory_parameters}')

@@ -8,7 +8,7 @@ Deviations, all documented in DESIGN.md: ``--validation`` parses real booleans (
 ``type=bool`` makes any non-empty string true, :29); ``--gpu`` selects the CUDA device (the
 reference's default -1 means CPU, which does not exist here, so the default is 0) and ``--rec``
 defaults to ``vbpr``; new optional flags ``--adam_mode``, ``--sampler``, ``--seed``,
-``--tensor_cores``, ``--data_root``, ``--results_root``.
+``--tensor_cores`` (default on), ``--graph_steps`` (default on), ``--data_root``, ``--results_root``.
 """
 import argparse
 
@@ -41,10 +41,11 @@ REFERENCE_FLAGS = (
     ("reg", float, 0, {}),
 )
 ENGINE_FLAGS = (
-    ("adam_mode", None, "deferred", {"choices": ["deferred", "dense", "lazy"]}),
+    ("adam_mode", None, "auto", {"choices": ["auto", "deferred", "dense", "lazy"]}),
     ("sampler", None, "host_ref", {"choices": ["host_ref", "device"]}),
     ("seed", int, 0, {}),
-    ("tensor_cores", _flag, False, {}),
+    ("tensor_cores", _flag, True, {}),
+    ("graph_steps", _flag, True, {}),
     ("data_root", None, None, {}),
     ("results_root", None, None, {}),
 )

@@ -194,27 +194,33 @@ int fvx_bpr_step_timed(const FvxModel* model, const int32_t* user, const int32_t
  * owned in contiguous blocks too (user_lo, user_cnt): the owner keeps a user's Adam state and applies its
  * updates; E is replicated.  Every rank sees the same batch (global ids).  x_uij = s_ui - s_uj is linear in
  * the item-side terms, so a rank scores the (triple, side) slots whose item it owns, and the ranks exchange
- * four buffers per step, all by sum (a buffer holds zeros where a rank has nothing to say):
- *   WU [max_runs, users.stride]  the up-to-date rows of the batch's users, indexed by RUN of equal users (the
- *                                reference's sampler emits runs of one user, dataset.py:96-99); written by
- *                                the owner of the user
- *   S  [2B]                      partial scores of the slots [pos(B) | neg(B)]
- *   RU [max_runs, users.stride]  user-row gradient shares by run; the owner adds its runs into its accumulators
+ * four buffers per step:
+ *   WU [owners * run_cap, users.stride]  the up-to-date rows of the batch's users, one row per RUN of equal users
+ *                                (the reference's sampler emits runs of one user, dataset.py:96-99), grouped in one
+ *                                segment of run_cap rows per OWNER of the user: all-gather (each owner publishes
+ *                                its segment)
+ *   S  [2B]                      partial scores of the slots [pos(B) | neg(B)], zero where a rank owns nothing:
+ *                                all-reduce (sum)
+ *   RU [owners * run_cap, users.stride]  user-row gradient shares in the same layout: reduce-scatter (each owner
+ *                                receives the sum of its segment and adds its runs into its accumulators)
  *   dE [D*de + 4]                dense gradient of E_ext, then the loss share (two floats, hi + lo) and the
- *                                run-overflow flag
+ *                                run-overflow flag: all-reduce (sum)
  * Work per rank: 2B/R slots, B/R user rows - nothing grows with the number of ranks except the scans of the
- * batch indices.  No item row ever leaves its owner.  run_id[b] = index of the run triple b belongs to; a batch
- * with more than max_runs runs poisons the step's loss with NaN on every rank (nothing fails silently). */
+ * batch indices.  No item row ever leaves its owner.  run_id[b] = row of the run triple b belongs to (fvx_run_slots:
+ * owner * run_cap + index of the run among that owner's runs, identical on every rank); a batch in which one owner
+ * has more than run_cap runs poisons the step's loss with NaN on every rank (nothing fails silently). */
 typedef struct FvxShardWs {
   float* S;
   int32_t* run_id;       /* [max_batch] */
-  int32_t* run_scratch;  /* [max_batch / 4096 + 2] */
+  int32_t* run_scratch;  /* [8 * (max_batch / 1024 + 2)] */
   float* WU;
   float* RU;
   float* dE;
   double* loss_part;     /* [1] this rank's loss share of the step in flight */
-  int32_t max_runs;
-  int32_t _pad;
+  int32_t max_runs;      /* rows of WU / RU = owners * run_cap */
+  int32_t run_cap;       /* rows per owner segment */
+  int32_t owners;        /* number of ranks (<= 8) */
+  int32_t users_per_owner;   /* block size of the user ownership: owner(u) = u / users_per_owner */
 } FvxShardWs;
 
 /* Communicators of the sharded step: two NCCL communicators over the same ranks, one for the collectives on
@@ -231,22 +237,27 @@ int fvx_comm_destroy(FvxComm* comm);
 /* all-reduce (sum) of n floats in place on the caller's stream, e.g. to assemble per-rank statistics */
 int fvx_comm_all_reduce_f32(FvxComm* comm, float* buf, int64_t n, fvx_stream_t stream);
 
-/* run_id of a batch (see above) in two small launches; scratch: >= n / 4096 + 2 int32. */
+/* run_id[b] = index of the run of equal users triple b belongs to, counted from 0 in batch order; two small
+ * launches; scratch: >= n / 4096 + 2 int32. */
 int fvx_run_ids(const int32_t* user, int64_t n, int32_t* run_id, int32_t* scratch, fvx_stream_t stream);
+/* run_slot[b] = owner * cap + (index of b's run among the runs of that owner), owner = user / users_per_owner
+ * (clamped to owners - 1); 0x7fffffff when the index reaches cap.  owners <= 8; scratch: >= 8 * (n / 1024 + 2) int32. */
+int fvx_run_slots(const int32_t* user, int64_t n, int32_t users_per_owner, int32_t owners, int32_t cap,
+                  int32_t* run_slot, int32_t* scratch, fvx_stream_t stream);
 
-/* One optimiser step of the sharded model: ONE call per rank per step; the four all-reduces are issued inside
+/* One optimiser step of the sharded model: ONE call per rank per step; the four collectives are issued inside
  * (NCCL), WU and RU on a side stream.  The batch loss lands in model->loss[loss_slot] on EVERY rank. */
 int fvx_bpr_step_sharded(const FvxModel* model, const FvxShardWs* ws, FvxComm* comm, const int32_t* user,
                          const int32_t* pos, const int32_t* neg, int32_t B, int32_t loss_slot, fvx_stream_t stream);
 
 /* The same step cut at its collectives, everything on `stream`, for callers that perform the sums themselves
  * (tests that emulate R ranks inside one process; other transports):
- *   phase 0  run ids, rows of the owned slots, catch-up of the owned users, their fresh rows -> WU
- *            -- sum WU over the ranks --
+ *   phase 0  run slots, rows of the owned slots, catch-up of the owned users, their fresh rows -> own segment of WU
+ *            -- every rank receives every owner's segment of WU --
  *   phase 1  projection of the distinct owned rows, partial scores -> S
  *            -- sum S --
  *   phase 2  gradients of the owned slots (item rows, RU, backward coefficients), dE, loss share -> dE
- *            -- sum RU, sum dE --
+ *            -- sum RU (at least each owner's segment), sum dE --
  *   phase 3  RU rows of the owned users -> their accumulators; Adam on E; loss; step += 1               */
 int fvx_bpr_step_sharded_phase(const FvxModel* model, const FvxShardWs* ws, const int32_t* user, const int32_t* pos,
                                const int32_t* neg, int32_t B, int32_t loss_slot, int32_t phase, fvx_stream_t stream);
@@ -360,6 +371,10 @@ int fvx_debug_set_dedup(int on);
  * grad_E, upd0, upd1, end) relative to the first one and synchronises. */
 int fvx_debug_trace(int on);
 int fvx_debug_trace_read(float* us_host);
+/* The same for fvx_bpr_step_sharded: 13 times (begin, piece 1, piece 2 [side], all-reduce WU [side], piece 3, piece 4,
+ * all-reduce S, piece 5, all-reduce RU [side], piece 7 [side], piece 6, all-reduce dE, end). */
+int fvx_debug_trace_sharded(int on);
+int fvx_debug_trace_sharded_read(float* us_host);
 
 #ifdef __cplusplus
 }

@@ -1,53 +1,67 @@
-"""Profiling aid: per-phase device time of the item-sharded step (torchrun, one rank per GPU)."""
+"""Profiling aid: timeline of fvx_bpr_step_sharded (torchrun, one rank per GPU): where the pieces and the four
+all-reduces of one step start and end on the two streams (fvx_debug_trace_sharded), averaged over steps.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29520 \
+        scripts/sharded_phases.py [--config weak|c3] [--batch 65536]
+"""
 import argparse, ctypes as C, os, sys
 import numpy as np
 import torch
 import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from fvx import parallel, synth
-from fvx._lib import call, ptr, stream_ptr
+from fvx import _lib, parallel, synth
 from fvx.dataset.dataset import DataLoader
-from fvx.engine import Engine
 
-ap = argparse.ArgumentParser(); ap.add_argument("--batch", type=int, default=65536); a = ap.parse_args()
+ap = argparse.ArgumentParser()
+ap.add_argument("--config", default="weak", choices=["weak", "c3"])
+ap.add_argument("--batch", type=int, default=65536)
+ap.add_argument("--steps", type=int, default=20)
+a = ap.parse_args()
 world, rank, local = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
 dev = torch.device("cuda", local); torch.cuda.set_device(dev)
 dist.init_process_group("nccl", device_id=dev)
-U, I, K, d, D, B = 40000 * world, 100000, 64, 20, 2048, a.batch * world
+if a.config == "weak":
+    U, I, B = 40000 * world, 100000 * world, a.batch * world
+else:
+    U, I, B = 1000000, 500000, 524288
+K, d, D = 64, 20, 2048
 inter = synth.make_interactions(U, I, seed=1234)
 p = argparse.Namespace(dataset="synthetic", batch_size=B, epochs=10 ** 6, sampler="device", seed=0)
 data = DataLoader(p, interactions=inter)
-lo, cnt = parallel.shard_bounds(I, world, rank)
-e = Engine(U, I, K, d=d, D=D, max_batch=B, device=str(dev), use_tensor_cores=True, item_lo=lo, item_cnt=cnt)
-g = torch.Generator(device=dev).manual_seed(1)
-e.set_features(torch.rand(cnt, D, device=dev, generator=g), keep_fp32=False)
-min_len = int(np.diff(inter.row_ptr).min())
-ss = parallel.ShardedStep([e], parallel.DistGroup(), max_runs=B // max(min_len, 1) + 2)
+e = parallel.sharded_engine(world, rank, U, I, K, d=d, D=D, max_batch=B, device=str(dev), use_tensor_cores=True)
+g = torch.Generator(device=dev).manual_seed(1 + rank)
+e.set_features(torch.rand(e.Ic, D, device=dev, generator=g), keep_fp32=False)
+lens = np.diff(inter.row_ptr)
+max_runs = min(B // max(int(lens.min()), 1) + 2, int(1.3 * B / float(lens.mean())) + 1024)
+grp = parallel.DistGroup()
+ss = parallel.ShardedStep([e], grp, max_runs=max_runs)
 batches = data.next_triple_batch(str(dev))
 for _ in range(5):
     ss.step(*next(batches))
 torch.cuda.synchronize(); dist.barrier()
-names = ["run_ids", "A", "ar_S", "B1", "ar_RU", "B2", "ar_dE", "C"]
-acc = {n: 0.0 for n in names}
-N = 10
-for _ in range(N):
-    user, pos, neg = next(batches)
-    Bq = user.numel()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
-    S, RU, dE = ss.S[0], ss.RU[0], ss.dE[0]
-    ev[0].record()
-    rid = parallel.run_ids(user); ev[1].record()
-    call("fvx_bpr_step_sharded_a", C.byref(e.struct()), ptr(user), ptr(pos), ptr(neg), Bq, ptr(S), stream_ptr()); ev[2].record()
-    dist.all_reduce(S); ev[3].record()
-    call("fvx_bpr_step_sharded_b1", C.byref(e.struct()), ptr(user), Bq, ptr(S), ptr(rid), ptr(RU), RU.shape[0], 0, stream_ptr()); ev[4].record()
-    dist.all_reduce(RU); ev[5].record()
-    call("fvx_bpr_step_sharded_b2", C.byref(e.struct()), Bq, ptr(dE), stream_ptr()); ev[6].record()
-    dist.all_reduce(dE); ev[7].record()
-    call("fvx_bpr_step_sharded_c", C.byref(e.struct()), ptr(user), Bq, ptr(rid), ptr(RU), RU.shape[0], ptr(dE), 0 if rank == 0 else -1, stream_ptr()); ev[8].record()
-    torch.cuda.synchronize()
-    for i, n in enumerate(names):
-        acc[n] += ev[i].elapsed_time(ev[i + 1]) / N
+lib = _lib.load()
+names = ["begin", "p1 run ids+rows+claims", "p2 user catch-up+pack [side]", "all-gather WU [side]", "p3 owned list+projection",
+         "p4 partial scores", "all-reduce S", "p5 grads+planes", "reduce-scatter RU [side]", "p7 scatter runs [side]",
+         "p6 grad_E+pack", "all-reduce dE", "p8 update / end"]
+acc = np.zeros(len(names))
+lib.fvx_debug_trace_sharded(1)
+out = (C.c_float * len(names))()
+t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+for _ in range(a.steps):
+    ss.step(*next(batches))
+    assert lib.fvx_debug_trace_sharded_read(out) == 0
+    acc += np.array(list(out)) / a.steps
+lib.fvx_debug_trace_sharded(0)
+dist.barrier()
+t0.record()
+for _ in range(a.steps):
+    ss.step(*next(batches))
+t1.record(); torch.cuda.synchronize()
 if rank == 0:
-    print("world", world, "global batch", B, "RU rows", ss.RU[0].shape, "phases ms:", {k: round(v, 4) for k, v in acc.items()},
-          "sum", round(sum(acc.values()), 4))
+    print("world %d, %d users x %d items, global batch %d, exchanged user rows %d x %d floats (%.1f MB per buffer)"
+          % (world, U, I, B, max_runs, e.Su, max_runs * e.Su * 4 / 1e6))
+    for n, v in zip(names, acc):
+        print("%-32s %8.1f us" % (n, v))
+    print("untraced: %.1f us per step" % (t0.elapsed_time(t1) / a.steps * 1e3))
+grp.close()
 dist.destroy_process_group()

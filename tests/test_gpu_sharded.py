@@ -144,3 +144,31 @@ def test_run_ids_kernel_equals_torch(n):
     scratch = torch.zeros(n // 4096 + 2, dtype=torch.int32, device="cuda")
     _lib.call("fvx_run_ids", _lib.ptr(user), n, _lib.ptr(out), _lib.ptr(scratch), _lib.stream_ptr())
     assert torch.equal(out, run_ids(user))
+
+
+@pytest.mark.parametrize("n,R,cap", [(1, 1, 4), (300, 2, 40), (4097, 3, 400), (70001, 8, 1200), (262144, 8, 3000), (5000, 4, 20)])
+def test_run_slots_kernel_equals_numpy(n, R, cap):
+    """fvx_run_slots: run slot = owner * cap + index of the run among its owner's runs (0x7fffffff past cap)."""
+    from fvx import _lib
+    g = torch.Generator().manual_seed(n + R)
+    U = 997
+    per = (U + R - 1) // R
+    lens = torch.randint(1, 9, (n,), generator=g)
+    user = torch.repeat_interleave(torch.randint(0, U, (n,), generator=g), lens)[:n].to(torch.int32)
+    u = user.numpy()
+    start = np.ones(n, dtype=bool)
+    start[1:] = u[1:] != u[:-1]
+    owner = np.minimum(u // per, R - 1)
+    want = np.zeros(n, dtype=np.int64)
+    cnt = np.zeros(R, dtype=np.int64)
+    cur = 0
+    for b in range(n):
+        if start[b]:
+            o = owner[b]
+            cur = o * cap + cnt[o] if cnt[o] < cap else 0x7fffffff
+            cnt[o] += 1
+        want[b] = cur
+    out = torch.full((n,), -7, dtype=torch.int32, device="cuda")
+    scratch = torch.zeros(8 * (n // 1024 + 2), dtype=torch.int32, device="cuda")
+    _lib.call("fvx_run_slots", _lib.ptr(user.cuda()), n, per, R, cap, _lib.ptr(out), _lib.ptr(scratch), _lib.stream_ptr())
+    assert np.array_equal(out.cpu().numpy().astype(np.int64), want)
