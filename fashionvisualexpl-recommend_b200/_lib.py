@@ -48,7 +48,7 @@ COMM_ID_BYTES = 256
 
 class FvxEvalWs(C.Structure):
     _fields_ = [("A", _p), ("Bm", _p), ("epsa", _p), ("nb", _p), ("stat", _p), ("cand", _p), ("ccount", _p),
-                ("flags", _p), ("thr", _p), ("gmax", _p), ("lists", C.c_int64), ("gmax_elems", C.c_int64),
+                ("flags", _p), ("thr", _p), ("gmax", _p), ("nbc", _p), ("lists", C.c_int64), ("gmax_elems", C.c_int64),
                 ("u_cap", C.c_int32), ("i_cap", C.c_int32), ("KP", C.c_int32), ("splits", C.c_int32),
                 ("cap", C.c_int32), ("n_ut", C.c_int32), ("a_stride", C.c_int32), ("_pad", C.c_int32)]
 
@@ -84,6 +84,8 @@ PROTOTYPES = {
     "fvx_score_topk_users": (C.c_int, [_MP, _p, _p, _i32, _p, _p, _i32, _p, _p, _p]),
     "fvx_eval_ws_query": (C.c_int, [_MP, _i32, C.POINTER(FvxEvalWs)]),
     "fvx_score_topk_tc": (C.c_int, [_MP, _p, _i32, _i32, _p, _p, _i32, _p, _p, C.POINTER(FvxEvalWs), _p]),
+    "fvx_score_topk_tc_bounds": (C.c_int, [_MP, _p, _i32, _i32, _p, _i32, C.POINTER(FvxEvalWs), _p]),
+    "fvx_score_topk_tc_select": (C.c_int, [_MP, _p, _i32, _i32, _p, _p, _i32, _p, _p, C.POINTER(FvxEvalWs), _p]),
     "fvx_score_pairs": (C.c_int, [_MP, _p, _p, _p, _i64, _p, _p]),
     "fvx_topk_merge": (C.c_int, [_p, _p, _i64, _i32, _i32, _p, _p, _p]),
     "fvx_split_planes": (C.c_int, [_p, _p, _i64, _i32, _p]),

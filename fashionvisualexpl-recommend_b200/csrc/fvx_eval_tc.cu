@@ -38,10 +38,11 @@
 //   accumulation),  beta0 = (2^-17 + KP * 2^-21) * max_i |bias_i|                (hi+lo residual).
 // One more K column holds eps_u = c*|a_u| (rounded up to bf16) on the user side and |b_i| (rounded up) on
 // the item side, so the UMMA itself delivers an UPPER bound s_ub = s_bf16 + eps_u * |b_i| >= s_fp32, and
-// s_ub - margin_u <= s_fp32 with margin_u = 2.001 * eps_u * max_i |b_i| + beta0.  If theta is a value that
-// at least kk = k + #train group maxima (of s_ub) reach, kk distinct items have a true score >=
-// theta - margin_u =: tau, so every item of the true top-kk has s_ub >= s >= tau: keeping {s_ub >= tau}
-// loses nothing, and the output equals the fp32 kernel's bit for bit.  A row whose list overflows, or whose
+// s_ub - 2.001 * eps_u * |b_i| - beta0 <= s_fp32.  A group's entry is max(s_ub over the group) - 2.001 * eps_u *
+// (largest |b_i| of the group) - beta0: a lower bound of the true score of the group's best column.  If tau is a
+// value that at least kk = k + #train group entries reach, kk distinct items have a true score >= tau, so every
+// item of the true top-kk has s_ub >= s >= tau: keeping {s_ub >= tau} loses nothing, and the output equals the
+// fp32 kernel's bit for bit.  A row whose list overflows, or whose
 // range has fewer than kk groups, is flagged and re-run through the fp32 kernel inside the same call.
 #include <cuda_bf16.h>
 #include <math_constants.h>
@@ -74,6 +75,13 @@ __device__ __forceinline__ unsigned long long tck_key(float s, int32_t id) {
   return ((unsigned long long)(~tck_mono(s)) << 32) | (uint32_t)id;
 }
 __device__ __forceinline__ float tck_score_of_hi(uint32_t hi) { return tck_unmono(~hi); }
+// float <-> int32 whose SIGNED order is the float order (atomicMax on int, all-reduce MAX on int32 tensors)
+__device__ __forceinline__ int32_t tck_enc(float s) {
+  const int32_t b = __float_as_int(s);
+  return b >= 0 ? b : (b ^ 0x7FFFFFFF);
+}
+__device__ __forceinline__ float tck_dec(int32_t e) { return __int_as_float(e >= 0 ? e : (e ^ 0x7FFFFFFF)); }
+#define TCK_ENC_NEG_INF ((int32_t)0x807FFFFF)
 __device__ __forceinline__ float max3(float a, float b, float c) {
   float r;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
@@ -88,7 +96,7 @@ __device__ __forceinline__ __nv_bfloat16 bf16_up(float x) {   // smallest bf16 >
 }
 
 __global__ void k_pack_users(FvxModel M, int u0, int u1, __nv_bfloat16* __restrict__ A, float* __restrict__ epsa,
-                             int KP, float c_rel) {
+                             int32_t* __restrict__ thr_g, int KP, float c_rel) {
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   const int kd = M.K + M.d;
@@ -105,7 +113,7 @@ __global__ void k_pack_users(FvxModel M, int u0, int u1, __nv_bfloat16* __restri
       else if (c == kd + 2) o = eh;                                     // multiplies |b_i|
       A[(size_t)(u - u0) * KP + c] = o;
     }
-    if (lane == 0) epsa[u - u0] = __bfloat162float(eh);
+    if (lane == 0) { epsa[u - u0] = __bfloat162float(eh); thr_g[u - u0] = TCK_ENC_NEG_INF; }
   }
 }
 
@@ -144,6 +152,21 @@ __global__ void k_pack_items(FvxModel M, const float* __restrict__ theta, __nv_b
   }
 }
 
+// nbc[c] = max of nb over the 32 items of chunk c (the rounding margin of a column group uses the largest item
+// norm IN the group, not the largest of the catalog: a few heavy items no longer loosen every row's bound)
+__global__ void k_chunk_nbmax(const float* __restrict__ nb, int item_cnt, float* __restrict__ nbc) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int n_chunks = (item_cnt + 31) >> 5;
+  for (int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < n_chunks; c += warps) {
+    const int i = c * 32 + lane;
+    float v = i < item_cnt ? nb[i] : 0.0f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (lane == 0) nbc[c] = v;
+  }
+}
+
 // ---------------------------------------------------------------------------------
 struct TckParams {
   int n_users;          // users in this call (rows of A)
@@ -159,14 +182,18 @@ struct TckParams {
   int k;
   int u0;
   int a_stride;         // the bounds sweep visits every a_stride-th tile of the range (1 or 2)
+  int do_a, do_b;       // which sweeps this launch runs: bounds (tau -> thr_g), candidates (tau <- thr_g)
   float beta_c;         // 2^-17 + KP * 2^-21: bias residual + fp32 accumulation, per unit of max|bias|
   const float* epsa;    // [n_users] eps_u as multiplied by the UMMA (bf16 value)
   const uint32_t* stat; // [0] max_i |b_i| as multiplied by the UMMA, [1] max |bias|  (float bits)
+  const float* nbc;     // [ceil(item_cnt / 32)] max |b_i| over each 32-item chunk
   const int64_t* mask_row_ptr;
   float* gmax;                // [grid][TCK_GMAX][n_ut * 128] group maxima of the unit in flight
   unsigned long long* cand;   // [lists * CAP]
   int32_t* ccount;            // [lists]
   int32_t* flags;             // [n_users]
+  int32_t* thr_g;             // [n_users] the row's bound tau (tck_enc: ordered like the float under SIGNED compare), the
+                              //   maximum over the item splits of the row - and, item-sharded, over the ranks
 };
 
 // list index of (row, split): rows of the full groups own one list, tail rows `splits` lists
@@ -272,7 +299,7 @@ k_topk_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       for (int w = blockIdx.x; w < n_units; w += gridDim.x, ++unit_i) {
         int grp, sp, t0, t1;
         tck_unit(P, w, grp, sp, t0, t1);
-        const int nt = t1 - t0, na = (nt + P.a_stride - 1) / P.a_stride;
+        const int nt = P.do_b ? t1 - t0 : 0, na = P.do_a ? (t1 - t0 + P.a_stride - 1) / P.a_stride : 0;
         mbar_wait(a_empty, (unit_i & 1) ^ 1);
         mbar_expect_tx(a_full, (uint32_t)P.n_ut * a_bytes);
         for (int ut = 0; ut < P.n_ut; ++ut)
@@ -315,7 +342,7 @@ k_topk_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       for (int w = blockIdx.x; w < n_units; w += gridDim.x, ++unit_i) {
         int grp, sp, t0, t1;
         tck_unit(P, w, grp, sp, t0, t1);
-        const int nt = t1 - t0, na = (nt + P.a_stride - 1) / P.a_stride;
+        const int nt = P.do_b ? t1 - t0 : 0, na = P.do_a ? (t1 - t0 + P.a_stride - 1) / P.a_stride : 0;
         mbar_wait(a_full, unit_i & 1);
         for (int seq = 0; seq < na + nt; ++seq) {
           const uint32_t acc = ut * 2 + buf;
@@ -344,28 +371,29 @@ k_topk_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const int rit = quad * 32 + lane;     // row in tile
     const int rows_u = P.n_ut * TCK_BM;   // rows of a unit
     const float beta0 = P.beta_c * __uint_as_float(P.stat[1]) + 1e-30f;
-    const float nbmax = __uint_as_float(P.stat[0]);
     float* gm = P.gmax + (size_t)blockIdx.x * TCK_GMAX * rows_u + ut * TCK_BM + rit;   // [group][rows_u], this row
     uint32_t buf = 0, buf_phase = 0;
     for (int w = blockIdx.x; w < n_units; w += gridDim.x) {
       int grp, sp, t0, t1;
       tck_unit(P, w, grp, sp, t0, t1);
-      const int nt = t1 - t0, na = (nt + P.a_stride - 1) / P.a_stride;
+      const int nt = P.do_b ? t1 - t0 : 0, na = P.do_a ? (t1 - t0 + P.a_stride - 1) / P.a_stride : 0;
       const int row = (grp * P.n_ut + ut) * TCK_BM + rit;
       const bool live = row < P.n_users;
       int kk = P.k;
-      float margin = 0.0f;
+      float eps2 = 0.0f;                        // 2.001 * eps_u: times the item norm = the width of the rounding band
       if (live) {
         const int gu = P.u0 + row;
         kk = P.k + (int)(P.mask_row_ptr[gu + 1] - P.mask_row_ptr[gu]);
-        margin = 2.001f * P.epsa[row] * nbmax + beta0;
+        eps2 = 2.001f * P.epsa[row];
       }
       // ---- sweep A: group maxima of s_ub -> gm[g * rows_u] ----
       const int nch = P.bn >> 5;                // 32-column chunks per tile
       const int gch = tck_gchunks(na * nch);    // chunks per group (power of two)
       const int gsh = 31 - __clz(gch);
       const int n_grp = (na * nch + gch - 1) >> gsh;
-      float run = -CUDART_INF_F, lo = CUDART_INF_F, hi = -CUDART_INF_F;
+      // a group's entry is a LOWER bound of the true score of its best column: max s_ub - eps2 * (largest item norm
+      // of the group) - beta0
+      float run = -CUDART_INF_F, run_nb = 0.0f, lo = CUDART_INF_F, hi = -CUDART_INF_F;
       int cdone = 0;                            // chunks of the sweep consumed so far
       int n_fin = 0;                            // groups that hold at least one catalog column
       for (int seq = 0; seq < na; ++seq) {
@@ -392,10 +420,16 @@ k_topk_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             }
             float g4[4];
             run = fmaxf(run, tck_chunk_max(v, g4));
+            {
+              const int ch = ((t * P.bn) >> 5) + c;                                // warp-uniform address
+              if (ch < ((P.item_cnt + 31) >> 5)) run_nb = fmaxf(run_nb, __ldg(P.nbc + ch));
+            }
             if ((++cdone & (gch - 1)) == 0) {
-              gm[(size_t)((cdone >> gsh) - 1) * rows_u] = run;
-              if (run > -CUDART_INF_F) { lo = fminf(lo, run); hi = fmaxf(hi, run); ++n_fin; }
+              const float lb = run - eps2 * run_nb - beta0;
+              gm[(size_t)((cdone >> gsh) - 1) * rows_u] = lb;
+              if (run > -CUDART_INF_F) { lo = fminf(lo, lb); hi = fmaxf(hi, lb); ++n_fin; }
               run = -CUDART_INF_F;
+              run_nb = 0.0f;
             }
           }
         }
@@ -405,17 +439,15 @@ k_topk_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         if (++buf == 2) { buf = 0; buf_phase ^= 1; }
       }
       if ((cdone & (gch - 1)) != 0) {           // the last, shorter group
-        gm[(size_t)(cdone >> gsh) * rows_u] = run;
-        if (run > -CUDART_INF_F) { lo = fminf(lo, run); hi = fmaxf(hi, run); ++n_fin; }
+        const float lb = run - eps2 * run_nb - beta0;
+        gm[(size_t)(cdone >> gsh) * rows_u] = lb;
+        if (run > -CUDART_INF_F) { lo = fminf(lo, lb); hi = fmaxf(hi, lb); ++n_fin; }
       }
       // ---- the row's bound: a value at least kk group maxima reach (bisection; counts in [kk, kk + kk/4]
       //      stop it early - a looser value only lets a few more candidates through) ----
       float thr = CUDART_INF_F;                 // dead rows keep nothing
-      bool unbounded = false;
-      if (live) {
-        if (n_fin < kk) {
-          unbounded = true;                     // fewer groups than kk (tiny range): the exact kernel takes the row
-        } else {
+      if (live && P.do_a) {
+        if (n_fin >= kk) {                      // (fewer groups than kk - a tiny range - bound nothing)
           float a = lo, b = hi;                 // invariant: count(>= a) >= kk (lo: the smallest finite maximum)
           for (int it = 0; it < 16 && a < b; ++it) {
             const float mid = 0.5f * a + 0.5f * b;
@@ -424,9 +456,15 @@ k_topk_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             for (int g = 0; g < n_grp; ++g) c += (__ldcg(gm + (size_t)g * rows_u) >= mid) ? 1 : 0;
             if (c >= kk) { a = mid; if (c <= kk + (kk >> 2)) break; } else b = mid;
           }
-          thr = a - margin;
+          // the row's bound is the best one any range (item split, item shard) finds
+          atomicMax(P.thr_g + row, tck_enc(a));
         }
       }
+      if (!P.do_b) continue;
+      // a launch that runs both sweeps reads its own bound back (other splits may have raised it meanwhile); a
+      // candidates-only launch finds the maximum over all splits and ranks.  -inf (no range could bound the row):
+      // everything passes, the list overflows, the exact kernel takes the row.
+      if (live) thr = tck_dec(__ldcg(P.thr_g + row));
       // ---- sweep B: candidates with s_ub >= thr ----
       int cnt = 0;
       unsigned long long* lbuf = P.cand + tck_list(P, live ? row : 0, sp) * TCK_CAP;
@@ -456,7 +494,7 @@ k_topk_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         if (++buf == 2) { buf = 0; buf_phase ^= 1; }
       }
       if (live) {
-        if (unbounded || cnt > TCK_CAP) { P.flags[row] = 1; cnt = 0; }
+        if (cnt > TCK_CAP) { P.flags[row] = 1; cnt = 0; }
         P.ccount[tck_list(P, row, sp)] = cnt;
       }
     }
@@ -683,74 +721,111 @@ int fvx_eval_ws_query(const FvxModel* model, int32_t n_users, FvxEvalWs* ws) {
   return 0;
 }
 
-int fvx_score_topk_tc(const FvxModel* model, const float* theta_ext, int32_t u0, int32_t u1,
-                      const int64_t* mask_row_ptr, const int32_t* mask_col, int32_t k, int32_t* out_ids,
-                      float* out_scores, const FvxEvalWs* ws, fvx_stream_t stream) {
-  FVX_CHECK_ARG(model && model->abi_version == FVX_ABI_VERSION && ws, "fvx_score_topk_tc: bad model / workspace");
-  FVX_CHECK_ARG(model->d == 0 || theta_ext, "fvx_score_topk_tc: VBPR scoring needs theta_ext");
-  FVX_CHECK_ARG(0 <= u0 && u0 < u1 && u1 <= model->num_users, "fvx_score_topk_tc: bad user range");
-  FVX_CHECK_ARG(k >= 1 && k <= 128, "fvx_score_topk_tc: k=%d outside [1,128]", k);
-  const int n_users = u1 - u0;
+// what both launches share: argument checks, geometry, tensor maps, kernel parameters
+struct TckLaunch {
   TckGeom g;
-  FVX_CHECK_ARG(tck_geometry(model, n_users, &g) == 0,
-                "fvx_score_topk_tc: K+d+3=%d too wide for the tensor-core sweep (use fvx_score_topk)",
-                model->K + model->d + 3);
+  TckParams P;
+  CUtensorMap tmA, tmB;
+  int n_users;
+};
+static int tck_setup(TckLaunch* L, const FvxModel* model, const float* theta_ext, int32_t u0, int32_t u1,
+                     const int64_t* mask_row_ptr, int32_t k, const FvxEvalWs* ws, const char* who) {
+  FVX_CHECK_ARG(model && model->abi_version == FVX_ABI_VERSION && ws, "%s: bad model / workspace", who);
+  FVX_CHECK_ARG(model->d == 0 || theta_ext, "%s: VBPR scoring needs theta_ext", who);
+  FVX_CHECK_ARG(0 <= u0 && u0 < u1 && u1 <= model->num_users, "%s: bad user range", who);
+  FVX_CHECK_ARG(k >= 1 && k <= 128, "%s: k=%d outside [1,128]", who, k);
+  FVX_CHECK_ARG(mask_row_ptr != nullptr, "%s: null mask", who);
+  const int n_users = u1 - u0;
+  L->n_users = n_users;
+  TckGeom& g = L->g;
+  FVX_CHECK_ARG(tck_geometry(model, n_users, &g) == 0, "%s: K+d+3=%d too wide for the tensor-core sweep (use fvx_score_topk)",
+                who, model->K + model->d + 3);
   FVX_CHECK_ARG(ws->KP == g.KP && ws->splits == g.splits && ws->cap == TCK_CAP && ws->u_cap >= n_users &&
                 ws->i_cap >= model->item_cnt && ws->lists >= g.lists && ws->gmax_elems >= g.gmax_elems &&
-                ws->n_ut == g.n_ut,
-                "fvx_score_topk_tc: workspace does not match fvx_eval_ws_query");
-  FVX_CHECK_ARG(ws->A && ws->Bm && ws->epsa && ws->nb && ws->stat && ws->cand && ws->ccount && ws->flags && ws->thr &&
-                ws->gmax, "fvx_score_topk_tc: null workspace buffer");
-  const int KP = g.KP, nkb = g.nkb;
-  cudaStream_t st = fvx_cu(stream);
-
-  cudaMemsetAsync(ws->stat, 0, 8, st);
-  cudaMemsetAsync(ws->flags, 0, sizeof(int32_t) * n_users, st);
-  cudaMemsetAsync(ws->ccount, 0, sizeof(int32_t) * g.lists, st);
-  const float c_rel = 1.003f * 0.00390625f + (float)KP * 4.76837158e-7f;
-  int gr = (n_users * 32 + 255) / 256;
-  if (gr > fvx_num_sms() * 8) gr = fvx_num_sms() * 8;
-  k_pack_users<<<gr, 256, 0, st>>>(*model, u0, u1, reinterpret_cast<__nv_bfloat16*>(ws->A), ws->epsa, KP, c_rel);
-  gr = fvx_num_sms() * 8;
-  k_pack_items<<<gr, 256, 0, st>>>(*model, theta_ext, reinterpret_cast<__nv_bfloat16*>(ws->Bm), ws->nb,
-                                   reinterpret_cast<uint32_t*>(ws->stat), KP);
-  FVX_CHECK_LAUNCH("k_pack");
-
-  CUtensorMap tmA, tmB;
-  int rc = tc_make_tensor_map_bf16(&tmA, ws->A, n_users, KP, (uint64_t)KP * 2, TCK_KB, TCK_BM, 3);
-  if (rc == 0) rc = tc_make_tensor_map_bf16(&tmB, ws->Bm, model->item_cnt, KP, (uint64_t)KP * 2, TCK_KB, g.bn, 3);
-  if (rc != 0) FVX_FAIL(-4, "fvx_score_topk_tc: cuTensorMapEncodeTiled failed (%d)", rc);
-
-  TckParams P;
-  P.n_users = n_users; P.item_cnt = model->item_cnt; P.item_lo = model->item_lo; P.nkb = nkb;
+                ws->n_ut == g.n_ut, "%s: workspace does not match fvx_eval_ws_query", who);
+  FVX_CHECK_ARG(ws->A && ws->Bm && ws->epsa && ws->nb && ws->nbc && ws->stat && ws->cand && ws->ccount && ws->flags &&
+                ws->thr && ws->gmax, "%s: null workspace buffer", who);
+  const int KP = g.KP;
+  int rc = tc_make_tensor_map_bf16(&L->tmA, ws->A, n_users, KP, (uint64_t)KP * 2, TCK_KB, TCK_BM, 3);
+  if (rc == 0) rc = tc_make_tensor_map_bf16(&L->tmB, ws->Bm, model->item_cnt, KP, (uint64_t)KP * 2, TCK_KB, g.bn, 3);
+  if (rc != 0) FVX_FAIL(-4, "%s: cuTensorMapEncodeTiled failed (%d)", who, rc);
+  TckParams& P = L->P;
+  P.n_users = n_users; P.item_cnt = model->item_cnt; P.item_lo = model->item_lo; P.nkb = g.nkb;
   P.nk16 = (model->K + model->d + 3 + 15) / 16;
   P.n_ut = g.n_ut; P.bn = g.bn; P.n_groups = g.n_groups; P.n_full = g.n_full;
   P.n_item_tiles = (model->item_cnt + g.bn - 1) / g.bn;
   P.splits = g.splits;
   P.tiles_per_split = (P.n_item_tiles + P.splits - 1) / P.splits;
-  P.k = k; P.u0 = u0; P.epsa = ws->epsa; P.stat = reinterpret_cast<const uint32_t*>(ws->stat);
+  P.k = k; P.u0 = u0; P.epsa = ws->epsa; P.stat = reinterpret_cast<const uint32_t*>(ws->stat); P.nbc = ws->nbc;
   P.a_stride = ws->a_stride == 2 ? 2 : 1;
+  P.do_a = P.do_b = 1;
   P.beta_c = 7.6294e-6f + (float)KP * 4.76837158e-7f;
   P.mask_row_ptr = mask_row_ptr;
   P.gmax = ws->gmax;
   P.cand = reinterpret_cast<unsigned long long*>(ws->cand); P.ccount = ws->ccount; P.flags = ws->flags;
+  P.thr_g = reinterpret_cast<int32_t*>(ws->thr);
   P.stages = g.stages;
-  const size_t smem = g.smem;
-  const int grid = g.grid;
   static FvxSmemMark topk_tc_smem;
-  if (int r = fvx_ensure_smem((const void*)k_topk_tc, &topk_tc_smem, smem, "fvx_score_topk_tc")) return r;
-  k_topk_tc<<<grid, TCK_THREADS, smem, st>>>(tmA, tmB, P);
-  FVX_CHECK_LAUNCH("k_topk_tc");
+  return fvx_ensure_smem((const void*)k_topk_tc, &topk_tc_smem, g.smem, who);
+}
 
+// Bounds: operands packed, then one sweep of every work unit for the group maxima; every row's bound tau lands in
+// ws->thr (int32, ordered like the float under signed compare: an item-sharded caller takes the MAXIMUM over the
+// ranks before fvx_score_topk_tc_select - each shard's bound is a valid bound of the whole catalog's top).
+int fvx_score_topk_tc_bounds(const FvxModel* model, const float* theta_ext, int32_t u0, int32_t u1,
+                             const int64_t* mask_row_ptr, int32_t k, const FvxEvalWs* ws, fvx_stream_t stream) {
+  TckLaunch L;
+  if (int rc = tck_setup(&L, model, theta_ext, u0, u1, mask_row_ptr, k, ws, "fvx_score_topk_tc_bounds")) return rc;
+  cudaStream_t st = fvx_cu(stream);
+  const int n_users = L.n_users, KP = L.g.KP;
+  cudaMemsetAsync(ws->stat, 0, 8, st);
+  cudaMemsetAsync(ws->flags, 0, sizeof(int32_t) * n_users, st);
+  const float c_rel = 1.003f * 0.00390625f + (float)KP * 4.76837158e-7f;
+  int gr = (n_users * 32 + 255) / 256;
+  if (gr > fvx_num_sms() * 8) gr = fvx_num_sms() * 8;
+  k_pack_users<<<gr, 256, 0, st>>>(*model, u0, u1, reinterpret_cast<__nv_bfloat16*>(ws->A), ws->epsa,
+                                   reinterpret_cast<int32_t*>(ws->thr), KP, c_rel);
+  gr = fvx_num_sms() * 8;
+  k_pack_items<<<gr, 256, 0, st>>>(*model, theta_ext, reinterpret_cast<__nv_bfloat16*>(ws->Bm), ws->nb,
+                                   reinterpret_cast<uint32_t*>(ws->stat), KP);
+  k_chunk_nbmax<<<gr, 256, 0, st>>>(ws->nb, model->item_cnt, ws->nbc);
+  FVX_CHECK_LAUNCH("k_pack");
+  L.P.do_b = 0;
+  k_topk_tc<<<L.g.grid, TCK_THREADS, L.g.smem, st>>>(L.tmA, L.tmB, L.P);
+  FVX_CHECK_LAUNCH("k_topk_tc (bounds)");
+  return 0;
+}
+
+// Candidates: one sweep with the bounds in ws->thr, exact fp32 re-scoring of the survivors, top-k; rows whose lists
+// overflow go through the exact kernel inside the call.
+int fvx_score_topk_tc_select(const FvxModel* model, const float* theta_ext, int32_t u0, int32_t u1,
+                             const int64_t* mask_row_ptr, const int32_t* mask_col, int32_t k, int32_t* out_ids,
+                             float* out_scores, const FvxEvalWs* ws, fvx_stream_t stream) {
+  TckLaunch L;
+  if (int rc = tck_setup(&L, model, theta_ext, u0, u1, mask_row_ptr, k, ws, "fvx_score_topk_tc_select")) return rc;
+  FVX_CHECK_ARG(out_ids && out_scores, "fvx_score_topk_tc_select: null output");
+  cudaStream_t st = fvx_cu(stream);
+  const int n_users = L.n_users;
+  cudaMemsetAsync(ws->ccount, 0, sizeof(int32_t) * L.g.lists, st);
+  L.P.do_a = 0;
+  k_topk_tc<<<L.g.grid, TCK_THREADS, L.g.smem, st>>>(L.tmA, L.tmB, L.P);
+  FVX_CHECK_LAUNCH("k_topk_tc (candidates)");
   long long rg = ((long long)n_users + RS_WARPS - 1) / RS_WARPS;
   if (rg > (long long)fvx_num_sms() * 8) rg = (long long)fvx_num_sms() * 8;
-  k_rescore_select<<<(int)rg, RS_WARPS * 32, 0, st>>>(*model, theta_ext, P, mask_row_ptr, mask_col, k, out_ids,
+  k_rescore_select<<<(int)rg, RS_WARPS * 32, 0, st>>>(*model, theta_ext, L.P, mask_row_ptr, mask_col, k, out_ids,
                                                       out_scores);
   FVX_CHECK_LAUNCH("k_rescore_select");
   // rows whose candidate lists could not bound the result: exact fp32 sweep, written in place (ws->thr is
-  // the scratch for their list; the statistics are dead by now and serve as its counter)
+  // the scratch for their list - the bounds are dead by now; the statistics serve as its counter)
   return fvx_launch_topk_flagged(model, theta_ext, ws->flags, n_users, u0, mask_row_ptr, mask_col, k, out_ids,
                                  out_scores, reinterpret_cast<int32_t*>(ws->thr), reinterpret_cast<int32_t*>(ws->stat), st);
+}
+
+int fvx_score_topk_tc(const FvxModel* model, const float* theta_ext, int32_t u0, int32_t u1,
+                      const int64_t* mask_row_ptr, const int32_t* mask_col, int32_t k, int32_t* out_ids,
+                      float* out_scores, const FvxEvalWs* ws, fvx_stream_t stream) {
+  if (int rc = fvx_score_topk_tc_bounds(model, theta_ext, u0, u1, mask_row_ptr, k, ws, stream)) return rc;
+  return fvx_score_topk_tc_select(model, theta_ext, u0, u1, mask_row_ptr, mask_col, k, out_ids, out_scores, ws, stream);
 }
 
 }  // extern "C"

@@ -377,6 +377,34 @@ class Engine:
              ptr(mask_col), k, ptr(ids), ptr(sc), n_thr, ptr(thr_scores), ptr(counts), stream_ptr())
         return (ids, sc, counts) if thr_scores is not None else (ids, sc)
 
+    def topk_bounds(self, mask_row_ptr, k, u0=0, u1=None):
+        """First half of the tensor-core sweep (fvx_score_topk_tc_bounds): returns the int32 tensor of per-user
+        bounds (signed order = float order).  Item-sharded callers take the element-wise MAX over the ranks of it,
+        in place, before ``topk_select``."""
+        u1 = self.U if u1 is None else u1
+        self.flush()
+        n = u1 - u0
+        ws = self._eval_ws(n)
+        call("fvx_score_topk_tc_bounds", C.byref(self.struct()), ptr(self.theta()), u0, u1, ptr(mask_row_ptr), k,
+             C.byref(ws["struct"]), stream_ptr())
+        return ws["thr"][:n]
+
+    def topk_select(self, mask_row_ptr, mask_col, k, u0=0, u1=None):
+        """Second half (fvx_score_topk_tc_select): candidates sweep with the bounds of ``topk_bounds``, exact
+        re-scoring, top-k: (ids, scores)."""
+        u1 = self.U if u1 is None else u1
+        n = u1 - u0
+        ws = self._eval_ws(n)
+        ids = torch.empty(n, k, dtype=torch.int32, device=self.device)
+        sc = torch.empty(n, k, dtype=torch.float32, device=self.device)
+        call("fvx_score_topk_tc_select", C.byref(self.struct()), ptr(self.theta()), u0, u1, ptr(mask_row_ptr),
+             ptr(mask_col), k, ptr(ids), ptr(sc), C.byref(ws["struct"]), stream_ptr())
+        self._last_flags = ws["flags"][:n]
+        return ids, sc
+
+    def tc_eval_eligible(self):
+        return self.K + self.d + 3 <= 448
+
     def rank_counts(self, mask_row_ptr, mask_col, thr_scores, u0=0, u1=None):
         """counts[u, t] = number of owned, non-masked items scoring >= thr_scores[u, t] (NaN: unused) for
         users [u0,u1): the register-tiled sweep of fvx_rank_counts (at most 4 thresholds per launch)."""
@@ -435,6 +463,7 @@ class Engine:
                   "Bm": torch.empty(Ic * q.KP, dtype=torch.uint16, device=dv),
                   "epsa": torch.empty(n_users, dtype=torch.float32, device=dv),
                   "nb": torch.empty(Ic, dtype=torch.float32, device=dv),
+                  "nbc": torch.empty(Ic // 32 + 1, dtype=torch.float32, device=dv),
                   "stat": torch.zeros(2, dtype=torch.float32, device=dv),
                   "thr": torch.zeros(n_users, dtype=torch.int32, device=dv),
                   "cand": torch.empty(q.lists * q.cap, dtype=torch.int64, device=dv),
@@ -443,6 +472,7 @@ class Engine:
             q.A, q.Bm, q.epsa, q.nb, q.stat = ptr(ws["A"]), ptr(ws["Bm"]), ptr(ws["epsa"]), ptr(ws["nb"]), ptr(ws["stat"])
             q.cand, q.ccount, q.flags, q.thr = ptr(ws["cand"]), ptr(ws["ccount"]), ptr(ws["flags"]), ptr(ws["thr"])
             q.gmax = ptr(gm)
+            q.nbc = ptr(ws["nbc"])
             ws["struct"] = q
             setattr(self, key, ws)
         ws["struct"].a_stride = int(getattr(self, "eval_a_stride", 1))

@@ -94,6 +94,10 @@ class DistGroup:
         for t in tensors:
             self.dist.all_reduce(t, group=self.group)
 
+    def all_reduce_max(self, tensors):
+        for t in tensors:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
+
     def all_reduce_start(self, tensors):
         """Starts the all-reduce on NCCL's own stream (it waits for the work already queued on the
         current stream); ``all_reduce_finish`` makes the current stream wait for the result."""
@@ -119,6 +123,11 @@ class LocalGroup:
 
     def all_reduce(self, tensors):
         total = torch.stack(list(tensors)).sum(0)
+        for t in tensors:
+            t.copy_(total)
+
+    def all_reduce_max(self, tensors):
+        total = torch.stack(list(tensors)).max(0).values
         for t in tensors:
             t.copy_(total)
 
@@ -268,14 +277,29 @@ def exchange_topk(ids, scores, group):
 
 def sharded_topk(engines, group, mask_row_ptr, mask_col, k, tc=None):
     """Full-catalog masked top-k with the catalog sharded: returns, per local rank, the merged
-    ``(ids, scores)`` of that rank's user slice ``[U/R (padded), k]``."""
+    ``(ids, scores)`` of that rank's user slice ``[U/R (padded), k]``.
+
+    Tensor-core path: every rank first runs the BOUNDS sweep of all users over its shard; a shard's bound is a
+    valid lower bound of the (k + #train)-th best score of the whole catalog, so one all-reduce (MAX, 4 bytes per
+    user) gives every rank the best bound any shard found, and the candidates sweep then keeps, per shard, only
+    what can reach the global top-k: candidate lists, exact re-scoring and list lengths shrink with the number of
+    shards.  Then the per-shard lists are exchanged by user slice (all-to-all) and merged (``fvx_topk_merge``)."""
     from .engine import topk_merge
     gather_users(engines, group)
     ids, scores = [], []
-    for e in engines:
-        i_, s_ = e.score_topk(mask_row_ptr, mask_col, k, tc=tc)
-        ids.append(i_)
-        scores.append(s_)
+    use_tc = all((e.use_tensor_cores if tc is None else tc) and e.tc_eval_eligible() for e in engines)
+    if use_tc:
+        thr = [e.topk_bounds(mask_row_ptr, k) for e in engines]
+        group.all_reduce_max(thr)
+        for e in engines:
+            i_, s_ = e.topk_select(mask_row_ptr, mask_col, k)
+            ids.append(i_)
+            scores.append(s_)
+    else:
+        for e in engines:
+            i_, s_ = e.score_topk(mask_row_ptr, mask_col, k, tc=False)
+            ids.append(i_)
+            scores.append(s_)
     xi, xs = exchange_topk(ids, scores, group)
     return [topk_merge(a, b) for a, b in zip(xi, xs)]
 
@@ -292,24 +316,35 @@ def gathered_view(engines, group):
     I = e0.I
     cnts = [shard_bounds(I, R, r)[1] for r in range(R)]
     mx = max(cnts)
+    equal = min(cnts) == mx                 # equal shards: the gathered buffer IS the catalog-ordered operand
     views, ins_w, ins_t, outs_w, outs_t = [], [], [], [], []
     for e in engines:
         e.flush()
-        w = torch.zeros(mx, e.Si, dtype=torch.float32, device=e.device)
-        w[:e.Ic] = e.items["w"]
+        if equal:
+            w = e.items["w"]
+        else:
+            w = torch.zeros(mx, e.Si, dtype=torch.float32, device=e.device)
+            w[:e.Ic] = e.items["w"]
         ins_w.append(w)
         outs_w.append(torch.empty(R, mx, e.Si, dtype=torch.float32, device=e.device))
         if e.D:
-            t = torch.zeros(mx, e.de, dtype=torch.float32, device=e.device)
-            t[:e.Ic] = e.theta()
+            if equal:
+                t = e.theta()
+            else:
+                t = torch.zeros(mx, e.de, dtype=torch.float32, device=e.device)
+                t[:e.Ic] = e.theta()
             ins_t.append(t)
             outs_t.append(torch.empty(R, mx, e.de, dtype=torch.float32, device=e.device))
     group.all_gather(outs_w, ins_w)
     if ins_t:
         group.all_gather(outs_t, ins_t)
     for i, e in enumerate(engines):
-        W = torch.cat([outs_w[i][r, :cnts[r]] for r in range(R)]).contiguous()
-        T = torch.cat([outs_t[i][r, :cnts[r]] for r in range(R)]).contiguous() if e.D else None
+        if equal:
+            W = outs_w[i].reshape(R * mx, e.Si)
+            T = outs_t[i].reshape(R * mx, e.de) if e.D else None
+        else:
+            W = torch.cat([outs_w[i][r, :cnts[r]] for r in range(R)]).contiguous()
+            T = torch.cat([outs_t[i][r, :cnts[r]] for r in range(R)]).contiguous() if e.D else None
         m = _lib.FvxModel()
         C.pointer(m)[0] = e.struct()
         m.item_lo, m.item_cnt = 0, I

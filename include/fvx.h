@@ -312,7 +312,7 @@ int fvx_score_topk_users(const FvxModel* model, const float* theta_ext, const in
  * and scores.  The caller owns the workspace: fill KP / splits / cap / n_ut / lists / gmax_elems with
  * fvx_eval_ws_query() and allocate A [u_cap*KP] bf16, Bm [i_cap*KP] bf16, epsa [u_cap] f32, nb [i_cap] f32,
  * stat [2] f32, cand [lists*cap] u64, ccount [lists] i32, flags [u_cap] i32, thr [u_cap] u32,
- * gmax [gmax_elems] f32.  a_stride (0 / 1: every tile, 2: every other tile) thins the bounds sweep.
+ * gmax [gmax_elems] f32, nbc [i_cap/32 + 1] f32.  a_stride (0 / 1: every tile, 2: every other tile) thins the bounds sweep.
  * Rows whose candidate list overflows are recomputed by the exact fp32 kernel inside the same call;
  * flags[u-u0] != 0 tells which (diagnostics only).  Needs K+d+3 <= 448. */
 typedef struct FvxEvalWs {
@@ -326,6 +326,7 @@ typedef struct FvxEvalWs {
   int32_t* flags;
   uint32_t* thr;
   float* gmax;
+  float* nbc;
   int64_t lists;
   int64_t gmax_elems;
   int32_t u_cap, i_cap, KP, splits, cap, n_ut, a_stride, _pad;
@@ -334,6 +335,16 @@ int fvx_eval_ws_query(const FvxModel* model, int32_t n_users, FvxEvalWs* ws);
 int fvx_score_topk_tc(const FvxModel* model, const float* theta_ext, int32_t u0, int32_t u1,
                       const int64_t* mask_row_ptr, const int32_t* mask_col, int32_t k,
                       int32_t* out_ids, float* out_scores, const FvxEvalWs* ws, fvx_stream_t stream);
+/* The two halves of fvx_score_topk_tc, for an item-sharded catalog: after _bounds, ws->thr [n_users] holds every
+ * row's bound as an int32 whose signed order is the float's; a shard's bound is a valid lower bound of the
+ * (k + #train)-th best score of the WHOLE catalog, so the ranks take the element-wise MAXIMUM of their ws->thr
+ * (one all-reduce of 4 bytes per user) and _select then keeps, per shard, only what can reach the global top:
+ * candidate lists, re-scoring and the top-k exchange shrink with the number of shards. */
+int fvx_score_topk_tc_bounds(const FvxModel* model, const float* theta_ext, int32_t u0, int32_t u1,
+                             const int64_t* mask_row_ptr, int32_t k, const FvxEvalWs* ws, fvx_stream_t stream);
+int fvx_score_topk_tc_select(const FvxModel* model, const float* theta_ext, int32_t u0, int32_t u1,
+                             const int64_t* mask_row_ptr, const int32_t* mask_col, int32_t k, int32_t* out_ids,
+                             float* out_scores, const FvxEvalWs* ws, fvx_stream_t stream);
 
 /* Scores of explicit (user, item) pairs with owned items (0 for others):
  * BPRMF.call / VBPR.call x_ui (BPRMF.py:69-74, VBPR.py:73-84). */

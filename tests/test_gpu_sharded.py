@@ -104,7 +104,7 @@ def test_sharded_step_run_overflow_poisons_the_loss():
 @pytest.mark.parametrize("R", [2, 4])
 def test_sharded_topk_equals_single_rank(R):
     from fvx.parallel import LocalGroup, sharded_topk, user_slices
-    U, I, K, d, D, k = 300, 2000, 32, 12, 64, 20
+    U, I, K, d, D, k = 300, 9000, 32, 12, 64, 20
     P, F, rng = _random_problem(U, I, K, d, D, seed=9)
     one = _engine(U, I, K, d=d, D=D, max_batch=64)
     one.set_features(F)
@@ -114,11 +114,12 @@ def test_sharded_topk_equals_single_rank(R):
     cs = torch.as_tensor(np.concatenate(tr), dtype=torch.int32).cuda()
     ids1, sc1 = one.score_topk(rp, cs, k)
     es = _shards(U, I, K, d, D, R, P, F, max_batch=64)
-    merged = sharded_topk(es, LocalGroup(R), rp, cs, k)
-    per, _ = user_slices(U, R)
-    ids = torch.cat([m[0] for m in merged])[:U]
-    sc = torch.cat([m[1] for m in merged])[:U]
-    assert torch.equal(ids, ids1) and torch.equal(sc, sc1)
+    for tc in (False, True):     # fp32 sweep per shard; tcgen05 sweeps with the bounds maximised over the shards
+        merged = sharded_topk(es, LocalGroup(R), rp, cs, k, tc=tc)
+        per, _ = user_slices(U, R)
+        ids = torch.cat([m[0] for m in merged])[:U]
+        sc = torch.cat([m[1] for m in merged])[:U]
+        assert torch.equal(ids, ids1) and torch.equal(sc, sc1), tc
     o_ids, o_sc = oe.masked_topk(bpr.predict_all(P, F), tr, k)
     for u in range(U):
         ok, msg = oe.topk_matches(ids[u].cpu().numpy(), sc[u].cpu().numpy(), o_ids[u], o_sc[u])
