@@ -40,7 +40,9 @@ class FvxModel(C.Structure):
 
 class FvxShardWs(C.Structure):
     _fields_ = [("S", _p), ("run_id", _p), ("run_scratch", _p), ("WU", _p), ("RU", _p), ("dE", _p), ("loss_part", _p),
-                ("max_runs", C.c_int32), ("run_cap", C.c_int32), ("owners", C.c_int32), ("users_per_owner", C.c_int32)]
+                ("max_runs", C.c_int32), ("run_cap", C.c_int32), ("owners", C.c_int32), ("users_per_owner", C.c_int32),
+                ("p2p", C.c_int32), ("_pad", C.c_int32), ("RUin", _p), ("dEall", _p), ("tails", _p), ("flags", _p),
+                ("run_user", _p), ("run_counts", _p)]
 
 
 COMM_ID_BYTES = 256
@@ -61,6 +63,8 @@ PROTOTYPES = {
     "fvx_last_error": (C.c_char_p, []),
     "fvx_sizeof_model": (C.c_int, []),
     "fvx_sizeof_table": (C.c_int, []),
+    "fvx_sizeof_shard_ws": (C.c_int, []),
+    "fvx_sizeof_eval_ws": (C.c_int, []),
     "fvx_enumerate_epoch": (C.c_int, [_p, _p, _p, _p, _i32, _p, _p, _p]),
     "fvx_epoch_perm": (C.c_int, [_p, _p, _p, _i32, _u64, _u32, _p]),
     "fvx_epoch_triples": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _u64, _u64, _p, _p, _p, _p]),
@@ -75,6 +79,7 @@ PROTOTYPES = {
     "fvx_comm_unique_id": (C.c_int, [_p]),
     "fvx_comm_create": (C.c_int, [_p, _i32, _i32, C.POINTER(_p)]),
     "fvx_comm_destroy": (C.c_int, [_p]),
+    "fvx_comm_arena": (C.c_int, [_p, _i64, C.POINTER(_p)]),
     "fvx_comm_all_reduce_f32": (C.c_int, [_p, _p, _i64, _p]),
     "fvx_adam_flush": (C.c_int, [_MP, _p]),
     "fvx_project": (C.c_int, [_MP, _p, _p]),
@@ -120,7 +125,8 @@ def load():
         fn.restype, fn.argtypes = res, args
     if lib.fvx_abi_version() != ABI_VERSION:
         raise FvxError("libfvx ABI %d != binding %d" % (lib.fvx_abi_version(), ABI_VERSION))
-    if lib.fvx_sizeof_model() != C.sizeof(FvxModel) or lib.fvx_sizeof_table() != C.sizeof(FvxTable):
+    if lib.fvx_sizeof_model() != C.sizeof(FvxModel) or lib.fvx_sizeof_table() != C.sizeof(FvxTable) or \
+            lib.fvx_sizeof_shard_ws() != C.sizeof(FvxShardWs) or lib.fvx_sizeof_eval_ws() != C.sizeof(FvxEvalWs):
         raise FvxError("struct layout mismatch between include/fvx.h and fvx/_lib.py")
     _lib = lib
     return lib

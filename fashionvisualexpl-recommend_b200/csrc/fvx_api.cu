@@ -44,4 +44,6 @@ int fvx_abi_version(void) { return FVX_ABI_VERSION; }
 const char* fvx_last_error(void) { return g_err; }
 int fvx_sizeof_model(void) { return (int)sizeof(FvxModel); }
 int fvx_sizeof_table(void) { return (int)sizeof(FvxTable); }
+int fvx_sizeof_shard_ws(void) { return (int)sizeof(FvxShardWs); }
+int fvx_sizeof_eval_ws(void) { return (int)sizeof(FvxEvalWs); }
 }

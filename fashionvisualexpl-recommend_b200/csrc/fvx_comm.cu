@@ -118,8 +118,67 @@ int fvx_comm_create(const uint8_t* id_host, int32_t rank, int32_t world, FvxComm
   return 0;
 }
 
+// Peer-mapped arena: every rank allocates `bytes`, the CUDA IPC handles travel through an all-gather on the
+// communicator, and each rank maps its peers' allocations (NVLink peer access is enabled by the mapping).
+int fvx_comm_arena(FvxComm* c, int64_t bytes, void** local_out) {
+  FVX_CHECK_ARG(c && local_out && bytes > 0, "fvx_comm_arena: bad arguments");
+  FVX_CHECK_ARG(c->world <= FVX_COMM_MAX_RANKS, "fvx_comm_arena: at most %d ranks", FVX_COMM_MAX_RANKS);
+  if (c->arena) {
+    // a new arena replaces the old one (whoever used it must be done): every rank drains its device, the ranks
+    // meet in a collective, then the mappings and the allocation go
+    cudaDeviceSynchronize();
+    float* tmp = nullptr;
+    if (cudaMalloc(&tmp, 256) != cudaSuccess) FVX_FAIL(-3, "fvx_comm_arena: cudaMalloc failed");
+    cudaMemset(tmp, 0, 256);
+    FVX_NCCL(g_nccl.AllReduce(tmp, tmp, 1, ncclFloat, ncclSum, reinterpret_cast<ncclComm_t>(c->nccl[0]), 0), "fvx_comm_arena");
+    cudaDeviceSynchronize();
+    cudaFree(tmp);
+    for (int r = 0; r < c->world; ++r)
+      if (r != c->rank && c->peer[r]) cudaIpcCloseMemHandle(c->peer[r]);
+    cudaFree(c->arena);
+    c->arena = nullptr;
+  }
+  void* base = nullptr;
+  if (cudaMalloc(&base, (size_t)bytes) != cudaSuccess)
+    FVX_FAIL(-3, "fvx_comm_arena: cudaMalloc(%lld) failed: %s", (long long)bytes, cudaGetErrorString(cudaGetLastError()));
+  cudaMemset(base, 0, (size_t)bytes);
+  cudaIpcMemHandle_t mine;
+  if (cudaIpcGetMemHandle(&mine, base) != cudaSuccess)
+    FVX_FAIL(-3, "fvx_comm_arena: cudaIpcGetMemHandle failed: %s", cudaGetErrorString(cudaGetLastError()));
+  static_assert(sizeof(cudaIpcMemHandle_t) % 4 == 0, "handle size");
+  const size_t hs = sizeof(cudaIpcMemHandle_t);
+  uint8_t* dev = nullptr;
+  if (cudaMalloc(&dev, hs * c->world) != cudaSuccess) FVX_FAIL(-3, "fvx_comm_arena: cudaMalloc failed");
+  cudaMemcpy(dev + hs * c->rank, &mine, hs, cudaMemcpyHostToDevice);
+  FVX_NCCL(g_nccl.AllGather(dev + hs * c->rank, dev, hs / 4, ncclFloat, reinterpret_cast<ncclComm_t>(c->nccl[0]), 0),
+           "fvx_comm_arena");
+  if (cudaDeviceSynchronize() != cudaSuccess)
+    FVX_FAIL(-3, "fvx_comm_arena: handle exchange failed: %s", cudaGetErrorString(cudaGetLastError()));
+  cudaIpcMemHandle_t all[FVX_COMM_MAX_RANKS];
+  cudaMemcpy(all, dev, hs * c->world, cudaMemcpyDeviceToHost);
+  cudaFree(dev);
+  for (int r = 0; r < c->world; ++r) {
+    if (r == c->rank) { c->peer[r] = reinterpret_cast<uint8_t*>(base); continue; }
+    void* p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess)
+      FVX_FAIL(-3, "fvx_comm_arena: cannot map the arena of rank %d: %s", r, cudaGetErrorString(cudaGetLastError()));
+    c->peer[r] = reinterpret_cast<uint8_t*>(p);
+  }
+  c->arena = reinterpret_cast<uint8_t*>(base);
+  c->arena_bytes = (size_t)bytes;
+  c->epoch = 0;
+  *local_out = base;
+  return 0;
+}
+
 int fvx_comm_destroy(FvxComm* c) {
   if (!c) return 0;
+  if (c->arena) {
+    cudaDeviceSynchronize();
+    for (int r = 0; r < c->world; ++r)
+      if (r != c->rank && c->peer[r]) cudaIpcCloseMemHandle(c->peer[r]);
+    cudaFree(c->arena);
+  }
   for (int i = 0; i < 2; ++i)
     if (c->nccl[i]) g_nccl.CommDestroy(reinterpret_cast<ncclComm_t>(c->nccl[i]));
   if (c->side) cudaStreamDestroy(c->side);

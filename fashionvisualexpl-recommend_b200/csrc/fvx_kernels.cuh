@@ -75,7 +75,7 @@ int fvx_launch_prep(const FvxModel* m, const int32_t* user, const int32_t* pos, 
 // what: ALL = tables + E_ext + finalisation; TABLES = touched rows only; E = E_ext + finalisation
 enum { FVX_UPD_ALL = 0, FVX_UPD_TABLES = 1, FVX_UPD_E = 2 };
 int fvx_launch_update(const FvxModel* m, int B, int parts, int gnp, const float* gE_src, int loss_slot,
-                      cudaStream_t st, int what = FVX_UPD_ALL, const float* loss_pair = nullptr);
+                      cudaStream_t st, int what = FVX_UPD_ALL, const float* loss_pair = nullptr, int n_tails = 1);
 // dedup = 1 (unique-row step): theta rows / coefficient sums are addressed through upos, th_ks is the CAP of
 // the K split (the kernel derives the split from the list length like the projection does)
 int fvx_launch_score_grad(const FvxModel* m, const int32_t* user, int B, int loss_slot, int th_ks, cudaStream_t st,

@@ -715,7 +715,9 @@ struct UpdParams {
   int finalize;         // the last block advances the step counter and resets the lists
   int32_t* sync;        // [1] blocks-done counter (zero between launches)
   const float* gE_src;  // partial gradients of E_ext (model->gE_part, or an all-reduced [D, de] buffer)
-  const float* loss_pair;   // sharded step: {hi, lo, overflow flag} - the all-reduced loss shares of the ranks
+  const float* loss_pair;   // sharded step: n_tails x {hi, lo, overflow flag, -}: the loss shares of the ranks (all-reduced
+                            //   into one tail, or one tail per rank)
+  int n_tails;
 };
 
 __device__ __forceinline__ void adam4(float4& w, float4& m, float4& v, const float4 g, float a) {
@@ -809,8 +811,13 @@ k_update(FvxModel M, UpdParams U) {
     if ((threadIdx.x & 31) == 0 && sq != 0.0f && U.loss_slot >= 0) atomicAdd(M.loss + U.loss_slot, (double)(reg * sq));
     if (U.loss_pair && b == U.nb_u + U.nb_i && threadIdx.x == 0 && U.loss_slot >= 0) {
       // a batch with more runs than the exchange buffers hold poisons the loss: nothing fails silently
-      const double l = U.loss_pair[2] != 0.0f ? (double)__int_as_float(0x7fc00000) : (double)U.loss_pair[0] + (double)U.loss_pair[1];
-      atomicAdd(M.loss + U.loss_slot, l);
+      double l = 0.0;
+      bool over = false;
+      for (int r = 0; r < U.n_tails; ++r) {
+        l += (double)U.loss_pair[4 * r] + (double)U.loss_pair[4 * r + 1];
+        over = over || U.loss_pair[4 * r + 2] != 0.0f;
+      }
+      atomicAdd(M.loss + U.loss_slot, over ? (double)__int_as_float(0x7fc00000) : l);
     }
   }
   // last block: the step is complete
@@ -935,7 +942,7 @@ int fvx_launch_prep(const FvxModel* m, const int32_t* user, const int32_t* pos, 
 }
 
 int fvx_launch_update(const FvxModel* m, int B, int parts, int gnp, const float* gE_src, int loss_slot,
-                      cudaStream_t st, int what, const float* loss_pair) {
+                      cudaStream_t st, int what, const float* loss_pair, int n_tails) {
   UpdParams U;
   U.dense = m->adam_mode == FVX_ADAM_DENSE;
   if (U.dense) {
@@ -951,7 +958,7 @@ int fvx_launch_update(const FvxModel* m, int B, int parts, int gnp, const float*
   if (what == FVX_UPD_TABLES) U.nb_e = 0;
   if (what == FVX_UPD_E) { U.nb_u = 0; U.nb_i = 0; if (U.nb_e == 0) U.nb_e = 1; }
   U.finalize = what != FVX_UPD_TABLES;
-  U.parts = parts; U.gnp = gnp; U.loss_slot = loss_slot; U.sync = m->sync; U.gE_src = gE_src; U.loss_pair = loss_pair;
+  U.parts = parts; U.gnp = gnp; U.loss_slot = loss_slot; U.sync = m->sync; U.gE_src = gE_src; U.loss_pair = loss_pair; U.n_tails = n_tails;
   if (loss_pair && U.nb_e == 0) U.nb_e = 1;
   k_update<<<U.nb_u + U.nb_i + U.nb_e, 256, 0, st>>>(*m, U);
   FVX_CHECK_LAUNCH("k_update");

@@ -490,7 +490,7 @@ k_slot_count(const int32_t* __restrict__ user, long long n, int per, int R, int3
 }
 __global__ void __launch_bounds__(RI_THREADS)
 k_slot_write(const int32_t* __restrict__ user, long long n, int per, int R, int cap, const int32_t* __restrict__ part,
-             int32_t* __restrict__ run_id) {
+             int32_t* __restrict__ run_id, int32_t* __restrict__ totals) {
   __shared__ unsigned long long sh[RI_THREADS / 32][2];
   __shared__ int carry[RS_OWNERS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -540,10 +540,18 @@ k_slot_write(const int32_t* __restrict__ user, long long n, int per, int R, int 
     }
     __syncthreads();
   }
+  // runs of every owner in the whole batch (capped at cap): what the peer-to-peer exchange moves per segment
+  if (totals && blockIdx.x == gridDim.x - 1 && threadIdx.x < RS_OWNERS) totals[threadIdx.x] = min(carry[threadIdx.x], cap);
 }
 
+static int run_slots_impl(const int32_t* user, int64_t n, int32_t users_per_owner, int32_t owners, int32_t cap,
+                          int32_t* run_slot, int32_t* scratch, int32_t* totals, fvx_stream_t stream);
 extern "C" int fvx_run_slots(const int32_t* user, int64_t n, int32_t users_per_owner, int32_t owners, int32_t cap,
                              int32_t* run_slot, int32_t* scratch, fvx_stream_t stream) {
+  return run_slots_impl(user, n, users_per_owner, owners, cap, run_slot, scratch, nullptr, stream);
+}
+static int run_slots_impl(const int32_t* user, int64_t n, int32_t users_per_owner, int32_t owners, int32_t cap,
+                          int32_t* run_slot, int32_t* scratch, int32_t* totals, fvx_stream_t stream) {
   FVX_CHECK_ARG(user && run_slot && scratch && n >= 0, "fvx_run_slots: bad arguments");
   FVX_CHECK_ARG(owners >= 1 && owners <= RS_OWNERS && users_per_owner >= 1 && cap >= 1, "fvx_run_slots: owners=%d outside [1, %d]",
                 owners, RS_OWNERS);
@@ -552,9 +560,169 @@ extern "C" int fvx_run_slots(const int32_t* user, int64_t n, int32_t users_per_o
   FVX_CHECK_ARG(nb <= 8192, "fvx_run_slots: n=%lld too large", (long long)n);
   cudaStream_t st = fvx_cu(stream);
   k_slot_count<<<(int)nb, RI_THREADS, 0, st>>>(user, n, users_per_owner, owners, scratch);
-  k_slot_write<<<(int)nb, RI_THREADS, 0, st>>>(user, n, users_per_owner, owners, cap, scratch, run_slot);
+  k_slot_write<<<(int)nb, RI_THREADS, 0, st>>>(user, n, users_per_owner, owners, cap, scratch, run_slot, totals);
   FVX_CHECK_LAUNCH("k_run_slots");
   return 0;
+}
+
+// ---- peer-to-peer exchange (FvxComm arena: every rank's exchange buffers are mapped into every other rank) ----
+// The NCCL collectives of the step are latency-bound at these sizes and slow down beside the tensor-core kernels
+// (8 GPUs: all-gather of the user rows 220 us, all-reduce of S 128 us, reduce-scatter of the gradient shares 273 us
+// per step - profiles/r2_sharded_*).  Here the kernels that PRODUCE the data store it straight into the consumers'
+// memory over NVLink, and a one-warp barrier kernel separates producers from consumers.
+struct PeerPtrs {
+  uint8_t* p[FVX_COMM_MAX_RANKS];      // p[r]: rank r's arena as mapped here
+  uint8_t* self;                       // this rank's arena
+  int rank, world;
+};
+template <typename T>
+__device__ __forceinline__ T* peer_of(const PeerPtrs& X, int r, T* local) {
+  return reinterpret_cast<T*>(X.p[r] + (reinterpret_cast<uint8_t*>(local) - X.self));
+}
+
+// Cross-GPU barrier: every rank writes `epoch` into its slot of every peer's flag array, then waits until all slots
+// of its own array have reached it.  One warp; the kernel boundary before it has made the producer kernel's peer
+// stores visible (plus the fence below).  A protocol error traps after ~2 s instead of hanging the box.
+__global__ void k_xbar(PeerPtrs X, uint32_t* flags, uint32_t epoch) {
+  const int lane = threadIdx.x;
+  __threadfence_system();
+  if (lane < X.world) {
+    volatile uint32_t* dst = peer_of(X, lane, flags) + X.rank;
+    *dst = epoch;
+  }
+  __threadfence_system();
+  if (lane < X.world) {
+    volatile uint32_t* mine = flags + lane;
+    const long long t0 = clock64();
+    while ((int32_t)(*mine - epoch) < 0) {
+      if (clock64() - t0 > 4000000000LL) __trap();
+    }
+  }
+  __threadfence_system();
+}
+
+// owner of a catalog item under shard_bounds(): the first `rem` shards hold base + 1 rows
+__device__ __forceinline__ int item_owner(int32_t i, int base, int rem) {
+  const int cut = rem * (base + 1);
+  return i < cut ? i / (base + 1) : rem + (i - cut) / (base > 0 ? base : 1);
+}
+
+// k_pack_wu, peer-to-peer: the fresh row of an owned run goes into EVERY rank's WU (its own included); the user of
+// the run is kept for the gradient scatter (run_user[index in this rank's segment])
+__global__ void k_pack_wu_p2p(FvxModel M, const int32_t* __restrict__ user, int B, const int32_t* __restrict__ run_id,
+                              float* __restrict__ WU, long long ru_rows, int32_t* __restrict__ run_user, int cap, PeerPtrs X) {
+  const int lane = threadIdx.x & 31;
+  const int Su = M.users.stride, S4 = Su >> 2;
+  const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long npass = ((long long)B + 31) >> 5;
+  for (long long p = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; p < npass; p += nw) {
+    const long long b = p * 32 + lane;
+    int32_t u = -1, run = 0;
+    bool start = false;
+    if (b < B) {
+      u = user[b];
+      run = run_id[b];
+      start = (b == 0 || user[b - 1] != u) && u >= M.user_lo && u < M.user_lo + M.user_cnt;
+      if (start && run >= ru_rows) { M.sync[2] = 1; start = false; }    // more runs than the buffers hold
+    }
+    uint32_t msk = __ballot_sync(0xffffffffu, start);
+    while (msk) {
+      const int src = __ffs(msk) - 1;
+      msk &= msk - 1;
+      const int32_t uu = __shfl_sync(0xffffffffu, u, src);
+      const int32_t rr = __shfl_sync(0xffffffffu, run, src);
+      const float4* s4 = reinterpret_cast<const float4*>(M.users.w + (size_t)uu * Su);
+      if (lane == 0) run_user[rr - X.rank * cap] = uu;
+      for (int c = lane; c < S4; c += 32) {
+        const float4 v = s4[c];
+        for (int r = 0; r < X.world; ++r) reinterpret_cast<float4*>(peer_of(X, r, WU) + (size_t)rr * Su)[c] = v;
+      }
+    }
+  }
+}
+
+// After k_partial_scores_v4 (which fills this rank's S): the partial score of an owned slot also goes to the one
+// other rank that needs it - the owner of the triple's OTHER item (x_b = S[b] - S[B+b] is formed by the owners of
+// the two sides only).
+__global__ void k_send_scores(FvxModel M, const int32_t* __restrict__ pos, const int32_t* __restrict__ neg, int B,
+                              float* __restrict__ S, const int32_t* __restrict__ count, int ibase, int irem, PeerPtrs X) {
+  const int32_t* cslot = M.cmap + 2 * (size_t)M.max_batch;
+  const long long n_owned = *count;
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n_owned; j += (long long)gridDim.x * blockDim.x) {
+    const int32_t slot = cslot[j];
+    const int32_t other = slot < B ? neg[slot] : pos[slot - B];
+    if (other < 0 || other >= M.num_items) continue;
+    const int o = item_owner(other, ibase, irem);
+    if (o != X.rank) peer_of(X, o, S)[slot] = S[slot];
+  }
+}
+
+// The gradient shares of the runs of owner o (segment o of this rank's RU) go into owner o's RUin[this rank]
+__global__ void k_push_ru(const float* __restrict__ RU, float* __restrict__ RUin, const int32_t* __restrict__ run_counts,
+                          int cap, int S4, PeerPtrs X) {
+  for (int o = 0; o < X.world; ++o) {
+    const int n = run_counts[o];
+    const float4* src = reinterpret_cast<const float4*>(RU) + (size_t)o * cap * S4;
+    float4* dst = reinterpret_cast<float4*>(peer_of(X, o, RUin)) + (size_t)X.rank * cap * S4;
+    const long long total = (long long)n * S4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+      dst[i] = src[i];
+  }
+}
+
+// The owner sums the shares of every source rank (fixed order: deterministic) and adds the run into the user's
+// accumulator (a user may own two runs of a batch)
+__global__ void k_scatter_runs_p2p(FvxModel M, const float* __restrict__ RUin, const int32_t* __restrict__ run_user,
+                                   const int32_t* __restrict__ run_counts, int cap, PeerPtrs X) {
+  const int lane = threadIdx.x & 31;
+  const int Su = M.users.stride, S4 = Su >> 2;
+  const int n = run_counts[X.rank];
+  const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long k = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < n; k += nw) {
+    const int32_t u = run_user[k];
+    float* g = M.users.g + (size_t)u * Su;
+    for (int c = lane; c < S4; c += 32) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int r = 0; r < X.world; ++r) {
+        const float4 v = reinterpret_cast<const float4*>(RUin + ((size_t)r * cap + k) * Su)[c];
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      ss_red_add4(g + 4 * c, acc);
+    }
+  }
+}
+
+// k_dE_pack, peer-to-peer: this rank's dE and tail go into slot `rank` of every rank's dEall / tails
+__global__ void k_dE_pack_p2p(const float* __restrict__ part, int parts, int D, int gnp, int de, float* __restrict__ dEall,
+                              float* __restrict__ tails, double* __restrict__ loss_part, int32_t* __restrict__ sync, PeerPtrs X) {
+  const int n = D * de;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int f = i / de, c = i - f * de;
+    const float* gp = part + (size_t)f * gnp + c;
+    const size_t ps = (size_t)D * gnp;
+    float g = 0.0f;
+    int p = 0;
+    for (; p + 8 <= parts; p += 8) {
+      float t_[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) t_[q] = gp[(size_t)(p + q) * ps];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) g += t_[q];
+    }
+    for (; p < parts; ++p) g += gp[(size_t)p * ps];
+    for (int r = 0; r < X.world; ++r) peer_of(X, r, dEall)[(size_t)X.rank * n + i] = g;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const double l = *loss_part;
+    const float hi = (float)l;
+    const float lo = (float)(l - (double)hi), fl = sync[2] ? 1.0f : 0.0f;
+    for (int r = 0; r < X.world; ++r) {
+      float* t = peer_of(X, r, tails) + 4 * X.rank;
+      t[0] = hi; t[1] = lo; t[2] = fl; t[3] = 0.0f;
+    }
+    sync[2] = 0;
+    *loss_part = 0.0;
+  }
 }
 
 static int sharded_common(const FvxModel* m, const FvxShardWs* ws, const int32_t* user, int B, const char* who) {
@@ -638,7 +806,8 @@ static int sh_p1a(const ShCtx& c, cudaStream_t st) {
 }
 static int sh_p1b(const ShCtx& c, cudaStream_t st) {
   // (WU needs no clearing: every row a kernel reads was written by the run's owner and gathered)
-  return fvx_run_slots(c.user, c.B, c.ws->users_per_owner, c.ws->owners, c.ws->run_cap, c.ws->run_id, c.ws->run_scratch, st);
+  return run_slots_impl(c.user, c.B, c.ws->users_per_owner, c.ws->owners, c.ws->run_cap, c.ws->run_id, c.ws->run_scratch,
+                        c.ws->run_counts, st);
 }
 static int sh_clear_ru(const ShCtx& c, cudaStream_t st) {
   const FvxModel& M = *c.m;
@@ -738,7 +907,14 @@ static int sh_p8(const ShCtx& c, cudaStream_t st) {
   // DEFERRED: the touched rows keep their gradient and take the step when they are next needed (replay_row);
   // the reduced dE, the loss (sum of the ranks' shares, NaN after a run overflow) and the step counter
   return fvx_launch_update(&M, c.B, M.D > 0 ? 1 : 0, M.de, c.ws->dE, c.loss_slot, st,
-                           fvx_merged_update(&M) ? FVX_UPD_E : FVX_UPD_ALL, c.ws->dE + (size_t)M.D * M.de);
+                           fvx_merged_update(&M) ? FVX_UPD_E : FVX_UPD_ALL, c.ws->dE + (size_t)M.D * M.de, 1);
+}
+// peer-to-peer: dE arrives as one partial per rank (dEall[R][D*de], summed in rank order by the update), the loss
+// shares as one tail per rank
+static int sh_p8_p2p(const ShCtx& c, int world, cudaStream_t st) {
+  const FvxModel& M = *c.m;
+  return fvx_launch_update(&M, c.B, M.D > 0 ? world : 0, M.de, c.ws->dEall, c.loss_slot, st,
+                           fvx_merged_update(&M) ? FVX_UPD_E : FVX_UPD_ALL, c.ws->tails, world);
 }
 
 static int make_ctx(ShCtx* c, const FvxModel* m, const FvxShardWs* ws, const int32_t* user, const int32_t* pos,
@@ -806,11 +982,129 @@ int fvx_bpr_step_sharded_phase(const FvxModel* model, const FvxShardWs* ws, cons
   }
 }
 
+// The step with the peer-to-peer exchange (file header; needs the communicator's arena): same pieces, the four
+// collectives replaced by peer stores inside the producing kernels + one-warp barrier kernels.
+static int step_sharded_p2p(ShCtx& c, FvxComm* comm, cudaStream_t st) {
+  const FvxModel& M = *c.m;
+  const FvxShardWs* ws = c.ws;
+  cudaStream_t sd = comm->side;
+  PeerPtrs X;
+  for (int r = 0; r < FVX_COMM_MAX_RANKS; ++r) X.p[r] = r < comm->world ? comm->peer[r] : nullptr;
+  X.self = comm->arena; X.rank = comm->rank; X.world = comm->world;
+  const uint8_t *lo = comm->arena, *hi = comm->arena + comm->arena_bytes;
+  auto in_arena = [&](const void* p) { return (const uint8_t*)p >= lo && (const uint8_t*)p < hi; };
+  FVX_CHECK_ARG(in_arena(ws->WU) && in_arena(ws->S) && in_arena(ws->RUin) && in_arena(ws->dEall) && in_arena(ws->tails) &&
+                in_arena(ws->flags) && ws->run_user && ws->run_counts,
+                "fvx_bpr_step_sharded: peer-to-peer mode needs WU, S, RUin, dEall, tails, flags inside the communicator's arena");
+  const uint32_t epoch = ++comm->epoch;                 // one value per step; one flag array per barrier of the step
+  uint32_t* flags = ws->flags;
+  const int base = M.num_items / comm->world, rem = M.num_items % comm->world;
+  const int cap = ws->run_cap, S4 = M.users.stride >> 2;
+  STRACE(ST_BEGIN, st);
+  if (int rc = sh_p1a(c, st)) return rc;
+  if (int rc = sh_p1b(c, st)) return rc;
+  STRACE(ST_P1, st);
+  if (int rc = fvx_launch_prep(&M, c.user, c.pos, c.neg, c.B, st, c.uniq ? FVX_PREP_USERS_ONLY : FVX_PREP_CLAIMS)) return rc;
+  cudaMemsetAsync(ws->S, 0, sizeof(float) * 2 * (size_t)c.B, st);
+  k_pack_wu_p2p<<<scan_grid(c.B), 256, 0, st>>>(M, c.user, c.B, ws->run_id, ws->WU, (long long)ws->max_runs, ws->run_user, cap, X);
+  FVX_CHECK_LAUNCH("k_pack_wu_p2p");
+  STRACE(ST_P2, st);
+  cudaEventRecord(comm->ev[0], st);
+  cudaStreamWaitEvent(sd, comm->ev[0], 0);
+  // side, beside the projection: barrier 0 (every rank's fresh user rows have landed), cleared RU, item catch-up
+  k_xbar<<<1, 32, 0, sd>>>(X, flags + 0 * FVX_COMM_MAX_RANKS, epoch);
+  STRACE(ST_AR_WU, sd);
+  if (int rc = sh_clear_ru(c, sd)) return rc;
+  if (int rc = sh_p2i(c, sd)) return rc;
+  cudaEventRecord(comm->ev[1], sd);
+  {
+    // piece 3 without its own clearing of S (cleared above, before this rank's barrier signal: peers store into it)
+    int32_t* count = M.sync + 1;
+    cudaMemsetAsync(M.cmap, 0xFF, sizeof(int32_t) * 2 * (size_t)M.max_batch, st);
+    long long g = (2LL * c.B + 255) / 256;
+    if (g > (long long)fvx_num_sms() * 8) g = (long long)fvx_num_sms() * 8;
+    k_compact_owned<<<(int)g, 256, 0, st>>>(M, c.B, count);
+    FVX_CHECK_LAUNCH("k_compact_owned");
+    if (c.uniq) {
+      FVX_CHECK_ARG(2LL * c.B * fvx_tc_np(M.de) <= M.th_cap, "fvx_bpr_step_sharded: TH scratch too small");
+      if (int rc = fvx_launch_project_tc(&M, M.items.list, 0, 2 * c.B, c.ks, M.TH, st, M.items.count, 1, c.sm_reserve)) return rc;
+    } else if (M.D > 0) {
+      if (M.use_tensor_cores) {
+        if (int rc = fvx_launch_project_tc(&M, M.cmap, 0, 2 * c.B, c.ks, M.TH, st, count, 0, c.sm_reserve)) return rc;
+      } else {
+        if (int rc = fvx_launch_project(&M, M.cmap, 2 * c.B, M.TH, st)) return rc;
+      }
+    }
+  }
+  STRACE(ST_P3, st);
+  cudaStreamWaitEvent(st, comm->ev[1], 0);
+  if (int rc = sh_p4(c, st)) return rc;
+  {
+    long long g = (2LL * c.B / comm->world + 255) / 256 + 1;
+    if (g > (long long)fvx_num_sms() * 8) g = (long long)fvx_num_sms() * 8;
+    k_send_scores<<<(int)g, 256, 0, st>>>(M, c.pos, c.neg, c.B, ws->S, M.sync + 1, base, rem, X);
+    FVX_CHECK_LAUNCH("k_send_scores");
+  }
+  STRACE(ST_P4, st);
+  k_xbar<<<1, 32, 0, st>>>(X, flags + 1 * FVX_COMM_MAX_RANKS, epoch);       // barrier 1: both sides of every owned triple
+  STRACE(ST_AR_S, st);
+  if (int rc = sh_p5(c, st)) return rc;
+  STRACE(ST_P5, st);
+  cudaEventRecord(comm->ev[2], st);
+  cudaStreamWaitEvent(sd, comm->ev[2], 0);
+  // side, beside grad_E: the gradient shares go to the owners of their runs, who add them up
+  {
+    long long g = ((long long)ws->max_runs * S4 + 255) / 256;
+    if (g > (long long)fvx_num_sms() * 4) g = (long long)fvx_num_sms() * 4;
+    k_push_ru<<<(int)g, 256, 0, sd>>>(ws->RU, ws->RUin, ws->run_counts, cap, S4, X);
+    FVX_CHECK_LAUNCH("k_push_ru");
+    k_xbar<<<1, 32, 0, sd>>>(X, flags + 2 * FVX_COMM_MAX_RANKS, epoch);     // barrier 2: every source's shares have landed
+    STRACE(ST_AR_RU, sd);
+    long long g2 = ((long long)cap * 32 + 255) / 256;
+    if (g2 > (long long)fvx_num_sms() * 8) g2 = (long long)fvx_num_sms() * 8;
+    k_scatter_runs_p2p<<<(int)g2, 256, 0, sd>>>(M, ws->RUin, ws->run_user, ws->run_counts, cap, X);
+    FVX_CHECK_LAUNCH("k_scatter_runs_p2p");
+  }
+  STRACE(ST_P7, sd);
+  cudaEventRecord(comm->ev[3], sd);
+  {
+    int parts = 0;
+    const bool tc = M.D > 0 && M.use_tensor_cores;
+    if (M.D > 0) {
+      if (c.uniq) {
+        if (int rc = fvx_launch_grad_E_tc(&M, M.items.list, 2 * c.B, &parts, st, M.items.count, c.sm_reserve)) return rc;
+      } else if (tc) {
+        if (int rc = fvx_launch_grad_E_tc(&M, M.cmap, 2 * c.B, &parts, st, M.sync + 1, c.sm_reserve)) return rc;
+      } else {
+        if (int rc = fvx_launch_grad_E(&M, M.cmap, 2 * c.B, &parts, st)) return rc;
+      }
+    }
+    const int n = M.D * M.de;
+    k_dE_pack_p2p<<<n > 0 ? (n + 255) / 256 : 1, 256, 0, st>>>(M.gE_part, parts, M.D, tc ? fvx_tc_np(M.de) : M.de, M.de,
+                                                              ws->dEall, ws->tails, ws->loss_part, M.sync, X);
+    FVX_CHECK_LAUNCH("k_dE_pack_p2p");
+  }
+  STRACE(ST_P6, st);
+  k_xbar<<<1, 32, 0, st>>>(X, flags + 3 * FVX_COMM_MAX_RANKS, epoch);       // barrier 3: every rank's dE has landed
+  STRACE(ST_AR_DE, st);
+  cudaStreamWaitEvent(st, comm->ev[3], 0);
+  if (int rc = sh_p8_p2p(c, comm->world, st)) return rc;
+  STRACE(ST_END, st);
+  return 0;
+}
+
 int fvx_bpr_step_sharded(const FvxModel* model, const FvxShardWs* ws, FvxComm* comm, const int32_t* user,
                          const int32_t* pos, const int32_t* neg, int32_t B, int32_t loss_slot, fvx_stream_t stream) {
   ShCtx c;
   if (int rc = make_ctx(&c, model, ws, user, pos, neg, B, loss_slot, "fvx_bpr_step_sharded")) return rc;
   FVX_CHECK_ARG(comm != nullptr, "fvx_bpr_step_sharded: null communicator");
+  if (ws->p2p) {
+    FVX_CHECK_ARG(comm->arena != nullptr, "fvx_bpr_step_sharded: FvxShardWs.p2p needs fvx_comm_arena");
+    FVX_CHECK_ARG(ws->owners == comm->world, "fvx_bpr_step_sharded: FvxShardWs.owners %d != communicator size %d", ws->owners,
+                  comm->world);
+    c.sm_reserve = 0;
+    return step_sharded_p2p(c, comm, fvx_cu(stream));
+  }
   const FvxModel& M = *model;
   cudaStream_t st = fvx_cu(stream), sd = comm->side;
   {

@@ -153,8 +153,12 @@ class LocalGroup:
 class ShardedStep:
     """``engines``: this process's engines - ONE with a ``DistGroup``, or all R with a ``LocalGroup``."""
 
-    def __init__(self, engines, group, max_runs=None):
-        """``max_runs``: upper bound of the number of runs of equal users in a batch.  Default: the batch size
+    def __init__(self, engines, group, max_runs=None, transport=None):
+        """``transport`` (real process groups): "p2p" (default: the kernels of the step store into their peers'
+        exchange buffers over NVLink - a CUDA-IPC arena - and one-warp barrier kernels replace the collectives) or
+        "nccl" (all-gather / all-reduce / reduce-scatter / all-reduce inside the C call).
+
+        ``max_runs``: upper bound of the number of runs of equal users in a batch.  Default: the batch size
         (the hard bound).  The user rows (WU) and user-gradient shares (RU) exchanged per step are laid out in one
         segment per owner of ``run_cap`` = max_runs / R (+ 15 % + 64 for the spread of the owners' shares) rows, so
         a tight bound - B // (shortest train list) + 2 is exact for batches of the reference's sampler - saves
@@ -176,11 +180,34 @@ class ShardedStep:
                  "run_scratch": torch.zeros(8 * (B // 1024 + 2), **i32), "WU": torch.zeros(rows, e.Su, **f32),
                  "RU": torch.zeros(rows, e.Su, **f32), "dE": torch.zeros(e.D * e.de + 4, **f32),
                  "loss_part": torch.zeros(1, dtype=torch.float64, device=dv)}
+            t["run_user"] = torch.zeros(self.run_cap, **i32)
+            t["run_counts"] = torch.zeros(8, **i32)
             w = _lib.FvxShardWs(ptr(t["S"]), ptr(t["run_id"]), ptr(t["run_scratch"]), ptr(t["WU"]), ptr(t["RU"]),
                                 ptr(t["dE"]), ptr(t["loss_part"]), rows, self.run_cap, R, max(per, 1))
+            w.run_user, w.run_counts = ptr(t["run_user"]), ptr(t["run_counts"])
             t["struct"] = w
             self.ws.append(t)
         self._comm = group.comm(self.engines[0].device) if isinstance(group, DistGroup) else None
+        import os
+        self.transport = transport or os.environ.get("FVX_SHARDED_TRANSPORT") or ("p2p" if self._comm is not None and R > 1 else "nccl")
+        if self.transport == "p2p":
+            if self._comm is None:
+                raise _lib.FvxError("the peer-to-peer transport needs a real process group")
+            # the exchange buffers inside the peer-mapped arena, at the same offsets on every rank
+            e, w = self.engines[0], self.ws[0]["struct"]
+            sizes = (("WU", rows * e.Su * 4), ("S", 2 * B * 4), ("RUin", R * self.run_cap * e.Su * 4),
+                     ("dEall", R * max(e.D * e.de, 1) * 4), ("tails", R * 16), ("flags", 4 * 8 * 4))
+            off, total = {}, 0
+            for name, nbytes in sizes:
+                off[name] = total
+                total += (nbytes + 255) // 256 * 256
+            base = C.c_void_p()
+            with torch.cuda.device(e.device):
+                call("fvx_comm_arena", self._comm, total, C.byref(base))
+            for name, _ in sizes:
+                setattr(w, name, base.value + off[name])
+            w.p2p = 1
+            self.ws[0]["WU"] = self.ws[0]["S"] = None        # (the torch copies are not the ones in use)
 
     def step(self, user, pos, neg, loss_slot=0):
         """One optimiser step on every (local) rank; asynchronous."""

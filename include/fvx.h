@@ -134,6 +134,8 @@ const char* fvx_last_error(void);
 /* size of the structs as compiled, so a binding can assert its own layout */
 int fvx_sizeof_model(void);
 int fvx_sizeof_table(void);
+int fvx_sizeof_shard_ws(void);
+int fvx_sizeof_eval_ws(void);
 
 /* ---- data: replaces DataLoader.all_triple_batches (dataset.py:83-114) ---------- */
 
@@ -221,6 +223,17 @@ typedef struct FvxShardWs {
   int32_t run_cap;       /* rows per owner segment */
   int32_t owners;        /* number of ranks (<= 8) */
   int32_t users_per_owner;   /* block size of the user ownership: owner(u) = u / users_per_owner */
+  /* peer-to-peer exchange (p2p != 0; fvx_comm_arena): WU, S and the four buffers below lie inside the communicator's
+   * peer-mapped arena at the same offsets on every rank; the kernels that produce the data store it straight into
+   * their consumers' copies over NVLink and one-warp barrier kernels replace the collectives */
+  int32_t p2p;
+  int32_t _pad;
+  float* RUin;           /* [owners, run_cap, users.stride] gradient shares of THIS rank's runs, one block per source */
+  float* dEall;          /* [owners, D*de] one dE per rank */
+  float* tails;          /* [owners, 4] loss share (hi, lo) and run-overflow flag of every rank */
+  uint32_t* flags;       /* [4, 8] barrier flags, zero-initialised */
+  int32_t* run_user;     /* [run_cap] (local) user of each run of this rank's segment */
+  int32_t* run_counts;   /* [8] (local) runs per owner in the batch in flight */
 } FvxShardWs;
 
 /* Communicators of the sharded step: two NCCL communicators over the same ranks, one for the collectives on
@@ -234,6 +247,11 @@ typedef struct FvxComm FvxComm;
 int fvx_comm_unique_id(uint8_t* id_host);
 int fvx_comm_create(const uint8_t* id_host, int32_t rank, int32_t world, FvxComm** out);
 int fvx_comm_destroy(FvxComm* comm);
+/* Peer-mapped arena [collective]: every rank allocates `bytes` (zero-filled) and maps every other rank's allocation
+ * (CUDA IPC; NVLink peer access) - kernels of the sharded step then store into their peers' exchange buffers
+ * directly.  *local receives this rank's base address; lay the buffers out at the same offsets on every rank.
+ * A second call replaces the arena (the buffers of the first become invalid on every rank). */
+int fvx_comm_arena(FvxComm* comm, int64_t bytes, void** local);
 /* all-reduce (sum) of n floats in place on the caller's stream, e.g. to assemble per-rank statistics */
 int fvx_comm_all_reduce_f32(FvxComm* comm, float* buf, int64_t n, fvx_stream_t stream);
 
