@@ -11,7 +11,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libfvx.so")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 ADAM_DENSE, ADAM_DEFERRED, ADAM_LAZY = 0, 1, 2
 N_PHASES = 5
 PHASES = ("prep", "project", "score_grad", "grad_E", "update")
@@ -35,7 +35,10 @@ class FvxModel(C.Structure):
                 ("step", _p), ("loss", _p), ("loss_slots", C.c_int32), ("_pad1", C.c_int32), ("TH", _p),
                 ("th_cap", C.c_int64), ("W", _p), ("rows", _p), ("sync", _p), ("cmap", _p), ("max_batch", C.c_int32),
                 ("use_tensor_cores", C.c_int32), ("upos", _p), ("W_sum", _p), ("uslot", _p), ("user_lo", C.c_int32),
-                ("user_cnt", C.c_int32), ("batch_stage", _p)]
+                ("user_cnt", C.c_int32), ("two_stage", C.c_int32), ("Dc", C.c_int32), ("De", C.c_int32),
+                ("ec", C.c_int32), ("ee", C.c_int32), ("bias_neg_scale", C.c_float), ("Ec", _p), ("mEc", _p), ("vEc", _p),
+                ("Ee", _p), ("mEe", _p), ("vEe", _p), ("E2", _p), ("mE2", _p), ("vE2", _p), ("gf_scratch", _p),
+                ("batch_stage", _p)]
 
 
 class FvxShardWs(C.Structure):

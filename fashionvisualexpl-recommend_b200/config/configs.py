@@ -37,6 +37,14 @@ def cnn_features_path(dataset, cnn_model, output_layer):   # configs.py:17
     return _data(dataset, "original", "cnn_features_%s_%s.npy" % (cnn_model, output_layer))
 
 
+def edge_features_path(dataset, cnn_model, output_layer):  # configs.py:20
+    return _data(dataset, "original", "edge_features_%s_%s.npy" % (cnn_model, output_layer))
+
+
+def hist_color_features_path(dataset):                     # configs.py:24
+    return _data(dataset, "original", "features", "histograms.npy")
+
+
 def weight_dir():                  # configs.py:32
     return _ROOTS["results"] + "/rec_model_weights"
 

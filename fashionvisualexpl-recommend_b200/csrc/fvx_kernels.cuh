@@ -83,6 +83,8 @@ int fvx_launch_score_grad(const FvxModel* m, const int32_t* user, int B, int los
 // switches of the step (environment: FVX_STEP_DEDUP; test hook fvx_debug_set_dedup)
 bool fvx_dedup_enabled();
 bool fvx_merged_update(const FvxModel* m);   // DEFERRED mode without the row-update kernel
+// GradFashion: E = blockdiag(Ec, Ee) * E2 (the effective [D, de] projection matrix; ahead of anything that projects)
+int fvx_launch_gf_compose(const FvxModel* m, cudaStream_t st);
 // W_sum -> bf16 planes of the listed rows (unique-row step)
 int fvx_launch_w_planes(const FvxModel* m, int B, cudaStream_t st);
 

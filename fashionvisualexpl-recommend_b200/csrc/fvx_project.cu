@@ -235,6 +235,9 @@ static int project_any(const FvxModel* m, const int32_t* rows, int row0, int64_t
 int fvx_project(const FvxModel* model, float* theta_ext, fvx_stream_t stream) {
   FVX_CHECK_ARG(model && model->abi_version == FVX_ABI_VERSION, "fvx_project: bad model");
   FVX_CHECK_ARG(model->D > 0 && model->E && theta_ext, "fvx_project: model has no visual part");
+  if (model->two_stage) {                       // GradFashion: E is composed from Ec, Ee, E2 first
+    if (int rc = fvx_launch_gf_compose(model, fvx_cu(stream))) return rc;
+  }
   return project_any(model, nullptr, 0, model->item_cnt, theta_ext, fvx_cu(stream));
 }
 
@@ -244,6 +247,9 @@ int fvx_project_rows(const FvxModel* model, const int32_t* rows, int64_t nrows, 
   FVX_CHECK_ARG(model && model->abi_version == FVX_ABI_VERSION, "fvx_project_rows: bad model");
   FVX_CHECK_ARG(model->D > 0 && model->E && rows && out, "fvx_project_rows: bad arguments");
   FVX_CHECK_ARG(nrows >= 0 && nrows <= 2LL * model->max_batch, "fvx_project_rows: nrows outside [0, 2*max_batch]");
+  if (model->two_stage) {
+    if (int rc = fvx_launch_gf_compose(model, fvx_cu(stream))) return rc;
+  }
   return project_any(model, rows, 0, nrows, out, fvx_cu(stream));
 }
 

@@ -382,7 +382,7 @@ k_score_grad(FvxModel M, const int32_t* __restrict__ user, int B, int loss_slot,
     const float z = -fminf(fmaxf(xs, FVX_CLIP_LO), FVX_CLIP_HI);
     const float sp = z > 13.942385f ? z : (z < -13.942385f ? expf(z) : log1pf(expf(z)));
     if (lane == 0) loss_acc += (double)sp + (double)(reg * sqs) + (double)(reg * bi * bi) +
-                               (double)(reg * bj * bj / 10.0f);
+                               (double)(reg * bj * bj * M.bias_neg_scale);
     float* gu = M.users.g + (size_t)u * Su;
     float* ggi = M.items.g + (size_t)li * Si;
     float* ggj = M.items.g + (size_t)lj * Si;
@@ -398,7 +398,7 @@ k_score_grad(FvxModel M, const int32_t* __restrict__ user, int B, int loss_slot,
     }
     if (lane == 0) {
       fvx_red_add(ggi + K, coef + reg2 * bi);
-      fvx_red_add(ggj + K, -coef + (reg2 / 10.0f) * bj);
+      fvx_red_add(ggj + K, -coef + (reg2 * M.bias_neg_scale) * bj);
     }
     if (vis) {
       const int nw_ = wnp > 0 ? wnp : de;
@@ -596,7 +596,7 @@ k_score_grad_v4(FvxModel M, const int32_t* __restrict__ user, int B, int loss_sl
       const float z = -fminf(fmaxf(xs, FVX_CLIP_LO), FVX_CLIP_HI);
       const float sp = z > 13.942385f ? z : (z < -13.942385f ? expf(z) : log1pf(expf(z)));
       if (sub == 0) loss_acc += (double)sp + (double)(reg * sqs) + (double)(reg * bi * bi) +
-                                (double)(reg * bj * bj / 10.0f);
+                                (double)(reg * bj * bj * M.bias_neg_scale);
       float* gu = M.users.g + (size_t)u * Su;
       float* ggi = M.items.g + (size_t)li * Si;
       float* ggj = M.items.g + (size_t)lj * Si;
@@ -624,7 +624,7 @@ k_score_grad_v4(FvxModel M, const int32_t* __restrict__ user, int B, int loss_sl
       }
       if (sub == 0) {
         fvx_red_add(ggi + K, coef + reg2 * bi);
-        fvx_red_add(ggj + K, -coef + (reg2 / 10.0f) * bj);
+        fvx_red_add(ggj + K, -coef + (reg2 * M.bias_neg_scale) * bj);
       }
     }
     if (vis && live && !(DEDUP && dead)) {
@@ -718,6 +718,7 @@ struct UpdParams {
   const float* loss_pair;   // sharded step: n_tails x {hi, lo, overflow flag, -}: the loss shares of the ranks (all-reduced
                             //   into one tail, or one tail per rank)
   int n_tails;
+  int skip_E;           // GradFashion: E is a composed scratch matrix - its Adam step happens in k_gf_adam
 };
 
 __device__ __forceinline__ void adam4(float4& w, float4& m, float4& v, const float4 g, float a) {
@@ -775,7 +776,7 @@ k_update(FvxModel M, UpdParams U) {
   } else {
     // dense Adam on E_ext [D,de]: gradient = sum of the row-group partials + 2*reg*E
     // (VBPR.py:129 puts reg*(|E|^2+|Bp|^2) into the loss); adds that loss term as well.
-    const int n = M.D * M.de;
+    const int n = U.skip_E ? 0 : M.D * M.de;
     const float reg = M.reg;
     float sq = 0.0f;
     for (int i = (b - U.nb_u - U.nb_i) * blockDim.x + threadIdx.x; i < n; i += U.nb_e * blockDim.x) {
@@ -838,6 +839,103 @@ k_update(FvxModel M, UpdParams U) {
 }
 
 // ---------------------------------------------------------------------------------
+// GradFashion (GradFashion.py:97-134): theta_ext = F * Eff with Eff = blockdiag(Ec, Ee) * E2, F = [Fc | Fe].
+// k_gf_compose builds Eff into M.E ahead of the step; after grad_E, k_gf_grads turns the gradient of Eff (the
+// row-group partials) into the gradients of Ec, Ee, E2 (+ 2 reg w, GradFashion.py:173-176) and k_gf_adam applies
+// Keras-Adam to the three tensors and adds their L2 loss term.
+__global__ void k_gf_compose(FvxModel M) {
+  const int n = M.D * M.de, ecee = M.ec + M.ee;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int f = i / M.de, c = i - f * M.de;
+    float s = 0.0f;
+    if (c <= M.d) {
+      if (f < M.Dc) { for (int r = 0; r < M.ec; ++r) s = fmaf(M.Ec[(size_t)f * M.ec + r], M.E2[(size_t)r * M.de + c], s); }
+      else { for (int r = 0; r < M.ee; ++r) s = fmaf(M.Ee[(size_t)(f - M.Dc) * M.ee + r], M.E2[(size_t)(M.ec + r) * M.de + c], s); }
+    }
+    (void)ecee;
+    M.E[i] = s;
+  }
+}
+// scratch layout: gEff [D*de] | gEc [Dc*ec] | gEe [De*ee] | gE2 [(ec+ee)*de]
+__global__ void k_gf_reduce(FvxModel M, int parts, int gnp) {
+  const int n = M.D * M.de;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int f = i / M.de, c = i - f * M.de;
+    float g = 0.0f;
+    for (int p = 0; p < parts; ++p) g += M.gE_part[((size_t)p * M.D + f) * gnp + c];
+    M.gf_scratch[i] = g;
+  }
+}
+__global__ void k_gf_grads(FvxModel M) {
+  const float* gEff = M.gf_scratch;
+  float* gEc = M.gf_scratch + (size_t)M.D * M.de;
+  float* gEe = gEc + (size_t)M.Dc * M.ec;
+  float* gE2 = gEe + (size_t)M.De * M.ee;
+  const float reg2 = 2.0f * M.reg;
+  const int nEc = M.Dc * M.ec, nEe = M.De * M.ee, nE2 = (M.ec + M.ee) * M.de;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nEc + nEe + nE2; i += gridDim.x * blockDim.x) {
+    if (i < nEc) {                     // dEc[f, r] = sum_c gEff[f, c] * E2[r, c]
+      const int f = i / M.ec, r = i - f * M.ec;
+      float g = 0.0f;
+      for (int c = 0; c <= M.d; ++c) g = fmaf(gEff[(size_t)f * M.de + c], M.E2[(size_t)r * M.de + c], g);
+      gEc[i] = g + reg2 * M.Ec[i];
+    } else if (i < nEc + nEe) {        // dEe[f, r] = sum_c gEff[Dc + f, c] * E2[ec + r, c]
+      const int j = i - nEc, f = j / M.ee, r = j - f * M.ee;
+      float g = 0.0f;
+      for (int c = 0; c <= M.d; ++c) g = fmaf(gEff[(size_t)(M.Dc + f) * M.de + c], M.E2[(size_t)(M.ec + r) * M.de + c], g);
+      gEe[j] = g + reg2 * M.Ee[j];
+    } else {                           // dE2[r, c] = sum_f Mblock[f, r] * gEff[f, c]
+      const int j = i - nEc - nEe, r = j / M.de, c = j - r * M.de;
+      float g = 0.0f;
+      if (c <= M.d) {
+        if (r < M.ec) { for (int f = 0; f < M.Dc; ++f) g = fmaf(M.Ec[(size_t)f * M.ec + r], gEff[(size_t)f * M.de + c], g); }
+        else { for (int f = 0; f < M.De; ++f) g = fmaf(M.Ee[(size_t)f * M.ee + (r - M.ec)], gEff[(size_t)(M.Dc + f) * M.de + c], g); }
+        g += reg2 * M.E2[j];
+      }
+      gE2[j] = g;
+    }
+  }
+}
+__global__ void k_gf_adam(FvxModel M, int loss_slot) {
+  const long long t = *M.step + 1;
+  const float a = fvx_alpha(M.lr, t);
+  const float* gEc = M.gf_scratch + (size_t)M.D * M.de;
+  const float* gEe = gEc + (size_t)M.Dc * M.ec;
+  const float* gE2 = gEe + (size_t)M.De * M.ee;
+  const int nEc = M.Dc * M.ec, nEe = M.De * M.ee, nE2 = (M.ec + M.ee) * M.de;
+  float sq = 0.0f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nEc + nEe + nE2; i += gridDim.x * blockDim.x) {
+    float *w, *m, *v;
+    float g;
+    if (i < nEc) { w = M.Ec + i; m = M.mEc + i; v = M.vEc + i; g = gEc[i]; }
+    else if (i < nEc + nEe) { const int j = i - nEc; w = M.Ee + j; m = M.mEe + j; v = M.vEe + j; g = gEe[j]; }
+    else { const int j = i - nEc - nEe; w = M.E2 + j; m = M.mE2 + j; v = M.vE2 + j; g = gE2[j]; }
+    const float w0 = *w;
+    sq += w0 * w0;
+    const float mn = FVX_BETA1 * *m + (1.0f - FVX_BETA1) * g;
+    const float vn = FVX_BETA2 * *v + (1.0f - FVX_BETA2) * (g * g);
+    *m = mn; *v = vn;
+    *w = w0 - a * mn / (sqrtf(vn) + FVX_EPS);
+  }
+  sq = fvx_warp_sum(sq);
+  if ((threadIdx.x & 31) == 0 && sq != 0.0f && loss_slot >= 0) atomicAdd(M.loss + loss_slot, (double)(M.reg * sq));
+}
+int fvx_launch_gf_compose(const FvxModel* m, cudaStream_t st) {
+  k_gf_compose<<<(m->D * m->de + 255) / 256, 256, 0, st>>>(*m);
+  FVX_CHECK_LAUNCH("k_gf_compose");
+  return 0;
+}
+// gradient of the effective matrix (row-group partials, pitch gnp) -> Adam on Ec, Ee, E2; before the step counter moves
+static int gf_backward(const FvxModel* m, int parts, int gnp, int loss_slot, cudaStream_t st) {
+  k_gf_reduce<<<(m->D * m->de + 255) / 256, 256, 0, st>>>(*m, parts, gnp);
+  const int n = m->Dc * m->ec + m->De * m->ee + (m->ec + m->ee) * m->de;
+  k_gf_grads<<<(n + 127) / 128, 128, 0, st>>>(*m);
+  k_gf_adam<<<(n + 255) / 256, 256, 0, st>>>(*m, loss_slot);
+  FVX_CHECK_LAUNCH("k_gf_backward");
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
 static int check_model(const FvxModel* m, const char* who) {
   FVX_CHECK_ARG(m != nullptr, "%s: null model", who);
   FVX_CHECK_ARG(m->abi_version == FVX_ABI_VERSION, "%s: FvxModel.abi_version %d != %d", who, m->abi_version,
@@ -852,6 +950,10 @@ static int check_model(const FvxModel* m, const char* who) {
   if (m->D > 0) {
     FVX_CHECK_ARG(m->d > 0 && m->de % 4 == 0 && m->de >= m->d + 1, "%s: bad de", who);
     FVX_CHECK_ARG(m->E && (m->F || (m->use_tensor_cores && m->F_pl)), "%s: VBPR needs E and F", who);
+    if (m->two_stage)
+      FVX_CHECK_ARG(m->Dc > 0 && m->De > 0 && m->Dc + m->De == m->D && m->ec > 0 && m->ee > 0 && m->Ec && m->Ee && m->E2 &&
+                    m->mEc && m->vEc && m->mEe && m->vEe && m->mE2 && m->vE2 && m->gf_scratch,
+                    "%s: GradFashion (two_stage) needs Ec, Ee, E2, their Adam moments and the scratch", who);
   }
   return 0;
 }
@@ -958,7 +1060,7 @@ int fvx_launch_update(const FvxModel* m, int B, int parts, int gnp, const float*
   if (what == FVX_UPD_TABLES) U.nb_e = 0;
   if (what == FVX_UPD_E) { U.nb_u = 0; U.nb_i = 0; if (U.nb_e == 0) U.nb_e = 1; }
   U.finalize = what != FVX_UPD_TABLES;
-  U.parts = parts; U.gnp = gnp; U.loss_slot = loss_slot; U.sync = m->sync; U.gE_src = gE_src; U.loss_pair = loss_pair; U.n_tails = n_tails;
+  U.parts = parts; U.gnp = gnp; U.loss_slot = loss_slot; U.sync = m->sync; U.gE_src = gE_src; U.loss_pair = loss_pair; U.n_tails = n_tails; U.skip_E = m->two_stage ? 1 : 0;
   if (loss_pair && U.nb_e == 0) U.nb_e = 1;
   k_update<<<U.nb_u + U.nb_i + U.nb_e, 256, 0, st>>>(*m, U);
   FVX_CHECK_LAUNCH("k_update");
@@ -1071,6 +1173,9 @@ enum { PH_PREP = 0, PH_PROJECT, PH_SCORE_GRAD, PH_GRAD_E, PH_UPDATE, PH_COUNT };
 // kernel less per step; DENSE / LAZY keep the row update (k_update, tables part).
 bool fvx_merged_update(const FvxModel* m) { return m->adam_mode == FVX_ADAM_DEFERRED; }
 static int step_update(const FvxModel* m, int B, int parts, int gnp, int loss_slot, cudaStream_t st, int what) {
+  if (m->two_stage && what != FVX_UPD_TABLES) {
+    if (int rc = gf_backward(m, parts, gnp, loss_slot, st)) return rc;
+  }
   if (fvx_merged_update(m)) {
     if (what == FVX_UPD_TABLES) return 0;
     what = FVX_UPD_E;
@@ -1107,6 +1212,9 @@ static int bpr_step_impl(const FvxModel* model, const int32_t* user, const int32
     FVX_CHECK_ARG(2LL * B * M.de <= M.th_cap, "fvx_bpr_step: TH scratch too small");
   }
 #define PHASE(i) do { if (ev) cudaEventRecord(ev[i], st); } while (0)
+  if (M.two_stage) {
+    if (int rc = fvx_launch_gf_compose(&M, st)) return rc;   // the effective projection matrix of this step
+  }
 
   // Two-stream schedule (VBPR): the claims + deferred-Adam catch-up touch only the embedding tables and run
   // BESIDE the projection; in DENSE / LAZY mode the Adam update of the touched rows runs beside grad_E.  The

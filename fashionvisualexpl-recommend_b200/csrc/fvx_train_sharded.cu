@@ -239,7 +239,7 @@ k_grads_owned(FvxModel M, const int32_t* __restrict__ user, int B, int loss_slot
           if (!side) sq += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
         }
         bi = M.items.w[(size_t)li * Si + K];
-        if (sub == 0) fvx_red_add(gg + K, cs + (side == 0 ? reg2 : reg2 / 10.0f) * bi);
+        if (sub == 0) fvx_red_add(gg + K, cs + (side == 0 ? reg2 : reg2 * M.bias_neg_scale) * bi);
         if (vis) {
           for (int c = sub; c < nw4; c += 16) {
             const int n0 = 4 * c;
@@ -279,7 +279,7 @@ k_grads_owned(FvxModel M, const int32_t* __restrict__ user, int B, int loss_slot
     }
     const float sqs = ss_half_sum(sq);
     if (live && sub == 0) {
-      loss_acc += (double)(reg * sqs) + (double)(reg * bi * bi / (side == 0 ? 1.0f : 10.0f));
+      loss_acc += (double)(reg * sqs) + (double)(reg * bi * bi * (side == 0 ? 1.0f : M.bias_neg_scale));
       if (side == 0) {
         const float z = -fminf(fmaxf(xs, FVX_CLIP_LO), FVX_CLIP_HI);
         loss_acc += (double)(z > 13.942385f ? z : (z < -13.942385f ? expf(z) : log1pf(expf(z))));
@@ -731,6 +731,7 @@ static int sharded_common(const FvxModel* m, const FvxShardWs* ws, const int32_t
   FVX_CHECK_ARG(m->users.list_cap >= B && m->items.list_cap >= 2 * B, "%s: touched-row lists too small", who);
   FVX_CHECK_ARG(m->rows && m->loss && m->sync && m->cmap, "%s: null scratch (rows / loss / sync / cmap)", who);
   FVX_CHECK_ARG(m->K % 4 == 0, "%s: the sharded step needs embed_k %% 4 == 0 (got %d)", who, m->K);
+  FVX_CHECK_ARG(!m->two_stage, "%s: GradFashion (two_stage) runs on one GPU", who);
   FVX_CHECK_ARG(ws && ws->S && ws->run_id && ws->run_scratch && ws->WU && ws->RU && ws->dE && ws->loss_part &&
                 ws->run_cap >= 1 && ws->owners >= 1 && ws->max_runs == ws->owners * ws->run_cap && ws->users_per_owner >= 1,
                 "%s: incomplete FvxShardWs", who);

@@ -31,10 +31,14 @@ class Engine:
     def __init__(self, num_users, num_items, K, d=0, D=0, lr=1e-3, reg=0.0, adam_mode="deferred",
                  max_batch=4096, device="cuda:0", item_lo=0, item_cnt=None, loss_slots=4096,
                  ge_parts=80, seed=0, use_tensor_cores=False, unique_rows=True, user_lo=0, user_cnt=None,
-                 user_rows=None, sharded=False):
+                 user_rows=None, sharded=False, two_stage=None):
         """``item_lo / item_cnt``: the catalog rows this rank owns; ``user_lo / user_cnt``: the users it owns (their
         Adam state lives here; the user tables are still allocated and indexed globally - ``user_rows`` rows, at
-        least ``num_users``, so that equal-sized blocks can be gathered in place)."""
+        least ``num_users``, so that equal-sized blocks can be gathered in place).
+
+        ``two_stage=(Dc, De, ec, ee)``: GradFashion (GradFashion.py:97-134) - the features are ``[Fc | Fe]`` (D = Dc +
+        De) and the trained visual tensors are Ec [Dc, ec], Ee [De, ee], E [ec + ee, d], Bp [ec + ee, 1]; the
+        negative item's bias enters the L2 term with weight 1 instead of VBPR's 1/10."""
         if not torch.cuda.is_available():
             raise _lib.FvxError("no CUDA device: the fvx engine has no CPU path")
         _lib.load()
@@ -124,6 +128,17 @@ class Engine:
         else:
             self.E = self.mE = self.vE = self.gE_part = self.TH = self.W = None
             self.ge_parts = 0
+        self.two_stage = tuple(int(x) for x in two_stage) if two_stage else None
+        self.bias_neg_scale = 1.0 if self.two_stage else 0.1
+        if self.two_stage:
+            Dc, De, ec, ee = self.two_stage
+            if Dc + De != self.D or min(Dc, De, ec, ee) <= 0:
+                raise ValueError("two_stage=(Dc, De, ec, ee) must satisfy Dc + De == D")
+            self.gf = {}
+            for name, shape in (("Ec", (Dc, ec)), ("Ee", (De, ee)), ("E2", (ec + ee, self.de))):
+                for pre in ("", "m", "v"):
+                    self.gf[pre + name] = torch.zeros(*shape, **f32)
+            self.gf_scratch = torch.zeros(self.D * self.de + Dc * ec + De * ee + (ec + ee) * self.de, **f32)
         self._theta = None
         self._theta_step = -1
         self.init_glorot(seed)
@@ -164,6 +179,13 @@ class Engine:
             self.E.zero_()
             self.E[:, :self.d] = glorot(gen(4), self.D, self.d, self.D, self.d)
             self.E[:, self.d:self.d + 1] = glorot(gen(5), self.D, 1, self.D, 1)
+            if self.two_stage:                              # GradFashion.py:60-80: Ec, Ee, E [ec+ee, d], Bp [ec+ee, 1]
+                Dc, De, ec, ee = self.two_stage
+                self.gf["Ec"].copy_(glorot(gen(6), Dc, ec, Dc, ec))
+                self.gf["Ee"].copy_(glorot(gen(7), De, ee, De, ee))
+                self.gf["E2"].zero_()
+                self.gf["E2"][:, :self.d] = glorot(gen(4), ec + ee, self.d, ec + ee, self.d)
+                self.gf["E2"][:, self.d:self.d + 1] = glorot(gen(5), ec + ee, 1, ec + ee, 1)
 
     # reference attribute names as views into the packed tables
     @property
@@ -190,15 +212,24 @@ class Engine:
         self.Bi.copy_(dv(P["Bi"])[lo:hi])
         if self.D:
             self.Tu.copy_(dv(P["Tu"]))
-            self.Ew.copy_(dv(P["E"]))
-            self.Bp.copy_(dv(P["Bp"]).reshape(self.D, 1))
+            if self.two_stage:
+                self.gf["Ec"].copy_(dv(P["Ec"]))
+                self.gf["Ee"].copy_(dv(P["Ee"]))
+                self.gf["E2"][:, :self.d].copy_(dv(P["E"]))
+                self.gf["E2"][:, self.d:self.d + 1].copy_(dv(P["Bp"]).reshape(-1, 1))
+            else:
+                self.Ew.copy_(dv(P["E"]))
+                self.Bp.copy_(dv(P["Bp"]).reshape(self.D, 1))
         self._theta_step = -1
 
     def params(self):
         """Flushes deferred optimiser state and returns the parameters as numpy arrays."""
         self.flush()
         out = {"Gu": self.Gu, "Gi": self.Gi, "Bi": self.Bi}
-        if self.D:
+        if self.D and self.two_stage:
+            out.update({"Tu": self.Tu, "Ec": self.gf["Ec"], "Ee": self.gf["Ee"], "E": self.gf["E2"][:, :self.d],
+                        "Bp": self.gf["E2"][:, self.d:self.d + 1]})
+        elif self.D:
             out.update({"Tu": self.Tu, "E": self.Ew, "Bp": self.Bp})
         return {k: v.detach().cpu().numpy().copy() for k, v in out.items()}
 
@@ -248,6 +279,15 @@ class Engine:
             m.use_tensor_cores = 1 if self.use_tensor_cores else 0
             m.upos, m.W_sum, m.uslot = ptr(self.upos_t), ptr(self.W_sum), ptr(self.uslot_t)
             m.batch_stage = ptr(self.stage_t)
+            m.bias_neg_scale = self.bias_neg_scale
+            if self.two_stage:
+                m.two_stage = 1
+                m.Dc, m.De, m.ec, m.ee = self.two_stage
+                g = self.gf
+                m.Ec, m.mEc, m.vEc = ptr(g["Ec"]), ptr(g["mEc"]), ptr(g["vEc"])
+                m.Ee, m.mEe, m.vEe = ptr(g["Ee"]), ptr(g["mEe"]), ptr(g["vEe"])
+                m.E2, m.mE2, m.vE2 = ptr(g["E2"]), ptr(g["mE2"]), ptr(g["vE2"])
+                m.gf_scratch = ptr(self.gf_scratch)
             self._struct = m
         return self._struct
 

@@ -1,6 +1,6 @@
 """Command-line driver: the flag surface of the reference's src/train_rec.py (:17-46 - same names,
 same defaults, same per-regulariser loop and console block), for the models on the hot path
-(``--rec bprmf | vbpr``).
+(``--rec bprmf | vbpr | gradfashion``).
 
     cd src && python -m fvx.train_rec --dataset amazon_men --rec vbpr --gpu 0 ...
 
@@ -39,6 +39,10 @@ REFERENCE_FLAGS = (
     ("embed_k", int, 128, {}),
     ("embed_d", int, 20, {}),
     ("reg", float, 0, {}),
+    # GradFashion.py:30-31 reads these two; the reference's own parser never defines them (its --rec gradfashion run
+    # fails with AttributeError): added here with the sizes of its experiments' defaults
+    ("embed_color", int, 8, {}),
+    ("embed_edges", int, 8, {}),
 )
 ENGINE_FLAGS = (
     ("adam_mode", None, "auto", {"choices": ["auto", "deferred", "dense", "lazy"]}),
@@ -63,8 +67,9 @@ def parse_args(argv=None):
 
 def _model_class(rec):
     from .recommender.models.BPRMF import BPRMF
+    from .recommender.models.GradFashion import GradFashion
     from .recommender.models.VBPR import VBPR
-    table = {"bprmf": BPRMF, "vbpr": VBPR}
+    table = {"bprmf": BPRMF, "vbpr": VBPR, "gradfashion": GradFashion}
     if rec not in table:
         raise NotImplementedError('Not implemented or unknown Recommender Model.')
     return table[rec]

@@ -30,7 +30,7 @@ extern "C" {
 
 typedef void* fvx_stream_t; /* cudaStream_t */
 
-#define FVX_ABI_VERSION 4
+#define FVX_ABI_VERSION 5
 
 /* Adam semantics.  The reference's Keras Adam moves
  * EVERY row of an embedding table on every step (rows without gradient keep
@@ -124,6 +124,19 @@ typedef struct FvxModel {
                            and indexed globally on every rank, but only the owner keeps a user's Adam state
                            (m, v, g, last) and its authoritative row; other ranks' copies of w are stale until
                            the rows are gathered (evaluation, checkpoint)                                      */
+  /* GradFashion (two_stage != 0; src/recommender/models/GradFashion.py:97-134): the item's visual feature is a
+   * learned projection of two descriptors, v_i = [Fc[i] Ec | Fe[i] Ee], and theta_i = v_i E, vbias_i = v_i Bp.
+   * With F = [Fc | Fe] (D = Dc + De) that is theta_ext = F * (blockdiag(Ec, Ee) * E2): every step composes the
+   * effective [D, de] matrix into `E` (scratch here), runs the VBPR kernels on it, and carries the gradient of the
+   * effective matrix back to Ec, Ee and E2 = [E | Bp] ([ec + ee, de]), which are the trained tensors. */
+  int32_t two_stage;
+  int32_t Dc, De, ec, ee;     /* feature dims of the colour / edge descriptors, embed_color, embed_edges */
+  float bias_neg_scale;       /* weight of the NEGATIVE item's bias in the L2 term: 0.1 (BPRMF.py:110, VBPR.py:125:
+                                 beta_neg / 10) or 1.0 (GradFashion.py:171-172)                              */
+  float *Ec, *mEc, *vEc;      /* [Dc, ec] + Adam moments */
+  float *Ee, *mEe, *vEe;      /* [De, ee] */
+  float *E2, *mE2, *vE2;      /* [ec + ee, de]: cols [0, d) = E, col d = Bp */
+  float* gf_scratch;          /* [D*de + Dc*ec + De*ee + (ec+ee)*de] gradients of one step */
   int32_t* batch_stage; /* [3*max_batch + 4] staging area of fvx_bpr_steps: the (user | pos | neg) indices of
                            the batch in flight and the 64-bit batch cursor (may be NULL otherwise)     */
 } FvxModel;

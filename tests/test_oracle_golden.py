@@ -164,3 +164,34 @@ def test_gradfashion_oracle_matches_reference_model_code():
         lm = gf.loss_and_grads(P64, b, reg, Fc.astype(np.float64), Fe.astype(np.float64))[0]
         P64[k][idx] = old
         assert G[k][idx] == pytest.approx((lp - lm) / (2 * h), rel=1e-5, abs=1e-8), (k, idx)
+
+
+def _evaluator_random():
+    g = golden("evaluator_random.npz")
+    U = len(g["train_ptr"]) - 1
+
+    def lists(ptr, col):
+        return [col[ptr[u]:ptr[u + 1]].tolist() for u in range(U)]
+    return g, U, lists(g["train_ptr"], g["train_col"]), lists(g["val_ptr"], g["val_col"]), lists(g["test_ptr"], g["test_col"])
+
+
+def test_oracle_eval_by_user_matches_reference_on_random_model():
+    """oracle.evaluator.eval_by_user against the reference's own _eval_by_user (fixture generated by
+    tests/golden/make_golden_evaluator_random.py): 2 000 users, exact ties from duplicated items, 0 / 1 / 3 held-out
+    items - every user, every metric."""
+    g, U, tr, va, te = _evaluator_random()
+    Gu, Gi, Bi, k = g["Gu"], g["Gi"], g["Bi"], int(g["k"])
+    I = Gi.shape[0]
+    scores = (Bi[None, :].astype(np.float64) + Gu.astype(np.float64) @ Gi.astype(np.float64).T).astype(np.float32)
+    _, first = np.unique(np.concatenate([Gi, Bi[:, None]], 1), axis=0, return_index=True)   # duplicates score identically
+    rep = {tuple(np.concatenate([Gi[i], Bi[i:i + 1]])): i for i in sorted(first)}
+    for i in range(I):
+        scores[:, i] = scores[:, rep[tuple(np.concatenate([Gi[i], Bi[i:i + 1]]))]]
+    for name, held in (("metrics_v", va), ("metrics_t", te)):
+        want = g[name]
+        for u in range(U):
+            got = evaluator.eval_by_user(scores[u], I, tr[u], held[u], k)
+            if not held[u]:
+                assert got == () and np.isnan(want[u, 0])
+            else:
+                assert np.allclose(got, want[u], rtol=0, atol=1e-12), (name, u, got, want[u])
