@@ -301,11 +301,19 @@ def parity_full(e, data, F_host, reg, lr, dev, top_k, n_steps=3, n_eval_users=25
     st = data.device_state(str(dev))
     ids, sc = e.score_topk(st["row_ptr"], st["col_sorted"], top_k)
     ids, sc = ids[torch.as_tensor(users, device=dev)].cpu().numpy(), sc[torch.as_tensor(users, device=dev)].cpu().numpy()
-    Sc = bpr.predict_all(P, F64, users=users)
+    # (the evaluation kernels are checked on the parameters the GPU holds: after Adam steps of size lr on weights of
+    # size ~1e-2, a gradient at rounding-noise level moves a weight differently in fp32 and fp64 - the training
+    # arithmetic is pinned by the losses above and by tests/)
+    Pg = {k: v.astype(np.float64) for k, v in e.params().items()}
+    Sc = bpr.predict_all(Pg, F64, users=users)
     tr = [data.training_list[int(u)] for u in users]
     o_ids, o_sc = oe.masked_topk(Sc, tr, top_k)
     for j in range(len(users)):
-        ok, msg = oe.topk_matches(ids[j], sc[j], o_ids[j], o_sc[j])
+        # scores: <= 1e-4 of the row's score scale (north_star; SURVEY 8(c): per tensor, absolute floor 1e-7); ids:
+        # equal wherever the oracle's scores are not tied within 1e-5
+        scale = max(float(np.max(np.abs(Sc[j]))), 1e-3)
+        assert np.max(np.abs(sc[j].astype(np.float64) - o_sc[j])) <= 1e-4 * scale + 1e-7, ("parity: scores of user %d" % users[j])
+        ok, msg = oe.topk_matches(ids[j], sc[j], o_ids[j], o_sc[j], rel_tol=1e-2)
         assert ok, ("parity: top-%d of user %d" % (top_k, users[j]), msg)
     return {"kind": "full", "what": "%d steps of the timed sampler stream on the run's own tables vs the fp64 oracle (loss <= 1e-4 "
                                    "rel per step, worst %.2e); masked top-%d of %d users vs the oracle (ids at tie-free scores, "
@@ -361,7 +369,18 @@ def parity_small(world, rank, dev, grp, K, d, D, tc, top_k):
     rp = torch.as_tensor(np.arange(U + 1) * 6, dtype=torch.int64).to(dev)
     cs = torch.as_tensor(np.array(tr).reshape(-1), dtype=torch.int32).to(dev)
     k = min(top_k, 100)
-    o_ids, o_sc = oe.masked_topk(bpr.predict_all(Q, F64), tr, k)
+    Pg = {}
+    for name in Q:                                                # the model as the GPUs hold it, assembled
+        t = torch.as_tensor(R_[name]).to(dev)
+        if world > 1 and name in ("Gi", "Bi"):
+            cnts = [parallel.shard_bounds(I, world, r)[1] for r in range(world)]
+            pad = torch.zeros((max(cnts),) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
+            pad[:t.shape[0]] = t
+            outs = [torch.zeros_like(pad) for _ in range(world)]
+            dist.all_gather(outs, pad)
+            t = torch.cat([o[:c] for o, c in zip(outs, cnts)])
+        Pg[name] = t.cpu().numpy().astype(np.float64)
+    o_ids, o_sc = oe.masked_topk(bpr.predict_all(Pg, F64), tr, k)
     if world > 1:
         ids, sc = parallel.sharded_topk([e], grp, rp, cs, k)[0]
         per, _ = parallel.user_slices(U, world)
@@ -371,7 +390,9 @@ def parity_small(world, rank, dev, grp, K, d, D, tc, top_k):
         per, u0 = U, 0
     ids, sc = ids.cpu().numpy(), sc.cpu().numpy()
     for j in range(0, min(per, U - u0), 7):
-        ok, msg = oe.topk_matches(ids[j], sc[j], o_ids[u0 + j], o_sc[u0 + j])
+        scale = max(float(np.max(np.abs(o_sc[u0 + j]))), 1e-3)
+        assert np.max(np.abs(sc[j].astype(np.float64) - o_sc[u0 + j])) <= 1e-4 * scale + 1e-7, ("parity: scores", u0 + j, rank)
+        ok, msg = oe.topk_matches(ids[j], sc[j], o_ids[u0 + j], o_sc[u0 + j], rel_tol=1e-2)
         assert ok, ("parity: top-k of user %d on rank %d" % (u0 + j, rank), msg)
     if world > 1:
         t = torch.tensor([worst], device=dev)
