@@ -138,15 +138,21 @@ int fvx_comm_arena(FvxComm* c, int64_t bytes, void** local_out) {
     cudaFree(c->arena);
     c->arena = nullptr;
   }
+  // a rank whose allocation or export fails still takes part in the exchange (with ok = 0), so that every rank
+  // leaves this call with the same verdict instead of waiting in the collective for the one that gave up
+  struct Slot { cudaIpcMemHandle_t h; int32_t ok, pad[3]; };
+  static_assert(sizeof(Slot) % 4 == 0, "slot size");
+  Slot mine;
+  memset(&mine, 0, sizeof(mine));
   void* base = nullptr;
-  if (cudaMalloc(&base, (size_t)bytes) != cudaSuccess)
-    FVX_FAIL(-3, "fvx_comm_arena: cudaMalloc(%lld) failed: %s", (long long)bytes, cudaGetErrorString(cudaGetLastError()));
-  cudaMemset(base, 0, (size_t)bytes);
-  cudaIpcMemHandle_t mine;
-  if (cudaIpcGetMemHandle(&mine, base) != cudaSuccess)
-    FVX_FAIL(-3, "fvx_comm_arena: cudaIpcGetMemHandle failed: %s", cudaGetErrorString(cudaGetLastError()));
-  static_assert(sizeof(cudaIpcMemHandle_t) % 4 == 0, "handle size");
-  const size_t hs = sizeof(cudaIpcMemHandle_t);
+  const char* why = nullptr;
+  if (cudaMalloc(&base, (size_t)bytes) != cudaSuccess) { why = "cudaMalloc"; base = nullptr; }
+  else if (cudaMemset(base, 0, (size_t)bytes) != cudaSuccess) why = "cudaMemset";
+  else if (cudaIpcGetMemHandle(&mine.h, base) != cudaSuccess) why = "cudaIpcGetMemHandle";
+  char why_msg[256] = "";
+  if (why) snprintf(why_msg, sizeof(why_msg), "%s(%lld bytes): %s", why, (long long)bytes, cudaGetErrorString(cudaGetLastError()));
+  mine.ok = why ? 0 : 1;
+  const size_t hs = sizeof(Slot);
   uint8_t* dev = nullptr;
   if (cudaMalloc(&dev, hs * c->world) != cudaSuccess) FVX_FAIL(-3, "fvx_comm_arena: cudaMalloc failed");
   cudaMemcpy(dev + hs * c->rank, &mine, hs, cudaMemcpyHostToDevice);
@@ -154,14 +160,29 @@ int fvx_comm_arena(FvxComm* c, int64_t bytes, void** local_out) {
            "fvx_comm_arena");
   if (cudaDeviceSynchronize() != cudaSuccess)
     FVX_FAIL(-3, "fvx_comm_arena: handle exchange failed: %s", cudaGetErrorString(cudaGetLastError()));
-  cudaIpcMemHandle_t all[FVX_COMM_MAX_RANKS];
+  Slot all[FVX_COMM_MAX_RANKS];
   cudaMemcpy(all, dev, hs * c->world, cudaMemcpyDeviceToHost);
   cudaFree(dev);
+  for (int r = 0; r < c->world; ++r)
+    if (!all[r].ok) {
+      if (base) cudaFree(base);
+      if (r == c->rank) FVX_FAIL(-3, "fvx_comm_arena: %s", why_msg);
+      FVX_FAIL(-3, "fvx_comm_arena: rank %d could not allocate or export its arena", r);
+    }
+  for (int r = 0; r < c->world; ++r) c->peer[r] = nullptr;
   for (int r = 0; r < c->world; ++r) {
     if (r == c->rank) { c->peer[r] = reinterpret_cast<uint8_t*>(base); continue; }
     void* p = nullptr;
-    if (cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess)
-      FVX_FAIL(-3, "fvx_comm_arena: cannot map the arena of rank %d: %s", r, cudaGetErrorString(cudaGetLastError()));
+    if (cudaIpcOpenMemHandle(&p, all[r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      const cudaError_t e = cudaGetLastError();
+      for (int q = 0; q < r; ++q)
+        if (q != c->rank && c->peer[q]) { cudaIpcCloseMemHandle(c->peer[q]); c->peer[q] = nullptr; }
+      c->peer[c->rank] = nullptr;
+      // (the allocation stays alive until the communicator goes: a peer may have mapped it already)
+      c->arena = reinterpret_cast<uint8_t*>(base);
+      c->arena_bytes = (size_t)bytes;
+      FVX_FAIL(-3, "fvx_comm_arena: cannot map the arena of rank %d: %s", r, cudaGetErrorString(e));
+    }
     c->peer[r] = reinterpret_cast<uint8_t*>(p);
   }
   c->arena = reinterpret_cast<uint8_t*>(base);

@@ -60,6 +60,9 @@ def _sort_rows(row_ptr, col):
     return col[order]
 
 
+_SHARED_STREAMS = {}     # seed -> (random.Random, RandomState) shared by the loaders of this process
+
+
 class DataLoader(object):
     def __init__(self, params, interactions=None):
         """``params``: the argparse namespace of train_rec.py.  ``interactions``: an
@@ -87,9 +90,15 @@ class DataLoader(object):
         self.validation_list = CSRLists(self.val_ptr, self.val_col)
         self.test_list = CSRLists(self.test_ptr, self.test_col)
         self.num_train = int(self.train_ptr[-1])
-        # host_ref streams: seeded like the model modules do at import (BPRMF.py:15-16)
-        self._py_rng = random.Random(self.seed)
-        self._np_rng = np.random.RandomState(self.seed)
+        # host_ref streams: seeded like the model modules do at import (BPRMF.py:15-16).  The reference seeds the
+        # GLOBAL streams once and keeps consuming them from one DataLoader to the next (train_rec.py builds one per
+        # regulariser): ``params.share_sampler_streams`` gives the loaders of one process that one stream pair.
+        if getattr(params, "share_sampler_streams", False):
+            self._py_rng, self._np_rng = _SHARED_STREAMS.setdefault(
+                self.seed, (random.Random(self.seed), np.random.RandomState(self.seed)))
+        else:
+            self._py_rng = random.Random(self.seed)
+            self._np_rng = np.random.RandomState(self.seed)
         self._dev = None
 
     # ---- files (dataset.py:41-81) --------------------------------------------------------

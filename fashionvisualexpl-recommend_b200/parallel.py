@@ -189,25 +189,47 @@ class ShardedStep:
             self.ws.append(t)
         self._comm = group.comm(self.engines[0].device) if isinstance(group, DistGroup) else None
         import os
-        self.transport = transport or os.environ.get("FVX_SHARDED_TRANSPORT") or ("p2p" if self._comm is not None and R > 1 else "nccl")
-        if self.transport == "p2p":
-            if self._comm is None:
-                raise _lib.FvxError("the peer-to-peer transport needs a real process group")
-            # the exchange buffers inside the peer-mapped arena, at the same offsets on every rank
-            e, w = self.engines[0], self.ws[0]["struct"]
-            sizes = (("WU", rows * e.Su * 4), ("S", 2 * B * 4), ("RUin", R * self.run_cap * e.Su * 4),
-                     ("dEall", R * max(e.D * e.de, 1) * 4), ("tails", R * 16), ("flags", 4 * 8 * 4))
-            off, total = {}, 0
-            for name, nbytes in sizes:
-                off[name] = total
-                total += (nbytes + 255) // 256 * 256
-            base = C.c_void_p()
-            with torch.cuda.device(e.device):
-                call("fvx_comm_arena", self._comm, total, C.byref(base))
-            for name, _ in sizes:
-                setattr(w, name, base.value + off[name])
-            w.p2p = 1
-            self.ws[0]["WU"] = self.ws[0]["S"] = None        # (the torch copies are not the ones in use)
+        asked = transport or os.environ.get("FVX_SHARDED_TRANSPORT")
+        self.transport = asked or ("p2p" if self._comm is not None and R > 1 else "nccl")
+        if self.transport == "p2p" and not asked:
+            # the default: every rank tries to map its peers' arenas; unless ALL succeed (CUDA IPC can be refused,
+            # e.g. across containers) every rank takes the NCCL transport - the ranks must agree
+            err = None
+            try:
+                self._map_arena(rows, B, R)
+            except _lib.FvxError as ex:
+                err = ex
+            ok = torch.tensor([0 if err else 1], dtype=torch.int32, device=self.engines[0].device)
+            group.dist.all_reduce(ok, op=group.dist.ReduceOp.MIN, group=group.group)
+            if int(ok.item()) == 0:
+                import sys
+                print("fvx: peer-mapped exchange buffers unavailable (%s); the sharded step uses NCCL collectives"
+                      % (err or "a peer failed"), file=sys.stderr)
+                w = self.ws[0]["struct"]
+                w.p2p = 0
+                for name in ("WU", "S"):
+                    setattr(w, name, ptr(self.ws[0][name]))
+                self.transport = "nccl"
+        elif self.transport == "p2p":
+            self._map_arena(rows, B, R)
+
+    def _map_arena(self, rows, B, R):
+        if self._comm is None:
+            raise _lib.FvxError("the peer-to-peer transport needs a real process group")
+        # the exchange buffers inside the peer-mapped arena, at the same offsets on every rank
+        e, w = self.engines[0], self.ws[0]["struct"]
+        sizes = (("WU", rows * e.Su * 4), ("S", 2 * B * 4), ("RUin", R * self.run_cap * e.Su * 4),
+                 ("dEall", R * max(e.D * e.de, 1) * 4), ("tails", R * 16), ("flags", 4 * 8 * 4))
+        off, total = {}, 0
+        for name, nbytes in sizes:
+            off[name] = total
+            total += (nbytes + 255) // 256 * 256
+        base = C.c_void_p()
+        with torch.cuda.device(e.device):
+            call("fvx_comm_arena", self._comm, total, C.byref(base))
+        for name, _ in sizes:
+            setattr(w, name, base.value + off[name])
+        w.p2p = 1          # (the torch copies of WU and S stay allocated: the NCCL transport uses them)
 
     def step(self, user, pos, neg, loss_slot=0):
         """One optimiser step on every (local) rank; asynchronous."""

@@ -78,8 +78,13 @@ def _model_class(rec):
 def train(argv=None):
     """One full ``model.train()`` per entry of ``--list_of_regs`` (train_rec.py:60-90); returns the
     list of results dicts."""
+    from .dataset import dataset as _dataset
     from .dataset.dataset import DataLoader
     args = parse_args(argv)
+    # the host_ref sampler streams are seeded once per run and consumed across the regulariser iterations, as the
+    # reference's global streams are (BPRMF.py:15-16 seeds at import; dataset.py:83-114 draws from them)
+    _dataset._SHARED_STREAMS.clear()
+    args.share_sampler_streams = True
     configs.set_roots(data=args.data_root, results=args.results_root)
     args.device = "cuda:%d" % max(args.gpu, 0)
     regs = list(args.list_of_regs)

@@ -59,6 +59,24 @@ def test_host_ref_sampler_empty_and_truncated():
     assert (u == full["users"][:len(u)]).all() and (n == full["neg"][:len(u)]).all()
 
 
+def test_host_ref_streams_shared_across_loaders():
+    """train_rec.py builds one DataLoader per regulariser; the reference's global streams (seeded once at import,
+    BPRMF.py:15-16) keep running from one to the next - so do the loaders that share a stream pair."""
+    from fvx.dataset import dataset as ds
+    configs.set_roots(data=GOLDEN)
+    one = DataLoader(tiny_params(epochs=1))
+    first, second = one.all_triple_batches(), one.all_triple_batches()     # one loader, stream consumed twice
+    ds._SHARED_STREAMS.clear()
+    a = DataLoader(tiny_params(epochs=1, share_sampler_streams=True)).all_triple_batches()
+    b = DataLoader(tiny_params(epochs=1, share_sampler_streams=True)).all_triple_batches()
+    ds._SHARED_STREAMS.clear()
+    for x, y in zip(a + b, first + second):
+        assert (x == y).all()
+    assert not (a[0] == b[0]).all() or not (a[2] == b[2]).all()
+    c = DataLoader(tiny_params(epochs=1)).all_triple_batches()            # private streams: the first stream again
+    assert all((x == y).all() for x, y in zip(c, first))
+
+
 class _MockEngine:
     """Stands in for fvx.engine.Engine on the CPU: same call contract, scores from a matrix."""
 
