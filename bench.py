@@ -15,7 +15,7 @@ Workloads (synthetic Amazon-fashion-shaped data, random-init weights; SURVEY.md 
   c3      VBPR K=64 d=20 D=2048, 1 M x 500 k, global batch 524 288             (configs[2]; strong scaling)
   c4      = c3, evaluation only: top-100 sweep over all users                  (configs[3]; strong scaling)
   c5      VBPR K=256 d=20 D=4096, 40 k x 100 k                                 (configs[4])
-  c5d256  ... with embed_d = 256 (fp32 CUDA-core projection: d+1 > 256 columns)
+  c5d256  ... with embed_d = 256 (257 columns of E_ext: two column slices on the tensor cores)
 With --gpus N > 1 and no --config the job is the WEAK scaling of c2: per GPU 40 k users, 100 k catalog rows and
 65 536 triples per step (N=8: 320 k users x 800 k items, 524 288 triples per step); every rank's item shard is
 the size of c2's catalog (819 MB of features, far beyond L2).
@@ -716,7 +716,7 @@ def run_fvx(args):
         line["eval"] = {"metric": "users/s full-catalog top-%d eval" % args.top_k, "value": nu / best * 1e3,
                         "unit": "users/s", "users": nu, "items": I, "ms": best,
                         "scaling": None if world == 1 else args.scaling,
-                        "kernel": "k_topk_tc (tcgen05 bf16 bounds sweep + candidates sweep, exact fp32 re-scoring)" if e.use_tensor_cores
+                        "kernel": "k_topk_tc (tcgen05 bf16 bounds sweep + candidates sweep, exact fp32 re-scoring)" if (e.use_tensor_cores and e.tc_eval_eligible())
                         else "k_score_topk (fp32 CUDA cores)",
                         "fallback_rows": getattr(e, "tc_overflow_rows", 0),
                         "decomposition": "item shards: per-shard sweep of all users, all-to-all by user slice, merge" if world > 1 else "1 GPU",

@@ -52,7 +52,8 @@ struct ProjFwdParams {
   const int32_t* nrows_dev;   // optional: the number of valid rows lives on the device (<= nrows)
   int row0;
   int D;
-  int NP;               // padded output width (multiple of 32)
+  int NP;               // padded output width of THIS launch (multiple of 32): a column slice of the ld columns
+  int ld;               // row stride of `out` in floats (the padded width of the whole of E_ext)
   int ksplit;           // K splits
   int chunks;           // 64-feature chunks per split
   int n_tiles;          // 128-row tiles
@@ -64,7 +65,7 @@ struct ProjFwdParams {
                         //    at most `ksplit`): the unique-row step learns its row count on the device
   int chunks_total;     // D / 64
   int nsm;
-  float* out;           // [ksplit][nrows][NP]
+  float* out;           // [ksplit][nrows][ld], already advanced to the first column of the slice
 };
 
 // Work of one CTA of the forward kernel, walked identically by its three roles.
@@ -277,9 +278,9 @@ k_proj_fwd_tc(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant_
       const long long row = (long long)tile * PT_BM + quad * 32 + lane;
       mbar_wait(&t_full[acc], acc_phase);
       tc_fence_after();
-      float* dst = P.out + ((size_t)slot * P.nrows + (size_t)(row < nvalid ? row : 0)) * P.NP;
+      float* dst = P.out + ((size_t)slot * P.nrows + (size_t)(row < nvalid ? row : 0)) * P.ld;
       if (whole && row < nvalid) {            // stream-K: an uncut tile has no second fragment - its partial 1 is zero
-        float4* z = reinterpret_cast<float4*>(dst + (size_t)P.nrows * P.NP);
+        float4* z = reinterpret_cast<float4*>(dst + (size_t)P.nrows * P.ld);
         for (int n4 = 0; n4 < (P.NP >> 2); ++n4) z[n4] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
       for (int n0 = 0; n0 < P.NP; n0 += 32) {
@@ -321,7 +322,8 @@ struct GradEParams {
   long long nrows;
   const int32_t* nrows_dev;   // optional: the number of valid rows lives on the device (<= nrows)
   int n_groups;         // row groups of the launch
-  int D, NP;
+  int D, NP;            // NP: padded width of THIS launch (a column slice of the ld columns of W / of gE_part)
+  int ld;               // row stride of `out` in floats
   int fgs;              // features per CTA (multiple of 128)
   int nfg;              // feature groups = D / fgs
   int rows_per_group;   // multiple of GE_RT (recomputed on the device when nrows_dev is set)
@@ -330,7 +332,7 @@ struct GradEParams {
   int w_sw;             // swizzle of the W tile: TC_SWZ_64B (NP == 32) or TC_SWZ_128B
   int cat;              // 1 (NP == 32, interleaved W planes): the W tile is [32 rows x (hi 32 | lo 32)], ONE operand
                         //    of N = 64 - two UMMAs per K step (F_hi^T, F_lo^T) instead of three
-  float* out;           // [row groups][D][NP]
+  float* out;           // [row groups][D][ld], already advanced to the first column of the slice
 };
 
 __global__ void __launch_bounds__(PT_THREADS, 1)
@@ -496,7 +498,7 @@ k_grad_E_tc(const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ 
     }
     for (int mb = 0; mb < nmb; ++mb) {
       const int f = fg * P.fgs + mb * 128 + quad * 32 + lane;
-      float* dst = P.out + ((size_t)rg * P.D + f) * P.NP;
+      float* dst = P.out + ((size_t)rg * P.D + f) * P.ld;
       for (int n0 = 0; n0 < P.NP; n0 += 32) {
         uint32_t v[32];
         if (n_tiles > 0) {
@@ -561,6 +563,21 @@ __global__ void k_split_E(const float* __restrict__ E, int D, int de, int NP, __
 // ---------------------------------------------------------------------------------
 int fvx_tc_np(int de) { return de <= 32 ? 32 : (de + 63) / 64 * 64; }
 
+// One launch of either tensor-core kernel covers at most 256 columns of E_ext (UMMA N, the TMA box, the TMEM
+// columns of the accumulators); a wider model (BASELINE configs[4] with embed_d = 256: 257 columns, NP = 320)
+// is cut into balanced COLUMN SLICES of a multiple of 64 columns, one launch each.  Every launch re-reads the
+// gathered rows, which costs little here: with three hi/lo passes of N >= 128 the tensor pipe, not HBM, paces
+// a 64-feature stage, so two launches of half the width take about as long as one launch of the whole would.
+#define TC_MAX_SLICES 4
+static int tc_slices(int NP, int* c0, int* w) {
+  if (NP <= 256) { c0[0] = 0; w[0] = NP; return 1; }
+  const int n = (NP + 255) / 256;
+  const int per = (NP / n + 63) / 64 * 64;
+  int k = 0;
+  for (int c = 0; c < NP && k < TC_MAX_SLICES; c += per, ++k) { c0[k] = c; w[k] = NP - c < per ? NP - c : per; }
+  return k;
+}
+
 int fvx_tc_ksplit(const FvxModel* m, long long nrows) {
   return fvx_tc_ksplit_rule((nrows + PT_BM - 1) / PT_BM, m->D / PT_KC, fvx_num_sms(), 1 << 30);
 }
@@ -580,54 +597,59 @@ int fvx_launch_project_tc(const FvxModel* m, const int32_t* rows, int row0, int6
                           cudaStream_t st, const int32_t* nrows_dev, int dyn_ks, int sm_reserve) {
   FVX_CHECK_ARG(m->F_pl && m->ET_hi && m->ET_lo, "tensor-core projection: bf16 planes missing");
   FVX_CHECK_ARG(m->D % PT_KC == 0, "tensor-core projection: D=%d must be a multiple of %d", m->D, PT_KC);
-  const int NP = fvx_tc_np(m->de);
-  FVX_CHECK_ARG(NP <= 256, "tensor-core projection: d+1=%d too wide", m->de);
+  const int NPT = fvx_tc_np(m->de);
+  FVX_CHECK_ARG(NPT <= 256 * TC_MAX_SLICES, "tensor-core projection: d+1=%d too wide", m->de);
   if (nrows <= 0) return 0;
   const int chunks_total = m->D / PT_KC;
   FVX_CHECK_ARG(ksplit >= 1 && (dyn_ks || chunks_total % ksplit == 0), "tensor-core projection: bad K split %d", ksplit);
   FVX_CHECK_ARG(!dyn_ks || nrows_dev != nullptr, "tensor-core projection: a device-side K split needs nrows_dev");
-  CUtensorMap b_hi, b_lo;
-  int rc = 0;
-  const uint64_t pitch = (uint64_t)m->D * 2;
-  rc |= tc_make_tensor_map_bf16(&b_hi, m->ET_hi, NP, m->D, pitch, PT_KC, NP, 3);
-  rc |= tc_make_tensor_map_bf16(&b_lo, m->ET_lo, NP, m->D, pitch, PT_KC, NP, 3);
-  if (rc != 0) FVX_FAIL(-4, "tensor-core projection: cuTensorMapEncodeTiled failed");
-  ProjFwdParams P;
-  P.Fpl = reinterpret_cast<const uint8_t*>(m->F_pl); P.D = m->D;
-  P.rows = rows; P.row0 = row0; P.nrows = nrows; P.nrows_dev = nrows_dev; P.NP = NP; P.ksplit = ksplit;
-  P.chunks = dyn_ks ? chunks_total : chunks_total / ksplit;
-  P.dyn_ks = dyn_ks; P.chunks_total = chunks_total; P.nsm = fvx_num_sms();
-  P.n_tiles = (int)((nrows + PT_BM - 1) / PT_BM);
-  P.out = out;
-  P.cat = NP <= 64 ? 1 : 0;                       // N = 2*NP <= 128 and 2 buffers x nacc x 2*NP <= 512 columns
-  {
-    const int nw = P.cat ? 2 * NP : NP;
-    P.nacc = 256 / nw < 4 ? (256 / nw < 1 ? 1 : 256 / nw) : 4;
+  int sl_c0[TC_MAX_SLICES], sl_w[TC_MAX_SLICES];
+  const int n_slices = tc_slices(NPT, sl_c0, sl_w);
+  for (int sl = 0; sl < n_slices; ++sl) {
+    const int NP = sl_w[sl], c0 = sl_c0[sl];
+    CUtensorMap b_hi, b_lo;
+    int rc = 0;
+    const uint64_t pitch = (uint64_t)m->D * 2;
+    rc |= tc_make_tensor_map_bf16(&b_hi, m->ET_hi + (size_t)c0 * m->D, NP, m->D, pitch, PT_KC, NP, 3);
+    rc |= tc_make_tensor_map_bf16(&b_lo, m->ET_lo + (size_t)c0 * m->D, NP, m->D, pitch, PT_KC, NP, 3);
+    if (rc != 0) FVX_FAIL(-4, "tensor-core projection: cuTensorMapEncodeTiled failed");
+    ProjFwdParams P;
+    P.Fpl = reinterpret_cast<const uint8_t*>(m->F_pl); P.D = m->D;
+    P.rows = rows; P.row0 = row0; P.nrows = nrows; P.nrows_dev = nrows_dev; P.NP = NP; P.ld = NPT; P.ksplit = ksplit;
+    P.chunks = dyn_ks ? chunks_total : chunks_total / ksplit;
+    P.dyn_ks = dyn_ks; P.chunks_total = chunks_total; P.nsm = fvx_num_sms();
+    P.n_tiles = (int)((nrows + PT_BM - 1) / PT_BM);
+    P.out = out + c0;
+    P.cat = NP <= 64 ? 1 : 0;                       // N = 2*NP <= 128 and 2 buffers x nacc x 2*NP <= 512 columns
+    {
+      const int nw = P.cat ? 2 * NP : NP;
+      P.nacc = 256 / nw < 4 ? (256 / nw < 1 ? 1 : 256 / nw) : 4;
+    }
+    const size_t stage_bytes = 2 * PT_BM * 128 + 2 * (size_t)NP * 128;
+    int stages = (int)((220 * 1024) / stage_bytes);
+    if (stages > 6) stages = 6;
+    {
+      static int cap = -1;                 // FVX_FWD_STAGES: cap on the pipeline depth (measurements)
+      if (cap < 0) { const char* e = getenv("FVX_FWD_STAGES"); cap = e ? atoi(e) : 0; }
+      if (cap >= 2 && stages > cap) stages = cap;
+      // the step's forward kernel shares the memory system with the catch-up kernel on the side stream:
+      // six 32 KB stages per SM keep ~28 MB of requests queued and the latency-bound neighbour waits behind
+      // them (its end moved from 146 to 138 us of the step with four stages; the projection itself did not slow)
+      if (cap < 2 && dyn_ks && stages > 4) stages = 4;
+    }
+    FVX_CHECK_ARG(stages >= 2, "tensor-core projection: tile does not fit shared memory");
+    P.stages = stages;
+    const size_t smem = stages * stage_bytes + (2 * stages + 4) * 8 + 16 + 1024;
+    static FvxSmemMark fwd_smem;
+    if (int r = fvx_ensure_smem((const void*)k_proj_fwd_tc, &fwd_smem, smem, "k_proj_fwd_tc")) return r;
+    long long grid = (long long)P.n_tiles * ksplit;
+    int sms = fvx_num_sms() - sm_reserve;
+    if (sms < 8) sms = 8;
+    if (grid > sms || dyn_ks) grid = sms;
+    P.nsm = sms;
+    k_proj_fwd_tc<<<(int)grid, PT_THREADS, smem, st>>>(b_hi, b_lo, P);
+    FVX_CHECK_LAUNCH("k_proj_fwd_tc");
   }
-  const size_t stage_bytes = 2 * PT_BM * 128 + 2 * (size_t)NP * 128;
-  int stages = (int)((220 * 1024) / stage_bytes);
-  if (stages > 6) stages = 6;
-  {
-    static int cap = -1;                 // FVX_FWD_STAGES: cap on the pipeline depth (measurements)
-    if (cap < 0) { const char* e = getenv("FVX_FWD_STAGES"); cap = e ? atoi(e) : 0; }
-    if (cap >= 2 && stages > cap) stages = cap;
-    // the step's forward kernel shares the memory system with the catch-up kernel on the side stream:
-    // six 32 KB stages per SM keep ~28 MB of requests queued and the latency-bound neighbour waits behind
-    // them (its end moved from 146 to 138 us of the step with four stages; the projection itself did not slow)
-    if (cap < 2 && dyn_ks && stages > 4) stages = 4;
-  }
-  FVX_CHECK_ARG(stages >= 2, "tensor-core projection: tile does not fit shared memory");
-  P.stages = stages;
-  const size_t smem = stages * stage_bytes + (2 * stages + 4) * 8 + 16 + 1024;
-  static FvxSmemMark fwd_smem;
-  if (int r = fvx_ensure_smem((const void*)k_proj_fwd_tc, &fwd_smem, smem, "k_proj_fwd_tc")) return r;
-  long long grid = (long long)P.n_tiles * ksplit;
-  int sms = fvx_num_sms() - sm_reserve;
-  if (sms < 8) sms = 8;
-  if (grid > sms || dyn_ks) grid = sms;
-  P.nsm = sms;
-  k_proj_fwd_tc<<<(int)grid, PT_THREADS, smem, st>>>(b_hi, b_lo, P);
-  FVX_CHECK_LAUNCH("k_proj_fwd_tc");
   return 0;
 }
 
@@ -636,10 +658,19 @@ int fvx_launch_grad_E_tc(const FvxModel* m, const int32_t* rows, int64_t nrows, 
                          const int32_t* nrows_dev, int sm_reserve) {
   FVX_CHECK_ARG(m->F_pl && m->W_hi && m->W_lo && m->gE_part, "tensor-core grad_E: buffers missing");
   FVX_CHECK_ARG(m->D % 128 == 0, "tensor-core grad_E: D=%d must be a multiple of 128", m->D);
-  const int NP = fvx_tc_np(m->de);
-  int fgs = GE_FG;
-  while (fgs > 128 && (m->D % fgs != 0 || (fgs / 128) * NP > 512)) fgs >>= 1;
-  FVX_CHECK_ARG(m->D % fgs == 0 && (fgs / 128) * NP <= 512, "tensor-core grad_E: d+1=%d too wide", m->de);
+  const int NPT = fvx_tc_np(m->de);
+  FVX_CHECK_ARG(NPT <= 256 * TC_MAX_SLICES, "tensor-core grad_E: d+1=%d too wide", m->de);
+  int sl_c0[TC_MAX_SLICES], sl_w[TC_MAX_SLICES];
+  const int n_slices = tc_slices(NPT, sl_c0, sl_w);
+  // the row groups (= partials the E update sums) are the same for every slice: the widest slice decides
+  int fgs_all = GE_FG;
+  for (int sl = 0; sl < n_slices; ++sl) {
+    int fgs = GE_FG;
+    while (fgs > 128 && (m->D % fgs != 0 || (fgs / 128) * sl_w[sl] > 512)) fgs >>= 1;
+    FVX_CHECK_ARG(m->D % fgs == 0 && (fgs / 128) * sl_w[sl] <= 512, "tensor-core grad_E: d+1=%d too wide", m->de);
+    if (fgs < fgs_all) fgs_all = fgs;
+  }
+  const int fgs = fgs_all;
   const int nfg = m->D / fgs;
   int max_rg = (fvx_num_sms() - sm_reserve) / nfg;
   if (max_rg < 1) max_rg = 1;
@@ -650,44 +681,48 @@ int fvx_launch_grad_E_tc(const FvxModel* m, const int32_t* rows, int64_t nrows, 
   const int parts = nrows > 0 ? (int)((nrows + rpg - 1) / rpg) : 0;
   *parts_out = parts;
   if (parts == 0) return 0;
-  CUtensorMap w_hi, w_lo;
-  int rc = 0;
   const int wpitch = fvx_w_pitch(m);
-  const int cat = (NP == 32 && wpitch == 2 * NP) ? 1 : 0;
-  const int wbox = NP <= 64 ? NP : 64;
-  const int wsw = NP == 32 ? 2 : 3;
-  if (cat) {
-    // one map over the interleaved rows [nrows, hi 32 | lo 32]: 128-byte rows, 128B swizzle
-    rc |= tc_make_tensor_map_bf16(&w_hi, m->W_hi, nrows, 2 * NP, (uint64_t)wpitch * 2, 2 * NP, GE_RT, 3);
-    w_lo = w_hi;
-  } else {
-    rc |= tc_make_tensor_map_bf16(&w_hi, m->W_hi, nrows, NP, (uint64_t)wpitch * 2, wbox, GE_RT, wsw);
-    rc |= tc_make_tensor_map_bf16(&w_lo, m->W_lo, nrows, NP, (uint64_t)wpitch * 2, wbox, GE_RT, wsw);
+  for (int sl = 0; sl < n_slices; ++sl) {
+    const int NP = sl_w[sl], c0 = sl_c0[sl];
+    CUtensorMap w_hi, w_lo;
+    int rc = 0;
+    const int cat = (NPT == 32 && wpitch == 2 * NP) ? 1 : 0;
+    const int wbox = NP <= 64 ? NP : 64;
+    const int wsw = NP == 32 ? 2 : 3;
+    if (cat) {
+      // one map over the interleaved rows [nrows, hi 32 | lo 32]: 128-byte rows, 128B swizzle
+      rc |= tc_make_tensor_map_bf16(&w_hi, m->W_hi, nrows, 2 * NP, (uint64_t)wpitch * 2, 2 * NP, GE_RT, 3);
+      w_lo = w_hi;
+    } else {
+      rc |= tc_make_tensor_map_bf16(&w_hi, m->W_hi + c0, nrows, NP, (uint64_t)wpitch * 2, wbox, GE_RT, wsw);
+      rc |= tc_make_tensor_map_bf16(&w_lo, m->W_lo + c0, nrows, NP, (uint64_t)wpitch * 2, wbox, GE_RT, wsw);
+    }
+    if (rc != 0) FVX_FAIL(-4, "tensor-core grad_E: cuTensorMapEncodeTiled failed");
+    GradEParams P;
+    P.Fpl = reinterpret_cast<const uint8_t*>(m->F_pl);
+    P.rows = rows; P.nrows = nrows; P.nrows_dev = nrows_dev; P.n_groups = parts; P.D = m->D; P.NP = NP; P.ld = NPT;
+    P.fgs = fgs; P.nfg = nfg; P.rows_per_group = (int)rpg;
+    P.w_atoms = NP <= 64 ? 1 : NP / 64;
+    P.w_sw = NP == 32 ? TC_SWZ_64B : TC_SWZ_128B;
+    P.cat = cat;
+    P.out = m->gE_part + c0;
+    const size_t wrow = cat ? 128 : (NP <= 64 ? (size_t)NP * 2 : 128);
+    const size_t stage_bytes = 2 * (size_t)(fgs / PT_KC) * GE_RT * 128 + (cat ? 1 : 2) * (size_t)P.w_atoms * GE_RT * wrow;
+    int stages = (int)((220 * 1024) / stage_bytes);
+    if (stages > 4) stages = 4;
+    {
+      static int cap = -1;                 // FVX_GE_STAGES: cap on the pipeline depth (measurements)
+      if (cap < 0) { const char* e = getenv("FVX_GE_STAGES"); cap = e ? atoi(e) : 0; }
+      if (cap >= 2 && stages > cap) stages = cap;
+    }
+    FVX_CHECK_ARG(stages >= 2, "tensor-core grad_E: tile does not fit shared memory");
+    P.stages = stages;
+    const size_t smem = stages * stage_bytes + (2 * stages + 1) * 8 + 16 + 1024;
+    static FvxSmemMark ge_smem;
+    if (int r = fvx_ensure_smem((const void*)k_grad_E_tc, &ge_smem, smem, "k_grad_E_tc")) return r;
+    k_grad_E_tc<<<parts * nfg, PT_THREADS, smem, st>>>(w_hi, w_lo, P);
+    FVX_CHECK_LAUNCH("k_grad_E_tc");
   }
-  if (rc != 0) FVX_FAIL(-4, "tensor-core grad_E: cuTensorMapEncodeTiled failed");
-  GradEParams P;
-  P.Fpl = reinterpret_cast<const uint8_t*>(m->F_pl);
-  P.rows = rows; P.nrows = nrows; P.nrows_dev = nrows_dev; P.n_groups = parts; P.D = m->D; P.NP = NP; P.fgs = fgs; P.nfg = nfg; P.rows_per_group = (int)rpg;
-  P.w_atoms = NP <= 64 ? 1 : NP / 64;
-  P.w_sw = NP == 32 ? TC_SWZ_64B : TC_SWZ_128B;
-  P.cat = cat;
-  P.out = m->gE_part;
-  const size_t wrow = cat ? 128 : (NP <= 64 ? (size_t)NP * 2 : 128);
-  const size_t stage_bytes = 2 * (size_t)(fgs / PT_KC) * GE_RT * 128 + (cat ? 1 : 2) * (size_t)P.w_atoms * GE_RT * wrow;
-  int stages = (int)((220 * 1024) / stage_bytes);
-  if (stages > 4) stages = 4;
-  {
-    static int cap = -1;                 // FVX_GE_STAGES: cap on the pipeline depth (measurements)
-    if (cap < 0) { const char* e = getenv("FVX_GE_STAGES"); cap = e ? atoi(e) : 0; }
-    if (cap >= 2 && stages > cap) stages = cap;
-  }
-  FVX_CHECK_ARG(stages >= 2, "tensor-core grad_E: tile does not fit shared memory");
-  P.stages = stages;
-  const size_t smem = stages * stage_bytes + (2 * stages + 1) * 8 + 16 + 1024;
-  static FvxSmemMark ge_smem;
-  if (int r = fvx_ensure_smem((const void*)k_grad_E_tc, &ge_smem, smem, "k_grad_E_tc")) return r;
-  k_grad_E_tc<<<parts * nfg, PT_THREADS, smem, st>>>(w_hi, w_lo, P);
-  FVX_CHECK_LAUNCH("k_grad_E_tc");
   return 0;
 }
 

@@ -491,7 +491,7 @@ __device__ __forceinline__ float half_sum(float v) {
 // DEDUP (unique-row step): theta of slot (b, side) is row upos[item row] of TH, and the backward
 // coefficients are ADDED into W_sum[upos[item row]] (fp32; k_w_planes turns the sums into bf16 planes).
 template <int MQ, int MD, bool DEDUP>
-__global__ void __launch_bounds__(SG_WARPS * 32, 4)
+__global__ void __launch_bounds__(SG_WARPS * 32, (MQ + MD > 4 ? 2 : 4))   // the wide variants hold up to 100 row values per lane
 k_score_grad_v4(FvxModel M, const int32_t* __restrict__ user, int B, int loss_slot, SgTheta T, int wnp, int wpitch) {
   __shared__ double loss_sh[SG_WARPS * 2];
   if (DEDUP) {
@@ -981,11 +981,12 @@ int fvx_launch_score_grad(const FvxModel* m, const int32_t* user, int B, int los
   const int wnp = tc ? T.np : 0;
   const int wpitch = tc ? fvx_w_pitch(m) : 0;
   const int need = (m->K > m->d + 1 ? m->K : m->d + 1);
-  FVX_CHECK_ARG(need <= 288 && (wnp == 0 || wnp <= 256), "fvx_bpr_step: K=%d / d=%d too large for the score kernel",
+  FVX_CHECK_ARG(need <= 288 && (wnp == 0 || wnp <= 320), "fvx_bpr_step: K=%d / d=%d too large for the score kernel",
                 m->K, m->d);
   const int wcols = wnp > 0 ? wnp : m->de;
-  if (m->K % 4 == 0 && m->K <= 256 && m->d <= 252 && wcols <= 256) {
-    // vector path: a lane owns 4 columns, 16 lanes per triple
+  if (m->K % 4 == 0 && m->K <= 256 && ((m->d <= 252 && wcols <= 256) || (wnp > 0 && wcols <= 320))) {
+    // vector path: a lane owns 4 columns, 16 lanes per triple (MD = 5: the 320 padded columns of embed_d = 256 on
+    // the tensor-core path)
     const long long g2 = (g + 1) / 2 > 0 ? (g + 1) / 2 : 1;
     if (dedup) {
       FVX_CHECK_ARG(tc && m->upos && m->W_sum && m->uslot, "fvx_bpr_step: unique-row step without upos / W_sum / uslot");
@@ -993,14 +994,18 @@ int fvx_launch_score_grad(const FvxModel* m, const int32_t* user, int B, int los
         k_score_grad_v4<1, 1, true><<<(int)g2, SG_WARPS * 32, 0, st>>>(*m, user, B, loss_slot, T, wnp, wpitch);
       else if (m->K <= 128 && wcols <= 128)
         k_score_grad_v4<2, 2, true><<<(int)g2, SG_WARPS * 32, 0, st>>>(*m, user, B, loss_slot, T, wnp, wpitch);
-      else
+      else if (wcols <= 256)
         k_score_grad_v4<4, 4, true><<<(int)g2, SG_WARPS * 32, 0, st>>>(*m, user, B, loss_slot, T, wnp, wpitch);
+      else
+        k_score_grad_v4<4, 5, true><<<(int)g2, SG_WARPS * 32, 0, st>>>(*m, user, B, loss_slot, T, wnp, wpitch);
     } else if (m->K <= 64 && wcols <= 64)
       k_score_grad_v4<1, 1, false><<<(int)g2, SG_WARPS * 32, 0, st>>>(*m, user, B, loss_slot, T, wnp, wpitch);
     else if (m->K <= 128 && wcols <= 128)
       k_score_grad_v4<2, 2, false><<<(int)g2, SG_WARPS * 32, 0, st>>>(*m, user, B, loss_slot, T, wnp, wpitch);
-    else
+    else if (wcols <= 256)
       k_score_grad_v4<4, 4, false><<<(int)g2, SG_WARPS * 32, 0, st>>>(*m, user, B, loss_slot, T, wnp, wpitch);
+    else
+      k_score_grad_v4<4, 5, false><<<(int)g2, SG_WARPS * 32, 0, st>>>(*m, user, B, loss_slot, T, wnp, wpitch);
   } else if (dedup) {
     FVX_FAIL(-2, "fvx_bpr_step: the unique-row step needs K %% 4 == 0");
   } else {
@@ -1226,7 +1231,7 @@ static int bpr_step_impl(const FvxModel* model, const int32_t* user, const int32
   // scoring kernel reads theta through uslot and sums the backward coefficients per listed row, k_w_planes
   // turns the sums into the bf16 planes grad_E reads.  At B = 65 536 on a 100 k catalog 2B slots are
   // ~58 k distinct rows: both contractions shrink by more than half.
-  const bool dedup = tc && M.upos && M.W_sum && M.uslot && M.K % 4 == 0 && M.K <= 256 && M.d <= 252 && NP <= 256 &&
+  const bool dedup = tc && M.upos && M.W_sum && M.uslot && M.K % 4 == 0 && M.K <= 256 && M.d <= 256 && NP <= 320 &&
                      fvx_dedup_enabled();
   if (dedup) {
     int ks_cap = 8;

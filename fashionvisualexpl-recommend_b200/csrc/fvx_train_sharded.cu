@@ -769,7 +769,7 @@ static SsTheta make_theta(const FvxModel* m, int B, int ks, int sm_reserve = 0) 
 // Needs the tensor-core path and the scratch (upos, W_sum, uslot); FVX_STEP_DEDUP=0 turns it off.
 static bool sharded_uniq(const FvxModel* m) {
   return m->D > 0 && m->use_tensor_cores && m->upos && m->W_sum && m->uslot &&
-         fvx_tc_np(m->de) <= 256 && fvx_dedup_enabled();
+         fvx_tc_np(m->de) <= 320 && fvx_dedup_enabled();
 }
 static int uniq_ks_cap(const FvxModel* m, int B) {
   int ks_cap = 8;

@@ -89,10 +89,10 @@ class Engine:
         self.ET_hi = self.ET_lo = self.W_hi = self.W_lo = None
         self.upos_t = self.W_sum = self.uslot_t = None
         self.use_tensor_cores = bool(use_tensor_cores) and self.D > 0
-        if self.use_tensor_cores and (self.D % 128 != 0 or (self.d + 1 + 63) // 64 * 64 > 256):
-            # the tcgen05 projection kernels take D % 128 == 0 and d + 1 <= 256 (one UMMA N block);
-            # wider / ragged models (BASELINE configs[4] with embed_d = 256) run on the exact fp32
-            # CUDA-core kernels - still this library, still the GPU
+        if self.use_tensor_cores and (self.D % 128 != 0 or (self.d + 1 + 63) // 64 * 64 > 320):
+            # the tcgen05 projection kernels take D % 128 == 0 and d + 1 <= 320 padded columns (more than 256
+            # columns - BASELINE configs[4] with embed_d = 256 - are cut into column slices, one launch each);
+            # wider / ragged models run on the exact fp32 CUDA-core kernels - still this library, still the GPU
             self.use_tensor_cores = False
         if self.D:
             self.E = torch.zeros(self.D, self.de, **f32)

@@ -26,7 +26,9 @@ def _pair(U, I, K, d, D, B, seed=0, **kw):
 
 
 @pytest.mark.parametrize("I,d,D,n", [(900, 20, 256, 1000), (300, 20, 2048, 517), (2000, 5, 128, 4096),
-                                       (500, 40, 512, 700), (400, 64, 256, 300)])
+                                       (500, 40, 512, 700), (400, 64, 256, 300),
+                                       (400, 256, 256, 300),      # 257 columns: two column slices (192 + 128)
+                                       (300, 270, 512, 1100)])
 def test_project_rows_tensor_cores(I, d, D, n):
     P, F, rng, e32, etc = _pair(50, I, 8, d, D, B=max(n // 2 + 1, 64), seed=d + D)
     rows = rng.integers(0, I, n)
@@ -43,7 +45,8 @@ def test_project_rows_tensor_cores(I, d, D, n):
 
 
 @pytest.mark.parametrize("I,d,D,n", [(900, 20, 256, 1000), (300, 20, 2048, 517), (2000, 5, 128, 4096),
-                                       (500, 40, 512, 96), (400, 64, 256, 300)])
+                                       (500, 40, 512, 96), (400, 64, 256, 300),
+                                       (400, 256, 512, 300), (300, 270, 256, 1100)])    # column slices
 def test_grad_e_rows_tensor_cores(I, d, D, n):
     P, F, rng, e32, etc = _pair(50, I, 8, d, D, B=max(n // 2 + 1, 64), seed=d + D + 1)
     rows = rng.integers(0, I, n)
@@ -85,7 +88,9 @@ def _perturbed_oracle(P, F, batches, reg, lr, rel=2.0 ** -16, seed=7):
 @pytest.mark.parametrize("mode", ["dense", "deferred"])
 @pytest.mark.parametrize("K,d,D,B", [(64, 20, 256, 512), (16, 64, 128, 96), (8, 5, 128, 33), (32, 20, 2048, 1024),
                                        (256, 20, 4096, 512),      # BASELINE configs[4]: K = 256, 4096-d features
-                                       (256, 255, 4096, 96)])     # ... and the widest tensor-core operand (NP = 256)
+                                       (256, 255, 4096, 96),      # ... the widest single-launch operand (NP = 256)
+                                       (256, 256, 4096, 96),      # ... and configs[4] with embed_d = 256: two column slices
+                                       (16, 256, 256, 300)])
 def test_train_steps_tensor_cores_match_oracle(K, d, D, B, mode):
     U, I, steps, lr, reg = 700, 900, 20, 0.001, 1e-3
     P, F, rng = _random_problem(U, I, K, d, D, seed=K + d)
@@ -105,8 +110,10 @@ def test_train_steps_tensor_cores_match_oracle(K, d, D, B, mode):
         ref = P64[k]
         dlt = np.abs(Q[k].reshape(ref.shape) - ref) / np.abs(ref).max()
         e_f32, e_pert = rel_err(P32[k], ref), rel_err(Pp[k], ref)
-        assert dlt.max() <= max(REL, 3 * e_f32, e_pert), (mode, k, dlt.max(), e_f32, e_pert)
         assert (dlt > REL).mean() <= 1e-3, (mode, k, "elements beyond 1e-4", int((dlt > REL).sum()), dlt.size)
+        # the perturbed oracle is ONE draw of the discontinuity noise (the largest of ~1e5 elements): a factor 2 on it
+        assert dlt.max() <= max(REL, 3 * e_f32, 2 * e_pert), (mode, k, dlt.max(), e_f32, e_pert,
+                                                               np.unravel_index(dlt.argmax(), dlt.shape))
 
 
 @pytest.mark.parametrize("K,d,D,B,tc", [(64, 20, 256, 256, True), (64, 20, 2048, 300, True), (32, 0, 0, 256, False),
@@ -154,7 +161,8 @@ def test_graph_replayed_steps_equal_single_steps(K, d, D, B, tc):
 @pytest.mark.parametrize("K,d,D,B,I", [(64, 20, 2048, 3000, 400),     # ~every catalog row repeats 15 times
                                         (64, 20, 256, 4097, 50000),    # hardly any duplicates, ragged batch
                                         (32, 63, 512, 777, 300),       # NP = 64
-                                        (16, 100, 256, 500, 200)])     # NP = 128 (three-pass operands)
+                                        (16, 100, 256, 500, 200),      # NP = 128 (three-pass operands)
+                                        (16, 256, 256, 500, 200)])     # NP = 320: two column slices
 def test_unique_row_step_equals_per_slot_step(K, d, D, B, I, mode):
     """fvx_bpr_step projects each DISTINCT catalog row of the batch once (k_uniq_rows / upos / W_sum,
     DESIGN.md section 3).  Against the per-slot path on the same batches - including triples whose
