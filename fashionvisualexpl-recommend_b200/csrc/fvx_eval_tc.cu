@@ -555,22 +555,83 @@ __device__ __forceinline__ float rs_score(const float* __restrict__ urow, const 
   return s;
 }
 
-__global__ void __launch_bounds__(RS_WARPS * 32)
+// Shared memory of one warp of k_rescore_select (11 KB: five 4-warp blocks per SM).
+#define RS_MASK 256         // train items of a user staged in shared memory (longer lists: searched in global memory)
+struct RsWarpSmem {
+  unsigned long long keys[TCK_RS_MAX];
+  float user[448];                      // K + d <= 445 (KP <= 448)
+  int32_t mask[RS_MASK];
+};
+
+__device__ __forceinline__ bool rs_in_mask(const int32_t* __restrict__ m, int n, int32_t x) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    const int32_t v = m[mid];
+    if (v == x) return true;
+    if (v < x) lo = mid + 1; else hi = mid;
+  }
+  return false;
+}
+
+// rs_score with the row pieces fetched EIGHT 16-byte loads at a time ahead of their 32 fmaf: the chain is the same
+// (index order over [Gi | theta], then the two biases - fvx_score_one bit for bit), but a candidate costs three
+// L2 round trips at K + d = 84 instead of twenty-one (the loop above is load -> 4 fmaf -> load ...: its loads sit
+// behind the chain in program order and ptxas does not hoist them across a loop of unknown trip count; the kernel
+// spent 1.0 ms of the 3.4 ms sweep at configs[1] waiting for them, profiles/r2_eval_full.txt).  K % 4 == 0.
+__device__ __forceinline__ float rs_score8(const float* __restrict__ us, const float* __restrict__ irow,
+                                           const float* __restrict__ th, int K, int d) {
+  const int kc = K >> 2, nc = kc + ((d + 3) >> 2), kd = K + d;
+  const float tail_b = irow[K];
+  const float tail_v = d > 0 ? th[d] : 0.0f;
+  float s = 0.0f;
+  for (int g0 = 0; g0 < nc; g0 += 8) {
+    float4 x[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int g = g0 + j;
+      x[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (g < nc) x[j] = *reinterpret_cast<const float4*>(g < kc ? irow + 4 * g : th + 4 * (g - kc));
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = 4 * (g0 + j);                 // index into [Gu | Tu]: the latent columns end on a multiple of 4
+      if (c < kd) {
+        const float4 u = *reinterpret_cast<const float4*>(us + c);
+        s = fmaf(u.x, x[j].x, s);
+        if (c + 1 < kd) s = fmaf(u.y, x[j].y, s);
+        if (c + 2 < kd) s = fmaf(u.z, x[j].z, s);
+        if (c + 3 < kd) s = fmaf(u.w, x[j].w, s);
+      }
+    }
+  }
+  s += tail_b;
+  if (d > 0) s += tail_v;
+  return s;
+}
+
+// One warp per user row, one lane per candidate.
+__global__ void __launch_bounds__(RS_WARPS * 32, 5)
 k_rescore_select(FvxModel M, const float* __restrict__ theta, TckParams P,
                  const int64_t* __restrict__ mask_row_ptr, const int32_t* __restrict__ mask_col, int k,
                  int32_t* __restrict__ out_ids, float* __restrict__ out_scores) {
-  __shared__ unsigned long long rs_keys[RS_WARPS][TCK_RS_MAX];
-  __shared__ float rs_user[RS_WARPS][448];      // K + d <= 445 (KP <= 448)
+  __shared__ __align__(16) RsWarpSmem rs_sm[RS_WARPS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  unsigned long long* kk = rs_keys[warp];
-  float* us = rs_user[warp];
+  RsWarpSmem& W = rs_sm[warp];
+  unsigned long long* kk = W.keys;
+  float* us = W.user;
   const int full_rows = P.n_full * P.n_ut * TCK_BM;
-  const int kd = M.K + M.d;
+  const int K = M.K, d = M.d, kd = K + d;
+  const bool vec = (K & 3) == 0;          // 16-byte pieces must not straddle the end of the latent columns
   for (int r = blockIdx.x * RS_WARPS + warp; r < P.n_users; r += gridDim.x * RS_WARPS) {
     const int gu = P.u0 + r;
     const float* urow = M.users.w + (size_t)gu * M.users.stride;
     for (int c = lane; c < kd; c += 32) us[c] = urow[c];
     const long long mlo = mask_row_ptr[gu], mhi = mask_row_ptr[gu + 1];
+    const int mlen = (int)(mhi - mlo);
+    const bool mask_sh = mlen <= RS_MASK;
+    if (mask_sh)
+      for (int c = lane; c < mlen; c += 32) W.mask[c] = mask_col[mlo + c];
     // the candidates of the row's lists (one per item split)
     const int nlists = r < full_rows ? 1 : P.splits;
     int total = 0;
@@ -597,10 +658,12 @@ k_rescore_select(FvxModel M, const float* __restrict__ theta, TckParams P,
     for (int i = lane; i < total; i += 32) {
       const int32_t gid = (int32_t)(kk[i] & 0xFFFFFFFFu);
       unsigned long long key = KEY_PAD;
-      if (!fvx_in_sorted(mask_col, mlo, mhi, gid)) {
+      const bool masked = mask_sh ? rs_in_mask(W.mask, mlen, gid) : fvx_in_sorted(mask_col, mlo, mhi, gid);
+      if (!masked) {
         const int32_t li = gid - M.item_lo;
-        const float* th = M.d > 0 ? theta + (size_t)li * M.de : nullptr;
-        key = tck_key(rs_score(us, M.items.w + (size_t)li * M.items.stride, th, M.K, M.d), gid);
+        const float* irow = M.items.w + (size_t)li * M.items.stride;
+        const float* th = d > 0 ? theta + (size_t)li * M.de : nullptr;
+        key = tck_key(vec ? rs_score8(us, irow, th, K, d) : rs_score(us, irow, th, K, d), gid);
       }
       kk[i] = key;
     }
