@@ -704,6 +704,39 @@ def run_fvx(args):
                 best = min(best, max_over_ranks(a.elapsed_time(b2)))
             return best
 
+        if os.environ.get("FVX_BENCH_EVAL_TRACE") and world == 1:
+            # where the sweep's time goes on the host's clock and on the device's (diagnostics, stderr)
+            for rep in range(3):
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                ev[0].record()
+                e.theta(refresh=True)
+                t1 = time.perf_counter()
+                ev[1].record()
+                e.score_topk(st["row_ptr"], st["col_sorted"], args.top_k)
+                t2 = time.perf_counter()
+                ev[2].record()
+                torch.cuda.synchronize()
+                t3 = time.perf_counter()
+                if rep == 2:
+                    ev2 = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+                    ev2[0].record()
+                    e.topk_bounds(st["row_ptr"], args.top_k)
+                    ev2[1].record()
+                    e.topk_select(st["row_ptr"], st["col_sorted"], args.top_k)
+                    ev2[2].record()
+                    torch.cuda.synchronize()
+                    sys.stderr.write("eval trace: bounds %.3f ms, select %.3f ms\n"
+                                     % (ev2[0].elapsed_time(ev2[1]), ev2[1].elapsed_time(ev2[2])))
+                    w_ = e._eval_ws(U)
+                    cc_ = w_["ccount"][:w_["lists"]].float()
+                    sys.stderr.write("eval trace: KP %d splits %d n_ut %d lists %d a_stride %d cand mean %.1f max %d flags %d\n"
+                                     % (w_["KP"], w_["splits"], w_["n_ut"], w_["lists"], w_["struct"].a_stride,
+                                        cc_.mean().item(), int(cc_.max().item()), int(w_["flags"].sum().item())))
+                sys.stderr.write("eval trace: theta %.3f ms (host %.3f), topk %.3f ms (host %.3f), host total %.3f\n"
+                                 % (ev[0].elapsed_time(ev[1]), (t1 - t0) * 1e3, ev[1].elapsed_time(ev[2]),
+                                    (t2 - t1) * 1e3, (t3 - t0) * 1e3))
         nu = U
         flops_user = 2.0 * I * (K + d) + 2.0 * I
         modes = {"item_shards": timed(sweep_item_shards)}

@@ -83,7 +83,10 @@ k_score_topk(FvxModel M, const float* __restrict__ theta, int u0, int u1,
              const float* __restrict__ thr_scores, int32_t* __restrict__ out_counts,
              const int32_t* __restrict__ ulist,     // ulist: user of local index j (nullptr: j itself)
              const int32_t* __restrict__ n_dev,     // list mode: number of valid list entries lives on the device
-             int scatter_base) {                    // >= 0: output row of list entry j is ulist[j] - scatter_base
+             int scatter_base,                      // >= 0: output row of list entry j is ulist[j] - scatter_base
+             const int32_t* __restrict__ tau_enc) { // list mode, optional: a proven lower bound of the k-th best unmasked
+                                                    // score of row ulist[j] - scatter_base (int32 whose signed order is the
+                                                    // float's, fvx_score_topk_tc_bounds): the row's threshold starts there
   extern __shared__ __align__(16) unsigned char tk_smem[];
   const int Su = M.users.stride, Si = M.items.stride, K = M.K, d = M.d, de = M.de;
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(tk_smem);          // [UB][CAP]
@@ -106,7 +109,18 @@ k_score_topk(FvxModel M, const float* __restrict__ theta, int u0, int u1,
       const int u = e / Su, c = e - u * Su;
       us[e] = (u < nu) ? M.users.w[(size_t)(ulist ? ulist[ub + u] : ub + u) * Su + c] : 0.0f;
     }
-    if (tid < TK_UB) { tau[tid] = -CUDART_INF_F; cnt[tid] = 0; }
+    if (tid < TK_UB) {
+      float t0 = -CUDART_INF_F;
+      if (tau_enc && scatter_base >= 0 && tid < nu) {
+        // without it every item passes until the first compaction and the list is sorted once per 256-item tile:
+        // 4 ms per flagged row at 100 k items; the bound cuts the insertions to the few hundred items that reach it
+        const int32_t e = tau_enc[ulist[ub + tid] - scatter_base];
+        const float a = __int_as_float(e >= 0 ? e : (e ^ 0x7FFFFFFF));
+        if (a > -CUDART_INF_F && a < CUDART_INF_F) t0 = nextafterf(a, -CUDART_INF_F);   // items with s >= a pass (s > tau)
+      }
+      tau[tid] = t0;
+      cnt[tid] = 0;
+    }
     if (tid < TK_UB * TK_MAXTHR) {
       const int u = tid / TK_MAXTHR, t = tid - u * TK_MAXTHR;
       thr[tid] = (u < nu && t < n_thr) ? thr_scores[(size_t)(ub + u - u0) * n_thr + t] : CUDART_NAN_F;
@@ -321,7 +335,7 @@ static int score_topk_impl(const FvxModel* model, const float* theta_ext, int32_
   if (g > (long long)fvx_num_sms() * 4) g = (long long)fvx_num_sms() * 4;
   k_score_topk<<<(int)g, TK_TILE, smem, fvx_cu(stream)>>>(*model, theta_ext, u0, u1, mask_row_ptr, mask_col, k,
                                                           out_ids, out_scores, n_thr, thr_scores, out_counts, ulist,
-                                                          nullptr, -1);
+                                                          nullptr, -1, nullptr);
   FVX_CHECK_LAUNCH("k_score_topk");
   return 0;
 }
@@ -339,7 +353,8 @@ __global__ void k_flag_list(const int32_t* __restrict__ flags, int n, int u0, in
 // own slots of out_ids / out_scores.  No host synchronisation: the list and its length stay on the device.
 int fvx_launch_topk_flagged(const FvxModel* model, const float* theta_ext, const int32_t* flags, int n, int u0,
                             const int64_t* mask_row_ptr, const int32_t* mask_col, int k, int32_t* out_ids,
-                            float* out_scores, int32_t* list_scratch, int32_t* count_scratch, cudaStream_t st) {
+                            float* out_scores, int32_t* list_scratch, int32_t* count_scratch, cudaStream_t st,
+                            const int32_t* tau_enc) {
   cudaMemsetAsync(count_scratch, 0, sizeof(int32_t), st);
   int g = (n + 255) / 256;
   if (g > fvx_num_sms() * 4) g = fvx_num_sms() * 4;
@@ -349,7 +364,7 @@ int fvx_launch_topk_flagged(const FvxModel* model, const float* theta_ext, const
   if (int r = fvx_ensure_smem((const void*)k_score_topk, &g_topk_smem, smem, "fvx_score_topk")) return r;
   k_score_topk<<<fvx_num_sms() * 2, TK_TILE, smem, st>>>(*model, theta_ext, 0, n, mask_row_ptr, mask_col, k, out_ids,
                                                          out_scores, 0, nullptr, nullptr, list_scratch, count_scratch,
-                                                         u0);
+                                                         u0, tau_enc);
   FVX_CHECK_LAUNCH("k_score_topk (flagged rows)");
   return 0;
 }

@@ -239,6 +239,8 @@ __device__ __forceinline__ void tck_scan_chunk(const uint32_t (&v)[32], float th
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     if (!__any_sync(0xffffffffu, g[q] >= thr)) continue;
+    // (a vote per column of a visited octet, to skip the append code nobody needs, was measured slower: 3.0 ->
+    // 3.6 ms for the select half at configs[1])
     if (g[q] >= thr) {
 #pragma unroll
       for (int j = 8 * q; j < 8 * q + 8; ++j) {
@@ -878,10 +880,12 @@ int fvx_score_topk_tc_select(const FvxModel* model, const float* theta_ext, int3
   k_rescore_select<<<(int)rg, RS_WARPS * 32, 0, st>>>(*model, theta_ext, L.P, mask_row_ptr, mask_col, k, out_ids,
                                                       out_scores);
   FVX_CHECK_LAUNCH("k_rescore_select");
-  // rows whose candidate lists could not bound the result: exact fp32 sweep, written in place (ws->thr is
-  // the scratch for their list - the bounds are dead by now; the statistics serve as its counter)
+  // rows whose candidate lists could not bound the result: exact fp32 sweep, written in place, each row's
+  // threshold seeded with its proven bound (ws->ccount is the scratch for their list - the counts are dead by now
+  // and cleared at the start of every select; the statistics serve as the list's counter)
   return fvx_launch_topk_flagged(model, theta_ext, ws->flags, n_users, u0, mask_row_ptr, mask_col, k, out_ids,
-                                 out_scores, reinterpret_cast<int32_t*>(ws->thr), reinterpret_cast<int32_t*>(ws->stat), st);
+                                 out_scores, ws->ccount, reinterpret_cast<int32_t*>(ws->stat), st,
+                                 reinterpret_cast<const int32_t*>(ws->thr));
 }
 
 int fvx_score_topk_tc(const FvxModel* model, const float* theta_ext, int32_t u0, int32_t u1,

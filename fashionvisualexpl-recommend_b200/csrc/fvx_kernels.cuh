@@ -91,7 +91,8 @@ int fvx_launch_w_planes(const FvxModel* m, int B, cudaStream_t st);
 // exact fp32 top-k for the flagged rows of [u0, u0+n), in place, no host synchronisation (fvx_eval.cu)
 int fvx_launch_topk_flagged(const FvxModel* model, const float* theta_ext, const int32_t* flags, int n, int u0,
                             const int64_t* mask_row_ptr, const int32_t* mask_col, int k, int32_t* out_ids,
-                            float* out_scores, int32_t* list_scratch, int32_t* count_scratch, cudaStream_t st);
+                            float* out_scores, int32_t* list_scratch, int32_t* count_scratch, cudaStream_t st,
+                            const int32_t* tau_enc = nullptr);
 
 // x_ui for one (user row, item row, theta row): the single definition every scoring
 // kernel uses, so that a score compared with itself compares equal

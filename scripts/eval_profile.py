@@ -56,6 +56,19 @@ for i in range(a.sweeps + 1):          # the first sweep allocates the workspace
     t0.record(); ids, sc = sweep(); t1.record(); torch.cuda.synchronize()
     if i > 0 or a.sweeps == 0:
         best = min(best, t0.elapsed_time(t1))
+ev2 = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+ev2[0].record()
+e.topk_bounds(st["row_ptr"], a.k)
+ev2[1].record()
+e.topk_select(st["row_ptr"], st["col_sorted"], a.k)
+ev2[2].record()
+torch.cuda.synchronize()
+sys.stderr.write("eval trace: bounds %.3f ms, select %.3f ms\n" % (ev2[0].elapsed_time(ev2[1]), ev2[1].elapsed_time(ev2[2])))
+w_ = e._eval_ws(a.users)
+cc_ = w_["ccount"][:w_["lists"]].float()
+sys.stderr.write("eval trace: KP %d splits %d n_ut %d lists %d a_stride %d cand mean %.1f max %d flags %d\n"
+                 % (w_["KP"], w_["splits"], w_["n_ut"], w_["lists"], w_["struct"].a_stride, cc_.mean().item(),
+                    int(cc_.max().item()), int(w_["flags"].sum().item())))
 out = {"users": a.users, "items": a.items, "K": a.K, "d": a.d, "k": a.k, "sweep_ms": best,
        "users_per_s": a.users / best * 1e3, "fallback_rows": e.tc_overflow_rows,
        "checksum": int(ids.to(torch.int64).sum().item())}
