@@ -174,12 +174,23 @@ __device__ __forceinline__ float4 ss_unpack_bf16x4(uint2 p) {
   return make_float4(a.x, a.y, b.x, b.y);
 }
 
-__global__ void __launch_bounds__(SS_WARPS * 32)
+#define GH_HOT 4             // hot rows per block
+#define GH_W 592             // floats per hot row: item row (<= 260) + coefficient sums (<= 320), 9.3 KB for four
+__global__ void __launch_bounds__(SS_WARPS * 32, 4)
 k_grads_owned(FvxModel M, const int32_t* __restrict__ user, int B, int loss_slot, SsTheta T, int wnp, int wpitch,
               const float* __restrict__ S, const int32_t* __restrict__ run_id, float* __restrict__ RU,
               long long ru_rows, const int32_t* __restrict__ count, int uniq, const float* __restrict__ WU,
               double* __restrict__ loss_out) {
   __shared__ double loss_sh[SS_WARPS * 2];
+  // Hot rows.  With a popularity law the most popular item of a shard draws a large share of the shard's slots
+  // (Zipf(1.0), 8 ranks, 524 k triples: 37 k of the owner's 131 k slots), and every one of them is a chain of
+  // red.add onto the SAME accumulator row - L2 serialises them, and the rank that owns the item holds up every
+  // exchange of the step (57 ... 256 us across the ranks, profiles/r2_sharded_emul8_grads.txt).  Each block
+  // therefore looks at a sample of 64 of its own slots, takes the rows that appear at least three times as its
+  // hot rows (at most GH_HOT), sums their contributions in shared memory and adds them to the global
+  // accumulators once at the end: a few hundred reductions per address instead of tens of thousands.
+  __shared__ int32_t hot_row[GH_HOT], hot_tj[GH_HOT];
+  __shared__ float hot_acc[GH_HOT][GH_W];
   const int Su = M.users.stride, Si = M.items.stride, K = M.K, d = M.d, de = M.de;
   const int K4 = K >> 2, D4 = (d + 3) >> 2;
   const int grp = threadIdx.x >> 4, sub = threadIdx.x & 15;     // 16 lanes per slot
@@ -196,6 +207,45 @@ k_grads_owned(FvxModel M, const int32_t* __restrict__ user, int B, int loss_slot
   const int32_t* crow = M.cmap;
   const int32_t* cslot = M.cmap + 2 * (size_t)M.max_batch;
   double loss_acc = 0.0;
+  const int hot_w = Si + ((uniq && vis) ? wnp : 0);
+  const bool hot_on = hot_w <= GH_W;
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    // this block's first four passes of the slot loop: 64 slots, two per lane
+    int32_t a[2];
+    int c[2] = {0, 0};
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const long long j = (long long)blockIdx.x * (SS_WARPS * 2) + (lane & 15) + (long long)(2 * (lane >> 4) + h) * ng;
+      a[h] = (hot_on && j < n_owned) ? crow[j] : -2 - 2 * lane - h;           // (no slot: a value nobody shares)
+    }
+    for (int it = 0; it < 32; ++it) {
+      const int32_t b0 = __shfl_sync(0xffffffffu, a[0], it), b1 = __shfl_sync(0xffffffffu, a[1], it);
+      c[0] += (a[0] == b0) + (a[0] == b1);
+      c[1] += (a[1] == b0) + (a[1] == b1);
+    }
+    for (int h = 0; h < GH_HOT; ++h) {
+      // the most frequent row still in the sample (count in the high word, row in the low one)
+      long long best = -1;
+#pragma unroll
+      for (int q = 0; q < 2; ++q)
+        if (c[q] >= 3 && a[q] >= 0) { const long long key = ((long long)c[q] << 32) | (uint32_t)a[q]; best = key > best ? key : best; }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { const long long y = __shfl_xor_sync(0xffffffffu, best, o); best = y > best ? y : best; }
+      const int32_t row = best >= 0 ? (int32_t)(best & 0xFFFFFFFFLL) : -1;
+      if (lane == 0) {
+        hot_row[h] = row;
+        hot_tj[h] = (row >= 0 && uniq && vis) ? M.upos[row] : 0;
+      }
+#pragma unroll
+      for (int q = 0; q < 2; ++q) if (a[q] == row) c[q] = 0;
+    }
+  }
+  for (int i = threadIdx.x; i < GH_HOT * GH_W; i += blockDim.x) (&hot_acc[0][0])[i] = 0.0f;
+  __syncthreads();
+  int32_t hr[GH_HOT];
+#pragma unroll
+  for (int h = 0; h < GH_HOT; ++h) hr[h] = hot_row[h];
   if (blockIdx.x == 0 && wnp > 0 && !uniq) {   // (unique-row step: k_w_planes writes the planes and clears the tail)
     // the last 32-row tile of the backward reads W rows past the owned ones: they must be zero
     const long long cap = 2LL * M.max_batch;
@@ -229,17 +279,30 @@ k_grads_owned(FvxModel M, const int32_t* __restrict__ user, int B, int loss_slot
         float* gg = M.items.g + (size_t)li * Si;
         float* ru = RU + (size_t)run * Su;
         const long long tj = uniq ? (long long)M.uslot[slot] : j;   // row of TH / of the coefficient sums
+        int hot = -1;
+#pragma unroll
+        for (int h = 0; h < GH_HOT; ++h) if (li == hr[h]) hot = h;
+        float* hacc = hot >= 0 ? hot_acc[hot] : nullptr;
         for (int c = sub; c < K4; c += 16) {
           const float4 a = ur[c], x = gi[c];
-          ss_red_add4(gg + 4 * c, make_float4(cs * a.x + reg2 * x.x, cs * a.y + reg2 * x.y, cs * a.z + reg2 * x.z,
-                                              cs * a.w + reg2 * x.w));
+          const float4 gv = make_float4(cs * a.x + reg2 * x.x, cs * a.y + reg2 * x.y, cs * a.z + reg2 * x.z,
+                                        cs * a.w + reg2 * x.w);
+          if (hacc) {
+            atomicAdd(hacc + 4 * c, gv.x); atomicAdd(hacc + 4 * c + 1, gv.y);
+            atomicAdd(hacc + 4 * c + 2, gv.z); atomicAdd(hacc + 4 * c + 3, gv.w);
+          } else {
+            ss_red_add4(gg + 4 * c, gv);
+          }
           ss_red_add4(ru + 4 * c, make_float4(cs * x.x + ul2 * a.x, cs * x.y + ul2 * a.y, cs * x.z + ul2 * a.z,
                                               cs * x.w + ul2 * a.w));
           sq += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
           if (!side) sq += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
         }
         bi = M.items.w[(size_t)li * Si + K];
-        if (sub == 0) fvx_red_add(gg + K, cs + (side == 0 ? reg2 : reg2 * M.bias_neg_scale) * bi);
+        if (sub == 0) {
+          const float gb = cs + (side == 0 ? reg2 : reg2 * M.bias_neg_scale) * bi;
+          if (hacc) atomicAdd(hacc + K, gb); else fvx_red_add(gg + K, gb);
+        }
         if (vis) {
           for (int c = sub; c < nw4; c += 16) {
             const int n0 = 4 * c;
@@ -263,7 +326,14 @@ k_grads_owned(FvxModel M, const int32_t* __restrict__ user, int B, int loss_slot
             if (n0 + 2 == d) wv.z = cs;
             if (n0 + 3 == d) wv.w = cs;
             if (uniq) {            // the slots of one catalog row are summed: one backward row per distinct row
-              if (n0 <= d) ss_red_add4(M.W_sum + (size_t)tj * wnp + n0, wv);
+              if (n0 <= d) {
+                if (hacc) {
+                  float* hw = hacc + Si + n0;
+                  atomicAdd(hw, wv.x); atomicAdd(hw + 1, wv.y); atomicAdd(hw + 2, wv.z); atomicAdd(hw + 3, wv.w);
+                } else {
+                  ss_red_add4(M.W_sum + (size_t)tj * wnp + n0, wv);
+                }
+              }
             } else if (wnp > 0) {
               const uint2 h = ss_pack_bf16x4(wv);
               const float4 hf = ss_unpack_bf16x4(h);
@@ -292,6 +362,17 @@ k_grads_owned(FvxModel M, const int32_t* __restrict__ user, int B, int loss_slot
     double s = 0.0;
     for (int w = 0; w < SS_WARPS * 2; ++w) s += loss_sh[w];
     if (s != 0.0) atomicAdd(loss_out, s);
+  }
+  // the block's sums of its hot rows -> the global accumulators
+  for (int h = 0; h < GH_HOT; ++h) {
+    const int32_t row = hot_row[h];
+    if (row < 0) continue;
+    float* gg = M.items.g + (size_t)row * Si;
+    float* ws = (uniq && vis) ? M.W_sum + (size_t)hot_tj[h] * wnp : nullptr;
+    for (int i = threadIdx.x; i < hot_w; i += blockDim.x) {
+      const float v = hot_acc[h][i];
+      if (v != 0.0f) fvx_red_add(i < Si ? gg + i : ws + (i - Si), v);
+    }
   }
 }
 
