@@ -125,8 +125,11 @@ __device__ __forceinline__ uint32_t claim_rows(const FvxTable& T, int32_t r, boo
 __device__ __forceinline__ void claim_pair_pos(const FvxTable& T, int32_t* __restrict__ upos, int32_t ri, int32_t rj,
                                                int32_t t, int lane) {
   bool wi = false, wj = false;
-  if (ri >= 0) wi = atomicMax(&T.mark[ri], t) < t;
-  if (rj >= 0) wj = atomicMax(&T.mark[rj], t) < t;      // rj == ri: the second stamp finds t and loses
+  // a row that already carries this step's stamp is lost without asking: the stamps of a popular row (tens of
+  // thousands of slots of one batch on an item shard) would otherwise queue up as atomics on one address
+  const int32_t mi = ri >= 0 ? __ldcg(&T.mark[ri]) : t, mj = rj >= 0 ? __ldcg(&T.mark[rj]) : t;
+  if (mi != t) wi = atomicMax(&T.mark[ri], t) < t;
+  if (mj != t) wj = atomicMax(&T.mark[rj], t) < t;      // rj == ri: the second stamp finds t and loses
   const uint32_t bi = __ballot_sync(0xffffffffu, wi), bj = __ballot_sync(0xffffffffu, wj);
   const int ni = __popc(bi), total = ni + __popc(bj);
   if (total) {
