@@ -269,8 +269,9 @@ def workload_config(args, n):
                 if args.scaling == "weak" else "strong: users, catalog and global batch fixed"),
             "parallelism": "1 GPU" if n == 1 else
             "item catalog (Gi, Bi, F) row-sharded and users block-owned over %d GPUs, E replicated; one C call per "
-            "step issues 4 NCCL all-reduces (fresh user rows, partial scores, user-row gradient shares, dE); eval: "
-            "per-shard top-k + all-to-all merge" % n,
+            "step with 4 exchanges inside (fresh user rows, partial scores, user-row gradient shares, dE), transport %s; "
+            "eval: per-shard bounds, all-reduce(MAX), per-shard candidates + top-k, all-to-all merge"
+            % (n, getattr(args, "transport_resolved", "p2p (peer stores over NVLink) unless FVX_SHARDED_TRANSPORT=nccl")),
             "l2": "F (%.2f GB%s) and the tables exceed the 126 MB L2; rows are gathered at random, no flush needed"
                   % (I * D * 4 / 1e9 / n, " per GPU" if n > 1 else "") if D else
                   "tables: %.0f MB; batches touch random rows" % ((U + I) * K * 16 / 1e6)}
@@ -490,6 +491,9 @@ def run_fvx(args):
     min_len, mean_len = int(lens.min()), float(lens.mean())
     max_runs = min(B // max(min_len, 1) + 2, int(1.3 * B / mean_len) + 1024)
     sharded = parallel.ShardedStep([e], grp, max_runs=max_runs) if world > 1 else None
+    if sharded is not None:
+        args.transport_resolved = {"p2p": "p2p (the kernels store into their peers' buffers over NVLink, one-warp barriers)",
+                                   "nccl": "nccl (all-gather / all-reduce / reduce-scatter / all-reduce)"}[sharded.transport]
     graph = world == 1 and B <= 8192                 # small batches: 8 steps per CUDA-graph launch (fvx_bpr_steps)
     runs = data.next_batch_run(str(dev))
     cur = {"bufs": None, "n": 0, "pos": 0}
