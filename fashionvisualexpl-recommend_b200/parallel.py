@@ -5,10 +5,11 @@ state and publishes the user's row to the others for the steps that touch it), E
 * ``shard_bounds`` / ``user_bounds``   contiguous item block / user block of a rank;
 * ``sharded_engine``          an ``Engine`` holding one rank's part;
 * ``ShardedStep``             the BPR step: ONE C-ABI call per rank per step (``fvx_bpr_step_sharded``) that
-                              issues its four all-reduces itself - WU (fresh user rows) beside the projection
+                              issues its four exchanges itself - WU (fresh user rows) beside the projection
                               and RU (user-row gradient shares) beside grad_E on a side stream, S (partial
-                              scores) and dE on the caller's - over NCCL communicators created from an id that
-                              ``torch.distributed`` broadcasts;
+                              scores) and dE on the caller's - either as NCCL collectives over communicators
+                              created from an id that ``torch.distributed`` broadcasts, or (default) as stores
+                              into the peers' buffers of a CUDA-IPC arena with one-warp barrier kernels;
 * ``exchange_topk`` / ``sharded_topk``   evaluation: every rank sweeps all users over its shard, the per-shard
                               top-k lists are exchanged by user slice (all-to-all) and merged there
                               (``fvx_topk_merge``).

@@ -276,8 +276,12 @@ int fvx_run_ids(const int32_t* user, int64_t n, int32_t* run_id, int32_t* scratc
 int fvx_run_slots(const int32_t* user, int64_t n, int32_t users_per_owner, int32_t owners, int32_t cap,
                   int32_t* run_slot, int32_t* scratch, fvx_stream_t stream);
 
-/* One optimiser step of the sharded model: ONE call per rank per step; the four collectives are issued inside
- * (NCCL), WU and RU on a side stream.  The batch loss lands in model->loss[loss_slot] on EVERY rank. */
+/* One optimiser step of the sharded model: ONE call per rank per step; the four exchanges (WU: fresh user rows,
+ * S: partial scores, RU: user-gradient shares, dE) are issued inside, WU and RU on a side stream.  ws->p2p = 0:
+ * NCCL collectives (all-gather, all-reduce, reduce-scatter, all-reduce); ws->p2p = 1: the producer kernels store
+ * into their peers' buffers of the arena (fvx_comm_arena: ws->WU, S, RUin, dEall, tails, flags point into it) and
+ * one-warp barrier kernels order the steps.  The batch loss lands in model->loss[loss_slot] on EVERY rank; a batch
+ * with more runs of equal users per owner than ws->run_cap makes it NaN on every rank. */
 int fvx_bpr_step_sharded(const FvxModel* model, const FvxShardWs* ws, FvxComm* comm, const int32_t* user,
                          const int32_t* pos, const int32_t* neg, int32_t B, int32_t loss_slot, fvx_stream_t stream);
 
