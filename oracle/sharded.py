@@ -1,5 +1,7 @@
-"""Oracle (TEST INFRASTRUCTURE): the item-sharded BPR step as the three phases of
-``fvx_bpr_step_sharded_a/b/c`` (include/fvx.h), restated in NumPy per rank.
+"""Oracle (TEST INFRASTRUCTURE): the item-sharded BPR step of ``fvx_bpr_step_sharded`` /
+``fvx_bpr_step_sharded_phase`` (include/fvx.h), restated in NumPy per rank - first with replicated user tables
+(three phases, two sums), then (``run_slots`` ... ``owned_user_grads`` at the end of the file) with the users
+block-OWNED as the CUDA path has them: four exchanges (WU, S, RU, dE).
 
 The reference has no multi-GPU path; what is restated here is the DECOMPOSITION of its train step
 (BPRMF.py:87-125 / VBPR.py:99-144, oracle/bpr.py) that the CUDA path uses: x_uij = s_ui - s_uj is linear in
@@ -117,3 +119,142 @@ def phase_c_grads(P, batch, G_items, RU, dE, dBp, reg, add_e_reg=True):
         if add_e_reg:
             extra = reg * (np.sum(P["E"] * P["E"], dtype=dt) + np.sum(P["Bp"] * P["Bp"], dtype=dt))
     return G, extra
+
+
+# ---- users block-owned (FvxModel.user_lo / user_cnt; fashionvisualexpl-recommend_b200/parallel.py: user_bounds) ----
+#
+# The owner of a user keeps the user's Adam state and is the only rank whose copy of the row is current.  Per step:
+#
+#     phase 0   run_slots: the runs of equal users of the batch, grouped by owner (slot = owner * cap + index among
+#               that owner's runs) - a function of the batch alone, so every rank computes the same layout;
+#               the owner writes the CURRENT rows of its users into its segment of WU
+#     -- all-gather(WU): every rank receives every owner's segment --
+#     phase 1   partial scores of the owned slots, user rows read from WU (never from the local table)
+#     -- sum(S) --
+#     phase 2   as phase B above, user rows from WU, the user-gradient shares indexed by run slot
+#     -- sum(RU) (each owner needs its own segment: a reduce-scatter), sum(dE) --
+#     phase 3   the owner adds the RU rows of its segment into ITS users' gradients; Adam on the owned users, on E
+#               (everywhere) and on the owned items
+#
+# tests/test_parallel_cpu.py::test_owned_users_decomposition_gloo_world2 runs it with the foreign user rows of every
+# rank poisoned with NaN: nothing may ever read them.
+
+def user_bounds(num_users, world, rank):
+    per = (int(num_users) + world - 1) // world
+    lo = min(int(num_users), rank * per)
+    return lo, max(0, min(int(num_users), lo + per) - lo), per
+
+
+def run_slots(user, per, owners, cap):
+    """slot[b] = owner * cap + (index of b's run among the runs of that owner), owner = min(user // per, owners-1)
+    (fvx_run_slots); raises when an owner has more than ``cap`` runs (the CUDA step poisons the loss instead)."""
+    user = np.asarray(user, dtype=np.int64)
+    start = np.ones(len(user), dtype=bool)
+    start[1:] = user[1:] != user[:-1]
+    owner = np.minimum(user // per, owners - 1)
+    slot = np.zeros(len(user), dtype=np.int64)
+    seen = np.zeros(owners, dtype=np.int64)
+    cur = 0
+    for b in range(len(user)):
+        if start[b]:
+            o = owner[b]
+            if seen[o] >= cap:
+                raise OverflowError("owner %d has more than %d runs" % (o, cap))
+            cur = o * cap + seen[o]
+            seen[o] += 1
+        slot[b] = cur
+    return slot
+
+
+def publish_users(P, ulo, ucnt, batch, slot, owners, cap, vis):
+    """This owner's contribution to WU [owners * cap, K + d]: the current rows of ITS users at their run slots
+    (zero elsewhere, so that a sum over the ranks is the all-gather)."""
+    user = np.asarray(batch[0], dtype=np.int64)
+    K = P["Gu"].shape[1]
+    d = P["Tu"].shape[1] if vis else 0
+    WU = np.zeros((owners * cap, K + d), dtype=P["Gu"].dtype)
+    mine = (user >= ulo) & (user < ulo + ucnt)
+    WU[slot[mine], :K] = P["Gu"][user[mine]]
+    if vis:
+        WU[slot[mine], K:] = P["Tu"][user[mine]]
+    return WU
+
+
+def owned_scores(P, lo, cnt, batch, WU, slot, F=None):
+    """phase 1: as phase_a, the user rows taken from WU."""
+    user, pos, neg = (np.asarray(a, dtype=np.int64) for a in batch)
+    B = len(user)
+    dt = P["Gi"].dtype
+    K = P["Gi"].shape[1]
+    S = np.zeros(2 * B, dtype=dt)
+    for side, item in ((0, pos), (1, neg)):
+        own = (item >= lo) & (item < lo + cnt)
+        b = np.nonzero(own)[0]
+        i, w = item[b], WU[slot[b]]
+        s = P["Bi"][i] + np.sum(w[:, :K] * P["Gi"][i], axis=1)
+        if F is not None:
+            f = F[i].astype(dt)
+            s = s + np.sum(w[:, K:] * (f @ P["E"]), axis=1) + (f @ P["Bp"])[:, 0]
+        S[side * B + b] = s
+    return S
+
+
+def owned_grads(P, lo, cnt, batch, S, WU, slot, reg, F=None):
+    """phase 2: as phase_b with the user rows from WU and RU indexed by run slot ([owners * cap, K + d])."""
+    user, pos, neg = (np.asarray(a, dtype=np.int64) for a in batch)
+    B = len(user)
+    dt = P["Gi"].dtype
+    reg, two = dt.type(reg), dt.type(2)
+    K = P["Gi"].shape[1]
+    vis = F is not None
+    x = S[:B] - S[B:]
+    inside = (x >= dt.type(CLIP_LO)) & (x <= dt.type(CLIP_HI))
+    c = np.where(inside, -1.0 / (1.0 + np.exp(x.astype(np.float64))), 0.0).astype(dt)
+    G = {"Gi": np.zeros_like(P["Gi"]), "Bi": np.zeros_like(P["Bi"])}
+    RU = np.zeros_like(WU)
+    dE = np.zeros_like(P["E"]) if vis else None
+    dBp = np.zeros_like(P["Bp"]) if vis else None
+    loss = dt.type(0)
+    for side, item in ((0, pos), (1, neg)):
+        own = (item >= lo) & (item < lo + cnt)
+        b = np.nonzero(own)[0]
+        i, w = item[b], WU[slot[b]]
+        gu = w[:, :K]
+        cs = c[b] if side == 0 else -c[b]
+        gi, bi = P["Gi"][i], P["Bi"][i]
+        breg = reg if side == 0 else reg / dt.type(10)
+        np.add.at(G["Gi"], i, cs[:, None] * gu + two * reg * gi)
+        np.add.at(G["Bi"], i, cs + two * breg * bi)
+        ushare = cs[:, None] * gi
+        loss = loss + reg * np.sum(gi * gi, dtype=dt) + breg * np.sum(bi * bi, dtype=dt)
+        if side == 0:
+            ushare = ushare + two * reg * gu
+            xc = np.clip(x[b], dt.type(CLIP_LO), dt.type(CLIP_HI))
+            loss = loss + np.sum(softplus(-xc), dtype=dt) + reg * np.sum(gu * gu, dtype=dt)
+        np.add.at(RU[:, :K], slot[b], ushare)
+        if vis:
+            tu, f = w[:, K:], F[i].astype(dt)
+            tshare = cs[:, None] * (f @ P["E"])
+            if side == 0:
+                tshare = tshare + two * reg * tu
+                loss = loss + reg * np.sum(tu * tu, dtype=dt)
+            np.add.at(RU[:, K:], slot[b], tshare)
+            dE += f.T @ (cs[:, None] * tu)
+            dBp += f.T @ cs[:, None]
+    return G, RU, dE, dBp, loss
+
+
+def owned_user_grads(P, ulo, ucnt, batch, slot, RU, vis):
+    """phase 3: the summed RU rows of the OWNED users' runs -> (Gu, Tu) gradients (zero rows for foreign users)."""
+    user = np.asarray(batch[0], dtype=np.int64)
+    K = P["Gu"].shape[1]
+    first = np.ones(len(user), dtype=bool)
+    first[1:] = slot[1:] != slot[:-1]
+    mine = first & (user >= ulo) & (user < ulo + ucnt)
+    gGu = np.zeros_like(P["Gu"])
+    np.add.at(gGu, user[mine], RU[slot[mine], :K])
+    gTu = None
+    if vis:
+        gTu = np.zeros_like(P["Tu"])
+        np.add.at(gTu, user[mine], RU[slot[mine], K:])
+    return gGu, gTu
