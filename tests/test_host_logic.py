@@ -197,6 +197,47 @@ def test_no_cpu_fallback():
         _lib.ptr(torch.zeros(4))
 
 
+def test_product_never_imports_the_oracle_or_the_reference():
+    """oracle/ is test infrastructure: only tests/, __graft_entry__.smoke() and bench.py's CPU legs / in-run parity
+    check may import it; nothing shipped may read /root/reference."""
+    import ast
+    pkg = os.path.join(REPO, "fashionvisualexpl-recommend_b200")
+    for root, _, files in os.walk(pkg):
+        for fn in files:
+            if not fn.endswith(".py"):
+                continue
+            path = os.path.join(root, fn)
+            src = open(path).read()
+            assert "/root/reference" not in src, path
+            for node in ast.walk(ast.parse(src)):
+                names = []
+                if isinstance(node, ast.Import):
+                    names = [a.name for a in node.names]
+                elif isinstance(node, ast.ImportFrom):
+                    names = [node.module or ""]
+                assert not any(n == "oracle" or n.startswith("oracle.") for n in names), (path, names)
+    for fn in ("bench.py", "__graft_entry__.py"):
+        assert "/root/reference" not in open(os.path.join(REPO, fn)).read(), fn
+    # bench.py: the oracle only inside the parity checks, the CPU-baseline legs and the reference arm
+    src = open(os.path.join(REPO, "bench.py")).read()
+    tree = ast.parse(src)
+    allowed = {"parity_full", "parity_small", "cpu_oracle_rate", "run_reference"}
+
+    def visit(node, fn, guarded):
+        if isinstance(node, ast.FunctionDef) and fn is None:
+            fn = node.name
+        if isinstance(node, ast.If) and "no_cpu_baseline" in ast.get_source_segment(src, node.test):
+            guarded = True
+        if isinstance(node, (ast.Import, ast.ImportFrom)):
+            mods = [a.name for a in node.names] if isinstance(node, ast.Import) else [node.module or ""]
+            if any(m.split(".")[0] == "oracle" for m in mods):
+                assert fn in allowed or (fn == "run_fvx" and guarded), (fn, node.lineno)
+        for ch in ast.iter_child_nodes(node):
+            visit(ch, fn, guarded)
+
+    visit(tree, None, False)
+
+
 def test_cli_surface_matches_reference():
     """fvx.train_rec keeps the flag names and defaults of the reference's train_rec.py:17-46 (listed here;
     /root/reference is not read at run time).  Documented deviations: --gpu defaults to 0 (no CPU path),
