@@ -37,12 +37,14 @@
 //   |s_bf16 - s_fp32| <= c * |a| * |b_i| + beta0,   c = 1.003 * 2^-8 + KP * 2^-21  (rounding + fp32
 //   accumulation),  beta0 = (2^-17 + KP * 2^-21) * max_i |bias_i|                (hi+lo residual).
 // One more K column holds eps_u = c*|a_u| (rounded up to bf16) on the user side and |b_i| (rounded up) on
-// the item side, so the UMMA itself delivers an UPPER bound s_ub = s_bf16 + eps_u * |b_i| >= s_fp32, and
-// s_ub - 2.001 * eps_u * |b_i| - beta0 <= s_fp32.  A group's entry is max(s_ub over the group) - 2.001 * eps_u *
-// (largest |b_i| of the group) - beta0: a lower bound of the true score of the group's best column.  If tau is a
-// value that at least kk = k + #train group entries reach, kk distinct items have a true score >= tau, so every
-// item of the true top-kk has s_ub >= s >= tau: keeping {s_ub >= tau} loses nothing, and the output equals the
-// fp32 kernel's bit for bit.  A row whose list overflows, or whose
+// the item side, so the UMMA itself delivers s_ub = s_bf16 + eps_u * |b_i| >= s_fp32 - beta0 (an upper bound up to
+// the bias residual), and s_ub - 2.001 * eps_u * |b_i| - beta0 <= s_fp32.  A group's entry is max(s_ub over the
+// group) - 2.001 * eps_u * (largest |b_i| of the group) - beta0: a lower bound of the true score of the group's
+// best column.  If tau is a value that at least kk = k + #train group entries reach, kk distinct items have a true
+// score >= tau, so every item of the true top-kk has s >= tau and s_ub >= tau - beta0: the bound a row publishes is
+// tau - beta0, keeping {s_ub >= bound} loses nothing, and the output equals the fp32 kernel's bit for bit
+// (oracle/tc_bound.py restates this arithmetic; tests/test_oracle_tc_bound.py checks it on the CPU, including
+// models whose scores are dominated by the biases, where beta0 is what matters).  A row whose list overflows, or whose
 // range has fewer than kk groups, is flagged and re-run through the fp32 kernel inside the same call.
 #include <cuda_bf16.h>
 #include <math_constants.h>
@@ -458,8 +460,9 @@ k_topk_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             for (int g = 0; g < n_grp; ++g) c += (__ldcg(gm + (size_t)g * rows_u) >= mid) ? 1 : 0;
             if (c >= kk) { a = mid; if (c <= kk + (kk >> 2)) break; } else b = mid;
           }
-          // the row's bound is the best one any range (item split, item shard) finds
-          atomicMax(P.thr_g + row, tck_enc(a));
+          // the row's bound is the best one any range (item split, item shard) finds; minus beta0: s_ub may lie
+          // below the true score by the bias residual, and the candidates sweep compares s_ub with this value
+          atomicMax(P.thr_g + row, tck_enc(a - beta0));
         }
       }
       if (!P.do_b) continue;
