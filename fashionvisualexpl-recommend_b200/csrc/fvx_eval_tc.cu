@@ -41,8 +41,9 @@
 // the bias residual), and s_ub - 2.001 * eps_u * |b_i| - beta0 <= s_fp32.  A group's entry is max(s_ub over the
 // group) - 2.001 * eps_u * (largest |b_i| of the group) - beta0: a lower bound of the true score of the group's
 // best column.  If tau is a value that at least kk = k + #train group entries reach, kk distinct items have a true
-// score >= tau, so every item of the true top-kk has s >= tau and s_ub >= tau - beta0: the bound a row publishes is
-// tau - beta0, keeping {s_ub >= bound} loses nothing, and the output equals the fp32 kernel's bit for bit
+// score >= tau, so every item of the true top-kk has s >= tau and s_ub >= tau - beta0: the row publishes tau (a
+// statement about true scores: item splits and item shards combine theirs with MAX), the candidates sweep keeps
+// {s_ub >= tau - beta0} with its own beta0, which loses nothing, and the output equals the fp32 kernel's bit for bit
 // (oracle/tc_bound.py restates this arithmetic; tests/test_oracle_tc_bound.py checks it on the CPU, including
 // models whose scores are dominated by the biases, where beta0 is what matters).  A row whose list overflows, or whose
 // range has fewer than kk groups, is flagged and re-run through the fp32 kernel inside the same call.
@@ -460,16 +461,17 @@ k_topk_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             for (int g = 0; g < n_grp; ++g) c += (__ldcg(gm + (size_t)g * rows_u) >= mid) ? 1 : 0;
             if (c >= kk) { a = mid; if (c <= kk + (kk >> 2)) break; } else b = mid;
           }
-          // the row's bound is the best one any range (item split, item shard) finds; minus beta0: s_ub may lie
-          // below the true score by the bias residual, and the candidates sweep compares s_ub with this value
-          atomicMax(P.thr_g + row, tck_enc(a - beta0));
+          // the row's bound is the best one any range (item split, item shard) finds: a statement about TRUE
+          // scores (the k-th best unmasked one is >= it); whoever compares s_ub with it subtracts its own beta0
+          atomicMax(P.thr_g + row, tck_enc(a));
         }
       }
       if (!P.do_b) continue;
       // a launch that runs both sweeps reads its own bound back (other splits may have raised it meanwhile); a
       // candidates-only launch finds the maximum over all splits and ranks.  -inf (no range could bound the row):
       // everything passes, the list overflows, the exact kernel takes the row.
-      if (live) thr = tck_dec(__ldcg(P.thr_g + row));
+      // (minus beta0: s_ub may lie below the true score by the bias residual of THIS shard's items)
+      if (live) thr = tck_dec(__ldcg(P.thr_g + row)) - beta0;
       // ---- sweep B: candidates with s_ub >= thr ----
       int cnt = 0;
       unsigned long long* lbuf = P.cand + tck_list(P, live ? row : 0, sp) * TCK_CAP;

@@ -15,8 +15,9 @@ checks on the CPU:
 * selection (``topk_via_bounds``): per row, the maximum of ``s_ub`` over every group of 32 consecutive items minus the
   group's margin is a lower bound of the true score of the group's best item; a value tau that at least
   ``kk = k + #train`` group entries reach is therefore reached by kk distinct items, the exact top-k lies inside
-  ``{s_ub >= tau - beta0}`` (the bound a row publishes is ``tau - beta0``), and re-scoring that set exactly gives the
-  exact answer;
+  ``{s_ub >= tau - beta0}`` (a row publishes tau - a statement about true scores that item splits and shards
+  combine with MAX - and the candidates sweep subtracts the beta0 of its own items), and re-scoring that set
+  exactly gives the exact answer;
 * ``enc`` / ``dec``: the int32 encoding of a bound whose signed order is the float's (``FvxEvalWs.thr``: combined
   over item splits with ``atomicMax`` and over ranks with an all-reduce MAX).
 """
@@ -125,7 +126,7 @@ ENC_NEG_INF = np.int32(-2139095041)         # 0x807FFFFF
 
 # ---- selection ------------------------------------------------------------------------------------
 def row_bound(s_ub_row, eps_u, nb, beta0, kk, group=32):
-    """The bound one row publishes for one item range, tau - beta0: bisection over the group entries as in k_topk_tc
+    """The bound tau one row publishes for one item range: bisection over the group entries as in k_topk_tc
     (<= 16 iterations, stops when the count of entries >= tau lies in [kk, kk + kk/4]); -inf when the range has
     fewer than kk groups."""
     n = len(s_ub_row)
@@ -151,12 +152,12 @@ def row_bound(s_ub_row, eps_u, nb, beta0, kk, group=32):
                 break
         else:
             b = mid
-    return np.float32(a - beta0)
+    return np.float32(a)
 
 
 def topk_via_bounds(a, b, bias, train_lists, k, shards=1, rng=None):
     """The whole procedure for every user: bounds (per item shard, combined with MAX through the int encoding),
-    candidates {s_ub >= tau}, exact re-scoring, mask, top-k.  Returns (ids [U, k], scores [U, k], candidate counts)."""
+    candidates {s_ub >= tau - beta0}, exact re-scoring, mask, top-k.  Returns (ids [U, k], scores [U, k], candidate counts)."""
     bias_total = (np.asarray(bias[0], np.float32) + np.asarray(bias[1], np.float32)).astype(np.float32) \
         if isinstance(bias, tuple) else np.asarray(bias, np.float32)
     A, B, eps, nb, beta0 = pack(a, b, bias_total)
@@ -174,7 +175,7 @@ def topk_via_bounds(a, b, bias, train_lists, k, shards=1, rng=None):
             lo, hi = cuts[r], cuts[r + 1]
             e = max(e, int(enc(row_bound(s_ub[u, lo:hi], eps[u], nb[lo:hi], beta0, kk))))
         tau = dec(np.int32(e))
-        cand = np.nonzero(s_ub[u] >= tau)[0]
+        cand = np.nonzero(s_ub[u] >= np.float32(tau - beta0))[0]
         counts[u] = len(cand)
         cand = np.setdiff1d(cand, np.asarray(train_lists[u], dtype=np.int64))
         order = np.lexsort((cand, -s_ex[u, cand].astype(np.float64)))[:k]       # score descending, id ascending
