@@ -663,7 +663,8 @@ __device__ __forceinline__ T* peer_of(const PeerPtrs& X, int r, T* local) {
 
 // Cross-GPU barrier: every rank writes `epoch` into its slot of every peer's flag array, then waits until all slots
 // of its own array have reached it.  One warp; the kernel boundary before it has made the producer kernel's peer
-// stores visible (plus the fence below).  A protocol error traps after ~2 s instead of hanging the box.
+// stores visible (plus the fence below).  A peer that never arrives (a crashed rank, a protocol error) traps this
+// rank after ~30 s instead of hanging the box; ranks that are merely late (host work between steps) are waited for.
 __global__ void k_xbar(PeerPtrs X, uint32_t* flags, uint32_t epoch) {
   const int lane = threadIdx.x;
   __threadfence_system();
@@ -676,7 +677,7 @@ __global__ void k_xbar(PeerPtrs X, uint32_t* flags, uint32_t epoch) {
     volatile uint32_t* mine = flags + lane;
     const long long t0 = clock64();
     while ((int32_t)(*mine - epoch) < 0) {
-      if (clock64() - t0 > 4000000000LL) __trap();
+      if (clock64() - t0 > 60000000000LL) __trap();
     }
   }
   __threadfence_system();
