@@ -13,11 +13,19 @@ What it restates (all citations relative to the reference tree, see SURVEY.md §
                          Keras-Adam update (``src/recommender/models/BPRMF.py:55-125``,
                          ``src/recommender/models/VBPR.py:59-144``).
 * ``oracle.gradfashion`` - the GradFashion linear variant (two-stage visual projection of colour and edge
-                         descriptors, ``src/recommender/models/GradFashion.py:81-190,304-320``): the next
-                         model family on the path; pinned, no CUDA path yet.
-* ``oracle.sharded``   - the item-sharded step as the three phases of ``fvx_bpr_step_sharded_a/b/c`` (partial
-                         scores, per-rank gradient shares packed by run of equal users, ownership of the
-                         per-triple terms), run by tests/test_parallel_cpu.py in two gloo processes.
+                         descriptors, ``src/recommender/models/GradFashion.py:81-190,304-320``; SURVEY.md
+                         section 8(f) row 4), pinned against the reference's own file; its CUDA path
+                         (``FvxModel.two_stage``) is checked against it.
+* ``oracle.deferred_adam`` - the lazy form of Keras Adam the CUDA step uses by default (pending step, replayed
+                         zero-gradient steps, closed-form decay, flush) next to the literal whole-table form.
+* ``oracle.sharded``   - the item-sharded step of ``fvx_bpr_step_sharded`` / ``fvx_bpr_step_sharded_phase``:
+                         partial scores, per-rank gradient shares packed by run of equal users, ownership of
+                         the per-triple terms - with replicated users and with the users block-owned (run slots
+                         by owner; exchanges WU, S, RU, dE); run by tests/test_parallel_cpu.py in two gloo
+                         processes.
+* ``oracle.tc_bound`` / ``oracle.tc_project`` - the bf16 arithmetic of the two tensor-core paths: operand packing,
+                         score bounds, bound encoding and selection rule of the evaluation sweep; hi/lo planes
+                         and the three-pass product of the projection.
 * ``oracle.sampler``   - the host triple sampler (``src/dataset/dataset.py:83-114``)
                          in the reference's own RNG streams, plus the counter-based
                          Philox sampler the device path implements.

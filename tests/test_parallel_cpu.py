@@ -74,8 +74,8 @@ def test_topk_exchange_layout_gloo_world2():
 
 
 def _step_worker(rank, world, port, out):
-    """Two gloo ranks run the item-sharded step of oracle/sharded.py (the phases of
-    fvx_bpr_step_sharded_a/b/c) with real all-reduces; every rank must end with the parameters of the
+    """Two gloo ranks run the item-sharded step of oracle/sharded.py (first half: replicated users, the phases of
+    fvx_bpr_step_sharded_phase with S, RU and dE summed) with real all-reduces; every rank must end with the parameters of the
     single-rank oracle step, the item rows on their owner."""
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
