@@ -76,7 +76,7 @@ def parse():
     for k in ("users", "items", "embed_k", "embed_d", "feat_dim", "batch"):
         if getattr(a, k) is None:
             setattr(a, k, cfg[k])
-        else:
+        elif not a.config.endswith("*"):
             a.config = a.config + "*"                       # a shape flag overrides the named configuration
     a.scaling = a.scaling or cfg["scaling"]
     a.eval_only = bool(cfg.get("eval_only"))

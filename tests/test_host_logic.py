@@ -256,3 +256,25 @@ def test_cli_surface_matches_reference():
     assert b.rec == "bprmf" and b.list_of_regs == [0.1, 0.01] and b.validation is False and b.embed_k == 64
     with pytest.raises(NotImplementedError):
         train_rec._model_class("acf")
+
+
+def test_bench_reference_arm_runs_on_the_host(tmp_path):
+    """`bench.py --impl reference` (the driver's reference arm): no GPU involved, ONE JSON line on stdout with the
+    contract's keys; under torchrun only rank 0 prints."""
+    import json
+    import subprocess
+    import sys
+    cmd = [sys.executable, os.path.join(REPO, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+           "--users", "300", "--items", "500", "--feat_dim", "128", "--batch", "256"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["metric"] == "BPR triples/s (train)" and line["unit"] == "triples/s"
+    assert line["value"] > 0 and line["gpu_launches"] == 0 and line["config"]["name"] == "c2*"
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "triples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=str(tmp_path), env=env)
+    assert r.returncode == 0 and r.stdout.strip() == ""
