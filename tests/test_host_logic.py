@@ -278,3 +278,15 @@ def test_bench_reference_arm_runs_on_the_host(tmp_path):
     env = dict(os.environ, RANK="1", WORLD_SIZE="2")
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=str(tmp_path), env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_bench_product_arm_needs_a_gpu(tmp_path):
+    """Without a CUDA device the product arm of bench.py fails loudly and prints no line (no CPU fallback)."""
+    import subprocess
+    import sys
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    cmd = [sys.executable, os.path.join(REPO, "bench.py"), "--steps", "1", "--warmup", "0", "--users", "300",
+           "--items", "500", "--feat_dim", "128", "--batch", "256", "--no_cpu_baseline"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=str(tmp_path))
+    assert r.returncode != 0 and r.stdout.strip() == ""
