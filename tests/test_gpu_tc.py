@@ -111,8 +111,10 @@ def test_train_steps_tensor_cores_match_oracle(K, d, D, B, mode):
         dlt = np.abs(Q[k].reshape(ref.shape) - ref) / np.abs(ref).max()
         e_f32, e_pert = rel_err(P32[k], ref), rel_err(Pp[k], ref)
         assert (dlt > REL).mean() <= 1e-3, (mode, k, "elements beyond 1e-4", int((dlt > REL).sum()), dlt.size)
-        # the perturbed oracle is ONE draw of the discontinuity noise (the largest of ~1e5 elements): a factor 2 on it
-        assert dlt.max() <= max(REL, 3 * e_f32, 2 * e_pert), (mode, k, dlt.max(), e_f32, e_pert,
+        # the perturbed oracle is ONE draw of the discontinuity noise (the largest of ~1e5 elements, each of them an
+        # Adam update whose sign a rounding-level gradient decides): a factor 3 on it; systematic errors are caught
+        # by the fraction above and by the per-step losses
+        assert dlt.max() <= max(REL, 3 * e_f32, 3 * e_pert), (mode, k, dlt.max(), e_f32, e_pert,
                                                                np.unravel_index(dlt.argmax(), dlt.shape))
 
 
